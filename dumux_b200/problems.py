@@ -1,0 +1,308 @@
+"""Problem set-ups (the inputs a DuMux Problem/SpatialParams pair provides), sampled into flat arrays.
+
+In DuMux the user supplies C++ callables (``boundaryTypesAtPos``, ``dirichletAtPos``, ``neumannAtPos``,
+``permeability``, ``porosityAtPos``, ``fluidMatrixInteraction`` ...; dumux/common/fvproblem.hh:126-283,
+dumux/porousmediumflow/fvspatialparams.hh:83-99).  The B200 path evaluates them ONCE on the host into the
+flat per-cell / per-boundary-face arrays below; these arrays are what crosses the C ABI.
+
+Each factory cites the reference test it reproduces.  Cells are numbered x-fastest (YaspGrid), boundary
+faces of a side are numbered with the lower remaining axis fastest.
+"""
+from __future__ import annotations
+
+import dataclasses
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+
+MODEL_1P, MODEL_2P = 1, 2
+LAW_BC, LAW_VG = 0, 1
+BC_NEUMANN, BC_DIRICHLET, BC_NONE = 0, 1, 2
+
+
+@dataclasses.dataclass
+class Material:
+    law: int
+    params: Tuple[float, ...]          # BC: (pcEntry, lambda); VG: (alpha, n, l)
+    swr: float = 0.0
+    snr: float = 0.0
+    regularize: bool = True
+    reg: Tuple[float, ...] = ()        # BC: (pcLowSwe,), VG: (pcLowSwe, pcHighSwe, krnLowSwe, krwHighSwe)
+
+
+@dataclasses.dataclass
+class Options:
+    enable_gravity: bool = True
+    gravity: float = 9.81
+    upwind_weight: float = 1.0
+    fd_method: int = 1
+    base_eps: float = 1e-10
+    privar_magnitude: Tuple[float, float] = (-1.0, -1.0)
+    stationary: bool = False
+    dt: float = 1.0
+    extrusion: float = 1.0
+
+
+@dataclasses.dataclass
+class ProblemSpec:
+    name: str
+    model: int
+    dim: int
+    cells: Tuple[int, ...]
+    lower: Tuple[float, ...]
+    upper: Tuple[float, ...]
+    K: np.ndarray
+    phi: np.ndarray
+    region: np.ndarray
+    materials: List[Material]
+    rho: Tuple[float, ...]
+    mu: Tuple[float, ...]
+    bc_type: Dict[int, np.ndarray]      # side -> int32[nf]
+    bc_values: Dict[int, np.ndarray]    # side -> float64[nf, numEq]
+    options: Options
+    initial: np.ndarray                 # float64[n, numEq]
+    source: Optional[np.ndarray] = None
+    fluid_table: Optional[dict] = None  # tabulated liquid (1p compressible)
+
+    @property
+    def num_eq(self) -> int:
+        return 2 if self.model == MODEL_2P else 1
+
+    @property
+    def num_cells(self) -> int:
+        return int(np.prod(self.cells))
+
+    @property
+    def cells3(self) -> Tuple[int, int, int]:
+        c = tuple(self.cells) + (1,) * (3 - len(self.cells))
+        return c  # type: ignore
+
+
+# ------------------------------------------------------------------------------------------------------
+# geometry helpers (YaspGrid equidistant coordinates: x_i = lower + i*h; centres 0.5*(x_i + x_{i+1}))
+# ------------------------------------------------------------------------------------------------------
+def node_coords(cells, lower, upper):
+    out = []
+    for a in range(len(cells)):
+        h = (upper[a] - lower[a]) / cells[a]
+        out.append(lower[a] + np.arange(cells[a] + 1, dtype=np.float64) * h)
+    return out
+
+
+def cell_centers(cells, lower, upper):
+    """float64[n, dim], x fastest."""
+    xs = node_coords(cells, lower, upper)
+    ctr = [0.5 * (x[:-1] + x[1:]) for x in xs]
+    grids = np.meshgrid(*ctr, indexing="ij")
+    # x fastest: flatten in Fortran order
+    return np.stack([g.reshape(-1, order="F") for g in grids], axis=1)
+
+
+def side_face_centers(cells, lower, upper, side):
+    """float64[nf, dim] centres of the boundary faces of `side` (lower remaining axis fastest)."""
+    dim = len(cells)
+    a = side // 2
+    xs = node_coords(cells, lower, upper)
+    ctr = [0.5 * (x[:-1] + x[1:]) for x in xs]
+    ctr[a] = np.array([xs[a][-1] if side & 1 else xs[a][0]])
+    grids = np.meshgrid(*ctr, indexing="ij")
+    return np.stack([g.reshape(-1, order="F") for g in grids], axis=1)[:, :dim]
+
+
+def _in_box(pos, lo, hi, eps):
+    ok = np.ones(pos.shape[0], dtype=bool)
+    for a in range(pos.shape[1]):
+        ok &= ~((pos[:, a] < lo[a] + eps) | (pos[:, a] > hi[a] - eps))
+    return ok
+
+
+# ------------------------------------------------------------------------------------------------------
+# std::mt19937 + Dumux::SimpleLogNormalDistribution (dumux/common/random.hh; Box-Mueller with cached pair)
+# ------------------------------------------------------------------------------------------------------
+class DumuxLogNormalField:
+    """Replays ``std::mt19937 rand(seed)`` feeding one or more ``SimpleLogNormalDistribution`` objects.
+
+    Each distribution keeps its own Box-Mueller cache (dumux/common/random.hh SimpleNormalDistribution::operator()),
+    returns z1 first and the cached z0 on the next call; lognormal = exp(normal).
+    """
+
+    def __init__(self, seed: int = 0):
+        self._rs = np.random.RandomState(seed)          # init_genrand(seed) == std::mt19937(seed)
+        self._buf = np.empty(0, dtype=np.uint64)
+        self._pos = 0
+
+    def _next_u32(self) -> int:
+        if self._pos >= self._buf.size:
+            # RandomState.randint draws masked 32-bit outputs one per value for this range
+            self._buf = self._rs.randint(0, 2 ** 32, size=1 << 16, dtype=np.uint64)
+            self._pos = 0
+        v = int(self._buf[self._pos])
+        self._pos += 1
+        return v
+
+    def make_dist(self, mean: float, stddev: float):
+        state = {"cached": None}
+        eps = np.finfo(np.float64).eps
+
+        def draw() -> float:
+            if state["cached"] is not None:
+                v = state["cached"]
+                state["cached"] = None
+                return float(np.exp(v))
+            while True:
+                u1 = 2.0 ** -32 * self._next_u32()
+                u2 = 2.0 ** -32 * self._next_u32()
+                if u1 > eps:
+                    break
+            magnitude = stddev * np.sqrt(-2.0 * np.log(u1))
+            z0 = magnitude * np.cos(2.0 * np.pi * u2) + mean
+            z1 = magnitude * np.sin(2.0 * np.pi * u2) + mean
+            state["cached"] = z0
+            return float(np.exp(z1))
+
+        return draw
+
+
+def lognormal_permeability(n: int, kmean: float, seed: int = 0, in_lens: Optional[np.ndarray] = None,
+                           kmean_lens: Optional[float] = None) -> np.ndarray:
+    """examples/1ptracer/spatialparams_1p.hh:95-104: one draw per element in element order."""
+    gen = DumuxLogNormalField(seed)
+    dist = gen.make_dist(np.log(kmean), np.log(kmean) * 0.1)
+    dist_lens = gen.make_dist(np.log(kmean_lens), np.log(kmean_lens) * 0.1) if kmean_lens is not None else None
+    out = np.empty(n, dtype=np.float64)
+    for i in range(n):
+        if in_lens is not None and in_lens[i]:
+            out[i] = dist_lens()
+        else:
+            out[i] = dist()
+    return out
+
+
+def fast_lognormal_multiplier(n: int, sigma: float, seed: int = 0) -> np.ndarray:
+    """Vectorised heterogeneity multiplier exp(N(0, sigma)) for the large synthetic grids:
+    same generator family (MT19937 seeded with init_genrand(seed)), numpy's normal transform."""
+    rs = np.random.RandomState(seed)
+    return np.exp(rs.normal(0.0, sigma, size=n))
+
+
+# ------------------------------------------------------------------------------------------------------
+# C1: test/porousmediumflow/1p/incompressible (params.input, problem.hh:41-100, spatialparams.hh:44-106)
+# ------------------------------------------------------------------------------------------------------
+def onep_incompressible(cells=(10, 10), lower=None, upper=None, numdiff_params=True) -> ProblemSpec:
+    dim = len(cells)
+    lower = tuple([0.0] * dim) if lower is None else lower
+    upper = tuple([1.0] * dim) if upper is None else upper
+    n = int(np.prod(cells))
+    ctr = cell_centers(cells, lower, upper)
+    lens = _in_box(ctr, [0.2] * dim, [0.8] * dim, 1.5e-7)
+    K = np.where(lens, 1e-12, 1e-10)
+    bc_type, bc_values = {}, {}
+    ymax = upper[dim - 1]
+    for side in range(2 * dim):
+        fc = side_face_centers(cells, lower, upper, side)
+        y = fc[:, dim - 1]
+        dirichlet = (y < 1e-6) | (y > ymax - 1e-6)
+        bc_type[side] = np.where(dirichlet, BC_DIRICHLET, BC_NEUMANN).astype(np.int32)
+        vals = np.zeros((fc.shape[0], 1))
+        vals[dirichlet, 0] = 1.0e5 + (-1.0e5) * (y[dirichlet] - ymax)
+        bc_values[side] = vals
+    opt = Options(stationary=True)
+    if numdiff_params:
+        opt.base_eps = 0.1
+        opt.privar_magnitude = (1e5, -1.0)
+    return ProblemSpec(
+        name="1p_incompressible", model=MODEL_1P, dim=dim, cells=tuple(cells), lower=tuple(lower), upper=tuple(upper),
+        K=K, phi=np.full(n, 0.4), region=np.zeros(n, dtype=np.int32), materials=[],
+        rho=(1000.0,), mu=(1e-3,), bc_type=bc_type, bc_values=bc_values, options=opt,
+        initial=np.zeros((n, 1)))
+
+
+# ------------------------------------------------------------------------------------------------------
+# 2p lens, the reference test: test/porousmediumflow/2p/incompressible (params.input, problem.hh:50-168,
+# spatialparams.hh:46-140).  2-D: y vertical.  `vertical_axis` = dim-1 always (gravity acts along -e_{dim-1}).
+# ------------------------------------------------------------------------------------------------------
+def twop_lens(cells=(48, 32), law="vg", lower=None, upper=None, lens_lower=None, lens_upper=None,
+              dt=250.0, heterogeneity_sigma=0.0, seed=0, bc_params=None) -> ProblemSpec:
+    dim = len(cells)
+    if dim == 2:
+        lower = (0.0, 0.0) if lower is None else lower
+        upper = (6.0, 4.0) if upper is None else upper
+        lens_lower = (1.0, 2.0) if lens_lower is None else lens_lower
+        lens_upper = (4.0, 3.0) if lens_upper is None else lens_upper
+    else:
+        # 3-D extension: [0,6]x[0,4]x[0,4], z vertical, lens box [1,4]x[1,3]x[2,3]
+        lower = (0.0, 0.0, 0.0) if lower is None else lower
+        upper = (6.0, 4.0, 4.0) if upper is None else upper
+        lens_lower = (1.0, 1.0, 2.0) if lens_lower is None else lens_lower
+        lens_upper = (4.0, 3.0, 3.0) if lens_upper is None else lens_upper
+    n = int(np.prod(cells))
+    va = dim - 1
+    ctr = cell_centers(cells, lower, upper)
+    lens = _in_box(ctr, lens_lower, lens_upper, 1.5e-7)
+    K = np.where(lens, 9.05e-12, 4.6e-10)
+    if heterogeneity_sigma > 0.0:
+        K = K * fast_lognormal_multiplier(n, heterogeneity_sigma, seed)
+    region = lens.astype(np.int32)
+    if law == "vg":
+        mats = [Material(LAW_VG, (0.0037, 4.7, 0.5), swr=0.05, reg=(0.01, 0.99, 0.1, 0.9)),
+                Material(LAW_VG, (0.00045, 7.3, 0.5), swr=0.18, reg=(0.01, 0.99, 0.1, 0.9))]
+    else:
+        bp = bc_params or ((500.0, 2.0), (2000.0, 2.0))
+        mats = [Material(LAW_BC, bp[0], swr=0.05, reg=(0.01,)),
+                Material(LAW_BC, bp[1], swr=0.18, reg=(0.01,))]
+    rho_w, g = 1000.0, -9.81
+    height = upper[va] - lower[va]
+    width = upper[0] - lower[0]
+    alpha = 1 + 1.5 / height
+    bc_type, bc_values = {}, {}
+    eps = 1e-6
+    for side in range(2 * dim):
+        fc = side_face_centers(cells, lower, upper, side)
+        nf = fc.shape[0]
+        x, y = fc[:, 0], fc[:, va]
+        left = x < lower[0] + eps
+        right = x > upper[0] - eps
+        dirichlet = left | right
+        t = np.where(dirichlet, BC_DIRICHLET, BC_NEUMANN).astype(np.int32)
+        vals = np.zeros((nf, 2))
+        depth = upper[va] - y
+        factor = (width * alpha + (1.0 - alpha) * x) / width
+        vals[dirichlet, 0] = (1e5 - factor * rho_w * g * depth)[dirichlet]
+        vals[dirichlet, 1] = 0.0
+        lam = (upper[0] - x) / width
+        inlet = (y > upper[va] - eps) & (0.5 < lam) & (lam < 2.0 / 3.0) & ~dirichlet
+        vals[inlet, 1] = -0.04
+        bc_type[side], bc_values[side] = t, vals
+    init = np.zeros((n, 2))
+    init[:, 0] = 1e5 - rho_w * g * (upper[va] - ctr[:, va])
+    return ProblemSpec(
+        name=f"2p_lens_{dim}d_{law}", model=MODEL_2P, dim=dim, cells=tuple(cells), lower=tuple(lower), upper=tuple(upper),
+        K=K, phi=np.full(n, 0.4), region=region, materials=mats, rho=(1000.0, 1460.0), mu=(1e-3, 5.7e-4),
+        bc_type=bc_type, bc_values=bc_values, options=Options(stationary=False, dt=dt), initial=init)
+
+
+# ------------------------------------------------------------------------------------------------------
+# 1p incompressible on the log-normal field of examples/1ptracer (spatialparams_1p.hh:95-104, problem_1p.hh)
+# ------------------------------------------------------------------------------------------------------
+def onep_tracer_pressure(cells=(50, 50)) -> ProblemSpec:
+    dim = len(cells)
+    lower, upper = tuple([0.0] * dim), tuple([1.0] * dim)
+    n = int(np.prod(cells))
+    ctr = cell_centers(cells, lower, upper)
+    lens = _in_box(ctr, [0.2] * dim, [0.8] * dim, 1.5e-7)
+    K = lognormal_permeability(n, 1e-10, 0, lens, 1e-11)
+    ymax = upper[dim - 1]
+    bc_type, bc_values = {}, {}
+    for side in range(2 * dim):
+        fc = side_face_centers(cells, lower, upper, side)
+        y = fc[:, dim - 1]
+        dirichlet = (y < 1e-6) | (y > ymax - 1e-6)
+        bc_type[side] = np.where(dirichlet, BC_DIRICHLET, BC_NEUMANN).astype(np.int32)
+        vals = np.zeros((fc.shape[0], 1))
+        vals[dirichlet, 0] = 1.0e5 * (2.0 - y[dirichlet])
+        bc_values[side] = vals
+    return ProblemSpec(
+        name="1ptracer_pressure", model=MODEL_1P, dim=dim, cells=tuple(cells), lower=lower, upper=upper,
+        K=K, phi=np.full(n, 0.2), region=np.zeros(n, dtype=np.int32), materials=[],
+        rho=(1000.0,), mu=(1e-3,), bc_type=bc_type, bc_values=bc_values,
+        options=Options(stationary=True, enable_gravity=False), initial=np.zeros((n, 1)))

@@ -1,0 +1,1236 @@
+/*
+ * oracle/oracle.cpp -- CPU restatement of DuMux's CCTpfa Newton-step hot path.
+ * TEST INFRASTRUCTURE ONLY: loaded by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs.  The product (dumux_b200/csrc) never includes or links this file.
+ *
+ * Every function cites the reference file:line it restates (paths relative to the DuMux tree).
+ * dune-istl / dune-grid arithmetic is restated from DUNE 2.10 (not vendored in the reference tree):
+ * "parity unpinned" at tight tolerance for those parts, see oracle.h.
+ *
+ * Floating-point contract (the "canonical operation sequence" the CUDA kernels must reproduce):
+ * compiled with -ffp-contract=off; source order of operations below is the order executed; the only
+ * fused operations are the explicit fma calls inside orc_det_pow.
+ */
+#include "oracle.h"
+#include "det_math.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace {
+
+typedef double (*pow_fn)(double, double);
+double std_pow_(double x, double y) { return std::pow(x, y); }
+double det_pow_(double x, double y) { return orc_det_pow(x, y); }
+
+inline double clamp01(double v) { return v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v); }
+
+// ---------------------------------------------------------------------------------------------
+// 2-point cubic spline with prescribed end slopes: dumux/common/spline.hh:263-347 (Spline<Scalar,2>),
+// dumux/common/splinecommon_.hh:419-436 (makeFullSystem_), :444-474 (natural part), :478-501 (eval_),
+// :504-523 (evalDerivative_).  The 2x2 moment system is solved with Dune::FieldMatrix<2,2>::solve
+// (dune-common densematrix.hh, explicit Cramer branch for n==2) [DUNE-ext].
+// ---------------------------------------------------------------------------------------------
+struct Spline2 {
+    double x0 = 0, x1 = 1, y0 = 0, y1 = 0, M0 = 0, M1 = 0;
+    void set(double x0_, double x1_, double y0_, double y1_, double m0, double m1)
+    {
+        x0 = x0_; x1 = x1_; y0 = y0_; y1 = y1_;
+        const double h = x1 - x0;
+        // makeNaturalSystem_: M[0][0]=2, M[n][n]=2; makeFullSystem_: M[0][1]=1, M[n][n-1]=1
+        const double m00 = 2, m01 = 1, m10 = 1, m11 = 2;
+        const double d0 = 6 / h * ((y1 - y0) / h - m0);
+        const double d1 = 6 / h * (m1 - (y1 - y0) / h);
+        double detinv = m00 * m11 - m01 * m10;
+        detinv = 1.0 / detinv;
+        M0 = detinv * (m11 * d0 - m01 * d1);
+        M1 = detinv * (m00 * d1 - m10 * d0);
+    }
+    double eval(double x) const
+    {
+        const double h = x1 - x0;
+        const double xi = x - x0;
+        const double xi1 = x1 - x;
+        const double A = (y1 - y0) / h - h / 6 * (M1 - M0);
+        const double B = y0 - M0 * (h * h) / 6;
+        return M0 * xi1 * xi1 * xi1 / (6 * h) + M1 * xi * xi * xi / (6 * h) + A * xi + B;
+    }
+    double evalDerivative(double x) const
+    {
+        const double h = x1 - x0;
+        const double xi = x - x0;
+        const double xi1 = x1 - x;
+        const double A = (y1 - y0) / h - h / 6 * (M1 - M0);
+        return -M0 * xi1 * xi1 / (2 * h) + M1 * xi * xi / (2 * h) + A;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Material law = TwoPMaterialLaw<BaseLaw, Regularization, TwoPEffToAbsDefaultPolicy>
+//   wrapper:        dumux/material/fluidmatrixinteractions/2p/materiallaw.hh:104-243
+//   eff<->abs:      .../2p/efftoabsdefaultpolicy.hh:106-152
+//   Brooks-Corey:   .../2p/brookscorey.hh:100-108 (pc), :165-174 (dpc_dswe), :215-223 (krw), :266-276 (krn),
+//                   regularisation :365-477, initPcParameters_ :481-489
+//   van Genuchten:  .../2p/vangenuchten.hh pc/krw/krn/derivatives, regularisation (pc spline on (pcHighSwe,1),
+//                   krw spline on [krwHighSwe,1), krn spline on (0,krnLowSwe]), initPcParameters_/initKrParameters_
+// ---------------------------------------------------------------------------------------------
+struct Law {
+    int kind = ORC_LAW_BROOKSCOREY;
+    bool reg = true;
+    double swr = 0, snr = 0;
+    // BC
+    double pe = 0, lambda = 2;
+    // VG
+    double alpha = 0, n = 2, m = 0.5, l = 0.5;
+    // regularisation thresholds
+    double pcLowSwe = 0.01, pcHighSwe = 0.99, krnLowSwe = 0.1, krwHighSwe = 0.9;
+    // derived
+    double pcLowSwePcValue = 0, pcHighSwePcValue = 0, pcDerivativeLowSw = 0, pcDerivativeHighSwEnd = 0,
+           pcDerivativeHighSweThreshold = 0;
+    Spline2 pcSpline, krwSpline, krnSpline;
+    pow_fn pw = det_pow_;
+
+    // efftoabsdefaultpolicy.hh:106-152
+    double swToSwe(double sw) const { return (sw - swr) / (1.0 - swr - snr); }
+    double sweToSw(double swe) const { return swe * (1.0 - swr - snr) + swr; }
+    double dswe_dsw() const { return 1.0 / (1.0 - swr - snr); }
+    double dsw_dswe() const { return 1.0 - swr - snr; }
+
+    // ---- base laws (unregularised, effective saturation) ----
+    double base_pc(double swe) const
+    {
+        swe = clamp01(swe);
+        if (kind == ORC_LAW_BROOKSCOREY)
+            return pe * pw(swe, -1.0 / lambda);                                  // brookscorey.hh:107
+        return pw(pw(swe, -1.0 / m) - 1, 1.0 / n) / alpha;                        // vangenuchten.hh pc
+    }
+    double base_dpc_dswe(double swe) const
+    {
+        swe = clamp01(swe);
+        if (kind == ORC_LAW_BROOKSCOREY)
+            return -pe / lambda * pw(swe, -1.0 / lambda - 1.0);                  // brookscorey.hh:173
+        const double powSwe = pw(swe, -1 / m);                                    // vangenuchten.hh:179-181
+        return -1.0 / alpha * pw(powSwe - 1, 1.0 / n - 1) / n * powSwe / swe / m;
+    }
+    double base_krw(double swe) const
+    {
+        swe = clamp01(swe);
+        if (kind == ORC_LAW_BROOKSCOREY)
+            return pw(swe, 2.0 / lambda + 3.0);                                  // brookscorey.hh:222
+        const double r = 1.0 - pw(1.0 - pw(swe, 1.0 / m), m);                     // vangenuchten.hh krw
+        return pw(swe, l) * r * r;
+    }
+    double base_dkrw_dswe(double swe) const
+    {
+        swe = clamp01(swe);
+        if (kind == ORC_LAW_BROOKSCOREY)
+            return (2.0 / lambda + 3.0) * pw(swe, 2.0 / lambda + 2.0);           // brookscorey.hh:247
+        const double x = 1.0 - pw(swe, 1.0 / m);
+        const double xToM = pw(x, m);
+        return (1.0 - xToM) * pw(swe, l - 1) * ((1.0 - xToM) * l + 2 * xToM * (1.0 - x) / x);
+    }
+    double base_krn(double swe) const
+    {
+        swe = clamp01(swe);
+        if (kind == ORC_LAW_BROOKSCOREY) {
+            const double exponent = 2.0 / lambda + 1.0;                          // brookscorey.hh:273-275
+            const double sne = 1.0 - swe;
+            return sne * sne * (1.0 - pw(swe, exponent));
+        }
+        return pw(1 - swe, l) * pw(1 - pw(swe, 1.0 / m), 2 * m);                  // vangenuchten.hh krn
+    }
+    double base_dkrn_dswe(double swe) const
+    {
+        swe = clamp01(swe);
+        if (kind == ORC_LAW_BROOKSCOREY) {
+            const double lambdaInv = 1.0 / lambda;                               // brookscorey.hh:302-304
+            const double swePow = pw(swe, 2 * lambdaInv);
+            return 2.0 * (swe - 1.0) * (1.0 + (0.5 + lambdaInv) * swePow - (1.5 + lambdaInv) * swePow * swe);
+        }
+        const double sne = 1.0 - swe;
+        const double x = 1.0 - pw(swe, 1.0 / m);
+        return -pw(sne, l - 1.0) * pw(x, 2 * m - 1.0) * (l * x + 2.0 * sne / swe * (1.0 - x));
+    }
+
+    // unregularised absolute-saturation versions used by the regularisation init (materiallaw.hh, <false>)
+    double pc_noreg(double sw) const { return base_pc(swToSwe(sw)); }
+    double dpc_dsw_noreg(double sw) const { return base_dpc_dswe(swToSwe(sw)) * dswe_dsw(); }
+    double krw_noreg(double sw) const { return base_krw(swToSwe(sw)); }
+    double dkrw_dsw_noreg(double sw) const { return base_dkrw_dswe(swToSwe(sw)) * dswe_dsw(); }
+    double krn_noreg(double sw) const { return base_krn(swToSwe(sw)); }
+    double dkrn_dsw_noreg(double sw) const { return base_dkrn_dswe(swToSwe(sw)) * dswe_dsw(); }
+
+    void init()
+    {
+        if (!reg) return;
+        if (kind == ORC_LAW_BROOKSCOREY) {
+            // brookscorey.hh:481-489
+            const double lowSw = sweToSw(pcLowSwe);
+            const double highSw = sweToSw(1.0);
+            const double dsw = dsw_dswe();
+            pcDerivativeLowSw = dpc_dsw_noreg(lowSw) * dsw;
+            pcDerivativeHighSwEnd = dpc_dsw_noreg(highSw) * dsw;
+            pcLowSwePcValue = pc_noreg(lowSw);
+        } else {
+            // vangenuchten.hh initPcParameters_
+            {
+                const double lowSw = sweToSw(pcLowSwe);
+                const double highSw = sweToSw(pcHighSwe);
+                const double dsw = dsw_dswe();
+                pcDerivativeLowSw = dpc_dsw_noreg(lowSw) * dsw;
+                pcDerivativeHighSweThreshold = dpc_dsw_noreg(highSw) * dsw;
+                pcDerivativeHighSwEnd = 2.0 * (0.0 - pc_noreg(highSw)) / (1.0 - pcHighSwe);
+                pcLowSwePcValue = pc_noreg(lowSw);
+                pcHighSwePcValue = pc_noreg(highSw);
+                if (pcHighSwe < 1.0)
+                    pcSpline.set(pcHighSwe, 1.0, pcHighSwePcValue, 0, pcDerivativeHighSweThreshold, pcDerivativeHighSwEnd);
+            }
+            // vangenuchten.hh initKrParameters_
+            {
+                const double lowSw = sweToSw(krnLowSwe);
+                const double highSw = sweToSw(krwHighSwe);
+                const double dsw = dsw_dswe();
+                const double krwHighSw = krw_noreg(highSw);
+                const double dkrwHighSw = dkrw_dsw_noreg(highSw) * dsw;
+                const double krnLowSw = krn_noreg(lowSw);
+                const double dkrnLowSw = dkrn_dsw_noreg(lowSw) * dsw;
+                if (krwHighSwe < 1.0) krwSpline.set(krwHighSwe, 1.0, krwHighSw, 1.0, dkrwHighSw, 0.0);
+                if (krnLowSwe > 0.0) krnSpline.set(0.0, krnLowSwe, 1.0, krnLowSw, 0.0, dkrnLowSw);
+            }
+        }
+    }
+
+    // materiallaw.hh:104-118 + brookscorey.hh:365-380 / vangenuchten.hh regularised pc
+    double pc(double sw) const
+    {
+        const double swe = swToSwe(sw);
+        if (reg) {
+            if (kind == ORC_LAW_BROOKSCOREY) {
+                if (swe <= pcLowSwe) return pcLowSwePcValue + pcDerivativeLowSw * (swe - pcLowSwe);
+                else if (swe >= 1.0) return pcDerivativeHighSwEnd * (swe - 1.0) + pe;
+            } else {
+                if (swe <= pcLowSwe) return pcLowSwePcValue + pcDerivativeLowSw * (swe - pcLowSwe);
+                else if (swe >= 1.0) return pcDerivativeHighSwEnd * (swe - 1.0);
+                else if (swe > pcHighSwe) return pcSpline.eval(swe);
+            }
+        }
+        return base_pc(swe);
+    }
+    double dpc_dsw(double sw) const
+    {
+        const double swe = swToSwe(sw);
+        if (reg) {
+            if (swe <= pcLowSwe) return pcDerivativeLowSw * dswe_dsw();
+            else if (swe >= 1.0) return pcDerivativeHighSwEnd * dswe_dsw();
+            else if (kind == ORC_LAW_VANGENUCHTEN && swe > pcHighSwe) return pcSpline.evalDerivative(swe) * dswe_dsw();
+        }
+        return base_dpc_dswe(swe) * dswe_dsw();
+    }
+    // materiallaw.hh:176-188 + regularised krw
+    double krw(double sw) const
+    {
+        const double swe = swToSwe(sw);
+        if (reg) {
+            if (swe <= 0.0) return 0.0;
+            else if (swe >= 1.0) return 1.0;
+            else if (kind == ORC_LAW_VANGENUCHTEN && swe >= krwHighSwe) return krwSpline.eval(swe);
+        }
+        return base_krw(swe);
+    }
+    double dkrw_dsw(double sw) const
+    {
+        const double swe = swToSwe(sw);
+        if (reg) {
+            if (swe <= 0.0) return 0.0;
+            else if (swe >= 1.0) return 0.0;
+            else if (kind == ORC_LAW_VANGENUCHTEN && swe >= krwHighSwe) return krwSpline.evalDerivative(swe) * dswe_dsw();
+        }
+        return base_dkrw_dswe(swe) * dswe_dsw();
+    }
+    // materiallaw.hh:210-222 + regularised krn
+    double krn(double sw) const
+    {
+        const double swe = swToSwe(sw);
+        if (reg) {
+            if (swe <= 0.0) return 1.0;
+            else if (swe >= 1.0) return 0.0;
+            else if (kind == ORC_LAW_VANGENUCHTEN && swe <= krnLowSwe) return krnSpline.eval(swe);
+        }
+        return base_krn(swe);
+    }
+    double dkrn_dsw(double sw) const
+    {
+        const double swe = swToSwe(sw);
+        if (reg) {
+            if (swe <= 0.0) return 0.0;
+            else if (swe >= 1.0) return 0.0;
+            else if (kind == ORC_LAW_VANGENUCHTEN && swe <= krnLowSwe) return krnSpline.evalDerivative(swe) * dswe_dsw();
+        }
+        return base_dkrn_dswe(swe) * dswe_dsw();
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Fluids.  Incompressible constants: SimpleH2O rho=1000, mu=1e-3 (dumux/material/components/simpleh2o.hh:265-312),
+// Trichloroethene rho=1460, mu=5.7e-4 (trichloroethene.hh:148-172).  Tabulated liquid: bilinear (T,p) lookup
+// dumux/material/components/tabulatedcomponent.hh:1166-1203 (interpolateTP_), table layout values[iT + iP*nT].
+// ---------------------------------------------------------------------------------------------
+struct Fluids {
+    double rho[2] = {1000.0, 1460.0};
+    double mu[2] = {1e-3, 5.7e-4};
+    bool tabulated = false;
+    int nT = 0, nP = 0;
+    double Tmin = 0, Tmax = 0, T = 293.15;
+    std::vector<double> pmin, pmax, rhoTab, muTab;
+
+    double interp(const std::vector<double>& values, double p) const
+    {
+        double alphaT = (nT - 1) * (T - Tmin) / (Tmax - Tmin);                       // tempIdx
+        if (alphaT < 0 - 1e-7 * nT || alphaT >= nT - 1 + 1e-7 * nT) return std::numeric_limits<double>::quiet_NaN();
+        const int iT = std::min(std::max((int)alphaT, 0), nT - 2);
+        alphaT -= iT;
+        double alphaP1 = (nP - 1) * (p - pmin[iT]) / (pmax[iT] - pmin[iT]);           // pressIdx(p, iT)
+        double alphaP2 = (nP - 1) * (p - pmin[iT + 1]) / (pmax[iT + 1] - pmin[iT + 1]);
+        const int iP1 = std::min(std::max((int)alphaP1, 0), nP - 2);
+        const int iP2 = std::min(std::max((int)alphaP2, 0), nP - 2);
+        alphaP1 -= iP1;
+        alphaP2 -= iP2;
+        return values[(iT) + (iP1)*nT] * (1 - alphaT) * (1 - alphaP1) + values[(iT) + (iP1 + 1) * nT] * (1 - alphaT) * (alphaP1)
+             + values[(iT + 1) + (iP2)*nT] * (alphaT) * (1 - alphaP2) + values[(iT + 1) + (iP2 + 1) * nT] * (alphaT) * (alphaP2);
+    }
+    double density(int phase, double p) const { return tabulated ? interp(rhoTab, p) : rho[phase]; }
+    double viscosity(int phase, double p) const { return tabulated ? interp(muTab, p) : mu[phase]; }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Secondary variables.
+//   2p: dumux/porousmediumflow/2p/volumevariables.hh:75-102 (update), :118-190 (completeFluidState, p0s1,
+//       wetting phase = phase 0); 1p: dumux/porousmediumflow/1p/volumevariables.hh:65-125.
+//   porosity = 1 - inertVolumeFraction, inertVolumeFraction = 1 - porosity(x)
+//       (dumux/common/fvporousmediumspatialparams.hh:112-118, material/solidstates/inertsolidstate.hh:55-61).
+// ---------------------------------------------------------------------------------------------
+struct VolVars {
+    double p[2], S[2], rho[2], mu[2], mob[2], pc, porosity, K, extr;
+};
+
+} // namespace
+
+struct orc_problem {
+    int model = ORC_MODEL_1P, b = 1, dim = 2;
+    int nc[3] = {1, 1, 1};
+    std::vector<double> xn[3];                 // node coordinates per axis
+    int n = 0;
+    orc_options opt;
+    std::vector<double> K, phi, q;
+    std::vector<int> region;
+    std::vector<Law> laws;
+    Fluids fluids;
+    std::vector<int> bcType[6];
+    std::vector<double> bcVal[6];
+    std::vector<int> rowptr, colidx;
+
+    // ---- grid geometry: YaspGrid equidistant / tensor coordinates, AxisAlignedCubeGeometry [DUNE-ext] ----
+    int idx(int i, int j, int k) const { return i + nc[0] * (j + nc[1] * k); }
+    void ijk(int c, int* o) const { o[0] = c % nc[0]; o[1] = (c / nc[0]) % nc[1]; o[2] = c / (nc[0] * nc[1]); }
+    double center(int a, int i) const { return 0.5 * (xn[a][i] + xn[a][i + 1]); }
+    double width(int a, int i) const { return xn[a][i + 1] - xn[a][i]; }
+    double volume(const int* c) const
+    {
+        double vol = 1.0;
+        for (int a = 0; a < dim; ++a) vol *= width(a, c[a]);
+        return vol;
+    }
+    double faceArea(int axis, const int* c) const
+    {
+        double vol = 1.0;
+        for (int a = 0; a < dim; ++a)
+            if (a != axis) vol *= width(a, c[a]);
+        return vol;
+    }
+    int sideFaces(int side) const
+    {
+        const int a = side / 2;
+        int nf = 1;
+        for (int d = 0; d < 3; ++d)
+            if (d != a) nf *= nc[d];
+        return nf;
+    }
+    // face index within its side: lower remaining axis fastest
+    int sideFaceIndex(int side, const int* c) const
+    {
+        const int a = side / 2;
+        if (a == 0) return c[1] + nc[1] * c[2];
+        if (a == 1) return c[0] + nc[0] * c[2];
+        return c[0] + nc[0] * c[1];
+    }
+    int neighbor(const int* c, int side) const
+    {
+        const int a = side / 2;
+        if (a >= dim) return -1;
+        int d[3] = {c[0], c[1], c[2]};
+        d[a] += (side & 1) ? 1 : -1;
+        if (d[a] < 0 || d[a] >= nc[a]) return -1;
+        return idx(d[0], d[1], d[2]);
+    }
+
+    // gravity vector: dumux/common/fvspatialparams.hh:48-52 (g[dimWorld-1] = -9.81 if enabled)
+    void gravityVec(double* g) const
+    {
+        g[0] = g[1] = g[2] = 0.0;
+        if (opt.enable_gravity) g[dim - 1] = -opt.gravity;
+    }
+
+    // ---- volume variables ----
+    void updateVolVars(VolVars& v, const double* priVars, int cell) const
+    {
+        const double phiInert = 1.0 - phi[cell];
+        v.porosity = 1.0 - phiInert;
+        v.K = K[cell];
+        v.extr = opt.extrusion;
+        if (model == ORC_MODEL_1P) {
+            v.S[0] = 1.0; v.S[1] = 0.0;
+            v.p[0] = priVars[0]; v.p[1] = 0.0;
+            v.rho[0] = fluids.density(0, v.p[0]);
+            v.mu[0] = fluids.viscosity(0, v.p[0]);
+            v.mob[0] = 1.0 / v.mu[0];                                   // 1p/volumevariables.hh:178
+            v.rho[1] = v.mu[1] = v.mob[1] = 0.0; v.pc = 0.0;
+            return;
+        }
+        const Law& law = laws[region[cell]];
+        const double Sn = priVars[1];
+        v.p[0] = priVars[0];
+        v.S[1] = Sn;
+        v.S[0] = 1 - Sn;
+        v.pc = law.pc(v.S[0]);
+        v.p[1] = priVars[0] + v.pc;
+        for (int ph = 0; ph < 2; ++ph) {
+            v.mu[ph] = fluids.viscosity(ph, v.p[ph]);
+            v.rho[ph] = fluids.density(ph, v.p[ph]);
+        }
+        v.mob[0] = law.krw(v.S[0]) / v.mu[0];
+        v.mob[1] = law.krn(v.S[0]) / v.mu[1];
+    }
+
+    // ---- TPFA transmissibility: dumux/discretization/cellcentered/tpfa/computetransmissibility.hh:69-80 ----
+    // scvf of cell c on `side`; scv = cell sc (either c itself or its neighbour across that face).
+    double computeTpfaTransmissibility(const int* c, int side, const int* sc, double t, double extr) const
+    {
+        const int a = side / 2;
+        double ip[3] = {0, 0, 0}, ctr[3] = {0, 0, 0}, nrm[3] = {0, 0, 0};
+        for (int d = 0; d < dim; ++d) {
+            ip[d] = (d == a) ? ((side & 1) ? xn[a][c[a] + 1] : xn[a][c[a]]) : center(d, c[d]);
+            // AxisAlignedCubeGeometry::center of the (degenerate) face box: 0.5*(x+x) = x exactly
+            if (d == a) ip[d] = 0.5 * (ip[d] + ip[d]);
+            ctr[d] = center(d, sc[d]);
+        }
+        nrm[a] = (side & 1) ? 1.0 : -1.0;
+        double dv[3];
+        double n2 = 0.0;
+        for (int d = 0; d < dim; ++d) { dv[d] = ip[d] - ctr[d]; n2 += dv[d] * dv[d]; }
+        double dot = 0.0;
+        for (int d = 0; d < dim; ++d) { dv[d] /= n2; dot += dv[d] * nrm[d]; }
+        return t * extr * dot;
+    }
+
+    // ---- advective TPFA flux of one phase over the face `side` of `cI`: flux/cctpfa/darcyslaw.hh:154-213,
+    //      transmissibility :218-259, upwinding flux/upwindscheme.hh:36-54,
+    //      phase mass flux porousmediumflow/immiscible/localresidual.hh:98-127 ----
+    void computeFlux(double* flux, const int* cI, int side, const VolVars& in, const VolVars& out, bool boundary, const int* cJ) const
+    {
+        const int a = side / 2;
+        const double area = faceArea(a, cI);
+        const double ti = computeTpfaTransmissibility(cI, side, cI, in.K, in.extr);
+        double tij, tj = 0.0;
+        if (boundary)
+            tij = area * ti;
+        else {
+            tj = -1.0 * computeTpfaTransmissibility(cI, side, cJ, out.K, out.extr);
+            if (ti * tj <= 0.0) tij = 0;
+            else tij = area * (ti * tj) / (ti + tj);
+        }
+        double g[3];
+        gravityVec(g);
+        double nrm[3] = {0, 0, 0};
+        nrm[a] = (side & 1) ? 1.0 : -1.0;
+        const int nph = (model == ORC_MODEL_1P) ? 1 : 2;
+        for (int ph = 0; ph < nph; ++ph) {
+            double f;
+            if (opt.enable_gravity) {
+                const double rho = boundary ? out.rho[ph] : (in.rho[ph] + out.rho[ph]) * 0.5;
+                const double pInside = in.p[ph];
+                const double pOutside = out.p[ph];
+                double ng = 0.0;
+                for (int d = 0; d < dim; ++d) ng += nrm[d] * g[d];
+                const double alpha_inside = in.K * ng * in.extr;      // vtmv(n,K,g)*extr, dumux/common/math.hh:908-913
+                f = tij * (pInside - pOutside) + rho * area * alpha_inside;
+                if (!boundary) {
+                    const double outsideTi = tj;                       // same expression as in calculateTransmissibility
+                    const double alpha_outside = out.K * ng * out.extr;
+                    f -= rho * tij / outsideTi * (alpha_inside - alpha_outside);
+                }
+            } else {
+                f = tij * (in.p[ph] - out.p[ph]);
+            }
+            // upwindscheme.hh:43-53, upwind term = density*mobility (immiscible/localresidual.hh:113-114)
+            const double w = opt.upwind_weight;
+            const double upIn = in.rho[ph] * in.mob[ph];
+            const double upOut = out.rho[ph] * out.mob[ph];
+            double mult;
+            if (std::signbit(f)) mult = w * upOut + (1.0 - w) * upIn;
+            else mult = w * upIn + (1.0 - w) * upOut;
+            flux[ph] = f * mult;
+        }
+    }
+
+    // Dirichlet "outside" vol vars are built with the INSIDE cell's spatial parameters:
+    // dumux/discretization/cellcentered/tpfa/elementvolumevariables.hh:318-346
+    // Flux over one scvf of cell I incl. boundary dispatch: dumux/assembly/cclocalresidual.hh:64-105
+    // vvI: (possibly deflected) vol vars of I; vvJ: vol vars of the neighbour (ignored on boundaries)
+    bool evalFlux(double* flux, int I, const int* cI, int side, const VolVars& vvI, const VolVars* vvJ) const
+    {
+        const int a = side / 2;
+        flux[0] = flux[1] = 0.0;
+        if (a >= dim) return false;
+        const int J = neighbor(cI, side);
+        if (J >= 0) {
+            int cJ[3];
+            ijk(J, cJ);
+            double f[2];
+            computeFlux(f, cI, side, vvI, *vvJ, false, cJ);
+            for (int e = 0; e < b; ++e) flux[e] += f[e];
+            return true;
+        }
+        const int fidx = sideFaceIndex(side, cI);
+        const int type = bcType[side].empty() ? ORC_BC_NEUMANN : bcType[side][fidx];
+        if (type == ORC_BC_NONE) return false;   // processor boundary of an overlap cell: no scvf (tpfa/fvgridgeometry.hh:272-320)
+        if (type == ORC_BC_DIRICHLET) {
+            VolVars bv;
+            double pv[2] = {0, 0};
+            for (int e = 0; e < b; ++e) pv[e] = bcVal[side][(size_t)fidx * b + e];
+            updateVolVars(bv, pv, I);
+            double f[2];
+            computeFlux(f, cI, side, vvI, bv, true, nullptr);
+            for (int e = 0; e < b; ++e) flux[e] += f[e];
+        } else {
+            // Neumann: cclocalresidual.hh:89-98: neumannFluxes *= area*extrusion
+            const double area = faceArea(a, cI);
+            for (int e = 0; e < b; ++e) {
+                double nf = bcVal[side].empty() ? 0.0 : bcVal[side][(size_t)fidx * b + e];
+                nf *= area * vvI.extr;
+                flux[e] += nf;
+            }
+        }
+        return true;
+    }
+
+    // storage term: porousmediumflow/immiscible/localresidual.hh:64-83
+    void computeStorage(double* s, const VolVars& v) const
+    {
+        const int nph = (model == ORC_MODEL_1P) ? 1 : 2;
+        for (int ph = 0; ph < nph; ++ph) s[ph] = v.porosity * v.rho[ph] * v.S[ph];
+    }
+
+    // complete local residual of element I: dumux/assembly/fvlocalassemblerbase.hh:108-135,
+    // flux+source dumux/assembly/fvlocalresidual.hh:150-169 (source first :319-333, then all scvfs in
+    // intersection order -x,+x,-y,+y,-z,+z), storage :274-304 added afterwards.
+    void evalLocalResidual(double* res, int I, const int* cI, const VolVars& vvI, const VolVars* nb /*[6]*/, const VolVars* prevI) const
+    {
+        const double vol = volume(cI);
+        for (int e = 0; e < b; ++e) {
+            double source = q.empty() ? 0.0 : q[(size_t)I * b + e];
+            source *= vol * vvI.extr;
+            res[e] = 0.0;
+            res[e] -= source;
+        }
+        for (int side = 0; side < 2 * dim; ++side) {
+            double f[2];
+            if (evalFlux(f, I, cI, side, vvI, &nb[side]))
+                for (int e = 0; e < b; ++e) res[e] += f[e];
+        }
+        if (!opt.stationary) {
+            double prevStorage[2], storage[2];
+            computeStorage(prevStorage, *prevI);
+            computeStorage(storage, vvI);
+            for (int e = 0; e < b; ++e) {
+                prevStorage[e] *= prevI->extr;
+                storage[e] *= vvI.extr;
+                storage[e] -= prevStorage[e];
+                storage[e] *= vol;
+                storage[e] /= opt.dt;
+                double st = 0.0;
+                st += storage[e];
+                res[e] += st;
+            }
+        }
+    }
+
+    // FD epsilon: dumux/assembly/numericepsilon.hh:47-51, dumux/common/numericdifferentiation.hh:36-41
+    double fdEps(double priVar, int pvIdx) const
+    {
+        return opt.privar_magnitude[pvIdx] > 0.0 ? opt.base_eps * opt.privar_magnitude[pvIdx]
+                                                 : opt.base_eps * (std::fabs(priVar) + 1.0);
+    }
+
+    void buildPattern()
+    {
+        // dumux/assembly/jacobianpattern.hh:27-52 + cellcentered/connectivitymap.hh:66-115: (I,I) and (J,I) for all
+        // face neighbours; BCRS columns ascending (Dune::MatrixIndexSet::exportIdx) [DUNE-ext]
+        rowptr.assign(n + 1, 0);
+        colidx.clear();
+        for (int I = 0; I < n; ++I) {
+            int c[3];
+            ijk(I, c);
+            int cols[7], nn = 0;
+            cols[nn++] = I;
+            for (int side = 0; side < 2 * dim; ++side) {
+                const int J = neighbor(c, side);
+                if (J >= 0) cols[nn++] = J;
+            }
+            std::sort(cols, cols + nn);
+            for (int k = 0; k < nn; ++k) colidx.push_back(cols[k]);
+            rowptr[I + 1] = (int)colidx.size();
+        }
+    }
+    int findEntry(int row, int col) const
+    {
+        for (int k = rowptr[row]; k < rowptr[row + 1]; ++k)
+            if (colidx[k] == col) return k;
+        return -1;
+    }
+
+    // ---------------------------------------------------------------------------------------------
+    // Column-wise numeric-differentiation assembly of one element:
+    // dumux/assembly/cclocalassembler.hh:164-348 (assembleJacobianAndResidualImpl), FD formula
+    // dumux/common/numericdifferentiation.hh:67-123.
+    // ---------------------------------------------------------------------------------------------
+    void assembleElement(int I, const double* cur, const double* prev, double* residual, double* jac) const
+    {
+        int cI[3];
+        ijk(I, cI);
+        VolVars vvI, prevVV, nb[6];
+        int nbIdx[6];
+        int nbC[6][3];
+        updateVolVars(vvI, cur + (size_t)I * b, I);
+        if (!opt.stationary) updateVolVars(prevVV, prev + (size_t)I * b, I);
+        for (int side = 0; side < 6; ++side) {
+            nbIdx[side] = (side < 2 * dim) ? neighbor(cI, side) : -1;
+            if (nbIdx[side] >= 0) {
+                ijk(nbIdx[side], nbC[side]);
+                updateVolVars(nb[side], cur + (size_t)nbIdx[side] * b, nbIdx[side]);
+            }
+        }
+        // origResiduals[0] (:191) and neighbour fluxes in the undeflected state (:211-218)
+        double orig0[2];
+        evalLocalResidual(orig0, I, cI, vvI, nb, &prevVV);
+        double origN[6][2];
+        for (int side = 0; side < 2 * dim; ++side) {
+            origN[side][0] = origN[side][1] = 0.0;
+            if (nbIdx[side] < 0) continue;
+            // flux from J's side over the shared face: J's face is the opposite side
+            double f[2];
+            evalFlux(f, nbIdx[side], nbC[side], side ^ 1, nb[side], &vvI);
+            for (int e = 0; e < b; ++e) origN[side][e] += f[e];
+        }
+        if (residual)
+            for (int e = 0; e < b; ++e) residual[(size_t)I * b + e] = orig0[e];
+        if (!jac) return;
+
+        for (int pv = 0; pv < b; ++pv) {
+            const double x0 = cur[(size_t)I * b + pv];
+            const double eps = fdEps(x0, pv);
+            // evalResiduals(priVar) (:241-261)
+            auto evalResiduals = [&](double priVar, double* r0, double rN[6][2]) {
+                double pvs[2] = {cur[(size_t)I * b], b > 1 ? cur[(size_t)I * b + 1] : 0.0};
+                pvs[pv] = priVar;
+                VolVars defl;
+                updateVolVars(defl, pvs, I);
+                evalLocalResidual(r0, I, cI, defl, nb, &prevVV);
+                for (int side = 0; side < 2 * dim; ++side) {
+                    rN[side][0] = rN[side][1] = 0.0;
+                    if (nbIdx[side] < 0) continue;
+                    double f[2];
+                    evalFlux(f, nbIdx[side], nbC[side], side ^ 1, nb[side], &defl);
+                    for (int e = 0; e < b; ++e) rN[side][e] += f[e];
+                }
+            };
+            double d0[2] = {0, 0}, dN[6][2];
+            for (int s = 0; s < 6; ++s) dN[s][0] = dN[s][1] = 0.0;
+            const int method = opt.fd_method;
+            auto forEach = [&](auto&& fn) {
+                for (int e = 0; e < b; ++e) fn(d0[e], -1, e);
+                for (int side = 0; side < 2 * dim; ++side)
+                    if (nbIdx[side] >= 0)
+                        for (int e = 0; e < b; ++e) fn(dN[side][e], side, e);
+            };
+            if (method == 5) {
+                double a0[2], aN[6][2], t0[2], tN[6][2];
+                evalResiduals(x0 + eps, a0, aN);
+                evalResiduals(x0 - eps, t0, tN);
+                forEach([&](double& d, int s, int e) { d = (s < 0 ? a0[e] : aN[s][e]); d -= (s < 0 ? t0[e] : tN[s][e]); d *= 8.0; });
+                evalResiduals(x0 - 2.0 * eps, t0, tN);
+                forEach([&](double& d, int s, int e) { d += (s < 0 ? t0[e] : tN[s][e]); });
+                evalResiduals(x0 + 2.0 * eps, t0, tN);
+                forEach([&](double& d, int s, int e) { d -= (s < 0 ? t0[e] : tN[s][e]); d /= 12.0 * eps; });
+            } else {
+                double delta = 0.0;
+                if (method >= 0) {
+                    delta += eps;
+                    double a0[2], aN[6][2];
+                    evalResiduals(x0 + eps, a0, aN);
+                    forEach([&](double& d, int s, int e) { d = (s < 0 ? a0[e] : aN[s][e]); });
+                } else
+                    forEach([&](double& d, int s, int e) { d = (s < 0 ? orig0[e] : origN[s][e]); });
+                if (method <= 0) {
+                    delta += eps;
+                    double t0[2], tN[6][2];
+                    evalResiduals(x0 - eps, t0, tN);
+                    forEach([&](double& d, int s, int e) { d -= (s < 0 ? t0[e] : tN[s][e]); });
+                } else
+                    forEach([&](double& d, int s, int e) { d -= (s < 0 ? orig0[e] : origN[s][e]); });
+                forEach([&](double& d, int, int) { d /= delta; });
+            }
+            // scatter (:324-333): A[I][I][eq][pv] += d0[eq]; A[J][I][eq][pv] += dN[j][eq]
+            const int kd = findEntry(I, I);
+            for (int e = 0; e < b; ++e) jac[((size_t)kd * b + e) * b + pv] += d0[e];
+            for (int side = 0; side < 2 * dim; ++side) {
+                if (nbIdx[side] < 0) continue;
+                const int k = findEntry(nbIdx[side], I);
+                for (int e = 0; e < b; ++e) jac[((size_t)k * b + e) * b + pv] += dN[side][e];
+            }
+        }
+    }
+};
+
+// =================================================================================================
+// dune-istl 2.10 restatement [DUNE-ext]
+// =================================================================================================
+namespace {
+
+// FieldMatrix<double,b,b>::invert() [DUNE-ext, dune-common densematrix.hh]: n==1: 1/a; n==2: explicit
+// (detinv = 1/(a00*a11 - a01*a10); swap diag, negate off-diag, scale).
+bool invertBlock(double* A, int b)
+{
+    if (b == 1) {
+        if (A[0] == 0.0) return false;
+        A[0] = 1.0 / A[0];
+        return true;
+    }
+    double detinv = A[0] * A[3] - A[1] * A[2];
+    if (detinv == 0.0 || !(detinv == detinv)) return false;
+    detinv = 1.0 / detinv;
+    const double temp = A[0];
+    A[0] = A[3] * detinv;
+    A[1] = -A[1] * detinv;
+    A[2] = -A[2] * detinv;
+    A[3] = temp * detinv;
+    return true;
+}
+// C = A*B (rightmultiply semantic: A <- A*B) with Dune's loop order: C[i][j] = sum_k A[i][k]*B[k][j], sum from 0
+inline void rightMultiply(double* A, const double* B, int b)
+{
+    double C[4];
+    for (int i = 0; i < b; ++i)
+        for (int j = 0; j < b; ++j) {
+            double s = 0.0;
+            for (int k = 0; k < b; ++k) s += A[i * b + k] * B[k * b + j];
+            C[i * b + j] = s;
+        }
+    for (int i = 0; i < b * b; ++i) A[i] = C[i];
+}
+// y -= A x  (FieldMatrix::mmv)
+inline void mmv(const double* A, const double* x, double* y, int b)
+{
+    for (int i = 0; i < b; ++i)
+        for (int j = 0; j < b; ++j) y[i] -= A[i * b + j] * x[j];
+}
+// y += A x (umv)
+inline void umv(const double* A, const double* x, double* y, int b)
+{
+    for (int i = 0; i < b; ++i)
+        for (int j = 0; j < b; ++j) y[i] += A[i * b + j] * x[j];
+}
+
+// ILU::blockILU0Decomposition (dune-istl ilu.hh) [DUNE-ext]
+int ilu0Factor(int n, int b, const int* rowptr, const int* colidx, double* A)
+{
+    const int bb = b * b;
+    for (int i = 0; i < n; ++i) {
+        int kdiag = -1;
+        for (int kij = rowptr[i]; kij < rowptr[i + 1]; ++kij) {
+            const int j = colidx[kij];
+            if (j >= i) { if (j == i) kdiag = kij; break; }
+            // find diagonal of row j
+            int kjj = -1;
+            for (int k = rowptr[j]; k < rowptr[j + 1]; ++k) if (colidx[k] == j) { kjj = k; break; }
+            rightMultiply(A + (size_t)kij * bb, A + (size_t)kjj * bb, b);      // A_ij <- A_ij * A_jj^{-1}
+            // for all k>j present in both rows: A_ik -= A_ij * A_jk
+            int ik = kij + 1, jk = kjj + 1;
+            const int iend = rowptr[i + 1], jend = rowptr[j + 1];
+            while (ik < iend && jk < jend) {
+                if (colidx[ik] == colidx[jk]) {
+                    // FieldMatrix mmm: C -= A*B
+                    double* C = A + (size_t)ik * bb;
+                    const double* L = A + (size_t)kij * bb;
+                    const double* U = A + (size_t)jk * bb;
+                    for (int r = 0; r < b; ++r)
+                        for (int c = 0; c < b; ++c)
+                            for (int k = 0; k < b; ++k) C[r * b + c] -= L[r * b + k] * U[k * b + c];
+                    ++ik; ++jk;
+                } else if (colidx[ik] < colidx[jk]) ++ik;
+                else ++jk;
+            }
+        }
+        if (kdiag < 0) return 1;
+        if (!invertBlock(A + (size_t)kdiag * bb, b)) return 1;
+    }
+    return 0;
+}
+
+// ILU::blockILUBacksolve [DUNE-ext]
+void ilu0Apply(int n, int b, const int* rowptr, const int* colidx, const double* A, double* v, const double* d)
+{
+    const int bb = b * b;
+    for (int i = 0; i < n; ++i) {
+        double rhs[2];
+        for (int e = 0; e < b; ++e) rhs[e] = d[(size_t)i * b + e];
+        for (int k = rowptr[i]; k < rowptr[i + 1] && colidx[k] < i; ++k) mmv(A + (size_t)k * bb, v + (size_t)colidx[k] * b, rhs, b);
+        for (int e = 0; e < b; ++e) v[(size_t)i * b + e] = rhs[e];
+    }
+    for (int i = n - 1; i >= 0; --i) {
+        double rhs[2];
+        for (int e = 0; e < b; ++e) rhs[e] = v[(size_t)i * b + e];
+        int kd = -1;
+        for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+            if (colidx[k] == i) kd = k;
+            else if (colidx[k] > i) mmv(A + (size_t)k * bb, v + (size_t)colidx[k] * b, rhs, b);
+        }
+        double out[2] = {0, 0};
+        umv(A + (size_t)kd * bb, rhs, out, b);      // v_i = A_ii^{-1} * rhs (FieldMatrix::mv, sum from 0)
+        for (int e = 0; e < b; ++e) v[(size_t)i * b + e] = out[e];
+    }
+}
+
+// BCRSMatrix::mv: y = A x, per row sum from 0 in column order
+void spmv(int n, int b, const int* rowptr, const int* colidx, const double* A, const double* x, double* y)
+{
+    const int bb = b * b;
+    for (int i = 0; i < n; ++i) {
+        double acc[2] = {0, 0};
+        for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) umv(A + (size_t)k * bb, x + (size_t)colidx[k] * b, acc, b);
+        for (int e = 0; e < b; ++e) y[(size_t)i * b + e] = acc[e];
+    }
+}
+double dot(size_t n, const double* a, const double* c)
+{
+    double s = 0.0;
+    for (size_t i = 0; i < n; ++i) s += a[i] * c[i];
+    return s;
+}
+
+// Dune::BiCGSTABSolver::apply (dune-istl solvers.hh) [DUNE-ext], SURVEY Appendix A.
+// `prec(v,d)`: v = M^-1 d;  `op(x,y)`: y = A x;  `sp(a,b)`: scalar product.
+template <class Op, class Prec, class Dot>
+int bicgstab(size_t N, Op&& op, Prec&& prec, Dot&& sp, double* x, const double* rhs, double reduction, int maxit,
+             int* iterations, double* achieved)
+{
+    std::vector<double> r(rhs, rhs + N), rt(N), p(N, 0.0), v(N, 0.0), t(N), y(N), tmp(N);
+    // r = b - A x
+    op(x, tmp.data());
+    for (size_t i = 0; i < N; ++i) r[i] -= tmp[i];
+    rt = r;
+    double norm0 = std::sqrt(sp(r.data(), r.data()));
+    double norm = norm0;
+    auto converged = [&](double nrm) { return nrm < reduction * norm0 || nrm < 1e-30; };
+    *iterations = 0;
+    *achieved = 1.0;
+    if (!(norm0 == norm0) || std::isinf(norm0)) return 3;
+    if (converged(norm0)) { *achieved = (norm0 > 0 ? norm / norm0 : 0.0); return 0; }
+    double rho = 1, alpha = 1, omega = 1, rho_new, h, beta;
+    const double EPSILON = 1e-80;
+    double it;
+    int status = 1;
+    for (it = 0.5; it < maxit; it += .5) {
+        rho_new = sp(rt.data(), r.data());
+        if (std::fabs(rho) <= EPSILON || std::fabs(omega) <= EPSILON) { status = 2; break; }
+        if (it < 1)
+            p = r;
+        else {
+            beta = (rho_new / rho) * (alpha / omega);
+            for (size_t i = 0; i < N; ++i) p[i] += -omega * v[i];   // p.axpy(-omega,v)
+            for (size_t i = 0; i < N; ++i) p[i] *= beta;
+            for (size_t i = 0; i < N; ++i) p[i] += r[i];
+        }
+        std::fill(y.begin(), y.end(), 0.0);
+        prec(y.data(), p.data());
+        op(y.data(), v.data());
+        h = sp(rt.data(), v.data());
+        if (std::fabs(h) < EPSILON) { status = 2; break; }
+        alpha = rho_new / h;
+        for (size_t i = 0; i < N; ++i) x[i] += alpha * y[i];
+        for (size_t i = 0; i < N; ++i) r[i] += -alpha * v[i];
+        norm = std::sqrt(sp(r.data(), r.data()));
+        if (!(norm == norm) || std::isinf(norm)) { status = 3; break; }
+        if (converged(norm)) { status = 0; break; }
+        it += .5;
+        std::fill(y.begin(), y.end(), 0.0);
+        prec(y.data(), r.data());
+        op(y.data(), t.data());
+        omega = sp(t.data(), r.data()) / sp(t.data(), t.data());
+        for (size_t i = 0; i < N; ++i) x[i] += omega * y[i];
+        for (size_t i = 0; i < N; ++i) r[i] += -omega * t[i];
+        rho = rho_new;
+        norm = std::sqrt(sp(r.data(), r.data()));
+        if (!(norm == norm) || std::isinf(norm)) { status = 3; break; }
+        if (converged(norm)) { status = 0; break; }
+    }
+    *iterations = (int)std::ceil(std::min(it, (double)maxit));
+    *achieved = norm0 > 0 ? norm / norm0 : 0.0;
+    return status;
+}
+
+double nowSec()
+{
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+} // namespace
+
+// =================================================================================================
+// C API
+// =================================================================================================
+extern "C" {
+
+void orc_default_options(orc_options* o)
+{
+    o->enable_gravity = 1;
+    o->gravity = 9.81;
+    o->upwind_weight = 1.0;
+    o->fd_method = 1;
+    o->base_eps = 1e-10;
+    o->privar_magnitude[0] = o->privar_magnitude[1] = -1.0;
+    o->stationary = 0;
+    o->dt = 1.0;
+    o->extrusion = 1.0;
+    o->use_std_pow = 0;
+    o->num_threads = 0;
+}
+
+static orc_problem* createCommon(int model, int dim, const int* cells)
+{
+    orc_problem* p = new orc_problem;
+    p->model = model;
+    p->b = (model == ORC_MODEL_2P) ? 2 : 1;
+    p->dim = dim;
+    for (int a = 0; a < 3; ++a) p->nc[a] = (a < dim) ? cells[a] : 1;
+    p->n = p->nc[0] * p->nc[1] * p->nc[2];
+    orc_default_options(&p->opt);
+    p->K.assign(p->n, 1e-10);
+    p->phi.assign(p->n, 0.4);
+    p->region.assign(p->n, 0);
+    p->laws.resize(1);
+    return p;
+}
+
+orc_problem* orc_create(int model, int dim, const int* cells, const double* lower, const double* upper)
+{
+    orc_problem* p = createCommon(model, dim, cells);
+    // YaspGrid EquidistantOffsetCoordinates: x_i = origin + i*h, h = (upper-lower)/cells [DUNE-ext]
+    for (int a = 0; a < 3; ++a) {
+        p->xn[a].resize(p->nc[a] + 1);
+        if (a < dim) {
+            const double h = (upper[a] - lower[a]) / cells[a];
+            for (int i = 0; i <= p->nc[a]; ++i) p->xn[a][i] = lower[a] + i * h;
+        } else { p->xn[a][0] = 0.0; p->xn[a][1] = 1.0; }
+    }
+    p->buildPattern();
+    return p;
+}
+
+orc_problem* orc_create_tensor(int model, int dim, const int* cells, const double* x, const double* y, const double* z)
+{
+    orc_problem* p = createCommon(model, dim, cells);
+    const double* src[3] = {x, y, z};
+    for (int a = 0; a < 3; ++a) {
+        p->xn[a].resize(p->nc[a] + 1);
+        if (a < dim) for (int i = 0; i <= p->nc[a]; ++i) p->xn[a][i] = src[a][i];
+        else { p->xn[a][0] = 0.0; p->xn[a][1] = 1.0; }
+    }
+    p->buildPattern();
+    return p;
+}
+
+void orc_destroy(orc_problem* p) { delete p; }
+int orc_num_cells(const orc_problem* p) { return p->n; }
+int orc_num_eq(const orc_problem* p) { return p->b; }
+
+void orc_set_options(orc_problem* p, const orc_options* o)
+{
+    p->opt = *o;
+    for (auto& l : p->laws) { l.pw = o->use_std_pow ? std_pow_ : det_pow_; l.init(); }
+}
+void orc_set_cell_fields(orc_problem* p, const double* K, const double* phi, const int* region)
+{
+    if (K) p->K.assign(K, K + p->n);
+    if (phi) p->phi.assign(phi, phi + p->n);
+    if (region) p->region.assign(region, region + p->n);
+}
+void orc_set_source(orc_problem* p, const double* q) { p->q.assign(q, q + (size_t)p->n * p->b); }
+
+void orc_set_material(orc_problem* p, int region, int law, const double* params, double swr, double snr,
+                      int regularize, const double* reg)
+{
+    if ((int)p->laws.size() <= region) p->laws.resize(region + 1);
+    Law& l = p->laws[region];
+    l.kind = law;
+    l.swr = swr; l.snr = snr;
+    l.reg = regularize != 0;
+    l.pw = p->opt.use_std_pow ? std_pow_ : det_pow_;
+    if (law == ORC_LAW_BROOKSCOREY) {
+        l.pe = params[0]; l.lambda = params[1];
+        l.pcLowSwe = reg ? reg[0] : 0.01;
+    } else {
+        l.alpha = params[0]; l.n = params[1]; l.m = 1.0 - 1.0 / l.n;   // vangenuchten.hh Params::setN
+        l.l = params[2];
+        if (reg) { l.pcLowSwe = reg[0]; l.pcHighSwe = reg[1]; l.krnLowSwe = reg[2]; l.krwHighSwe = reg[3]; }
+    }
+    l.init();
+}
+void orc_set_fluids(orc_problem* p, const double* rho, const double* mu)
+{
+    p->fluids.tabulated = false;
+    for (int i = 0; i < (p->model == ORC_MODEL_2P ? 2 : 1); ++i) { p->fluids.rho[i] = rho[i]; p->fluids.mu[i] = mu[i]; }
+}
+void orc_set_fluid_table(orc_problem* p, int nT, int nP, double Tmin, double Tmax, const double* pmin, const double* pmax,
+                         const double* rho, const double* mu, double temperature);
+
+int orc_side_faces(const orc_problem* p, int side) { return p->sideFaces(side); }
+void orc_set_boundary(orc_problem* p, int side, const int* type, const double* values)
+{
+    const int nf = p->sideFaces(side);
+    p->bcType[side].assign(type, type + nf);
+    p->bcVal[side].assign(values, values + (size_t)nf * p->b);
+}
+void orc_side_face_center(const orc_problem* p, int side, int f, double* out)
+{
+    const int a = side / 2;
+    int c[3] = {0, 0, 0};
+    if (a == 0) { c[1] = f % p->nc[1]; c[2] = f / p->nc[1]; c[0] = (side & 1) ? p->nc[0] - 1 : 0; }
+    else if (a == 1) { c[0] = f % p->nc[0]; c[2] = f / p->nc[0]; c[1] = (side & 1) ? p->nc[1] - 1 : 0; }
+    else { c[0] = f % p->nc[0]; c[1] = f / p->nc[0]; c[2] = (side & 1) ? p->nc[2] - 1 : 0; }
+    for (int d = 0; d < 3; ++d) out[d] = (d < p->dim) ? p->center(d, c[d]) : 0.0;
+    out[a] = (side & 1) ? p->xn[a][c[a] + 1] : p->xn[a][c[a]];
+}
+void orc_cell_center(const orc_problem* p, int cell, double* out)
+{
+    int c[3];
+    p->ijk(cell, c);
+    for (int d = 0; d < 3; ++d) out[d] = (d < p->dim) ? p->center(d, c[d]) : 0.0;
+}
+
+int orc_pattern_nnz(const orc_problem* p) { return (int)p->colidx.size(); }
+void orc_pattern(const orc_problem* p, int* rowptr, int* colidx)
+{
+    std::memcpy(rowptr, p->rowptr.data(), sizeof(int) * (p->n + 1));
+    std::memcpy(colidx, p->colidx.data(), sizeof(int) * p->colidx.size());
+}
+
+// global assembly: dumux/assembly/fvassembler.hh:179-207 (reset J and r, loop all elements :462-510)
+void orc_assemble(orc_problem* p, const double* cur, const double* prev, double* residual, double* jac)
+{
+    const size_t nnz = p->colidx.size();
+    if (jac) std::memset(jac, 0, sizeof(double) * nnz * p->b * p->b);
+    if (residual) std::memset(residual, 0, sizeof(double) * (size_t)p->n * p->b);
+#ifdef _OPENMP
+    const int nt = p->opt.num_threads > 0 ? p->opt.num_threads : omp_get_max_threads();
+#pragma omp parallel for schedule(static) num_threads(nt)
+#endif
+    for (int I = 0; I < p->n; ++I) p->assembleElement(I, cur, prev, residual, jac);
+}
+
+void orc_volvars(orc_problem* p, const double* cur, double* out)
+{
+    for (int I = 0; I < p->n; ++I) {
+        VolVars v;
+        p->updateVolVars(v, cur + (size_t)I * p->b, I);
+        double* o = out + (size_t)I * 12;
+        o[0] = v.S[0]; o[1] = v.S[1]; o[2] = v.p[0]; o[3] = v.p[1]; o[4] = v.rho[0]; o[5] = v.rho[1];
+        o[6] = v.mob[0]; o[7] = v.mob[1]; o[8] = v.pc; o[9] = v.porosity; o[10] = v.K; o[11] = 0.0;
+    }
+}
+
+int orc_ilu0_factor(int n, int b, const int* rowptr, const int* colidx, const double* values, double* ilu)
+{
+    std::memcpy(ilu, values, sizeof(double) * (size_t)rowptr[n] * b * b);
+    return ilu0Factor(n, b, rowptr, colidx, ilu);
+}
+void orc_ilu0_apply(int n, int b, const int* rowptr, const int* colidx, const double* ilu, double* v, const double* d)
+{
+    ilu0Apply(n, b, rowptr, colidx, ilu, v, d);
+}
+void orc_spmv(int n, int b, const int* rowptr, const int* colidx, const double* values, const double* x, double* y)
+{
+    spmv(n, b, rowptr, colidx, values, x, y);
+}
+double orc_norm2(int n, const double* v) { return std::sqrt(dot((size_t)n, v, v)); }
+double orc_dot(int n, const double* a, const double* b) { return dot((size_t)n, a, b); }
+
+// dumux/nonlinear/newtonsolver.hh:111-129
+double orc_max_relative_shift(int n, const double* u1, const double* u2)
+{
+    double s = 0.0;
+    for (int i = 0; i < n; ++i) {
+        const double v = std::fabs(u1[i] - u2[i]) / std::max(1.0, std::fabs(u1[i] + u2[i]) * 0.5);
+        s = std::max(s, v);
+    }
+    return s;
+}
+
+// IstlIterativeLinearSolver::solve -> SeqILU(n=0,w=1) + BiCGSTABSolver, built fresh per call
+// (dumux/linear/istlsolvers.hh:457-464,535-568,636-642)
+int orc_ilu0_bicgstab(int n, int b, const int* rowptr, const int* colidx, const double* values,
+                      double* x, const double* rhs, double reduction, int maxit, int* iterations, double* achieved)
+{
+    const size_t N = (size_t)n * b;
+    std::vector<double> ilu((size_t)rowptr[n] * b * b);
+    std::memcpy(ilu.data(), values, sizeof(double) * ilu.size());
+    if (ilu0Factor(n, b, rowptr, colidx, ilu.data())) return 2;
+    return bicgstab(
+        N, [&](const double* in, double* out) { spmv(n, b, rowptr, colidx, values, in, out); },
+        [&](double* v, const double* d) { ilu0Apply(n, b, rowptr, colidx, ilu.data(), v, d); },
+        [&](const double* a, const double* c) { return dot(N, a, c); }, x, rhs, reduction, maxit, iterations, achieved);
+}
+
+// Newton loop at fixed dt: dumux/nonlinear/newtonsolver.hh:976-1072 (solveImpl_), newtonProceed :428-446,
+// newtonUpdate :543-557, shift :1138-1144, newtonConverged :657-666 (shift criterion only, defaults :1213-1247)
+int orc_newton_solve(orc_problem* p, double* u, const double* prev, double lin_reduction, int lin_maxit,
+                     double max_rel_shift, int min_steps, int max_steps, orc_newton_report* rep)
+{
+    const int n = p->n, b = p->b;
+    const size_t N = (size_t)n * b;
+    const size_t nnz = p->colidx.size();
+    std::vector<double> J(nnz * b * b), r(N), delta(N), uLast(u, u + N);
+    int numSteps = 0;
+    double shift = 0.0, lastShift = 0.0;
+    bool converged = false;
+    std::memset(rep, 0, sizeof(*rep));
+    auto proceed = [&]() {
+        if (numSteps < min_steps) return true;
+        else if (converged) return false;
+        else if (numSteps >= max_steps) return shift * 4.0 < lastShift;
+        return true;
+    };
+    while (proceed()) {
+        lastShift = shift;
+        if (numSteps > 0) uLast.assign(u, u + N);
+        double t0 = nowSec();
+        orc_assemble(p, u, prev, r.data(), J.data());
+        double t1 = nowSec();
+        for (size_t i = 0; i < N; ++i)
+            if (!(r[i] == r[i]) || std::isinf(r[i])) return 3;
+        std::fill(delta.begin(), delta.end(), 0.0);
+        int its = 0;
+        double red = 0;
+        const int st = orc_ilu0_bicgstab(n, b, p->rowptr.data(), p->colidx.data(), J.data(), delta.data(), r.data(),
+                                         lin_reduction, lin_maxit, &its, &red);
+        double t2 = nowSec();
+        if (numSteps < 64) rep->linear_iterations[numSteps] = its;
+        rep->linear_iterations_total += its;
+        if (st != 0) { rep->newton_iterations = numSteps; rep->converged = 0; return st; }
+        for (size_t i = 0; i < N; ++i) u[i] = uLast[i] + (-1.0) * delta[i];     // uCurrentIter = uLastIter; axpy(-1, deltaU)
+        shift = orc_max_relative_shift((int)N, u, uLast.data());
+        double t3 = nowSec();
+        rep->t_assemble += t1 - t0; rep->t_solve += t2 - t1; rep->t_update += t3 - t2;
+        if (numSteps < 64) rep->shifts[numSteps] = shift;
+        ++numSteps;
+        converged = shift <= max_rel_shift;
+    }
+    rep->newton_iterations = numSteps;
+    rep->converged = converged ? 1 : 0;
+    rep->last_shift = shift;
+    return converged ? 0 : 1;
+}
+
+// test/porousmediumflow/2p/incompressible/main.cc:126-163 with dumux/common/timeloop.hh:239-252,320-332,385-411
+// and NewtonSolver::solve(vars,timeLoop) retry logic newtonsolver.hh:309-355, suggestTimeStepSize :784-798
+int orc_run_timeloop(orc_problem* p, double* u, double t_end, double dt_initial, double max_dt,
+                     int* newton_its, double* dts, int max_steps_out)
+{
+    const size_t N = (size_t)p->n * p->b;
+    std::vector<double> uOld(u, u + N);
+    double time = 0.0, tStart = 0.0;
+    const double baseEps = 1e-10;
+    auto finished = [&]() { return (t_end - time) < baseEps * (time - tStart); };
+    auto maxTimeStepSize = [&]() { return finished() ? 0.0 : std::min(max_dt, std::max(0.0, t_end - time)); };
+    double dt = std::min(dt_initial, maxTimeStepSize());
+    int step = 0;
+    const int targetSteps = 10;
+    do {
+        int numSteps = 0;
+        bool ok = false;
+        for (int i = 0; i <= 10; ++i) {
+            p->opt.dt = dt;
+            orc_newton_report rep;
+            const int st = orc_newton_solve(p, u, uOld.data(), 1e-6, 250, 1e-8, 2, 18, &rep);
+            numSteps = rep.newton_iterations;
+            if (st == 0) { ok = true; break; }
+            if (i < 10) {
+                std::copy(uOld.begin(), uOld.end(), u);
+                dt = std::min(dt * 0.5, maxTimeStepSize());
+            }
+        }
+        if (!ok) return -1;
+        uOld.assign(u, u + N);
+        if (step < max_steps_out) { if (newton_its) newton_its[step] = numSteps; if (dts) dts[step] = dt; }
+        ++step;
+        time += dt;
+        dt = std::min(dt, maxTimeStepSize());
+        double suggested;
+        if (numSteps > targetSteps) {
+            const double percent = double(numSteps - targetSteps) / targetSteps;
+            suggested = dt / (1.0 + percent);
+        } else {
+            const double percent = double(targetSteps - numSteps) / targetSteps;
+            suggested = dt * (1.0 + percent / 1.2);
+        }
+        dt = std::min(suggested, maxTimeStepSize());
+    } while (!finished());
+    return step;
+}
+
+double orc_law_eval(orc_problem* p, int region, int which, double sw)
+{
+    const Law& l = p->laws[region];
+    switch (which) {
+        case 0: return l.pc(sw);
+        case 1: return l.krw(sw);
+        case 2: return l.krn(sw);
+        case 3: return l.dpc_dsw(sw);
+        case 4: return l.dkrw_dsw(sw);
+        case 5: return l.dkrn_dsw(sw);
+    }
+    return 0.0;
+}
+double orc_pow(double x, double y) { return orc_det_pow(x, y); }
+
+void orc_set_fluid_table(orc_problem* p, int nT, int nP, double Tmin, double Tmax, const double* pmin, const double* pmax,
+                         const double* rho, const double* mu, double temperature)
+{
+    Fluids& f = p->fluids;
+    f.tabulated = true;
+    f.nT = nT; f.nP = nP; f.Tmin = Tmin; f.Tmax = Tmax; f.T = temperature;
+    f.pmin.assign(pmin, pmin + nT);
+    f.pmax.assign(pmax, pmax + nT);
+    f.rhoTab.assign(rho, rho + (size_t)nT * nP);
+    f.muTab.assign(mu, mu + (size_t)nT * nP);
+}
+
+} // extern "C"
