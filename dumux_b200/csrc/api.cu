@@ -1,0 +1,674 @@
+// api.cu -- the C ABI (include/dumux_b200.h): context, grid/pattern set-up, data movement, Newton driver.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+
+#include "common.cuh"
+
+using namespace dmx;
+
+namespace {
+
+int alloc_vectors(dmx_ctx* ctx)
+{
+    const size_t len = (size_t)ctx->n * ctx->b;
+    for (int v = 0; v < DMX_NUM_VECS; ++v) {
+        if (ctx->d_vec[v]) cudaFree(ctx->d_vec[v]);
+        DMX_CUDA(cudaMalloc((void**)&ctx->d_vec[v], len * sizeof(double)));
+        DMX_CUDA(cudaMemset(ctx->d_vec[v], 0, len * sizeof(double)));
+    }
+    double** w[] = {&ctx->d_rt, &ctx->d_p, &ctx->d_v, &ctx->d_t, &ctx->d_y};
+    for (double** p : w) {
+        if (*p) cudaFree(*p);
+        DMX_CUDA(cudaMalloc((void**)p, len * sizeof(double)));
+        DMX_CUDA(cudaMemset(*p, 0, len * sizeof(double)));
+    }
+    if (ctx->d_J) cudaFree(ctx->d_J);
+    if (ctx->d_ilu) { cudaFree(ctx->d_ilu); ctx->d_ilu = nullptr; }
+    if (ctx->d_dinv) { cudaFree(ctx->d_dinv); ctx->d_dinv = nullptr; }
+    DMX_CUDA(cudaMalloc((void**)&ctx->d_J, (size_t)ctx->nnzb * ctx->b * ctx->b * sizeof(double)));
+    DMX_CUDA(cudaMemset(ctx->d_J, 0, (size_t)ctx->nnzb * ctx->b * ctx->b * sizeof(double)));
+    return 0;
+}
+
+int upload_pattern(dmx_ctx* ctx)
+{
+    if (ctx->d_rowptr) cudaFree(ctx->d_rowptr);
+    if (ctx->d_colidx) cudaFree(ctx->d_colidx);
+    DMX_CUDA(cudaMalloc((void**)&ctx->d_rowptr, ctx->h_rowptr.size() * sizeof(int)));
+    DMX_CUDA(cudaMalloc((void**)&ctx->d_colidx, ctx->h_colidx.size() * sizeof(int)));
+    DMX_CUDA(cudaMemcpy(ctx->d_rowptr, ctx->h_rowptr.data(), ctx->h_rowptr.size() * sizeof(int), cudaMemcpyHostToDevice));
+    DMX_CUDA(cudaMemcpy(ctx->d_colidx, ctx->h_colidx.data(), ctx->h_colidx.size() * sizeof(int), cudaMemcpyHostToDevice));
+    return build_level_schedule(ctx);
+}
+
+// Jacobian pattern of the CCTpfa scheme on the local box: (I,I) and (I,J) for all face neighbours, columns ascending
+// (assembly/jacobianpattern.hh:27-52, discretization/cellcentered/connectivitymap.hh:66-115)
+void build_grid_pattern(dmx_ctx* ctx)
+{
+    const int nx = ctx->nc[0], ny = ctx->nc[1], nz = ctx->nc[2];
+    const int n = ctx->n;
+    ctx->h_rowptr.assign(n + 1, 0);
+    ctx->h_colidx.clear();
+    ctx->h_colidx.reserve((size_t)n * 7);
+    const int dim = ctx->dim;
+    for (int k = 0; k < nz; ++k)
+        for (int j = 0; j < ny; ++j)
+            for (int i = 0; i < nx; ++i) {
+                const int I = i + nx * (j + ny * k);
+                if (dim > 2 && k > 0) ctx->h_colidx.push_back(I - nx * ny);
+                if (dim > 1 && j > 0) ctx->h_colidx.push_back(I - nx);
+                if (i > 0) ctx->h_colidx.push_back(I - 1);
+                ctx->h_colidx.push_back(I);
+                if (i + 1 < nx) ctx->h_colidx.push_back(I + 1);
+                if (dim > 1 && j + 1 < ny) ctx->h_colidx.push_back(I + nx);
+                if (dim > 2 && k + 1 < nz) ctx->h_colidx.push_back(I + nx * ny);
+                ctx->h_rowptr[I + 1] = (int)ctx->h_colidx.size();
+            }
+    ctx->nnzb = (long long)ctx->h_colidx.size();
+}
+
+int setup_geometry(dmx_ctx* ctx)
+{
+    // per-axis arrays: width, |(x_f - x_c)/|x_f - x_c|^2| for the low and the high face of each cell
+    // (YaspGrid: x_i = origin + i*h; AxisAlignedCubeGeometry::center = 0.5*(lower+upper);
+    //  computeTpfaTransmissibility: d = x_f - x_c; d /= |d|^2; t*extrusion*(d.n)) [dune-grid semantics]
+    size_t total = 0;
+    for (int a = 0; a < 3; ++a) total += 3 * (size_t)ctx->nc[a];
+    std::vector<double> h(total);
+    size_t o = 0;
+    size_t offs[3][3];
+    for (int a = 0; a < 3; ++a) {
+        const int m = ctx->nc[a];
+        offs[a][0] = o; offs[a][1] = o + m; offs[a][2] = o + 2 * (size_t)m;
+        for (int i = 0; i < m; ++i) {
+            const double x0 = ctx->xn[a][i], x1 = ctx->xn[a][i + 1];
+            const double c = 0.5 * (x0 + x1);
+            h[o + i] = x1 - x0;
+            double dlo = 0.5 * (x0 + x0) - c;
+            dlo /= dlo * dlo;
+            double dhi = 0.5 * (x1 + x1) - c;
+            dhi /= dhi * dhi;
+            h[o + m + i] = dlo * -1.0;
+            h[o + 2 * (size_t)m + i] = dhi * 1.0;
+        }
+        o += 3 * (size_t)m;
+    }
+    if (ctx->d_geom) cudaFree(ctx->d_geom);
+    DMX_CUDA(cudaMalloc((void**)&ctx->d_geom, total * sizeof(double)));
+    DMX_CUDA(cudaMemcpy(ctx->d_geom, h.data(), total * sizeof(double), cudaMemcpyHostToDevice));
+    for (int a = 0; a < 3; ++a) {
+        ctx->d_width[a] = ctx->d_geom + offs[a][0];
+        ctx->d_gflo[a] = ctx->d_geom + offs[a][1];
+        ctx->d_gfhi[a] = ctx->d_geom + offs[a][2];
+    }
+    return 0;
+}
+
+int finish_grid(dmx_ctx* ctx, int model, int dim, const int* cells, const std::vector<double> (&gx)[3])
+{
+    if (model != DMX_MODEL_1P && model != DMX_MODEL_2P) return fail(ctx, DMX_ERR_USAGE, "unknown model");
+    if (dim < 1 || dim > 3) return fail(ctx, DMX_ERR_USAGE, "dim must be 1..3");
+    DMX_CUDA(cudaSetDevice(ctx->device));
+    ctx->model = model;
+    ctx->b = (model == DMX_MODEL_2P) ? 2 : 1;
+    ctx->dim = dim;
+    for (int a = 0; a < 3; ++a) { ctx->gcells[a] = (a < dim) ? cells[a] : 1; ctx->nc[a] = ctx->gcells[a]; ctx->off[a] = 0; }
+    ctx->split_axis = dim - 1;
+    // slab decomposition along the last axis, overlap 1 (Grid.Partitioning "1 .. P", Grid.Overlap 1)
+    const int sa = ctx->split_axis;
+    int lo = 0, hi = ctx->gcells[sa];
+    if (ctx->nranks > 1) {
+        const int N = ctx->gcells[sa], P = ctx->nranks, r = ctx->rank;
+        if (N < P) return fail(ctx, DMX_ERR_USAGE, "fewer cell layers than ranks along the split axis");
+        const int base = N / P, rem = N % P;
+        const int b0 = r * base + std::min(r, rem);
+        const int b1 = b0 + base + (r < rem ? 1 : 0);
+        lo = std::max(0, b0 - 1);
+        hi = std::min(N, b1 + 1);
+        ctx->own_begin = b0 - lo;
+        ctx->own_end = b1 - lo;
+    } else { ctx->own_begin = 0; ctx->own_end = hi; }
+    ctx->off[sa] = lo;
+    ctx->nc[sa] = hi - lo;
+    for (int a = 0; a < 3; ++a) {
+        ctx->xn[a].assign(gx[a].begin() + ctx->off[a], gx[a].begin() + ctx->off[a] + ctx->nc[a] + 1);
+    }
+    ctx->n = ctx->nc[0] * ctx->nc[1] * ctx->nc[2];
+    ctx->has_grid = true;
+    ctx->prepared = false;
+    ctx->h_K.assign(ctx->n, 1e-10);
+    ctx->h_phi.assign(ctx->n, 0.4);
+    ctx->h_region.assign(ctx->n, 0);
+    for (int s = 0; s < 6; ++s) { ctx->h_bc_type[s].clear(); ctx->h_bc_val[s].clear(); }
+    // processor boundaries: outer faces of overlap layers carry no scvf
+    if (ctx->nranks > 1) {
+        int nf = 1;
+        for (int d = 0; d < 3; ++d) if (d != sa) nf *= ctx->nc[d];
+        if (lo > 0) { ctx->h_bc_type[2 * sa].assign(nf, DMX_BC_NONE); ctx->h_bc_val[2 * sa].assign((size_t)nf * ctx->b, 0.0); }
+        if (hi < ctx->gcells[sa]) { ctx->h_bc_type[2 * sa + 1].assign(nf, DMX_BC_NONE); ctx->h_bc_val[2 * sa + 1].assign((size_t)nf * ctx->b, 0.0); }
+    }
+    build_grid_pattern(ctx);
+    if (int rc = setup_geometry(ctx)) return rc;
+    auto up = [&](auto** d, const auto& h) -> int {
+        if (*d) cudaFree(*d);
+        DMX_CUDA(cudaMalloc((void**)d, h.size() * sizeof(h[0])));
+        DMX_CUDA(cudaMemcpy(*d, h.data(), h.size() * sizeof(h[0]), cudaMemcpyHostToDevice));
+        return 0;
+    };
+    if (int rc = up(&ctx->d_K, ctx->h_K)) return rc;
+    if (int rc = up(&ctx->d_phi, ctx->h_phi)) return rc;
+    if (int rc = up(&ctx->d_region, ctx->h_region)) return rc;
+    if (ctx->d_q) { cudaFree(ctx->d_q); ctx->d_q = nullptr; }
+    for (int a = 0; a < 3; ++a) if (ctx->d_tij[a]) { cudaFree(ctx->d_tij[a]); ctx->d_tij[a] = nullptr; }
+    if (int rc = upload_pattern(ctx)) return rc;
+    if (int rc = alloc_vectors(ctx)) return rc;
+    // owner mask (distributed): a cell is owner where it is interior (parallelhelpers.hh:485-497)
+    if (ctx->d_owner) { cudaFree(ctx->d_owner); ctx->d_owner = nullptr; }
+    if (ctx->nranks > 1) {
+        std::vector<unsigned char> own(ctx->n, 0);
+        const int stride = (sa == 0) ? 1 : (sa == 1 ? ctx->nc[0] : ctx->nc[0] * ctx->nc[1]);
+        for (int I = 0; I < ctx->n; ++I) {
+            const int c = (I / stride) % ctx->nc[sa];
+            own[I] = (c >= ctx->own_begin && c < ctx->own_end) ? 1 : 0;
+        }
+        if (int rc = up(&ctx->d_owner, own)) return rc;
+        const size_t plane = (size_t)(ctx->n / ctx->nc[sa]) * ctx->b;
+        double** bufs[] = {&ctx->d_send_lo, &ctx->d_send_hi, &ctx->d_recv_lo, &ctx->d_recv_hi};
+        for (double** p : bufs) {
+            if (*p) cudaFree(*p);
+            DMX_CUDA(cudaMalloc((void**)p, plane * sizeof(double)));
+        }
+    }
+    return 0;
+}
+
+double now_ms()
+{
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+} // namespace
+
+extern "C" {
+
+const char* dmx_version(void) { return "dumux_b200 0.1 (sm_100a)"; }
+
+void dmx_default_options(dmx_options* o)
+{
+    o->enable_gravity = 1; o->gravity = 9.81; o->upwind_weight = 1.0; o->fd_method = 1; o->base_eps = 1e-10;
+    o->privar_magnitude[0] = o->privar_magnitude[1] = -1.0; o->stationary = 0; o->dt = 1.0; o->extrusion = 1.0;
+}
+void dmx_default_newton_params(dmx_newton_params* p)
+{
+    p->max_relative_shift = 1e-8; p->min_steps = 2; p->max_steps = 18; p->lin_reduction = 1e-6; p->lin_maxit = 250;
+    p->preconditioner = DMX_PRECOND_ILU0;
+}
+
+int dmx_create_distributed(dmx_ctx** out, int device, const void* uid, int rank, int nranks)
+{
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) return DMX_ERR_CUDA;   // no CPU fallback
+    if (device < 0 || device >= count) return DMX_ERR_USAGE;
+    dmx_ctx* ctx = new dmx_ctx;
+    ctx->device = device;
+    ctx->rank = rank;
+    ctx->nranks = nranks;
+    dmx_default_options(&ctx->opt);
+    if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return DMX_ERR_CUDA; }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    ctx->num_sms = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return DMX_ERR_CUDA; }
+    cudaMalloc((void**)&ctx->d_partials, 3 * 1184 * sizeof(double));
+    cudaMalloc((void**)&ctx->d_scalars, 8 * sizeof(double));
+    cudaMallocHost((void**)&ctx->h_scalars, 8 * sizeof(double));
+    cudaMalloc((void**)&ctx->d_flag, sizeof(int));
+    cudaMallocHost((void**)&ctx->h_flag, sizeof(int));
+    cudaMalloc((void**)&ctx->d_barrier, sizeof(unsigned int));
+    for (auto& e : ctx->ev) cudaEventCreate(&e);
+    if (cudaGetLastError() != cudaSuccess) { delete ctx; return DMX_ERR_CUDA; }
+    if (nranks > 1) {
+        if (int rc = nccl_init(ctx, uid)) { delete ctx; return rc; }
+    }
+    *out = ctx;
+    return 0;
+}
+int dmx_create(dmx_ctx** out, int device) { return dmx_create_distributed(out, device, nullptr, 0, 1); }
+int dmx_get_nccl_unique_id(void* out128) { return nccl_get_unique_id(out128); }
+
+int dmx_destroy(dmx_ctx* ctx)
+{
+    if (!ctx) return 0;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->nccl_comm) nccl_destroy(ctx);
+    void* ptrs[] = {ctx->d_geom, ctx->d_K, ctx->d_phi, ctx->d_q, ctx->d_region, ctx->d_tij[0], ctx->d_tij[1], ctx->d_tij[2], ctx->d_laws,
+                    ctx->d_tab_buf, ctx->d_rowptr, ctx->d_colidx, ctx->d_diag, ctx->d_J, ctx->d_ilu, ctx->d_rt, ctx->d_p, ctx->d_v, ctx->d_t,
+                    ctx->d_y, ctx->d_dinv, ctx->d_rec, ctx->d_lrows, ctx->d_urows, ctx->d_lptr, ctx->d_uptr, ctx->d_barrier, ctx->d_partials,
+                    ctx->d_scalars, ctx->d_flag, ctx->d_owner, ctx->d_send_lo, ctx->d_send_hi, ctx->d_recv_lo, ctx->d_recv_hi};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    for (int v = 0; v < DMX_NUM_VECS; ++v) if (ctx->d_vec[v]) cudaFree(ctx->d_vec[v]);
+    for (int s = 0; s < 6; ++s) {
+        void* b[] = {ctx->d_bc_type[s], ctx->d_bc_neumann[s], ctx->d_bc_p[s], ctx->d_bc_up[s], ctx->d_bc_rho[s]};
+        for (void* p : b) if (p) cudaFree(p);
+    }
+    if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
+    if (ctx->h_flag) cudaFreeHost(ctx->h_flag);
+    for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return 0;
+}
+const char* dmx_last_error(const dmx_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int dmx_grid_structured(dmx_ctx* ctx, int model, int dim, const int* cells, const double* lower, const double* upper)
+{
+    std::vector<double> gx[3];
+    for (int a = 0; a < 3; ++a) {
+        const int m = (a < dim) ? cells[a] : 1;
+        gx[a].resize(m + 1);
+        if (a < dim) {
+            const double h = (upper[a] - lower[a]) / cells[a];
+            for (int i = 0; i <= m; ++i) gx[a][i] = lower[a] + i * h;
+        } else { gx[a][0] = 0.0; gx[a][1] = 1.0; }
+    }
+    return finish_grid(ctx, model, dim, cells, gx);
+}
+int dmx_grid_tensor(dmx_ctx* ctx, int model, int dim, const int* cells, const double* x, const double* y, const double* z)
+{
+    const double* src[3] = {x, y, z};
+    std::vector<double> gx[3];
+    for (int a = 0; a < 3; ++a) {
+        const int m = (a < dim) ? cells[a] : 1;
+        gx[a].resize(m + 1);
+        if (a < dim) for (int i = 0; i <= m; ++i) gx[a][i] = src[a][i];
+        else { gx[a][0] = 0.0; gx[a][1] = 1.0; }
+    }
+    return finish_grid(ctx, model, dim, cells, gx);
+}
+int dmx_local_box(const dmx_ctx* ctx, int* cells, int* offset, int* owned_begin, int* owned_end)
+{
+    for (int a = 0; a < 3; ++a) { cells[a] = ctx->nc[a]; offset[a] = ctx->off[a]; }
+    *owned_begin = ctx->own_begin;
+    *owned_end = ctx->own_end;
+    return 0;
+}
+int dmx_num_cells(const dmx_ctx* ctx) { return ctx->n; }
+int dmx_num_eq(const dmx_ctx* ctx) { return ctx->b; }
+long long dmx_nnz_blocks(const dmx_ctx* ctx) { return ctx->nnzb; }
+int dmx_pattern(const dmx_ctx* ctx, int* rowptr, int* colidx)
+{
+    std::memcpy(rowptr, ctx->h_rowptr.data(), ctx->h_rowptr.size() * sizeof(int));
+    std::memcpy(colidx, ctx->h_colidx.data(), ctx->h_colidx.size() * sizeof(int));
+    return 0;
+}
+int dmx_bcrs_pattern(dmx_ctx* ctx, int n, int b, const int* rowptr, const int* colidx)
+{
+    if (b != 1 && b != 2) return fail(ctx, DMX_ERR_USAGE, "block size must be 1 or 2");
+    DMX_CUDA(cudaSetDevice(ctx->device));
+    ctx->has_grid = false;
+    ctx->model = 0;
+    ctx->n = n;
+    ctx->b = b;
+    ctx->h_rowptr.assign(rowptr, rowptr + n + 1);
+    ctx->h_colidx.assign(colidx, colidx + rowptr[n]);
+    ctx->nnzb = rowptr[n];
+    for (int i = 0; i < n; ++i)
+        for (int k = rowptr[i] + 1; k < rowptr[i + 1]; ++k)
+            if (colidx[k] <= colidx[k - 1]) return fail(ctx, DMX_ERR_USAGE, "column indices must be strictly ascending per row");
+    if (int rc = upload_pattern(ctx)) return rc;
+    return alloc_vectors(ctx);
+}
+
+int dmx_set_options(dmx_ctx* ctx, const dmx_options* o)
+{
+    const bool structural = (o->fd_method != ctx->opt.fd_method) || (o->extrusion != ctx->opt.extrusion);
+    ctx->opt = *o;
+    if (o->fd_method != 1 && o->fd_method != 0 && o->fd_method != -1 && o->fd_method != 5)
+        return fail(ctx, DMX_ERR_USAGE, "Assembly.NumericDifferenceMethod must be 1, 0, -1 or 5");
+    if (structural) ctx->prepared = false;
+    return 0;
+}
+int dmx_set_cell_fields(dmx_ctx* ctx, const double* K, const double* phi, const int* region)
+{
+    if (!ctx->has_grid) return fail(ctx, DMX_ERR_USAGE, "set grid first");
+    DMX_CUDA(cudaSetDevice(ctx->device));
+    const int n = ctx->n;
+    if (K) { ctx->h_K.assign(K, K + n); DMX_CUDA(cudaMemcpy(ctx->d_K, K, n * sizeof(double), cudaMemcpyHostToDevice)); }
+    if (phi) { ctx->h_phi.assign(phi, phi + n); DMX_CUDA(cudaMemcpy(ctx->d_phi, phi, n * sizeof(double), cudaMemcpyHostToDevice)); }
+    if (region) {
+        for (int i = 0; i < n; ++i)
+            if (region[i] < 0 || region[i] >= DMX_MAX_REGIONS) return fail(ctx, DMX_ERR_USAGE, "region id out of range");
+        ctx->h_region.assign(region, region + n);
+        DMX_CUDA(cudaMemcpy(ctx->d_region, region, n * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    ctx->prepared = false;
+    return 0;
+}
+int dmx_set_source(dmx_ctx* ctx, const double* q)
+{
+    if (!ctx->has_grid) return fail(ctx, DMX_ERR_USAGE, "set grid first");
+    DMX_CUDA(cudaSetDevice(ctx->device));
+    const size_t len = (size_t)ctx->n * ctx->b;
+    if (!ctx->d_q) DMX_CUDA(cudaMalloc((void**)&ctx->d_q, len * sizeof(double)));
+    DMX_CUDA(cudaMemcpy(ctx->d_q, q, len * sizeof(double), cudaMemcpyHostToDevice));
+    return 0;
+}
+int dmx_set_material(dmx_ctx* ctx, int region, int law, const double* params, double swr, double snr, int regularize, const double* reg)
+{
+    if (region < 0 || region >= DMX_MAX_REGIONS) return fail(ctx, DMX_ERR_USAGE, "region id out of range");
+    if ((int)ctx->laws.size() <= region) ctx->laws.resize(region + 1, MaterialLaw{});
+    MaterialLaw& l = ctx->laws[region];
+    std::memset(&l, 0, sizeof(l));
+    l.kind = law; l.regularized = regularize ? 1 : 0; l.swr = swr; l.snr = snr;
+    l.pcLowSwe = 0.01; l.pcHighSwe = 0.99; l.krnLowSwe = 0.1; l.krwHighSwe = 0.9;
+    if (law == DMX_LAW_BROOKSCOREY) {
+        l.pcEntry = params[0]; l.lambda = params[1];
+        if (reg) l.pcLowSwe = reg[0];
+    } else if (law == DMX_LAW_VANGENUCHTEN) {
+        l.alpha = params[0]; l.n = params[1]; l.m = 1.0 - 1.0 / l.n; l.l = params[2];
+        if (reg) { l.pcLowSwe = reg[0]; l.pcHighSwe = reg[1]; l.krnLowSwe = reg[2]; l.krwHighSwe = reg[3]; }
+    } else return fail(ctx, DMX_ERR_USAGE, "unknown material law");
+    ctx->prepared = false;
+    return 0;
+}
+int dmx_set_fluids(dmx_ctx* ctx, const double* density, const double* viscosity)
+{
+    const int nph = (ctx->model == DMX_MODEL_2P) ? 2 : 1;
+    for (int i = 0; i < nph; ++i) { ctx->rho[i] = density[i]; ctx->mu[i] = viscosity[i]; }
+    ctx->tabulated = false;
+    ctx->prepared = false;
+    return 0;
+}
+int dmx_set_fluid_table(dmx_ctx* ctx, int nT, int nP, double Tmin, double Tmax, const double* pmin, const double* pmax,
+                        const double* density, const double* viscosity, double temperature)
+{
+    if (ctx->model != DMX_MODEL_1P) return fail(ctx, DMX_ERR_USAGE, "tabulated fluid is supported for the 1p model");
+    DMX_CUDA(cudaSetDevice(ctx->device));
+    ctx->h_tab_pmin.assign(pmin, pmin + nT);
+    ctx->h_tab_pmax.assign(pmax, pmax + nT);
+    ctx->h_tab_rho.assign(density, density + (size_t)nT * nP);
+    ctx->h_tab_mu.assign(viscosity, viscosity + (size_t)nT * nP);
+    ctx->h_table = FluidTable{nT, nP, Tmin, Tmax, temperature, ctx->h_tab_pmin.data(), ctx->h_tab_pmax.data(), ctx->h_tab_rho.data(),
+                              ctx->h_tab_mu.data()};
+    const size_t total = 2 * (size_t)nT + 2 * (size_t)nT * nP;
+    if (ctx->d_tab_buf) cudaFree(ctx->d_tab_buf);
+    DMX_CUDA(cudaMalloc((void**)&ctx->d_tab_buf, total * sizeof(double)));
+    double* d = ctx->d_tab_buf;
+    DMX_CUDA(cudaMemcpy(d, pmin, nT * sizeof(double), cudaMemcpyHostToDevice));
+    DMX_CUDA(cudaMemcpy(d + nT, pmax, nT * sizeof(double), cudaMemcpyHostToDevice));
+    DMX_CUDA(cudaMemcpy(d + 2 * nT, density, (size_t)nT * nP * sizeof(double), cudaMemcpyHostToDevice));
+    DMX_CUDA(cudaMemcpy(d + 2 * nT + (size_t)nT * nP, viscosity, (size_t)nT * nP * sizeof(double), cudaMemcpyHostToDevice));
+    ctx->d_table = FluidTable{nT, nP, Tmin, Tmax, temperature, d, d + nT, d + 2 * nT, d + 2 * nT + (size_t)nT * nP};
+    ctx->tabulated = true;
+    ctx->prepared = false;
+    return 0;
+}
+int dmx_side_faces(const dmx_ctx* ctx, int side)
+{
+    const int a = side / 2;
+    int nf = 1;
+    for (int d = 0; d < 3; ++d) if (d != a) nf *= ctx->nc[d];
+    return nf;
+}
+int dmx_set_boundary(dmx_ctx* ctx, int side, const int* type, const double* values)
+{
+    if (!ctx->has_grid) return fail(ctx, DMX_ERR_USAGE, "set grid first");
+    if (side < 0 || side >= 2 * ctx->dim) return fail(ctx, DMX_ERR_USAGE, "side out of range");
+    // a processor boundary keeps its DMX_BC_NONE marking
+    const int sa = ctx->split_axis;
+    if (ctx->nranks > 1 && ((side == 2 * sa && ctx->off[sa] > 0) || (side == 2 * sa + 1 && ctx->off[sa] + ctx->nc[sa] < ctx->gcells[sa])))
+        return 0;
+    const int nf = dmx_side_faces(ctx, side);
+    ctx->h_bc_type[side].assign(type, type + nf);
+    ctx->h_bc_val[side].assign(values, values + (size_t)nf * ctx->b);
+    ctx->prepared = false;
+    return 0;
+}
+
+// ---- vectors ----
+static int vec_ok(dmx_ctx* ctx, int v)
+{
+    if (v < 0 || v >= DMX_NUM_VECS || !ctx->d_vec[v]) return fail(ctx, DMX_ERR_USAGE, "bad vector id or no pattern set");
+    return 0;
+}
+int dmx_vec_upload(dmx_ctx* ctx, int vec, const double* host)
+{
+    if (int rc = vec_ok(ctx, vec)) return rc;
+    DMX_CUDA(cudaMemcpyAsync(ctx->d_vec[vec], host, (size_t)ctx->n * ctx->b * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    DMX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+int dmx_vec_download(dmx_ctx* ctx, int vec, double* host)
+{
+    if (int rc = vec_ok(ctx, vec)) return rc;
+    DMX_CUDA(cudaMemcpyAsync(host, ctx->d_vec[vec], (size_t)ctx->n * ctx->b * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    DMX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+int dmx_vec_copy(dmx_ctx* ctx, int dst, int src)
+{
+    if (int rc = vec_ok(ctx, dst)) return rc;
+    if (int rc = vec_ok(ctx, src)) return rc;
+    DMX_CUDA(cudaMemcpyAsync(ctx->d_vec[dst], ctx->d_vec[src], (size_t)ctx->n * ctx->b * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    return 0;
+}
+int dmx_jacobian_upload(dmx_ctx* ctx, const double* values)
+{
+    if (!ctx->d_J) return fail(ctx, DMX_ERR_USAGE, "no pattern set");
+    DMX_CUDA(cudaMemcpyAsync(ctx->d_J, values, (size_t)ctx->nnzb * ctx->b * ctx->b * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    DMX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+int dmx_jacobian_download(dmx_ctx* ctx, double* values)
+{
+    if (!ctx->d_J) return fail(ctx, DMX_ERR_USAGE, "no pattern set");
+    DMX_CUDA(cudaMemcpyAsync(values, ctx->d_J, (size_t)ctx->nnzb * ctx->b * ctx->b * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    DMX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+void* dmx_vec_device_ptr(dmx_ctx* ctx, int vec) { return (vec >= 0 && vec < DMX_NUM_VECS) ? ctx->d_vec[vec] : nullptr; }
+void* dmx_jacobian_device_ptr(dmx_ctx* ctx) { return ctx->d_J; }
+int dmx_synchronize(dmx_ctx* ctx)
+{
+    DMX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+int dmx_kernel_launch_count(const dmx_ctx* ctx, long long* launches)
+{
+    *launches = ctx->launches;
+    return 0;
+}
+
+// ---- hot path ----
+int dmx_assemble(dmx_ctx* ctx, int with_jacobian)
+{
+    if (!ctx->has_grid) return fail(ctx, DMX_ERR_USAGE, "assemble: no grid");
+    DMX_CUDA(cudaSetDevice(ctx->device));
+    DMX_CUDA(cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream));
+    if (int rc = launch_assemble(ctx, with_jacobian != 0)) return rc;
+    DMX_CUDA(cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    DMX_CUDA(cudaStreamSynchronize(ctx->stream));
+    int bad = *ctx->h_flag;
+    if (bad) { ctx->err = "assemble: non-finite residual"; return DMX_STATUS_NONFINITE; }
+    return 0;
+}
+int dmx_assemble_host(dmx_ctx* ctx, const double* cur, const double* prev, double* residual, double* jacobian)
+{
+    int rc;
+    if ((rc = dmx_vec_upload(ctx, DMX_VEC_CUR, cur))) return rc;
+    if (prev && (rc = dmx_vec_upload(ctx, DMX_VEC_PREV, prev))) return rc;
+    if ((rc = dmx_assemble(ctx, jacobian != nullptr))) return rc;
+    if (residual && (rc = dmx_vec_download(ctx, DMX_VEC_RESIDUAL, residual))) return rc;
+    if (jacobian && (rc = dmx_jacobian_download(ctx, jacobian))) return rc;
+    return 0;
+}
+int dmx_linear_solve(dmx_ctx* ctx, double reduction, int maxit, int preconditioner, int* iterations, double* achieved)
+{
+    if (!ctx->d_J) return fail(ctx, DMX_ERR_USAGE, "linear_solve: no pattern");
+    DMX_CUDA(cudaSetDevice(ctx->device));
+    return bicgstab(ctx, reduction, maxit, preconditioner, iterations, achieved);
+}
+int dmx_linear_solve_host(dmx_ctx* ctx, const double* values, double* x, const double* b, double reduction, int maxit, int preconditioner,
+                          int* iterations, double* achieved)
+{
+    int rc;
+    if ((rc = dmx_jacobian_upload(ctx, values))) return rc;
+    if ((rc = dmx_vec_upload(ctx, DMX_VEC_DELTA, x))) return rc;
+    if ((rc = dmx_vec_upload(ctx, DMX_VEC_RESIDUAL, b))) return rc;
+    const int st = dmx_linear_solve(ctx, reduction, maxit, preconditioner, iterations, achieved);
+    if (st < 0) return st;
+    if ((rc = dmx_vec_download(ctx, DMX_VEC_DELTA, x))) return rc;
+    return st;
+}
+int dmx_norm2(dmx_ctx* ctx, int vec, double* out)
+{
+    if (int rc = vec_ok(ctx, vec)) return rc;
+    double s;
+    if (int rc = dot(ctx, ctx->d_vec[vec], ctx->d_vec[vec], &s)) return rc;
+    *out = std::sqrt(s);
+    return 0;
+}
+int dmx_dot(dmx_ctx* ctx, int a, int b, double* out)
+{
+    if (int rc = vec_ok(ctx, a)) return rc;
+    if (int rc = vec_ok(ctx, b)) return rc;
+    return dot(ctx, ctx->d_vec[a], ctx->d_vec[b], out);
+}
+int dmx_newton_update(dmx_ctx* ctx, double* shift) { return newton_update(ctx, shift); }
+int dmx_advance_timestep(dmx_ctx* ctx) { return dmx_vec_copy(ctx, DMX_VEC_PREV, DMX_VEC_CUR); }
+int dmx_reset_timestep(dmx_ctx* ctx) { return dmx_vec_copy(ctx, DMX_VEC_CUR, DMX_VEC_PREV); }
+
+int dmx_newton_step(dmx_ctx* ctx, const dmx_newton_params* prm, int* linear_iterations, double* shift, float* ms_assemble,
+                    float* ms_solve, float* ms_update)
+{
+    int rc;
+    DMX_CUDA(cudaSetDevice(ctx->device));
+    // uLastIter = current iterate (newtonsolver.hh:985,1000)
+    if ((rc = dmx_vec_copy(ctx, DMX_VEC_ULAST, DMX_VEC_CUR))) return rc;
+    DMX_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+    if ((rc = dmx_assemble(ctx, 1))) return rc;
+    DMX_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+    DMX_CUDA(cudaMemsetAsync(ctx->d_vec[DMX_VEC_DELTA], 0, (size_t)ctx->n * ctx->b * sizeof(double), ctx->stream));   // deltaU = 0 (:1032)
+    double red = 0;
+    rc = bicgstab(ctx, prm->lin_reduction, prm->lin_maxit, prm->preconditioner, linear_iterations, &red);
+    if (rc) return rc;
+    DMX_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
+    if ((rc = newton_update(ctx, shift))) return rc;
+    DMX_CUDA(cudaEventRecord(ctx->ev[3], ctx->stream));
+    DMX_CUDA(cudaEventSynchronize(ctx->ev[3]));
+    float a = 0, s = 0, u = 0;
+    cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&s, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&u, ctx->ev[2], ctx->ev[3]);
+    if (ms_assemble) *ms_assemble = a;
+    if (ms_solve) *ms_solve = s;
+    if (ms_update) *ms_update = u;
+    return 0;
+}
+
+// NewtonSolver::solveImpl_ (newtonsolver.hh:976-1072) with newtonProceed (:428-446), newtonConverged (:657-666, shift
+// criterion), on the device-resident CUR/PREV.  Returns 0 if converged, DMX_STATUS_* otherwise.
+int dmx_newton_solve(dmx_ctx* ctx, const dmx_newton_params* prm, dmx_newton_report* rep)
+{
+    std::memset(rep, 0, sizeof(*rep));
+    int numSteps = 0;
+    double shift = 0.0, lastShift = 0.0;
+    bool converged = false;
+    auto proceed = [&]() {
+        if (numSteps < prm->min_steps) return true;
+        else if (converged) return false;
+        else if (numSteps >= prm->max_steps) return shift * 4.0 < lastShift;
+        return true;
+    };
+    while (proceed()) {
+        lastShift = shift;
+        int its = 0;
+        float a = 0, s = 0, u = 0;
+        const int rc = dmx_newton_step(ctx, prm, &its, &shift, &a, &s, &u);
+        if (numSteps < 64) rep->linear_iterations[numSteps] = its;
+        rep->linear_iterations_total += its;
+        if (rc) { rep->newton_iterations = numSteps; rep->converged = 0; return rc; }
+        rep->t_assemble += a * 1e-3; rep->t_solve += s * 1e-3; rep->t_update += u * 1e-3;
+        if (numSteps < 64) rep->shifts[numSteps] = shift;
+        ++numSteps;
+        converged = shift <= prm->max_relative_shift;
+    }
+    rep->newton_iterations = numSteps;
+    rep->converged = converged ? 1 : 0;
+    rep->last_shift = shift;
+    return converged ? 0 : DMX_STATUS_NOT_CONVERGED;
+}
+int dmx_newton_solve_host(dmx_ctx* ctx, double* u, const double* prev, const dmx_newton_params* prm, dmx_newton_report* rep)
+{
+    int rc;
+    if ((rc = dmx_vec_upload(ctx, DMX_VEC_CUR, u))) return rc;
+    if (prev && (rc = dmx_vec_upload(ctx, DMX_VEC_PREV, prev))) return rc;
+    const int st = dmx_newton_solve(ctx, prm, rep);
+    if (st < 0) return st;
+    if ((rc = dmx_vec_download(ctx, DMX_VEC_CUR, u))) return rc;
+    return st;
+}
+
+// ---- kernel-level entry points ----
+int dmx_spmv(dmx_ctx* ctx, int x_vec, int y_vec)
+{
+    if (int rc = vec_ok(ctx, x_vec)) return rc;
+    if (int rc = vec_ok(ctx, y_vec)) return rc;
+    return launch_spmv(ctx, ctx->d_vec[x_vec], ctx->d_vec[y_vec]);
+}
+int dmx_ilu0_factor(dmx_ctx* ctx) { return ilu0_factor(ctx); }
+int dmx_ilu0_apply(dmx_ctx* ctx, int d_vec, int v_vec)
+{
+    if (!ctx->ilu_valid) return fail(ctx, DMX_ERR_USAGE, "ilu0_apply before ilu0_factor");
+    if (int rc = vec_ok(ctx, d_vec)) return rc;
+    if (int rc = vec_ok(ctx, v_vec)) return rc;
+    return ilu0_apply(ctx, ctx->d_vec[d_vec], ctx->d_vec[v_vec]);
+}
+int dmx_ilu0_download(dmx_ctx* ctx, double* values)
+{
+    if (!ctx->ilu_valid) return fail(ctx, DMX_ERR_USAGE, "no ILU factorisation");
+    DMX_CUDA(cudaMemcpyAsync(values, ctx->d_ilu, (size_t)ctx->nnzb * ctx->b * ctx->b * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    DMX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+int dmx_halo_exchange(dmx_ctx* ctx, int vec)
+{
+    if (int rc = vec_ok(ctx, vec)) return rc;
+    if (ctx->nranks == 1) return 0;
+    return halo_exchange(ctx, ctx->d_vec[vec]);
+}
+
+int dmx_time_kernel(dmx_ctx* ctx, int which, int reps, float* ms_avg)
+{
+    DMX_CUDA(cudaSetDevice(ctx->device));
+    if (reps < 1) reps = 1;
+    int rc = 0;
+    if (which == 2 && !ctx->ilu_valid) return fail(ctx, DMX_ERR_USAGE, "time ILU apply: factor first");
+    if ((which == 0 || which == 4) && (rc = prepare(ctx))) return rc;
+    DMX_CUDA(cudaStreamSynchronize(ctx->stream));
+    DMX_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+    for (int i = 0; i < reps && !rc; ++i) {
+        switch (which) {
+            case 0: rc = launch_assemble(ctx, true); break;
+            case 1: rc = launch_spmv(ctx, ctx->d_vec[DMX_VEC_WORK0], ctx->d_vec[DMX_VEC_WORK1]); break;
+            case 2: rc = ilu0_apply(ctx, ctx->d_vec[DMX_VEC_WORK0], ctx->d_vec[DMX_VEC_WORK1]); break;
+            case 3: rc = ilu0_factor(ctx); break;
+            case 4: rc = launch_volvars_only(ctx); break;
+            default: return fail(ctx, DMX_ERR_USAGE, "unknown kernel id");
+        }
+    }
+    if (rc) return rc;
+    DMX_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+    DMX_CUDA(cudaEventSynchronize(ctx->ev[1]));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+    *ms_avg = ms / reps;
+    (void)now_ms;
+    return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,191 @@
+// common.cuh -- context object and helpers shared by the translation units of libdumux_b200.so
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/dumux_b200.h"
+#include "physics.cuh"
+
+#define DMX_NUM_VECS 7
+#define DMX_MAX_REGIONS 8
+#define DMX_ERR_CUDA (-1)
+#define DMX_ERR_USAGE (-2)
+#define DMX_ERR_NCCL (-3)
+
+namespace dmx {
+
+// Everything the assembly kernels need, passed by value (fits the 4 KB kernel-parameter space).
+struct AsmParams {
+    int model, b, dim;
+    int nc[3];
+    int n;
+    // options
+    int enable_gravity, fd_method, stationary, nd;
+    double gravity, upwind_weight, base_eps, mag[2], dt, extrusion;
+    // geometry, per axis a: width[a][i], gf_lo[a][i] (>0), gf_hi[a][i] (>0): |(x_f - x_c)/|x_f - x_c|^2|
+    const double* width[3];
+    const double* gf_lo[3];
+    const double* gf_hi[3];
+    // cell fields
+    const double* K;
+    const double* phi;
+    const int* region;
+    const double* q;          // may be null
+    const double* tij[3];     // transmissibility of the + face of each cell along axis a
+    // fluids
+    double rho[2], mu[2];
+    int tabulated;
+    FluidTable table;
+    const MaterialLaw* laws;
+    // boundary data per side: type[nf], neumann[nf*b], Dirichlet state p[nf*2], up[nf*2], rho[nf*2]
+    const int* bc_type[6];
+    const double* bc_neumann[6];
+    const double* bc_p[6];
+    const double* bc_up[6];
+    const double* bc_rho[6];
+    // state
+    const double* cur;
+    const double* prev;
+    double* rec;              // secondary-variable records, SoA [nrec][n]
+    int nrec;
+    // outputs
+    const int* rowptr;
+    double* residual;
+    double* jac;
+    int* flag_nonfinite;
+};
+
+} // namespace dmx
+
+struct dmx_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    long long launches = 0;
+    int num_sms = 148;
+
+    // distributed
+    int rank = 0, nranks = 1;
+    void* nccl_comm = nullptr;
+    int split_axis = 2;
+    int own_begin = 0, own_end = 0;     // owned index range along split axis (local indices)
+
+    // grid
+    int model = 0, b = 0, dim = 0;
+    int gcells[3] = {1, 1, 1};
+    int nc[3] = {1, 1, 1}, off[3] = {0, 0, 0};
+    int n = 0;
+    long long nnzb = 0;
+    bool has_grid = false;
+    std::vector<double> xn[3];
+    double* d_geom = nullptr;
+    const double *d_width[3] = {}, *d_gflo[3] = {}, *d_gfhi[3] = {};
+
+    dmx_options opt;
+    bool prepared = false;
+
+    // cell fields
+    std::vector<double> h_K, h_phi;
+    std::vector<int> h_region;
+    double *d_K = nullptr, *d_phi = nullptr, *d_q = nullptr;
+    int* d_region = nullptr;
+    double* d_tij[3] = {nullptr, nullptr, nullptr};
+
+    std::vector<dmx::MaterialLaw> laws;
+    dmx::MaterialLaw* d_laws = nullptr;
+    double rho[2] = {1000.0, 1460.0}, mu[2] = {1e-3, 5.7e-4};
+    bool tabulated = false;
+    dmx::FluidTable h_table{};          // host copy of table (host pointers)
+    std::vector<double> h_tab_pmin, h_tab_pmax, h_tab_rho, h_tab_mu;
+    dmx::FluidTable d_table{};          // device pointers
+    double* d_tab_buf = nullptr;
+
+    // boundary
+    std::vector<int> h_bc_type[6];
+    std::vector<double> h_bc_val[6];
+    int* d_bc_type[6] = {};
+    double *d_bc_neumann[6] = {}, *d_bc_p[6] = {}, *d_bc_up[6] = {}, *d_bc_rho[6] = {};
+
+    // pattern + matrix
+    std::vector<int> h_rowptr, h_colidx;
+    int *d_rowptr = nullptr, *d_colidx = nullptr, *d_diag = nullptr;
+    double *d_J = nullptr, *d_ilu = nullptr;
+    bool ilu_valid = false;
+
+    // vectors
+    double* d_vec[DMX_NUM_VECS] = {};
+    double *d_rt = nullptr, *d_p = nullptr, *d_v = nullptr, *d_t = nullptr, *d_y = nullptr, *d_dinv = nullptr;
+    double* d_rec = nullptr;
+    int nrec = 0;
+
+    // ILU0 level schedule (rows sorted by level; level_ptr on host)
+    int *d_lrows = nullptr, *d_urows = nullptr;
+    std::vector<int> l_ptr, u_ptr;
+    int *d_lptr = nullptr, *d_uptr = nullptr;
+    unsigned int* d_barrier = nullptr;
+
+    // reductions
+    double* d_partials = nullptr;
+    double* d_scalars = nullptr;
+    double* h_scalars = nullptr;     // pinned
+    int* d_flag = nullptr;
+    int* h_flag = nullptr;           // pinned
+    unsigned char* d_owner = nullptr;  // 1 = owner (null in single-GPU mode)
+
+    // halo (distributed)
+    double *d_send_lo = nullptr, *d_send_hi = nullptr, *d_recv_lo = nullptr, *d_recv_hi = nullptr;
+
+    cudaEvent_t ev[4] = {};
+};
+
+namespace dmx {
+
+inline int fail(dmx_ctx* c, int code, const std::string& msg)
+{
+    if (c) c->err = msg;
+    return code;
+}
+
+#define DMX_CUDA(call)                                                                              \
+    do {                                                                                            \
+        cudaError_t e__ = (call);                                                                   \
+        if (e__ != cudaSuccess)                                                                     \
+            return dmx::fail(ctx, DMX_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+    } while (0)
+
+#define DMX_CHECK_LAUNCH()                                                                          \
+    do {                                                                                            \
+        ctx->launches++;                                                                            \
+        cudaError_t e__ = cudaGetLastError();                                                       \
+        if (e__ != cudaSuccess)                                                                     \
+            return dmx::fail(ctx, DMX_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e__)); \
+    } while (0)
+
+// implemented in assembly.cu
+int prepare(dmx_ctx* ctx);
+int launch_assemble(dmx_ctx* ctx, bool with_jacobian);
+int launch_volvars_only(dmx_ctx* ctx);
+// implemented in linalg.cu
+int build_level_schedule(dmx_ctx* ctx);
+int launch_spmv(dmx_ctx* ctx, const double* x, double* y);
+int ilu0_factor(dmx_ctx* ctx);
+int ilu0_apply(dmx_ctx* ctx, const double* d, double* v);
+int block_jacobi_setup(dmx_ctx* ctx);
+int block_jacobi_apply(dmx_ctx* ctx, const double* d, double* v);
+int dot(dmx_ctx* ctx, const double* a, const double* b, double* out);
+int bicgstab(dmx_ctx* ctx, double reduction, int maxit, int precond, int* iterations, double* achieved);
+int newton_update(dmx_ctx* ctx, double* shift);
+int check_finite(dmx_ctx* ctx, const double* v, size_t len, bool* ok);
+// implemented in dist.cu
+int nccl_init(dmx_ctx* ctx, const void* uid);
+int nccl_get_unique_id(void* out);
+int nccl_destroy(dmx_ctx* ctx);
+int halo_exchange(dmx_ctx* ctx, double* v);
+int allreduce_sum(dmx_ctx* ctx, double* d_buf, int count);
+int allreduce_max(dmx_ctx* ctx, double* d_buf, int count);
+int allreduce_min_int(dmx_ctx* ctx, int* d_buf, int count);
+
+} // namespace dmx

@@ -1,0 +1,145 @@
+// det_math.cuh -- deterministic pow() for the material laws, host + device.
+//
+// The FD Jacobian (eps = 1e-10*(|x|+1), dumux/common/numericdifferentiation.hh:36-41) amplifies last-ulp
+// differences in pow by 1e10, so the kernels cannot use CUDA's libdevice pow (2-ulp, different bits from
+// glibc).  dmx_pow executes one fixed sequence of IEEE +,-,*,/ and correctly rounded fma operations, so
+// it returns the same bits on sm_100a and on any IEEE host (<= 1 ulp from glibc pow over the range the
+// Brooks-Corey / van Genuchten laws use).  Compile device code with -fmad=false: the only fused
+// operations are the explicit fma() calls below.
+//
+//   x = 2^e * m, m in [0.75,1.5);  s = (m-1)/(m+1) in double-double (division residual via fma)
+//   log(m) = 2s + s^3 P(s^2) (atanh series);  log2(x) = e + log(m)/ln2 in double-double
+//   z = y*log2(x);  n = round(z), r = z - n;  2^r by a degree-14 Taylor polynomial;  scale by 2^n.
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <cmath>
+
+#ifdef __CUDACC__
+#define DMX_HD __host__ __device__ __forceinline__
+#else
+#define DMX_HD inline
+#endif
+
+namespace dmx {
+
+DMX_HD double u2d(uint64_t u)
+{
+#ifdef __CUDA_ARCH__
+    return __longlong_as_double((long long)u);
+#else
+    double x; memcpy(&x, &u, 8); return x;
+#endif
+}
+DMX_HD uint64_t d2u(double x)
+{
+#ifdef __CUDA_ARCH__
+    return (uint64_t)__double_as_longlong(x);
+#else
+    uint64_t u; memcpy(&u, &x, 8); return u;
+#endif
+}
+DMX_HD double fma_rn(double a, double b, double c)
+{
+#ifdef __CUDA_ARCH__
+    return __fma_rn(a, b, c);
+#else
+    return __builtin_fma(a, b, c);
+#endif
+}
+
+DMX_HD double det_pow(double x, double y)
+{
+    if (y == 0.0) return 1.0;
+    if (x == 1.0) return 1.0;
+    if (x != x || y != y) return x + y;
+    if (x < 0.0) return u2d(0x7ff8000000000000ull);
+    if (x == 0.0) return y > 0.0 ? 0.0 : u2d(0x7ff0000000000000ull);
+    if (x == u2d(0x7ff0000000000000ull)) return y > 0.0 ? x : 0.0;
+
+    uint64_t bits = d2u(x);
+    int e = (int)((bits >> 52) & 0x7ff);
+    if (e == 0) {
+        x = x * 18014398509481984.0;
+        bits = d2u(x);
+        e = (int)((bits >> 52) & 0x7ff) - 54;
+    }
+    e -= 1023;
+    double m = u2d((bits & 0x000fffffffffffffull) | 0x3ff0000000000000ull);
+    if (m >= 1.5) { m = m * 0.5; e += 1; }
+
+    const double a = m - 1.0;
+    const double b = m + 1.0;
+    const double b_lo = m - (b - 1.0);
+    const double s_hi = a / b;
+    double res = fma_rn(-s_hi, b, a);
+    res = fma_rn(-s_hi, b_lo, res);
+    const double s_lo = res / b;
+    const double s2 = s_hi * s_hi;
+
+    double P = 0x1.2f684bda12f68p-4;
+    P = fma_rn(P, s2, 0x1.47ae147ae147bp-4);
+    P = fma_rn(P, s2, 0x1.642c8590b2164p-4);
+    P = fma_rn(P, s2, 0x1.8618618618618p-4);
+    P = fma_rn(P, s2, 0x1.af286bca1af28p-4);
+    P = fma_rn(P, s2, 0x1.e1e1e1e1e1e1ep-4);
+    P = fma_rn(P, s2, 0x1.1111111111111p-3);
+    P = fma_rn(P, s2, 0x1.3b13b13b13b14p-3);
+    P = fma_rn(P, s2, 0x1.745d1745d1746p-3);
+    P = fma_rn(P, s2, 0x1.c71c71c71c71cp-3);
+    P = fma_rn(P, s2, 0x1.2492492492492p-2);
+    P = fma_rn(P, s2, 0x1.999999999999ap-2);
+    P = fma_rn(P, s2, 0x1.5555555555555p-1);
+    const double tail = (s_hi * s2) * P;
+
+    const double lh = 2.0 * s_hi;
+    const double ll = fma_rn(2.0, s_lo, tail);
+    const double th = lh + ll;
+    const double tl = ll - (th - lh);
+
+    const double INVLN2_HI = 0x1.71547652b82fep+0;
+    const double INVLN2_LO = 0x1.777d0ffda0d24p-56;
+    const double ph = th * INVLN2_HI;
+    double pl = fma_rn(th, INVLN2_HI, -ph);
+    pl = fma_rn(th, INVLN2_LO, pl);
+    pl = fma_rn(tl, INVLN2_HI, pl);
+
+    const double ed = (double)e;
+    const double Lh = ed + ph;
+    double Ll = (ed - Lh) + ph;
+    Ll = Ll + pl;
+
+    const double zh = y * Lh;
+    double zl = fma_rn(y, Lh, -zh);
+    zl = fma_rn(y, Ll, zl);
+
+    if (zh >= 1024.0) return u2d(0x7ff0000000000000ull);
+    if (zh <= -1100.0) return 0.0;
+
+    const long long n = (long long)(zh + (zh >= 0.0 ? 0.5 : -0.5));
+    const double r = (zh - (double)n) + zl;
+
+    double Q = 0x1.314964d5878a9p-44;
+    Q = fma_rn(Q, r, 0x1.816193166d0f9p-40);
+    Q = fma_rn(Q, r, 0x1.c3bd650fc2986p-36);
+    Q = fma_rn(Q, r, 0x1.e8cac7351bb25p-32);
+    Q = fma_rn(Q, r, 0x1.e4cf5158b8ecap-28);
+    Q = fma_rn(Q, r, 0x1.b5253d395e7c4p-24);
+    Q = fma_rn(Q, r, 0x1.62c0223a5c824p-20);
+    Q = fma_rn(Q, r, 0x1.ffcbfc588b0c7p-17);
+    Q = fma_rn(Q, r, 0x1.430912f86c787p-13);
+    Q = fma_rn(Q, r, 0x1.5d87fe78a6731p-10);
+    Q = fma_rn(Q, r, 0x1.3b2ab6fba4e77p-7);
+    Q = fma_rn(Q, r, 0x1.c6b08d704a0c0p-5);
+    Q = fma_rn(Q, r, 0x1.ebfbdff82c58fp-3);
+    Q = fma_rn(Q, r, 0x1.62e42fefa39efp-1);
+    Q = fma_rn(Q, r, 1.0);
+
+    if (n >= -1022 && n <= 1023) return Q * u2d((uint64_t)(n + 1023) << 52);
+    if (n > 1023) return (Q * 0x1p1023) * u2d((uint64_t)(n - 1023 + 1023) << 52);
+    long long n2 = n + 1022;
+    if (n2 < -1022) n2 = -1022;
+    return (Q * 0x1p-1022) * u2d((uint64_t)(n2 + 1023) << 52);
+}
+
+} // namespace dmx

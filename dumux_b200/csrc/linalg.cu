@@ -1,0 +1,669 @@
+// linalg.cu -- BCRS block SpMV, block ILU(0), fused BLAS-1 and the BiCGSTAB driver.
+//
+// Replaces what DuMux delegates to dune-istl through IstlIterativeLinearSolver
+// (dumux/linear/istlsolvers.hh:273,457-464,535-568; alias ILUBiCGSTABIstlSolver :636-642):
+//   Dune::BCRSMatrix::mv            -> bcrs_spmv_kernel<b>
+//   Dune::SeqILU(n=0,w=1)           -> ilu0_factor_kernel<b> / ilu0_lower_kernel<b> / ilu0_upper_kernel<b>
+//                                      (level-scheduled: rows of one dependency level run in parallel, per-row
+//                                      operation order identical to ILU::blockILU0Decomposition / blockILUBacksolve)
+//   Dune::BiCGSTABSolver::apply     -> bicgstab() below, same operation sequence and stopping rules
+//   SeqScalarProduct / OverlappingSchwarzScalarProduct -> dot kernels (fixed-shape, deterministic; owner-masked)
+// Compiled with -fmad=false so per-row sums match the sequential CPU arithmetic bit for bit.
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+
+#include "common.cuh"
+
+namespace dmx {
+
+static constexpr int RED_BLOCKS = 1184;   // 148 SMs x 8
+static constexpr int RED_THREADS = 256;
+
+// ---------------------------------------------------------------------------------------------
+// SpMV: one thread per scalar row (b threads per block row); per-row sum in column order from 0
+// ---------------------------------------------------------------------------------------------
+template <int B>
+__global__ void __launch_bounds__(256) bcrs_spmv_kernel(int n, const int* __restrict__ rowptr, const int* __restrict__ colidx,
+                                                        const double* __restrict__ A, const double* __restrict__ x,
+                                                        double* __restrict__ y, const unsigned char* __restrict__ owner)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int row = (int)(t / B);
+    const int e = (int)(t % B);
+    if (row >= n) return;
+    double acc = 0.0;
+    const int k0 = rowptr[row], k1 = rowptr[row + 1];
+    for (int k = k0; k < k1; ++k) {
+        const int c = colidx[k];
+        if (B == 2) {
+            const double2 a = *reinterpret_cast<const double2*>(A + ((size_t)k * 4 + e * 2));
+            const double2 xv = *reinterpret_cast<const double2*>(x + (size_t)c * 2);
+            acc += a.x * xv.x;
+            acc += a.y * xv.y;
+        } else {
+            acc += A[k] * x[c];
+        }
+    }
+    if (owner && !owner[row]) acc = 0.0;   // OverlappingSchwarzOperator: project() zeroes non-owner rows
+    y[(size_t)row * B + e] = acc;
+}
+
+int launch_spmv(dmx_ctx* ctx, const double* x, double* y)
+{
+    const long long threads = (long long)ctx->n * ctx->b;
+    const int bs = 256;
+    const int grid = (int)((threads + bs - 1) / bs);
+    if (ctx->b == 2)
+        bcrs_spmv_kernel<2><<<grid, bs, 0, ctx->stream>>>(ctx->n, ctx->d_rowptr, ctx->d_colidx, ctx->d_J, x, y, ctx->d_owner);
+    else
+        bcrs_spmv_kernel<1><<<grid, bs, 0, ctx->stream>>>(ctx->n, ctx->d_rowptr, ctx->d_colidx, ctx->d_J, x, y, ctx->d_owner);
+    DMX_CHECK_LAUNCH();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// reductions: fixed grid, per-block partials, single-block final pass in fixed order -> deterministic
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, o));
+    return v;
+}
+template <bool MAX>
+__device__ __forceinline__ double block_reduce(double v)
+{
+    __shared__ double sh[32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    v = MAX ? warp_max(v) : warp_sum(v);
+    __syncthreads();
+    if (lane == 0) sh[wid] = v;
+    __syncthreads();
+    const int nw = (blockDim.x + 31) >> 5;
+    v = (threadIdx.x < nw) ? sh[threadIdx.x] : 0.0;
+    if (wid == 0) v = MAX ? warp_max(v) : warp_sum(v);
+    return v;
+}
+
+// up to 3 simultaneous dot products: out[q] = sum_i a_q[i]*b_q[i] over owner entries
+template <int NQ>
+__global__ void __launch_bounds__(RED_THREADS) dot_kernel(size_t len, int b, const double* a0, const double* b0, const double* a1,
+                                                          const double* b1, const double* a2, const double* b2,
+                                                          const unsigned char* owner, double* partials)
+{
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (size_t)gridDim.x * blockDim.x) {
+        if (owner && !owner[i / b]) continue;
+        s0 += a0[i] * b0[i];
+        if (NQ > 1) s1 += a1[i] * b1[i];
+        if (NQ > 2) s2 += a2[i] * b2[i];
+    }
+    s0 = block_reduce<false>(s0);
+    if (NQ > 1) s1 = block_reduce<false>(s1);
+    if (NQ > 2) s2 = block_reduce<false>(s2);
+    if (threadIdx.x == 0) {
+        partials[blockIdx.x] = s0;
+        if (NQ > 1) partials[gridDim.x + blockIdx.x] = s1;
+        if (NQ > 2) partials[2 * gridDim.x + blockIdx.x] = s2;
+    }
+}
+template <bool MAX>
+__global__ void __launch_bounds__(RED_THREADS) final_reduce_kernel(int nblocks, int nq, const double* partials, double* out)
+{
+    for (int q = 0; q < nq; ++q) {
+        double s = 0.0;
+        for (int i = threadIdx.x; i < nblocks; i += blockDim.x) s = MAX ? fmax(s, partials[q * nblocks + i]) : s + partials[q * nblocks + i];
+        s = block_reduce<MAX>(s);
+        if (threadIdx.x == 0) out[q] = s;
+        __syncthreads();
+    }
+}
+
+// x += alpha*y ; r += -alpha*v ; partial ||r||^2   (the two axpy + norm of a BiCGSTAB half step)
+__global__ void __launch_bounds__(RED_THREADS) axpy2_norm_kernel(size_t len, int b, double alpha, const double* y, const double* v,
+                                                                 double* x, double* r, const unsigned char* owner, double* partials)
+{
+    double s = 0.0;
+    const double malpha = -alpha;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (size_t)gridDim.x * blockDim.x) {
+        x[i] += alpha * y[i];
+        const double ri = r[i] + malpha * v[i];
+        r[i] = ri;
+        if (!owner || owner[i / b]) s += ri * ri;
+    }
+    s = block_reduce<false>(s);
+    if (threadIdx.x == 0) partials[blockIdx.x] = s;
+}
+// p = ((p + (-omega)*v) * beta) + r
+__global__ void __launch_bounds__(256) p_update_kernel(size_t len, double beta, double omega, const double* r, const double* v, double* p)
+{
+    const double momega = -omega;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (size_t)gridDim.x * blockDim.x) {
+        double pi = p[i] + momega * v[i];
+        pi *= beta;
+        pi += r[i];
+        p[i] = pi;
+    }
+}
+// r = b - A x given t = A x ; rt = r ; partial ||r||^2
+__global__ void __launch_bounds__(RED_THREADS) residual_init_kernel(size_t len, int b, const double* rhs, const double* Ax, double* r,
+                                                                    double* rt, const unsigned char* owner, double* partials)
+{
+    double s = 0.0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (size_t)gridDim.x * blockDim.x) {
+        const double ri = rhs[i] - Ax[i];
+        r[i] = ri;
+        rt[i] = ri;
+        if (!owner || owner[i / b]) s += ri * ri;
+    }
+    s = block_reduce<false>(s);
+    if (threadIdx.x == 0) partials[blockIdx.x] = s;
+}
+
+// u = uLast + (-1)*delta ; shift = max_i |u - uLast| / max(1, |u + uLast|/2)   (newtonsolver.hh:111-129,556-557)
+__global__ void __launch_bounds__(RED_THREADS) newton_update_kernel(size_t len, int b, const double* uLast, const double* delta, double* u,
+                                                                    const unsigned char* owner, double* partials)
+{
+    double s = 0.0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (size_t)gridDim.x * blockDim.x) {
+        const double ul = uLast[i];
+        const double un = ul + (-1.0) * delta[i];
+        u[i] = un;
+        const double sh = fabs(un - ul) / fmax(1.0, fabs(un + ul) * 0.5);
+        if (!owner || owner[i / b]) s = fmax(s, sh);
+    }
+    s = block_reduce<true>(s);
+    if (threadIdx.x == 0) partials[blockIdx.x] = s;
+}
+__global__ void __launch_bounds__(RED_THREADS) finite_check_kernel(size_t len, const double* v, int* flag)
+{
+    bool bad = false;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (size_t)gridDim.x * blockDim.x)
+        bad = bad || !(fabs(v[i]) <= DBL_MAX);
+    if (bad) atomicOr(flag, 1);
+}
+
+static int reduce_to_host(dmx_ctx* ctx, int nq, bool max, double* out)
+{
+    if (max) final_reduce_kernel<true><<<1, RED_THREADS, 0, ctx->stream>>>(RED_BLOCKS, nq, ctx->d_partials, ctx->d_scalars);
+    else final_reduce_kernel<false><<<1, RED_THREADS, 0, ctx->stream>>>(RED_BLOCKS, nq, ctx->d_partials, ctx->d_scalars);
+    DMX_CHECK_LAUNCH();
+    if (ctx->nranks > 1) {
+        if (int rc = max ? allreduce_max(ctx, ctx->d_scalars, nq) : allreduce_sum(ctx, ctx->d_scalars, nq)) return rc;
+    }
+    DMX_CUDA(cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, nq * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    DMX_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int q = 0; q < nq; ++q) out[q] = ctx->h_scalars[q];
+    return 0;
+}
+
+int dot(dmx_ctx* ctx, const double* a, const double* b, double* out)
+{
+    const size_t len = (size_t)ctx->n * ctx->b;
+    dot_kernel<1><<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>>(len, ctx->b, a, b, nullptr, nullptr, nullptr, nullptr, ctx->d_owner, ctx->d_partials);
+    DMX_CHECK_LAUNCH();
+    return reduce_to_host(ctx, 1, false, out);
+}
+static int dot2(dmx_ctx* ctx, const double* a0, const double* b0, const double* a1, const double* b1, double* out)
+{
+    const size_t len = (size_t)ctx->n * ctx->b;
+    dot_kernel<2><<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>>(len, ctx->b, a0, b0, a1, b1, nullptr, nullptr, ctx->d_owner, ctx->d_partials);
+    DMX_CHECK_LAUNCH();
+    return reduce_to_host(ctx, 2, false, out);
+}
+
+int newton_update(dmx_ctx* ctx, double* shift)
+{
+    const size_t len = (size_t)ctx->n * ctx->b;
+    newton_update_kernel<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>>(len, ctx->b, ctx->d_vec[DMX_VEC_ULAST], ctx->d_vec[DMX_VEC_DELTA],
+                                                                      ctx->d_vec[DMX_VEC_CUR], ctx->d_owner, ctx->d_partials);
+    DMX_CHECK_LAUNCH();
+    return reduce_to_host(ctx, 1, true, shift);
+}
+
+int check_finite(dmx_ctx* ctx, const double* v, size_t len, bool* ok)
+{
+    DMX_CUDA(cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream));
+    finite_check_kernel<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>>(len, v, ctx->d_flag);
+    DMX_CHECK_LAUNCH();
+    DMX_CUDA(cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    DMX_CUDA(cudaStreamSynchronize(ctx->stream));
+    *ok = (*ctx->h_flag == 0);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// block ILU(0), level scheduled.  Level of row i (lower) = 1 + max level of rows j<i in its pattern; for the
+// 7-point stencil that is the hyperplane i+j+k.  Rows of one level are independent.
+// ---------------------------------------------------------------------------------------------
+int build_level_schedule(dmx_ctx* ctx)
+{
+    const int n = ctx->n;
+    const std::vector<int>& rp = ctx->h_rowptr;
+    const std::vector<int>& ci = ctx->h_colidx;
+    std::vector<int> lev(n, 0), diag(n, -1);
+    int nl = 0;
+    for (int i = 0; i < n; ++i) {
+        int l = 0;
+        for (int k = rp[i]; k < rp[i + 1]; ++k) {
+            const int j = ci[k];
+            if (j < i) l = std::max(l, lev[j] + 1);
+            else if (j == i) diag[i] = k;
+        }
+        if (diag[i] < 0) return fail(ctx, DMX_ERR_USAGE, "pattern without diagonal entry");
+        lev[i] = l;
+        nl = std::max(nl, l + 1);
+    }
+    auto bucket = [&](const std::vector<int>& level, int nlev, std::vector<int>& ptr, std::vector<int>& rows) {
+        ptr.assign(nlev + 1, 0);
+        for (int i = 0; i < n; ++i) ptr[level[i] + 1]++;
+        for (int l = 0; l < nlev; ++l) ptr[l + 1] += ptr[l];
+        rows.resize(n);
+        std::vector<int> cur(ptr.begin(), ptr.end() - 1);
+        for (int i = 0; i < n; ++i) rows[cur[level[i]]++] = i;
+    };
+    std::vector<int> lrows, urows;
+    bucket(lev, nl, ctx->l_ptr, lrows);
+    // upper: dependencies on rows j > i
+    std::vector<int> ulev(n, 0);
+    int nu = 0;
+    for (int i = n - 1; i >= 0; --i) {
+        int l = 0;
+        for (int k = rp[i]; k < rp[i + 1]; ++k)
+            if (ci[k] > i) l = std::max(l, ulev[ci[k]] + 1);
+        ulev[i] = l;
+        nu = std::max(nu, l + 1);
+    }
+    bucket(ulev, nu, ctx->u_ptr, urows);
+    auto up = [&](int** d, const std::vector<int>& h) -> int {
+        if (*d) cudaFree(*d);
+        DMX_CUDA(cudaMalloc((void**)d, h.size() * sizeof(int)));
+        DMX_CUDA(cudaMemcpy(*d, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice));
+        return 0;
+    };
+    if (int rc = up(&ctx->d_lrows, lrows)) return rc;
+    if (int rc = up(&ctx->d_urows, urows)) return rc;
+    if (int rc = up(&ctx->d_diag, diag)) return rc;
+    if (int rc = up(&ctx->d_lptr, ctx->l_ptr)) return rc;
+    if (int rc = up(&ctx->d_uptr, ctx->u_ptr)) return rc;
+    return 0;
+}
+
+template <int B>
+__device__ __forceinline__ bool invert_block(double* A)
+{
+    if (B == 1) {
+        if (A[0] == 0.0) return false;
+        A[0] = 1.0 / A[0];
+        return true;
+    } else {
+        double detinv = A[0] * A[3] - A[1] * A[2];
+        if (detinv == 0.0 || detinv != detinv) return false;
+        detinv = 1.0 / detinv;
+        const double temp = A[0];
+        A[0] = A[3] * detinv;
+        A[1] = -A[1] * detinv;
+        A[2] = -A[2] * detinv;
+        A[3] = temp * detinv;
+        return true;
+    }
+}
+
+// grid-wide barrier for the persistent level loops (all CTAs co-resident: cooperative launch)
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int& epoch)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        epoch += gridDim.x;
+        __threadfence();
+        atomicAdd(counter, 1u);
+        while (*((volatile unsigned int*)counter) < epoch) { }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+template <int B>
+__device__ __forceinline__ void factor_row(int i, const int* rowptr, const int* colidx, const int* diag, double* A, int* flag)
+{
+    constexpr int BB = B * B;
+    const int iend = rowptr[i + 1];
+    const int kd = diag[i];
+    for (int kij = rowptr[i]; kij < kd; ++kij) {
+        const int j = colidx[kij];
+        const int kjj = diag[j];
+        // A_ij <- A_ij * A_jj^-1   (rightmultiply: C[r][c] = sum_k A[r][k]*B[k][c], sum started from 0)
+        double L[BB], D[BB];
+#pragma unroll
+        for (int q = 0; q < BB; ++q) { L[q] = A[(size_t)kij * BB + q]; D[q] = __ldcg(A + (size_t)kjj * BB + q); }
+        double C[BB];
+#pragma unroll
+        for (int r = 0; r < B; ++r)
+#pragma unroll
+            for (int c = 0; c < B; ++c) {
+                double s = 0.0;
+#pragma unroll
+                for (int k = 0; k < B; ++k) s += L[r * B + k] * D[k * B + c];
+                C[r * B + c] = s;
+            }
+#pragma unroll
+        for (int q = 0; q < BB; ++q) A[(size_t)kij * BB + q] = C[q];
+        // A_ik -= A_ij * A_jk for k > j present in both rows
+        int ik = kij + 1, jk = kjj + 1;
+        const int jend = rowptr[j + 1];
+        while (ik < iend && jk < jend) {
+            const int ci = colidx[ik], cj = colidx[jk];
+            if (ci == cj) {
+                double* T = A + (size_t)ik * BB;
+                const double* U = A + (size_t)jk * BB;
+#pragma unroll
+                for (int r = 0; r < B; ++r)
+#pragma unroll
+                    for (int c = 0; c < B; ++c) {
+                        double t = T[r * B + c];
+#pragma unroll
+                        for (int k = 0; k < B; ++k) t -= C[r * B + k] * __ldcg(U + k * B + c);
+                        T[r * B + c] = t;
+                    }
+                ++ik; ++jk;
+            } else if (ci < cj) ++ik;
+            else ++jk;
+        }
+    }
+    if (!invert_block<B>(A + (size_t)kd * BB)) atomicOr(flag, 1);
+}
+
+template <int B>
+__global__ void __launch_bounds__(128) ilu0_factor_kernel(int nlev, const int* lptr, const int* lrows, const int* rowptr, const int* colidx,
+                                                          const int* diag, double* A, int* flag, unsigned int* barrier)
+{
+    unsigned int epoch = 0;
+    for (int l = 0; l < nlev; ++l) {
+        const int r0 = lptr[l], r1 = lptr[l + 1];
+        for (int q = r0 + blockIdx.x * blockDim.x + threadIdx.x; q < r1; q += gridDim.x * blockDim.x)
+            factor_row<B>(lrows[q], rowptr, colidx, diag, A, flag);
+        if (l + 1 < nlev) grid_barrier(barrier, epoch);
+    }
+}
+
+// v_i = d_i - sum_{j<i} A_ij v_j
+template <int B>
+__global__ void __launch_bounds__(128) ilu0_lower_kernel(int nlev, const int* lptr, const int* lrows, const int* rowptr, const int* colidx,
+                                                         const int* diag, const double* A, const double* d, double* v, unsigned int* barrier)
+{
+    constexpr int BB = B * B;
+    unsigned int epoch = 0;
+    for (int l = 0; l < nlev; ++l) {
+        const int r0 = lptr[l], r1 = lptr[l + 1];
+        for (int q = r0 + blockIdx.x * blockDim.x + threadIdx.x; q < r1; q += gridDim.x * blockDim.x) {
+            const int i = lrows[q];
+            double rhs[B];
+#pragma unroll
+            for (int e = 0; e < B; ++e) rhs[e] = d[(size_t)i * B + e];
+            const int kd = diag[i];
+            for (int k = rowptr[i]; k < kd; ++k) {
+                const int c = colidx[k];
+                const double* vc = v + (size_t)c * B;
+                double xv[B];
+#pragma unroll
+                for (int e = 0; e < B; ++e) xv[e] = __ldcg(vc + e);
+#pragma unroll
+                for (int r = 0; r < B; ++r)
+#pragma unroll
+                    for (int cc = 0; cc < B; ++cc) rhs[r] -= A[(size_t)k * BB + r * B + cc] * xv[cc];
+            }
+#pragma unroll
+            for (int e = 0; e < B; ++e) __stcg(v + (size_t)i * B + e, rhs[e]);
+        }
+        if (l + 1 < nlev) grid_barrier(barrier, epoch);
+    }
+}
+// v_i = A_ii^-1 (v_i - sum_{j>i} A_ij v_j)
+template <int B>
+__global__ void __launch_bounds__(128) ilu0_upper_kernel(int nlev, const int* uptr, const int* urows, const int* rowptr, const int* colidx,
+                                                         const int* diag, const double* A, double* v, unsigned int* barrier)
+{
+    constexpr int BB = B * B;
+    unsigned int epoch = 0;
+    for (int l = 0; l < nlev; ++l) {
+        const int r0 = uptr[l], r1 = uptr[l + 1];
+        for (int q = r0 + blockIdx.x * blockDim.x + threadIdx.x; q < r1; q += gridDim.x * blockDim.x) {
+            const int i = urows[q];
+            double rhs[B];
+#pragma unroll
+            for (int e = 0; e < B; ++e) rhs[e] = __ldcg(v + (size_t)i * B + e);
+            const int kd = diag[i];
+            const int kend = rowptr[i + 1];
+            for (int k = kd + 1; k < kend; ++k) {
+                const int c = colidx[k];
+                double xv[B];
+#pragma unroll
+                for (int e = 0; e < B; ++e) xv[e] = __ldcg(v + (size_t)c * B + e);
+#pragma unroll
+                for (int r = 0; r < B; ++r)
+#pragma unroll
+                    for (int cc = 0; cc < B; ++cc) rhs[r] -= A[(size_t)k * BB + r * B + cc] * xv[cc];
+            }
+            double out[B];
+#pragma unroll
+            for (int r = 0; r < B; ++r) {
+                double s = 0.0;
+#pragma unroll
+                for (int cc = 0; cc < B; ++cc) s += A[(size_t)kd * BB + r * B + cc] * rhs[cc];
+                out[r] = s;
+            }
+#pragma unroll
+            for (int e = 0; e < B; ++e) __stcg(v + (size_t)i * B + e, out[e]);
+        }
+        if (l + 1 < nlev) grid_barrier(barrier, epoch);
+    }
+}
+
+static int coop_grid(dmx_ctx* ctx, const void* kernel, int threads)
+{
+    int perSm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, threads, 0);
+    if (perSm < 1) perSm = 1;
+    if (perSm > 4) perSm = 4;
+    return perSm * ctx->num_sms;
+}
+
+template <class... Args>
+static int coop_launch(dmx_ctx* ctx, void (*kernel)(Args...), int threads, Args... args)
+{
+    const int grid = coop_grid(ctx, (const void*)kernel, threads);
+    DMX_CUDA(cudaMemsetAsync(ctx->d_barrier, 0, sizeof(unsigned int), ctx->stream));
+    void* params[] = {(void*)&args...};
+    DMX_CUDA(cudaLaunchCooperativeKernel((const void*)kernel, dim3(grid), dim3(threads), params, 0, ctx->stream));
+    ctx->launches++;
+    return 0;
+}
+
+int ilu0_factor(dmx_ctx* ctx)
+{
+    const size_t bytes = (size_t)ctx->nnzb * ctx->b * ctx->b * sizeof(double);
+    if (!ctx->d_ilu) DMX_CUDA(cudaMalloc((void**)&ctx->d_ilu, bytes));
+    DMX_CUDA(cudaMemcpyAsync(ctx->d_ilu, ctx->d_J, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    DMX_CUDA(cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream));
+    const int nlev = (int)ctx->l_ptr.size() - 1;
+    int rc;
+    if (ctx->b == 2)
+        rc = coop_launch(ctx, ilu0_factor_kernel<2>, 128, nlev, (const int*)ctx->d_lptr, (const int*)ctx->d_lrows, (const int*)ctx->d_rowptr,
+                         (const int*)ctx->d_colidx, (const int*)ctx->d_diag, ctx->d_ilu, ctx->d_flag, ctx->d_barrier);
+    else
+        rc = coop_launch(ctx, ilu0_factor_kernel<1>, 128, nlev, (const int*)ctx->d_lptr, (const int*)ctx->d_lrows, (const int*)ctx->d_rowptr,
+                         (const int*)ctx->d_colidx, (const int*)ctx->d_diag, ctx->d_ilu, ctx->d_flag, ctx->d_barrier);
+    if (rc) return rc;
+    DMX_CUDA(cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    DMX_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (*ctx->h_flag) { ctx->err = "ILU0: singular diagonal block"; return DMX_STATUS_BREAKDOWN; }
+    ctx->ilu_valid = true;
+    return 0;
+}
+
+int ilu0_apply(dmx_ctx* ctx, const double* d, double* v)
+{
+    const int nl = (int)ctx->l_ptr.size() - 1, nu = (int)ctx->u_ptr.size() - 1;
+    int rc;
+    if (ctx->b == 2) {
+        rc = coop_launch(ctx, ilu0_lower_kernel<2>, 128, nl, (const int*)ctx->d_lptr, (const int*)ctx->d_lrows, (const int*)ctx->d_rowptr,
+                         (const int*)ctx->d_colidx, (const int*)ctx->d_diag, (const double*)ctx->d_ilu, d, v, ctx->d_barrier);
+        if (rc) return rc;
+        rc = coop_launch(ctx, ilu0_upper_kernel<2>, 128, nu, (const int*)ctx->d_uptr, (const int*)ctx->d_urows, (const int*)ctx->d_rowptr,
+                         (const int*)ctx->d_colidx, (const int*)ctx->d_diag, (const double*)ctx->d_ilu, v, ctx->d_barrier);
+    } else {
+        rc = coop_launch(ctx, ilu0_lower_kernel<1>, 128, nl, (const int*)ctx->d_lptr, (const int*)ctx->d_lrows, (const int*)ctx->d_rowptr,
+                         (const int*)ctx->d_colidx, (const int*)ctx->d_diag, (const double*)ctx->d_ilu, d, v, ctx->d_barrier);
+        if (rc) return rc;
+        rc = coop_launch(ctx, ilu0_upper_kernel<1>, 128, nu, (const int*)ctx->d_uptr, (const int*)ctx->d_urows, (const int*)ctx->d_rowptr,
+                         (const int*)ctx->d_colidx, (const int*)ctx->d_diag, (const double*)ctx->d_ilu, v, ctx->d_barrier);
+    }
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// block-Jacobi alternative: v = D^-1 d
+// ---------------------------------------------------------------------------------------------
+template <int B>
+__global__ void __launch_bounds__(256) jacobi_setup_kernel(int n, const int* diag, const double* A, double* dinv, int* flag)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double D[B * B];
+#pragma unroll
+    for (int q = 0; q < B * B; ++q) D[q] = A[(size_t)diag[i] * B * B + q];
+    if (!invert_block<B>(D)) atomicOr(flag, 1);
+#pragma unroll
+    for (int q = 0; q < B * B; ++q) dinv[(size_t)i * B * B + q] = D[q];
+}
+template <int B>
+__global__ void __launch_bounds__(256) jacobi_apply_kernel(int n, const double* dinv, const double* d, double* v)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+#pragma unroll
+    for (int r = 0; r < B; ++r) {
+        double s = 0.0;
+#pragma unroll
+        for (int c = 0; c < B; ++c) s += dinv[(size_t)i * B * B + r * B + c] * d[(size_t)i * B + c];
+        v[(size_t)i * B + r] = s;
+    }
+}
+int block_jacobi_setup(dmx_ctx* ctx)
+{
+    if (!ctx->d_dinv) DMX_CUDA(cudaMalloc((void**)&ctx->d_dinv, (size_t)ctx->n * ctx->b * ctx->b * sizeof(double)));
+    DMX_CUDA(cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream));
+    const int grid = (ctx->n + 255) / 256;
+    if (ctx->b == 2) jacobi_setup_kernel<2><<<grid, 256, 0, ctx->stream>>>(ctx->n, ctx->d_diag, ctx->d_J, ctx->d_dinv, ctx->d_flag);
+    else jacobi_setup_kernel<1><<<grid, 256, 0, ctx->stream>>>(ctx->n, ctx->d_diag, ctx->d_J, ctx->d_dinv, ctx->d_flag);
+    DMX_CHECK_LAUNCH();
+    DMX_CUDA(cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    DMX_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (*ctx->h_flag) { ctx->err = "block-Jacobi: singular diagonal block"; return DMX_STATUS_BREAKDOWN; }
+    return 0;
+}
+int block_jacobi_apply(dmx_ctx* ctx, const double* d, double* v)
+{
+    const int grid = (ctx->n + 255) / 256;
+    if (ctx->b == 2) jacobi_apply_kernel<2><<<grid, 256, 0, ctx->stream>>>(ctx->n, ctx->d_dinv, d, v);
+    else jacobi_apply_kernel<1><<<grid, 256, 0, ctx->stream>>>(ctx->n, ctx->d_dinv, d, v);
+    DMX_CHECK_LAUNCH();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// BiCGSTAB: Dune::BiCGSTABSolver::apply restated.  x = DELTA (initial guess as given),
+// b = RESIDUAL (not modified).  In a distributed ctx: operator = local SpMV + project, preconditioner = local
+// ILU0 + copyOwnerToAll, scalar product = owner-masked dot + all-reduce (OverlappingSchwarz*, BlockPreconditioner).
+// ---------------------------------------------------------------------------------------------
+static int precond_apply(dmx_ctx* ctx, int precond, const double* d, double* v)
+{
+    int rc = (precond == DMX_PRECOND_ILU0) ? ilu0_apply(ctx, d, v) : block_jacobi_apply(ctx, d, v);
+    if (rc) return rc;
+    if (ctx->nranks > 1) return halo_exchange(ctx, v);
+    return 0;
+}
+
+int bicgstab(dmx_ctx* ctx, double reduction, int maxit, int precond, int* iterations, double* achieved)
+{
+    const size_t len = (size_t)ctx->n * ctx->b;
+    double* x = ctx->d_vec[DMX_VEC_DELTA];
+    const double* rhs = ctx->d_vec[DMX_VEC_RESIDUAL];
+    // r lives in WORK0 so that RESIDUAL stays intact for the caller (Newton's residual norm, tests)
+    double* r = ctx->d_vec[DMX_VEC_WORK0];
+    double *rt = ctx->d_rt, *p = ctx->d_p, *v = ctx->d_v, *t = ctx->d_t, *y = ctx->d_y;
+    int rc;
+    *iterations = 0;
+    *achieved = 1.0;
+
+    // fresh preconditioner per call (istlsolvers.hh:457-463)
+    if (precond == DMX_PRECOND_ILU0) { if ((rc = ilu0_factor(ctx))) return rc; }
+    else if ((rc = block_jacobi_setup(ctx))) return rc;
+
+    if (ctx->nranks > 1 && (rc = halo_exchange(ctx, x))) return rc;       // BlockPreconditioner::pre: copyOwnerToAll(x)
+    if ((rc = launch_spmv(ctx, x, t))) return rc;
+    residual_init_kernel<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>>(len, ctx->b, rhs, t, r, rt, ctx->d_owner, ctx->d_partials);
+    DMX_CHECK_LAUNCH();
+    double s[3];
+    if ((rc = reduce_to_host(ctx, 1, false, s))) return rc;
+    const double norm0 = std::sqrt(s[0]);
+    double norm = norm0;
+    if (!(norm0 == norm0) || std::isinf(norm0)) return DMX_STATUS_NONFINITE;
+    auto converged = [&](double nrm) { return nrm < reduction * norm0 || nrm < 1e-30; };
+    if (converged(norm0)) { *achieved = norm0 > 0 ? 1.0 : 0.0; return 0; }
+    DMX_CUDA(cudaMemsetAsync(p, 0, len * sizeof(double), ctx->stream));
+    DMX_CUDA(cudaMemsetAsync(v, 0, len * sizeof(double), ctx->stream));
+
+    double rho = 1, alpha = 1, omega = 1, rho_new, h, beta;
+    const double EPSILON = 1e-80;
+    double it;
+    int status = DMX_STATUS_NOT_CONVERGED;
+    for (it = 0.5; it < maxit; it += .5) {
+        if ((rc = dot(ctx, rt, r, &rho_new))) return rc;
+        if (std::fabs(rho) <= EPSILON || std::fabs(omega) <= EPSILON) { status = DMX_STATUS_BREAKDOWN; break; }
+        if (it < 1)
+            DMX_CUDA(cudaMemcpyAsync(p, r, len * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        else {
+            beta = (rho_new / rho) * (alpha / omega);
+            p_update_kernel<<<RED_BLOCKS, 256, 0, ctx->stream>>>(len, beta, omega, r, v, p);
+            DMX_CHECK_LAUNCH();
+        }
+        if ((rc = precond_apply(ctx, precond, p, y))) return rc;
+        if ((rc = launch_spmv(ctx, y, v))) return rc;
+        if ((rc = dot(ctx, rt, v, &h))) return rc;
+        if (std::fabs(h) < EPSILON) { status = DMX_STATUS_BREAKDOWN; break; }
+        alpha = rho_new / h;
+        axpy2_norm_kernel<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>>(len, ctx->b, alpha, y, v, x, r, ctx->d_owner, ctx->d_partials);
+        DMX_CHECK_LAUNCH();
+        if ((rc = reduce_to_host(ctx, 1, false, s))) return rc;
+        norm = std::sqrt(s[0]);
+        if (!(norm == norm) || std::isinf(norm)) { status = DMX_STATUS_NONFINITE; break; }
+        if (converged(norm)) { status = 0; break; }
+        it += .5;
+        if ((rc = precond_apply(ctx, precond, r, y))) return rc;
+        if ((rc = launch_spmv(ctx, y, t))) return rc;
+        if ((rc = dot2(ctx, t, r, t, t, s))) return rc;
+        omega = s[0] / s[1];
+        axpy2_norm_kernel<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>>(len, ctx->b, omega, y, t, x, r, ctx->d_owner, ctx->d_partials);
+        DMX_CHECK_LAUNCH();
+        if ((rc = reduce_to_host(ctx, 1, false, s))) return rc;
+        rho = rho_new;
+        norm = std::sqrt(s[0]);
+        if (!(norm == norm) || std::isinf(norm)) { status = DMX_STATUS_NONFINITE; break; }
+        if (converged(norm)) { status = 0; break; }
+    }
+    *iterations = (int)std::ceil(std::min(it, (double)maxit));
+    *achieved = norm0 > 0 ? norm / norm0 : 0.0;
+    if (status == DMX_STATUS_BREAKDOWN) ctx->err = "BiCGSTAB breakdown (rho/omega/h ~ 0)";
+    if (status == DMX_STATUS_NOT_CONVERGED) ctx->err = "BiCGSTAB: maximum iterations reached";
+    return status;
+}
+
+} // namespace dmx

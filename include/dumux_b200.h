@@ -1,0 +1,170 @@
+/*
+ * dumux_b200.h -- C ABI of the B200-native Newton-step engine (libdumux_b200.so).
+ *
+ * This is the drop-in boundary for DuMux's Newton-step hot path (cell-centred TPFA assembly + Krylov solve).
+ * Every entry point names the reference interface it replaces (paths relative to the DuMux source tree).
+ * Plain pointers and sizes only; no C++ or torch types.  All functions return 0 on success, a positive
+ * DMX_STATUS_* for recoverable numerical conditions (what DuMux turns into Dumux::NumericalProblem,
+ * dumux/nonlinear/newtonsolver.hh:514-523) and a negative value for CUDA/NCCL/usage errors; the message is
+ * available from dmx_last_error().  One dmx_ctx per GPU; a ctx is not thread-safe; all work is stream-ordered
+ * on the ctx's stream.  There is no CPU fallback: every compute entry point runs CUDA kernels or fails.
+ *
+ * Data layout at the boundary (what Dune::BCRSMatrix / Dune::BlockVector store):
+ *   vectors   double[n*b], block i at [i*b, i*b+b)                      (BlockVector<FieldVector<double,b>>)
+ *   matrix    rowptr int32[n+1], colidx int32[nnzb] ascending per row, values double[nnzb*b*b] row-major blocks
+ *   cells     numbered x fastest (YaspGrid); boundary faces of a side numbered lower remaining axis fastest
+ *   sides     0:-x 1:+x 2:-y 3:+y 4:-z 5:+z (intersection.indexInInside())
+ */
+#ifndef DUMUX_B200_H
+#define DUMUX_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dmx_ctx dmx_ctx;
+
+enum { DMX_MODEL_1P = 1, DMX_MODEL_2P = 2 };
+enum { DMX_LAW_BROOKSCOREY = 0, DMX_LAW_VANGENUCHTEN = 1 };
+enum { DMX_BC_NEUMANN = 0, DMX_BC_DIRICHLET = 1, DMX_BC_NONE = 2 };
+enum { DMX_PRECOND_ILU0 = 0, DMX_PRECOND_BLOCKJACOBI = 1 };
+enum { DMX_STATUS_OK = 0, DMX_STATUS_NOT_CONVERGED = 1, DMX_STATUS_BREAKDOWN = 2, DMX_STATUS_NONFINITE = 3 };
+/* device-resident vectors of a ctx */
+enum {
+    DMX_VEC_CUR = 0,      /* curSol: current Newton iterate                      */
+    DMX_VEC_PREV = 1,     /* prevSol: previous time level (fvassembler.hh:650)   */
+    DMX_VEC_RESIDUAL = 2, /* residual r                                          */
+    DMX_VEC_DELTA = 3,    /* deltaU, the linear-solve unknown                    */
+    DMX_VEC_ULAST = 4,    /* uLastIter (newtonsolver.hh:985)                     */
+    DMX_VEC_WORK0 = 5,    /* scratch for tests / SpMV input                      */
+    DMX_VEC_WORK1 = 6
+};
+
+/* Runtime parameters that change arithmetic (dumux/common/parameters.cc:231-260, assembly/numericepsilon.hh:37-53) */
+typedef struct {
+    int    enable_gravity;       /* Problem.EnableGravity (default 1)                                       */
+    double gravity;              /* 9.81, along -e_{dim-1} (common/fvspatialparams.hh:48-52)                */
+    double upwind_weight;        /* Flux.UpwindWeight (default 1.0; flux/upwindscheme.hh:42)                */
+    int    fd_method;            /* Assembly.NumericDifferenceMethod: 1 forward, 0 central, -1 backward, 5  */
+    double base_eps;             /* Assembly.NumericDifference.BaseEpsilon (default 1e-10)                  */
+    double privar_magnitude[2];  /* Assembly.NumericDifference.PriVarMagnitude (<=0: unset)                 */
+    int    stationary;           /* FVAssembler stationary ctor (fvassembler.hh:131): no storage term       */
+    double dt;                   /* timeLoop->timeStepSize() used by the storage term                       */
+    double extrusion;            /* constant extrusion factor                                               */
+} dmx_options;
+
+/* Newton parameters (dumux/nonlinear/newtonsolver.hh:1213-1247) + linear solver (linearsolverparameters.hh:56-73) */
+typedef struct {
+    double max_relative_shift;   /* Newton.MaxRelativeShift 1e-8 */
+    int    min_steps;            /* Newton.MinSteps 2            */
+    int    max_steps;            /* Newton.MaxSteps 18           */
+    double lin_reduction;        /* LinearSolver.ResidualReduction 1e-6 (newtonsolver.hh:232) */
+    int    lin_maxit;            /* LinearSolver.MaxIterations 250 */
+    int    preconditioner;       /* DMX_PRECOND_* */
+} dmx_newton_params;
+
+typedef struct {
+    int    newton_iterations;
+    int    converged;
+    int    linear_iterations_total;
+    double last_shift;
+    double t_assemble, t_solve, t_update;   /* seconds, CUDA-event timed; buckets of newtonsolver.hh:950-955 */
+    int    linear_iterations[64];
+    double shifts[64];
+} dmx_newton_report;
+
+/* ---- lifetime ------------------------------------------------------------------------------------------ */
+void dmx_default_options(dmx_options* o);
+void dmx_default_newton_params(dmx_newton_params* p);
+int  dmx_create(dmx_ctx** out, int device);
+/* One ctx per rank of a slab-decomposed run; nccl_unique_id = the 128-byte ncclUniqueId from rank 0.
+   Replaces the MPI communicator DuMux gets from Dune::MPIHelper / gridView.comm() (linear/istlsolvers.hh:192). */
+int  dmx_create_distributed(dmx_ctx** out, int device, const void* nccl_unique_id, int rank, int nranks);
+int  dmx_get_nccl_unique_id(void* out128);
+int  dmx_destroy(dmx_ctx* ctx);
+const char* dmx_last_error(const dmx_ctx* ctx);
+const char* dmx_version(void);
+
+/* ---- grid + pattern (GridManager<YaspGrid>, io/grid/gridmanager_yasp.hh:84-135; CCTpfaFVGridGeometry::update_,
+        discretization/cellcentered/tpfa/fvgridgeometry.hh:216-345; getJacobianPattern, assembly/jacobianpattern.hh:27-52) ---- */
+/* cells/lower/upper describe the GLOBAL grid.  In a distributed ctx the grid is slab-decomposed along the last
+   axis (Grid.Partitioning "1 1 P") with overlap 1 (Grid.Overlap default, gridmanager_yasp.hh:129). */
+int  dmx_grid_structured(dmx_ctx* ctx, int model, int dim, const int* cells, const double* lower, const double* upper);
+int  dmx_grid_tensor(dmx_ctx* ctx, int model, int dim, const int* cells, const double* x, const double* y, const double* z);
+/* local box (incl. overlap) of this rank: cells[3], offset[3] in the global index space; owned range of the split axis */
+int  dmx_local_box(const dmx_ctx* ctx, int* cells, int* offset, int* owned_begin, int* owned_end);
+int  dmx_num_cells(const dmx_ctx* ctx);
+int  dmx_num_eq(const dmx_ctx* ctx);
+long long dmx_nnz_blocks(const dmx_ctx* ctx);
+int  dmx_pattern(const dmx_ctx* ctx, int* rowptr, int* colidx);
+/* generic BCRS pattern instead of a grid (the ILUBiCGSTABIstlSolver::solve(A,x,b) entry, linear/istlsolvers.hh:273) */
+int  dmx_bcrs_pattern(dmx_ctx* ctx, int n, int b, const int* rowptr, const int* colidx);
+
+/* ---- Problem / SpatialParams sampled into flat arrays (common/fvproblem.hh:126-283,
+        porousmediumflow/fvspatialparams.hh:83-99, common/fvporousmediumspatialparams.hh:75-118).  LOCAL arrays. ---- */
+int  dmx_set_options(dmx_ctx* ctx, const dmx_options* o);
+int  dmx_set_cell_fields(dmx_ctx* ctx, const double* permeability, const double* porosity, const int* region);
+int  dmx_set_source(dmx_ctx* ctx, const double* q);
+/* BC: params {pcEntry, lambda}, reg {pcLowSwe}; VG: params {alpha, n, l}, reg {pcLowSwe, pcHighSwe, krnLowSwe, krwHighSwe} */
+int  dmx_set_material(dmx_ctx* ctx, int region, int law, const double* params, double swr, double snr,
+                      int regularize, const double* reg);
+int  dmx_set_fluids(dmx_ctx* ctx, const double* density, const double* viscosity);
+int  dmx_set_fluid_table(dmx_ctx* ctx, int nT, int nP, double Tmin, double Tmax, const double* pmin, const double* pmax,
+                         const double* density, const double* viscosity, double temperature);
+int  dmx_side_faces(const dmx_ctx* ctx, int side);
+int  dmx_set_boundary(dmx_ctx* ctx, int side, const int* type, const double* values);
+
+/* ---- device-resident vectors ---------------------------------------------------------------------------- */
+int  dmx_vec_upload(dmx_ctx* ctx, int vec, const double* host);
+int  dmx_vec_download(dmx_ctx* ctx, int vec, double* host);
+int  dmx_vec_copy(dmx_ctx* ctx, int dst, int src);
+int  dmx_jacobian_upload(dmx_ctx* ctx, const double* values);
+int  dmx_jacobian_download(dmx_ctx* ctx, double* values);
+void* dmx_vec_device_ptr(dmx_ctx* ctx, int vec);
+void* dmx_jacobian_device_ptr(dmx_ctx* ctx);
+
+/* ---- hot path -------------------------------------------------------------------------------------------- */
+/* FVAssembler::assembleJacobianAndResidual / assembleResidual (assembly/fvassembler.hh:179-207,240-267):
+   reads CUR (+PREV), writes RESIDUAL (+ Jacobian values).  Returns DMX_STATUS_NONFINITE if the residual is not finite. */
+int  dmx_assemble(dmx_ctx* ctx, int with_jacobian);
+/* host-buffer form (the call a DuMux main makes): uploads curSol (+prevSol), assembles, downloads what is non-NULL */
+int  dmx_assemble_host(dmx_ctx* ctx, const double* cur, const double* prev, double* residual, double* jacobian);
+/* IstlIterativeLinearSolver::solve(A, x, b) (linear/istlsolvers.hh:273,457-464): fresh preconditioner + BiCGSTAB,
+   Jacobian * DELTA = RESIDUAL, DELTA zeroed first (newtonsolver.hh:1032). */
+int  dmx_linear_solve(dmx_ctx* ctx, double reduction, int maxit, int preconditioner, int* iterations, double* achieved_reduction);
+/* host-buffer form: A values, x (in: initial guess, out: solution), b */
+int  dmx_linear_solve_host(dmx_ctx* ctx, const double* values, double* x, const double* b, double reduction, int maxit,
+                           int preconditioner, int* iterations, double* achieved_reduction);
+/* IstlIterativeLinearSolver::norm (linear/istlsolvers.hh:306-337): owner-masked 2-norm, all-reduced */
+int  dmx_norm2(dmx_ctx* ctx, int vec, double* out);
+/* NewtonSolver::newtonUpdate + newtonComputeShift_ (nonlinear/newtonsolver.hh:543-557,1138-1144):
+   CUR = ULAST - DELTA; shift = max relative shift (all-reduced max) */
+int  dmx_newton_update(dmx_ctx* ctx, double* shift);
+/* NewtonSolver::solveImpl_ (nonlinear/newtonsolver.hh:976-1072) on the device-resident state */
+int  dmx_newton_solve(dmx_ctx* ctx, const dmx_newton_params* params, dmx_newton_report* report);
+/* host-buffer Newton solve: uploads u and prev, solves, downloads u */
+int  dmx_newton_solve_host(dmx_ctx* ctx, double* u, const double* prev, const dmx_newton_params* params, dmx_newton_report* report);
+/* one Newton iteration (assemble + solve + update) on device state; used by bench.py */
+int  dmx_newton_step(dmx_ctx* ctx, const dmx_newton_params* params, int* linear_iterations, double* shift, float* ms_assemble,
+                     float* ms_solve, float* ms_update);
+/* gridVariables->advanceTimeStep(): PREV = CUR;  resetTimeStep: CUR = PREV (discretization/fvgridvariables.hh:99-117) */
+int  dmx_advance_timestep(dmx_ctx* ctx);
+int  dmx_reset_timestep(dmx_ctx* ctx);
+
+/* ---- kernel-level entry points (parity tests and roofline measurement) ----------------------------------- */
+int  dmx_spmv(dmx_ctx* ctx, int x_vec, int y_vec);                       /* y = J x (BCRSMatrix::mv) */
+int  dmx_ilu0_factor(dmx_ctx* ctx);                                      /* ILU copy of J, in place */
+int  dmx_ilu0_apply(dmx_ctx* ctx, int d_vec, int v_vec);                 /* v = (LU)^-1 d */
+int  dmx_ilu0_download(dmx_ctx* ctx, double* values);
+int  dmx_dot(dmx_ctx* ctx, int a_vec, int b_vec, double* out);
+int  dmx_halo_exchange(dmx_ctx* ctx, int vec);                           /* copyOwnerToAll */
+/* average device time in ms of `reps` back-to-back launches of one kernel, CUDA-event timed on the ctx stream.
+   which: 0 assembly (residual+Jacobian), 1 SpMV, 2 ILU0 apply, 3 ILU0 factor, 4 secondary-variable pass only */
+int  dmx_time_kernel(dmx_ctx* ctx, int which, int reps, float* ms_avg);
+int  dmx_kernel_launch_count(const dmx_ctx* ctx, long long* launches);
+int  dmx_synchronize(dmx_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,132 @@
+"""GPU parity of the Krylov path (SpMV, block ILU0, BiCGSTAB) against the dune-istl restatement in the oracle.
+
+SpMV and ILU0 execute the same per-row operation order as the sequential CPU code (no FMA contraction), so they
+are compared bit for bit.  Dot products use a fixed-shape tree reduction, so BiCGSTAB iterates differ from the
+sequential sums in the last bits: solutions are compared at the solver tolerance and iteration counts exactly.
+"""
+import numpy as np
+import pytest
+
+from dumux_b200 import problems
+from dumux_b200 import binding as B
+from oracle import oracle_py as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _system(spec, seed=0):
+    o = O.Oracle(spec)
+    rng = np.random.RandomState(seed)
+    cur = spec.initial.copy()
+    cur[:, 0] += rng.uniform(-100, 100, size=cur.shape[0])
+    if spec.num_eq == 2:
+        cur[:, 1] = rng.uniform(0, 0.3, size=cur.shape[0])
+    res, jac = o.assemble(cur, spec.initial)
+    return o, res, jac
+
+
+@pytest.mark.parametrize("spec", [problems.onep_incompressible((30, 20)), problems.twop_lens((24, 16), law="vg"),
+                                  problems.twop_lens((12, 10, 8), law="bc", heterogeneity_sigma=0.5)],
+                         ids=["1p2d", "2p2d", "2p3d"])
+def test_spmv_bit_exact(engine_factory, spec):
+    o, res, jac = _system(spec)
+    e = engine_factory(spec)
+    x = np.random.RandomState(1).standard_normal(o.n * o.b)
+    e.upload_jacobian(jac)
+    e.upload(B.VEC_WORK0, x)
+    e.spmv(B.VEC_WORK0, B.VEC_WORK1)
+    y = e.download(B.VEC_WORK1)
+    assert np.array_equal(y, O.spmv(o.n, o.b, o.rowptr, o.colidx, jac, x))
+
+
+@pytest.mark.parametrize("spec", [problems.onep_incompressible((30, 20)), problems.twop_lens((24, 16), law="vg"),
+                                  problems.twop_lens((12, 10, 8), law="bc", heterogeneity_sigma=0.5)],
+                         ids=["1p2d", "2p2d", "2p3d"])
+def test_ilu0_bit_exact(engine_factory, spec):
+    o, res, jac = _system(spec)
+    e = engine_factory(spec)
+    e.upload_jacobian(jac)
+    assert e.ilu0_factor() == 0
+    ilu_o, st = O.ilu0_factor(o.n, o.b, o.rowptr, o.colidx, jac)
+    assert st == 0
+    assert np.array_equal(e.ilu0_values(), ilu_o)
+    d = np.random.RandomState(2).standard_normal(o.n * o.b)
+    e.upload(B.VEC_WORK0, d)
+    e.ilu0_apply(B.VEC_WORK0, B.VEC_WORK1)
+    assert np.array_equal(e.download(B.VEC_WORK1), O.ilu0_apply(o.n, o.b, o.rowptr, o.colidx, ilu_o, d))
+
+
+@pytest.mark.parametrize("spec", [problems.onep_incompressible((40, 40)), problems.twop_lens((48, 32), law="vg"),
+                                  problems.twop_lens((16, 12, 10), law="bc", heterogeneity_sigma=0.5)],
+                         ids=["1p2d", "2p2d", "2p3d"])
+def test_ilu_bicgstab_matches_oracle(engine_factory, spec):
+    o, res, jac = _system(spec)
+    e = engine_factory(spec)
+    xo, sto, ito, redo = o.solve(jac, res, reduction=1e-8)
+    xg, stg, itg, redg = e.solve(jac, res, reduction=1e-8)
+    assert sto == 0 and stg == 0
+    assert itg == ito, (itg, ito)
+    # both satisfy ||b - A x|| <= 1e-8 ||b||; compare the solutions at that level
+    assert np.linalg.norm(xg - xo) <= 1e-6 * np.linalg.norm(xo)
+    r = res - O.spmv(o.n, o.b, o.rowptr, o.colidx, jac, xg)
+    assert np.linalg.norm(r) <= 1.01e-8 * np.linalg.norm(res)
+
+
+def test_generic_bcrs_2x2_laplacian(engine_factory):
+    """test/linear/test_linearsolver.cc: 2x2-block Laplacian (dune-istl setupLaplacian), asserts convergence."""
+    N = 20
+    n = N * N
+    rows, cols = [], []
+    for j in range(N):
+        for i in range(N):
+            I = i + N * j
+            nb = [I]
+            if i > 0: nb.append(I - 1)
+            if i < N - 1: nb.append(I + 1)
+            if j > 0: nb.append(I - N)
+            if j < N - 1: nb.append(I + N)
+            for c in sorted(nb):
+                rows.append(I); cols.append(c)
+    rows, cols = np.array(rows), np.array(cols)
+    rowptr = np.zeros(n + 1, dtype=np.int32)
+    np.add.at(rowptr, rows + 1, 1)
+    rowptr = np.cumsum(rowptr).astype(np.int32)
+    vals = np.zeros((len(cols), 2, 2))
+    vals[rows == cols] = 4.0 * np.eye(2)
+    vals[rows != cols] = -1.0 * np.eye(2)
+    e = engine_factory()
+    e.set_bcrs_pattern(n, 2, rowptr, cols.astype(np.int32))
+    b = np.ones(n * 2)
+    for pre in (B.PRECOND_ILU0, B.PRECOND_BLOCKJACOBI):
+        x, st, it, red = e.solve(vals.reshape(-1), b, reduction=1e-13, maxit=250, precond=pre)
+        assert st == 0 and red <= 1e-13
+        r = b - O.spmv(n, 2, rowptr, cols.astype(np.int32), vals.reshape(-1), x)
+        assert np.linalg.norm(r) <= 1e-11 * np.linalg.norm(b)
+
+
+def test_norm_dot_update(engine_factory):
+    spec = problems.twop_lens((24, 16), law="vg")
+    e = engine_factory(spec)
+    rng = np.random.RandomState(3)
+    a, b = rng.standard_normal(e.n * 2), rng.standard_normal(e.n * 2)
+    e.upload(B.VEC_WORK0, a)
+    e.upload(B.VEC_WORK1, b)
+    assert abs(e.dot(B.VEC_WORK0, B.VEC_WORK1) - float(a @ b)) <= 1e-12 * np.linalg.norm(a) * np.linalg.norm(b)
+    assert abs(e.norm(B.VEC_WORK0) - np.linalg.norm(a)) <= 1e-13 * np.linalg.norm(a)
+    u_last = spec.initial.reshape(-1) + rng.standard_normal(e.n * 2)
+    e.upload(B.VEC_ULAST, u_last)
+    e.upload(B.VEC_DELTA, a)
+    shift = e.newton_update()
+    u = e.download(B.VEC_CUR)
+    assert np.array_equal(u, u_last + (-1.0) * a)
+    assert shift == O.lib().orc_max_relative_shift(u.size, u, np.ascontiguousarray(u_last))
+
+
+def test_singular_block_reports_breakdown(engine_factory):
+    spec = problems.onep_incompressible((6, 6))
+    o, res, jac = _system(spec)
+    jac = jac.copy()
+    jac[o.rowptr[0] + 0] = 0.0   # first diagonal entry
+    e = engine_factory(spec)
+    e.upload_jacobian(jac)
+    assert e.ilu0_factor() == B.STATUS_BREAKDOWN

@@ -1,0 +1,80 @@
+"""GPU parity of the whole Newton step / time loop against the oracle and the reference's golden fields.
+
+Bar (north_star): same Newton iteration count, final pressure and saturation fields to a relative L2 error of 1e-8.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from dumux_b200 import problems
+from dumux_b200 import binding as B
+from oracle.oracle_py import Oracle
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _rel_l2(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def test_1p_incompressible_golden(engine_factory):
+    """test_1p_incompressible_tpfa_numdiff: one assembly + one solve (main.cc:150-161) vs test_1p_cc-reference.vtu"""
+    spec = problems.onep_incompressible((10, 10))
+    e = engine_factory(spec)
+    x = spec.initial.reshape(-1).copy()
+    res, jac = e.assemble(x, None)
+    dx, st, its, red = e.solve(jac, res, reduction=1e-13)
+    assert st == 0
+    x -= dx
+    g = np.load(os.path.join(GOLDEN, "test_1p_cc.npz"))["p"].astype(np.float64)
+    assert np.abs(x - g).max() <= 1e-2 * np.abs(g).max() and np.abs((x - g) / g).max() < 2e-5
+    o = Oracle(spec)
+    ro, jo = o.assemble(spec.initial.reshape(-1))
+    dxo, *_ = o.solve(jo, ro, reduction=1e-13)
+    assert _rel_l2(x, spec.initial.reshape(-1) - dxo) <= 1e-8
+
+
+@pytest.mark.parametrize("cells,law", [((48, 32), "vg"), ((20, 12, 10), "bc")])
+def test_newton_step_matches_oracle(engine_factory, cells, law):
+    spec = problems.twop_lens(cells, law=law, heterogeneity_sigma=0.3 if len(cells) == 3 else 0.0)
+    o = Oracle(spec)
+    uo, sto, repo = o.newton(spec.initial, spec.initial)
+    e = engine_factory(spec)
+    ug, stg, repg = e.newton(spec.initial, spec.initial)
+    assert sto == 0 and stg == 0
+    assert repg.newton_iterations == repo.newton_iterations
+    uo2, ug2 = uo.reshape(-1, 2), ug.reshape(-1, 2)
+    assert _rel_l2(ug2[:, 0], uo2[:, 0]) <= 1e-8
+    assert np.linalg.norm(ug2[:, 1] - uo2[:, 1]) <= 1e-8 * max(1.0, np.linalg.norm(uo2[:, 1]))
+
+
+def test_2p_lens_timeloop_golden(engine_factory):
+    """test_2p_incompressible_tpfa: t_end = 3000 s, dt0 = 250 s, vs test_2p_incompressible_cc-reference.vtu and the oracle."""
+    spec = problems.twop_lens((48, 32), law="vg")
+    o = Oracle(spec)
+    uo, nso, itso, dtso = o.run_timeloop(spec.initial, 3000.0, 250.0)
+    e = engine_factory(spec)
+    ug, itsg, dtsg = e.run_timeloop(spec.initial, 3000.0, 250.0)
+    assert list(itsg) == list(itso), (itsg, itso)
+    assert np.allclose(dtsg, dtso, rtol=0, atol=0)
+    uo2, ug2 = uo.reshape(-1, 2), ug.reshape(-1, 2)
+    assert _rel_l2(ug2[:, 0], uo2[:, 0]) <= 1e-8
+    assert _rel_l2(ug2[:, 1], uo2[:, 1]) <= 1e-8
+    g = np.load(os.path.join(GOLDEN, "test_2p_incompressible_cc.npz"))
+    for name, col in (("p_aq", 0), ("S_napl", 1)):
+        ref = g[name].astype(np.float64)
+        d = np.abs(ug2[:, col] - ref)
+        assert np.all((d <= 1.5e-7) | (d <= 1e-2 * np.abs(ref))), name
+
+
+def test_block_jacobi_newton_same_count(engine_factory):
+    """A different preconditioner changes BiCGSTAB counts but must not change the Newton count or the fields."""
+    spec = problems.twop_lens((24, 16), law="bc")
+    e = engine_factory(spec)
+    u1, st1, rep1 = e.newton(spec.initial, spec.initial)
+    u2, st2, rep2 = e.newton(spec.initial, spec.initial, preconditioner=B.PRECOND_BLOCKJACOBI, lin_maxit=2000)
+    assert st1 == 0 and st2 == 0
+    assert rep1.newton_iterations == rep2.newton_iterations
+    assert _rel_l2(u2.reshape(-1, 2)[:, 0], u1.reshape(-1, 2)[:, 0]) <= 1e-8
