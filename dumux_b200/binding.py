@@ -29,8 +29,10 @@ EXPORTS = [
     "dmx_linear_solve", "dmx_linear_solve_host", "dmx_norm2", "dmx_newton_update", "dmx_newton_solve",
     "dmx_newton_solve_host", "dmx_newton_step", "dmx_advance_timestep", "dmx_reset_timestep", "dmx_spmv",
     "dmx_ilu0_factor", "dmx_ilu0_apply", "dmx_ilu0_download", "dmx_dot", "dmx_halo_exchange", "dmx_time_kernel",
-    "dmx_kernel_launch_count", "dmx_synchronize",
+    "dmx_kernel_launch_count", "dmx_synchronize", "dmx_profile", "dmx_profile_read",
+    "dmx_newton_step_host", "dmx_timer_start", "dmx_timer_stop",
 ]
+K_ASSEMBLY, K_SPMV, K_ILU_APPLY, K_ILU_FACTOR, K_VOLVARS, K_BLAS1, K_HALO, K_JACOBI = range(8)
 
 
 class DmxOptions(C.Structure):
@@ -125,6 +127,11 @@ def load_library():
     L.dmx_time_kernel.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_float)]
     L.dmx_kernel_launch_count.argtypes = [vp, C.POINTER(C.c_longlong)]
     L.dmx_synchronize.argtypes = [vp]
+    L.dmx_newton_step_host.argtypes = [vp, C.c_void_p, C.POINTER(DmxNewtonParams), C.POINTER(C.c_int), C.POINTER(C.c_double)]
+    L.dmx_timer_start.argtypes = [vp]
+    L.dmx_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
+    L.dmx_profile.argtypes = [vp, C.c_int]
+    L.dmx_profile_read.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
     _lib = L
     return L
 
@@ -202,6 +209,11 @@ class Engine:
         ob, oe = C.c_int(0), C.c_int(0)
         L.dmx_local_box(self.h, lc, off, C.byref(ob), C.byref(oe))
         self.local_cells, self.offset, self.own_begin, self.own_end = lc, off, ob.value, oe.value
+        if getattr(spec, "slab", None) is not None:
+            sa = spec.dim - 1
+            if (int(off[sa]), int(off[sa] + lc[sa])) != tuple(spec.slab):
+                raise DmxError(f"slab-local spec covers layers {spec.slab}, this rank holds "
+                               f"{(int(off[sa]), int(off[sa] + lc[sa]))}")
         o = spec.options
         self.opt.enable_gravity = int(o.enable_gravity)
         self.opt.gravity = o.gravity
@@ -236,7 +248,7 @@ class Engine:
     def localize_cells(self, a):
         """Cut the local slab (incl. overlap) out of a global per-cell array (x fastest)."""
         a = np.asarray(a)
-        if self.nranks == 1:
+        if self.nranks == 1 or getattr(self.spec, "slab", None) is not None:
             return np.ascontiguousarray(a)
         gc = self.spec.cells3
         sa = self.spec.dim - 1
@@ -250,7 +262,7 @@ class Engine:
     def localize_side(self, side, t, v):
         t = np.asarray(t, dtype=np.int32)
         v = np.asarray(v, dtype=np.float64)
-        if self.nranks == 1:
+        if self.nranks == 1 or getattr(self.spec, "slab", None) is not None:
             return np.ascontiguousarray(t), np.ascontiguousarray(v)
         gc = self.spec.cells3
         sa = self.spec.dim - 1
@@ -371,6 +383,21 @@ class Engine:
                                                 C.byref(s), C.byref(u)), allow_status=True)
         return st, its.value, shift.value, a.value, s.value, u.value
 
+    def newton_step_host(self, u, params):
+        """One Newton iteration with a HOST solution vector (numpy or pinned torch tensor), updated in place."""
+        its, shift = C.c_int(0), C.c_double(0)
+        st = self._check(self.L.dmx_newton_step_host(self.h, _hostptr(u), C.byref(params), C.byref(its), C.byref(shift)),
+                         allow_status=True)
+        return st, its.value, shift.value
+
+    def timer_start(self):
+        self._check(self.L.dmx_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_float(0)
+        self._check(self.L.dmx_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
     def newton_update(self):
         out = C.c_double(0)
         self._check(self.L.dmx_newton_update(self.h, C.byref(out)))
@@ -412,6 +439,15 @@ class Engine:
         out = C.c_longlong(0)
         self.L.dmx_kernel_launch_count(self.h, C.byref(out))
         return out.value
+
+    def profile(self, enable=True):
+        self._check(self.L.dmx_profile(self.h, int(enable)))
+
+    def profile_read(self, kclass):
+        """(device ms accumulated, timed units) of one K_* kernel class since profile(True)."""
+        ms, n = C.c_double(0), C.c_longlong(0)
+        self._check(self.L.dmx_profile_read(self.h, kclass, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
 
     def synchronize(self):
         self._check(self.L.dmx_synchronize(self.h))

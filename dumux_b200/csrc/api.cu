@@ -258,6 +258,8 @@ int dmx_destroy(dmx_ctx* ctx)
     if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
     if (ctx->h_flag) cudaFreeHost(ctx->h_flag);
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
+    for (auto& r : ctx->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (auto& e : ctx->prof_pool) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return 0;
@@ -483,6 +485,28 @@ int dmx_kernel_launch_count(const dmx_ctx* ctx, long long* launches)
     return 0;
 }
 
+int dmx_profile(dmx_ctx* ctx, int enable)
+{
+    DMX_CUDA(cudaSetDevice(ctx->device));
+    DMX_CUDA(cudaStreamSynchronize(ctx->stream));
+    prof_drain(ctx);
+    if (enable) {
+        for (int k = 0; k < DMX_NUM_KCLASS; ++k) { ctx->prof_ms[k] = 0.0; ctx->prof_n[k] = 0; }
+    }
+    ctx->prof_on = enable != 0;
+    return 0;
+}
+int dmx_profile_read(dmx_ctx* ctx, int kclass, double* ms_total, long long* units)
+{
+    if (kclass < 0 || kclass >= DMX_NUM_KCLASS) return fail(ctx, DMX_ERR_USAGE, "unknown kernel class");
+    DMX_CUDA(cudaSetDevice(ctx->device));
+    DMX_CUDA(cudaStreamSynchronize(ctx->stream));
+    prof_drain(ctx);
+    *ms_total = ctx->prof_ms[kclass];
+    *units = ctx->prof_n[kclass];
+    return 0;
+}
+
 // ---- hot path ----
 int dmx_assemble(dmx_ctx* ctx, int with_jacobian)
 {
@@ -547,9 +571,9 @@ int dmx_newton_step(dmx_ctx* ctx, const dmx_newton_params* prm, int* linear_iter
 {
     int rc;
     DMX_CUDA(cudaSetDevice(ctx->device));
+    DMX_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
     // uLastIter = current iterate (newtonsolver.hh:985,1000)
     if ((rc = dmx_vec_copy(ctx, DMX_VEC_ULAST, DMX_VEC_CUR))) return rc;
-    DMX_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
     if ((rc = dmx_assemble(ctx, 1))) return rc;
     DMX_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
     DMX_CUDA(cudaMemsetAsync(ctx->d_vec[DMX_VEC_DELTA], 0, (size_t)ctx->n * ctx->b * sizeof(double), ctx->stream));   // deltaU = 0 (:1032)
@@ -567,6 +591,29 @@ int dmx_newton_step(dmx_ctx* ctx, const dmx_newton_params* prm, int* linear_iter
     if (ms_assemble) *ms_assemble = a;
     if (ms_solve) *ms_solve = s;
     if (ms_update) *ms_update = u;
+    return 0;
+}
+
+int dmx_newton_step_host(dmx_ctx* ctx, double* u, const dmx_newton_params* prm, int* linear_iterations, double* shift)
+{
+    int rc;
+    if ((rc = dmx_vec_upload(ctx, DMX_VEC_CUR, u))) return rc;
+    const int st = dmx_newton_step(ctx, prm, linear_iterations, shift, nullptr, nullptr, nullptr);
+    if (st) return st;
+    return dmx_vec_download(ctx, DMX_VEC_CUR, u);
+}
+int dmx_timer_start(dmx_ctx* ctx)
+{
+    DMX_CUDA(cudaSetDevice(ctx->device));
+    DMX_CUDA(cudaEventRecord(ctx->ev[4], ctx->stream));
+    return 0;
+}
+int dmx_timer_stop(dmx_ctx* ctx, float* ms)
+{
+    DMX_CUDA(cudaSetDevice(ctx->device));
+    DMX_CUDA(cudaEventRecord(ctx->ev[5], ctx->stream));
+    DMX_CUDA(cudaEventSynchronize(ctx->ev[5]));
+    DMX_CUDA(cudaEventElapsedTime(ms, ctx->ev[4], ctx->ev[5]));
     return 0;
 }
 

@@ -647,10 +647,12 @@ static int launch_nd(dmx_ctx* ctx, const AsmParams& P, bool with_jac, bool volva
 #define DMX_LAUNCH_ND(ND)                                                                                    \
     do {                                                                                                     \
         if (needRec) {                                                                                       \
+            ProfScope ps__(ctx, DMX_K_VOLVARS);                                                              \
             volvars_kernel<MODEL, ND><<<(n + vt - 1) / vt, vt, 0, ctx->stream>>>(P);                         \
             DMX_CHECK_LAUNCH();                                                                              \
         }                                                                                                    \
         if (!volvars_only) {                                                                                 \
+            ProfScope ps__(ctx, DMX_K_ASSEMBLY);                                                             \
             assemble_kernel<MODEL, TABLE, ND><<<(n + at - 1) / at, at, 0, ctx->stream>>>(P, with_jac ? 1 : 0); \
             DMX_CHECK_LAUNCH();                                                                              \
         }                                                                                                    \

@@ -11,6 +11,7 @@
 
 #define DMX_NUM_VECS 7
 #define DMX_MAX_REGIONS 8
+#define DMX_NUM_KCLASS 8
 #define DMX_ERR_CUDA (-1)
 #define DMX_ERR_USAGE (-2)
 #define DMX_ERR_NCCL (-3)
@@ -138,7 +139,15 @@ struct dmx_ctx {
     // halo (distributed)
     double *d_send_lo = nullptr, *d_send_hi = nullptr, *d_recv_lo = nullptr, *d_recv_hi = nullptr;
 
-    cudaEvent_t ev[4] = {};
+    cudaEvent_t ev[6] = {};
+
+    // per-kernel-class device timers (dmx_profile_*): CUDA-event pairs recorded on the ctx stream around the launches
+    bool prof_on = false;
+    struct ProfRec { int cls; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof_pending;
+    std::vector<cudaEvent_t> prof_pool;
+    double prof_ms[DMX_NUM_KCLASS] = {};
+    long long prof_n[DMX_NUM_KCLASS] = {};
 };
 
 namespace dmx {
@@ -163,6 +172,44 @@ inline int fail(dmx_ctx* c, int code, const std::string& msg)
         if (e__ != cudaSuccess)                                                                     \
             return dmx::fail(ctx, DMX_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e__)); \
     } while (0)
+
+// Times everything launched on the ctx stream during its lifetime as one unit of kernel class `cls` (no-op unless
+// dmx_profile(ctx, 1)).  Events are resolved by prof_drain() at a point where the stream is known to be idle.
+struct ProfScope {
+    dmx_ctx* c;
+    int cls;
+    cudaEvent_t a = nullptr, b = nullptr;
+    static cudaEvent_t get(dmx_ctx* c)
+    {
+        cudaEvent_t e = nullptr;
+        if (!c->prof_pool.empty()) { e = c->prof_pool.back(); c->prof_pool.pop_back(); }
+        else cudaEventCreate(&e);
+        return e;
+    }
+    ProfScope(dmx_ctx* ctx, int k) : c(ctx), cls(k)
+    {
+        if (!c->prof_on) return;
+        a = get(c); b = get(c);
+        cudaEventRecord(a, c->stream);
+    }
+    ~ProfScope()
+    {
+        if (!a) return;
+        cudaEventRecord(b, c->stream);
+        c->prof_pending.push_back({cls, a, b});
+    }
+};
+// call only right after a stream synchronisation
+inline void prof_drain(dmx_ctx* c)
+{
+    for (auto& r : c->prof_pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { c->prof_ms[r.cls] += ms; c->prof_n[r.cls]++; }
+        c->prof_pool.push_back(r.a);
+        c->prof_pool.push_back(r.b);
+    }
+    c->prof_pending.clear();
+}
 
 // implemented in assembly.cu
 int prepare(dmx_ctx* ctx);

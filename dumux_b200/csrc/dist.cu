@@ -132,6 +132,7 @@ int nccl_destroy(dmx_ctx* ctx)
 int halo_exchange(dmx_ctx* ctx, double* v)
 {
     if (ctx->nranks == 1) return 0;
+    ProfScope ps(ctx, DMX_K_HALO);
     ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
     const int sa = ctx->split_axis;
     const int nx = ctx->nc[0], ny = ctx->nc[1], nz = ctx->nc[2], b = ctx->b;

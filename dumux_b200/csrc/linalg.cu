@@ -51,6 +51,7 @@ __global__ void __launch_bounds__(256) bcrs_spmv_kernel(int n, const int* __rest
 
 int launch_spmv(dmx_ctx* ctx, const double* x, double* y)
 {
+    ProfScope ps(ctx, DMX_K_SPMV);
     const long long threads = (long long)ctx->n * ctx->b;
     const int bs = 256;
     const int grid = (int)((threads + bs - 1) / bs);
@@ -200,6 +201,7 @@ static int reduce_to_host(dmx_ctx* ctx, int nq, bool max, double* out)
     }
     DMX_CUDA(cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, nq * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     DMX_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->prof_pending.size() > 512) prof_drain(ctx);
     for (int q = 0; q < nq; ++q) out[q] = ctx->h_scalars[q];
     return 0;
 }
@@ -207,6 +209,7 @@ static int reduce_to_host(dmx_ctx* ctx, int nq, bool max, double* out)
 int dot(dmx_ctx* ctx, const double* a, const double* b, double* out)
 {
     const size_t len = (size_t)ctx->n * ctx->b;
+    ProfScope ps(ctx, DMX_K_BLAS1);
     dot_kernel<1><<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>>(len, ctx->b, a, b, nullptr, nullptr, nullptr, nullptr, ctx->d_owner, ctx->d_partials);
     DMX_CHECK_LAUNCH();
     return reduce_to_host(ctx, 1, false, out);
@@ -214,6 +217,7 @@ int dot(dmx_ctx* ctx, const double* a, const double* b, double* out)
 static int dot2(dmx_ctx* ctx, const double* a0, const double* b0, const double* a1, const double* b1, double* out)
 {
     const size_t len = (size_t)ctx->n * ctx->b;
+    ProfScope ps(ctx, DMX_K_BLAS1);
     dot_kernel<2><<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>>(len, ctx->b, a0, b0, a1, b1, nullptr, nullptr, ctx->d_owner, ctx->d_partials);
     DMX_CHECK_LAUNCH();
     return reduce_to_host(ctx, 2, false, out);
@@ -222,6 +226,7 @@ static int dot2(dmx_ctx* ctx, const double* a0, const double* b0, const double* 
 int newton_update(dmx_ctx* ctx, double* shift)
 {
     const size_t len = (size_t)ctx->n * ctx->b;
+    ProfScope ps(ctx, DMX_K_BLAS1);
     newton_update_kernel<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>>(len, ctx->b, ctx->d_vec[DMX_VEC_ULAST], ctx->d_vec[DMX_VEC_DELTA],
                                                                       ctx->d_vec[DMX_VEC_CUR], ctx->d_owner, ctx->d_partials);
     DMX_CHECK_LAUNCH();
@@ -488,6 +493,7 @@ static int coop_launch(dmx_ctx* ctx, void (*kernel)(Args...), int threads, Args.
 
 int ilu0_factor(dmx_ctx* ctx)
 {
+    ProfScope ps(ctx, DMX_K_ILU_FACTOR);
     const size_t bytes = (size_t)ctx->nnzb * ctx->b * ctx->b * sizeof(double);
     if (!ctx->d_ilu) DMX_CUDA(cudaMalloc((void**)&ctx->d_ilu, bytes));
     DMX_CUDA(cudaMemcpyAsync(ctx->d_ilu, ctx->d_J, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -510,6 +516,7 @@ int ilu0_factor(dmx_ctx* ctx)
 
 int ilu0_apply(dmx_ctx* ctx, const double* d, double* v)
 {
+    ProfScope ps(ctx, DMX_K_ILU_APPLY);
     const int nl = (int)ctx->l_ptr.size() - 1, nu = (int)ctx->u_ptr.size() - 1;
     int rc;
     if (ctx->b == 2) {
@@ -571,6 +578,7 @@ int block_jacobi_setup(dmx_ctx* ctx)
 }
 int block_jacobi_apply(dmx_ctx* ctx, const double* d, double* v)
 {
+    ProfScope ps(ctx, DMX_K_JACOBI);
     const int grid = (ctx->n + 255) / 256;
     if (ctx->b == 2) jacobi_apply_kernel<2><<<grid, 256, 0, ctx->stream>>>(ctx->n, ctx->d_dinv, d, v);
     else jacobi_apply_kernel<1><<<grid, 256, 0, ctx->stream>>>(ctx->n, ctx->d_dinv, d, v);
@@ -609,8 +617,11 @@ int bicgstab(dmx_ctx* ctx, double reduction, int maxit, int precond, int* iterat
 
     if (ctx->nranks > 1 && (rc = halo_exchange(ctx, x))) return rc;       // BlockPreconditioner::pre: copyOwnerToAll(x)
     if ((rc = launch_spmv(ctx, x, t))) return rc;
-    residual_init_kernel<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>>(len, ctx->b, rhs, t, r, rt, ctx->d_owner, ctx->d_partials);
-    DMX_CHECK_LAUNCH();
+    {
+        ProfScope ps(ctx, DMX_K_BLAS1);
+        residual_init_kernel<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>>(len, ctx->b, rhs, t, r, rt, ctx->d_owner, ctx->d_partials);
+        DMX_CHECK_LAUNCH();
+    }
     double s[3];
     if ((rc = reduce_to_host(ctx, 1, false, s))) return rc;
     const double norm0 = std::sqrt(s[0]);
@@ -632,6 +643,7 @@ int bicgstab(dmx_ctx* ctx, double reduction, int maxit, int precond, int* iterat
             DMX_CUDA(cudaMemcpyAsync(p, r, len * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
         else {
             beta = (rho_new / rho) * (alpha / omega);
+            ProfScope ps(ctx, DMX_K_BLAS1);
             p_update_kernel<<<RED_BLOCKS, 256, 0, ctx->stream>>>(len, beta, omega, r, v, p);
             DMX_CHECK_LAUNCH();
         }
@@ -640,8 +652,11 @@ int bicgstab(dmx_ctx* ctx, double reduction, int maxit, int precond, int* iterat
         if ((rc = dot(ctx, rt, v, &h))) return rc;
         if (std::fabs(h) < EPSILON) { status = DMX_STATUS_BREAKDOWN; break; }
         alpha = rho_new / h;
-        axpy2_norm_kernel<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>>(len, ctx->b, alpha, y, v, x, r, ctx->d_owner, ctx->d_partials);
-        DMX_CHECK_LAUNCH();
+        {
+            ProfScope ps(ctx, DMX_K_BLAS1);
+            axpy2_norm_kernel<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>>(len, ctx->b, alpha, y, v, x, r, ctx->d_owner, ctx->d_partials);
+            DMX_CHECK_LAUNCH();
+        }
         if ((rc = reduce_to_host(ctx, 1, false, s))) return rc;
         norm = std::sqrt(s[0]);
         if (!(norm == norm) || std::isinf(norm)) { status = DMX_STATUS_NONFINITE; break; }
@@ -651,8 +666,11 @@ int bicgstab(dmx_ctx* ctx, double reduction, int maxit, int precond, int* iterat
         if ((rc = launch_spmv(ctx, y, t))) return rc;
         if ((rc = dot2(ctx, t, r, t, t, s))) return rc;
         omega = s[0] / s[1];
-        axpy2_norm_kernel<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>>(len, ctx->b, omega, y, t, x, r, ctx->d_owner, ctx->d_partials);
-        DMX_CHECK_LAUNCH();
+        {
+            ProfScope ps(ctx, DMX_K_BLAS1);
+            axpy2_norm_kernel<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>>(len, ctx->b, omega, y, t, x, r, ctx->d_owner, ctx->d_partials);
+            DMX_CHECK_LAUNCH();
+        }
         if ((rc = reduce_to_host(ctx, 1, false, s))) return rc;
         rho = rho_new;
         norm = std::sqrt(s[0]);

@@ -63,6 +63,9 @@ class ProblemSpec:
     initial: np.ndarray                 # float64[n, numEq]
     source: Optional[np.ndarray] = None
     fluid_table: Optional[dict] = None  # tabulated liquid (1p compressible)
+    # slab-local spec (multi-GPU set-up without materialising the global arrays): the per-cell / per-face arrays above
+    # cover only the layers [slab[0], slab[1]) of the last axis (overlap included); cells/lower/upper stay GLOBAL.
+    slab: Optional[Tuple[int, int]] = None
 
     @property
     def num_eq(self) -> int:
@@ -89,21 +92,37 @@ def node_coords(cells, lower, upper):
     return out
 
 
-def cell_centers(cells, lower, upper):
-    """float64[n, dim], x fastest."""
+def slab_partition(n_layers: int, nranks: int, rank: int, overlap: int = 1):
+    """Layers [lo, hi) of the split axis held by `rank` (overlap included) and its owned range [b0, b1): the
+    Yasp-style fixed-size partitioning "1 1 P" with Grid.Overlap 1 (io/grid/gridmanager_yasp.hh:129,194-203) as
+    dmx_grid_structured cuts it."""
+    base, rem = divmod(n_layers, nranks)
+    b0 = rank * base + min(rank, rem)
+    b1 = b0 + base + (1 if rank < rem else 0)
+    if nranks == 1:
+        return 0, n_layers, 0, n_layers
+    return max(0, b0 - overlap), min(n_layers, b1 + overlap), b0, b1
+
+
+def cell_centers(cells, lower, upper, slab=None):
+    """float64[n, dim], x fastest; `slab` = (lo, hi) restricts the last axis to those layers."""
     xs = node_coords(cells, lower, upper)
     ctr = [0.5 * (x[:-1] + x[1:]) for x in xs]
+    if slab is not None:
+        ctr[-1] = ctr[-1][slab[0]:slab[1]]
     grids = np.meshgrid(*ctr, indexing="ij")
     # x fastest: flatten in Fortran order
     return np.stack([g.reshape(-1, order="F") for g in grids], axis=1)
 
 
-def side_face_centers(cells, lower, upper, side):
+def side_face_centers(cells, lower, upper, side, slab=None):
     """float64[nf, dim] centres of the boundary faces of `side` (lower remaining axis fastest)."""
     dim = len(cells)
     a = side // 2
     xs = node_coords(cells, lower, upper)
     ctr = [0.5 * (x[:-1] + x[1:]) for x in xs]
+    if slab is not None and a != dim - 1:
+        ctr[-1] = ctr[-1][slab[0]:slab[1]]
     ctr[a] = np.array([xs[a][-1] if side & 1 else xs[a][0]])
     grids = np.meshgrid(*ctr, indexing="ij")
     return np.stack([g.reshape(-1, order="F") for g in grids], axis=1)[:, :dim]
@@ -178,6 +197,17 @@ def lognormal_permeability(n: int, kmean: float, seed: int = 0, in_lens: Optiona
     return out
 
 
+def plane_lognormal_multiplier(cells, sigma: float, seed: int = 0, slab=None) -> np.ndarray:
+    """exp(N(0, sigma)) per cell with one MT19937 stream per layer of the last axis (seeded seed*1000003 + layer), so
+    that any slab of a slab-decomposed grid can be generated without the global field."""
+    per_layer = int(np.prod(cells[:-1]))
+    lo, hi = (0, cells[-1]) if slab is None else slab
+    out = np.empty((hi - lo, per_layer))
+    for k in range(lo, hi):
+        out[k - lo] = np.exp(np.random.RandomState(seed * 1000003 + k).normal(0.0, sigma, size=per_layer))
+    return out.reshape(-1)
+
+
 def fast_lognormal_multiplier(n: int, sigma: float, seed: int = 0) -> np.ndarray:
     """Vectorised heterogeneity multiplier exp(N(0, sigma)) for the large synthetic grids:
     same generator family (MT19937 seeded with init_genrand(seed)), numpy's normal transform."""
@@ -222,7 +252,9 @@ def onep_incompressible(cells=(10, 10), lower=None, upper=None, numdiff_params=T
 # spatialparams.hh:46-140).  2-D: y vertical.  `vertical_axis` = dim-1 always (gravity acts along -e_{dim-1}).
 # ------------------------------------------------------------------------------------------------------
 def twop_lens(cells=(48, 32), law="vg", lower=None, upper=None, lens_lower=None, lens_upper=None,
-              dt=250.0, heterogeneity_sigma=0.0, seed=0, bc_params=None) -> ProblemSpec:
+              dt=250.0, heterogeneity_sigma=0.0, seed=0, bc_params=None, slab=None, plane_rng=False) -> ProblemSpec:
+    """`slab` = (lo, hi): build only those layers of the last axis (see ProblemSpec.slab); `plane_rng`: per-layer
+    heterogeneity streams (implied by `slab`)."""
     dim = len(cells)
     if dim == 2:
         lower = (0.0, 0.0) if lower is None else lower
@@ -236,12 +268,17 @@ def twop_lens(cells=(48, 32), law="vg", lower=None, upper=None, lens_lower=None,
         lens_lower = (1.0, 1.0, 2.0) if lens_lower is None else lens_lower
         lens_upper = (4.0, 3.0, 3.0) if lens_upper is None else lens_upper
     n = int(np.prod(cells))
+    if slab is not None:
+        n = int(np.prod(cells[:-1])) * (slab[1] - slab[0])
     va = dim - 1
-    ctr = cell_centers(cells, lower, upper)
+    ctr = cell_centers(cells, lower, upper, slab)
     lens = _in_box(ctr, lens_lower, lens_upper, 1.5e-7)
     K = np.where(lens, 9.05e-12, 4.6e-10)
     if heterogeneity_sigma > 0.0:
-        K = K * fast_lognormal_multiplier(n, heterogeneity_sigma, seed)
+        if slab is not None or plane_rng:
+            K = K * plane_lognormal_multiplier(cells, heterogeneity_sigma, seed, slab)
+        else:
+            K = K * fast_lognormal_multiplier(n, heterogeneity_sigma, seed)
     region = lens.astype(np.int32)
     if law == "vg":
         mats = [Material(LAW_VG, (0.0037, 4.7, 0.5), swr=0.05, reg=(0.01, 0.99, 0.1, 0.9)),
@@ -257,7 +294,7 @@ def twop_lens(cells=(48, 32), law="vg", lower=None, upper=None, lens_lower=None,
     bc_type, bc_values = {}, {}
     eps = 1e-6
     for side in range(2 * dim):
-        fc = side_face_centers(cells, lower, upper, side)
+        fc = side_face_centers(cells, lower, upper, side, slab)
         nf = fc.shape[0]
         x, y = fc[:, 0], fc[:, va]
         left = x < lower[0] + eps
@@ -278,7 +315,7 @@ def twop_lens(cells=(48, 32), law="vg", lower=None, upper=None, lens_lower=None,
     return ProblemSpec(
         name=f"2p_lens_{dim}d_{law}", model=MODEL_2P, dim=dim, cells=tuple(cells), lower=tuple(lower), upper=tuple(upper),
         K=K, phi=np.full(n, 0.4), region=region, materials=mats, rho=(1000.0, 1460.0), mu=(1e-3, 5.7e-4),
-        bc_type=bc_type, bc_values=bc_values, options=Options(stationary=False, dt=dt), initial=init)
+        bc_type=bc_type, bc_values=bc_values, options=Options(stationary=False, dt=dt), initial=init, slab=slab)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -299,10 +336,12 @@ def onep_tracer_pressure(cells=(50, 50)) -> ProblemSpec:
         dirichlet = (y < 1e-6) | (y > ymax - 1e-6)
         bc_type[side] = np.where(dirichlet, BC_DIRICHLET, BC_NEUMANN).astype(np.int32)
         vals = np.zeros((fc.shape[0], 1))
-        vals[dirichlet, 0] = 1.0e5 * (2.0 - y[dirichlet])
+        vals[dirichlet, 0] = 1.0e5 * (1.1 - y[dirichlet] * 0.1)       # problem_1p.hh:85-95: 1.1 bar bottom, 1 bar top
         bc_values[side] = vals
+    # The example assembles this LINEAR problem with DiffMethod::analytic (examples/1ptracer/main.cc:112); a large FD
+    # step (the numdiff test's BaseEpsilon 0.1 x PriVarMagnitude 1e5) reproduces the analytic Jacobian to rounding.
     return ProblemSpec(
         name="1ptracer_pressure", model=MODEL_1P, dim=dim, cells=tuple(cells), lower=lower, upper=upper,
         K=K, phi=np.full(n, 0.2), region=np.zeros(n, dtype=np.int32), materials=[],
         rho=(1000.0,), mu=(1e-3,), bc_type=bc_type, bc_values=bc_values,
-        options=Options(stationary=True, enable_gravity=False), initial=np.zeros((n, 1)))
+        options=Options(stationary=True, base_eps=0.1, privar_magnitude=(1e5, -1.0)), initial=np.zeros((n, 1)))

@@ -147,6 +147,9 @@ int  dmx_newton_solve_host(dmx_ctx* ctx, double* u, const double* prev, const dm
 /* one Newton iteration (assemble + solve + update) on device state; used by bench.py */
 int  dmx_newton_step(dmx_ctx* ctx, const dmx_newton_params* params, int* linear_iterations, double* shift, float* ms_assemble,
                      float* ms_solve, float* ms_update);
+/* host-buffer Newton iteration (what one pass of the loop body of NewtonSolver::solveImpl_, newtonsolver.hh:998-1062,
+   costs a DuMux main that keeps curSol on the host): uploads u, assembles, solves, updates, downloads the new u */
+int  dmx_newton_step_host(dmx_ctx* ctx, double* u, const dmx_newton_params* params, int* linear_iterations, double* shift);
 /* gridVariables->advanceTimeStep(): PREV = CUR;  resetTimeStep: CUR = PREV (discretization/fvgridvariables.hh:99-117) */
 int  dmx_advance_timestep(dmx_ctx* ctx);
 int  dmx_reset_timestep(dmx_ctx* ctx);
@@ -162,7 +165,18 @@ int  dmx_halo_exchange(dmx_ctx* ctx, int vec);                           /* copy
    which: 0 assembly (residual+Jacobian), 1 SpMV, 2 ILU0 apply, 3 ILU0 factor, 4 secondary-variable pass only */
 int  dmx_time_kernel(dmx_ctx* ctx, int which, int reps, float* ms_avg);
 int  dmx_kernel_launch_count(const dmx_ctx* ctx, long long* launches);
+/* Per-kernel-class device timers inside the hot path (what Dune::Timer buckets are in newtonsolver.hh:921-955, at
+   kernel granularity): CUDA-event pairs on the ctx stream around every launch of the class while enabled.
+   dmx_profile(ctx, 1) resets and enables, dmx_profile(ctx, 0) disables; dmx_profile_read returns the accumulated
+   device milliseconds and the number of timed units of one DMX_K_* class. */
+enum { DMX_K_ASSEMBLY = 0, DMX_K_SPMV = 1, DMX_K_ILU_APPLY = 2, DMX_K_ILU_FACTOR = 3, DMX_K_VOLVARS = 4, DMX_K_BLAS1 = 5,
+       DMX_K_HALO = 6, DMX_K_JACOBI = 7 };
+int  dmx_profile(dmx_ctx* ctx, int enable);
+int  dmx_profile_read(dmx_ctx* ctx, int kclass, double* ms_total, long long* units);
 int  dmx_synchronize(dmx_ctx* ctx);
+/* device stopwatch on the ctx stream (CUDA events): start records, stop records + waits and returns the milliseconds */
+int  dmx_timer_start(dmx_ctx* ctx);
+int  dmx_timer_stop(dmx_ctx* ctx, float* ms);
 
 #ifdef __cplusplus
 }

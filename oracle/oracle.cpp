@@ -747,13 +747,13 @@ inline void rightMultiply(double* A, const double* B, int b)
     for (int i = 0; i < b * b; ++i) A[i] = C[i];
 }
 // y -= A x  (FieldMatrix::mmv)
-inline void mmv(const double* A, const double* x, double* y, int b)
+__attribute__((always_inline)) inline void mmv(const double* A, const double* x, double* y, int b)
 {
     for (int i = 0; i < b; ++i)
         for (int j = 0; j < b; ++j) y[i] -= A[i * b + j] * x[j];
 }
 // y += A x (umv)
-inline void umv(const double* A, const double* x, double* y, int b)
+__attribute__((always_inline)) inline void umv(const double* A, const double* x, double* y, int b)
 {
     for (int i = 0; i < b; ++i)
         for (int j = 0; j < b; ++j) y[i] += A[i * b + j] * x[j];
@@ -796,9 +796,10 @@ int ilu0Factor(int n, int b, const int* rowptr, const int* colidx, double* A)
 }
 
 // ILU::blockILUBacksolve [DUNE-ext]
-void ilu0Apply(int n, int b, const int* rowptr, const int* colidx, const double* A, double* v, const double* d)
+template <int b>
+void ilu0ApplyT(int n, const int* rowptr, const int* colidx, const double* A, double* v, const double* d)
 {
-    const int bb = b * b;
+    constexpr int bb = b * b;
     for (int i = 0; i < n; ++i) {
         double rhs[2];
         for (int e = 0; e < b; ++e) rhs[e] = d[(size_t)i * b + e];
@@ -819,15 +820,27 @@ void ilu0Apply(int n, int b, const int* rowptr, const int* colidx, const double*
     }
 }
 
-// BCRSMatrix::mv: y = A x, per row sum from 0 in column order
-void spmv(int n, int b, const int* rowptr, const int* colidx, const double* A, const double* x, double* y)
+void ilu0Apply(int n, int b, const int* rowptr, const int* colidx, const double* A, double* v, const double* d)
 {
-    const int bb = b * b;
+    if (b == 1) ilu0ApplyT<1>(n, rowptr, colidx, A, v, d);
+    else ilu0ApplyT<2>(n, rowptr, colidx, A, v, d);
+}
+
+// BCRSMatrix::mv: y = A x, per row sum from 0 in column order
+template <int b>
+void spmvT(int n, const int* rowptr, const int* colidx, const double* A, const double* x, double* y)
+{
+    constexpr int bb = b * b;
     for (int i = 0; i < n; ++i) {
         double acc[2] = {0, 0};
         for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) umv(A + (size_t)k * bb, x + (size_t)colidx[k] * b, acc, b);
         for (int e = 0; e < b; ++e) y[(size_t)i * b + e] = acc[e];
     }
+}
+void spmv(int n, int b, const int* rowptr, const int* colidx, const double* A, const double* x, double* y)
+{
+    if (b == 1) spmvT<1>(n, rowptr, colidx, A, x, y);
+    else spmvT<2>(n, rowptr, colidx, A, x, y);
 }
 double dot(size_t n, const double* a, const double* c)
 {
