@@ -30,7 +30,7 @@ EXPORTS = [
     "dmx_newton_solve_host", "dmx_newton_step", "dmx_advance_timestep", "dmx_reset_timestep", "dmx_spmv",
     "dmx_ilu0_factor", "dmx_ilu0_apply", "dmx_ilu0_download", "dmx_dot", "dmx_halo_exchange", "dmx_time_kernel",
     "dmx_kernel_launch_count", "dmx_synchronize", "dmx_profile", "dmx_profile_read",
-    "dmx_newton_step_host", "dmx_timer_start", "dmx_timer_stop",
+    "dmx_newton_step_host", "dmx_timer_start", "dmx_timer_stop", "dmx_debug_sweep_trace",
 ]
 K_ASSEMBLY, K_SPMV, K_ILU_APPLY, K_ILU_FACTOR, K_VOLVARS, K_BLAS1, K_HALO, K_JACOBI = range(8)
 
@@ -128,6 +128,7 @@ def load_library():
     L.dmx_kernel_launch_count.argtypes = [vp, C.POINTER(C.c_longlong)]
     L.dmx_synchronize.argtypes = [vp]
     L.dmx_newton_step_host.argtypes = [vp, C.c_void_p, C.POINTER(DmxNewtonParams), C.POINTER(C.c_int), C.POINTER(C.c_double)]
+    L.dmx_debug_sweep_trace.argtypes = [vp, C.c_void_p]
     L.dmx_timer_start.argtypes = [vp]
     L.dmx_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
     L.dmx_profile.argtypes = [vp, C.c_int]
@@ -448,6 +449,11 @@ class Engine:
         ms, n = C.c_double(0), C.c_longlong(0)
         self._check(self.L.dmx_profile_read(self.h, kclass, C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+    def sweep_trace(self):
+        out = np.zeros((2, 2, 64, 24), dtype=np.int64)
+        self._check(self.L.dmx_debug_sweep_trace(self.h, out.ctypes.data_as(C.c_void_p)))
+        return out
 
     def synchronize(self):
         self._check(self.L.dmx_synchronize(self.h))

@@ -2,6 +2,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -164,6 +165,13 @@ int finish_grid(dmx_ctx* ctx, int model, int dim, const int* cells, const std::v
     for (int a = 0; a < 3; ++a) if (ctx->d_tij[a]) { cudaFree(ctx->d_tij[a]); ctx->d_tij[a] = nullptr; }
     if (int rc = upload_pattern(ctx)) return rc;
     if (int rc = alloc_vectors(ctx)) return rc;
+    // structured-grid ILU sweeps (DMX_ILU_GENERIC=1 keeps the level-scheduled generic kernels, for A/B runs)
+    sk_free(ctx);
+    {
+        const char* env = getenv("DMX_ILU_GENERIC");
+        if (!(env && env[0] == '1'))
+            if (int rc = sk_setup(ctx)) return rc;
+    }
     // owner mask (distributed): a cell is owner where it is interior (parallelhelpers.hh:485-497)
     if (ctx->d_owner) { cudaFree(ctx->d_owner); ctx->d_owner = nullptr; }
     if (ctx->nranks > 1) {
@@ -244,6 +252,7 @@ int dmx_destroy(dmx_ctx* ctx)
     if (!ctx) return 0;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    sk_free(ctx);
     if (ctx->nccl_comm) nccl_destroy(ctx);
     void* ptrs[] = {ctx->d_geom, ctx->d_K, ctx->d_phi, ctx->d_q, ctx->d_region, ctx->d_tij[0], ctx->d_tij[1], ctx->d_tij[2], ctx->d_laws,
                     ctx->d_tab_buf, ctx->d_rowptr, ctx->d_colidx, ctx->d_diag, ctx->d_J, ctx->d_ilu, ctx->d_rt, ctx->d_p, ctx->d_v, ctx->d_t,
@@ -311,6 +320,7 @@ int dmx_bcrs_pattern(dmx_ctx* ctx, int n, int b, const int* rowptr, const int* c
 {
     if (b != 1 && b != 2) return fail(ctx, DMX_ERR_USAGE, "block size must be 1 or 2");
     DMX_CUDA(cudaSetDevice(ctx->device));
+    sk_free(ctx);
     ctx->has_grid = false;
     ctx->model = 0;
     ctx->n = n;
@@ -688,6 +698,8 @@ int dmx_halo_exchange(dmx_ctx* ctx, int vec)
     if (ctx->nranks == 1) return 0;
     return halo_exchange(ctx, ctx->d_vec[vec]);
 }
+
+int dmx_debug_sweep_trace(dmx_ctx* ctx, long long* out6144) { return sk_trace_read(ctx, out6144); }
 
 int dmx_time_kernel(dmx_ctx* ctx, int which, int reps, float* ms_avg)
 {

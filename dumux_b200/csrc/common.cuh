@@ -127,6 +127,7 @@ struct dmx_ctx {
     std::vector<int> l_ptr, u_ptr;
     int *d_lptr = nullptr, *d_uptr = nullptr;
     unsigned int* d_barrier = nullptr;
+    void* skew = nullptr;             // SkewState of ilu_structured.cu (structured-grid ILU sweeps), null: generic kernels
 
     // reductions
     double* d_partials = nullptr;
@@ -226,6 +227,12 @@ int dot(dmx_ctx* ctx, const double* a, const double* b, double* out);
 int bicgstab(dmx_ctx* ctx, double reduction, int maxit, int precond, int* iterations, double* achieved);
 int newton_update(dmx_ctx* ctx, double* shift);
 int check_finite(dmx_ctx* ctx, const double* v, size_t len, bool* ok);
+// implemented in ilu_structured.cu
+int sk_setup(dmx_ctx* ctx);
+void sk_free(dmx_ctx* ctx);
+int sk_skew(dmx_ctx* ctx);
+int sk_apply(dmx_ctx* ctx, const double* d, double* v);
+int sk_trace_read(dmx_ctx* ctx, long long* out);
 // implemented in dist.cu
 int nccl_init(dmx_ctx* ctx, const void* uid);
 int nccl_get_unique_id(void* out);

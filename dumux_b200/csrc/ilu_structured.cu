@@ -1,0 +1,586 @@
+// ilu_structured.cu -- block ILU(0) triangular sweeps for the 7-point CCTpfa pattern on a structured box.
+//
+// Replaces Dune::SeqILU::apply -> ILU::blockILUBacksolve (dune-istl, called through
+// dumux/linear/istlsolvers.hh:535-568) for matrices whose pattern comes from dmx_grid_structured.  The generic
+// level-scheduled kernels in linalg.cu pay one grid-wide barrier per hyperplane i+j+k (3N-2 levels per sweep, ~7 us
+// each at 256^3); here the same hyperplane order is executed WITHOUT grid barriers:
+//
+//   * the (i,j) plane is cut into 16x16 tiles, one CTA per tile, one thread per grid line (i,j); the CTA marches along
+//     k and thread (a,b) handles layer k = s - a - b at step s, so inside a tile the wavefront costs one
+//     __syncthreads per step and neighbour values travel through shared memory;
+//   * tiles depend only on their -x / -y neighbours (lower sweep; +x / +y for the upper sweep) which must run
+//     TI (TJ) steps ahead: point-to-point progress counters in global memory, published every SK_C steps, replace the
+//     grid barrier; tiles are handed out by an atomic ticket in dependency order, so waiting never deadlocks;
+//   * the factors are stored in a tile-skewed layout fac[tile][step][component][thread]: what a CTA needs at step s is
+//     ONE contiguous chunk (24-32 KB for 2x2 blocks), fetched with cp.async.bulk (TMA, 1-D) into a shared-memory ring
+//     several steps ahead and signalled through mbarriers -- HBM sees long sequential streams, no index arrays at all.
+//
+// Per-row arithmetic (operation order, no FMA contraction) is that of blockILUBacksolve: columns ascending
+// (-z,-y,-x | +x,+y,+z), y -= A x per block (FieldMatrix::mmv), v = Dinv * rhs last (FieldMatrix::mv, sum from 0), so
+// results are bit-identical to the generic kernels and to the CPU oracle.
+#include <algorithm>
+#include <cstdint>
+#include <cstdlib>
+
+#include "common.cuh"
+
+namespace dmx {
+
+constexpr int SK_TI = 16, SK_TJ = 16, SK_THREADS = SK_TI * SK_TJ;
+constexpr int SK_C = 8;                      // steps per chunk: progress is published / awaited once per chunk
+static_assert(SK_C * (SK_TI + SK_TJ) == SK_THREADS, "one halo load per thread and chunk");
+constexpr unsigned long long SK_EPOCH = 1ull << 20;
+
+struct SkewGrid {
+    int nx, ny, nz, ntx, nty, ntiles, NS;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(phase)
+        : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(unsigned long long* p, unsigned long long v)
+{
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// number of factor components (doubles) per cell: lower L_z,L_y,L_x ; upper U_x,U_y,U_z,Dinv
+template <int B, bool UPPER>
+struct SkewLayout {
+    static constexpr int NBLK = UPPER ? 4 : 3;
+    static constexpr int NC = NBLK * B * B;
+    static constexpr int STAGE_DOUBLES = NC * SK_THREADS;
+};
+
+// position of component (blk,r,c) of thread t inside one step chunk: 2x2 blocks are stored as double2 rows
+template <int B>
+__host__ __device__ __forceinline__ int sk_pos(int blk, int r, int c, int t)
+{
+    if (B == 2) return ((blk * 2 + r) * SK_THREADS + t) * 2 + c;
+    return blk * SK_THREADS + t;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// BCRS (factorised, ctx->d_ilu) -> tile-skewed L and U arrays.  One thread per (tile, step, thread slot).
+// Mirrored thread coordinates: slot t = a + 16*b; lower: il = a, jl = b, k = s - a - b;
+//                              upper: il = 15-a, jl = 15-b, k = nz-1 - (s - a - b).
+// ------------------------------------------------------------------------------------------------------------
+template <int B>
+__global__ void __launch_bounds__(SK_THREADS) ilu_skew_kernel(SkewGrid g, const int* __restrict__ rowptr, const int* __restrict__ diag,
+                                                               const double* __restrict__ ilu, double* __restrict__ Lsk,
+                                                               double* __restrict__ Usk)
+{
+    constexpr int BB = B * B;
+    const int t = threadIdx.x;
+    const int a = t & (SK_TI - 1), b = t >> 4;
+    const int s = blockIdx.x % g.NS;
+    const int tile = blockIdx.x / g.NS;
+    const int ti = tile % g.ntx, tj = tile / g.ntx;
+    {
+        // lower
+        const int i = ti * SK_TI + a, j = tj * SK_TJ + b, k = s - a - b;
+        double* dst = Lsk + ((size_t)tile * g.NS + s) * SkewLayout<B, false>::STAGE_DOUBLES;
+        const bool valid = i < g.nx && j < g.ny && k >= 0 && k < g.nz;
+        double blk[3][BB];
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+#pragma unroll
+            for (int e = 0; e < BB; ++e) blk[q][e] = 0.0;
+        if (valid) {
+            const int I = i + g.nx * (j + g.ny * k);
+            int p = rowptr[I];
+            if (k > 0) { for (int e = 0; e < BB; ++e) blk[0][e] = ilu[(size_t)p * BB + e]; ++p; }
+            if (j > 0) { for (int e = 0; e < BB; ++e) blk[1][e] = ilu[(size_t)p * BB + e]; ++p; }
+            if (i > 0) { for (int e = 0; e < BB; ++e) blk[2][e] = ilu[(size_t)p * BB + e]; ++p; }
+        }
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+#pragma unroll
+            for (int r = 0; r < B; ++r)
+#pragma unroll
+                for (int c = 0; c < B; ++c) dst[sk_pos<B>(q, r, c, t)] = blk[q][r * B + c];
+    }
+    {
+        // upper
+        const int i = ti * SK_TI + (SK_TI - 1 - a), j = tj * SK_TJ + (SK_TJ - 1 - b), k = g.nz - 1 - (s - a - b);
+        double* dst = Usk + ((size_t)tile * g.NS + s) * SkewLayout<B, true>::STAGE_DOUBLES;
+        const bool valid = i < g.nx && j < g.ny && k >= 0 && k < g.nz;
+        double blk[4][BB];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int e = 0; e < BB; ++e) blk[q][e] = 0.0;
+        if (valid) {
+            const int I = i + g.nx * (j + g.ny * k);
+            int p = diag[I];
+            for (int e = 0; e < BB; ++e) blk[3][e] = ilu[(size_t)p * BB + e];
+            ++p;
+            if (i + 1 < g.nx) { for (int e = 0; e < BB; ++e) blk[0][e] = ilu[(size_t)p * BB + e]; ++p; }
+            if (j + 1 < g.ny) { for (int e = 0; e < BB; ++e) blk[1][e] = ilu[(size_t)p * BB + e]; ++p; }
+            if (k + 1 < g.nz) { for (int e = 0; e < BB; ++e) blk[2][e] = ilu[(size_t)p * BB + e]; ++p; }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int r = 0; r < B; ++r)
+#pragma unroll
+                for (int c = 0; c < B; ++c) dst[sk_pos<B>(q, r, c, t)] = blk[q][r * B + c];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// vectors in the tile-skewed layout (LOWER indexing): xsk[((tile*NS + s)*256 + t)*B + e], thread slot t = a + 16 b,
+// cell (i0+a, j0+b, k = s-a-b).  The upper sweep walks the same storage backwards: step s_up = NS-1-s, lane 255-t.
+// ------------------------------------------------------------------------------------------------------------
+template <int B>
+__global__ void __launch_bounds__(SK_THREADS) vec_skew_kernel(SkewGrid g, const double* __restrict__ x, double* __restrict__ xsk)
+{
+    const int t = threadIdx.x;
+    const int a = t & (SK_TI - 1), b = t >> 4;
+    const int s = blockIdx.x % g.NS;
+    const int tile = blockIdx.x / g.NS;
+    const int i = (tile % g.ntx) * SK_TI + a, j = (tile / g.ntx) * SK_TJ + b, k = s - a - b;
+    const bool valid = i < g.nx && j < g.ny && k >= 0 && k < g.nz;
+    double val[B];
+#pragma unroll
+    for (int e = 0; e < B; ++e) val[e] = 0.0;
+    if (valid) {
+        const size_t I = (size_t)i + (size_t)g.nx * (j + (size_t)g.ny * k);
+        if (B == 2) {
+            const double2 w = *reinterpret_cast<const double2*>(x + I * 2);
+            val[0] = w.x; val[B - 1] = w.y;
+        } else val[0] = x[I];
+    }
+    double* dst = xsk + ((size_t)blockIdx.x * SK_THREADS + t) * B;
+    if (B == 2) *reinterpret_cast<double2*>(dst) = make_double2(val[0], val[B - 1]);
+    else dst[0] = val[0];
+}
+// one thread per cell: coalesced natural writes, gathered skewed reads
+template <int B>
+__global__ void __launch_bounds__(256) vec_unskew_kernel(SkewGrid g, const double* __restrict__ xsk, double* __restrict__ x)
+{
+    const size_t I = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t n = (size_t)g.nx * g.ny * g.nz;
+    if (I >= n) return;
+    const int i = (int)(I % g.nx), j = (int)((I / g.nx) % g.ny), k = (int)(I / ((size_t)g.nx * g.ny));
+    const int a = i & (SK_TI - 1), b = j & (SK_TJ - 1);
+    const int tile = (i / SK_TI) + g.ntx * (j / SK_TJ);
+    const int s = k + a + b;
+    const double* src = xsk + (((size_t)tile * g.NS + s) * SK_THREADS + (a + SK_TI * b)) * B;
+    if (B == 2) *reinterpret_cast<double2*>(x + I * 2) = *reinterpret_cast<const double2*>(src);
+    else x[I] = src[0];
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// one triangular sweep, in place on the skewed vector.  LOWER: x <- L^-1 x (unit lower).  UPPER: x <- U^-1 x.
+// ------------------------------------------------------------------------------------------------------------
+template <int B, bool UPPER, int S, int MINB>
+__global__ void __launch_bounds__(SK_THREADS, MINB) ilu_sweep_kernel(SkewGrid g, const double* __restrict__ fac, double* xsk,
+                                                                      const int* __restrict__ order, unsigned long long* ticket_ctr,
+                                                                      unsigned long long ticket_base, unsigned long long* prog,
+                                                                      unsigned long long epoch, long long* trace)
+{
+    using LY = SkewLayout<B, UPPER>;
+    constexpr int VEC_DOUBLES = SK_THREADS * B;
+    constexpr int STAGE_ALL = LY::STAGE_DOUBLES + VEC_DOUBLES;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* stages = reinterpret_cast<double*>(smem_raw);                              // [S][factors | vector]
+    double* sv = stages + (size_t)S * STAGE_ALL;                                       // [2][TJ+1][TI+1][B]
+    double* hx = sv + 2 * (SK_TJ + 1) * (SK_TI + 1) * B;                               // [C][TJ][B]
+    double* hy = hx + SK_C * SK_TJ * B;                                                // [C][TI][B]
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(hy + SK_C * SK_TI * B);               // [S]
+    __shared__ int s_tile;
+
+    const int t = threadIdx.x;
+    const int a = t & (SK_TI - 1), b = t >> 4;          // mirrored coordinates for UPPER
+    const int tl = UPPER ? SK_THREADS - 1 - t : t;      // lane in LOWER indexing (storage)
+    if (t == 0) {
+        const unsigned long long ticket = atomicAdd(ticket_ctr, 1ull) - ticket_base;
+        s_tile = order[(int)ticket];
+        for (int q = 0; q < S; ++q) mbar_init(&mbar[q], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int tile = s_tile;
+    const int ti = tile % g.ntx, tj = tile / g.ntx;
+    const int NS = g.NS;
+    const double* fac_tile = fac + (size_t)tile * NS * LY::STAGE_DOUBLES;
+    double* x_tile = xsk + (size_t)tile * NS * VEC_DOUBLES;
+    constexpr uint32_t FAC_BYTES = LY::STAGE_DOUBLES * sizeof(double), VEC_BYTES = VEC_DOUBLES * sizeof(double);
+    auto issue = [&](int s) {          // thread 0: fetch the factors and the vector chunk of step s into its ring slot
+        const int q = s % S;
+        double* dst = stages + (size_t)q * STAGE_ALL;
+        const int sl = UPPER ? NS - 1 - s : s;
+        mbar_expect_tx(&mbar[q], FAC_BYTES + VEC_BYTES);
+        bulk_g2s(dst, fac_tile + (size_t)s * LY::STAGE_DOUBLES, FAC_BYTES, &mbar[q]);
+        bulk_g2s(dst + LY::STAGE_DOUBLES, x_tile + (size_t)sl * VEC_DOUBLES, VEC_BYTES, &mbar[q]);
+    };
+    if (t == 0)
+        for (int q = 0; q < S && q < NS; ++q) issue(q);
+
+    // actual cell line of this thread and the tiles it depends on
+    const int i = ti * SK_TI + (UPPER ? SK_TI - 1 - a : a);
+    const int j = tj * SK_TJ + (UPPER ? SK_TJ - 1 - b : b);
+    const bool line = i < g.nx && j < g.ny;
+    const bool depx = UPPER ? (i + 1 < g.nx) : (i > 0);          // a -x (+x) neighbour cell exists
+    const bool depy = UPPER ? (j + 1 < g.ny) : (j > 0);
+    const int tix = UPPER ? ti + 1 : ti - 1, tjy = UPPER ? tj + 1 : tj - 1;
+    const bool tilex = tix >= 0 && tix < g.ntx, tiley = tjy >= 0 && tjy < g.nty;
+    const unsigned long long* progx = prog + (tilex ? tix + g.ntx * tj : 0);
+    const unsigned long long* progy = prog + (tiley ? ti + g.ntx * tjy : 0);
+    // halo duty of this thread: threads [0, C*TJ) fetch the x halo, the rest the y halo (one value per chunk)
+    const bool hx_duty = t < SK_C * SK_TJ;
+    const int hc = hx_duty ? t / SK_TJ : (t - SK_C * SK_TJ) / SK_TI;       // step within the chunk
+    const int hl = hx_duty ? t % SK_TJ : (t - SK_C * SK_TJ) % SK_TI;       // b (x halo) or a (y halo), mirrored for UPPER
+    bool hvalid;
+    const double* hsrc;
+    {
+        // the upstream tile computed the wanted value TI-1 (TJ-1) steps after my step; lane on its far edge
+        const int lane_lo = hx_duty ? (SK_TI - 1) + SK_TI * hl : hl + SK_TI * (SK_TJ - 1);
+        const int lane = UPPER ? SK_THREADS - 1 - lane_lo : lane_lo;
+        const int htile = hx_duty ? tix + g.ntx * tj : ti + g.ntx * tjy;
+        const int other = hx_duty ? tj * SK_TJ + (UPPER ? SK_TJ - 1 - hl : hl) : ti * SK_TI + (UPPER ? SK_TI - 1 - hl : hl);
+        hvalid = (hx_duty ? tilex : tiley) && other < (hx_duty ? g.ny : g.nx);
+        hsrc = xsk + ((size_t)(hvalid ? htile : 0) * NS * SK_THREADS + lane) * B;
+    }
+    constexpr int HSHIFT = SK_TI - 1;       // == SK_TJ - 1
+    static_assert(SK_TI == SK_TJ, "square tiles");
+
+    double vprev[B];
+#pragma unroll
+    for (int e = 0; e < B; ++e) vprev[e] = 0.0;
+
+    long long* tr = nullptr;       // optional timeline (developer diagnostic): tiles ticketed 0 and ntiles/2
+    if (trace && t == 0) {
+        if (tile == order[0]) tr = trace;
+        else if (tile == order[g.ntiles / 2]) tr = trace + 24 * 64;
+    }
+#define SK_STAMP(slot) do { if (tr && s0 / SK_C < 64) tr[(s0 / SK_C) * 24 + (slot)] = clock64(); } while (0)
+    for (int s0 = 0; s0 < NS; s0 += SK_C) {
+        // ---- chunk head: wait for the upstream tiles, fetch their boundary values of this chunk ----
+        SK_STAMP(0);
+        if (t == 0) {
+            if (tilex) {
+                const unsigned long long need = epoch + (unsigned long long)min(s0 + SK_C + SK_TI - 1, NS);
+                while (ld_acquire(progx) < need) { }
+            }
+            if (tiley) {
+                const unsigned long long need = epoch + (unsigned long long)min(s0 + SK_C + SK_TJ - 1, NS);
+                while (ld_acquire(progy) < need) { }
+            }
+        }
+        __syncthreads();
+        SK_STAMP(1);
+        {
+            const int s = s0 + hc;
+            const int kk = s - hl;
+            const bool ok = hvalid && kk >= 0 && kk < g.nz;
+            const int sl = UPPER ? NS - 1 - (s + HSHIFT) : s + HSHIFT;
+            double* dst = (hx_duty ? hx + (hc * SK_TJ + hl) * B : hy + (hc * SK_TI + hl) * B);
+#pragma unroll
+            for (int e = 0; e < B; ++e) dst[e] = ok ? __ldcg(hsrc + (size_t)sl * VEC_DOUBLES + e) : 0.0;
+        }
+        __syncthreads();
+        SK_STAMP(2);
+
+#pragma unroll
+        for (int c = 0; c < SK_C; ++c) {
+            const int s = s0 + c;
+            if (s < NS) {       // uniform
+                const int stage = s % S;
+                mbar_wait(&mbar[stage], (uint32_t)((s / S) & 1));
+                SK_STAMP(3 + 2 * c);
+                const double* f = stages + (size_t)stage * STAGE_ALL;
+                const int kk = s - a - b;
+                const bool active = line && kk >= 0 && kk < g.nz;
+                const int rb = (s + 1) & 1, wb = s & 1;       // buffer written at step s-1 / written now
+                double* svw = sv + ((wb * (SK_TJ + 1) + (b + 1)) * (SK_TI + 1) + (a + 1)) * B;
+                if (active) {
+                    double r[B];
+#pragma unroll
+                    for (int e = 0; e < B; ++e) r[e] = f[LY::STAGE_DOUBLES + tl * B + e];
+                    double xv[B], yv[B];
+                    const double* xs = (a == 0) ? hx + (c * SK_TJ + b) * B : sv + ((rb * (SK_TJ + 1) + (b + 1)) * (SK_TI + 1) + a) * B;
+                    const double* ys = (b == 0) ? hy + (c * SK_TI + a) * B : sv + ((rb * (SK_TJ + 1) + b) * (SK_TI + 1) + (a + 1)) * B;
+#pragma unroll
+                    for (int e = 0; e < B; ++e) { xv[e] = xs[e]; yv[e] = ys[e]; }
+                    double blk[LY::NBLK][B * B];
+                    if (B == 2) {
+#pragma unroll
+                        for (int q = 0; q < LY::NBLK; ++q)
+#pragma unroll
+                            for (int rr = 0; rr < 2; ++rr) {
+                                const double2 w = reinterpret_cast<const double2*>(f)[(q * 2 + rr) * SK_THREADS + t];
+                                blk[q][rr * 2] = w.x;
+                                blk[q][rr * 2 + 1] = w.y;
+                            }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < LY::NBLK; ++q) blk[q][0] = f[q * SK_THREADS + t];
+                    }
+                    const bool depz = kk > 0;
+                    if (!UPPER) {
+                        // columns ascending: -z, -y, -x   (rhs -= A_ij v_j, FieldMatrix::mmv order)
+                        if (depz) {
+#pragma unroll
+                            for (int rr = 0; rr < B; ++rr)
+#pragma unroll
+                                for (int cc = 0; cc < B; ++cc) r[rr] -= blk[0][rr * B + cc] * vprev[cc];
+                        }
+                        if (depy) {
+#pragma unroll
+                            for (int rr = 0; rr < B; ++rr)
+#pragma unroll
+                                for (int cc = 0; cc < B; ++cc) r[rr] -= blk[1][rr * B + cc] * yv[cc];
+                        }
+                        if (depx) {
+#pragma unroll
+                            for (int rr = 0; rr < B; ++rr)
+#pragma unroll
+                                for (int cc = 0; cc < B; ++cc) r[rr] -= blk[2][rr * B + cc] * xv[cc];
+                        }
+                    } else {
+                        // columns ascending: +x, +y, +z, then v = Dinv * rhs (sum from 0)
+                        if (depx) {
+#pragma unroll
+                            for (int rr = 0; rr < B; ++rr)
+#pragma unroll
+                                for (int cc = 0; cc < B; ++cc) r[rr] -= blk[0][rr * B + cc] * xv[cc];
+                        }
+                        if (depy) {
+#pragma unroll
+                            for (int rr = 0; rr < B; ++rr)
+#pragma unroll
+                                for (int cc = 0; cc < B; ++cc) r[rr] -= blk[1][rr * B + cc] * yv[cc];
+                        }
+                        if (depz) {
+#pragma unroll
+                            for (int rr = 0; rr < B; ++rr)
+#pragma unroll
+                                for (int cc = 0; cc < B; ++cc) r[rr] -= blk[2][rr * B + cc] * vprev[cc];
+                        }
+                        double o[B];
+#pragma unroll
+                        for (int rr = 0; rr < B; ++rr) {
+                            double acc = 0.0;
+#pragma unroll
+                            for (int cc = 0; cc < B; ++cc) acc += blk[3][rr * B + cc] * r[cc];
+                            o[rr] = acc;
+                        }
+#pragma unroll
+                        for (int e = 0; e < B; ++e) r[e] = o[e];
+                    }
+#pragma unroll
+                    for (int e = 0; e < B; ++e) { vprev[e] = r[e]; svw[e] = r[e]; }
+                    const int sl = UPPER ? NS - 1 - s : s;
+                    double* out = x_tile + ((size_t)sl * SK_THREADS + tl) * B;
+                    if (B == 2) __stcg(reinterpret_cast<double2*>(out), make_double2(r[0], r[B - 1]));
+                    else __stcg(out, r[0]);
+                }
+                __syncthreads();
+                SK_STAMP(4 + 2 * c);
+                if (t == 0) {
+                    if (s + S < NS) issue(s + S);
+                    if (c == SK_C - 1 || s == NS - 1) st_release(prog + tile, epoch + (unsigned long long)(s + 1));
+                }
+            }
+        }
+        SK_STAMP(19);
+    }
+#undef SK_STAMP
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------
+struct SkewState {
+    SkewGrid g{};
+    int b = 0;
+    double *Lsk = nullptr, *Usk = nullptr, *xsk = nullptr;
+    int *order_lo = nullptr, *order_up = nullptr;
+    unsigned long long* ctl = nullptr;       // [0],[1]: tickets lower/upper; [2 .. 2+ntiles): prog lower; then prog upper
+    unsigned long long seq_lo = 0, seq_up = 0;
+    int deep = 0;                          // 1: one CTA per SM with a deep TMA ring, 0: two CTAs per SM
+    long long* trace = nullptr;            // 2 kernels x 2 tiles x 64 chunks x 24 stamps (DMX_SK_TRACE=1)
+};
+
+template <int B, bool UPPER, int S>
+static size_t sweep_smem()
+{
+    using LY = SkewLayout<B, UPPER>;
+    return ((size_t)S * (LY::STAGE_DOUBLES + SK_THREADS * B) + 2 * (SK_TJ + 1) * (SK_TI + 1) * B + SK_C * (SK_TI + SK_TJ) * B) * sizeof(double) +
+           S * sizeof(uint64_t);
+}
+
+// ring depth per variant: {two CTAs per SM, one CTA per SM}
+template <int B, bool UPPER> struct Depth;
+template <> struct Depth<2, false> { static constexpr int S2 = 3, S1 = 7; };
+template <> struct Depth<2, true> { static constexpr int S2 = 2, S1 = 5; };
+template <> struct Depth<1, false> { static constexpr int S2 = 8, S1 = 16; };
+template <> struct Depth<1, true> { static constexpr int S2 = 8, S1 = 16; };
+
+template <int B, bool UPPER>
+static int sweep_launch(dmx_ctx* ctx, SkewState* st, const double* fac, const int* order, unsigned long long* tick, unsigned long long base,
+                        unsigned long long* prog, unsigned long long epoch, long long* trace)
+{
+    const SkewGrid& g = st->g;
+    if (st->deep) {
+        constexpr int S = Depth<B, UPPER>::S1;
+        auto kern = ilu_sweep_kernel<B, UPPER, S, 1>;
+        const size_t smem = sweep_smem<B, UPPER, S>();
+        static bool attr = false;
+        if (!attr) { DMX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+        kern<<<g.ntiles, SK_THREADS, smem, ctx->stream>>>(g, fac, st->xsk, order, tick, base, prog, epoch, trace);
+    } else {
+        constexpr int S = Depth<B, UPPER>::S2;
+        auto kern = ilu_sweep_kernel<B, UPPER, S, 2>;
+        const size_t smem = sweep_smem<B, UPPER, S>();
+        static bool attr = false;
+        if (!attr) { DMX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+        kern<<<g.ntiles, SK_THREADS, smem, ctx->stream>>>(g, fac, st->xsk, order, tick, base, prog, epoch, trace);
+    }
+    DMX_CHECK_LAUNCH();
+    return 0;
+}
+
+bool sk_supported(const dmx_ctx* ctx)
+{
+    if (!ctx->has_grid) return false;
+    for (int a = 0; a < ctx->dim; ++a)
+        if (ctx->nc[a] < 3) return false;      // smaller boxes alias stencil columns (fill inside the pattern): generic path
+    return true;
+}
+
+void sk_free(dmx_ctx* ctx)
+{
+    SkewState* st = static_cast<SkewState*>(ctx->skew);
+    if (!st) return;
+    cudaFree(st->Lsk); cudaFree(st->Usk); cudaFree(st->xsk); cudaFree(st->order_lo); cudaFree(st->order_up); cudaFree(st->ctl);
+    if (st->trace) cudaFree(st->trace);
+    delete st;
+    ctx->skew = nullptr;
+}
+
+int sk_setup(dmx_ctx* ctx)
+{
+    sk_free(ctx);
+    if (!sk_supported(ctx)) return 0;
+    SkewState* st = new SkewState;
+    ctx->skew = st;
+    SkewGrid& g = st->g;
+    g.nx = ctx->nc[0]; g.ny = ctx->nc[1]; g.nz = ctx->nc[2];
+    g.ntx = (g.nx + SK_TI - 1) / SK_TI; g.nty = (g.ny + SK_TJ - 1) / SK_TJ;
+    g.ntiles = g.ntx * g.nty;
+    g.NS = g.nz + SK_TI + SK_TJ - 2;
+    st->b = ctx->b;
+    const int BB = ctx->b * ctx->b;
+    const size_t slots = (size_t)g.ntiles * g.NS * SK_THREADS;
+    DMX_CUDA(cudaMalloc((void**)&st->Lsk, slots * 3 * BB * sizeof(double)));
+    DMX_CUDA(cudaMalloc((void**)&st->Usk, slots * 4 * BB * sizeof(double)));
+    DMX_CUDA(cudaMalloc((void**)&st->xsk, slots * ctx->b * sizeof(double)));
+    std::vector<int> lo(g.ntiles), up(g.ntiles);
+    for (int q = 0; q < g.ntiles; ++q) lo[q] = up[q] = q;
+    auto key = [&](int q) { return (q % g.ntx) + (q / g.ntx); };
+    std::stable_sort(lo.begin(), lo.end(), [&](int x, int y) { return key(x) < key(y); });
+    std::stable_sort(up.begin(), up.end(), [&](int x, int y) { return key(x) > key(y); });
+    DMX_CUDA(cudaMalloc((void**)&st->order_lo, g.ntiles * sizeof(int)));
+    DMX_CUDA(cudaMalloc((void**)&st->order_up, g.ntiles * sizeof(int)));
+    DMX_CUDA(cudaMemcpy(st->order_lo, lo.data(), g.ntiles * sizeof(int), cudaMemcpyHostToDevice));
+    DMX_CUDA(cudaMemcpy(st->order_up, up.data(), g.ntiles * sizeof(int), cudaMemcpyHostToDevice));
+    DMX_CUDA(cudaMalloc((void**)&st->ctl, (2 + 2 * (size_t)g.ntiles) * sizeof(unsigned long long)));
+    DMX_CUDA(cudaMemset(st->ctl, 0, (2 + 2 * (size_t)g.ntiles) * sizeof(unsigned long long)));
+    {
+        const char* env = getenv("DMX_SK_TRACE");
+        if (env && env[0] == '1') {
+            DMX_CUDA(cudaMalloc((void**)&st->trace, 2 * 2 * 64 * 24 * sizeof(long long)));
+            DMX_CUDA(cudaMemset(st->trace, 0, 2 * 2 * 64 * 24 * sizeof(long long)));
+        }
+        // default: one CTA per SM with the deep ring (measured faster at 256^3 and 512^2 x 66); DMX_SK_DEEP=0 for A/B runs
+        const char* deep = getenv("DMX_SK_DEEP");
+        st->deep = deep ? (deep[0] == '1') : 1;
+    }
+    return 0;
+}
+
+// after ilu0_factor(): re-layout the factors
+int sk_skew(dmx_ctx* ctx)
+{
+    SkewState* st = static_cast<SkewState*>(ctx->skew);
+    const SkewGrid& g = st->g;
+    const unsigned grid = (unsigned)((size_t)g.ntiles * g.NS);
+    if (ctx->b == 2) ilu_skew_kernel<2><<<grid, SK_THREADS, 0, ctx->stream>>>(g, ctx->d_rowptr, ctx->d_diag, ctx->d_ilu, st->Lsk, st->Usk);
+    else ilu_skew_kernel<1><<<grid, SK_THREADS, 0, ctx->stream>>>(g, ctx->d_rowptr, ctx->d_diag, ctx->d_ilu, st->Lsk, st->Usk);
+    DMX_CHECK_LAUNCH();
+    return 0;
+}
+
+template <int B>
+static int sk_apply_t(dmx_ctx* ctx, SkewState* st, const double* d, double* v)
+{
+    const SkewGrid& g = st->g;
+    unsigned long long* tick_lo = st->ctl;
+    unsigned long long* tick_up = st->ctl + 1;
+    unsigned long long* prog_lo = st->ctl + 2;
+    unsigned long long* prog_up = st->ctl + 2 + g.ntiles;
+    const unsigned long long base_lo = st->seq_lo * (unsigned long long)g.ntiles, ep_lo = (st->seq_lo + 1) * SK_EPOCH;
+    const unsigned long long base_up = st->seq_up * (unsigned long long)g.ntiles, ep_up = (st->seq_up + 1) * SK_EPOCH;
+    st->seq_lo++;
+    st->seq_up++;
+    vec_skew_kernel<B><<<(unsigned)((size_t)g.ntiles * g.NS), SK_THREADS, 0, ctx->stream>>>(g, d, st->xsk);
+    DMX_CHECK_LAUNCH();
+    if (int rc = sweep_launch<B, false>(ctx, st, st->Lsk, st->order_lo, tick_lo, base_lo, prog_lo, ep_lo, st->trace)) return rc;
+    if (int rc = sweep_launch<B, true>(ctx, st, st->Usk, st->order_up, tick_up, base_up, prog_up, ep_up,
+                                       st->trace ? st->trace + 2 * 64 * 24 : nullptr))
+        return rc;
+    vec_unskew_kernel<B><<<(unsigned)((ctx->n + 255) / 256), 256, 0, ctx->stream>>>(g, st->xsk, v);
+    DMX_CHECK_LAUNCH();
+    return 0;
+}
+
+int sk_apply(dmx_ctx* ctx, const double* d, double* v)
+{
+    SkewState* st = static_cast<SkewState*>(ctx->skew);
+    return ctx->b == 2 ? sk_apply_t<2>(ctx, st, d, v) : sk_apply_t<1>(ctx, st, d, v);
+}
+
+int sk_trace_read(dmx_ctx* ctx, long long* out)
+{
+    SkewState* st = static_cast<SkewState*>(ctx->skew);
+    if (!st || !st->trace) return fail(ctx, DMX_ERR_USAGE, "no sweep trace (set DMX_SK_TRACE=1 before creating the grid)");
+    DMX_CUDA(cudaStreamSynchronize(ctx->stream));
+    DMX_CUDA(cudaMemcpy(out, st->trace, 2 * 2 * 64 * 24 * sizeof(long long), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+} // namespace dmx

@@ -510,6 +510,9 @@ int ilu0_factor(dmx_ctx* ctx)
     DMX_CUDA(cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     DMX_CUDA(cudaStreamSynchronize(ctx->stream));
     if (*ctx->h_flag) { ctx->err = "ILU0: singular diagonal block"; return DMX_STATUS_BREAKDOWN; }
+    if (ctx->skew) {
+        if (int rc2 = sk_skew(ctx)) return rc2;
+    }
     ctx->ilu_valid = true;
     return 0;
 }
@@ -517,6 +520,7 @@ int ilu0_factor(dmx_ctx* ctx)
 int ilu0_apply(dmx_ctx* ctx, const double* d, double* v)
 {
     ProfScope ps(ctx, DMX_K_ILU_APPLY);
+    if (ctx->skew) return sk_apply(ctx, d, v);
     const int nl = (int)ctx->l_ptr.size() - 1, nu = (int)ctx->u_ptr.size() - 1;
     int rc;
     if (ctx->b == 2) {

@@ -164,6 +164,9 @@ int  dmx_halo_exchange(dmx_ctx* ctx, int vec);                           /* copy
 /* average device time in ms of `reps` back-to-back launches of one kernel, CUDA-event timed on the ctx stream.
    which: 0 assembly (residual+Jacobian), 1 SpMV, 2 ILU0 apply, 3 ILU0 factor, 4 secondary-variable pass only */
 int  dmx_time_kernel(dmx_ctx* ctx, int which, int reps, float* ms_avg);
+/* developer diagnostic: clock64 timeline of the structured ILU sweeps (enabled by DMX_SK_TRACE=1 at grid set-up):
+   out[kernel 2][tile 2][chunk 64][stamp 24] */
+int  dmx_debug_sweep_trace(dmx_ctx* ctx, long long* out6144);
 int  dmx_kernel_launch_count(const dmx_ctx* ctx, long long* launches);
 /* Per-kernel-class device timers inside the hot path (what Dune::Timer buckets are in newtonsolver.hh:921-955, at
    kernel granularity): CUDA-event pairs on the ctx stream around every launch of the class while enabled.
