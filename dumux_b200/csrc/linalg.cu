@@ -159,10 +159,11 @@ __global__ void __launch_bounds__(RED_THREADS) residual_init_kernel(size_t len, 
 {
     double s = 0.0;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (size_t)gridDim.x * blockDim.x) {
-        const double ri = rhs[i] - Ax[i];
+        // OverlappingSchwarzOperator::applyscaleadd(-1, x, r) projects r: non-owner entries are zero
+        const double ri = (!owner || owner[i / b]) ? rhs[i] - Ax[i] : 0.0;
         r[i] = ri;
         rt[i] = ri;
-        if (!owner || owner[i / b]) s += ri * ri;
+        s += ri * ri;
     }
     s = block_reduce<false>(s);
     if (threadIdx.x == 0) partials[blockIdx.x] = s;

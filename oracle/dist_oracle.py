@@ -1,0 +1,288 @@
+"""Slab-decomposed (overlapping Schwarz) restatement of the Newton step on the CPU oracle.  TEST INFRASTRUCTURE ONLY.
+
+What DuMux does for a cell-centred scheme on P MPI ranks (SURVEY 2.2, 8e, Appendix A "Overlapping variant"):
+  * YaspGrid cuts the structured box into slabs (Grid.Partitioning "1 1 P") and adds `Grid.Overlap 1` layers; every rank
+    assembles the rows of ALL its cells (interior + overlap); the outer face of an overlap cell carries no scvf
+    (discretization/cellcentered/tpfa/fvgridgeometry.hh:272-320), so those rows are incomplete;
+  * linear/linearsolvertraits.hh:79-91 + linear/istlsolvers.hh:550-566 wire dune-istl's
+    OverlappingSchwarzOperator (local A.mv, then project = zero the non-owner entries),
+    OverlappingSchwarzScalarProduct (owner-masked dot + global sum) and
+    BlockPreconditioner (pre: copyOwnerToAll(x); apply: local SeqILU, then copyOwnerToAll(v)) around BiCGSTABSolver.
+
+The algorithm below is written SPMD (one call per rank) against a tiny communicator interface with two implementations:
+`ThreadComm` (P python threads in one process: the reference run) and `TorchComm` (torch.distributed, gloo or nccl: the
+world_size-2 CPU tests).  The GPU path (dumux_b200/csrc/dist.cu + linalg.cu) is compared against it.
+"""
+from __future__ import annotations
+
+import math
+import threading
+
+import numpy as np
+
+from dumux_b200 import problems
+from oracle import oracle_py as O
+
+
+# ----------------------------------------------------------------------------------------------------------
+# communicators
+# ----------------------------------------------------------------------------------------------------------
+class ThreadComm:
+    """P ranks as threads of one process; collectives through a barrier and shared slots (deterministic rank order)."""
+
+    class Shared:
+        def __init__(self, nranks):
+            self.nranks = nranks
+            self.barrier = threading.Barrier(nranks)
+            self.slots = [None] * nranks
+            self.mail = {}
+
+    def __init__(self, shared, rank):
+        self.s, self.rank, self.nranks = shared, rank, shared.nranks
+
+    def allreduce(self, value, op="sum"):
+        self.s.slots[self.rank] = value
+        self.s.barrier.wait()
+        vals = list(self.s.slots)
+        self.s.barrier.wait()
+        if op == "sum":
+            acc = vals[0]
+            for v in vals[1:]:
+                acc = acc + v
+            return acc
+        return max(vals) if op == "max" else min(vals)
+
+    def exchange(self, to_lo, to_hi):
+        """send `to_lo` to rank-1 and `to_hi` to rank+1 (None: no neighbour); returns (from_lo, from_hi)."""
+        self.s.mail[(self.rank, -1)] = None if to_lo is None else to_lo.copy()
+        self.s.mail[(self.rank, +1)] = None if to_hi is None else to_hi.copy()
+        self.s.barrier.wait()
+        from_lo = self.s.mail.get((self.rank - 1, +1)) if self.rank > 0 else None
+        from_hi = self.s.mail.get((self.rank + 1, -1)) if self.rank + 1 < self.nranks else None
+        self.s.barrier.wait()
+        return from_lo, from_hi
+
+
+class TorchComm:
+    """torch.distributed backend (gloo on CPU)."""
+
+    def __init__(self):
+        import torch.distributed as dist
+        self.dist = dist
+        self.rank, self.nranks = dist.get_rank(), dist.get_world_size()
+
+    def allreduce(self, value, op="sum"):
+        import torch
+        t = torch.tensor(np.atleast_1d(np.asarray(value, dtype=np.float64)))
+        self.dist.all_reduce(t, op={"sum": self.dist.ReduceOp.SUM, "max": self.dist.ReduceOp.MAX, "min": self.dist.ReduceOp.MIN}[op])
+        out = t.numpy()
+        return float(out[0]) if np.ndim(value) == 0 else out
+
+    def exchange(self, to_lo, to_hi):
+        import torch
+        reqs, from_lo, from_hi = [], None, None
+        if to_lo is not None:
+            from_lo = torch.empty(to_lo.size, dtype=torch.float64)
+            reqs.append(self.dist.isend(torch.from_numpy(np.ascontiguousarray(to_lo)), self.rank - 1))
+            reqs.append(self.dist.irecv(from_lo, self.rank - 1))
+        if to_hi is not None:
+            from_hi = torch.empty(to_hi.size, dtype=torch.float64)
+            reqs.append(self.dist.isend(torch.from_numpy(np.ascontiguousarray(to_hi)), self.rank + 1))
+            reqs.append(self.dist.irecv(from_hi, self.rank + 1))
+        for r in reqs:
+            r.wait()
+        return (None if from_lo is None else from_lo.numpy()), (None if from_hi is None else from_hi.numpy())
+
+
+# ----------------------------------------------------------------------------------------------------------
+# one rank
+# ----------------------------------------------------------------------------------------------------------
+class SlabRank:
+    """Local problem of one rank: slab [lo, hi) of the last axis incl. overlap, owned layers [b0, b1)."""
+
+    def __init__(self, make_spec, cells, comm):
+        self.comm = comm
+        dim = len(cells)
+        self.layers = cells[-1]
+        self.lo, self.hi, self.b0, self.b1 = problems.slab_partition(self.layers, comm.nranks, comm.rank)
+        self.spec = make_spec((self.lo, self.hi)) if comm.nranks > 1 else make_spec(None)
+        spec = self.spec
+        # the local oracle works on the local box: cut the geometry, mark processor boundaries as "no scvf"
+        import copy
+        loc = copy.copy(spec)
+        h = (spec.upper[-1] - spec.lower[-1]) / cells[-1]
+        loc.cells = tuple(cells[:-1]) + (self.hi - self.lo,)
+        loc.lower = tuple(spec.lower[:-1]) + (spec.lower[-1] + self.lo * h,)
+        loc.upper = tuple(spec.upper[:-1]) + (spec.lower[-1] + self.hi * h,)
+        loc.bc_type = dict(spec.bc_type)
+        loc.bc_values = dict(spec.bc_values)
+        nf = int(np.prod(cells[:-1]))
+        if self.lo > 0:
+            loc.bc_type[2 * (dim - 1)] = np.full(nf, problems.BC_NONE, dtype=np.int32)
+            loc.bc_values[2 * (dim - 1)] = np.zeros((nf, spec.num_eq))
+        if self.hi < self.layers:
+            loc.bc_type[2 * (dim - 1) + 1] = np.full(nf, problems.BC_NONE, dtype=np.int32)
+            loc.bc_values[2 * (dim - 1) + 1] = np.zeros((nf, spec.num_eq))
+        loc.slab = None
+        nodes = problems.node_coords(cells, spec.lower, spec.upper)
+        nodes[-1] = nodes[-1][self.lo:self.hi + 1]
+        loc.node_coords = nodes
+        self.local = loc
+        self.o = O.Oracle(loc)
+        self.b = self.o.b
+        self.n = self.o.n
+        self.plane = nf
+        own = np.zeros(self.hi - self.lo, dtype=bool)
+        own[self.b0 - self.lo:self.b1 - self.lo] = True
+        self.owner = np.repeat(np.repeat(own, nf), self.b)          # per scalar dof
+
+    # copyOwnerToAll for slabs with overlap 1: my first / last OWNED plane -> neighbour's overlap plane
+    def copy_owner_to_all(self, v):
+        pb = self.plane * self.b
+        o0, o1 = (self.b0 - self.lo) * pb, (self.b1 - self.lo) * pb
+        to_lo = v[o0:o0 + pb] if self.lo > 0 else None
+        to_hi = v[o1 - pb:o1] if self.hi < self.layers else None
+        from_lo, from_hi = self.comm.exchange(to_lo, to_hi)
+        if from_lo is not None:
+            v[o0 - pb:o0] = from_lo
+        if from_hi is not None:
+            v[o1:o1 + pb] = from_hi
+
+    def dot(self, a, b):
+        return self.comm.allreduce(float(np.dot(a[self.owner], b[self.owner])), "sum")
+
+    def apply_operator(self, jac, x):
+        y = O.spmv(self.n, self.b, self.o.rowptr, self.o.colidx, jac, x)
+        y[~self.owner] = 0.0                                         # project()
+        return y
+
+    def bicgstab(self, jac, rhs, reduction=1e-6, maxit=250):
+        """Dune::BiCGSTABSolver::apply with the overlapping-Schwarz operator / scalar product / BlockPreconditioner; x0 = 0."""
+        ilu, st = O.ilu0_factor(self.n, self.b, self.o.rowptr, self.o.colidx, jac)
+        st = int(self.comm.allreduce(float(st), "max"))
+        if st != 0:
+            return np.zeros_like(rhs), 2, 0, 1.0
+
+        def prec(d):
+            v = O.ilu0_apply(self.n, self.b, self.o.rowptr, self.o.colidx, ilu, d)
+            self.copy_owner_to_all(v)
+            return v
+
+        x = np.zeros_like(rhs)
+        self.copy_owner_to_all(x)                                    # BlockPreconditioner::pre
+        r = rhs - O.spmv(self.n, self.b, self.o.rowptr, self.o.colidx, jac, x)
+        r[~self.owner] = 0.0                                         # applyscaleadd(-1, x, r) projects r
+        rt = r.copy()
+        norm0 = math.sqrt(self.dot(r, r))
+        norm = norm0
+        conv = lambda nrm: nrm < reduction * norm0 or nrm < 1e-30
+        if not math.isfinite(norm0):
+            return x, 3, 0, 1.0
+        if conv(norm0):
+            return x, 0, 0, (1.0 if norm0 > 0 else 0.0)
+        p = np.zeros_like(rhs)
+        v = np.zeros_like(rhs)
+        rho = alpha = omega = 1.0
+        it = 0.5
+        status = 1
+        while it < maxit:
+            rho_new = self.dot(rt, r)
+            if abs(rho) <= 1e-80 or abs(omega) <= 1e-80:
+                status = 2
+                break
+            if it < 1:
+                p = r.copy()
+            else:
+                beta = (rho_new / rho) * (alpha / omega)
+                p = (p + (-omega) * v) * beta + r
+            y = prec(p)
+            v = self.apply_operator(jac, y)
+            h = self.dot(rt, v)
+            if abs(h) < 1e-80:
+                status = 2
+                break
+            alpha = rho_new / h
+            x += alpha * y
+            r += (-alpha) * v
+            norm = math.sqrt(self.dot(r, r))
+            if not math.isfinite(norm):
+                status = 3
+                break
+            if conv(norm):
+                status = 0
+                break
+            it += 0.5
+            y = prec(r)
+            t = self.apply_operator(jac, y)
+            omega = self.dot(t, r) / self.dot(t, t)
+            x += omega * y
+            r += (-omega) * t
+            rho = rho_new
+            norm = math.sqrt(self.dot(r, r))
+            if not math.isfinite(norm):
+                status = 3
+                break
+            if conv(norm):
+                status = 0
+                break
+            it += 0.5
+        return x, status, int(math.ceil(min(it, maxit))), (norm / norm0 if norm0 > 0 else 0.0)
+
+    def newton(self, u0, prev, lin_reduction=1e-6, lin_maxit=250, max_rel_shift=1e-8, min_steps=2, max_steps=18):
+        """NewtonSolver::solveImpl_ (nonlinear/newtonsolver.hh:976-1072) on the local slab; u0/prev are LOCAL arrays."""
+        u = np.ascontiguousarray(u0, dtype=np.float64).reshape(-1).copy()
+        prev = np.ascontiguousarray(prev, dtype=np.float64).reshape(-1)
+        steps, shift, last_shift, converged = 0, 0.0, 0.0, False
+        lin_its = []
+        while True:
+            if steps >= min_steps:
+                if converged:
+                    break
+                if steps >= max_steps and not (shift * 4.0 < last_shift):
+                    break
+            last_shift = shift
+            res, jac = self.o.assemble(u, prev)
+            dx, st, its, red = self.bicgstab(jac, res, lin_reduction, lin_maxit)
+            lin_its.append(its)
+            if st != 0:
+                return u, st, steps, lin_its
+            u_new = u + (-1.0) * dx
+            sh = np.abs(u_new - u) / np.maximum(1.0, np.abs(u_new + u) * 0.5)
+            shift = self.comm.allreduce(float(sh[self.owner].max()), "max")
+            u = u_new
+            steps += 1
+            converged = shift <= max_rel_shift
+        return u, (0 if converged else 1), steps, lin_its
+
+
+def run_threads(make_spec, cells, nranks, fn):
+    """Runs fn(SlabRank) on `nranks` threads; returns the per-rank results."""
+    shared = ThreadComm.Shared(nranks)
+    out = [None] * nranks
+    err = []
+
+    def work(r):
+        try:
+            out[r] = fn(SlabRank(make_spec, cells, ThreadComm(shared, r)))
+        except BaseException as e:       # noqa: BLE001
+            err.append(e)
+            shared.barrier.abort()
+
+    th = [threading.Thread(target=work, args=(r,)) for r in range(nranks)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    if err:
+        raise err[0]
+    return out
+
+
+def gather_owned(results, cells, nranks, b):
+    """Concatenate the owned layers of per-rank local vectors (x fastest) into the global vector."""
+    nf = int(np.prod(cells[:-1]))
+    parts = []
+    for r, v in enumerate(results):
+        lo, hi, b0, b1 = problems.slab_partition(cells[-1], nranks, r)
+        parts.append(np.asarray(v).reshape(hi - lo, nf * b)[b0 - lo:b1 - lo].reshape(-1))
+    return np.concatenate(parts)

@@ -50,6 +50,8 @@ def lib():
         vp = C.c_void_p
         L.orc_create.restype = vp
         L.orc_create.argtypes = [C.c_int, C.c_int, _ip, _dp, _dp]
+        L.orc_create_tensor.restype = vp
+        L.orc_create_tensor.argtypes = [C.c_int, C.c_int, _ip, _dp, _dp, _dp]
         L.orc_destroy.argtypes = [vp]
         L.orc_default_options.argtypes = [C.POINTER(OrcOptions)]
         L.orc_set_options.argtypes = [vp, C.POINTER(OrcOptions)]
@@ -107,7 +109,13 @@ class Oracle:
         cells = np.ascontiguousarray(spec.cells, dtype=np.int32)
         lower = np.ascontiguousarray(spec.lower, dtype=np.float64)
         upper = np.ascontiguousarray(spec.upper, dtype=np.float64)
-        self.h = C.c_void_p(L.orc_create(spec.model, spec.dim, cells, lower, upper))
+        nodes = getattr(spec, "node_coords", None)
+        if nodes is not None:
+            # explicit node coordinates per axis (a slab of a larger YaspGrid keeps the GLOBAL coordinates origin + i*h)
+            xs = [np.ascontiguousarray(nodes[a], dtype=np.float64) if a < spec.dim else np.array([0.0, 1.0]) for a in range(3)]
+            self.h = C.c_void_p(L.orc_create_tensor(spec.model, spec.dim, cells, xs[0], xs[1], xs[2]))
+        else:
+            self.h = C.c_void_p(L.orc_create(spec.model, spec.dim, cells, lower, upper))
         self.opt = OrcOptions()
         L.orc_default_options(C.byref(self.opt))
         o = spec.options

@@ -1,0 +1,148 @@
+"""N > 1 path on CPU: slab decomposition with overlap 1, owner-masked scalar products, copyOwnerToAll halo exchange and
+per-rank ILU0 (overlapping Schwarz), run as 2 real processes over torch.distributed/gloo and compared with the
+in-process multi-rank reference and with the single-domain solve.  The GPU path implements the same
+sequence with NCCL (dumux_b200/csrc/dist.cu); tests/test_gpu_dist.py compares it with the same reference."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from dumux_b200 import problems
+from oracle import dist_oracle as D
+from oracle import oracle_py as O
+
+CELLS = (12, 10, 14)
+
+
+def _make_spec(slab):
+    return problems.twop_lens(CELLS, law="bc", heterogeneity_sigma=0.4, slab=slab, plane_rng=True)
+
+
+def _perturb(spec, slab, seed=3):
+    """deterministic global perturbation, cut to the slab"""
+    n = int(np.prod(CELLS))
+    rng = np.random.RandomState(seed)
+    sn = rng.uniform(0.0, 0.25, size=n)
+    dp = rng.uniform(-40.0, 40.0, size=n)
+    if slab is not None:
+        nf = CELLS[0] * CELLS[1]
+        sn = sn.reshape(CELLS[2], nf)[slab[0]:slab[1]].reshape(-1)
+        dp = dp.reshape(CELLS[2], nf)[slab[0]:slab[1]].reshape(-1)
+    u = spec.initial.copy()
+    u[:, 0] += dp
+    u[:, 1] = sn
+    return u
+
+
+def _rank_job(rank_obj):
+    """what every rank does: assemble its slab, solve to a tight tolerance, take one Newton solve"""
+    slab = (rank_obj.lo, rank_obj.hi) if rank_obj.comm.nranks > 1 else None
+    cur = _perturb(rank_obj.spec, slab).reshape(-1)
+    prev = rank_obj.spec.initial.reshape(-1)
+    res, jac = rank_obj.o.assemble(cur, prev)
+    x, st, its, red = rank_obj.bicgstab(jac, res, reduction=1e-11, maxit=500)
+    u, nst, nsteps, lin_its = rank_obj.newton(rank_obj.spec.initial, rank_obj.spec.initial)
+    return {"x": x, "st": st, "its": its, "red": red, "res": res, "u": u, "nst": nst, "nsteps": nsteps, "lin_its": lin_its,
+            "owner": rank_obj.owner.copy()}
+
+
+def _gloo_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        out = _rank_job(D.SlabRank(_make_spec, CELLS, D.TorchComm()))
+        q.put((rank, out))
+    finally:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+@pytest.fixture(scope="module")
+def reference_runs():
+    single = D.run_threads(_make_spec, CELLS, 1, _rank_job)[0]
+    two = D.run_threads(_make_spec, CELLS, 2, _rank_job)
+    three = D.run_threads(_make_spec, CELLS, 3, _rank_job)
+    return single, two, three
+
+
+def test_partition_layout():
+    """overlap 1: rank r holds its owned layers plus one layer of each neighbour; every layer has exactly one owner"""
+    for P in (2, 3, 4):
+        owners = np.zeros(CELLS[2], dtype=int)
+        for r in range(P):
+            lo, hi, b0, b1 = problems.slab_partition(CELLS[2], P, r)
+            assert lo == max(0, b0 - 1) and hi == min(CELLS[2], b1 + 1)
+            owners[b0:b1] += 1
+        assert np.all(owners == 1)
+
+
+def test_overlap_rows_are_incomplete_but_owned_rows_match(reference_runs):
+    """Residual rows of owned cells equal the single-domain rows bit for bit; the overlap rows lack the outer-face flux."""
+    single, two, _ = reference_runs
+    nf = CELLS[0] * CELLS[1] * 2
+    glob = single["res"].reshape(CELLS[2], nf)
+    for r, out in enumerate(two):
+        lo, hi, b0, b1 = problems.slab_partition(CELLS[2], 2, r)
+        loc = out["res"].reshape(hi - lo, nf)
+        assert np.array_equal(loc[b0 - lo:b1 - lo], glob[b0:b1])
+        ghost = [k for k in range(lo, hi) if not (b0 <= k < b1)]
+        assert ghost and any(not np.array_equal(loc[k - lo], glob[k]) for k in ghost)
+
+
+@pytest.mark.parametrize("P", [2, 3])
+def test_schwarz_bicgstab_converges_to_single_domain_solution(reference_runs, P):
+    single, two, three = reference_runs
+    runs = two if P == 2 else three
+    assert single["st"] == 0 and all(o["st"] == 0 for o in runs)
+    x = D.gather_owned([o["x"] for o in runs], CELLS, P, 2)
+    assert np.linalg.norm(x - single["x"]) <= 1e-8 * np.linalg.norm(single["x"])
+    # per-rank ILU0 is a weaker preconditioner than the global one: more iterations, the same for every rank
+    assert len({o["its"] for o in runs}) == 1 and runs[0]["its"] >= single["its"]
+    # after copyOwnerToAll the overlap copies agree with the owner's values
+    nf = CELLS[0] * CELLS[1] * 2
+    for r in range(P - 1):
+        lo0, hi0, b00, b10 = problems.slab_partition(CELLS[2], P, r)
+        lo1, hi1, b01, b11 = problems.slab_partition(CELLS[2], P, r + 1)
+        a = runs[r]["x"].reshape(hi0 - lo0, nf)
+        b = runs[r + 1]["x"].reshape(hi1 - lo1, nf)
+        assert np.array_equal(a[b10 - lo0], b[b10 - lo1]) and np.array_equal(a[b10 - 1 - lo0], b[b10 - 1 - lo1])
+
+
+@pytest.mark.parametrize("P", [2, 3])
+def test_newton_iteration_count_independent_of_partition(reference_runs, P):
+    """north_star: same Newton iteration count, fields to 1e-8 relative L2 (BiCGSTAB counts may depend on P)."""
+    single, two, three = reference_runs
+    runs = two if P == 2 else three
+    assert single["nst"] == 0 and all(o["nst"] == 0 for o in runs)
+    assert all(o["nsteps"] == single["nsteps"] for o in runs)
+    u = D.gather_owned([o["u"] for o in runs], CELLS, P, 2).reshape(-1, 2)
+    us = single["u"].reshape(-1, 2)
+    assert np.linalg.norm(u[:, 0] - us[:, 0]) <= 1e-8 * np.linalg.norm(us[:, 0])
+    assert np.linalg.norm(u[:, 1] - us[:, 1]) <= 1e-8 * max(1.0, np.linalg.norm(us[:, 1]))
+
+
+def test_two_processes_over_gloo_match_reference(reference_runs):
+    """world_size 2 over torch.distributed/gloo: identical to the in-process reference (same arithmetic, real messages)."""
+    import torch.multiprocessing as mp
+    _, two, _ = reference_runs
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29650 + os.getpid() % 200
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=300) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r in range(2):
+        assert got[r]["st"] == 0 and got[r]["its"] == two[r]["its"]
+        assert np.array_equal(got[r]["x"], two[r]["x"])
+        assert got[r]["nsteps"] == two[r]["nsteps"] and got[r]["lin_its"] == two[r]["lin_its"]
+        assert np.array_equal(got[r]["u"], two[r]["u"])
