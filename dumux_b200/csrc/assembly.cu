@@ -17,7 +17,9 @@
 //
 // Floating-point contract: compiled with -fmad=false; every expression is written in the operation order of
 // the reference (see the op-order notes inline) so results are reproducible against the CPU oracle.
+#include <algorithm>
 #include <cfloat>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -495,6 +497,535 @@ __global__ void __launch_bounds__(128) assemble_kernel(AsmParams P, int with_jac
     }
 }
 
+// ================================================================================================
+// Fused tile kernel (the production path).
+//
+// One CTA owns a 32 x 8 column of cells and marches along the last axis over `zchunk` layers.  Per layer it
+//   1. evaluates the secondary variables (TwoPVolumeVariables::update / OnePVolumeVariables::update) of the next layer's
+//      tile + one-cell halo at the base and FD-deflected states ONCE into a three-layer shared-memory ring
+//      (material-law pows share their log, see law_eval3), together with K and the reciprocal FD denominators;
+//   2. assembles the rows of its 256 cells from shared memory: storage, source, 2*dim TPFA fluxes at the base state,
+//      at the own deflections (diagonal block) and at each neighbour's deflections (off-diagonal blocks), FD quotients
+//      through div_by (correctly rounded, shared reciprocal), 32-byte block stores into the BCRS values.
+// HBM traffic per cell: cur, prev, K, phi, region, 3 transmissibilities, rowptr in; residual + 7 blocks out -- no
+// secondary-variable records in global memory.  Arithmetic and operation order are those of assemble_kernel above
+// (bit-identical results).
+// ================================================================================================
+constexpr int AT_TX = 32, AT_TY = 8, AT_THREADS = AT_TX * AT_TY;
+constexpr int AT_HX = AT_TX + 2, AT_HY = AT_TY + 2, AT_HC = AT_HX * AT_HY;
+
+// shared-memory record of one cell, SoA: field f of halo slot h lives at rec[f * AT_HC + h]
+template <int MODEL, bool TABLE, int NDR>
+struct RecLayout {
+    static constexpr int NB = (MODEL == DMX_MODEL_2P) ? 2 : 1;
+    static constexpr int NS = (MODEL == DMX_MODEL_2P) ? 3 : (TABLE ? 2 : 0);   // 2p: pc, rho_w*mob_w, rho_n*mob_n; 1p table: rho, rho*mob
+    static constexpr int U = 0;               // primary variables
+    static constexpr int RD = NB;             // reciprocal FD denominators per primary variable
+    static constexpr int KF = 2 * NB;         // permeability
+    static constexpr int ST = 2 * NB + 1;     // states: base, then one per deflection of the state-changing primary variable
+    static constexpr int NF = ST + NS * (1 + NDR);
+};
+
+template <int ND>
+__device__ __forceinline__ double fd_den(double eps)
+{
+    if (ND == 1) return eps;              // delta = 0 + eps
+    if (ND == 2) return eps + eps;        // delta = (0 + eps) + eps
+    return 12.0 * eps;
+}
+// fd_quotient with the division by the step replaced by div_by (same bits)
+template <int ND>
+__device__ __forceinline__ double fd_quotient_r(int method, double f0, const double* f, double eps, double rden)
+{
+    double d;
+    if (ND == 1) {
+        if (method >= 0) { d = f[0]; d -= f0; }
+        else { d = f0; d -= f[0]; }
+    } else if (ND == 2) {
+        d = f[0];
+        d -= f[1];
+    } else {
+        d = f[0];
+        d -= f[1];
+        d *= 8.0;
+        d += f[2];
+        d -= f[3];
+    }
+    return div_by(d, fd_den<ND>(eps), rden);
+}
+
+// secondary variables of cell C into its shared-memory record
+template <int MODEL, bool TABLE, int ND, bool JAC>
+__device__ __forceinline__ void fill_cell(const AsmParams& P, const MaterialLaw* slaws, size_t C, double* rec)
+{
+    using L = RecLayout<MODEL, TABLE, JAC ? ND : 0>;
+    rec[L::KF * AT_HC] = __ldg(P.K + C);
+    if constexpr (MODEL == DMX_MODEL_2P) {
+        const double2 u = __ldg(reinterpret_cast<const double2*>(P.cur) + C);
+        rec[(L::U + 0) * AT_HC] = u.x;
+        rec[(L::U + 1) * AT_HC] = u.y;
+        const MaterialLaw& law = slaws[__ldg(P.region + C)];
+        Law3 c = law_eval3_call(&law, 1 - u.y);
+        rec[(L::ST + 0) * AT_HC] = c.pc;
+        rec[(L::ST + 1) * AT_HC] = P.rho[0] * div_by(c.krw, P.mu[0], P.rmu[0]);
+        rec[(L::ST + 2) * AT_HC] = P.rho[1] * div_by(c.krn, P.mu[1], P.rmu[1]);
+        if constexpr (JAC) {
+            const double epsP = fd_eps(P, u.x, 0), epsS = fd_eps(P, u.y, 1);
+            rec[(L::RD + 0) * AT_HC] = 1.0 / fd_den<ND>(epsP);
+            rec[(L::RD + 1) * AT_HC] = 1.0 / fd_den<ND>(epsS);
+#pragma unroll
+            for (int k = 0; k < ND; ++k) {
+                const double Snk = fd_deflect(P.fd_method, k, u.y, epsS);
+                c = law_eval3_call(&law, 1 - Snk);
+                rec[(L::ST + 3 * (1 + k) + 0) * AT_HC] = c.pc;
+                rec[(L::ST + 3 * (1 + k) + 1) * AT_HC] = P.rho[0] * div_by(c.krw, P.mu[0], P.rmu[0]);
+                rec[(L::ST + 3 * (1 + k) + 2) * AT_HC] = P.rho[1] * div_by(c.krn, P.mu[1], P.rmu[1]);
+            }
+        }
+    } else {
+        const double p = __ldg(P.cur + C);
+        rec[L::U * AT_HC] = p;
+        double eps = 0.0;
+        if constexpr (JAC) {
+            eps = fd_eps(P, p, 0);
+            rec[L::RD * AT_HC] = 1.0 / fd_den<ND>(eps);
+        }
+        if constexpr (TABLE) {
+            double rho, mu;
+            table_interp2(P.table, p, &rho, &mu);
+            rec[(L::ST + 0) * AT_HC] = rho;
+            rec[(L::ST + 1) * AT_HC] = rho * (1.0 / mu);
+            if constexpr (JAC) {
+#pragma unroll
+                for (int k = 0; k < ND; ++k) {
+                    table_interp2(P.table, fd_deflect(P.fd_method, k, p, eps), &rho, &mu);
+                    rec[(L::ST + 2 * (1 + k) + 0) * AT_HC] = rho;
+                    rec[(L::ST + 2 * (1 + k) + 1) * AT_HC] = rho * (1.0 / mu);
+                }
+            }
+        }
+    }
+}
+
+// state of a cell at the base point (pv < 0) or at deflection (pv, k), from its shared-memory record
+template <int MODEL, bool TABLE, int NDR, int NPH>
+__device__ __forceinline__ void tile_state(const AsmParams& P, const double* rec, int pv, int k, const double* uC, const double* epsC,
+                                           CellState<NPH>& s, double* Sn_out)
+{
+    using L = RecLayout<MODEL, TABLE, NDR>;
+    if constexpr (MODEL == DMX_MODEL_2P) {
+        double pw = uC[0], Sn = uC[1];
+        int st = 0;
+        if (pv == 0) pw = fd_deflect(P.fd_method, k, pw, epsC[0]);
+        if (pv == 1) { Sn = fd_deflect(P.fd_method, k, Sn, epsC[1]); st = 1 + k; }
+        const double pc = rec[(L::ST + 3 * st + 0) * AT_HC];
+        s.p[0] = pw;
+        s.p[NPH - 1] = pw + pc;
+        s.up[0] = rec[(L::ST + 3 * st + 1) * AT_HC];
+        s.up[NPH - 1] = rec[(L::ST + 3 * st + 2) * AT_HC];
+        s.rho[0] = P.rho[0];
+        s.rho[NPH - 1] = P.rho[1];
+        *Sn_out = Sn;
+    } else {
+        double p = uC[0];
+        if (pv == 0) p = fd_deflect(P.fd_method, k, p, epsC[0]);
+        s.p[0] = p;
+        if constexpr (TABLE) {
+            const int st = (pv == 0) ? 1 + k : 0;
+            s.rho[0] = rec[(L::ST + 2 * st + 0) * AT_HC];
+            s.up[0] = rec[(L::ST + 2 * st + 1) * AT_HC];
+        } else {
+            s.rho[0] = P.rho[0];
+            s.up[0] = P.rho[0] * (1.0 / P.mu[0]);
+        }
+        *Sn_out = 0.0;
+    }
+}
+
+// as face_flux, the division by the neighbour's half transmissibility through its reciprocal (TABLE only)
+template <int NPH, bool TABLE>
+__device__ __forceinline__ void face_flux_r(const FaceData<NPH>& F, double rtJ, const CellState<NPH>& sI, const CellState<NPH>& sJ,
+                                            bool fullUpwind, double w, double* out)
+{
+#pragma unroll
+    for (int ph = 0; ph < NPH; ++ph) {
+        double f = F.tij * (sI.p[ph] - sJ.p[ph]);
+        if (F.grav) {
+            if constexpr (TABLE) {
+                const double rho = F.interior ? (sI.rho[ph] + sJ.rho[ph]) * 0.5 : sJ.rho[ph];
+                f = f + rho * F.area * F.alphaI;
+                if (F.interior) f -= div_by(rho * F.tij, F.tJ, rtJ) * (F.alphaI - F.alphaJ);
+            } else {
+                f = f + F.c1[ph];
+                if (F.interior) f -= F.c2[ph];
+            }
+        }
+        double mult;
+        if (fullUpwind) mult = signbit(f) ? sJ.up[ph] : sI.up[ph];
+        else if (signbit(f)) mult = w * sJ.up[ph] + (1.0 - w) * sI.up[ph];
+        else mult = w * sI.up[ph] + (1.0 - w) * sJ.up[ph];
+        out[ph] = f * mult;
+    }
+}
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+template <int NB>
+__device__ __forceinline__ void store_block(double* dst, const double (&blk)[NB][NB])
+{
+    if constexpr (NB == 2) {
+        asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst), "d"(blk[0][0]), "d"(blk[0][1]), "d"(blk[1][0]), "d"(blk[1][1])
+                     : "memory");
+    } else
+        dst[0] = blk[0][0];
+}
+
+template <int MODEL, bool TABLE, int ND, bool JAC>
+__global__ void __launch_bounds__(AT_THREADS, (ND == 1) ? 2 : 1) assemble_tile_kernel(const AsmParams P)
+{
+    constexpr int NDR = JAC ? ND : 0;
+    using L = RecLayout<MODEL, TABLE, NDR>;
+    constexpr int NB = L::NB, NPH = NB;
+    constexpr int NDE = JAC ? ND : 1;       // array extents (unused when !JAC)
+    extern __shared__ __align__(16) double sm[];
+    MaterialLaw* slaws = reinterpret_cast<MaterialLaw*>(sm + 3 * L::NF * AT_HC);
+
+    const int t = threadIdx.x, li = t & (AT_TX - 1), lj = t / AT_TX;
+    const int nx = P.nc[0], ny = P.nc[1], nz = P.nc[2];
+    const int dim = P.dim, va = dim - 1;
+    const int ntx = (nx + AT_TX - 1) / AT_TX;
+    const int i0 = ((int)blockIdx.x % ntx) * AT_TX, j0 = ((int)blockIdx.x / ntx) * AT_TY;
+    const int kz0 = (int)blockIdx.y * P.zchunk, kz1 = min(nz, kz0 + P.zchunk);
+    const int i = i0 + li, j = j0 + lj;
+    const bool own = i < nx && j < ny;
+    const bool fullUpwind = (P.upwind_weight == 1.0);
+    const double w = P.upwind_weight;
+    const double extr = P.extrusion;
+
+    if constexpr (MODEL == DMX_MODEL_2P) {
+        const int words = P.nlaws * (int)(sizeof(MaterialLaw) / sizeof(double));
+        for (int q = t; q < words; q += AT_THREADS) reinterpret_cast<double*>(slaws)[q] = reinterpret_cast<const double*>(P.laws)[q];
+        __syncthreads();
+    }
+
+    auto slot_of = [&](int k) { return sm + ((k + 3) % 3) * (L::NF * AT_HC); };
+    auto fill = [&](int k, bool core_only) {
+        if (k < 0 || k >= nz) return;
+        double* dst = slot_of(k);
+        for (int h = t; h < AT_HC; h += AT_THREADS) {
+            const int hi = h % AT_HX, hj = h / AT_HX;
+            const bool xh = (hi == 0 || hi == AT_HX - 1), yh = (hj == 0 || hj == AT_HY - 1);
+            if ((xh && yh) || (core_only && (xh || yh))) continue;
+            const int ci = i0 - 1 + hi, cj = j0 - 1 + hj;
+            if (ci < 0 || ci >= nx || cj < 0 || cj >= ny) continue;
+            fill_cell<MODEL, TABLE, ND, JAC>(P, slaws, (size_t)ci + (size_t)nx * (cj + (size_t)ny * k), dst + h);
+        }
+    };
+
+    // in-plane geometry of this thread's column
+    const int h0 = (lj + 1) * AT_HX + (li + 1);
+    const double wx = own ? P.width[0][i] : 1.0;
+    const double wy = (own && dim > 1) ? P.width[1][j] : 1.0;
+    bool exxy[4];
+    exxy[0] = i > 0; exxy[1] = i + 1 < nx; exxy[2] = (dim > 1) && j > 0; exxy[3] = (dim > 1) && j + 1 < ny;
+
+    fill(kz0 - 1, true);
+    fill(kz0, false);
+    double tz_below = 0.0;
+    if (own && dim == 3 && kz0 > 0) tz_below = P.tij[2][(size_t)i + (size_t)nx * (j + (size_t)ny * (kz0 - 1))];
+
+    for (int k = kz0; k < kz1; ++k) {
+        // global data of this thread's own row, requested before the secondary-variable phase so that the DRAM latency
+        // overlaps it; the next layer's lines are pulled into L2 one iteration ahead
+        const size_t I = (size_t)i + (size_t)nx * (j + (size_t)ny * k);
+        double g_tij[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, g_phi = 0.0, g_prev = 0.0;
+        int g_rowStart = 0;
+        if (own) {
+            if (exxy[0]) g_tij[0] = __ldg(P.tij[0] + I - 1);
+            if (exxy[1]) g_tij[1] = __ldg(P.tij[0] + I);
+            if (exxy[2]) g_tij[2] = __ldg(P.tij[1] + I - nx);
+            if (exxy[3]) g_tij[3] = __ldg(P.tij[1] + I);
+            if (dim > 2 && k + 1 < nz) g_tij[5] = __ldg(P.tij[2] + I);
+            g_tij[4] = tz_below;
+            if constexpr (JAC) g_rowStart = __ldg(P.rowptr + I);
+            if (!P.stationary) {
+                g_phi = __ldg(P.phi + I);
+                if constexpr (MODEL == DMX_MODEL_2P) g_prev = __ldg(P.prev + I * NB + NB - 1);
+                else g_prev = __ldg(P.prev + I);
+            }
+            if (k + 1 < kz1) {
+                const size_t In = I + (size_t)nx * ny;
+                prefetch_l2(P.tij[0] + In);
+                if (dim > 1) prefetch_l2(P.tij[1] + In);
+                if (dim > 2) prefetch_l2(P.tij[2] + In);
+                if constexpr (JAC) prefetch_l2(P.rowptr + In);
+                if (!P.stationary) { prefetch_l2(P.phi + In); prefetch_l2(P.prev + In * NB); }
+            }
+        }
+        if (own && k + 2 < nz && k + 2 <= kz1) {
+            const size_t I2 = I + 2 * (size_t)nx * ny;
+            prefetch_l2(P.cur + I2 * NB);
+            prefetch_l2(P.K + I2);
+            if constexpr (MODEL == DMX_MODEL_2P) prefetch_l2(P.region + I2);
+        }
+        fill(k + 1, k + 1 == kz1);
+        __syncthreads();
+        if (own) {
+            const int ci[3] = {i, j, k};
+            const double* recI = slot_of(k) + h0;
+            const double* recN[6] = {recI - 1, recI + 1, recI - AT_HX, recI + AT_HX, slot_of(k - 1) + h0, slot_of(k + 1) + h0};
+
+            double uI[NB], epsI[NB], rdI[NB];
+#pragma unroll
+            for (int e = 0; e < NB; ++e) {
+                uI[e] = recI[(L::U + e) * AT_HC];
+                epsI[e] = fd_eps(P, uI[e], e);
+                rdI[e] = JAC ? recI[(L::RD + e) * AT_HC] : 0.0;
+            }
+            CellState<NPH> sI0, sId[NB][NDE];
+            double SnI0, SnId[NB][NDE];
+            tile_state<MODEL, TABLE, NDR, NPH>(P, recI, -1, 0, uI, epsI, sI0, &SnI0);
+            if constexpr (JAC) {
+#pragma unroll
+                for (int pv = 0; pv < NB; ++pv)
+#pragma unroll
+                    for (int kk = 0; kk < ND; ++kk) tile_state<MODEL, TABLE, NDR, NPH>(P, recI, pv, kk, uI, epsI, sId[pv][kk], &SnId[pv][kk]);
+            }
+
+            const double KI = recI[L::KF * AT_HC];
+            const double wz = (dim > 2) ? P.width[2][k] : 1.0;
+            // volume = ((1*w0)*w1)*w2 (AxisAlignedCubeGeometry::volume)
+            double vol = 1.0;
+            vol *= wx;
+            if (dim > 1) vol *= wy;
+            if (dim > 2) vol *= wz;
+
+            double R0[NB], Rd[NB][NDE][NB];
+#pragma unroll
+            for (int e = 0; e < NB; ++e) {
+                double source = P.q ? P.q[I * NB + e] : 0.0;      // fvlocalresidual.hh:319-333
+                source *= vol * extr;
+                double r = 0.0;
+                r -= source;
+                R0[e] = r;
+#pragma unroll
+                for (int pv = 0; pv < NB; ++pv)
+#pragma unroll
+                    for (int kk = 0; kk < NDE; ++kk) Rd[pv][kk][e] = r;
+            }
+
+            bool ex[6];
+            ex[0] = exxy[0]; ex[1] = exxy[1]; ex[2] = exxy[2]; ex[3] = exxy[3];
+            ex[4] = (dim > 2) && k > 0;
+            ex[5] = (dim > 2) && k + 1 < nz;
+            int pos[6], posDiag = 0;
+            if constexpr (JAC) {
+                const int rowStart = g_rowStart;
+                posDiag = rowStart + (ex[4] ? 1 : 0) + (ex[2] ? 1 : 0) + (ex[0] ? 1 : 0);
+                pos[4] = rowStart;
+                pos[2] = rowStart + (ex[4] ? 1 : 0);
+                pos[0] = pos[2] + (ex[2] ? 1 : 0);
+                pos[1] = posDiag + 1;
+                pos[3] = pos[1] + (ex[1] ? 1 : 0);
+                pos[5] = pos[3] + (ex[3] ? 1 : 0);
+            }
+#pragma unroll
+            for (int s = 0; s < 6; ++s) {
+                const int a = s >> 1;
+                if (a >= dim) continue;
+                const bool hi = (s & 1);
+                // face area = product of the widths of the other axes, ascending axis order
+                double area = 1.0;
+                if (a != 0) area *= wx;
+                if (a != 1 && dim > 1) area *= wy;
+                if (a != 2 && dim > 2) area *= wz;
+                FaceData<NPH> F;
+                F.area = area;
+                F.grav = P.enable_gravity && (a == va);
+                const double ng = hi ? -P.gravity : P.gravity;       // n.g with g = -gravity*e_va
+                F.alphaI = KI * ng * extr;                           // vtmv(n,K,g)*extrusion (common/math.hh:908-913)
+                F.alphaJ = 0.0;
+                F.tJ = 1.0;
+                double rtJ = 1.0;
+                if (ex[s]) {
+                    const double* recJ = recN[s];
+                    const int cj = hi ? ci[a] + 1 : ci[a] - 1;
+                    F.interior = true;
+                    F.tij = g_tij[s];
+                    if (F.grav) {
+                        const double KJ = recJ[L::KF * AT_HC];
+                        F.tJ = KJ * extr * (hi ? P.gf_lo[a][cj] : P.gf_hi[a][cj]);
+                        rtJ = 1.0 / F.tJ;
+                        F.alphaJ = KJ * ng * extr;
+                        if (!TABLE) {
+#pragma unroll
+                            for (int ph = 0; ph < NPH; ++ph) {
+                                const double rho = (P.rho[ph] + P.rho[ph]) * 0.5;
+                                F.c1[ph] = rho * area * F.alphaI;
+                                F.c2[ph] = div_by(rho * F.tij, F.tJ, rtJ) * (F.alphaI - F.alphaJ);
+                            }
+                        }
+                    }
+                    double uJ[NB], epsJ[NB];
+#pragma unroll
+                    for (int e = 0; e < NB; ++e) { uJ[e] = recJ[(L::U + e) * AT_HC]; epsJ[e] = fd_eps(P, uJ[e], e); }
+                    CellState<NPH> sJ0;
+                    double SnJ;
+                    tile_state<MODEL, TABLE, NDR, NPH>(P, recJ, -1, 0, uJ, epsJ, sJ0, &SnJ);
+                    double F0[NPH];
+                    face_flux_r<NPH, TABLE>(F, rtJ, sI0, sJ0, fullUpwind, w, F0);
+#pragma unroll
+                    for (int e = 0; e < NB; ++e) R0[e] += F0[e];
+                    if constexpr (JAC) {
+#pragma unroll
+                        for (int pv = 0; pv < NB; ++pv)
+#pragma unroll
+                            for (int kk = 0; kk < ND; ++kk) {
+                                double Fk[NPH];
+                                face_flux_r<NPH, TABLE>(F, rtJ, sId[pv][kk], sJ0, fullUpwind, w, Fk);
+#pragma unroll
+                                for (int e = 0; e < NB; ++e) Rd[pv][kk][e] += Fk[e];
+                            }
+                        // A[I][J][e][pv] = FD quotient of the face flux w.r.t. u_J[pv] (cclocalassembler.hh:211-218,254-258,331-332)
+                        double blk[NB][NB];
+#pragma unroll
+                        for (int pv = 0; pv < NB; ++pv) {
+                            double Fd[ND][NPH];
+#pragma unroll
+                            for (int kk = 0; kk < ND; ++kk) {
+                                CellState<NPH> sJd;
+                                double dummy;
+                                tile_state<MODEL, TABLE, NDR, NPH>(P, recJ, pv, kk, uJ, epsJ, sJd, &dummy);
+                                face_flux_r<NPH, TABLE>(F, rtJ, sI0, sJd, fullUpwind, w, Fd[kk]);
+                            }
+                            const double rdJ = recJ[(L::RD + pv) * AT_HC];
+#pragma unroll
+                            for (int e = 0; e < NB; ++e) {
+                                double fk[ND];
+#pragma unroll
+                                for (int kk = 0; kk < ND; ++kk) fk[kk] = Fd[kk][e];
+                                blk[e][pv] = fd_quotient_r<ND>(P.fd_method, F0[e], fk, epsJ[pv], rdJ);
+                            }
+                        }
+                        store_block<NB>(P.jac + (size_t)pos[s] * (NB * NB), blk);
+                    }
+                } else {
+                    // boundary face: cclocalresidual.hh:64-105
+                    int f;   // face index within the side, lower remaining axis fastest
+                    if (a == 0) f = ci[1] + ny * ci[2];
+                    else if (a == 1) f = ci[0] + nx * ci[2];
+                    else f = ci[0] + nx * ci[1];
+                    const int type = P.bc_type[s] ? P.bc_type[s][f] : DMX_BC_NEUMANN;
+                    if (type == DMX_BC_DIRICHLET) {
+                        F.interior = false;
+                        const double ti = KI * extr * (hi ? P.gf_hi[a][ci[a]] : P.gf_lo[a][ci[a]]);
+                        F.tij = area * ti;
+                        CellState<NPH> sD;
+#pragma unroll
+                        for (int ph = 0; ph < NPH; ++ph) {
+                            sD.p[ph] = P.bc_p[s][(size_t)f * 2 + ph];
+                            sD.up[ph] = P.bc_up[s][(size_t)f * 2 + ph];
+                            sD.rho[ph] = P.bc_rho[s][(size_t)f * 2 + ph];
+                            F.c1[ph] = sD.rho[ph] * area * F.alphaI;
+                            F.c2[ph] = 0.0;
+                        }
+                        double F0[NPH];
+                        face_flux_r<NPH, TABLE>(F, rtJ, sI0, sD, fullUpwind, w, F0);
+#pragma unroll
+                        for (int e = 0; e < NB; ++e) R0[e] += F0[e];
+                        if constexpr (JAC) {
+#pragma unroll
+                            for (int pv = 0; pv < NB; ++pv)
+#pragma unroll
+                                for (int kk = 0; kk < ND; ++kk) {
+                                    double Fk[NPH];
+                                    face_flux_r<NPH, TABLE>(F, rtJ, sId[pv][kk], sD, fullUpwind, w, Fk);
+#pragma unroll
+                                    for (int e = 0; e < NB; ++e) Rd[pv][kk][e] += Fk[e];
+                                }
+                        }
+                    } else if (type == DMX_BC_NEUMANN) {
+#pragma unroll
+                        for (int e = 0; e < NB; ++e) {
+                            double nf = P.bc_neumann[s] ? P.bc_neumann[s][(size_t)f * NB + e] : 0.0;
+                            nf *= area * extr;
+                            R0[e] += nf;
+#pragma unroll
+                            for (int pv = 0; pv < NB; ++pv)
+#pragma unroll
+                                for (int kk = 0; kk < NDE; ++kk) Rd[pv][kk][e] += nf;
+                        }
+                    }
+                    // DMX_BC_NONE: outer face of an overlap cell, no scvf exists (tpfa/fvgridgeometry.hh:272-320)
+                }
+            }
+            tz_below = g_tij[5];
+
+            // storage: fvlocalresidual.hh:274-304: ((S(cur)*extr - S(prev)*extr)*V)/dt, added after flux+source
+            if (!P.stationary) {
+                const double phiI = g_phi;
+                const double phiE = 1.0 - (1.0 - phiI);     // porosity = 1 - inert volume fraction
+                double prevSt[NB];
+                {
+                    CellState<NPH> sP;
+                    double SnP = 0.0;
+                    if constexpr (MODEL == DMX_MODEL_2P) {
+                        SnP = g_prev;
+                        sP.rho[0] = P.rho[0];
+                        sP.rho[NPH - 1] = P.rho[1];
+                    } else {
+                        sP.rho[0] = TABLE ? table_interp(P.table, P.table.rho, g_prev) : P.rho[0];
+                    }
+                    storage_term<MODEL, NPH>(phiE, sP, SnP, prevSt);
+#pragma unroll
+                    for (int e = 0; e < NB; ++e) prevSt[e] *= extr;
+                }
+                auto addStorage = [&](const CellState<NPH>& s, double Sn, double* acc) {
+                    double st[NB];
+                    storage_term<MODEL, NPH>(phiE, s, Sn, st);
+#pragma unroll
+                    for (int e = 0; e < NB; ++e) {
+                        st[e] *= extr;
+                        st[e] -= prevSt[e];
+                        st[e] *= vol;
+                        st[e] = div_by(st[e], P.dt, P.rdt);
+                        acc[e] += st[e];
+                    }
+                };
+                addStorage(sI0, SnI0, R0);
+                if constexpr (JAC) {
+#pragma unroll
+                    for (int pv = 0; pv < NB; ++pv)
+#pragma unroll
+                        for (int kk = 0; kk < ND; ++kk) addStorage(sId[pv][kk], SnId[pv][kk], Rd[pv][kk]);
+                }
+            }
+
+            bool finite = true;
+#pragma unroll
+            for (int e = 0; e < NB; ++e) finite = finite && (fabs(R0[e]) <= DBL_MAX);
+            if constexpr (NB == 2) reinterpret_cast<double2*>(P.residual)[I] = make_double2(R0[0], R0[NB - 1]);
+            else P.residual[I] = R0[0];
+            if (!finite) atomicOr(P.flag_nonfinite, 1);
+
+            if constexpr (JAC) {
+                double blk[NB][NB];
+#pragma unroll
+                for (int pv = 0; pv < NB; ++pv)
+#pragma unroll
+                    for (int e = 0; e < NB; ++e) {
+                        double fk[ND];
+#pragma unroll
+                        for (int kk = 0; kk < ND; ++kk) fk[kk] = Rd[pv][kk][e];
+                        blk[e][pv] = fd_quotient_r<ND>(P.fd_method, R0[e], fk, epsI[pv], rdI[pv]);
+                    }
+                store_block<NB>(P.jac + (size_t)posDiag * (NB * NB), blk);
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -514,7 +1045,17 @@ static void fill_params(dmx_ctx* ctx, AsmParams& P)
     P.mag[0] = o.privar_magnitude[0]; P.mag[1] = o.privar_magnitude[1];
     P.dt = o.dt; P.extrusion = o.extrusion;
     P.K = ctx->d_K; P.phi = ctx->d_phi; P.region = ctx->d_region; P.q = ctx->d_q;
-    for (int i = 0; i < 2; ++i) { P.rho[i] = ctx->rho[i]; P.mu[i] = ctx->mu[i]; }
+    for (int i = 0; i < 2; ++i) { P.rho[i] = ctx->rho[i]; P.mu[i] = ctx->mu[i]; P.rmu[i] = 1.0 / ctx->mu[i]; }
+    P.rdt = 1.0 / o.dt;
+    P.nlaws = (int)ctx->laws.size();
+    {
+        // layers per CTA of the tile kernel: about six waves of two CTAs per SM, at least 16 layers (halo layers cost 2/zchunk)
+        const int tiles = ((ctx->nc[0] + AT_TX - 1) / AT_TX) * ((ctx->nc[1] + AT_TY - 1) / AT_TY);
+        const int want = std::max(1, (12 * ctx->num_sms + tiles - 1) / tiles);
+        int zc = (ctx->nc[2] + want - 1) / want;
+        zc = std::max(zc, std::min(16, ctx->nc[2]));
+        P.zchunk = zc;
+    }
     P.tabulated = ctx->tabulated ? 1 : 0;
     P.table = ctx->d_table;
     P.laws = ctx->d_laws;
@@ -664,12 +1205,48 @@ static int launch_nd(dmx_ctx* ctx, const AsmParams& P, bool with_jac, bool volva
     return 0;
 }
 
+template <int MODEL, bool TABLE, int ND, bool JAC>
+static int launch_tile_inst(dmx_ctx* ctx, const AsmParams& P)
+{
+    using L = RecLayout<MODEL, TABLE, JAC ? ND : 0>;
+    const size_t smem = 3 * (size_t)L::NF * AT_HC * sizeof(double) + (MODEL == DMX_MODEL_2P ? DMX_MAX_REGIONS * sizeof(MaterialLaw) : 0);
+    auto kern = assemble_tile_kernel<MODEL, TABLE, ND, JAC>;
+    DMX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int ntx = (ctx->nc[0] + AT_TX - 1) / AT_TX, nty = (ctx->nc[1] + AT_TY - 1) / AT_TY;
+    const dim3 grid((unsigned)(ntx * nty), (unsigned)((ctx->nc[2] + P.zchunk - 1) / P.zchunk));
+    ProfScope ps__(ctx, DMX_K_ASSEMBLY);
+    kern<<<grid, AT_THREADS, smem, ctx->stream>>>(P);
+    DMX_CHECK_LAUNCH();
+    return 0;
+}
+
+template <int MODEL, bool TABLE>
+static int launch_tile(dmx_ctx* ctx, const AsmParams& P, bool with_jac)
+{
+    if (P.nlaws > DMX_MAX_REGIONS) return fail(ctx, DMX_ERR_USAGE, "too many material-law regions");
+    if (!with_jac) return launch_tile_inst<MODEL, TABLE, 1, false>(ctx, P);
+    if (P.nd == 1) return launch_tile_inst<MODEL, TABLE, 1, true>(ctx, P);
+    if (P.nd == 2) return launch_tile_inst<MODEL, TABLE, 2, true>(ctx, P);
+    return launch_tile_inst<MODEL, TABLE, 4, true>(ctx, P);
+}
+
+static bool use_legacy_kernels()
+{
+    static const bool legacy = [] { const char* e = getenv("DMX_ASM_LEGACY"); return e && e[0] == '1'; }();
+    return legacy;
+}
+
 static int launch_impl(dmx_ctx* ctx, bool with_jac, bool volvars_only)
 {
     if (int rc = prepare(ctx)) return rc;
     if (!ctx->opt.stationary && ctx->opt.dt <= 0.0) return fail(ctx, DMX_ERR_USAGE, "assemble: dt must be > 0");
     AsmParams P;
     fill_params(ctx, P);
+    if (!volvars_only && !use_legacy_kernels()) {
+        if (ctx->model == DMX_MODEL_2P) return launch_tile<DMX_MODEL_2P, false>(ctx, P, with_jac);
+        if (ctx->tabulated) return launch_tile<DMX_MODEL_1P, true>(ctx, P, with_jac);
+        return launch_tile<DMX_MODEL_1P, false>(ctx, P, with_jac);
+    }
     if (ctx->model == DMX_MODEL_2P) return launch_nd<DMX_MODEL_2P, false>(ctx, P, with_jac, volvars_only);
     if (ctx->tabulated) return launch_nd<DMX_MODEL_1P, true>(ctx, P, with_jac, volvars_only);
     return launch_nd<DMX_MODEL_1P, false>(ctx, P, with_jac, volvars_only);

@@ -38,9 +38,12 @@ struct AsmParams {
     const double* tij[3];     // transmissibility of the + face of each cell along axis a
     // fluids
     double rho[2], mu[2];
+    double rmu[2], rdt;       // correctly rounded 1/mu, 1/dt (host IEEE division) for div_by
+    int zchunk;               // layers per CTA of the tile kernel
     int tabulated;
     FluidTable table;
     const MaterialLaw* laws;
+    int nlaws;
     // boundary data per side: type[nf], neumann[nf*b], Dirichlet state p[nf*2], up[nf*2], rho[nf*2]
     const int* bc_type[6];
     const double* bc_neumann[6];

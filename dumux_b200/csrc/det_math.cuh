@@ -17,8 +17,11 @@
 
 #ifdef __CUDACC__
 #define DMX_HD __host__ __device__ __forceinline__
+// out-of-line building blocks (one copy per translation unit): keeps the assembly kernels' code inside the instruction cache
+#define DMX_HD_NOINLINE static __host__ __device__ __noinline__
 #else
 #define DMX_HD inline
+#define DMX_HD_NOINLINE static inline
 #endif
 
 namespace dmx {
@@ -48,15 +51,15 @@ DMX_HD double fma_rn(double a, double b, double c)
 #endif
 }
 
-DMX_HD double det_pow(double x, double y)
-{
-    if (y == 0.0) return 1.0;
-    if (x == 1.0) return 1.0;
-    if (x != x || y != y) return x + y;
-    if (x < 0.0) return u2d(0x7ff8000000000000ull);
-    if (x == 0.0) return y > 0.0 ? 0.0 : u2d(0x7ff0000000000000ull);
-    if (x == u2d(0x7ff0000000000000ull)) return y > 0.0 ? x : 0.0;
+// log2(x) in double-double for finite x > 0: the first half of det_pow.  Several powers of the same base (the three
+// Brooks-Corey curves, the nested van Genuchten terms) share ONE det_log2 -- same operation sequence per power, so
+// det_pow_from_log2(det_log2(x), x, y) returns exactly the bits of det_pow(x, y).
+struct DetLog2 {
+    double Lh, Ll;
+};
 
+DMX_HD_NOINLINE DetLog2 det_log2(double x)
+{
     uint64_t bits = d2u(x);
     int e = (int)((bits >> 52) & 0x7ff);
     if (e == 0) {
@@ -105,13 +108,22 @@ DMX_HD double det_pow(double x, double y)
     pl = fma_rn(tl, INVLN2_HI, pl);
 
     const double ed = (double)e;
-    const double Lh = ed + ph;
-    double Ll = (ed - Lh) + ph;
-    Ll = Ll + pl;
+    DetLog2 L;
+    L.Lh = ed + ph;
+    double Ll = (ed - L.Lh) + ph;
+    L.Ll = Ll + pl;
+    return L;
+}
 
-    const double zh = y * Lh;
-    double zl = fma_rn(y, Lh, -zh);
-    zl = fma_rn(y, Ll, zl);
+// true when det_pow(x, y) takes the log/exp path for every y != 0 (finite x > 0, x != 1)
+DMX_HD bool det_pow_regular(double x) { return x > 0.0 && x != 1.0 && x < u2d(0x7ff0000000000000ull); }
+
+// 2^(y*L): the second half of det_pow
+DMX_HD_NOINLINE double det_exp2_scaled(DetLog2 L, double y)
+{
+    const double zh = y * L.Lh;
+    double zl = fma_rn(y, L.Lh, -zh);
+    zl = fma_rn(y, L.Ll, zl);
 
     if (zh >= 1024.0) return u2d(0x7ff0000000000000ull);
     if (zh <= -1100.0) return 0.0;
@@ -140,6 +152,52 @@ DMX_HD double det_pow(double x, double y)
     long long n2 = n + 1022;
     if (n2 < -1022) n2 = -1022;
     return (Q * 0x1p-1022) * u2d((uint64_t)(n2 + 1023) << 52);
+}
+
+// special cases of pow that never reach the log/exp path
+DMX_HD double det_pow_special(double x, double y)
+{
+    if (y == 0.0) return 1.0;
+    if (x == 1.0) return 1.0;
+    if (x != x || y != y) return x + y;
+    if (x < 0.0) return u2d(0x7ff8000000000000ull);
+    if (x == 0.0) return y > 0.0 ? 0.0 : u2d(0x7ff0000000000000ull);
+    return y > 0.0 ? x : 0.0;       // x == +inf
+}
+
+DMX_HD double det_pow(double x, double y)
+{
+    if (y == 0.0 || y != y || !det_pow_regular(x)) return det_pow_special(x, y);
+    return det_exp2_scaled(det_log2(x), y);
+}
+
+// A base whose log2 is evaluated lazily at most once: pw.pow(y) == det_pow(x, y) bit for bit.
+struct PowBase {
+    double x;
+    DetLog2 L;
+    bool regular;
+    DMX_HD explicit PowBase(double x_) : x(x_), regular(det_pow_regular(x_))
+    {
+        if (regular) L = det_log2(x_);
+        else { L.Lh = 0.0; L.Ll = 0.0; }
+    }
+    DMX_HD double pow(double y) const
+    {
+        if (y == 0.0 || y != y || !regular) return det_pow_special(x, y);
+        return det_exp2_scaled(L, y);
+    }
+};
+
+/* Correctly rounded a/b from the correctly rounded reciprocal y = RN(1/b) (Markstein): q0 = RN(a*y), two residual
+   corrections with exact FMA residuals.  Bit-identical to the IEEE division a/b for normal-range operands; used where
+   many quotients share one divisor (FD steps, viscosities, dt). */
+DMX_HD double div_by(double a, double b, double y)
+{
+    double q = a * y;
+    double r = fma_rn(-b, q, a);
+    q = fma_rn(r, y, q);
+    r = fma_rn(-b, q, a);
+    return fma_rn(r, y, q);
 }
 
 } // namespace dmx

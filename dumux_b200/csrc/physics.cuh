@@ -60,6 +60,7 @@ struct MaterialLaw {
     double pcLowSwe, pcHighSwe, krnLowSwe, krwHighSwe;
     double pcLowSwePcValue, pcHighSwePcValue, pcDerivativeLowSw, pcDerivativeHighSwEnd, pcDerivativeHighSweThreshold;
     Spline2 pcSpline, krwSpline, krnSpline;
+    double sdenom, rsdenom;        // 1 - swr - snr and its correctly rounded reciprocal (law_init; used by law_eval3)
 };
 
 DMX_HD double clamp01(double v) { return v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v); }
@@ -159,6 +160,8 @@ DMX_HD double law_krn(const MaterialLaw& p, double sw)
 // derived regularisation constants: brookscorey.hh:481-489; vangenuchten.hh initPcParameters_/initKrParameters_
 inline void law_init(MaterialLaw& p)
 {
+    p.sdenom = 1.0 - p.swr - p.snr;
+    p.rsdenom = 1.0 / p.sdenom;
     if (!p.regularized) return;
     const double dsw = dsw_dswe(p);
     auto dpc_dsw_noreg = [&](double sw) { return base_dpc_dswe(p, swToSwe(p, sw)) * dswe_dsw(p); };
@@ -194,6 +197,66 @@ inline void law_init(MaterialLaw& p)
     }
 }
 
+// pc, krw and krn of one saturation in one go (what TwoPVolumeVariables::completeFluidState needs,
+// porousmediumflow/2p/volumevariables.hh:141-190).  Returns exactly the bits of law_pc / law_krw / law_krn: the
+// same operations in the same order, but powers of a common base share one det_log2 (PowBase) and the division by
+// 1 - swr - snr uses the precomputed reciprocal (div_by is correctly rounded).
+struct Law3 {
+    double pc, krw, krn;
+};
+DMX_HD void law_eval3(const MaterialLaw& p, double sw, double* pc, double* krw, double* krn);
+// out-of-line entry for the kernels (results in registers)
+DMX_HD_NOINLINE Law3 law_eval3_call(const MaterialLaw* p, double sw)
+{
+    Law3 r;
+    law_eval3(*p, sw, &r.pc, &r.krw, &r.krn);
+    return r;
+}
+DMX_HD void law_eval3(const MaterialLaw& p, double sw, double* pc, double* krw, double* krn)
+{
+    const double swe = div_by(sw - p.swr, p.sdenom, p.rsdenom);
+    const bool reg = p.regularized != 0;
+    const bool mid = !reg || (swe > 0.0 && swe < 1.0);
+    if (!mid) {
+        // end points: the kr curves are constants, pc is linear (or, for an exotic pcLowSwe < 0, the plain law)
+        *pc = law_pc(p, sw);
+        *krw = swe <= 0.0 ? 0.0 : 1.0;
+        *krn = swe <= 0.0 ? 1.0 : 0.0;
+        return;
+    }
+    const double c = clamp01(swe);
+    const PowBase B(c);
+    if (p.kind == LAW_BROOKSCOREY) {
+        if (reg && swe <= p.pcLowSwe) *pc = p.pcLowSwePcValue + p.pcDerivativeLowSw * (swe - p.pcLowSwe);
+        else if (reg && swe >= 1.0) *pc = p.pcDerivativeHighSwEnd * (swe - 1.0) + p.pcEntry;
+        else *pc = p.pcEntry * B.pow(-1.0 / p.lambda);
+        *krw = B.pow(2.0 / p.lambda + 3.0);
+        const double exponent = 2.0 / p.lambda + 1.0;
+        const double sne = 1.0 - c;
+        *krn = sne * sne * (1.0 - B.pow(exponent));
+        return;
+    }
+    if (reg && swe <= p.pcLowSwe) *pc = p.pcLowSwePcValue + p.pcDerivativeLowSw * (swe - p.pcLowSwe);
+    else if (reg && swe >= 1.0) *pc = p.pcDerivativeHighSwEnd * (swe - 1.0);
+    else if (reg && swe > p.pcHighSwe) *pc = spline_eval(p.pcSpline, swe);
+    else *pc = det_pow(B.pow(-1.0 / p.m) - 1, 1.0 / p.n) / p.alpha;
+    const bool krwSpl = reg && swe >= p.krwHighSwe;
+    const bool krnSpl = reg && swe <= p.krnLowSwe;
+    if (krwSpl && krnSpl) {
+        *krw = spline_eval(p.krwSpline, swe);
+        *krn = spline_eval(p.krnSpline, swe);
+        return;
+    }
+    const PowBase BX(1.0 - B.pow(1.0 / p.m));
+    if (krwSpl) *krw = spline_eval(p.krwSpline, swe);
+    else {
+        const double r = 1.0 - BX.pow(p.m);
+        *krw = B.pow(p.l) * r * r;
+    }
+    if (krnSpl) *krn = spline_eval(p.krnSpline, swe);
+    else *krn = det_pow(1 - c, p.l) * BX.pow(2 * p.m);
+}
+
 // ---- fluids ----
 struct FluidTable {
     int nT, nP;
@@ -221,6 +284,33 @@ DMX_HD double table_interp(const FluidTable& t, const double* values, double p)
     alphaP2 -= iP2;
     return values[(iT) + (iP1)*t.nT] * (1 - alphaT) * (1 - alphaP1) + values[(iT) + (iP1 + 1) * t.nT] * (1 - alphaT) * (alphaP1)
          + values[(iT + 1) + (iP2)*t.nT] * (alphaT) * (1 - alphaP2) + values[(iT + 1) + (iP2 + 1) * t.nT] * (alphaT) * (alphaP2);
+}
+
+// density and viscosity of one pressure in one go: same operations as two table_interp calls, shared index search
+DMX_HD void table_interp2(const FluidTable& t, double p, double* rho, double* mu)
+{
+    double alphaT = (t.nT - 1) * (t.T - t.Tmin) / (t.Tmax - t.Tmin);
+    if (alphaT < 0 - 1e-7 * t.nT || alphaT >= t.nT - 1 + 1e-7 * t.nT) {
+        *rho = *mu = u2d(0x7ff8000000000000ull);
+        return;
+    }
+    int iT = (int)alphaT;
+    iT = iT < 0 ? 0 : (iT > t.nT - 2 ? t.nT - 2 : iT);
+    alphaT -= iT;
+    double alphaP1 = (t.nP - 1) * (p - t.pmin[iT]) / (t.pmax[iT] - t.pmin[iT]);
+    double alphaP2 = (t.nP - 1) * (p - t.pmin[iT + 1]) / (t.pmax[iT + 1] - t.pmin[iT + 1]);
+    int iP1 = (int)alphaP1;
+    iP1 = iP1 < 0 ? 0 : (iP1 > t.nP - 2 ? t.nP - 2 : iP1);
+    int iP2 = (int)alphaP2;
+    iP2 = iP2 < 0 ? 0 : (iP2 > t.nP - 2 ? t.nP - 2 : iP2);
+    alphaP1 -= iP1;
+    alphaP2 -= iP2;
+    const double* v = t.rho;
+    *rho = v[(iT) + (iP1)*t.nT] * (1 - alphaT) * (1 - alphaP1) + v[(iT) + (iP1 + 1) * t.nT] * (1 - alphaT) * (alphaP1)
+         + v[(iT + 1) + (iP2)*t.nT] * (alphaT) * (1 - alphaP2) + v[(iT + 1) + (iP2 + 1) * t.nT] * (alphaT) * (alphaP2);
+    v = t.mu;
+    *mu = v[(iT) + (iP1)*t.nT] * (1 - alphaT) * (1 - alphaP1) + v[(iT) + (iP1 + 1) * t.nT] * (1 - alphaT) * (alphaP1)
+        + v[(iT + 1) + (iP2)*t.nT] * (alphaT) * (1 - alphaP2) + v[(iT + 1) + (iP2 + 1) * t.nT] * (alphaT) * (alphaP2);
 }
 
 } // namespace dmx

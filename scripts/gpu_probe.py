@@ -42,12 +42,12 @@ def timing(n):
     p = e.newton_params()
     for i in range(3):
         st, its, shift, a, s, u = e.newton_step(p)
-        print(f"newton step {i}: st {st} bicgstab its {its} shift {shift:.3e} assemble {a:.2f} ms solve {s:.2f} ms update {u:.2f} ms -> {cells*2/((a+s+u)*1e-3)/1e6:.1f} MDOF/s")
+        print(f"newton step {i}: st {st} bicgstab its {its} shift {shift:.3e} assemble {a:.2f} ms solve {s:.2f} ms update {u:.2f} ms -> {cells*2/(max(a+s+u,1e-9)*1e-3)/1e6:.1f} MDOF/s")
     p = e.newton_params(preconditioner=B.PRECOND_BLOCKJACOBI, lin_maxit=2000)
     e.upload(B.VEC_CUR, spec.initial)
     for i in range(2):
         st, its, shift, a, s, u = e.newton_step(p)
-        print(f"[jacobi] newton step {i}: st {st} bicgstab its {its} shift {shift:.3e} assemble {a:.2f} ms solve {s:.2f} ms update {u:.2f} ms -> {cells*2/((a+s+u)*1e-3)/1e6:.1f} MDOF/s")
+        print(f"[jacobi] newton step {i}: st {st} bicgstab its {its} shift {shift:.3e} assemble {a:.2f} ms solve {s:.2f} ms update {u:.2f} ms -> {cells*2/(max(a+s+u,1e-9)*1e-3)/1e6:.1f} MDOF/s")
     e.close()
 
 

@@ -117,3 +117,16 @@ def test_nonfinite_residual_is_reported(engine_factory):
     e = engine_factory(spec)
     with pytest.raises(DmxError):
         e.assemble(cur, spec.initial)
+
+
+@pytest.mark.parametrize("cells,law", [((33, 9, 37), "bc"), ((70, 19, 21), "vg")])
+def test_tile_kernel_chunks_bit_identical(engine_factory, cells, law):
+    """Partial 32x8 tiles, several z-chunks per tile column and chunk-boundary halo layers of the fused tile kernel; the
+    kernel executes the oracle's IEEE operation sequence (shared-log pow, div_by are exact), so equality is bitwise."""
+    spec = problems.twop_lens(cells, law=law, heterogeneity_sigma=0.5)
+    prev = _perturbed(spec, 11)
+    cur = _perturbed(spec, 12)
+    rerr, jerr, (res_o, jac_o, res_g, jac_g) = _compare(spec, engine_factory, cur, prev)
+    assert rerr <= 1e-13 and jerr <= RTOL, (rerr, jerr)
+    assert np.array_equal(res_g, res_o)
+    assert np.array_equal(jac_g, jac_o), int((jac_g != jac_o).sum())
