@@ -68,81 +68,6 @@ __device__ __forceinline__ double fd_deflect(int method, int k, double x0, doubl
     if (k == 2) return x0 - 2.0 * eps;
     return x0 + 2.0 * eps;
 }
-// f0: undeflected value, f[k]: deflected values
-template <int ND>
-__device__ __forceinline__ double fd_quotient(int method, double f0, const double* f, double eps)
-{
-    if (ND == 1) {
-        double d, delta = 0.0;
-        if (method >= 0) { delta += eps; d = f[0]; d -= f0; }
-        else { delta += eps; d = f0; d -= f[0]; }
-        return d / delta;
-    } else if (ND == 2) {
-        double delta = 0.0;
-        delta += eps;
-        double d = f[0];
-        delta += eps;
-        d -= f[1];
-        return d / delta;
-    } else {
-        double d = f[0];
-        d -= f[1];
-        d *= 8.0;
-        d += f[2];
-        d -= f[3];
-        return d / (12.0 * eps);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// secondary variables at base + deflected states, SoA records rec[r*n + I]
-//   2p:         r = 0: pc, 1: rho_w*mob_w, 2: rho_n*mob_n;  then per deflection k of S_n: 3+3k .. 5+3k
-//   1p (table): r = 0: rho, 1: rho*mob;                     then per deflection k of p:   2+2k .. 3+2k
-// ------------------------------------------------------------------------------------------------
-template <int MODEL, int ND>
-__global__ void __launch_bounds__(256) volvars_kernel(AsmParams P)
-{
-    const int I = blockIdx.x * blockDim.x + threadIdx.x;
-    if (I >= P.n) return;
-    const size_t n = (size_t)P.n;
-    if constexpr (MODEL == DMX_MODEL_2P) {
-        const MaterialLaw& law = P.laws[P.region[I]];
-        const double Sn = P.cur[2 * (size_t)I + 1];
-        {
-            const double sw = 1 - Sn;
-            P.rec[0 * n + I] = law_pc(law, sw);
-            P.rec[1 * n + I] = P.rho[0] * (law_krw(law, sw) / P.mu[0]);
-            P.rec[2 * n + I] = P.rho[1] * (law_krn(law, sw) / P.mu[1]);
-        }
-        const double eps = fd_eps(P, Sn, 1);
-#pragma unroll
-        for (int k = 0; k < ND; ++k) {
-            const double Snk = fd_deflect(P.fd_method, k, Sn, eps);
-            const double sw = 1 - Snk;
-            P.rec[(3 + 3 * k + 0) * n + I] = law_pc(law, sw);
-            P.rec[(3 + 3 * k + 1) * n + I] = P.rho[0] * (law_krw(law, sw) / P.mu[0]);
-            P.rec[(3 + 3 * k + 2) * n + I] = P.rho[1] * (law_krn(law, sw) / P.mu[1]);
-        }
-    } else {
-        const double p = P.cur[I];
-        {
-            const double rho = table_interp(P.table, P.table.rho, p);
-            const double mu = table_interp(P.table, P.table.mu, p);
-            P.rec[0 * n + I] = rho;
-            P.rec[1 * n + I] = rho * (1.0 / mu);
-        }
-        const double eps = fd_eps(P, p, 0);
-#pragma unroll
-        for (int k = 0; k < ND; ++k) {
-            const double pk = fd_deflect(P.fd_method, k, p, eps);
-            const double rho = table_interp(P.table, P.table.rho, pk);
-            const double mu = table_interp(P.table, P.table.mu, pk);
-            P.rec[(2 + 2 * k + 0) * n + I] = rho;
-            P.rec[(2 + 2 * k + 1) * n + I] = rho * (1.0 / mu);
-        }
-    }
-}
-
 // per-cell state entering a flux evaluation
 template <int NPH>
 struct CellState {
@@ -159,69 +84,6 @@ struct FaceData {
     double c1[NPH], c2[NPH];   // gravity terms for constant density
 };
 
-// TPFA Darcy flux with gravity + upwinding for all phases: flux/cctpfa/darcyslaw.hh:154-213, flux/upwindscheme.hh:36-54
-//   f = tij*(pI - pJ) + (rho*A)*alphaI;  interior: f -= ((rho*tij)/tJ)*(alphaI - alphaJ);  flux = f * upwind(rho*mob)
-template <int NPH, bool TABLE>
-__device__ __forceinline__ void face_flux(const FaceData<NPH>& F, const CellState<NPH>& sI, const CellState<NPH>& sJ,
-                                          bool fullUpwind, double w, double* out)
-{
-#pragma unroll
-    for (int ph = 0; ph < NPH; ++ph) {
-        double f = F.tij * (sI.p[ph] - sJ.p[ph]);
-        if (F.grav) {
-            if constexpr (TABLE) {
-                const double rho = F.interior ? (sI.rho[ph] + sJ.rho[ph]) * 0.5 : sJ.rho[ph];
-                f = f + rho * F.area * F.alphaI;
-                if (F.interior) f -= rho * F.tij / F.tJ * (F.alphaI - F.alphaJ);
-            } else {
-                f = f + F.c1[ph];
-                if (F.interior) f -= F.c2[ph];
-            }
-        }
-        double mult;
-        if (fullUpwind) mult = signbit(f) ? sJ.up[ph] : sI.up[ph];
-        else if (signbit(f)) mult = w * sJ.up[ph] + (1.0 - w) * sI.up[ph];
-        else mult = w * sI.up[ph] + (1.0 - w) * sJ.up[ph];
-        out[ph] = f * mult;
-    }
-}
-
-// Builds the state of cell C (own or neighbour) at the base point or at deflection (pv,k).
-// pv < 0: base.  Records come from volvars_kernel.
-template <int MODEL, bool TABLE, int NPH>
-__device__ __forceinline__ void load_state(const AsmParams& P, int C, int pv, int k, const double* uC, const double* epsC,
-                                           CellState<NPH>& s, double* Sn_out)
-{
-    const size_t n = (size_t)P.n;
-    if constexpr (MODEL == DMX_MODEL_2P) {
-        double pw = uC[0], Sn = uC[1];
-        int r = 0;
-        if (pv == 0) pw = fd_deflect(P.fd_method, k, pw, epsC[0]);
-        if (pv == 1) { Sn = fd_deflect(P.fd_method, k, Sn, epsC[1]); r = 3 + 3 * k; }
-        const double pc = P.rec[(r + 0) * n + C];
-        s.p[0] = pw;
-        s.p[NPH - 1] = pw + pc;
-        s.up[0] = P.rec[(r + 1) * n + C];
-        s.up[NPH - 1] = P.rec[(r + 2) * n + C];
-        s.rho[0] = P.rho[0];
-        s.rho[NPH - 1] = P.rho[1];
-        *Sn_out = Sn;
-    } else {
-        double p = uC[0];
-        if (pv == 0) p = fd_deflect(P.fd_method, k, p, epsC[0]);
-        s.p[0] = p;
-        if constexpr (TABLE) {
-            const int r = (pv == 0) ? 2 + 2 * k : 0;
-            s.rho[0] = P.rec[(r + 0) * n + C];
-            s.up[0] = P.rec[(r + 1) * n + C];
-        } else {
-            s.rho[0] = P.rho[0];
-            s.up[0] = P.rho[0] * (1.0 / P.mu[0]);
-        }
-        *Sn_out = 0.0;
-    }
-}
-
 // storage term: immiscible/localresidual.hh:64-83: porosity*density*saturation per phase
 template <int MODEL, int NPH>
 __device__ __forceinline__ void storage_term(double phiE, const CellState<NPH>& s, double Sn, double* st)
@@ -231,269 +93,6 @@ __device__ __forceinline__ void storage_term(double phiE, const CellState<NPH>& 
         st[NPH - 1] = phiE * s.rho[NPH - 1] * Sn;
     } else {
         st[0] = phiE * s.rho[0] * 1.0;
-    }
-}
-
-template <int MODEL, bool TABLE, int ND>
-__global__ void __launch_bounds__(128) assemble_kernel(AsmParams P, int with_jac)
-{
-    constexpr int NB = (MODEL == DMX_MODEL_2P) ? 2 : 1;   // block size = numEq = phases
-    constexpr int NPH = NB;
-    const int I = blockIdx.x * blockDim.x + threadIdx.x;
-    if (I >= P.n) return;
-    const int nx = P.nc[0], ny = P.nc[1], nz = P.nc[2];
-    const int ci[3] = {I % nx, (I / nx) % ny, I / (nx * ny)};
-    const int stride[3] = {1, nx, nx * ny};
-    const int dim = P.dim;
-    const int va = dim - 1;
-    const bool fullUpwind = (P.upwind_weight == 1.0);
-    const double w = P.upwind_weight;
-    const double extr = P.extrusion;
-    (void)nz;
-
-    // own primary variables, FD steps, states
-    double uI[NB], epsI[NB];
-#pragma unroll
-    for (int e = 0; e < NB; ++e) { uI[e] = P.cur[(size_t)I * NB + e]; epsI[e] = fd_eps(P, uI[e], e); }
-    CellState<NPH> sI0, sId[NB][ND];
-    double SnI0, SnId[NB][ND];
-    load_state<MODEL, TABLE, NPH>(P, I, -1, 0, uI, epsI, sI0, &SnI0);
-#pragma unroll
-    for (int pv = 0; pv < NB; ++pv)
-#pragma unroll
-        for (int k = 0; k < ND; ++k) load_state<MODEL, TABLE, NPH>(P, I, pv, k, uI, epsI, sId[pv][k], &SnId[pv][k]);
-
-    const double KI = P.K[I];
-    // volume = ((1*w0)*w1)*w2 (AxisAlignedCubeGeometry::volume)
-    double vol = 1.0;
-    for (int a = 0; a < dim; ++a) vol *= P.width[a][ci[a]];
-
-    // accumulators: residual at the base state and at each own deflection
-    double R0[NB], Rd[NB][ND][NB];
-#pragma unroll
-    for (int e = 0; e < NB; ++e) {
-        double source = P.q ? P.q[(size_t)I * NB + e] : 0.0;      // fvlocalresidual.hh:319-333
-        source *= vol * extr;
-        double r = 0.0;
-        r -= source;
-        R0[e] = r;
-#pragma unroll
-        for (int pv = 0; pv < NB; ++pv)
-#pragma unroll
-            for (int k = 0; k < ND; ++k) Rd[pv][k][e] = r;
-    }
-
-    // BCRS positions: columns ascending = -z,-y,-x,diag,+x,+y,+z among the existing neighbours
-    bool ex[6];
-#pragma unroll
-    for (int s = 0; s < 6; ++s) {
-        const int a = s >> 1;
-        ex[s] = (a < dim) && ((s & 1) ? (ci[a] + 1 < P.nc[a]) : (ci[a] > 0));
-    }
-    const int rowStart = P.rowptr[I];
-    const int posDiag = rowStart + (ex[4] ? 1 : 0) + (ex[2] ? 1 : 0) + (ex[0] ? 1 : 0);
-    int pos[6];
-    pos[4] = rowStart;
-    pos[2] = rowStart + (ex[4] ? 1 : 0);
-    pos[0] = pos[2] + (ex[2] ? 1 : 0);
-    pos[1] = posDiag + 1;
-    pos[3] = pos[1] + (ex[1] ? 1 : 0);
-    pos[5] = pos[3] + (ex[3] ? 1 : 0);
-
-#pragma unroll
-    for (int s = 0; s < 6; ++s) {
-        const int a = s >> 1;
-        if (a >= dim) continue;
-        const bool hi = (s & 1);
-        // face area = product of the widths of the other axes, ascending axis order
-        double area = 1.0;
-        for (int d = 0; d < dim; ++d)
-            if (d != a) area *= P.width[d][ci[d]];
-        FaceData<NPH> F;
-        F.area = area;
-        F.grav = P.enable_gravity && (a == va);
-        const double ng = hi ? -P.gravity : P.gravity;       // n.g with g = -gravity*e_va
-        F.alphaI = KI * ng * extr;                           // vtmv(n,K,g)*extrusion (common/math.hh:908-913)
-        F.alphaJ = 0.0;
-        F.tJ = 1.0;
-        if (ex[s]) {
-            const int J = hi ? I + stride[a] : I - stride[a];
-            const int cj = hi ? ci[a] + 1 : ci[a] - 1;
-            F.interior = true;
-            F.tij = hi ? P.tij[a][I] : P.tij[a][J];
-            const double KJ = P.K[J];
-            if (F.grav) {
-                F.tJ = KJ * extr * (hi ? P.gf_lo[a][cj] : P.gf_hi[a][cj]);
-                F.alphaJ = KJ * ng * extr;
-                if (!TABLE) {
-#pragma unroll
-                    for (int ph = 0; ph < NPH; ++ph) {
-                        const double rho = (P.rho[ph] + P.rho[ph]) * 0.5;
-                        F.c1[ph] = rho * area * F.alphaI;
-                        F.c2[ph] = rho * F.tij / F.tJ * (F.alphaI - F.alphaJ);
-                    }
-                }
-            }
-            double uJ[NB], epsJ[NB];
-#pragma unroll
-            for (int e = 0; e < NB; ++e) { uJ[e] = P.cur[(size_t)J * NB + e]; epsJ[e] = fd_eps(P, uJ[e], e); }
-            CellState<NPH> sJ0;
-            double SnJ;
-            load_state<MODEL, TABLE, NPH>(P, J, -1, 0, uJ, epsJ, sJ0, &SnJ);
-            double F0[NPH];
-            face_flux<NPH, TABLE>(F, sI0, sJ0, fullUpwind, w, F0);
-#pragma unroll
-            for (int e = 0; e < NB; ++e) R0[e] += F0[e];
-#pragma unroll
-            for (int pv = 0; pv < NB; ++pv)
-#pragma unroll
-                for (int k = 0; k < ND; ++k) {
-                    double Fk[NPH];
-                    face_flux<NPH, TABLE>(F, sId[pv][k], sJ0, fullUpwind, w, Fk);
-#pragma unroll
-                    for (int e = 0; e < NB; ++e) Rd[pv][k][e] += Fk[e];
-                }
-            if (with_jac) {
-                // A[I][J][e][pv] = FD quotient of the face flux w.r.t. u_J[pv] (cclocalassembler.hh:211-218,254-258,331-332)
-                double blk[NB][NB];
-#pragma unroll
-                for (int pv = 0; pv < NB; ++pv) {
-                    double Fd[ND][NPH];
-#pragma unroll
-                    for (int k = 0; k < ND; ++k) {
-                        CellState<NPH> sJd;
-                        double dummy;
-                        load_state<MODEL, TABLE, NPH>(P, J, pv, k, uJ, epsJ, sJd, &dummy);
-                        face_flux<NPH, TABLE>(F, sI0, sJd, fullUpwind, w, Fd[k]);
-                    }
-#pragma unroll
-                    for (int e = 0; e < NB; ++e) {
-                        double fk[ND];
-#pragma unroll
-                        for (int k = 0; k < ND; ++k) fk[k] = Fd[k][e];
-                        // reference accumulates the neighbour flux into a zeroed vector first (0 + f)
-                        blk[e][pv] = fd_quotient<ND>(P.fd_method, F0[e], fk, epsJ[pv]);
-                    }
-                }
-                double* dst = P.jac + (size_t)pos[s] * (NB * NB);
-                if (NB == 2) {
-                    reinterpret_cast<double2*>(dst)[0] = make_double2(blk[0][0], blk[0][NB - 1]);
-                    reinterpret_cast<double2*>(dst)[1] = make_double2(blk[NB - 1][0], blk[NB - 1][NB - 1]);
-                } else
-                    dst[0] = blk[0][0];
-            }
-        } else {
-            // boundary face: cclocalresidual.hh:64-105
-            int f;   // face index within the side, lower remaining axis fastest
-            if (a == 0) f = ci[1] + ny * ci[2];
-            else if (a == 1) f = ci[0] + nx * ci[2];
-            else f = ci[0] + nx * ci[1];
-            const int type = P.bc_type[s] ? P.bc_type[s][f] : DMX_BC_NEUMANN;
-            if (type == DMX_BC_DIRICHLET) {
-                F.interior = false;
-                const double ti = KI * extr * (hi ? P.gf_hi[a][ci[a]] : P.gf_lo[a][ci[a]]);
-                F.tij = area * ti;
-                CellState<NPH> sD;
-#pragma unroll
-                for (int ph = 0; ph < NPH; ++ph) {
-                    sD.p[ph] = P.bc_p[s][(size_t)f * 2 + ph];
-                    sD.up[ph] = P.bc_up[s][(size_t)f * 2 + ph];
-                    sD.rho[ph] = P.bc_rho[s][(size_t)f * 2 + ph];
-                    F.c1[ph] = sD.rho[ph] * area * F.alphaI;
-                    F.c2[ph] = 0.0;
-                }
-                double F0[NPH];
-                face_flux<NPH, TABLE>(F, sI0, sD, fullUpwind, w, F0);
-#pragma unroll
-                for (int e = 0; e < NB; ++e) R0[e] += F0[e];
-#pragma unroll
-                for (int pv = 0; pv < NB; ++pv)
-#pragma unroll
-                    for (int k = 0; k < ND; ++k) {
-                        double Fk[NPH];
-                        face_flux<NPH, TABLE>(F, sId[pv][k], sD, fullUpwind, w, Fk);
-#pragma unroll
-                        for (int e = 0; e < NB; ++e) Rd[pv][k][e] += Fk[e];
-                    }
-            } else if (type == DMX_BC_NEUMANN) {
-#pragma unroll
-                for (int e = 0; e < NB; ++e) {
-                    double nf = P.bc_neumann[s] ? P.bc_neumann[s][(size_t)f * NB + e] : 0.0;
-                    nf *= area * extr;
-                    R0[e] += nf;
-#pragma unroll
-                    for (int pv = 0; pv < NB; ++pv)
-#pragma unroll
-                        for (int k = 0; k < ND; ++k) Rd[pv][k][e] += nf;
-                }
-            }
-            // DMX_BC_NONE: outer face of an overlap cell, no scvf exists (tpfa/fvgridgeometry.hh:272-320)
-        }
-    }
-
-    // storage: fvlocalresidual.hh:274-304: ((S(cur)*extr - S(prev)*extr)*V)/dt, added after flux+source
-    if (!P.stationary) {
-        const double phiI = P.phi[I];
-        const double phiE = 1.0 - (1.0 - phiI);     // porosity = 1 - inert volume fraction
-        double prevSt[NB];
-        {
-            CellState<NPH> sP;
-            double SnP = 0.0;
-            if constexpr (MODEL == DMX_MODEL_2P) {
-                SnP = P.prev[(size_t)I * NB + NB - 1];
-                sP.rho[0] = P.rho[0];
-                sP.rho[NPH - 1] = P.rho[1];
-            } else {
-                sP.rho[0] = TABLE ? table_interp(P.table, P.table.rho, P.prev[I]) : P.rho[0];
-            }
-            storage_term<MODEL, NPH>(phiE, sP, SnP, prevSt);
-#pragma unroll
-            for (int e = 0; e < NB; ++e) prevSt[e] *= extr;
-        }
-        auto addStorage = [&](const CellState<NPH>& s, double Sn, double* acc) {
-            double st[NB];
-            storage_term<MODEL, NPH>(phiE, s, Sn, st);
-#pragma unroll
-            for (int e = 0; e < NB; ++e) {
-                st[e] *= extr;
-                st[e] -= prevSt[e];
-                st[e] *= vol;
-                st[e] /= P.dt;
-                acc[e] += st[e];
-            }
-        };
-        addStorage(sI0, SnI0, R0);
-#pragma unroll
-        for (int pv = 0; pv < NB; ++pv)
-#pragma unroll
-            for (int k = 0; k < ND; ++k) addStorage(sId[pv][k], SnId[pv][k], Rd[pv][k]);
-    }
-
-    bool finite = true;
-#pragma unroll
-    for (int e = 0; e < NB; ++e) {
-        P.residual[(size_t)I * NB + e] = R0[e];
-        finite = finite && (fabs(R0[e]) <= DBL_MAX);
-    }
-    if (!finite) atomicOr(P.flag_nonfinite, 1);
-
-    if (with_jac) {
-        double blk[NB][NB];
-#pragma unroll
-        for (int pv = 0; pv < NB; ++pv)
-#pragma unroll
-            for (int e = 0; e < NB; ++e) {
-                double fk[ND];
-#pragma unroll
-                for (int k = 0; k < ND; ++k) fk[k] = Rd[pv][k][e];
-                blk[e][pv] = fd_quotient<ND>(P.fd_method, R0[e], fk, epsI[pv]);
-            }
-        double* dst = P.jac + (size_t)posDiag * (NB * NB);
-        if (NB == 2) {
-            reinterpret_cast<double2*>(dst)[0] = make_double2(blk[0][0], blk[0][NB - 1]);
-            reinterpret_cast<double2*>(dst)[1] = make_double2(blk[NB - 1][0], blk[NB - 1][NB - 1]);
-        } else
-            dst[0] = blk[0][0];
     }
 }
 
@@ -508,8 +107,8 @@ __global__ void __launch_bounds__(128) assemble_kernel(AsmParams P, int with_jac
 //      at the own deflections (diagonal block) and at each neighbour's deflections (off-diagonal blocks), FD quotients
 //      through div_by (correctly rounded, shared reciprocal), 32-byte block stores into the BCRS values.
 // HBM traffic per cell: cur, prev, K, phi, region, 3 transmissibilities, rowptr in; residual + 7 blocks out -- no
-// secondary-variable records in global memory.  Arithmetic and operation order are those of assemble_kernel above
-// (bit-identical results).
+// secondary-variable records in global memory.  Arithmetic and operation order follow the reference's local assembler
+// (bit-identical to the CPU oracle).
 // ================================================================================================
 constexpr int AT_TX = 32, AT_TY = 8, AT_THREADS = AT_TX * AT_TY;
 constexpr int AT_HX = AT_TX + 2, AT_HY = AT_TY + 2, AT_HC = AT_HX * AT_HY;
@@ -520,12 +119,27 @@ struct RecLayout {
     static constexpr int NB = (MODEL == DMX_MODEL_2P) ? 2 : 1;
     static constexpr int NS = (MODEL == DMX_MODEL_2P) ? 3 : (TABLE ? 2 : 0);   // 2p: pc, rho_w*mob_w, rho_n*mob_n; 1p table: rho, rho*mob
     static constexpr int U = 0;               // primary variables
-    static constexpr int RD = NB;             // reciprocal FD denominators per primary variable
-    static constexpr int KF = 2 * NB;         // permeability
-    static constexpr int ST = 2 * NB + 1;     // states: base, then one per deflection of the state-changing primary variable
+    static constexpr int EPS = NB;            // FD step per primary variable (SIGNED for one-sided differences, see fd_step)
+    static constexpr int RD = 2 * NB;         // reciprocal FD denominators per primary variable
+    static constexpr int KF = 3 * NB;         // permeability
+    static constexpr int ST = 3 * NB + 1;     // states: base, then one per deflection of the state-changing primary variable
     static constexpr int NF = ST + NS * (1 + NDR);
 };
 
+// Step as stored per cell.  One-sided differences (ND == 1) keep the SIGNED step (backward: -eps): x0 + (-eps) == x0 - eps and
+// (f1 - f0)/(-eps) == (f0 - f1)/eps bit for bit, so neither the deflection nor the quotient needs to look at the method again.
+template <int ND>
+__device__ __forceinline__ double fd_step(const AsmParams& P, double x, int pv)
+{
+    const double eps = fd_eps(P, x, pv);
+    return (ND == 1 && P.fd_method < 0) ? -eps : eps;
+}
+template <int ND>
+__device__ __forceinline__ double fd_defl(const AsmParams& P, int k, double x0, double step)
+{
+    if (ND == 1) return x0 + step;
+    return fd_deflect(P.fd_method, k, x0, step);
+}
 template <int ND>
 __device__ __forceinline__ double fd_den(double eps)
 {
@@ -535,12 +149,12 @@ __device__ __forceinline__ double fd_den(double eps)
 }
 // fd_quotient with the division by the step replaced by div_by (same bits)
 template <int ND>
-__device__ __forceinline__ double fd_quotient_r(int method, double f0, const double* f, double eps, double rden)
+__device__ __forceinline__ double fd_quotient_r(double f0, const double* f, double eps, double rden)
 {
     double d;
     if (ND == 1) {
-        if (method >= 0) { d = f[0]; d -= f0; }
-        else { d = f0; d -= f[0]; }
+        d = f[0];
+        d -= f0;
     } else if (ND == 2) {
         d = f[0];
         d -= f[1];
@@ -570,12 +184,14 @@ __device__ __forceinline__ void fill_cell(const AsmParams& P, const MaterialLaw*
         rec[(L::ST + 1) * AT_HC] = P.rho[0] * div_by(c.krw, P.mu[0], P.rmu[0]);
         rec[(L::ST + 2) * AT_HC] = P.rho[1] * div_by(c.krn, P.mu[1], P.rmu[1]);
         if constexpr (JAC) {
-            const double epsP = fd_eps(P, u.x, 0), epsS = fd_eps(P, u.y, 1);
+            const double epsP = fd_step<ND>(P, u.x, 0), epsS = fd_step<ND>(P, u.y, 1);
+            rec[(L::EPS + 0) * AT_HC] = epsP;
+            rec[(L::EPS + 1) * AT_HC] = epsS;
             rec[(L::RD + 0) * AT_HC] = 1.0 / fd_den<ND>(epsP);
             rec[(L::RD + 1) * AT_HC] = 1.0 / fd_den<ND>(epsS);
 #pragma unroll
             for (int k = 0; k < ND; ++k) {
-                const double Snk = fd_deflect(P.fd_method, k, u.y, epsS);
+                const double Snk = fd_defl<ND>(P, k, u.y, epsS);
                 c = law_eval3_call(&law, 1 - Snk);
                 rec[(L::ST + 3 * (1 + k) + 0) * AT_HC] = c.pc;
                 rec[(L::ST + 3 * (1 + k) + 1) * AT_HC] = P.rho[0] * div_by(c.krw, P.mu[0], P.rmu[0]);
@@ -587,7 +203,8 @@ __device__ __forceinline__ void fill_cell(const AsmParams& P, const MaterialLaw*
         rec[L::U * AT_HC] = p;
         double eps = 0.0;
         if constexpr (JAC) {
-            eps = fd_eps(P, p, 0);
+            eps = fd_step<ND>(P, p, 0);
+            rec[L::EPS * AT_HC] = eps;
             rec[L::RD * AT_HC] = 1.0 / fd_den<ND>(eps);
         }
         if constexpr (TABLE) {
@@ -598,7 +215,7 @@ __device__ __forceinline__ void fill_cell(const AsmParams& P, const MaterialLaw*
             if constexpr (JAC) {
 #pragma unroll
                 for (int k = 0; k < ND; ++k) {
-                    table_interp2(P.table, fd_deflect(P.fd_method, k, p, eps), &rho, &mu);
+                    table_interp2(P.table, fd_defl<ND>(P, k, p, eps), &rho, &mu);
                     rec[(L::ST + 2 * (1 + k) + 0) * AT_HC] = rho;
                     rec[(L::ST + 2 * (1 + k) + 1) * AT_HC] = rho * (1.0 / mu);
                 }
@@ -616,8 +233,8 @@ __device__ __forceinline__ void tile_state(const AsmParams& P, const double* rec
     if constexpr (MODEL == DMX_MODEL_2P) {
         double pw = uC[0], Sn = uC[1];
         int st = 0;
-        if (pv == 0) pw = fd_deflect(P.fd_method, k, pw, epsC[0]);
-        if (pv == 1) { Sn = fd_deflect(P.fd_method, k, Sn, epsC[1]); st = 1 + k; }
+        if (pv == 0) pw = fd_defl<NDR>(P, k, pw, epsC[0]);
+        if (pv == 1) { Sn = fd_defl<NDR>(P, k, Sn, epsC[1]); st = 1 + k; }
         const double pc = rec[(L::ST + 3 * st + 0) * AT_HC];
         s.p[0] = pw;
         s.p[NPH - 1] = pw + pc;
@@ -628,7 +245,7 @@ __device__ __forceinline__ void tile_state(const AsmParams& P, const double* rec
         *Sn_out = Sn;
     } else {
         double p = uC[0];
-        if (pv == 0) p = fd_deflect(P.fd_method, k, p, epsC[0]);
+        if (pv == 0) p = fd_defl<NDR>(P, k, p, epsC[0]);
         s.p[0] = p;
         if constexpr (TABLE) {
             const int st = (pv == 0) ? 1 + k : 0;
@@ -680,7 +297,7 @@ __device__ __forceinline__ void store_block(double* dst, const double (&blk)[NB]
         dst[0] = blk[0][0];
 }
 
-template <int MODEL, bool TABLE, int ND, bool JAC>
+template <int MODEL, bool TABLE, int ND, bool JAC, int DIM>
 __global__ void __launch_bounds__(AT_THREADS, (ND == 1) ? 2 : 1) assemble_tile_kernel(const AsmParams P)
 {
     constexpr int NDR = JAC ? ND : 0;
@@ -692,7 +309,7 @@ __global__ void __launch_bounds__(AT_THREADS, (ND == 1) ? 2 : 1) assemble_tile_k
 
     const int t = threadIdx.x, li = t & (AT_TX - 1), lj = t / AT_TX;
     const int nx = P.nc[0], ny = P.nc[1], nz = P.nc[2];
-    const int dim = P.dim, va = dim - 1;
+    constexpr int dim = DIM, va = DIM - 1;
     const int ntx = (nx + AT_TX - 1) / AT_TX;
     const int i0 = ((int)blockIdx.x % ntx) * AT_TX, j0 = ((int)blockIdx.x / ntx) * AT_TY;
     const int kz0 = (int)blockIdx.y * P.zchunk, kz1 = min(nz, kz0 + P.zchunk);
@@ -779,7 +396,7 @@ __global__ void __launch_bounds__(AT_THREADS, (ND == 1) ? 2 : 1) assemble_tile_k
 #pragma unroll
             for (int e = 0; e < NB; ++e) {
                 uI[e] = recI[(L::U + e) * AT_HC];
-                epsI[e] = fd_eps(P, uI[e], e);
+                epsI[e] = JAC ? recI[(L::EPS + e) * AT_HC] : 0.0;
                 rdI[e] = JAC ? recI[(L::RD + e) * AT_HC] : 0.0;
             }
             CellState<NPH> sI0, sId[NB][NDE];
@@ -868,7 +485,7 @@ __global__ void __launch_bounds__(AT_THREADS, (ND == 1) ? 2 : 1) assemble_tile_k
                     }
                     double uJ[NB], epsJ[NB];
 #pragma unroll
-                    for (int e = 0; e < NB; ++e) { uJ[e] = recJ[(L::U + e) * AT_HC]; epsJ[e] = fd_eps(P, uJ[e], e); }
+                    for (int e = 0; e < NB; ++e) { uJ[e] = recJ[(L::U + e) * AT_HC]; epsJ[e] = JAC ? recJ[(L::EPS + e) * AT_HC] : 0.0; }
                     CellState<NPH> sJ0;
                     double SnJ;
                     tile_state<MODEL, TABLE, NDR, NPH>(P, recJ, -1, 0, uJ, epsJ, sJ0, &SnJ);
@@ -904,7 +521,7 @@ __global__ void __launch_bounds__(AT_THREADS, (ND == 1) ? 2 : 1) assemble_tile_k
                                 double fk[ND];
 #pragma unroll
                                 for (int kk = 0; kk < ND; ++kk) fk[kk] = Fd[kk][e];
-                                blk[e][pv] = fd_quotient_r<ND>(P.fd_method, F0[e], fk, epsJ[pv], rdJ);
+                                blk[e][pv] = fd_quotient_r<ND>(F0[e], fk, epsJ[pv], rdJ);
                             }
                         }
                         store_block<NB>(P.jac + (size_t)pos[s] * (NB * NB), blk);
@@ -1017,7 +634,7 @@ __global__ void __launch_bounds__(AT_THREADS, (ND == 1) ? 2 : 1) assemble_tile_k
                         double fk[ND];
 #pragma unroll
                         for (int kk = 0; kk < ND; ++kk) fk[kk] = Rd[pv][kk][e];
-                        blk[e][pv] = fd_quotient_r<ND>(P.fd_method, R0[e], fk, epsI[pv], rdI[pv]);
+                        blk[e][pv] = fd_quotient_r<ND>(R0[e], fk, epsI[pv], rdI[pv]);
                     }
                 store_block<NB>(P.jac + (size_t)posDiag * (NB * NB), blk);
             }
@@ -1064,7 +681,6 @@ static void fill_params(dmx_ctx* ctx, AsmParams& P)
         P.bc_p[s] = ctx->d_bc_p[s]; P.bc_up[s] = ctx->d_bc_up[s]; P.bc_rho[s] = ctx->d_bc_rho[s];
     }
     P.cur = ctx->d_vec[DMX_VEC_CUR]; P.prev = ctx->d_vec[DMX_VEC_PREV];
-    P.rec = ctx->d_rec; P.nrec = ctx->nrec;
     P.rowptr = ctx->d_rowptr; P.residual = ctx->d_vec[DMX_VEC_RESIDUAL]; P.jac = ctx->d_J;
     P.flag_nonfinite = ctx->d_flag;
 }
@@ -1157,16 +773,6 @@ int prepare(dmx_ctx* ctx)
         if (int rc = upload(ctx, &ctx->d_bc_up[s], up)) return rc;
         if (int rc = upload(ctx, &ctx->d_bc_rho[s], rho)) return rc;
     }
-    // records
-    const int nd = (ctx->opt.fd_method == 5) ? 4 : (ctx->opt.fd_method == 0 ? 2 : 1);
-    int nrec = 0;
-    if (ctx->model == DMX_MODEL_2P) nrec = 3 * (1 + nd);
-    else if (ctx->tabulated) nrec = 2 * (1 + nd);
-    if (nrec != ctx->nrec) {
-        if (ctx->d_rec) { cudaFree(ctx->d_rec); ctx->d_rec = nullptr; }
-        if (nrec) DMX_CUDA(cudaMalloc((void**)&ctx->d_rec, (size_t)nrec * ctx->n * sizeof(double)));
-        ctx->nrec = nrec;
-    }
     // transmissibilities
     for (int a = 0; a < 3; ++a)
         if (!ctx->d_tij[a]) DMX_CUDA(cudaMalloc((void**)&ctx->d_tij[a], (size_t)ctx->n * sizeof(double)));
@@ -1179,38 +785,12 @@ int prepare(dmx_ctx* ctx)
     return 0;
 }
 
-template <int MODEL, bool TABLE>
-static int launch_nd(dmx_ctx* ctx, const AsmParams& P, bool with_jac, bool volvars_only)
-{
-    const int n = ctx->n;
-    const int vt = 256, at = 128;
-    const bool needRec = (MODEL == DMX_MODEL_2P) || TABLE;
-#define DMX_LAUNCH_ND(ND)                                                                                    \
-    do {                                                                                                     \
-        if (needRec) {                                                                                       \
-            ProfScope ps__(ctx, DMX_K_VOLVARS);                                                              \
-            volvars_kernel<MODEL, ND><<<(n + vt - 1) / vt, vt, 0, ctx->stream>>>(P);                         \
-            DMX_CHECK_LAUNCH();                                                                              \
-        }                                                                                                    \
-        if (!volvars_only) {                                                                                 \
-            ProfScope ps__(ctx, DMX_K_ASSEMBLY);                                                             \
-            assemble_kernel<MODEL, TABLE, ND><<<(n + at - 1) / at, at, 0, ctx->stream>>>(P, with_jac ? 1 : 0); \
-            DMX_CHECK_LAUNCH();                                                                              \
-        }                                                                                                    \
-    } while (0)
-    if (P.nd == 1) DMX_LAUNCH_ND(1);
-    else if (P.nd == 2) DMX_LAUNCH_ND(2);
-    else DMX_LAUNCH_ND(4);
-#undef DMX_LAUNCH_ND
-    return 0;
-}
-
-template <int MODEL, bool TABLE, int ND, bool JAC>
-static int launch_tile_inst(dmx_ctx* ctx, const AsmParams& P)
+template <int MODEL, bool TABLE, int ND, bool JAC, int DIM>
+static int launch_tile_dim(dmx_ctx* ctx, const AsmParams& P)
 {
     using L = RecLayout<MODEL, TABLE, JAC ? ND : 0>;
     const size_t smem = 3 * (size_t)L::NF * AT_HC * sizeof(double) + (MODEL == DMX_MODEL_2P ? DMX_MAX_REGIONS * sizeof(MaterialLaw) : 0);
-    auto kern = assemble_tile_kernel<MODEL, TABLE, ND, JAC>;
+    auto kern = assemble_tile_kernel<MODEL, TABLE, ND, JAC, DIM>;
     DMX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int ntx = (ctx->nc[0] + AT_TX - 1) / AT_TX, nty = (ctx->nc[1] + AT_TY - 1) / AT_TY;
     const dim3 grid((unsigned)(ntx * nty), (unsigned)((ctx->nc[2] + P.zchunk - 1) / P.zchunk));
@@ -1218,6 +798,14 @@ static int launch_tile_inst(dmx_ctx* ctx, const AsmParams& P)
     kern<<<grid, AT_THREADS, smem, ctx->stream>>>(P);
     DMX_CHECK_LAUNCH();
     return 0;
+}
+
+template <int MODEL, bool TABLE, int ND, bool JAC>
+static int launch_tile_inst(dmx_ctx* ctx, const AsmParams& P)
+{
+    if (P.dim == 3) return launch_tile_dim<MODEL, TABLE, ND, JAC, 3>(ctx, P);
+    if (P.dim == 2) return launch_tile_dim<MODEL, TABLE, ND, JAC, 2>(ctx, P);
+    return launch_tile_dim<MODEL, TABLE, ND, JAC, 1>(ctx, P);
 }
 
 template <int MODEL, bool TABLE>
@@ -1230,29 +818,19 @@ static int launch_tile(dmx_ctx* ctx, const AsmParams& P, bool with_jac)
     return launch_tile_inst<MODEL, TABLE, 4, true>(ctx, P);
 }
 
-static bool use_legacy_kernels()
-{
-    static const bool legacy = [] { const char* e = getenv("DMX_ASM_LEGACY"); return e && e[0] == '1'; }();
-    return legacy;
-}
-
 static int launch_impl(dmx_ctx* ctx, bool with_jac, bool volvars_only)
 {
     if (int rc = prepare(ctx)) return rc;
     if (!ctx->opt.stationary && ctx->opt.dt <= 0.0) return fail(ctx, DMX_ERR_USAGE, "assemble: dt must be > 0");
     AsmParams P;
     fill_params(ctx, P);
-    if (!volvars_only && !use_legacy_kernels()) {
-        if (ctx->model == DMX_MODEL_2P) return launch_tile<DMX_MODEL_2P, false>(ctx, P, with_jac);
-        if (ctx->tabulated) return launch_tile<DMX_MODEL_1P, true>(ctx, P, with_jac);
-        return launch_tile<DMX_MODEL_1P, false>(ctx, P, with_jac);
-    }
-    if (ctx->model == DMX_MODEL_2P) return launch_nd<DMX_MODEL_2P, false>(ctx, P, with_jac, volvars_only);
-    if (ctx->tabulated) return launch_nd<DMX_MODEL_1P, true>(ctx, P, with_jac, volvars_only);
-    return launch_nd<DMX_MODEL_1P, false>(ctx, P, with_jac, volvars_only);
+    (void)volvars_only;
+    if (ctx->model == DMX_MODEL_2P) return launch_tile<DMX_MODEL_2P, false>(ctx, P, with_jac);
+    if (ctx->tabulated) return launch_tile<DMX_MODEL_1P, true>(ctx, P, with_jac);
+    return launch_tile<DMX_MODEL_1P, false>(ctx, P, with_jac);
 }
 
 int launch_assemble(dmx_ctx* ctx, bool with_jacobian) { return launch_impl(ctx, with_jacobian, false); }
-int launch_volvars_only(dmx_ctx* ctx) { return launch_impl(ctx, false, true); }
+int launch_volvars_only(dmx_ctx* ctx) { return fail(ctx, DMX_ERR_USAGE, "the secondary variables are evaluated inside the assembly kernel"); }
 
 } // namespace dmx

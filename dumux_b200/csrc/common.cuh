@@ -53,8 +53,6 @@ struct AsmParams {
     // state
     const double* cur;
     const double* prev;
-    double* rec;              // secondary-variable records, SoA [nrec][n]
-    int nrec;
     // outputs
     const int* rowptr;
     double* residual;
@@ -122,8 +120,6 @@ struct dmx_ctx {
     // vectors
     double* d_vec[DMX_NUM_VECS] = {};
     double *d_rt = nullptr, *d_p = nullptr, *d_v = nullptr, *d_t = nullptr, *d_y = nullptr, *d_dinv = nullptr;
-    double* d_rec = nullptr;
-    int nrec = 0;
 
     // ILU0 level schedule (rows sorted by level; level_ptr on host)
     int *d_lrows = nullptr, *d_urows = nullptr;

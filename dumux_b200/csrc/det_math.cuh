@@ -51,6 +51,24 @@ DMX_HD double fma_rn(double a, double b, double c)
 #endif
 }
 
+// Polynomial coefficients (atanh series for log, Taylor series of 2^r).  On the device they live in the constant bank so
+// that each Horner step is ONE DFMA with a c[][] operand (64-bit immediates cost two extra uniform moves per step).
+#define DMX_DET_LOG_COEFFS {0x1.2f684bda12f68p-4, 0x1.47ae147ae147bp-4, 0x1.642c8590b2164p-4, 0x1.8618618618618p-4, 0x1.af286bca1af28p-4, 0x1.e1e1e1e1e1e1ep-4, 0x1.1111111111111p-3, 0x1.3b13b13b13b14p-3, 0x1.745d1745d1746p-3, 0x1.c71c71c71c71cp-3, 0x1.2492492492492p-2, 0x1.999999999999ap-2, 0x1.5555555555555p-1}
+#define DMX_DET_EXP_COEFFS {0x1.314964d5878a9p-44, 0x1.816193166d0f9p-40, 0x1.c3bd650fc2986p-36, 0x1.e8cac7351bb25p-32, 0x1.e4cf5158b8ecap-28, 0x1.b5253d395e7c4p-24, 0x1.62c0223a5c824p-20, 0x1.ffcbfc588b0c7p-17, 0x1.430912f86c787p-13, 0x1.5d87fe78a6731p-10, 0x1.3b2ab6fba4e77p-7, 0x1.c6b08d704a0c0p-5, 0x1.ebfbdff82c58fp-3, 0x1.62e42fefa39efp-1}
+#ifdef __CUDACC__
+static __constant__ double det_log_c_dev[13] = DMX_DET_LOG_COEFFS;
+static __constant__ double det_exp_c_dev[14] = DMX_DET_EXP_COEFFS;
+#endif
+static const double det_log_c_host[13] = DMX_DET_LOG_COEFFS;
+static const double det_exp_c_host[14] = DMX_DET_EXP_COEFFS;
+#ifdef __CUDA_ARCH__
+#define DMX_DET_LOG_C det_log_c_dev
+#define DMX_DET_EXP_C det_exp_c_dev
+#else
+#define DMX_DET_LOG_C det_log_c_host
+#define DMX_DET_EXP_C det_exp_c_host
+#endif
+
 // log2(x) in double-double for finite x > 0: the first half of det_pow.  Several powers of the same base (the three
 // Brooks-Corey curves, the nested van Genuchten terms) share ONE det_log2 -- same operation sequence per power, so
 // det_pow_from_log2(det_log2(x), x, y) returns exactly the bits of det_pow(x, y).
@@ -80,19 +98,9 @@ DMX_HD_NOINLINE DetLog2 det_log2(double x)
     const double s_lo = res / b;
     const double s2 = s_hi * s_hi;
 
-    double P = 0x1.2f684bda12f68p-4;
-    P = fma_rn(P, s2, 0x1.47ae147ae147bp-4);
-    P = fma_rn(P, s2, 0x1.642c8590b2164p-4);
-    P = fma_rn(P, s2, 0x1.8618618618618p-4);
-    P = fma_rn(P, s2, 0x1.af286bca1af28p-4);
-    P = fma_rn(P, s2, 0x1.e1e1e1e1e1e1ep-4);
-    P = fma_rn(P, s2, 0x1.1111111111111p-3);
-    P = fma_rn(P, s2, 0x1.3b13b13b13b14p-3);
-    P = fma_rn(P, s2, 0x1.745d1745d1746p-3);
-    P = fma_rn(P, s2, 0x1.c71c71c71c71cp-3);
-    P = fma_rn(P, s2, 0x1.2492492492492p-2);
-    P = fma_rn(P, s2, 0x1.999999999999ap-2);
-    P = fma_rn(P, s2, 0x1.5555555555555p-1);
+    double P = DMX_DET_LOG_C[0];
+#pragma unroll
+    for (int q = 1; q < 13; ++q) P = fma_rn(P, s2, DMX_DET_LOG_C[q]);
     const double tail = (s_hi * s2) * P;
 
     const double lh = 2.0 * s_hi;
@@ -131,20 +139,9 @@ DMX_HD_NOINLINE double det_exp2_scaled(DetLog2 L, double y)
     const long long n = (long long)(zh + (zh >= 0.0 ? 0.5 : -0.5));
     const double r = (zh - (double)n) + zl;
 
-    double Q = 0x1.314964d5878a9p-44;
-    Q = fma_rn(Q, r, 0x1.816193166d0f9p-40);
-    Q = fma_rn(Q, r, 0x1.c3bd650fc2986p-36);
-    Q = fma_rn(Q, r, 0x1.e8cac7351bb25p-32);
-    Q = fma_rn(Q, r, 0x1.e4cf5158b8ecap-28);
-    Q = fma_rn(Q, r, 0x1.b5253d395e7c4p-24);
-    Q = fma_rn(Q, r, 0x1.62c0223a5c824p-20);
-    Q = fma_rn(Q, r, 0x1.ffcbfc588b0c7p-17);
-    Q = fma_rn(Q, r, 0x1.430912f86c787p-13);
-    Q = fma_rn(Q, r, 0x1.5d87fe78a6731p-10);
-    Q = fma_rn(Q, r, 0x1.3b2ab6fba4e77p-7);
-    Q = fma_rn(Q, r, 0x1.c6b08d704a0c0p-5);
-    Q = fma_rn(Q, r, 0x1.ebfbdff82c58fp-3);
-    Q = fma_rn(Q, r, 0x1.62e42fefa39efp-1);
+    double Q = DMX_DET_EXP_C[0];
+#pragma unroll
+    for (int q = 1; q < 14; ++q) Q = fma_rn(Q, r, DMX_DET_EXP_C[q]);
     Q = fma_rn(Q, r, 1.0);
 
     if (n >= -1022 && n <= 1023) return Q * u2d((uint64_t)(n + 1023) << 52);

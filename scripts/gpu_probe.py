@@ -33,7 +33,7 @@ def timing(n):
     e.set_dt(250.0)
     e.assemble_device(True)
     cells = n ** 3
-    for which, nm, bytes_per in ((B.KERNEL_VOLVARS, "volvars", 0), (B.KERNEL_ASSEMBLY, "assembly", 292), (B.KERNEL_SPMV, "spmv", 288)):
+    for which, nm, bytes_per in ((B.KERNEL_ASSEMBLY, "assembly", 292), (B.KERNEL_SPMV, "spmv", 288)):
         ms = e.time_kernel(which, 5)
         print(f"{nm}: {ms:.3f} ms" + (f"  -> {bytes_per*cells/ms/1e6:.0f} GB/s algorithmic" if bytes_per else ""))
     t = time.time(); st = e.ilu0_factor(); e.synchronize(); print("ilu factor status", st, f"{time.time()-t:.3f}s")
