@@ -11,9 +11,15 @@
 //   * tiles depend only on their -x / -y neighbours (lower sweep; +x / +y for the upper sweep) which must run
 //     TI (TJ) steps ahead: point-to-point progress counters in global memory, published every SK_C steps, replace the
 //     grid barrier; tiles are handed out by an atomic ticket in dependency order, so waiting never deadlocks;
-//   * the factors are stored in a tile-skewed layout fac[tile][step][component][thread]: what a CTA needs at step s is
-//     ONE contiguous chunk (24-32 KB for 2x2 blocks), fetched with cp.async.bulk (TMA, 1-D) into a shared-memory ring
-//     several steps ahead and signalled through mbarriers -- HBM sees long sequential streams, no index arrays at all.
+//   * factors AND the vector travel in one tile-skewed stream per sweep, stream[tile][step][factor components | vector][thread]:
+//     what a CTA needs at step s is ONE contiguous chunk (28 KB lower, 36 KB upper for 2x2 blocks), fetched with a single
+//     cp.async.bulk (TMA, 1-D) into a shared-memory ring by a dedicated PRODUCER thread (warp 8) that re-arms a slot as soon
+//     as the 256 compute threads release it (full/empty mbarriers).  Measured on B200 (scripts/probes/stream_probe.cu): with
+//     the copy issued by a compute thread after the step's barrier an SM gets ONE copy per ~850-1100 cycles (26-34 B/clk at
+//     28 KB), with a producer thread the same ring streams 76 B/clk -- what a tile that runs alone (fill/drain of the tile
+//     wavefront) needs.  The lower sweep reads its right-hand side from the lower stream and writes its result into the vector
+//     slots of the UPPER stream; the upper sweep writes the final result into a separate skewed vector.  HBM sees long
+//     sequential streams, no index arrays at all.
 //
 // Per-row arithmetic (operation order, no FMA contraction) is that of blockILUBacksolve: columns ascending
 // (-z,-y,-x | +x,+y,+z), y -= A x per block (FieldMatrix::mmv), v = Dinv * rhs last (FieldMatrix::mv, sum from 0), so
@@ -27,9 +33,15 @@
 namespace dmx {
 
 constexpr int SK_TI = 16, SK_TJ = 16, SK_THREADS = SK_TI * SK_TJ;
-constexpr int SK_C = 8;                      // steps per chunk: progress is published / awaited once per chunk
-static_assert(SK_C * (SK_TI + SK_TJ) == SK_THREADS, "one halo load per thread and chunk");
+#ifndef SK_CHUNK
+#define SK_CHUNK 8
+#endif
+constexpr int SK_C = SK_CHUNK;               // steps per chunk: progress is published / awaited once per chunk
+static_assert((SK_C * (SK_TI + SK_TJ)) % 32 == 0, "halo values of a chunk are fetched by one warp");
 constexpr unsigned long long SK_EPOCH = 1ull << 20;
+#ifndef SK_POLL_NS
+#define SK_POLL_NS 100       // back-off between polls of an upstream tile's progress word (148 spinning CTAs saturate its L2 slice)
+#endif
 
 struct SkewGrid {
     int nx, ny, nz, ntx, nty, ntiles, NS;
@@ -64,6 +76,26 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase)
         "r"(phase)
         : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// barrier among the 256 compute threads only (the producer warp does not take part)
+__device__ __forceinline__ void compute_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t phase)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(phase)
+        : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ unsigned long long ld_acquire(const unsigned long long* p)
 {
     unsigned long long v;
@@ -80,7 +112,11 @@ template <int B, bool UPPER>
 struct SkewLayout {
     static constexpr int NBLK = UPPER ? 4 : 3;
     static constexpr int NC = NBLK * B * B;
-    static constexpr int STAGE_DOUBLES = NC * SK_THREADS;
+    static constexpr int STAGE_DOUBLES = NC * SK_THREADS;                    // factor part of one step
+    static constexpr int VEC_DOUBLES = B * SK_THREADS;                       // vector part of one step
+    static constexpr int STEP_DOUBLES = STAGE_DOUBLES + VEC_DOUBLES;         // stream stride per step
+    // depth of the shared-memory ring (steps in flight): 7 x 28 KB lower, 5 x 36 KB upper for 2x2 blocks
+    static constexpr int S = (B == 2) ? (UPPER ? 5 : 7) : 16;
 };
 
 // position of component (blk,r,c) of thread t inside one step chunk: 2x2 blocks are stored as double2 rows
@@ -110,7 +146,7 @@ __global__ void __launch_bounds__(SK_THREADS) ilu_skew_kernel(SkewGrid g, const 
     {
         // lower
         const int i = ti * SK_TI + a, j = tj * SK_TJ + b, k = s - a - b;
-        double* dst = Lsk + ((size_t)tile * g.NS + s) * SkewLayout<B, false>::STAGE_DOUBLES;
+        double* dst = Lsk + ((size_t)tile * g.NS + s) * SkewLayout<B, false>::STEP_DOUBLES;
         const bool valid = i < g.nx && j < g.ny && k >= 0 && k < g.nz;
         double blk[3][BB];
 #pragma unroll
@@ -134,7 +170,7 @@ __global__ void __launch_bounds__(SK_THREADS) ilu_skew_kernel(SkewGrid g, const 
     {
         // upper
         const int i = ti * SK_TI + (SK_TI - 1 - a), j = tj * SK_TJ + (SK_TJ - 1 - b), k = g.nz - 1 - (s - a - b);
-        double* dst = Usk + ((size_t)tile * g.NS + s) * SkewLayout<B, true>::STAGE_DOUBLES;
+        double* dst = Usk + ((size_t)tile * g.NS + s) * SkewLayout<B, true>::STEP_DOUBLES;
         const bool valid = i < g.nx && j < g.ny && k >= 0 && k < g.nz;
         double blk[4][BB];
 #pragma unroll
@@ -160,8 +196,9 @@ __global__ void __launch_bounds__(SK_THREADS) ilu_skew_kernel(SkewGrid g, const 
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// vectors in the tile-skewed layout (LOWER indexing): xsk[((tile*NS + s)*256 + t)*B + e], thread slot t = a + 16 b,
-// cell (i0+a, j0+b, k = s-a-b).  The upper sweep walks the same storage backwards: step s_up = NS-1-s, lane 255-t.
+// vectors in the tile-skewed layout (LOWER indexing): [(tile*NS + s)][t][e], thread slot t = a + 16 b, cell (i0+a, j0+b,
+// k = s-a-b).  vec_skew writes the right-hand side into the vector slots of the LOWER stream; the upper sweep walks the same
+// ordering backwards: step s_up = NS-1-s, lane 255-t.
 // ------------------------------------------------------------------------------------------------------------
 template <int B>
 __global__ void __launch_bounds__(SK_THREADS) vec_skew_kernel(SkewGrid g, const double* __restrict__ x, double* __restrict__ xsk)
@@ -182,7 +219,8 @@ __global__ void __launch_bounds__(SK_THREADS) vec_skew_kernel(SkewGrid g, const 
             val[0] = w.x; val[B - 1] = w.y;
         } else val[0] = x[I];
     }
-    double* dst = xsk + ((size_t)blockIdx.x * SK_THREADS + t) * B;
+    using LY = SkewLayout<B, false>;
+    double* dst = xsk + (size_t)blockIdx.x * LY::STEP_DOUBLES + LY::STAGE_DOUBLES + (size_t)t * B;
     if (B == 2) *reinterpret_cast<double2*>(dst) = make_double2(val[0], val[B - 1]);
     else dst[0] = val[0];
 }
@@ -203,23 +241,32 @@ __global__ void __launch_bounds__(256) vec_unskew_kernel(SkewGrid g, const doubl
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// one triangular sweep, in place on the skewed vector.  LOWER: x <- L^-1 x (unit lower).  UPPER: x <- U^-1 x.
+// one triangular sweep.  LOWER: out <- L^-1 rhs (unit lower), rhs from the vector slots of the lower stream, result into the
+// vector slots of the upper stream.  UPPER: out <- U^-1 rhs, rhs from the upper stream, result into the skewed vector xsk.
+//   stream : this sweep's [factors | rhs] stream
+//   out    : where results go (LOWER: the upper stream, UPPER: xsk); upstream tiles' results are read back from it
 // ------------------------------------------------------------------------------------------------------------
-template <int B, bool UPPER, int S, int MINB>
-__global__ void __launch_bounds__(SK_THREADS, MINB) ilu_sweep_kernel(SkewGrid g, const double* __restrict__ fac, double* xsk,
-                                                                      const int* __restrict__ order, unsigned long long* ticket_ctr,
-                                                                      unsigned long long ticket_base, unsigned long long* prog,
-                                                                      unsigned long long epoch, long long* trace)
+template <int B, bool UPPER>
+__global__ void __launch_bounds__(SK_THREADS + 64, 1) ilu_sweep_kernel(SkewGrid g, const double* __restrict__ stream, double* out,
+                                                                   const int* __restrict__ order, unsigned long long* ticket_ctr,
+                                                                   unsigned long long ticket_base, unsigned long long* prog,
+                                                                   unsigned long long epoch, long long* trace)
 {
     using LY = SkewLayout<B, UPPER>;
-    constexpr int VEC_DOUBLES = SK_THREADS * B;
-    constexpr int STAGE_ALL = LY::STAGE_DOUBLES + VEC_DOUBLES;
+    using LYU = SkewLayout<B, true>;
+    constexpr int S = LY::S;
+    // where results live: LOWER -> vector slots of the upper stream (step stride STEP_U, offset FAC_U); UPPER -> xsk
+    constexpr size_t OUT_STEP = UPPER ? (size_t)LY::VEC_DOUBLES : (size_t)LYU::STEP_DOUBLES;
+    constexpr size_t OUT_OFF = UPPER ? 0 : (size_t)LYU::STAGE_DOUBLES;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double* stages = reinterpret_cast<double*>(smem_raw);                              // [S][factors | vector]
-    double* sv = stages + (size_t)S * STAGE_ALL;                                       // [2][TJ+1][TI+1][B]
-    double* hx = sv + 2 * (SK_TJ + 1) * (SK_TI + 1) * B;                               // [C][TJ][B]
-    double* hy = hx + SK_C * SK_TJ * B;                                                // [C][TI][B]
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(hy + SK_C * SK_TI * B);               // [S]
+    double* stages = reinterpret_cast<double*>(smem_raw);                              // [S][factors | rhs]
+    double* sv = stages + (size_t)S * LY::STEP_DOUBLES;                                // [2][TJ+1][TI+1][B]
+    double* hbuf = sv + 2 * (SK_TJ + 1) * (SK_TI + 1) * B;                             // [2][x halo C*TJ*B | y halo C*TI*B]
+    constexpr int HBUF_DOUBLES = SK_C * (SK_TI + SK_TJ) * B;
+    uint64_t* full = reinterpret_cast<uint64_t*>(hbuf + 2 * HBUF_DOUBLES);             // [S] data landed
+    uint64_t* empty = full + S;                                                        // [S] slot released by the compute threads
+    uint64_t* ready = empty + S;                                                       // [2] halo of a chunk staged by the sync warp
+    uint64_t* done = ready + 2;                                                        // [2] chunk finished by the compute threads
     __shared__ int s_tile;
 
     const int t = threadIdx.x;
@@ -228,54 +275,105 @@ __global__ void __launch_bounds__(SK_THREADS, MINB) ilu_sweep_kernel(SkewGrid g,
     if (t == 0) {
         const unsigned long long ticket = atomicAdd(ticket_ctr, 1ull) - ticket_base;
         s_tile = order[(int)ticket];
-        for (int q = 0; q < S; ++q) mbar_init(&mbar[q], 1);
+        for (int q = 0; q < S; ++q) { mbar_init(&full[q], 1); mbar_init(&empty[q], 1); }
+        for (int q = 0; q < 2; ++q) { mbar_init(&ready[q], 1); mbar_init(&done[q], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     const int tile = s_tile;
     const int ti = tile % g.ntx, tj = tile / g.ntx;
     const int NS = g.NS;
-    const double* fac_tile = fac + (size_t)tile * NS * LY::STAGE_DOUBLES;
-    double* x_tile = xsk + (size_t)tile * NS * VEC_DOUBLES;
-    constexpr uint32_t FAC_BYTES = LY::STAGE_DOUBLES * sizeof(double), VEC_BYTES = VEC_DOUBLES * sizeof(double);
-    auto issue = [&](int s) {          // thread 0: fetch the factors and the vector chunk of step s into its ring slot
-        const int q = s % S;
-        double* dst = stages + (size_t)q * STAGE_ALL;
-        const int sl = UPPER ? NS - 1 - s : s;
-        mbar_expect_tx(&mbar[q], FAC_BYTES + VEC_BYTES);
-        bulk_g2s(dst, fac_tile + (size_t)s * LY::STAGE_DOUBLES, FAC_BYTES, &mbar[q]);
-        bulk_g2s(dst + LY::STAGE_DOUBLES, x_tile + (size_t)sl * VEC_DOUBLES, VEC_BYTES, &mbar[q]);
-    };
-    if (t == 0)
-        for (int q = 0; q < S && q < NS; ++q) issue(q);
+    const double* stream_tile = stream + (size_t)tile * NS * LY::STEP_DOUBLES;
+    // results of step s (this sweep's step index) go to "lower step" sl = UPPER ? NS-1-s : s; the LOWER sweep stores them where
+    // the upper sweep will fetch them: upper step NS-1-sl
+    auto out_step_index = [&](int sl) { return UPPER ? sl : NS - 1 - sl; };
+    double* out_tile = out + (size_t)tile * NS * OUT_STEP + OUT_OFF;
+    const int nchunks = (NS + SK_C - 1) / SK_C;
+    constexpr int HSHIFT = SK_TI - 1;       // == SK_TJ - 1
+    static_assert(SK_TI == SK_TJ, "square tiles");
+    const int tix = UPPER ? ti + 1 : ti - 1, tjy = UPPER ? tj + 1 : tj - 1;
+    const bool tilex = tix >= 0 && tix < g.ntx, tiley = tjy >= 0 && tjy < g.nty;
 
-    // actual cell line of this thread and the tiles it depends on
+    if (t >= SK_THREADS + 32) {
+        // ---- sync warp: everything that talks to other tiles, one chunk ahead of the compute threads ----
+        //   prepare(ch): wait until the upstream tiles are far enough, stage their boundary values of chunk ch in shared memory
+        //   publish(ch): once the compute threads finished chunk ch, make their results visible and advance this tile's progress
+        const int lane = t - (SK_THREADS + 32);
+        const unsigned long long* progx = prog + (tilex ? tix + g.ntx * tj : 0);
+        const unsigned long long* progy = prog + (tiley ? ti + g.ntx * tjy : 0);
+        auto upstream_ready = [&](int ch) {       // lane 0 only: one non-blocking look at the upstream tiles' progress words
+            const int s0 = ch * SK_C;
+            if (tilex && ld_acquire(progx) < epoch + (unsigned long long)min(s0 + SK_C + SK_TI - 1, NS)) return false;
+            if (tiley && ld_acquire(progy) < epoch + (unsigned long long)min(s0 + SK_C + SK_TJ - 1, NS)) return false;
+            return true;
+        };
+        auto stage_halo = [&](int ch) {           // all lanes
+            const int s0 = ch * SK_C;
+            double* hb = hbuf + (ch & 1) * HBUF_DOUBLES;
+#pragma unroll
+            for (int m = 0; m < SK_C * (SK_TI + SK_TJ) / 32; ++m) {
+                const int v = lane + 32 * m;
+                // values [0, C*TJ): x halo (step hc, row hl), the rest: y halo (step hc, column hl); hl mirrored for UPPER
+                const bool hx_duty = v < SK_C * SK_TJ;
+                const int hc = hx_duty ? v / SK_TJ : (v - SK_C * SK_TJ) / SK_TI;
+                const int hl = hx_duty ? v % SK_TJ : (v - SK_C * SK_TJ) % SK_TI;
+                // the upstream tile computed the wanted value TI-1 (TJ-1) steps after my step; lane on its far edge
+                const int lane_lo = hx_duty ? (SK_TI - 1) + SK_TI * hl : hl + SK_TI * (SK_TJ - 1);
+                const int hlane = UPPER ? SK_THREADS - 1 - lane_lo : lane_lo;
+                const int htile = hx_duty ? tix + g.ntx * tj : ti + g.ntx * tjy;
+                const int other = hx_duty ? tj * SK_TJ + (UPPER ? SK_TJ - 1 - hl : hl) : ti * SK_TI + (UPPER ? SK_TI - 1 - hl : hl);
+                const bool hvalid = (hx_duty ? tilex : tiley) && other < (hx_duty ? g.ny : g.nx);
+                const int s = s0 + hc;
+                const int kk = s - hl;
+                const bool ok = hvalid && kk >= 0 && kk < g.nz;
+                const int sl = UPPER ? NS - 1 - (s + HSHIFT) : s + HSHIFT;       // lower-step index of the upstream tile's step
+                const double* src = out + ((size_t)(hvalid ? htile : 0) * NS + (size_t)(ok ? out_step_index(sl) : 0)) * OUT_STEP + OUT_OFF +
+                                    (size_t)hlane * B;
+#pragma unroll
+                for (int e = 0; e < B; ++e) hb[v * B + e] = ok ? __ldcg(src + e) : 0.0;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ready[ch & 1]);
+        };
+        // Event loop: publish a chunk as soon as the compute threads are done with it, stage the next chunk's halo as soon as
+        // the upstream tiles allow (at most two chunks ahead of the last published one: the halo buffer is double-buffered).
+        int next_prep = 0, next_pub = 0;
+        while (next_pub < nchunks) {
+            int act = 0;       // bit 0: publish next_pub, bit 1: stage next_prep
+            if (lane == 0) {
+                if (mbar_test(&done[next_pub & 1], (uint32_t)((next_pub >> 1) & 1))) act |= 1;
+                if (next_prep < nchunks && next_prep <= next_pub + 1 && upstream_ready(next_prep)) act |= 2;
+            }
+            act = __shfl_sync(0xffffffffu, act, 0);
+            if (act & 2) { stage_halo(next_prep); ++next_prep; }
+            if (act & 1) {
+                if (lane == 0) st_release(prog + tile, epoch + (unsigned long long)min((next_pub + 1) * SK_C, NS));
+                ++next_pub;
+            }
+            if (!act) __nanosleep(SK_POLL_NS);
+        }
+        return;
+    }
+    if (t >= SK_THREADS) {
+        // ---- producer: one bulk copy per step, as far ahead as the ring allows ----
+        if (t == SK_THREADS) {
+            constexpr uint32_t BYTES = LY::STEP_DOUBLES * sizeof(double);
+            for (int s = 0; s < NS; ++s) {
+                const int q = s % S;
+                if (s >= S) mbar_wait(&empty[q], (uint32_t)(((s / S) - 1) & 1));
+                mbar_expect_tx(&full[q], BYTES);
+                bulk_g2s(stages + (size_t)q * LY::STEP_DOUBLES, stream_tile + (size_t)s * LY::STEP_DOUBLES, BYTES, &full[q]);
+            }
+        }
+        return;
+    }
+
+    // ---- compute threads: actual cell line of this thread ----
     const int i = ti * SK_TI + (UPPER ? SK_TI - 1 - a : a);
     const int j = tj * SK_TJ + (UPPER ? SK_TJ - 1 - b : b);
     const bool line = i < g.nx && j < g.ny;
     const bool depx = UPPER ? (i + 1 < g.nx) : (i > 0);          // a -x (+x) neighbour cell exists
     const bool depy = UPPER ? (j + 1 < g.ny) : (j > 0);
-    const int tix = UPPER ? ti + 1 : ti - 1, tjy = UPPER ? tj + 1 : tj - 1;
-    const bool tilex = tix >= 0 && tix < g.ntx, tiley = tjy >= 0 && tjy < g.nty;
-    const unsigned long long* progx = prog + (tilex ? tix + g.ntx * tj : 0);
-    const unsigned long long* progy = prog + (tiley ? ti + g.ntx * tjy : 0);
-    // halo duty of this thread: threads [0, C*TJ) fetch the x halo, the rest the y halo (one value per chunk)
-    const bool hx_duty = t < SK_C * SK_TJ;
-    const int hc = hx_duty ? t / SK_TJ : (t - SK_C * SK_TJ) / SK_TI;       // step within the chunk
-    const int hl = hx_duty ? t % SK_TJ : (t - SK_C * SK_TJ) % SK_TI;       // b (x halo) or a (y halo), mirrored for UPPER
-    bool hvalid;
-    const double* hsrc;
-    {
-        // the upstream tile computed the wanted value TI-1 (TJ-1) steps after my step; lane on its far edge
-        const int lane_lo = hx_duty ? (SK_TI - 1) + SK_TI * hl : hl + SK_TI * (SK_TJ - 1);
-        const int lane = UPPER ? SK_THREADS - 1 - lane_lo : lane_lo;
-        const int htile = hx_duty ? tix + g.ntx * tj : ti + g.ntx * tjy;
-        const int other = hx_duty ? tj * SK_TJ + (UPPER ? SK_TJ - 1 - hl : hl) : ti * SK_TI + (UPPER ? SK_TI - 1 - hl : hl);
-        hvalid = (hx_duty ? tilex : tiley) && other < (hx_duty ? g.ny : g.nx);
-        hsrc = xsk + ((size_t)(hvalid ? htile : 0) * NS * SK_THREADS + lane) * B;
-    }
-    constexpr int HSHIFT = SK_TI - 1;       // == SK_TJ - 1
-    static_assert(SK_TI == SK_TJ, "square tiles");
 
     double vprev[B];
 #pragma unroll
@@ -288,30 +386,13 @@ __global__ void __launch_bounds__(SK_THREADS, MINB) ilu_sweep_kernel(SkewGrid g,
     }
 #define SK_STAMP(slot) do { if (tr && s0 / SK_C < 64) tr[(s0 / SK_C) * 24 + (slot)] = clock64(); } while (0)
     for (int s0 = 0; s0 < NS; s0 += SK_C) {
-        // ---- chunk head: wait for the upstream tiles, fetch their boundary values of this chunk ----
+        // ---- chunk head: the sync warp has staged the upstream tiles' boundary values of this chunk ----
+        const int ch = s0 / SK_C;
         SK_STAMP(0);
-        if (t == 0) {
-            if (tilex) {
-                const unsigned long long need = epoch + (unsigned long long)min(s0 + SK_C + SK_TI - 1, NS);
-                while (ld_acquire(progx) < need) { }
-            }
-            if (tiley) {
-                const unsigned long long need = epoch + (unsigned long long)min(s0 + SK_C + SK_TJ - 1, NS);
-                while (ld_acquire(progy) < need) { }
-            }
-        }
-        __syncthreads();
+        mbar_wait(&ready[ch & 1], (uint32_t)((ch >> 1) & 1));
         SK_STAMP(1);
-        {
-            const int s = s0 + hc;
-            const int kk = s - hl;
-            const bool ok = hvalid && kk >= 0 && kk < g.nz;
-            const int sl = UPPER ? NS - 1 - (s + HSHIFT) : s + HSHIFT;
-            double* dst = (hx_duty ? hx + (hc * SK_TJ + hl) * B : hy + (hc * SK_TI + hl) * B);
-#pragma unroll
-            for (int e = 0; e < B; ++e) dst[e] = ok ? __ldcg(hsrc + (size_t)sl * VEC_DOUBLES + e) : 0.0;
-        }
-        __syncthreads();
+        const double* hx = hbuf + (ch & 1) * HBUF_DOUBLES;
+        const double* hy = hx + SK_C * SK_TJ * B;
         SK_STAMP(2);
 
 #pragma unroll
@@ -319,9 +400,9 @@ __global__ void __launch_bounds__(SK_THREADS, MINB) ilu_sweep_kernel(SkewGrid g,
             const int s = s0 + c;
             if (s < NS) {       // uniform
                 const int stage = s % S;
-                mbar_wait(&mbar[stage], (uint32_t)((s / S) & 1));
+                mbar_wait(&full[stage], (uint32_t)((s / S) & 1));
                 SK_STAMP(3 + 2 * c);
-                const double* f = stages + (size_t)stage * STAGE_ALL;
+                const double* f = stages + (size_t)stage * LY::STEP_DOUBLES;
                 const int kk = s - a - b;
                 const bool active = line && kk >= 0 && kk < g.nz;
                 const int rb = (s + 1) & 1, wb = s & 1;       // buffer written at step s-1 / written now
@@ -404,15 +485,15 @@ __global__ void __launch_bounds__(SK_THREADS, MINB) ilu_sweep_kernel(SkewGrid g,
 #pragma unroll
                     for (int e = 0; e < B; ++e) { vprev[e] = r[e]; svw[e] = r[e]; }
                     const int sl = UPPER ? NS - 1 - s : s;
-                    double* out = x_tile + ((size_t)sl * SK_THREADS + tl) * B;
-                    if (B == 2) __stcg(reinterpret_cast<double2*>(out), make_double2(r[0], r[B - 1]));
-                    else __stcg(out, r[0]);
+                    double* dstp = out_tile + (size_t)out_step_index(sl) * OUT_STEP + (size_t)tl * B;
+                    if (B == 2) __stcg(reinterpret_cast<double2*>(dstp), make_double2(r[0], r[B - 1]));
+                    else __stcg(dstp, r[0]);
                 }
-                __syncthreads();
+                compute_barrier();
                 SK_STAMP(4 + 2 * c);
                 if (t == 0) {
-                    if (s + S < NS) issue(s + S);
-                    if (c == SK_C - 1 || s == NS - 1) st_release(prog + tile, epoch + (unsigned long long)(s + 1));
+                    mbar_arrive(&empty[stage]);
+                    if (c == SK_C - 1 || s == NS - 1) mbar_arrive(&done[ch & 1]);
                 }
             }
         }
@@ -431,45 +512,26 @@ struct SkewState {
     int *order_lo = nullptr, *order_up = nullptr;
     unsigned long long* ctl = nullptr;       // [0],[1]: tickets lower/upper; [2 .. 2+ntiles): prog lower; then prog upper
     unsigned long long seq_lo = 0, seq_up = 0;
-    int deep = 0;                          // 1: one CTA per SM with a deep TMA ring, 0: two CTAs per SM
     long long* trace = nullptr;            // 2 kernels x 2 tiles x 64 chunks x 24 stamps (DMX_SK_TRACE=1)
 };
 
-template <int B, bool UPPER, int S>
+template <int B, bool UPPER>
 static size_t sweep_smem()
 {
     using LY = SkewLayout<B, UPPER>;
-    return ((size_t)S * (LY::STAGE_DOUBLES + SK_THREADS * B) + 2 * (SK_TJ + 1) * (SK_TI + 1) * B + SK_C * (SK_TI + SK_TJ) * B) * sizeof(double) +
-           S * sizeof(uint64_t);
+    return ((size_t)LY::S * LY::STEP_DOUBLES + 2 * (SK_TJ + 1) * (SK_TI + 1) * B + 2 * SK_C * (SK_TI + SK_TJ) * B) * sizeof(double) +
+           (2 * LY::S + 4) * sizeof(uint64_t);
 }
 
-// ring depth per variant: {two CTAs per SM, one CTA per SM}
-template <int B, bool UPPER> struct Depth;
-template <> struct Depth<2, false> { static constexpr int S2 = 3, S1 = 7; };
-template <> struct Depth<2, true> { static constexpr int S2 = 2, S1 = 5; };
-template <> struct Depth<1, false> { static constexpr int S2 = 8, S1 = 16; };
-template <> struct Depth<1, true> { static constexpr int S2 = 8, S1 = 16; };
-
 template <int B, bool UPPER>
-static int sweep_launch(dmx_ctx* ctx, SkewState* st, const double* fac, const int* order, unsigned long long* tick, unsigned long long base,
-                        unsigned long long* prog, unsigned long long epoch, long long* trace)
+static int sweep_launch(dmx_ctx* ctx, SkewState* st, const double* stream, double* out, const int* order, unsigned long long* tick,
+                        unsigned long long base, unsigned long long* prog, unsigned long long epoch, long long* trace)
 {
     const SkewGrid& g = st->g;
-    if (st->deep) {
-        constexpr int S = Depth<B, UPPER>::S1;
-        auto kern = ilu_sweep_kernel<B, UPPER, S, 1>;
-        const size_t smem = sweep_smem<B, UPPER, S>();
-        static bool attr = false;
-        if (!attr) { DMX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
-        kern<<<g.ntiles, SK_THREADS, smem, ctx->stream>>>(g, fac, st->xsk, order, tick, base, prog, epoch, trace);
-    } else {
-        constexpr int S = Depth<B, UPPER>::S2;
-        auto kern = ilu_sweep_kernel<B, UPPER, S, 2>;
-        const size_t smem = sweep_smem<B, UPPER, S>();
-        static bool attr = false;
-        if (!attr) { DMX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
-        kern<<<g.ntiles, SK_THREADS, smem, ctx->stream>>>(g, fac, st->xsk, order, tick, base, prog, epoch, trace);
-    }
+    auto kern = ilu_sweep_kernel<B, UPPER>;
+    const size_t smem = sweep_smem<B, UPPER>();
+    DMX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<g.ntiles, SK_THREADS + 64, smem, ctx->stream>>>(g, stream, out, order, tick, base, prog, epoch, trace);
     DMX_CHECK_LAUNCH();
     return 0;
 }
@@ -506,8 +568,11 @@ int sk_setup(dmx_ctx* ctx)
     st->b = ctx->b;
     const int BB = ctx->b * ctx->b;
     const size_t slots = (size_t)g.ntiles * g.NS * SK_THREADS;
-    DMX_CUDA(cudaMalloc((void**)&st->Lsk, slots * 3 * BB * sizeof(double)));
-    DMX_CUDA(cudaMalloc((void**)&st->Usk, slots * 4 * BB * sizeof(double)));
+    // streams [factors | vector] per step: the vector slots of Lsk hold the right-hand side, those of Usk the lower sweep's result
+    DMX_CUDA(cudaMalloc((void**)&st->Lsk, slots * (3 * BB + ctx->b) * sizeof(double)));
+    DMX_CUDA(cudaMalloc((void**)&st->Usk, slots * (4 * BB + ctx->b) * sizeof(double)));
+    DMX_CUDA(cudaMemsetAsync(st->Lsk, 0, slots * (3 * BB + ctx->b) * sizeof(double), ctx->stream));
+    DMX_CUDA(cudaMemsetAsync(st->Usk, 0, slots * (4 * BB + ctx->b) * sizeof(double), ctx->stream));
     DMX_CUDA(cudaMalloc((void**)&st->xsk, slots * ctx->b * sizeof(double)));
     std::vector<int> lo(g.ntiles), up(g.ntiles);
     for (int q = 0; q < g.ntiles; ++q) lo[q] = up[q] = q;
@@ -526,9 +591,6 @@ int sk_setup(dmx_ctx* ctx)
             DMX_CUDA(cudaMalloc((void**)&st->trace, 2 * 2 * 64 * 24 * sizeof(long long)));
             DMX_CUDA(cudaMemset(st->trace, 0, 2 * 2 * 64 * 24 * sizeof(long long)));
         }
-        // default: one CTA per SM with the deep ring (measured faster at 256^3 and 512^2 x 66); DMX_SK_DEEP=0 for A/B runs
-        const char* deep = getenv("DMX_SK_DEEP");
-        st->deep = deep ? (deep[0] == '1') : 1;
     }
     return 0;
 }
@@ -557,10 +619,10 @@ static int sk_apply_t(dmx_ctx* ctx, SkewState* st, const double* d, double* v)
     const unsigned long long base_up = st->seq_up * (unsigned long long)g.ntiles, ep_up = (st->seq_up + 1) * SK_EPOCH;
     st->seq_lo++;
     st->seq_up++;
-    vec_skew_kernel<B><<<(unsigned)((size_t)g.ntiles * g.NS), SK_THREADS, 0, ctx->stream>>>(g, d, st->xsk);
+    vec_skew_kernel<B><<<(unsigned)((size_t)g.ntiles * g.NS), SK_THREADS, 0, ctx->stream>>>(g, d, st->Lsk);
     DMX_CHECK_LAUNCH();
-    if (int rc = sweep_launch<B, false>(ctx, st, st->Lsk, st->order_lo, tick_lo, base_lo, prog_lo, ep_lo, st->trace)) return rc;
-    if (int rc = sweep_launch<B, true>(ctx, st, st->Usk, st->order_up, tick_up, base_up, prog_up, ep_up,
+    if (int rc = sweep_launch<B, false>(ctx, st, st->Lsk, st->Usk, st->order_lo, tick_lo, base_lo, prog_lo, ep_lo, st->trace)) return rc;
+    if (int rc = sweep_launch<B, true>(ctx, st, st->Usk, st->xsk, st->order_up, tick_up, base_up, prog_up, ep_up,
                                        st->trace ? st->trace + 2 * 64 * 24 : nullptr))
         return rc;
     vec_unskew_kernel<B><<<(unsigned)((ctx->n + 255) / 256), 256, 0, ctx->stream>>>(g, st->xsk, v);

@@ -22,6 +22,8 @@ for s in $STEPS; do
     asm)   timeout 900 python -m pytest tests/test_gpu_assembly.py -m gpu -x -q > $OUT/asm_tests.log 2>&1; tail -3 $OUT/asm_tests.log
            timeout 600 python scripts/ilu_probe.py 256 5 > $OUT/probe_asm.log 2>&1; tail -5 $OUT/probe_asm.log;;
     asmfull) timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"assemble_tile" -c 1 -f -o $OUT/prof_asm python scripts/profile_step.py 256 1 > $OUT/asmfull.log 2>&1; tail -2 $OUT/asmfull.log;;
+    lin)   timeout 300 python -m pytest tests/test_gpu_linear.py tests/test_gpu_newton.py -m gpu -x -q > $OUT/lin_tests.log 2>&1; tail -3 $OUT/lin_tests.log
+           timeout 600 python scripts/ilu_probe.py 256 10 > $OUT/probe_ilu.log 2>&1; tail -5 $OUT/probe_ilu.log;;
     smoke) timeout 300 python __graft_entry__.py smoke > $OUT/smoke.log 2>&1; tail -3 $OUT/smoke.log;;
   esac
 done
