@@ -31,6 +31,7 @@ EXPORTS = [
     "dmx_ilu0_factor", "dmx_ilu0_apply", "dmx_ilu0_download", "dmx_dot", "dmx_halo_exchange", "dmx_time_kernel",
     "dmx_kernel_launch_count", "dmx_synchronize", "dmx_profile", "dmx_profile_read",
     "dmx_newton_step_host", "dmx_timer_start", "dmx_timer_stop", "dmx_debug_sweep_trace",
+    "dmx_volume_flux", "dmx_set_volume_flux", "dmx_set_tracer",
 ]
 K_ASSEMBLY, K_SPMV, K_ILU_APPLY, K_ILU_FACTOR, K_VOLVARS, K_BLAS1, K_HALO, K_JACOBI = range(8)
 
@@ -95,6 +96,9 @@ def load_library():
     L.dmx_set_fluids.argtypes = [vp, _dp, _dp]
     L.dmx_set_fluid_table.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_double, _dp, _dp, _dp, _dp, C.c_double]
     L.dmx_side_faces.argtypes = [vp, C.c_int]
+    L.dmx_volume_flux.argtypes = [vp, _dp]
+    L.dmx_set_volume_flux.argtypes = [vp, _dp]
+    L.dmx_set_tracer.argtypes = [vp, C.c_int]
     L.dmx_set_boundary.argtypes = [vp, C.c_int, _ip, _dp]
     L.dmx_vec_upload.argtypes = [vp, C.c_int, C.c_void_p]
     L.dmx_vec_download.argtypes = [vp, C.c_int, C.c_void_p]
@@ -245,6 +249,11 @@ class Engine:
             self._check(L.dmx_set_boundary(self.h, side, tl, vl))
         if spec.source is not None:
             self._check(L.dmx_set_source(self.h, self.localize_cells(spec.source)))
+        if getattr(spec, "volume_flux", None) is not None:
+            if self.nranks != 1:
+                raise DmxError("tracer transport: single-GPU only in this round")
+            self._check(L.dmx_set_volume_flux(self.h, np.ascontiguousarray(spec.volume_flux, dtype=np.float64).reshape(-1)))
+            self._check(L.dmx_set_tracer(self.h, int(spec.implicit)))
 
     def localize_cells(self, a):
         """Cut the local slab (incl. overlap) out of a global per-cell array (x fastest)."""
@@ -282,6 +291,13 @@ class Engine:
         self._check(self.L.dmx_bcrs_pattern(self.h, n, b, np.ascontiguousarray(rowptr, dtype=np.int32),
                                             np.ascontiguousarray(colidx, dtype=np.int32)))
         self.n, self.b, self.nnzb = n, b, int(rowptr[n])
+
+    def volume_flux(self, pressure):
+        """examples/1ptracer/main.cc:162-199 on the device: volume fluxes [n, 2*dim] of this 1p problem from `pressure`"""
+        self.upload(VEC_CUR, pressure)
+        out = np.zeros((self.n, 2 * self.spec.dim))
+        self._check(self.L.dmx_volume_flux(self.h, out.reshape(-1)))
+        return out
 
     def set_dt(self, dt):
         self.opt.dt = dt
@@ -457,6 +473,29 @@ class Engine:
 
     def synchronize(self):
         self._check(self.L.dmx_synchronize(self.h))
+
+    def run_instationary(self, u0, loop, **newton_kw):
+        """Instationary run driven by a dumux_b200.timeloop.TimeLoop / CheckPointTimeLoop (e.g. the periodic check points of
+        test/porousmediumflow/1p/compressible/instationary/main.cc:118-150).  State stays on the device between steps."""
+        from . import timeloop
+        eng = self
+
+        class _Stepper:
+            def solve(self, dt):
+                eng.set_dt(dt)
+                st, rep = eng.newton_device(**newton_kw)
+                return st == 0, rep.newton_iterations
+
+            def reset(self):
+                eng.reset_timestep()
+
+            def advance(self):
+                eng.advance_timestep()
+
+        self.upload(VEC_CUR, u0)
+        self.upload(VEC_PREV, u0)
+        its, dts = timeloop.run_instationary(_Stepper(), loop)
+        return self.download(VEC_CUR), its, dts
 
     def run_timeloop(self, u0, t_end, dt_initial, max_dt=1e300, **newton_kw):
         """Instationary run as in test/porousmediumflow/2p/incompressible/main.cc:126-163: plain TimeLoop

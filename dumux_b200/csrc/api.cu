@@ -109,7 +109,7 @@ int setup_geometry(dmx_ctx* ctx)
 
 int finish_grid(dmx_ctx* ctx, int model, int dim, const int* cells, const std::vector<double> (&gx)[3])
 {
-    if (model != DMX_MODEL_1P && model != DMX_MODEL_2P) return fail(ctx, DMX_ERR_USAGE, "unknown model");
+    if (model != DMX_MODEL_1P && model != DMX_MODEL_2P && model != DMX_MODEL_TRACER) return fail(ctx, DMX_ERR_USAGE, "unknown model");
     if (dim < 1 || dim > 3) return fail(ctx, DMX_ERR_USAGE, "dim must be 1..3");
     DMX_CUDA(cudaSetDevice(ctx->device));
     ctx->model = model;
@@ -256,7 +256,7 @@ int dmx_destroy(dmx_ctx* ctx)
     if (ctx->nccl_comm) nccl_destroy(ctx);
     void* ptrs[] = {ctx->d_geom, ctx->d_K, ctx->d_phi, ctx->d_q, ctx->d_region, ctx->d_tij[0], ctx->d_tij[1], ctx->d_tij[2], ctx->d_laws,
                     ctx->d_tab_buf, ctx->d_rowptr, ctx->d_colidx, ctx->d_diag, ctx->d_J, ctx->d_ilu, ctx->d_rt, ctx->d_p, ctx->d_v, ctx->d_t,
-                    ctx->d_y, ctx->d_dinv, ctx->d_lrows, ctx->d_urows, ctx->d_lptr, ctx->d_uptr, ctx->d_barrier, ctx->d_partials,
+                    ctx->d_y, ctx->d_dinv, ctx->d_vf, ctx->d_lrows, ctx->d_urows, ctx->d_lptr, ctx->d_uptr, ctx->d_barrier, ctx->d_partials,
                     ctx->d_scalars, ctx->d_flag, ctx->d_owner, ctx->d_send_lo, ctx->d_send_hi, ctx->d_recv_lo, ctx->d_recv_hi};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int v = 0; v < DMX_NUM_VECS; ++v) if (ctx->d_vec[v]) cudaFree(ctx->d_vec[v]);
@@ -518,6 +518,38 @@ int dmx_profile_read(dmx_ctx* ctx, int kclass, double* ms_total, long long* unit
 }
 
 // ---- hot path ----
+int dmx_volume_flux(dmx_ctx* ctx, double* out)
+{
+    if (!ctx->has_grid || ctx->model != DMX_MODEL_1P) return fail(ctx, DMX_ERR_USAGE, "volume_flux: needs a 1p ctx with a grid");
+    DMX_CUDA(cudaSetDevice(ctx->device));
+    const size_t len = (size_t)ctx->n * 2 * ctx->dim;
+    double* d_out = nullptr;
+    DMX_CUDA(cudaMalloc((void**)&d_out, len * sizeof(double)));
+    int rc = launch_volume_flux(ctx, d_out);
+    if (!rc) {
+        cudaError_t e = cudaMemcpyAsync(out, d_out, len * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = fail(ctx, DMX_ERR_CUDA, cudaGetErrorString(e));
+    }
+    cudaFree(d_out);
+    return rc;
+}
+int dmx_set_volume_flux(dmx_ctx* ctx, const double* vf)
+{
+    if (!ctx->has_grid || ctx->model != DMX_MODEL_TRACER) return fail(ctx, DMX_ERR_USAGE, "set_volume_flux: needs a tracer ctx with a grid");
+    DMX_CUDA(cudaSetDevice(ctx->device));
+    const size_t len = (size_t)ctx->n * 2 * ctx->dim;
+    if (!ctx->d_vf) DMX_CUDA(cudaMalloc((void**)&ctx->d_vf, len * sizeof(double)));
+    DMX_CUDA(cudaMemcpyAsync(ctx->d_vf, vf, len * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    DMX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+int dmx_set_tracer(dmx_ctx* ctx, int implicit)
+{
+    if (ctx->model != DMX_MODEL_TRACER) return fail(ctx, DMX_ERR_USAGE, "set_tracer: not a tracer ctx");
+    ctx->tracer_implicit = implicit ? 1 : 0;
+    return 0;
+}
 int dmx_assemble(dmx_ctx* ctx, int with_jacobian)
 {
     if (!ctx->has_grid) return fail(ctx, DMX_ERR_USAGE, "assemble: no grid");

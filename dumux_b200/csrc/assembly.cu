@@ -643,6 +643,199 @@ __global__ void __launch_bounds__(AT_THREADS, (ND == 1) ? 2 : 1) assemble_tile_k
     }
 }
 
+// ================================================================================================
+// Tracer transport on a frozen velocity field (BASELINE config 5, examples/1ptracer)
+// ================================================================================================
+// Volume fluxes over all scvfs from the 1p pressure field in CUR: examples/1ptracer/main.cc:162-199
+// (fluxVars.advectiveFlux(0, upwindTerm = mobility), flux/cctpfa/darcyslaw.hh:154-213); Neumann faces stay 0.
+template <bool TABLE, int DIM>
+__global__ void __launch_bounds__(256) volume_flux_kernel(const AsmParams P, double* __restrict__ out)
+{
+    const size_t I = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (I >= (size_t)P.n) return;
+    const int nx = P.nc[0], ny = P.nc[1];
+    const int ci[3] = {(int)(I % nx), (int)((I / nx) % ny), (int)(I / ((size_t)nx * ny))};
+    const size_t stride[3] = {1, (size_t)nx, (size_t)nx * ny};
+    const double w = P.upwind_weight, extr = P.extrusion;
+    auto fluid = [&](double p, double* rho, double* mob) {
+        double mu = P.mu[0];
+        *rho = P.rho[0];
+        if constexpr (TABLE) table_interp2(P.table, p, rho, &mu);
+        *mob = 1.0 / mu;                                            // 1p/volumevariables.hh:178
+    };
+    const double pI = P.cur[I], KI = P.K[I];
+    double rhoI, mobI;
+    fluid(pI, &rhoI, &mobI);
+#pragma unroll
+    for (int s = 0; s < 2 * DIM; ++s) {
+        const int a = s >> 1;
+        const bool hi = (s & 1);
+        double area = 1.0;
+        for (int d = 0; d < DIM; ++d)
+            if (d != a) area *= P.width[d][ci[d]];
+        const bool grav = P.enable_gravity && (a == DIM - 1);
+        const double ng = hi ? -P.gravity : P.gravity;
+        const double alphaI = KI * ng * extr;
+        double result = 0.0;
+        const bool exists = hi ? (ci[a] + 1 < P.nc[a]) : (ci[a] > 0);
+        if (exists) {
+            const size_t J = hi ? I + stride[a] : I - stride[a];
+            const int cj = hi ? ci[a] + 1 : ci[a] - 1;
+            const double pJ = P.cur[J], KJ = P.K[J];
+            double rhoJ, mobJ;
+            fluid(pJ, &rhoJ, &mobJ);
+            const double tij = hi ? P.tij[a][I] : P.tij[a][J];
+            double f = tij * (pI - pJ);
+            if (grav) {
+                const double rho = (rhoI + rhoJ) * 0.5;
+                f = f + rho * area * alphaI;
+                const double tJ = KJ * extr * (hi ? P.gf_lo[a][cj] : P.gf_hi[a][cj]);
+                const double alphaJ = KJ * ng * extr;
+                f -= rho * tij / tJ * (alphaI - alphaJ);
+            }
+            double mult;
+            if (signbit(f)) mult = w * mobJ + (1.0 - w) * mobI;
+            else mult = w * mobI + (1.0 - w) * mobJ;
+            result = f * mult;
+        } else {
+            int fidx;
+            if (a == 0) fidx = ci[1] + ny * ci[2];
+            else if (a == 1) fidx = ci[0] + nx * ci[2];
+            else fidx = ci[0] + nx * ci[1];
+            const int type = P.bc_type[s] ? P.bc_type[s][fidx] : DMX_BC_NEUMANN;
+            if (type == DMX_BC_DIRICHLET) {
+                const double pD = P.bc_p[s][(size_t)fidx * 2];
+                double rhoD, mobD;
+                fluid(pD, &rhoD, &mobD);
+                const double ti = KI * extr * (hi ? P.gf_hi[a][ci[a]] : P.gf_lo[a][ci[a]]);
+                const double tij = area * ti;
+                double f = tij * (pI - pD);
+                if (grav) f = f + rhoD * area * alphaI;
+                double mult;
+                if (signbit(f)) mult = w * mobD + (1.0 - w) * mobI;
+                else mult = w * mobI + (1.0 - w) * mobD;
+                result = f * mult;
+            }
+        }
+        out[I * (2 * DIM) + s] = result;
+    }
+}
+
+// TracerLocalResidual (porousmediumflow/tracer/localresidual.hh:74-107 storage, :119-186 advective flux over
+// StationaryVelocityField, flux/stationaryvelocityfield.hh:55; mass fractions, one component, D = 0) assembled as
+//   explicit: CCLocalAssembler<analytic, implicit=false> (assembly/cclocalassembler.hh:607-675): fluxes at PREV, the
+//             Jacobian is the storage derivative on the diagonal (localresidual.hh:193-214)
+//   implicit: CCLocalAssembler<analytic, implicit=true> (:490-600): fluxes at CUR, addFluxDerivatives (:237-296); the
+//             outflow Neumann term contributes volumeFlux*rho*extrusion to the diagonal (the reference has no analytic
+//             Robin derivative, fvlocalresidual.hh:455-464).
+// One thread per row; every entry of the row is written (zeros where the explicit scheme has none).
+template <int DIM, bool JAC>
+__global__ void __launch_bounds__(256) tracer_assemble_kernel(const AsmParams P)
+{
+    const size_t I = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (I >= (size_t)P.n) return;
+    const int nx = P.nc[0], ny = P.nc[1];
+    const int ci[3] = {(int)(I % nx), (int)((I / nx) % ny), (int)(I / ((size_t)nx * ny))};
+    const size_t stride[3] = {1, (size_t)nx, (size_t)nx * ny};
+    const double w = P.upwind_weight, extr = P.extrusion, rho = P.rho[0];
+    const bool implicit = P.tracer_implicit != 0;
+    const double* __restrict__ X = implicit ? P.cur : P.prev;
+    const double XI = X[I];
+
+    double vol = 1.0;
+    for (int a = 0; a < DIM; ++a) vol *= P.width[a][ci[a]];
+    double res = 0.0;
+    {
+        double source = P.q ? P.q[I] : 0.0;
+        source *= vol * extr;
+        res -= source;
+    }
+    const double phiInert = 1.0 - P.phi[I];
+    const double porosity = 1.0 - phiInert;
+    const double saturation = fmax(1e-8, 1.0);
+
+    bool ex[6] = {false, false, false, false, false, false};
+#pragma unroll
+    for (int s = 0; s < 2 * DIM; ++s) ex[s] = (s & 1) ? (ci[s >> 1] + 1 < P.nc[s >> 1]) : (ci[s >> 1] > 0);
+    int pos[6], posDiag = 0;
+    if constexpr (JAC) {
+        const int rowStart = P.rowptr[I];
+        posDiag = rowStart + (ex[4] ? 1 : 0) + (ex[2] ? 1 : 0) + (ex[0] ? 1 : 0);
+        pos[4] = rowStart;
+        pos[2] = rowStart + (ex[4] ? 1 : 0);
+        pos[0] = pos[2] + (ex[2] ? 1 : 0);
+        pos[1] = posDiag + 1;
+        pos[3] = pos[1] + (ex[1] ? 1 : 0);
+        pos[5] = pos[3] + (ex[3] ? 1 : 0);
+    }
+    double diag = 0.0;
+    if constexpr (JAC) {
+        const double d_storage = vol * porosity * rho * saturation / P.dt;
+        diag += d_storage;
+    }
+#pragma unroll
+    for (int s = 0; s < 2 * DIM; ++s) {
+        const int a = s >> 1;
+        const bool hi = (s & 1);
+        const double vflux = P.vf[I * (2 * DIM) + s];
+        if (ex[s]) {
+            const size_t J = hi ? I + stride[a] : I - stride[a];
+            const double upIn = rho * XI, upOut = rho * X[J];
+            double mult;
+            if (signbit(vflux)) mult = w * upOut + (1.0 - w) * upIn;
+            else mult = w * upIn + (1.0 - w) * upOut;
+            double flux = 0.0;
+            flux += vflux * mult;
+            flux += 0.0;       // diffusive flux, D = 0
+            res += flux;
+            if constexpr (JAC) {
+                double offdiag = 0.0;
+                if (implicit) {
+                    const double insideWeight = signbit(vflux) ? (1.0 - w) : w;
+                    const double outsideWeight = 1.0 - insideWeight;
+                    diag += vflux * rho * insideWeight;
+                    offdiag += vflux * rho * outsideWeight;
+                }
+                P.jac[pos[s]] = offdiag;
+            }
+        } else {
+            int fidx;
+            if (a == 0) fidx = ci[1] + ny * ci[2];
+            else if (a == 1) fidx = ci[0] + nx * ci[2];
+            else fidx = ci[0] + nx * ci[1];
+            const int type = P.bc_type[s] ? P.bc_type[s][fidx] : DMX_BC_NEUMANN;
+            if (type == DMX_BC_NONE) continue;
+            double area = 1.0;
+            for (int d = 0; d < DIM; ++d)
+                if (d != a) area *= P.width[d][ci[d]];
+            double nf;
+            if (type == DMX_BC_OUTFLOW) {
+                nf = vflux * XI * rho / area;
+                if (JAC && implicit) diag += vflux * rho * extr;
+            } else
+                nf = P.bc_neumann[s] ? P.bc_neumann[s][fidx] : 0.0;
+            nf *= area * extr;
+            res += nf;
+        }
+    }
+    {
+        // fvlocalresidual.hh:274-304
+        double prevStorage = porosity * rho * P.prev[I] * saturation;
+        double storage = porosity * rho * P.cur[I] * saturation;
+        prevStorage *= extr;
+        storage *= extr;
+        storage -= prevStorage;
+        storage *= vol;
+        storage /= P.dt;
+        double st = 0.0;
+        st += storage;
+        res += st;
+    }
+    P.residual[I] = res;
+    if (!(fabs(res) <= DBL_MAX)) atomicOr(P.flag_nonfinite, 1);
+    if constexpr (JAC) P.jac[posDiag] = 0.0 + diag;
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -681,6 +874,7 @@ static void fill_params(dmx_ctx* ctx, AsmParams& P)
         P.bc_p[s] = ctx->d_bc_p[s]; P.bc_up[s] = ctx->d_bc_up[s]; P.bc_rho[s] = ctx->d_bc_rho[s];
     }
     P.cur = ctx->d_vec[DMX_VEC_CUR]; P.prev = ctx->d_vec[DMX_VEC_PREV];
+    P.vf = ctx->d_vf; P.tracer_implicit = ctx->tracer_implicit;
     P.rowptr = ctx->d_rowptr; P.residual = ctx->d_vec[DMX_VEC_RESIDUAL]; P.jac = ctx->d_J;
     P.flag_nonfinite = ctx->d_flag;
 }
@@ -760,6 +954,8 @@ int prepare(dmx_ctx* ctx)
             type = ctx->h_bc_type[s];
             for (int f = 0; f < nf; ++f) {
                 const double* v = &ctx->h_bc_val[s][(size_t)f * ctx->b];
+                if (type[f] == DMX_BC_DIRICHLET && ctx->model == DMX_MODEL_TRACER)
+                    return fail(ctx, DMX_ERR_USAGE, "tracer: Dirichlet boundaries are not supported (use DMX_BC_OUTFLOW / Neumann)");
                 if (type[f] == DMX_BC_DIRICHLET) {
                     double pv[2] = {v[0], ctx->b > 1 ? v[1] : 0.0};
                     dirichlet_state(ctx, side_face_cell(ctx, s, f), pv, &p[(size_t)f * 2], &up[(size_t)f * 2], &rho[(size_t)f * 2]);
@@ -825,9 +1021,40 @@ static int launch_impl(dmx_ctx* ctx, bool with_jac, bool volvars_only)
     AsmParams P;
     fill_params(ctx, P);
     (void)volvars_only;
+    if (ctx->model == DMX_MODEL_TRACER) {
+        if (!ctx->d_vf) return fail(ctx, DMX_ERR_USAGE, "tracer: no volume fluxes set (dmx_set_volume_flux)");
+        if (ctx->opt.stationary) return fail(ctx, DMX_ERR_USAGE, "tracer: instationary only");
+        const unsigned grid = (unsigned)((ctx->n + 255) / 256);
+        ProfScope ps__(ctx, DMX_K_ASSEMBLY);
+#define DMX_TRACER(D)                                                                                         \
+        do {                                                                                                  \
+            if (with_jac) tracer_assemble_kernel<D, true><<<grid, 256, 0, ctx->stream>>>(P);                  \
+            else tracer_assemble_kernel<D, false><<<grid, 256, 0, ctx->stream>>>(P);                          \
+        } while (0)
+        if (ctx->dim == 3) DMX_TRACER(3);
+        else if (ctx->dim == 2) DMX_TRACER(2);
+        else DMX_TRACER(1);
+#undef DMX_TRACER
+        DMX_CHECK_LAUNCH();
+        return 0;
+    }
     if (ctx->model == DMX_MODEL_2P) return launch_tile<DMX_MODEL_2P, false>(ctx, P, with_jac);
     if (ctx->tabulated) return launch_tile<DMX_MODEL_1P, true>(ctx, P, with_jac);
     return launch_tile<DMX_MODEL_1P, false>(ctx, P, with_jac);
+}
+
+int launch_volume_flux(dmx_ctx* ctx, double* d_out)
+{
+    if (int rc = prepare(ctx)) return rc;
+    AsmParams P;
+    fill_params(ctx, P);
+    const unsigned grid = (unsigned)((ctx->n + 255) / 256);
+#define DMX_VF(T, D) volume_flux_kernel<T, D><<<grid, 256, 0, ctx->stream>>>(P, d_out)
+    if (ctx->tabulated) { if (ctx->dim == 3) DMX_VF(true, 3); else if (ctx->dim == 2) DMX_VF(true, 2); else DMX_VF(true, 1); }
+    else { if (ctx->dim == 3) DMX_VF(false, 3); else if (ctx->dim == 2) DMX_VF(false, 2); else DMX_VF(false, 1); }
+#undef DMX_VF
+    DMX_CHECK_LAUNCH();
+    return 0;
 }
 
 int launch_assemble(dmx_ctx* ctx, bool with_jacobian) { return launch_impl(ctx, with_jacobian, false); }

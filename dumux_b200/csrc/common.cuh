@@ -36,6 +36,8 @@ struct AsmParams {
     const int* region;
     const double* q;          // may be null
     const double* tij[3];     // transmissibility of the + face of each cell along axis a
+    const double* vf;         // tracer: frozen volume fluxes [n][2*dim]
+    int tracer_implicit;
     // fluids
     double rho[2], mu[2];
     double rmu[2], rdt;       // correctly rounded 1/mu, 1/dt (host IEEE division) for div_by
@@ -95,6 +97,8 @@ struct dmx_ctx {
     double *d_K = nullptr, *d_phi = nullptr, *d_q = nullptr;
     int* d_region = nullptr;
     double* d_tij[3] = {nullptr, nullptr, nullptr};
+    double* d_vf = nullptr;             // tracer: frozen volume fluxes [n][2*dim]
+    int tracer_implicit = 0;
 
     std::vector<dmx::MaterialLaw> laws;
     dmx::MaterialLaw* d_laws = nullptr;
@@ -215,6 +219,7 @@ inline void prof_drain(dmx_ctx* c)
 int prepare(dmx_ctx* ctx);
 int launch_assemble(dmx_ctx* ctx, bool with_jacobian);
 int launch_volvars_only(dmx_ctx* ctx);
+int launch_volume_flux(dmx_ctx* ctx, double* d_out);
 // implemented in linalg.cu
 int build_level_schedule(dmx_ctx* ctx);
 int launch_spmv(dmx_ctx* ctx, const double* x, double* y);

@@ -15,9 +15,9 @@ from typing import Dict, List, Optional, Tuple
 
 import numpy as np
 
-MODEL_1P, MODEL_2P = 1, 2
+MODEL_1P, MODEL_2P, MODEL_TRACER = 1, 2, 3
 LAW_BC, LAW_VG = 0, 1
-BC_NEUMANN, BC_DIRICHLET, BC_NONE = 0, 1, 2
+BC_NEUMANN, BC_DIRICHLET, BC_NONE, BC_OUTFLOW = 0, 1, 2, 3
 
 
 @dataclasses.dataclass
@@ -63,6 +63,10 @@ class ProblemSpec:
     initial: np.ndarray                 # float64[n, numEq]
     source: Optional[np.ndarray] = None
     fluid_table: Optional[dict] = None  # tabulated liquid (1p compressible)
+    # tracer transport (MODEL_TRACER): frozen volume fluxes [n, 2*dim] (sides -x,+x,-y,+y,-z,+z seen from the cell) and the
+    # time discretisation (False: explicit Euler as in examples/1ptracer/main.cc:236, True: implicit)
+    volume_flux: Optional[np.ndarray] = None
+    implicit: bool = False
     # slab-local spec (multi-GPU set-up without materialising the global arrays): the per-cell / per-face arrays above
     # cover only the layers [slab[0], slab[1]) of the last axis (overlap included); cells/lower/upper stay GLOBAL.
     slab: Optional[Tuple[int, int]] = None
@@ -248,6 +252,48 @@ def onep_incompressible(cells=(10, 10), lower=None, upper=None, numdiff_params=T
 
 
 # ------------------------------------------------------------------------------------------------------
+# C2: test/porousmediumflow/1p/compressible/instationary (params.input, problem.hh:41-108, spatialparams.hh:44-98):
+# tabulated H2O (TabulatedComponent<H2O>::init(273.15, 294.15, 10, 1e4, 1e6, 200)), T = 293.15 K, Dirichlet p = 1e5*(2 - z)
+# at bottom/top, no-flow sides, initial p = 1e5, default FD step.  `lognormal=True` swaps the lens for the log-normal
+# permeability field of examples/1ptracer (BASELINE config 2: "lognormal random permeability").
+# ------------------------------------------------------------------------------------------------------
+_H2O_TABLE = None
+
+
+def onep_compressible(cells=(10, 10), lower=None, upper=None, dt=0.002, lognormal=False, seed=0) -> ProblemSpec:
+    global _H2O_TABLE
+    from . import iapws
+    if _H2O_TABLE is None:
+        _H2O_TABLE = iapws.tabulated_h2o()
+    dim = len(cells)
+    lower = tuple([0.0] * dim) if lower is None else lower
+    upper = tuple([1.0] * dim) if upper is None else upper
+    n = int(np.prod(cells))
+    ctr = cell_centers(cells, lower, upper)
+    lens = _in_box(ctr, [0.2] * dim, [0.8] * dim, 1.5e-7)
+    if lognormal:
+        K = lognormal_permeability(n, 1e-10, seed, lens, 1e-11) if n <= 4_000_000 else \
+            np.where(lens, 1e-11, 1e-10) * fast_lognormal_multiplier(n, 0.5, seed)
+    else:
+        K = np.where(lens, 1e-12, 1e-10)
+    bc_type, bc_values = {}, {}
+    zmax = upper[dim - 1]
+    for side in range(2 * dim):
+        fc = side_face_centers(cells, lower, upper, side)
+        z = fc[:, dim - 1]
+        dirichlet = (z < 1e-6) | (z > zmax - 1e-6)
+        bc_type[side] = np.where(dirichlet, BC_DIRICHLET, BC_NEUMANN).astype(np.int32)
+        vals = np.zeros((fc.shape[0], 1))
+        vals[dirichlet, 0] = 1.0e5 * (2.0 - z[dirichlet])
+        bc_values[side] = vals
+    return ProblemSpec(
+        name="1p_compressible", model=MODEL_1P, dim=dim, cells=tuple(cells), lower=tuple(lower), upper=tuple(upper),
+        K=K, phi=np.full(n, 0.4), region=np.zeros(n, dtype=np.int32), materials=[],
+        rho=(1000.0,), mu=(1e-3,), bc_type=bc_type, bc_values=bc_values,
+        options=Options(stationary=False, dt=dt), initial=np.full((n, 1), 1.0e5), fluid_table=dict(_H2O_TABLE))
+
+
+# ------------------------------------------------------------------------------------------------------
 # 2p lens, the reference test: test/porousmediumflow/2p/incompressible (params.input, problem.hh:50-168,
 # spatialparams.hh:46-140).  2-D: y vertical.  `vertical_axis` = dim-1 always (gravity acts along -e_{dim-1}).
 # ------------------------------------------------------------------------------------------------------
@@ -345,3 +391,31 @@ def onep_tracer_pressure(cells=(50, 50)) -> ProblemSpec:
         K=K, phi=np.full(n, 0.2), region=np.zeros(n, dtype=np.int32), materials=[],
         rho=(1000.0,), mu=(1e-3,), bc_type=bc_type, bc_values=bc_values,
         options=Options(stationary=True, base_eps=0.1, privar_magnitude=(1e5, -1.0)), initial=np.zeros((n, 1)))
+
+
+# ------------------------------------------------------------------------------------------------------
+# C5: tracer transport on the velocity field of the 1p problem above (examples/1ptracer: problem_tracer.hh:60-145,
+# spatialparams_tracer.hh:40-110, properties_tracer.hh:60-91, params.input).  Mass fractions (UseMoles = false), one
+# component, D = 0, porosity 0.2, fluid density 1000; all boundaries Neumann: outflow volumeFlux*X*rho/area at the top,
+# zero elsewhere; initial X = 1e-9 * M_tracer / M_fluid (0.300 / 18.0) below y = 0.1.
+# ------------------------------------------------------------------------------------------------------
+def tracer_transport(cells, volume_flux, dt=10.0, implicit=False) -> ProblemSpec:
+    dim = len(cells)
+    lower, upper = tuple([0.0] * dim), tuple([1.0] * dim)
+    n = int(np.prod(cells))
+    ctr = cell_centers(cells, lower, upper)
+    zmax = upper[dim - 1]
+    bc_type, bc_values = {}, {}
+    for side in range(2 * dim):
+        fc = side_face_centers(cells, lower, upper, side)
+        top = fc[:, dim - 1] > zmax - 1e-6
+        bc_type[side] = np.where(top, BC_OUTFLOW, BC_NEUMANN).astype(np.int32)
+        bc_values[side] = np.zeros((fc.shape[0], 1))
+    init = np.zeros((n, 1))
+    init[ctr[:, dim - 1] < 0.1 + 1e-6, 0] = 1e-9 * 0.300 / 18.0
+    vf = np.ascontiguousarray(volume_flux, dtype=np.float64).reshape(n, 2 * dim)
+    return ProblemSpec(
+        name="tracer", model=MODEL_TRACER, dim=dim, cells=tuple(cells), lower=lower, upper=upper,
+        K=np.ones(n), phi=np.full(n, 0.2), region=np.zeros(n, dtype=np.int32), materials=[],
+        rho=(1000.0,), mu=(1e-3,), bc_type=bc_type, bc_values=bc_values,
+        options=Options(stationary=False, dt=dt, enable_gravity=False), initial=init, volume_flux=vf, implicit=implicit)

@@ -24,9 +24,11 @@ extern "C" {
 
 typedef struct dmx_ctx dmx_ctx;
 
-enum { DMX_MODEL_1P = 1, DMX_MODEL_2P = 2 };
+enum { DMX_MODEL_1P = 1, DMX_MODEL_2P = 2, DMX_MODEL_TRACER = 3 };
 enum { DMX_LAW_BROOKSCOREY = 0, DMX_LAW_VANGENUCHTEN = 1 };
-enum { DMX_BC_NEUMANN = 0, DMX_BC_DIRICHLET = 1, DMX_BC_NONE = 2 };
+/* DMX_BC_OUTFLOW (tracer model only): the solution-dependent Neumann flux volumeFlux * X * rho / area of
+   examples/1ptracer/problem_tracer.hh:92-115 */
+enum { DMX_BC_NEUMANN = 0, DMX_BC_DIRICHLET = 1, DMX_BC_NONE = 2, DMX_BC_OUTFLOW = 3 };
 enum { DMX_PRECOND_ILU0 = 0, DMX_PRECOND_BLOCKJACOBI = 1 };
 enum { DMX_STATUS_OK = 0, DMX_STATUS_NOT_CONVERGED = 1, DMX_STATUS_BREAKDOWN = 2, DMX_STATUS_NONFINITE = 3 };
 /* device-resident vectors of a ctx */
@@ -111,6 +113,16 @@ int  dmx_set_material(dmx_ctx* ctx, int region, int law, const double* params, d
 int  dmx_set_fluids(dmx_ctx* ctx, const double* density, const double* viscosity);
 int  dmx_set_fluid_table(dmx_ctx* ctx, int nT, int nP, double Tmin, double Tmax, const double* pmin, const double* pmax,
                          const double* density, const double* viscosity, double temperature);
+/* ---- tracer transport on a frozen velocity field (DMX_MODEL_TRACER; examples/1ptracer) --------------------- */
+/* 1p ctx: volume fluxes over every face of every cell from the pressure in CUR (main.cc:162-199, upwind term = mobility;
+   Neumann boundary faces stay 0): out[n * 2*dim], sides -x,+x,-y,+y,-z,+z as seen from the cell.  Host buffer. */
+int  dmx_volume_flux(dmx_ctx* ctx, double* out);
+/* tracer ctx: TracerTestSpatialParams::setVolumeFlux (spatialparams_tracer.hh:91-103), same layout.  Host buffer. */
+int  dmx_set_volume_flux(dmx_ctx* ctx, const double* volume_flux);
+/* tracer ctx: FVAssembler<TracerTypeTag, DiffMethod::analytic, implicit> (main.cc:236): 0 explicit Euler, 1 implicit.
+   Fluid density = density[0] of dmx_set_fluids, porosity from dmx_set_cell_fields, dt / extrusion / upwind weight from
+   dmx_options.  dmx_assemble / dmx_newton_step then run TracerLocalResidual (porousmediumflow/tracer/localresidual.hh). */
+int  dmx_set_tracer(dmx_ctx* ctx, int implicit);
 int  dmx_side_faces(const dmx_ctx* ctx, int side);
 int  dmx_set_boundary(dmx_ctx* ctx, int side, const int* type, const double* values);
 

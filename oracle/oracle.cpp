@@ -337,6 +337,7 @@ struct orc_problem {
     std::vector<int> bcType[6];
     std::vector<double> bcVal[6];
     std::vector<int> rowptr, colidx;
+    bool volumeFluxMode = false;               // upwind term = mobility only (examples/1ptracer/main.cc:170)
 
     // ---- grid geometry: YaspGrid equidistant / tensor coordinates, AxisAlignedCubeGeometry [DUNE-ext] ----
     int idx(int i, int j, int k) const { return i + nc[0] * (j + nc[1] * k); }
@@ -482,8 +483,8 @@ struct orc_problem {
             }
             // upwindscheme.hh:43-53, upwind term = density*mobility (immiscible/localresidual.hh:113-114)
             const double w = opt.upwind_weight;
-            const double upIn = in.rho[ph] * in.mob[ph];
-            const double upOut = out.rho[ph] * out.mob[ph];
+            const double upIn = volumeFluxMode ? in.mob[ph] : in.rho[ph] * in.mob[ph];
+            const double upOut = volumeFluxMode ? out.mob[ph] : out.rho[ph] * out.mob[ph];
             double mult;
             if (std::signbit(f)) mult = w * upOut + (1.0 - w) * upIn;
             else mult = w * upIn + (1.0 - w) * upOut;
@@ -1217,6 +1218,141 @@ int orc_run_timeloop(orc_problem* p, double* u, double t_end, double dt_initial,
         dt = std::min(suggested, maxTimeStepSize());
     } while (!finished());
     return step;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Tracer transport on a frozen velocity field (BASELINE config 5, examples/1ptracer).
+// ------------------------------------------------------------------------------------------------------------
+// Volume fluxes over all scvfs from a 1p pressure solution: examples/1ptracer/main.cc:162-199
+// (fluxVars.advectiveFlux(0, upwindTerm = mobility)); Neumann boundary faces are skipped (stay 0).
+// vf[I*2*dim + side]: flux through face `side` of cell I seen from I (each scvf has its own entry in the reference).
+void orc_volume_flux(orc_problem* p, const double* pressure, double* vf)
+{
+    const int dim = p->dim;
+    p->volumeFluxMode = true;
+    for (int I = 0; I < p->n; ++I) {
+        int cI[3];
+        p->ijk(I, cI);
+        VolVars vI;
+        p->updateVolVars(vI, &pressure[I], I);
+        for (int side = 0; side < 2 * dim; ++side) {
+            double out = 0.0;
+            const int J = p->neighbor(cI, side);
+            double f[2] = {0.0, 0.0};
+            if (J >= 0) {
+                int cJ[3];
+                p->ijk(J, cJ);
+                VolVars vJ;
+                p->updateVolVars(vJ, &pressure[J], J);
+                p->computeFlux(f, cI, side, vI, vJ, false, cJ);
+                out = f[0];
+            } else {
+                const int fidx = p->sideFaceIndex(side, cI);
+                const int type = p->bcType[side].empty() ? ORC_BC_NEUMANN : p->bcType[side][fidx];
+                if (type == ORC_BC_DIRICHLET) {
+                    VolVars bv;
+                    double pv[2] = {p->bcVal[side][(size_t)fidx], 0.0};
+                    p->updateVolVars(bv, pv, I);
+                    p->computeFlux(f, cI, side, vI, bv, true, nullptr);
+                    out = f[0];
+                }
+            }
+            vf[(size_t)I * 2 * dim + side] = out;
+        }
+    }
+    p->volumeFluxMode = false;
+}
+
+// TracerLocalResidual (porousmediumflow/tracer/localresidual.hh:74-107 storage, :119-186 advective flux with
+// StationaryVelocityField, flux/stationaryvelocityfield.hh:55; mass fractions, one component, D = 0) assembled by
+//   implicit = 0: CCLocalAssembler<analytic, implicit=false> (assembly/cclocalassembler.hh:607-675): fluxes at prevSol,
+//                 Jacobian = storage derivative on the diagonal (localresidual.hh:193-214)
+//   implicit = 1: CCLocalAssembler<analytic, implicit=true> (:490-600): fluxes at curSol, addFluxDerivatives (:237-296).
+//                 The reference has no analytic derivative for the solution-dependent outflow Neumann term
+//                 (fvlocalresidual.hh:455-464 throws); here it is volumeFlux*rho*extrusion on the diagonal (OUR extension).
+// Boundary faces: ORC_BC_NEUMANN with a fixed flux, ORC_BC_OUTFLOW = volumeFlux*X*rho/area (problem_tracer.hh:92-115).
+void orc_tracer_assemble(orc_problem* p, const double* vf, const double* cur, const double* prev, int implicit, double rho,
+                         double* residual, double* jac)
+{
+    const int dim = p->dim;
+    const double w = p->opt.upwind_weight;
+    const double extr = p->opt.extrusion;
+    const double* X = implicit ? cur : prev;
+    if (jac) std::fill(jac, jac + p->colidx.size(), 0.0);
+    for (int I = 0; I < p->n; ++I) {
+        int cI[3];
+        p->ijk(I, cI);
+        const double vol = p->volume(cI);
+        double res = 0.0;
+        {
+            double source = p->q.empty() ? 0.0 : p->q[I];
+            source *= vol * extr;
+            res -= source;
+        }
+        const double phiInert = 1.0 - p->phi[I];
+        const double porosity = 1.0 - phiInert;
+        const double saturation = std::max(1e-8, 1.0);
+        // position of the diagonal / neighbours in row I
+        auto pos = [&](int col) {
+            for (int k = p->rowptr[I]; k < p->rowptr[I + 1]; ++k)
+                if (p->colidx[k] == col) return k;
+            return -1;
+        };
+        double diag = 0.0;
+        if (jac) {
+            const double d_storage = vol * porosity * rho * saturation / p->opt.dt;
+            diag += d_storage;
+        }
+        for (int side = 0; side < 2 * dim; ++side) {
+            const int a = side / 2;
+            const double vflux = vf[(size_t)I * 2 * dim + side];
+            const int J = p->neighbor(cI, side);
+            if (J >= 0) {
+                const double upIn = rho * X[I], upOut = rho * X[J];
+                double mult;
+                if (std::signbit(vflux)) mult = w * upOut + (1.0 - w) * upIn;
+                else mult = w * upIn + (1.0 - w) * upOut;
+                double flux = 0.0;
+                flux += vflux * mult;
+                flux += 0.0;       // diffusive flux, D = 0 (examples/1ptracer/properties_tracer.hh binaryDiffusionCoefficient)
+                res += flux;
+                if (jac && implicit) {
+                    const double insideWeight = std::signbit(vflux) ? (1.0 - w) : w;
+                    const double outsideWeight = 1.0 - insideWeight;
+                    diag += vflux * rho * insideWeight;
+                    jac[pos(J)] += vflux * rho * outsideWeight;
+                }
+            } else {
+                const int fidx = p->sideFaceIndex(side, cI);
+                const int type = p->bcType[side].empty() ? ORC_BC_NEUMANN : p->bcType[side][fidx];
+                if (type == ORC_BC_NONE) continue;
+                const double area = p->faceArea(a, cI);
+                double nf;
+                if (type == ORC_BC_OUTFLOW) {
+                    nf = vflux * X[I] * rho / area;
+                    if (jac && implicit) diag += vflux * rho * extr;
+                } else
+                    nf = p->bcVal[side].empty() ? 0.0 : p->bcVal[side][fidx];
+                nf *= area * extr;
+                res += nf;
+            }
+        }
+        {
+            // fvlocalresidual.hh:274-304
+            double prevStorage = porosity * rho * prev[I] * saturation;
+            double storage = porosity * rho * cur[I] * saturation;
+            prevStorage *= extr;
+            storage *= extr;
+            storage -= prevStorage;
+            storage *= vol;
+            storage /= p->opt.dt;
+            double st = 0.0;
+            st += storage;
+            res += st;
+        }
+        if (residual) residual[I] = res;
+        if (jac) jac[pos(I)] += diag;
+    }
 }
 
 double orc_law_eval(orc_problem* p, int region, int which, double sw)

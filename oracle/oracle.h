@@ -38,7 +38,7 @@ typedef struct {
 
 enum { ORC_MODEL_1P = 1, ORC_MODEL_2P = 2 };
 enum { ORC_LAW_BROOKSCOREY = 0, ORC_LAW_VANGENUCHTEN = 1 };
-enum { ORC_BC_NEUMANN = 0, ORC_BC_DIRICHLET = 1, ORC_BC_NONE = 2 };
+enum { ORC_BC_NEUMANN = 0, ORC_BC_DIRICHLET = 1, ORC_BC_NONE = 2, ORC_BC_OUTFLOW = 3 };
 /* sides: 0 -x, 1 +x, 2 -y, 3 +y, 4 -z, 5 +z (YaspGrid indexInInside) */
 
 void orc_default_options(orc_options* o);
@@ -101,6 +101,12 @@ int  orc_newton_solve(orc_problem* p, double* u, const double* prev, double lin_
    returns number of time steps; newton_its[] receives the Newton count per step (up to max_steps_out). */
 int  orc_run_timeloop(orc_problem* p, double* u, double t_end, double dt_initial, double max_dt,
                       int* newton_its, double* dts, int max_steps_out);
+
+/* tracer transport on a frozen velocity field (examples/1ptracer): volume fluxes vf[n*2*dim] from a 1p pressure field
+   (main.cc:162-199), and the TracerLocalResidual assembled explicitly (implicit = 0, the example) or implicitly */
+void orc_volume_flux(orc_problem* p, const double* pressure, double* vf);
+void orc_tracer_assemble(orc_problem* p, const double* vf, const double* cur, const double* prev, int implicit, double rho,
+                         double* residual, double* jac);
 
 /* material-law probes for unit tests: which = 0 pc, 1 krw, 2 krn, 3 dpc_dsw, 4 dkrw_dsw, 5 dkrn_dsw */
 double orc_law_eval(orc_problem* p, int region, int which, double sw);

@@ -68,6 +68,8 @@ def lib():
         L.orc_pattern.argtypes = [vp, _ip, _ip]
         L.orc_assemble.argtypes = [vp, _dp, vp, vp, vp]
         L.orc_volvars.argtypes = [vp, _dp, _dp]
+        L.orc_volume_flux.argtypes = [vp, _dp, _dp]
+        L.orc_tracer_assemble.argtypes = [vp, _dp, _dp, _dp, C.c_int, C.c_double, C.c_void_p, C.c_void_p]
         L.orc_ilu0_bicgstab.argtypes = [C.c_int, C.c_int, _ip, _ip, _dp, _dp, _dp, C.c_double, C.c_int,
                                         C.POINTER(C.c_int), C.POINTER(C.c_double)]
         L.orc_ilu0_bicgstab.restype = C.c_int
@@ -113,9 +115,9 @@ class Oracle:
         if nodes is not None:
             # explicit node coordinates per axis (a slab of a larger YaspGrid keeps the GLOBAL coordinates origin + i*h)
             xs = [np.ascontiguousarray(nodes[a], dtype=np.float64) if a < spec.dim else np.array([0.0, 1.0]) for a in range(3)]
-            self.h = C.c_void_p(L.orc_create_tensor(spec.model, spec.dim, cells, xs[0], xs[1], xs[2]))
+            self.h = C.c_void_p(L.orc_create_tensor(min(spec.model, 2) if spec.model != 3 else 1, spec.dim, cells, xs[0], xs[1], xs[2]))
         else:
-            self.h = C.c_void_p(L.orc_create(spec.model, spec.dim, cells, lower, upper))
+            self.h = C.c_void_p(L.orc_create(1 if spec.model == 3 else spec.model, spec.dim, cells, lower, upper))
         self.opt = OrcOptions()
         L.orc_default_options(C.byref(self.opt))
         o = spec.options
@@ -174,11 +176,21 @@ class Oracle:
         self.opt.num_threads = nt
         lib().orc_set_options(self.h, C.byref(self.opt))
 
+    def volume_flux(self, pressure):
+        """examples/1ptracer/main.cc:162-199: volume fluxes [n, 2*dim] of a 1p problem from its pressure solution"""
+        out = np.zeros((self.n, 2 * self.spec.dim))
+        lib().orc_volume_flux(self.h, np.ascontiguousarray(pressure, dtype=np.float64).reshape(-1), out)
+        return out
+
     def assemble(self, cur, prev=None, jacobian=True):
         cur = np.ascontiguousarray(cur, dtype=np.float64).reshape(-1)
         prev_a = None if prev is None else np.ascontiguousarray(prev, dtype=np.float64).reshape(-1)
         res = np.zeros(self.n * self.b)
         jac = np.zeros(self.nnzb * self.b * self.b) if jacobian else None
+        if self.spec.model == 3:       # tracer transport on a frozen velocity field
+            lib().orc_tracer_assemble(self.h, np.ascontiguousarray(self.spec.volume_flux, dtype=np.float64), cur, prev_a,
+                                      int(self.spec.implicit), float(self.spec.rho[0]), _ptr(res), _ptr(jac))
+            return res, jac
         lib().orc_assemble(self.h, cur, _ptr(prev_a), _ptr(res), _ptr(jac))
         return res, jac
 
@@ -202,6 +214,28 @@ class Oracle:
         st = lib().orc_newton_solve(self.h, u, _ptr(prev_a), lin_reduction, lin_maxit, max_rel_shift, min_steps,
                                     max_steps, C.byref(rep))
         return u, st, rep
+
+    def run_instationary(self, u0, loop, **newton_kw):
+        """The same driver as Engine.run_instationary (dumux_b200.timeloop decides dt), Newton steps on the CPU."""
+        from dumux_b200 import timeloop
+        orc = self
+        state = {"u": np.ascontiguousarray(u0, dtype=np.float64).copy(), "prev": np.ascontiguousarray(u0, dtype=np.float64).copy()}
+
+        class _Stepper:
+            def solve(self, dt):
+                orc.set_dt(dt)
+                u, st, rep = orc.newton(state["u"], state["prev"], **newton_kw)
+                state["u"] = u
+                return st == 0, rep.newton_iterations
+
+            def reset(self):
+                state["u"] = state["prev"].copy()
+
+            def advance(self):
+                state["prev"] = state["u"].copy()
+
+        its, dts = timeloop.run_instationary(_Stepper(), loop)
+        return state["u"], its, dts
 
     def run_timeloop(self, u0, t_end, dt_initial, max_dt=1e300, max_steps_out=4096):
         u = np.ascontiguousarray(u0, dtype=np.float64).reshape(-1).copy()

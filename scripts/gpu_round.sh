@@ -24,6 +24,7 @@ for s in $STEPS; do
     asmfull) timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"assemble_tile" -c 1 -f -o $OUT/prof_asm python scripts/profile_step.py 256 1 > $OUT/asmfull.log 2>&1; tail -2 $OUT/asmfull.log;;
     lin)   timeout 300 python -m pytest tests/test_gpu_linear.py tests/test_gpu_newton.py -m gpu -x -q > $OUT/lin_tests.log 2>&1; tail -3 $OUT/lin_tests.log
            timeout 600 python scripts/ilu_probe.py 256 10 > $OUT/probe_ilu.log 2>&1; tail -5 $OUT/probe_ilu.log;;
+    new)   timeout 600 python -m pytest tests/test_tracer.py tests/test_gpu_compressible.py tests/test_abi_exports.py -m gpu -x -q > $OUT/new_tests.log 2>&1; tail -15 $OUT/new_tests.log;;
     smoke) timeout 300 python __graft_entry__.py smoke > $OUT/smoke.log 2>&1; tail -3 $OUT/smoke.log;;
   esac
 done
