@@ -123,7 +123,7 @@ struct dmx_ctx {
 
     // vectors
     double* d_vec[DMX_NUM_VECS] = {};
-    double *d_rt = nullptr, *d_p = nullptr, *d_v = nullptr, *d_t = nullptr, *d_y = nullptr, *d_dinv = nullptr;
+    double *d_rt = nullptr, *d_p = nullptr, *d_v = nullptr, *d_t = nullptr, *d_y = nullptr, *d_z = nullptr, *d_dinv = nullptr;
 
     // ILU0 level schedule (rows sorted by level; level_ptr on host)
     int *d_lrows = nullptr, *d_urows = nullptr;

@@ -49,9 +49,57 @@ __global__ void __launch_bounds__(256) bcrs_spmv_kernel(int n, const int* __rest
     y[(size_t)row * B + e] = acc;
 }
 
+// Structured-grid variant: same BCRS values, same per-row summation order (columns ascending = -z,-y,-x,diag,+x,+y,+z among
+// the existing neighbours), but the column indices come from the grid instead of colidx -- 28 of the 288 bytes per 2x2 block
+// row are not read.  Launched as (x-blocks, ny, nz): no integer division per thread.
+template <int B>
+__global__ void __launch_bounds__(128) stencil_spmv_kernel(int nx, int ny, int nz, int dim, const int* __restrict__ rowptr,
+                                                           const double* __restrict__ A, const double* __restrict__ x,
+                                                           double* __restrict__ y, const unsigned char* __restrict__ owner)
+{
+    const int tx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = tx / B, e = tx % B;
+    const int j = blockIdx.y, k = blockIdx.z;
+    if (i >= nx) return;
+    const int row = i + nx * (j + ny * k);
+    const int sx = 1, sy = nx, sz = nx * ny;
+    int kpos = rowptr[row];
+    double acc = 0.0;
+    auto term = [&](int c) {
+        if (B == 2) {
+            const double2 a = *reinterpret_cast<const double2*>(A + ((size_t)kpos * 4 + e * 2));
+            const double2 xv = *reinterpret_cast<const double2*>(x + (size_t)c * 2);
+            acc += a.x * xv.x;
+            acc += a.y * xv.y;
+        } else {
+            acc += A[kpos] * x[c];
+        }
+        ++kpos;
+    };
+    if (dim > 2 && k > 0) term(row - sz);
+    if (dim > 1 && j > 0) term(row - sy);
+    if (i > 0) term(row - sx);
+    term(row);
+    if (i + 1 < nx) term(row + sx);
+    if (dim > 1 && j + 1 < ny) term(row + sy);
+    if (dim > 2 && k + 1 < nz) term(row + sz);
+    if (owner && !owner[row]) acc = 0.0;   // OverlappingSchwarzOperator: project() zeroes non-owner rows
+    y[(size_t)row * B + e] = acc;
+}
+
 int launch_spmv(dmx_ctx* ctx, const double* x, double* y)
 {
     ProfScope ps(ctx, DMX_K_SPMV);
+    if (ctx->has_grid && ctx->nc[1] <= 65535 && ctx->nc[2] <= 65535) {
+        const int bs = 128;
+        const dim3 grid((unsigned)((ctx->nc[0] * ctx->b + bs - 1) / bs), (unsigned)ctx->nc[1], (unsigned)ctx->nc[2]);
+        if (ctx->b == 2)
+            stencil_spmv_kernel<2><<<grid, bs, 0, ctx->stream>>>(ctx->nc[0], ctx->nc[1], ctx->nc[2], ctx->dim, ctx->d_rowptr, ctx->d_J, x, y, ctx->d_owner);
+        else
+            stencil_spmv_kernel<1><<<grid, bs, 0, ctx->stream>>>(ctx->nc[0], ctx->nc[1], ctx->nc[2], ctx->dim, ctx->d_rowptr, ctx->d_J, x, y, ctx->d_owner);
+        DMX_CHECK_LAUNCH();
+        return 0;
+    }
     const long long threads = (long long)ctx->n * ctx->b;
     const int bs = 256;
     const int grid = (int)((threads + bs - 1) / bs);
@@ -141,6 +189,46 @@ __global__ void __launch_bounds__(RED_THREADS) axpy2_norm_kernel(size_t len, int
     }
     s = block_reduce<false>(s);
     if (threadIdx.x == 0) partials[blockIdx.x] = s;
+}
+// first half step of BiCGSTAB: r += -alpha*v ; partial ||r||^2.  The matching x += alpha*y is deferred to the second half
+// step (x is not needed in between), which saves one read and one write of x per iteration.
+__global__ void __launch_bounds__(RED_THREADS) axpy_r_norm_kernel(size_t len, int b, double alpha, const double* v, double* r,
+                                                                  const unsigned char* owner, double* partials)
+{
+    double s = 0.0;
+    const double malpha = -alpha;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (size_t)gridDim.x * blockDim.x) {
+        const double ri = r[i] + malpha * v[i];
+        r[i] = ri;
+        if (!owner || owner[i / b]) s += ri * ri;
+    }
+    s = block_reduce<false>(s);
+    if (threadIdx.x == 0) partials[blockIdx.x] = s;
+}
+// second half step: x = (x + alpha*y) + omega*z ; r += -omega*t ; partial ||r||^2 and partial <rt, r> (the next iteration's rho)
+__global__ void __launch_bounds__(RED_THREADS) axpy3_norm_dot_kernel(size_t len, int b, double alpha, double omega, const double* y,
+                                                                     const double* z, const double* t, const double* rt, double* x,
+                                                                     double* r, const unsigned char* owner, double* partials)
+{
+    double s = 0.0, d = 0.0;
+    const double momega = -omega;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (size_t)gridDim.x * blockDim.x) {
+        double xi = x[i];
+        xi += alpha * y[i];
+        xi += omega * z[i];
+        x[i] = xi;
+        const double ri = r[i] + momega * t[i];
+        r[i] = ri;
+        if (!owner || owner[i / b]) { s += ri * ri; d += rt[i] * ri; }
+    }
+    s = block_reduce<false>(s);
+    d = block_reduce<false>(d);
+    if (threadIdx.x == 0) { partials[blockIdx.x] = s; partials[gridDim.x + blockIdx.x] = d; }
+}
+// x += alpha*y (only when the solver stops after a first half step)
+__global__ void __launch_bounds__(256) axpy_kernel(size_t len, double alpha, const double* y, double* x)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (size_t)gridDim.x * blockDim.x) x[i] += alpha * y[i];
 }
 // p = ((p + (-omega)*v) * beta) + r
 __global__ void __launch_bounds__(256) p_update_kernel(size_t len, double beta, double omega, const double* r, const double* v, double* p)
@@ -637,12 +725,20 @@ int bicgstab(dmx_ctx* ctx, double reduction, int maxit, int precond, int* iterat
     DMX_CUDA(cudaMemsetAsync(p, 0, len * sizeof(double), ctx->stream));
     DMX_CUDA(cudaMemsetAsync(v, 0, len * sizeof(double), ctx->stream));
 
-    double rho = 1, alpha = 1, omega = 1, rho_new, h, beta;
+    double rho = 1, alpha = 1, omega = 1, rho_new = 0, h, beta;
     const double EPSILON = 1e-80;
     double it;
     int status = DMX_STATUS_NOT_CONVERGED;
+    double* z = ctx->d_z;       // M^-1 r of the second half step (y keeps M^-1 p until x is updated)
+    bool have_rho = false;      // <rt, r> already produced by the previous iteration's fused update
+    auto flush_x = [&]() -> int {      // x += alpha*y that the first half step deferred
+        ProfScope ps(ctx, DMX_K_BLAS1);
+        axpy_kernel<<<RED_BLOCKS, 256, 0, ctx->stream>>>(len, alpha, y, x);
+        DMX_CHECK_LAUNCH();
+        return 0;
+    };
     for (it = 0.5; it < maxit; it += .5) {
-        if ((rc = dot(ctx, rt, r, &rho_new))) return rc;
+        if (!have_rho && (rc = dot(ctx, rt, r, &rho_new))) return rc;
         if (std::fabs(rho) <= EPSILON || std::fabs(omega) <= EPSILON) { status = DMX_STATUS_BREAKDOWN; break; }
         if (it < 1)
             DMX_CUDA(cudaMemcpyAsync(p, r, len * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
@@ -659,25 +755,28 @@ int bicgstab(dmx_ctx* ctx, double reduction, int maxit, int precond, int* iterat
         alpha = rho_new / h;
         {
             ProfScope ps(ctx, DMX_K_BLAS1);
-            axpy2_norm_kernel<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>>(len, ctx->b, alpha, y, v, x, r, ctx->d_owner, ctx->d_partials);
+            axpy_r_norm_kernel<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>>(len, ctx->b, alpha, v, r, ctx->d_owner, ctx->d_partials);
             DMX_CHECK_LAUNCH();
         }
         if ((rc = reduce_to_host(ctx, 1, false, s))) return rc;
         norm = std::sqrt(s[0]);
-        if (!(norm == norm) || std::isinf(norm)) { status = DMX_STATUS_NONFINITE; break; }
-        if (converged(norm)) { status = 0; break; }
+        if (!(norm == norm) || std::isinf(norm)) { if ((rc = flush_x())) return rc; status = DMX_STATUS_NONFINITE; break; }
+        if (converged(norm)) { if ((rc = flush_x())) return rc; status = 0; break; }
         it += .5;
-        if ((rc = precond_apply(ctx, precond, r, y))) return rc;
-        if ((rc = launch_spmv(ctx, y, t))) return rc;
+        if ((rc = precond_apply(ctx, precond, r, z))) return rc;
+        if ((rc = launch_spmv(ctx, z, t))) return rc;
         if ((rc = dot2(ctx, t, r, t, t, s))) return rc;
         omega = s[0] / s[1];
         {
             ProfScope ps(ctx, DMX_K_BLAS1);
-            axpy2_norm_kernel<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>>(len, ctx->b, omega, y, t, x, r, ctx->d_owner, ctx->d_partials);
+            axpy3_norm_dot_kernel<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>>(len, ctx->b, alpha, omega, y, z, t, rt, x, r, ctx->d_owner,
+                                                                                 ctx->d_partials);
             DMX_CHECK_LAUNCH();
         }
-        if ((rc = reduce_to_host(ctx, 1, false, s))) return rc;
+        if ((rc = reduce_to_host(ctx, 2, false, s))) return rc;
         rho = rho_new;
+        rho_new = s[1];
+        have_rho = true;
         norm = std::sqrt(s[0]);
         if (!(norm == norm) || std::isinf(norm)) { status = DMX_STATUS_NONFINITE; break; }
         if (converged(norm)) { status = 0; break; }
