@@ -50,8 +50,10 @@ def algorithmic_bytes(n, nnzb, b):
     return {
         # read cur, prev, K, phi, region; write residual + Jacobian blocks (neighbour reads are cache hits)
         "assembly": n * (2 * b * 8 + 8 + 8 + 4 + b * 8) + nnzb * b * b * 8,
-        # values + colidx per block, rowptr + x + y per row
-        "spmv": nnzb * (8 * b * b + 4) + n * (4 + 16 * b),
+        # structured-grid SpMV (no column indices): values per block, rowptr + x + y per row -- what the kernel must move
+        "spmv": nnzb * 8 * b * b + n * (4 + 16 * b),
+        # the CSR/BCRS-equivalent figure of SURVEY 8d (values + colidx per block, rowptr + x + y per row), reported alongside
+        "spmv_csr_equivalent": nnzb * (8 * b * b + 4) + n * (4 + 16 * b),
         # factors + colidx, d read, v written / re-read / written
         "ilu0_apply": nnzb * (8 * b * b + 4) + n * (4 + 4 * 8 * b),
         "vec": vec,
@@ -268,7 +270,7 @@ def run_b200(args):
     wall = time.perf_counter() - wall0
     clocks = sampler.stop()
     launches = eng.launches() - launches0
-    prof = {k: eng.profile_read(v) for k, v in (("assembly", B.K_ASSEMBLY), ("volvars", B.K_VOLVARS), ("spmv", B.K_SPMV),
+    prof = {k: eng.profile_read(v) for k, v in (("assembly", B.K_ASSEMBLY), ("spmv", B.K_SPMV),
                                                 ("ilu0_apply", B.K_ILU_APPLY), ("ilu0_factor", B.K_ILU_FACTOR),
                                                 ("blas1", B.K_BLAS1), ("halo", B.K_HALO))}
     eng.profile(False)
@@ -313,22 +315,23 @@ def run_b200(args):
             ach = ab[name] / (avg * 1e-3) / 1e9
             k.update(bound="hbm", achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, algorithmic_bytes=ab[name],
                      traffic=traffic.get(name))
+            if name == "spmv":
+                csr = ab["spmv_csr_equivalent"]
+                k.update(csr_equivalent_bytes=csr, csr_equivalent_gbs=csr / (avg * 1e-3) / 1e9,
+                         note="read-dominated stream: the peak is the measured COPY bandwidth (half writes), pure reads run above it; "
+                              "against the nominal 8000 GB/s the fraction is %.2f" % (ach / 8000.0))
         kernels[name] = k
-    # volvars is the first half of the assembly: report assembly = volvars + assemble kernels together
-    if "assembly" in kernels and "volvars" in kernels:
-        avg = kernels["assembly"]["avg_ms"] + kernels["volvars"]["avg_ms"]
-        ach = ab["assembly"] / (avg * 1e-3) / 1e9
-        kernels["assembly_total"] = {"avg_ms": avg, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                                     "algorithmic_bytes": ab["assembly"],
-                                     "share_of_step": kernels["assembly"]["share_of_step"] + kernels["volvars"]["share_of_step"]}
-    graded = [k for k in ("spmv", "assembly_total", "assembly") if k in kernels]
+    # the dominant kernel of the step (largest share of the timed region) among the HBM-bound kernel classes
+    graded = [k for k in ("ilu0_apply", "spmv", "assembly") if k in kernels]
     dom = max(graded, key=lambda k: kernels[k]["share_of_step"]) if graded else None
     roofline = None
     if dom:
         kd = kernels[dom]
         roofline = {"kernel": dom, "bound": "hbm", "achieved": kd["achieved"], "peak": peak, "unit": "GB/s", "frac": kd["frac"],
                     "traffic": kd.get("traffic"), "peak_source": peak_src, "algorithmic_bytes": kd["algorithmic_bytes"],
-                    "avg_launch_ms": kd["avg_ms"]}
+                    "avg_launch_ms": kd["avg_ms"], "share_of_step": kd["share_of_step"],
+                    "note": ("one ILU0 application = vec_skew + lower sweep + upper sweep (3 launches timed as one unit); "
+                             "algorithmic bytes are the BCRS-equivalent figure of SURVEY 8d" if dom == "ilu0_apply" else None)}
 
     if rank != 0:
         if dist is not None:

@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdumux_b200.so")
+LIB_PATH = os.environ.get("DMX_LIB") or os.path.join(_HERE, "libdumux_b200.so")       # DMX_LIB: developer A/B builds
 
 VEC_CUR, VEC_PREV, VEC_RESIDUAL, VEC_DELTA, VEC_ULAST, VEC_WORK0, VEC_WORK1 = range(7)
 PRECOND_ILU0, PRECOND_BLOCKJACOBI = 0, 1

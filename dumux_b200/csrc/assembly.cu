@@ -859,12 +859,14 @@ static void fill_params(dmx_ctx* ctx, AsmParams& P)
     P.rdt = 1.0 / o.dt;
     P.nlaws = (int)ctx->laws.size();
     {
-        // layers per CTA of the tile kernel: about six waves of two CTAs per SM, at least 16 layers (halo layers cost 2/zchunk)
+        // layers per CTA of the tile kernel: about ten waves of two CTAs per SM (measured at 256^3: 2.53 ms with 24 layers, 2.68 with
+        // 37, 3.0 with 128 -- the tail of the last wave costs more than the 2/zchunk halo layers), at least 16 layers
         const int tiles = ((ctx->nc[0] + AT_TX - 1) / AT_TX) * ((ctx->nc[1] + AT_TY - 1) / AT_TY);
-        const int want = std::max(1, (12 * ctx->num_sms + tiles - 1) / tiles);
+        const int want = std::max(1, (20 * ctx->num_sms + tiles - 1) / tiles);
         int zc = (ctx->nc[2] + want - 1) / want;
         zc = std::max(zc, std::min(16, ctx->nc[2]));
-        P.zchunk = zc;
+        static const int zc_env = [] { const char* e = getenv("DMX_ZCHUNK"); return e ? atoi(e) : 0; }();   // tuning override
+        P.zchunk = zc_env > 0 ? std::min(zc_env, ctx->nc[2]) : zc;
     }
     P.tabulated = ctx->tabulated ? 1 : 0;
     P.table = ctx->d_table;

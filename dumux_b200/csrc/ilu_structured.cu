@@ -39,6 +39,13 @@ constexpr int SK_TI = 16, SK_TJ = 16, SK_THREADS = SK_TI * SK_TJ;
 constexpr int SK_C = SK_CHUNK;               // steps per chunk: progress is published / awaited once per chunk
 static_assert((SK_C * (SK_TI + SK_TJ)) % 32 == 0, "halo values of a chunk are fetched by one warp");
 constexpr unsigned long long SK_EPOCH = 1ull << 20;
+#ifndef SK_NAT_RHS
+#define SK_NAT_RHS 0        // 1: lower sweep gathers its right-hand side from the natural-layout vector (no vec_skew pass); measured slower (1.75 vs 1.66 ms)
+#endif
+#ifndef SK_NAT_OUT
+#define SK_NAT_OUT 1        // upper sweep scatters its result into the natural-layout vector (no vec_unskew pass)
+#endif
+constexpr int SK_PF = 4;                     // lower sweep: right-hand sides are gathered this many steps ahead
 #ifndef SK_POLL_NS
 #define SK_POLL_NS 100       // back-off between polls of an upstream tile's progress word (148 spinning CTAs saturate its L2 slice)
 #endif
@@ -113,8 +120,10 @@ struct SkewLayout {
     static constexpr int NBLK = UPPER ? 4 : 3;
     static constexpr int NC = NBLK * B * B;
     static constexpr int STAGE_DOUBLES = NC * SK_THREADS;                    // factor part of one step
-    static constexpr int VEC_DOUBLES = B * SK_THREADS;                       // vector part of one step
-    static constexpr int STEP_DOUBLES = STAGE_DOUBLES + VEC_DOUBLES;         // stream stride per step
+    static constexpr int VEC_DOUBLES = B * SK_THREADS;                       // one step of a skewed vector
+    // the upper stream carries the lower sweep's result next to the factors; the lower sweep reads its right-hand side
+    // straight from the natural-layout vector (prefetched into registers), so its stream is factors only
+    static constexpr int STEP_DOUBLES = STAGE_DOUBLES + ((UPPER || !SK_NAT_RHS) ? VEC_DOUBLES : 0);   // stream stride per step
     // depth of the shared-memory ring (steps in flight): 7 x 28 KB lower, 5 x 36 KB upper for 2x2 blocks
     static constexpr int S = (B == 2) ? (UPPER ? 5 : 7) : 16;
 };
@@ -241,13 +250,17 @@ __global__ void __launch_bounds__(256) vec_unskew_kernel(SkewGrid g, const doubl
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// one triangular sweep.  LOWER: out <- L^-1 rhs (unit lower), rhs from the vector slots of the lower stream, result into the
-// vector slots of the upper stream.  UPPER: out <- U^-1 rhs, rhs from the upper stream, result into the skewed vector xsk.
+// one triangular sweep.  LOWER: out <- L^-1 rhs (unit lower); the right-hand side comes from the vector slots of the lower
+// stream (written by vec_skew_kernel; SK_NAT_RHS = 1 gathers it from the natural-layout vector instead, measured slower),
+// the result goes into the vector slots of the upper stream.  UPPER: U^-1 rhs, rhs from the upper stream, result scattered
+// into the natural-layout vector `nat` (16-byte stores; the two halves of a 32-byte sector are written one step apart and
+// merge in L2 -- this replaces a separate un-skew pass) and, for the two edges a downstream tile reads, into the skewed xsk.
 //   stream : this sweep's [factors | rhs] stream
-//   out    : where results go (LOWER: the upper stream, UPPER: xsk); upstream tiles' results are read back from it
+//   out    : skewed results other tiles read back (LOWER: the upper stream, all lanes; UPPER: xsk, edge lanes only)
 // ------------------------------------------------------------------------------------------------------------
 template <int B, bool UPPER>
 __global__ void __launch_bounds__(SK_THREADS + 64, 1) ilu_sweep_kernel(SkewGrid g, const double* __restrict__ stream, double* out,
+                                                                        double* nat,
                                                                    const int* __restrict__ order, unsigned long long* ticket_ctr,
                                                                    unsigned long long ticket_base, unsigned long long* prog,
                                                                    unsigned long long epoch, long long* trace)
@@ -378,6 +391,22 @@ __global__ void __launch_bounds__(SK_THREADS + 64, 1) ilu_sweep_kernel(SkewGrid 
     double vprev[B];
 #pragma unroll
     for (int e = 0; e < B; ++e) vprev[e] = 0.0;
+    // natural-layout index of this thread's cell at wavefront distance kk (layer kk for the lower sweep, nz-1-kk for the upper)
+    auto cell_index = [&](int kk) { return (size_t)i + (size_t)g.nx * ((size_t)j + (size_t)g.ny * (size_t)(UPPER ? g.nz - 1 - kk : kk)); };
+    static_assert(SK_C % SK_PF == 0, "prefetch slots are indexed statically inside the unrolled chunk");
+    double rq[SK_PF][B];       // LOWER: right-hand sides of the next SK_PF steps
+#pragma unroll
+    for (int q = 0; q < SK_PF; ++q) {
+#pragma unroll
+        for (int e = 0; e < B; ++e) rq[q][e] = 0.0;
+        if (!UPPER && SK_NAT_RHS) {
+            const int kn = q - a - b;
+            if (line && kn >= 0 && kn < g.nz) {
+#pragma unroll
+                for (int e = 0; e < B; ++e) rq[q][e] = __ldg(nat + cell_index(kn) * B + e);
+            }
+        }
+    }
 
     long long* tr = nullptr;       // optional timeline (developer diagnostic): tiles ticketed 0 and ntiles/2
     if (trace && t == 0) {
@@ -410,7 +439,7 @@ __global__ void __launch_bounds__(SK_THREADS + 64, 1) ilu_sweep_kernel(SkewGrid 
                 if (active) {
                     double r[B];
 #pragma unroll
-                    for (int e = 0; e < B; ++e) r[e] = f[LY::STAGE_DOUBLES + tl * B + e];
+                    for (int e = 0; e < B; ++e) r[e] = (UPPER || !SK_NAT_RHS) ? f[LY::STAGE_DOUBLES + tl * B + e] : rq[c % SK_PF][e];
                     double xv[B], yv[B];
                     const double* xs = (a == 0) ? hx + (c * SK_TJ + b) * B : sv + ((rb * (SK_TJ + 1) + (b + 1)) * (SK_TI + 1) + a) * B;
                     const double* ys = (b == 0) ? hy + (c * SK_TI + a) * B : sv + ((rb * (SK_TJ + 1) + b) * (SK_TI + 1) + (a + 1)) * B;
@@ -485,9 +514,29 @@ __global__ void __launch_bounds__(SK_THREADS + 64, 1) ilu_sweep_kernel(SkewGrid 
 #pragma unroll
                     for (int e = 0; e < B; ++e) { vprev[e] = r[e]; svw[e] = r[e]; }
                     const int sl = UPPER ? NS - 1 - s : s;
-                    double* dstp = out_tile + (size_t)out_step_index(sl) * OUT_STEP + (size_t)tl * B;
-                    if (B == 2) __stcg(reinterpret_cast<double2*>(dstp), make_double2(r[0], r[B - 1]));
-                    else __stcg(dstp, r[0]);
+                    if (!UPPER || !SK_NAT_OUT || a == SK_TI - 1 || b == SK_TJ - 1) {
+                        double* dstp = out_tile + (size_t)out_step_index(sl) * OUT_STEP + (size_t)tl * B;
+                        if (B == 2) __stcg(reinterpret_cast<double2*>(dstp), make_double2(r[0], r[B - 1]));
+                        else __stcg(dstp, r[0]);
+                    }
+                    if (UPPER && SK_NAT_OUT) {
+                        double* dn = nat + cell_index(kk) * B;
+                        if (B == 2) *reinterpret_cast<double2*>(dn) = make_double2(r[0], r[B - 1]);
+                        else dn[0] = r[0];
+                    }
+                }
+                if (!UPPER && SK_NAT_RHS) {
+                    // right-hand side of step s + SK_PF
+                    const int kn = s + SK_PF - a - b;
+#pragma unroll
+                    for (int e = 0; e < B; ++e) rq[c % SK_PF][e] = 0.0;
+                    if (line && kn >= 0 && kn < g.nz) {
+                        const double* sn = nat + cell_index(kn) * B;
+                        if (B == 2) {
+                            const double2 wv = __ldg(reinterpret_cast<const double2*>(sn));
+                            rq[c % SK_PF][0] = wv.x; rq[c % SK_PF][B - 1] = wv.y;
+                        } else rq[c % SK_PF][0] = __ldg(sn);
+                    }
                 }
                 compute_barrier();
                 SK_STAMP(4 + 2 * c);
@@ -524,14 +573,14 @@ static size_t sweep_smem()
 }
 
 template <int B, bool UPPER>
-static int sweep_launch(dmx_ctx* ctx, SkewState* st, const double* stream, double* out, const int* order, unsigned long long* tick,
+static int sweep_launch(dmx_ctx* ctx, SkewState* st, const double* stream, double* out, double* nat, const int* order, unsigned long long* tick,
                         unsigned long long base, unsigned long long* prog, unsigned long long epoch, long long* trace)
 {
     const SkewGrid& g = st->g;
     auto kern = ilu_sweep_kernel<B, UPPER>;
     const size_t smem = sweep_smem<B, UPPER>();
     DMX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<g.ntiles, SK_THREADS + 64, smem, ctx->stream>>>(g, stream, out, order, tick, base, prog, epoch, trace);
+    kern<<<g.ntiles, SK_THREADS + 64, smem, ctx->stream>>>(g, stream, out, nat, order, tick, base, prog, epoch, trace);
     DMX_CHECK_LAUNCH();
     return 0;
 }
@@ -569,9 +618,9 @@ int sk_setup(dmx_ctx* ctx)
     const int BB = ctx->b * ctx->b;
     const size_t slots = (size_t)g.ntiles * g.NS * SK_THREADS;
     // streams [factors | vector] per step: the vector slots of Lsk hold the right-hand side, those of Usk the lower sweep's result
-    DMX_CUDA(cudaMalloc((void**)&st->Lsk, slots * (3 * BB + ctx->b) * sizeof(double)));
+    DMX_CUDA(cudaMalloc((void**)&st->Lsk, slots * (3 * BB + (SK_NAT_RHS ? 0 : ctx->b)) * sizeof(double)));
     DMX_CUDA(cudaMalloc((void**)&st->Usk, slots * (4 * BB + ctx->b) * sizeof(double)));
-    DMX_CUDA(cudaMemsetAsync(st->Lsk, 0, slots * (3 * BB + ctx->b) * sizeof(double), ctx->stream));
+    DMX_CUDA(cudaMemsetAsync(st->Lsk, 0, slots * (3 * BB + (SK_NAT_RHS ? 0 : ctx->b)) * sizeof(double), ctx->stream));
     DMX_CUDA(cudaMemsetAsync(st->Usk, 0, slots * (4 * BB + ctx->b) * sizeof(double), ctx->stream));
     DMX_CUDA(cudaMalloc((void**)&st->xsk, slots * ctx->b * sizeof(double)));
     std::vector<int> lo(g.ntiles), up(g.ntiles);
@@ -619,14 +668,20 @@ static int sk_apply_t(dmx_ctx* ctx, SkewState* st, const double* d, double* v)
     const unsigned long long base_up = st->seq_up * (unsigned long long)g.ntiles, ep_up = (st->seq_up + 1) * SK_EPOCH;
     st->seq_lo++;
     st->seq_up++;
-    vec_skew_kernel<B><<<(unsigned)((size_t)g.ntiles * g.NS), SK_THREADS, 0, ctx->stream>>>(g, d, st->Lsk);
-    DMX_CHECK_LAUNCH();
-    if (int rc = sweep_launch<B, false>(ctx, st, st->Lsk, st->Usk, st->order_lo, tick_lo, base_lo, prog_lo, ep_lo, st->trace)) return rc;
-    if (int rc = sweep_launch<B, true>(ctx, st, st->Usk, st->xsk, st->order_up, tick_up, base_up, prog_up, ep_up,
+    if (!SK_NAT_RHS) {
+        vec_skew_kernel<B><<<(unsigned)((size_t)g.ntiles * g.NS), SK_THREADS, 0, ctx->stream>>>(g, d, st->Lsk);
+        DMX_CHECK_LAUNCH();
+    }
+    if (int rc = sweep_launch<B, false>(ctx, st, st->Lsk, st->Usk, const_cast<double*>(d), st->order_lo, tick_lo, base_lo, prog_lo, ep_lo,
+                                        st->trace))
+        return rc;
+    if (int rc = sweep_launch<B, true>(ctx, st, st->Usk, st->xsk, v, st->order_up, tick_up, base_up, prog_up, ep_up,
                                        st->trace ? st->trace + 2 * 64 * 24 : nullptr))
         return rc;
-    vec_unskew_kernel<B><<<(unsigned)((ctx->n + 255) / 256), 256, 0, ctx->stream>>>(g, st->xsk, v);
-    DMX_CHECK_LAUNCH();
+    if (!SK_NAT_OUT) {
+        vec_unskew_kernel<B><<<(unsigned)((ctx->n + 255) / 256), 256, 0, ctx->stream>>>(g, st->xsk, v);
+        DMX_CHECK_LAUNCH();
+    }
     return 0;
 }
 
