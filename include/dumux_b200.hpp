@@ -107,6 +107,14 @@ struct ProblemData {
     struct Side { std::vector<int> type; std::vector<double> values; };   // values: [face][numEq] Dirichlet priVars or Neumann fluxes
     std::array<Side, 6> boundary;                    // sides -x,+x,-y,+y,-z,+z; empty = no-flow Neumann
     std::vector<double> source;                      // per cell and equation (empty: none)
+    //! tabulated liquid of the compressible 1p model: the tables TabulatedComponent<H2O>::init filled
+    //! (material/components/tabulatedcomponent.hh:330-345), values[iT + iP*nT]; empty: constant density / viscosity
+    struct FluidTable { int nT = 0, nP = 0; double Tmin = 0, Tmax = 0, temperature = 293.15; std::vector<double> pmin, pmax, density, viscosity; };
+    FluidTable fluidTable;
+    //! tracer model (DMX_MODEL_TRACER): frozen volume fluxes [cell][side] (spatialparams_tracer.hh:91-103) and the time
+    //! discretisation of FVAssembler<TracerTypeTag, DiffMethod::analytic, implicit> (examples/1ptracer/main.cc:236)
+    std::vector<double> volumeFlux;
+    bool tracerImplicit = false;
     dmx_options options;
     ProblemData() { dmx_default_options(&options); }
 };
@@ -179,6 +187,15 @@ public:
     }
     std::size_t numDofs() const { return static_cast<std::size_t>(dmx_num_cells(ctx_->get())); }
     int numEq() const { return numEq_; }
+    //! 1p assembler: volume fluxes over all scvfs of all elements from the pressure field `p`, [element][indexInInside]
+    //! -- the element loop of examples/1ptracer/main.cc:162-199, input of TracerTestSpatialParams::setVolumeFlux
+    std::vector<double> volumeFlux(const SolutionVector& p, int dim)
+    {
+        upload_(p);
+        std::vector<double> vf(numDofs() * 2 * static_cast<std::size_t>(dim));
+        ctx_->check(dmx_volume_flux(ctx_->get(), vf.data()));
+        return vf;
+    }
     const SolutionVector& prevSol() const { return *prevSol_; }
     void setPreviousSolution(const SolutionVector& u) { prevSol_ = &u; prevUploaded_ = false; }
     //! stands for setTimeLoop / timeLoop->timeStepSize() (fvassembler.hh:347-368)
@@ -212,6 +229,16 @@ private:
                                          m.reg.empty() ? nullptr : m.reg.data()));
         }
         ctx_->check(dmx_set_fluids(c, p.density.data(), p.viscosity.data()));
+        if (p.fluidTable.nT > 0) {
+            const auto& t = p.fluidTable;
+            ctx_->check(dmx_set_fluid_table(c, t.nT, t.nP, t.Tmin, t.Tmax, t.pmin.data(), t.pmax.data(), t.density.data(), t.viscosity.data(),
+                                            t.temperature));
+        }
+        if (p.model == DMX_MODEL_TRACER) {
+            if (p.volumeFlux.size() != numDofs() * 2 * static_cast<std::size_t>(p.dim)) throw InvalidState("tracer: volumeFlux must hold 2*dim values per cell");
+            ctx_->check(dmx_set_volume_flux(c, p.volumeFlux.data()));
+            ctx_->check(dmx_set_tracer(c, p.tracerImplicit ? 1 : 0));
+        }
         for (int s = 0; s < 2 * p.dim; ++s)
             if (!p.boundary[s].type.empty()) ctx_->check(dmx_set_boundary(c, s, p.boundary[s].type.data(), p.boundary[s].values.data()));
         if (!p.source.empty()) ctx_->check(dmx_set_source(c, p.source.data()));
