@@ -109,6 +109,16 @@ __device__ __forceinline__ unsigned long long ld_acquire(const unsigned long lon
     asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ unsigned long long ld_relaxed(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed(unsigned long long* p, unsigned long long v)
+{
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 __device__ __forceinline__ void st_release(unsigned long long* p, unsigned long long v)
 {
     asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -552,6 +562,325 @@ __global__ void __launch_bounds__(SK_THREADS + 64, 1) ilu_sweep_kernel(SkewGrid 
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Variant with flag-in-data halo exchange (SK_LL): the edge threads of a tile publish their values as 64-bit words that carry a
+// tag next to half a double (8-byte stores are single-copy atomic, so a word is valid as soon as its tag matches); the sync warp
+// of the downstream tile polls exactly the words it needs, step by step.  No progress counters, no release fences, and the
+// tile-to-tile lag is the geometric minimum of 16 steps instead of 23.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int SK_R = 8;                      // halo ring depth in steps
+constexpr int SK_NB = 4;                     // steps whose halo words the sync warp requests together
+template <int B, bool UPPER>
+__global__ void __launch_bounds__(SK_THREADS + 64, 1) ilu_sweep_ll_kernel(SkewGrid g, const double* __restrict__ stream, double* out,
+                                                                           double* nat, unsigned long long* ll, unsigned int tag,
+                                                                           const int* __restrict__ order, unsigned long long* ticket_ctr,
+                                                                           unsigned long long ticket_base, long long* trace)
+{
+    using LY = SkewLayout<B, UPPER>;
+    using LYU = SkewLayout<B, true>;
+    constexpr int S = LY::S;
+    // where results live: LOWER -> vector slots of the upper stream (step stride STEP_U, offset FAC_U); UPPER -> xsk
+    constexpr size_t OUT_STEP = UPPER ? (size_t)LY::VEC_DOUBLES : (size_t)LYU::STEP_DOUBLES;
+    constexpr size_t OUT_OFF = UPPER ? 0 : (size_t)LYU::STAGE_DOUBLES;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* stages = reinterpret_cast<double*>(smem_raw);                              // [S][factors | rhs]
+    double* sv = stages + (size_t)S * LY::STEP_DOUBLES;                                // [2][TJ+1][TI+1][B]
+    double* hring = sv + 2 * (SK_TJ + 1) * (SK_TI + 1) * B;                            // [SK_R][x halo TJ | y halo TI][B]
+    constexpr int HSTEP_DOUBLES = (SK_TI + SK_TJ) * B;
+    uint64_t* full = reinterpret_cast<uint64_t*>(hring + SK_R * HSTEP_DOUBLES);        // [S] data landed
+    uint64_t* empty = full + S;                                                        // [S] slot released by the compute threads
+    uint64_t* hready = empty + S;                                                      // [SK_R] halo of a step staged by the sync warp
+    uint64_t* hfree = hready + SK_R;                                                   // [SK_R] halo slot released by the compute threads
+    __shared__ int s_tile;
+
+    const int t = threadIdx.x;
+    const int a = t & (SK_TI - 1), b = t >> 4;          // mirrored coordinates for UPPER
+    const int tl = UPPER ? SK_THREADS - 1 - t : t;      // lane in LOWER indexing (storage)
+    if (t == 0) {
+        const unsigned long long ticket = atomicAdd(ticket_ctr, 1ull) - ticket_base;
+        s_tile = order[(int)ticket];
+        for (int q = 0; q < S; ++q) { mbar_init(&full[q], 1); mbar_init(&empty[q], 1); }
+        for (int q = 0; q < SK_R; ++q) { mbar_init(&hready[q], 1); mbar_init(&hfree[q], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int tile = s_tile;
+    const int ti = tile % g.ntx, tj = tile / g.ntx;
+    const int NS = g.NS;
+    const double* stream_tile = stream + (size_t)tile * NS * LY::STEP_DOUBLES;
+    // results of step s (this sweep's step index) go to "lower step" sl = UPPER ? NS-1-s : s; the LOWER sweep stores them where
+    // the upper sweep will fetch them: upper step NS-1-sl
+    auto out_step_index = [&](int sl) { return UPPER ? sl : NS - 1 - sl; };
+    double* out_tile = out + (size_t)tile * NS * OUT_STEP + OUT_OFF;
+    const int nchunks = (NS + SK_C - 1) / SK_C;
+    constexpr int HSHIFT = SK_TI - 1;       // == SK_TJ - 1
+    static_assert(SK_TI == SK_TJ, "square tiles");
+    const int tix = UPPER ? ti + 1 : ti - 1, tjy = UPPER ? tj + 1 : tj - 1;
+    const bool tilex = tix >= 0 && tix < g.ntx, tiley = tjy >= 0 && tjy < g.nty;
+
+    // halo words of (tile, step, direction, edge cell): 2*B 64-bit words {tag : 32 | half of a double : 32}
+    auto ll_words = [&](int tl_, int s_, int dir, int e) {
+        return ll + ((((size_t)tl_ * NS + s_) * 2 + dir) * SK_TI + e) * (2 * B);
+    };
+    if (t >= SK_THREADS + 32) {
+        // ---- sync warp: stages the upstream tiles' boundary values step by step, polling the self-validating words the
+        //      upstream edge threads wrote (no progress counters, no fences: every 8-byte word carries its own tag) ----
+        const int lane = t - (SK_THREADS + 32);
+        const int dir = lane / SK_TI, hl = lane % SK_TI;        // lanes 0-15: x halo (row hl), 16-31: y halo (column hl)
+        const int htile = dir == 0 ? tix + g.ntx * tj : ti + g.ntx * tjy;
+        const int other = dir == 0 ? tj * SK_TJ + (UPPER ? SK_TJ - 1 - hl : hl) : ti * SK_TI + (UPPER ? SK_TI - 1 - hl : hl);
+        const bool hvalid = (dir == 0 ? tilex : tiley) && other < (dir == 0 ? g.ny : g.nx);
+        // Batches of SK_NB steps: all words of a batch are requested at once (one L2 round trip per batch instead of 2*B
+        // dependent round trips per step); a word whose tag does not match yet is polled again when its step is due.
+        for (int s0 = 0; s0 < NS; s0 += SK_NB) {
+            unsigned long long wq[SK_NB][2 * B];
+            bool okq[SK_NB];
+#pragma unroll
+            for (int k = 0; k < SK_NB; ++k) {
+                const int s = s0 + k;
+                const int kk = s - hl;
+                okq[k] = s < NS && hvalid && kk >= 0 && kk < g.nz;
+                if (okq[k]) {
+                    const unsigned long long* w = ll_words(htile, s + HSHIFT, dir, hl);
+#pragma unroll
+                    for (int e = 0; e < 2 * B; ++e) wq[k][e] = ld_relaxed(w + e);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < SK_NB; ++k) {
+                const int s = s0 + k;
+                if (s >= NS) break;       // uniform
+                const int q = s % SK_R;
+                double val[B];
+#pragma unroll
+                for (int e = 0; e < B; ++e) val[e] = 0.0;
+                if (okq[k]) {
+                    const unsigned long long* w = ll_words(htile, s + HSHIFT, dir, hl);
+#pragma unroll
+                    for (int e = 0; e < 2 * B; ++e)
+                        while ((unsigned int)(wq[k][e] >> 32) != tag) wq[k][e] = ld_relaxed(w + e);
+#pragma unroll
+                    for (int e = 0; e < B; ++e)
+                        val[e] = __longlong_as_double((long long)((wq[k][2 * e + 1] << 32) | (wq[k][2 * e] & 0xffffffffull)));
+                }
+                if (s >= SK_R) {
+                    if (lane == 0) mbar_wait(&hfree[q], (uint32_t)(((s / SK_R) - 1) & 1));
+                }
+                __syncwarp();
+#pragma unroll
+                for (int e = 0; e < B; ++e) hring[q * HSTEP_DOUBLES + lane * B + e] = val[e];
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&hready[q]);
+            }
+        }
+        return;
+    }
+    if (t >= SK_THREADS) {
+        // ---- producer: one bulk copy per step, as far ahead as the ring allows ----
+        if (t == SK_THREADS) {
+            constexpr uint32_t BYTES = LY::STEP_DOUBLES * sizeof(double);
+            for (int s = 0; s < NS; ++s) {
+                const int q = s % S;
+                if (s >= S) mbar_wait(&empty[q], (uint32_t)(((s / S) - 1) & 1));
+                mbar_expect_tx(&full[q], BYTES);
+                bulk_g2s(stages + (size_t)q * LY::STEP_DOUBLES, stream_tile + (size_t)s * LY::STEP_DOUBLES, BYTES, &full[q]);
+            }
+        }
+        return;
+    }
+
+    // ---- compute threads: actual cell line of this thread ----
+    const int i = ti * SK_TI + (UPPER ? SK_TI - 1 - a : a);
+    const int j = tj * SK_TJ + (UPPER ? SK_TJ - 1 - b : b);
+    const bool line = i < g.nx && j < g.ny;
+    const bool depx = UPPER ? (i + 1 < g.nx) : (i > 0);          // a -x (+x) neighbour cell exists
+    const bool depy = UPPER ? (j + 1 < g.ny) : (j > 0);
+
+    double vprev[B];
+#pragma unroll
+    for (int e = 0; e < B; ++e) vprev[e] = 0.0;
+    // natural-layout index of this thread's cell at wavefront distance kk (layer kk for the lower sweep, nz-1-kk for the upper)
+    auto cell_index = [&](int kk) { return (size_t)i + (size_t)g.nx * ((size_t)j + (size_t)g.ny * (size_t)(UPPER ? g.nz - 1 - kk : kk)); };
+    static_assert(SK_C % SK_PF == 0, "prefetch slots are indexed statically inside the unrolled chunk");
+    double rq[SK_PF][B];       // LOWER: right-hand sides of the next SK_PF steps
+#pragma unroll
+    for (int q = 0; q < SK_PF; ++q) {
+#pragma unroll
+        for (int e = 0; e < B; ++e) rq[q][e] = 0.0;
+        if (!UPPER && SK_NAT_RHS) {
+            const int kn = q - a - b;
+            if (line && kn >= 0 && kn < g.nz) {
+#pragma unroll
+                for (int e = 0; e < B; ++e) rq[q][e] = __ldg(nat + cell_index(kn) * B + e);
+            }
+        }
+    }
+
+    long long* tr = nullptr;       // optional timeline (developer diagnostic): tiles ticketed 0 and ntiles/2
+    if (trace && t == 0) {
+        if (tile == order[0]) tr = trace;
+        else if (tile == order[g.ntiles / 2]) tr = trace + 24 * 64;
+    }
+#define SK_STAMP(slot) do { if (tr && s0 / SK_C < 64) tr[(s0 / SK_C) * 24 + (slot)] = clock64(); } while (0)
+    for (int s0 = 0; s0 < NS; s0 += SK_C) {
+        // ---- chunk head: the sync warp has staged the upstream tiles' boundary values of this chunk ----
+        SK_STAMP(0);
+        SK_STAMP(1);
+        SK_STAMP(2);
+
+#pragma unroll
+        for (int c = 0; c < SK_C; ++c) {
+            const int s = s0 + c;
+            if (s < NS) {       // uniform
+                const int stage = s % S;
+                const int hq = s % SK_R;
+                // only the threads on the two upstream edges consume staged halo values; the per-step barrier below keeps the
+                // others from running ahead of the ring
+                if (a == 0 || b == 0) mbar_wait(&hready[hq], (uint32_t)((s / SK_R) & 1));
+                const double* hx = hring + hq * HSTEP_DOUBLES;
+                const double* hy = hx + SK_TJ * B;
+                mbar_wait(&full[stage], (uint32_t)((s / S) & 1));
+                SK_STAMP(3 + 2 * c);
+                const double* f = stages + (size_t)stage * LY::STEP_DOUBLES;
+                const int kk = s - a - b;
+                const bool active = line && kk >= 0 && kk < g.nz;
+                const int rb = (s + 1) & 1, wb = s & 1;       // buffer written at step s-1 / written now
+                double* svw = sv + ((wb * (SK_TJ + 1) + (b + 1)) * (SK_TI + 1) + (a + 1)) * B;
+                if (active) {
+                    double r[B];
+#pragma unroll
+                    for (int e = 0; e < B; ++e) r[e] = (UPPER || !SK_NAT_RHS) ? f[LY::STAGE_DOUBLES + tl * B + e] : rq[c % SK_PF][e];
+                    double xv[B], yv[B];
+                    const double* xs = (a == 0) ? hx + b * B : sv + ((rb * (SK_TJ + 1) + (b + 1)) * (SK_TI + 1) + a) * B;
+                    const double* ys = (b == 0) ? hy + a * B : sv + ((rb * (SK_TJ + 1) + b) * (SK_TI + 1) + (a + 1)) * B;
+#pragma unroll
+                    for (int e = 0; e < B; ++e) { xv[e] = xs[e]; yv[e] = ys[e]; }
+                    double blk[LY::NBLK][B * B];
+                    if (B == 2) {
+#pragma unroll
+                        for (int q = 0; q < LY::NBLK; ++q)
+#pragma unroll
+                            for (int rr = 0; rr < 2; ++rr) {
+                                const double2 w = reinterpret_cast<const double2*>(f)[(q * 2 + rr) * SK_THREADS + t];
+                                blk[q][rr * 2] = w.x;
+                                blk[q][rr * 2 + 1] = w.y;
+                            }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < LY::NBLK; ++q) blk[q][0] = f[q * SK_THREADS + t];
+                    }
+                    const bool depz = kk > 0;
+                    if (!UPPER) {
+                        // columns ascending: -z, -y, -x   (rhs -= A_ij v_j, FieldMatrix::mmv order)
+                        if (depz) {
+#pragma unroll
+                            for (int rr = 0; rr < B; ++rr)
+#pragma unroll
+                                for (int cc = 0; cc < B; ++cc) r[rr] -= blk[0][rr * B + cc] * vprev[cc];
+                        }
+                        if (depy) {
+#pragma unroll
+                            for (int rr = 0; rr < B; ++rr)
+#pragma unroll
+                                for (int cc = 0; cc < B; ++cc) r[rr] -= blk[1][rr * B + cc] * yv[cc];
+                        }
+                        if (depx) {
+#pragma unroll
+                            for (int rr = 0; rr < B; ++rr)
+#pragma unroll
+                                for (int cc = 0; cc < B; ++cc) r[rr] -= blk[2][rr * B + cc] * xv[cc];
+                        }
+                    } else {
+                        // columns ascending: +x, +y, +z, then v = Dinv * rhs (sum from 0)
+                        if (depx) {
+#pragma unroll
+                            for (int rr = 0; rr < B; ++rr)
+#pragma unroll
+                                for (int cc = 0; cc < B; ++cc) r[rr] -= blk[0][rr * B + cc] * xv[cc];
+                        }
+                        if (depy) {
+#pragma unroll
+                            for (int rr = 0; rr < B; ++rr)
+#pragma unroll
+                                for (int cc = 0; cc < B; ++cc) r[rr] -= blk[1][rr * B + cc] * yv[cc];
+                        }
+                        if (depz) {
+#pragma unroll
+                            for (int rr = 0; rr < B; ++rr)
+#pragma unroll
+                                for (int cc = 0; cc < B; ++cc) r[rr] -= blk[2][rr * B + cc] * vprev[cc];
+                        }
+                        double o[B];
+#pragma unroll
+                        for (int rr = 0; rr < B; ++rr) {
+                            double acc = 0.0;
+#pragma unroll
+                            for (int cc = 0; cc < B; ++cc) acc += blk[3][rr * B + cc] * r[cc];
+                            o[rr] = acc;
+                        }
+#pragma unroll
+                        for (int e = 0; e < B; ++e) r[e] = o[e];
+                    }
+#pragma unroll
+                    for (int e = 0; e < B; ++e) { vprev[e] = r[e]; svw[e] = r[e]; }
+                    const int sl = UPPER ? NS - 1 - s : s;
+                    if (!UPPER) {
+                        double* dstp = out_tile + (size_t)out_step_index(sl) * OUT_STEP + (size_t)tl * B;
+                        if (B == 2) __stcg(reinterpret_cast<double2*>(dstp), make_double2(r[0], r[B - 1]));
+                        else __stcg(dstp, r[0]);
+                    }
+                    if (a == SK_TI - 1 || b == SK_TJ - 1) {
+                        // boundary values for the downstream tiles: each 64-bit word = {tag, half a double}
+                        unsigned long long wv[2 * B];
+#pragma unroll
+                        for (int e = 0; e < B; ++e) {
+                            const unsigned long long bits = (unsigned long long)__double_as_longlong(r[e]);
+                            wv[2 * e] = ((unsigned long long)tag << 32) | (bits & 0xffffffffull);
+                            wv[2 * e + 1] = ((unsigned long long)tag << 32) | (bits >> 32);
+                        }
+                        if (a == SK_TI - 1) {
+                            unsigned long long* w = ll_words(tile, s, 0, b);
+#pragma unroll
+                            for (int e = 0; e < 2 * B; ++e) __stcg(w + e, wv[e]);       // naturally aligned 8-byte stores are single-copy atomic
+                        }
+                        if (b == SK_TJ - 1) {
+                            unsigned long long* w = ll_words(tile, s, 1, a);
+#pragma unroll
+                            for (int e = 0; e < 2 * B; ++e) __stcg(w + e, wv[e]);       // naturally aligned 8-byte stores are single-copy atomic
+                        }
+                    }
+                    if (UPPER) {
+                        double* dn = nat + cell_index(kk) * B;
+                        if (B == 2) *reinterpret_cast<double2*>(dn) = make_double2(r[0], r[B - 1]);
+                        else dn[0] = r[0];
+                    }
+                }
+                if (!UPPER && SK_NAT_RHS) {
+                    // right-hand side of step s + SK_PF
+                    const int kn = s + SK_PF - a - b;
+#pragma unroll
+                    for (int e = 0; e < B; ++e) rq[c % SK_PF][e] = 0.0;
+                    if (line && kn >= 0 && kn < g.nz) {
+                        const double* sn = nat + cell_index(kn) * B;
+                        if (B == 2) {
+                            const double2 wv = __ldg(reinterpret_cast<const double2*>(sn));
+                            rq[c % SK_PF][0] = wv.x; rq[c % SK_PF][B - 1] = wv.y;
+                        } else rq[c % SK_PF][0] = __ldg(sn);
+                    }
+                }
+                compute_barrier();
+                SK_STAMP(4 + 2 * c);
+                if (t == 0) {
+                    mbar_arrive(&empty[stage]);
+                    mbar_arrive(&hfree[hq]);
+                }
+            }
+        }
+        SK_STAMP(19);
+    }
+#undef SK_STAMP
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------
 struct SkewState {
@@ -562,6 +891,9 @@ struct SkewState {
     unsigned long long* ctl = nullptr;       // [0],[1]: tickets lower/upper; [2 .. 2+ntiles): prog lower; then prog upper
     unsigned long long seq_lo = 0, seq_up = 0;
     long long* trace = nullptr;            // 2 kernels x 2 tiles x 64 chunks x 24 stamps (DMX_SK_TRACE=1)
+    unsigned long long* ll = nullptr;      // flag-in-data halo words [tile][step][dir 2][edge 16][2*b]
+    unsigned int ll_seq = 0;               // tag counter of the flag-in-data sweeps
+    int use_ll = 3;                        // DMX_SK_LL: bit 0 lower / bit 1 upper sweep with flag-in-data halos (0: progress counters)
 };
 
 template <int B, bool UPPER>
@@ -585,6 +917,21 @@ static int sweep_launch(dmx_ctx* ctx, SkewState* st, const double* stream, doubl
     return 0;
 }
 
+template <int B, bool UPPER>
+static int sweep_launch_ll(dmx_ctx* ctx, SkewState* st, const double* stream, double* out, double* nat, unsigned int tag, const int* order,
+                           unsigned long long* tick, unsigned long long base, long long* trace)
+{
+    using LY = SkewLayout<B, UPPER>;
+    const SkewGrid& g = st->g;
+    auto kern = ilu_sweep_ll_kernel<B, UPPER>;
+    const size_t smem = ((size_t)LY::S * LY::STEP_DOUBLES + 2 * (SK_TJ + 1) * (SK_TI + 1) * B + SK_R * (SK_TI + SK_TJ) * B) * sizeof(double) +
+                        (2 * LY::S + 2 * SK_R) * sizeof(uint64_t);
+    DMX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<g.ntiles, SK_THREADS + 64, smem, ctx->stream>>>(g, stream, out, nat, st->ll, tag, order, tick, base, trace);
+    DMX_CHECK_LAUNCH();
+    return 0;
+}
+
 bool sk_supported(const dmx_ctx* ctx)
 {
     if (!ctx->has_grid) return false;
@@ -597,7 +944,7 @@ void sk_free(dmx_ctx* ctx)
 {
     SkewState* st = static_cast<SkewState*>(ctx->skew);
     if (!st) return;
-    cudaFree(st->Lsk); cudaFree(st->Usk); cudaFree(st->xsk); cudaFree(st->order_lo); cudaFree(st->order_up); cudaFree(st->ctl);
+    cudaFree(st->Lsk); cudaFree(st->Usk); cudaFree(st->xsk); cudaFree(st->ll); cudaFree(st->order_lo); cudaFree(st->order_up); cudaFree(st->ctl);
     if (st->trace) cudaFree(st->trace);
     delete st;
     ctx->skew = nullptr;
@@ -623,6 +970,13 @@ int sk_setup(dmx_ctx* ctx)
     DMX_CUDA(cudaMemsetAsync(st->Lsk, 0, slots * (3 * BB + (SK_NAT_RHS ? 0 : ctx->b)) * sizeof(double), ctx->stream));
     DMX_CUDA(cudaMemsetAsync(st->Usk, 0, slots * (4 * BB + ctx->b) * sizeof(double), ctx->stream));
     DMX_CUDA(cudaMalloc((void**)&st->xsk, slots * ctx->b * sizeof(double)));
+    {
+        const char* env = getenv("DMX_SK_LL");
+        st->use_ll = env ? atoi(env) : 3;      // bit 0: lower sweep, bit 1: upper sweep
+        const size_t words = (size_t)g.ntiles * g.NS * 2 * SK_TI * 2 * ctx->b;
+        DMX_CUDA(cudaMalloc((void**)&st->ll, words * sizeof(unsigned long long)));
+        DMX_CUDA(cudaMemsetAsync(st->ll, 0, words * sizeof(unsigned long long), ctx->stream));
+    }
     std::vector<int> lo(g.ntiles), up(g.ntiles);
     for (int q = 0; q < g.ntiles; ++q) lo[q] = up[q] = q;
     auto key = [&](int q) { return (q % g.ntx) + (q / g.ntx); };
@@ -672,11 +1026,22 @@ static int sk_apply_t(dmx_ctx* ctx, SkewState* st, const double* d, double* v)
         vec_skew_kernel<B><<<(unsigned)((size_t)g.ntiles * g.NS), SK_THREADS, 0, ctx->stream>>>(g, d, st->Lsk);
         DMX_CHECK_LAUNCH();
     }
-    if (int rc = sweep_launch<B, false>(ctx, st, st->Lsk, st->Usk, const_cast<double*>(d), st->order_lo, tick_lo, base_lo, prog_lo, ep_lo,
-                                        st->trace))
+    // tags of the flag-in-data sweeps: never 0 (the buffer starts zeroed), different for every sweep
+    const unsigned int tag_lo = 2 * st->ll_seq + 1, tag_up = 2 * st->ll_seq + 2;
+    st->ll_seq = (st->ll_seq + 1) % 0x7ffffff0u;
+    const bool ll_lo = (st->use_ll & 1) != 0, ll_up = (st->use_ll & 2) != 0 && SK_NAT_OUT;
+    if (ll_lo) {
+        if (int rc = sweep_launch_ll<B, false>(ctx, st, st->Lsk, st->Usk, const_cast<double*>(d), tag_lo, st->order_lo, tick_lo, base_lo, st->trace))
+            return rc;
+    } else if (int rc = sweep_launch<B, false>(ctx, st, st->Lsk, st->Usk, const_cast<double*>(d), st->order_lo, tick_lo, base_lo, prog_lo, ep_lo,
+                                               st->trace))
         return rc;
-    if (int rc = sweep_launch<B, true>(ctx, st, st->Usk, st->xsk, v, st->order_up, tick_up, base_up, prog_up, ep_up,
-                                       st->trace ? st->trace + 2 * 64 * 24 : nullptr))
+    if (ll_up) {
+        if (int rc = sweep_launch_ll<B, true>(ctx, st, st->Usk, st->xsk, v, tag_up, st->order_up, tick_up, base_up,
+                                              st->trace ? st->trace + 2 * 64 * 24 : nullptr))
+            return rc;
+    } else if (int rc = sweep_launch<B, true>(ctx, st, st->Usk, st->xsk, v, st->order_up, tick_up, base_up, prog_up, ep_up,
+                                              st->trace ? st->trace + 2 * 64 * 24 : nullptr))
         return rc;
     if (!SK_NAT_OUT) {
         vec_unskew_kernel<B><<<(unsigned)((ctx->n + 255) / 256), 256, 0, ctx->stream>>>(g, st->xsk, v);
