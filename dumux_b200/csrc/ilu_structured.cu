@@ -6,20 +6,20 @@
 // each at 256^3); here the same hyperplane order is executed WITHOUT grid barriers:
 //
 //   * the (i,j) plane is cut into 16x16 tiles, one CTA per tile, one thread per grid line (i,j); the CTA marches along
-//     k and thread (a,b) handles layer k = s - a - b at step s, so inside a tile the wavefront costs one
-//     __syncthreads per step and neighbour values travel through shared memory;
-//   * tiles depend only on their -x / -y neighbours (lower sweep; +x / +y for the upper sweep) which must run
-//     TI (TJ) steps ahead: point-to-point progress counters in global memory, published every SK_C steps, replace the
-//     grid barrier; tiles are handed out by an atomic ticket in dependency order, so waiting never deadlocks;
-//   * factors AND the vector travel in one tile-skewed stream per sweep, stream[tile][step][factor components | vector][thread]:
+//     k and thread (a,b) handles layer k = s - a - b at step s, so inside a tile the wavefront costs one named barrier
+//     among the 256 compute threads per step and neighbour values travel through shared memory;
+//   * tiles depend only on their -x / -y neighbours (lower sweep; +x / +y for the upper sweep), which must be 16 steps
+//     ahead; the boundary values travel as self-validating tagged words (see ilu_sweep_kernel) instead of behind a grid
+//     barrier; tiles are handed out by an atomic ticket in dependency order, so waiting never deadlocks;
+//   * factors AND the right-hand side travel in one tile-skewed stream per sweep, stream[tile][step][factors | rhs][thread]:
 //     what a CTA needs at step s is ONE contiguous chunk (28 KB lower, 36 KB upper for 2x2 blocks), fetched with a single
 //     cp.async.bulk (TMA, 1-D) into a shared-memory ring by a dedicated PRODUCER thread (warp 8) that re-arms a slot as soon
 //     as the 256 compute threads release it (full/empty mbarriers).  Measured on B200 (scripts/probes/stream_probe.cu): with
 //     the copy issued by a compute thread after the step's barrier an SM gets ONE copy per ~850-1100 cycles (26-34 B/clk at
-//     28 KB), with a producer thread the same ring streams 76 B/clk -- what a tile that runs alone (fill/drain of the tile
-//     wavefront) needs.  The lower sweep reads its right-hand side from the lower stream and writes its result into the vector
-//     slots of the UPPER stream; the upper sweep writes the final result into a separate skewed vector.  HBM sees long
-//     sequential streams, no index arrays at all.
+//     28 KB), with a producer thread the same ring never makes the consumer wait -- what a tile that runs alone (fill/drain
+//     of the tile wavefront) needs.  HBM sees long sequential streams, no index arrays at all;
+//   * a SYNC warp (warp 9) does everything that talks to other tiles (polling and staging the upstream boundary values),
+//     so none of that latency is on the compute threads' critical path.
 //
 // Per-row arithmetic (operation order, no FMA contraction) is that of blockILUBacksolve: columns ascending
 // (-z,-y,-x | +x,+y,+z), y -= A x per block (FieldMatrix::mmv), v = Dinv * rhs last (FieldMatrix::mv, sum from 0), so
@@ -33,22 +33,8 @@
 namespace dmx {
 
 constexpr int SK_TI = 16, SK_TJ = 16, SK_THREADS = SK_TI * SK_TJ;
-#ifndef SK_CHUNK
-#define SK_CHUNK 8
-#endif
-constexpr int SK_C = SK_CHUNK;               // steps per chunk: progress is published / awaited once per chunk
-static_assert((SK_C * (SK_TI + SK_TJ)) % 32 == 0, "halo values of a chunk are fetched by one warp");
-constexpr unsigned long long SK_EPOCH = 1ull << 20;
-#ifndef SK_NAT_RHS
-#define SK_NAT_RHS 0        // 1: lower sweep gathers its right-hand side from the natural-layout vector (no vec_skew pass); measured slower (1.75 vs 1.66 ms)
-#endif
-#ifndef SK_NAT_OUT
-#define SK_NAT_OUT 1        // upper sweep scatters its result into the natural-layout vector (no vec_unskew pass)
-#endif
-constexpr int SK_PF = 4;                     // lower sweep: right-hand sides are gathered this many steps ahead
-#ifndef SK_POLL_NS
-#define SK_POLL_NS 100       // back-off between polls of an upstream tile's progress word (148 spinning CTAs saturate its L2 slice)
-#endif
+constexpr int SK_C = 8;                      // unroll factor of the step loop (and granularity of the developer timeline)
+static_assert(SK_TI + SK_TJ == 32, "one sync-warp lane per halo value of a step");
 
 struct SkewGrid {
     int nx, ny, nz, ntx, nty, ntiles, NS;
@@ -89,26 +75,6 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar)
 }
 // barrier among the 256 compute threads only (the producer warp does not take part)
 __device__ __forceinline__ void compute_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
-__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t phase)
-{
-    uint32_t ok;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(phase)
-        : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ unsigned long long ld_acquire(const unsigned long long* p)
-{
-    unsigned long long v;
-    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
 __device__ __forceinline__ unsigned long long ld_relaxed(const unsigned long long* p)
 {
     unsigned long long v;
@@ -118,10 +84,6 @@ __device__ __forceinline__ unsigned long long ld_relaxed(const unsigned long lon
 __device__ __forceinline__ void st_relaxed(unsigned long long* p, unsigned long long v)
 {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ void st_release(unsigned long long* p, unsigned long long v)
-{
-    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
 // number of factor components (doubles) per cell: lower L_z,L_y,L_x ; upper U_x,U_y,U_z,Dinv
@@ -133,7 +95,7 @@ struct SkewLayout {
     static constexpr int VEC_DOUBLES = B * SK_THREADS;                       // one step of a skewed vector
     // the upper stream carries the lower sweep's result next to the factors; the lower sweep reads its right-hand side
     // straight from the natural-layout vector (prefetched into registers), so its stream is factors only
-    static constexpr int STEP_DOUBLES = STAGE_DOUBLES + ((UPPER || !SK_NAT_RHS) ? VEC_DOUBLES : 0);   // stream stride per step
+    static constexpr int STEP_DOUBLES = STAGE_DOUBLES + VEC_DOUBLES;         // stream stride per step: [factors | right-hand side]
     // depth of the shared-memory ring (steps in flight): 7 x 28 KB lower, 5 x 36 KB upper for 2x2 blocks
     static constexpr int S = (B == 2) ? (UPPER ? 5 : 7) : 16;
 };
@@ -243,329 +205,21 @@ __global__ void __launch_bounds__(SK_THREADS) vec_skew_kernel(SkewGrid g, const 
     if (B == 2) *reinterpret_cast<double2*>(dst) = make_double2(val[0], val[B - 1]);
     else dst[0] = val[0];
 }
-// one thread per cell: coalesced natural writes, gathered skewed reads
-template <int B>
-__global__ void __launch_bounds__(256) vec_unskew_kernel(SkewGrid g, const double* __restrict__ xsk, double* __restrict__ x)
-{
-    const size_t I = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t n = (size_t)g.nx * g.ny * g.nz;
-    if (I >= n) return;
-    const int i = (int)(I % g.nx), j = (int)((I / g.nx) % g.ny), k = (int)(I / ((size_t)g.nx * g.ny));
-    const int a = i & (SK_TI - 1), b = j & (SK_TJ - 1);
-    const int tile = (i / SK_TI) + g.ntx * (j / SK_TJ);
-    const int s = k + a + b;
-    const double* src = xsk + (((size_t)tile * g.NS + s) * SK_THREADS + (a + SK_TI * b)) * B;
-    if (B == 2) *reinterpret_cast<double2*>(x + I * 2) = *reinterpret_cast<const double2*>(src);
-    else x[I] = src[0];
-}
-
 // ------------------------------------------------------------------------------------------------------------
-// one triangular sweep.  LOWER: out <- L^-1 rhs (unit lower); the right-hand side comes from the vector slots of the lower
-// stream (written by vec_skew_kernel; SK_NAT_RHS = 1 gathers it from the natural-layout vector instead, measured slower),
-// the result goes into the vector slots of the upper stream.  UPPER: U^-1 rhs, rhs from the upper stream, result scattered
-// into the natural-layout vector `nat` (16-byte stores; the two halves of a 32-byte sector are written one step apart and
-// merge in L2 -- this replaces a separate un-skew pass) and, for the two edges a downstream tile reads, into the skewed xsk.
-//   stream : this sweep's [factors | rhs] stream
-//   out    : skewed results other tiles read back (LOWER: the upper stream, all lanes; UPPER: xsk, edge lanes only)
-// ------------------------------------------------------------------------------------------------------------
-template <int B, bool UPPER>
-__global__ void __launch_bounds__(SK_THREADS + 64, 1) ilu_sweep_kernel(SkewGrid g, const double* __restrict__ stream, double* out,
-                                                                        double* nat,
-                                                                   const int* __restrict__ order, unsigned long long* ticket_ctr,
-                                                                   unsigned long long ticket_base, unsigned long long* prog,
-                                                                   unsigned long long epoch, long long* trace)
-{
-    using LY = SkewLayout<B, UPPER>;
-    using LYU = SkewLayout<B, true>;
-    constexpr int S = LY::S;
-    // where results live: LOWER -> vector slots of the upper stream (step stride STEP_U, offset FAC_U); UPPER -> xsk
-    constexpr size_t OUT_STEP = UPPER ? (size_t)LY::VEC_DOUBLES : (size_t)LYU::STEP_DOUBLES;
-    constexpr size_t OUT_OFF = UPPER ? 0 : (size_t)LYU::STAGE_DOUBLES;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    double* stages = reinterpret_cast<double*>(smem_raw);                              // [S][factors | rhs]
-    double* sv = stages + (size_t)S * LY::STEP_DOUBLES;                                // [2][TJ+1][TI+1][B]
-    double* hbuf = sv + 2 * (SK_TJ + 1) * (SK_TI + 1) * B;                             // [2][x halo C*TJ*B | y halo C*TI*B]
-    constexpr int HBUF_DOUBLES = SK_C * (SK_TI + SK_TJ) * B;
-    uint64_t* full = reinterpret_cast<uint64_t*>(hbuf + 2 * HBUF_DOUBLES);             // [S] data landed
-    uint64_t* empty = full + S;                                                        // [S] slot released by the compute threads
-    uint64_t* ready = empty + S;                                                       // [2] halo of a chunk staged by the sync warp
-    uint64_t* done = ready + 2;                                                        // [2] chunk finished by the compute threads
-    __shared__ int s_tile;
-
-    const int t = threadIdx.x;
-    const int a = t & (SK_TI - 1), b = t >> 4;          // mirrored coordinates for UPPER
-    const int tl = UPPER ? SK_THREADS - 1 - t : t;      // lane in LOWER indexing (storage)
-    if (t == 0) {
-        const unsigned long long ticket = atomicAdd(ticket_ctr, 1ull) - ticket_base;
-        s_tile = order[(int)ticket];
-        for (int q = 0; q < S; ++q) { mbar_init(&full[q], 1); mbar_init(&empty[q], 1); }
-        for (int q = 0; q < 2; ++q) { mbar_init(&ready[q], 1); mbar_init(&done[q], 1); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    const int tile = s_tile;
-    const int ti = tile % g.ntx, tj = tile / g.ntx;
-    const int NS = g.NS;
-    const double* stream_tile = stream + (size_t)tile * NS * LY::STEP_DOUBLES;
-    // results of step s (this sweep's step index) go to "lower step" sl = UPPER ? NS-1-s : s; the LOWER sweep stores them where
-    // the upper sweep will fetch them: upper step NS-1-sl
-    auto out_step_index = [&](int sl) { return UPPER ? sl : NS - 1 - sl; };
-    double* out_tile = out + (size_t)tile * NS * OUT_STEP + OUT_OFF;
-    const int nchunks = (NS + SK_C - 1) / SK_C;
-    constexpr int HSHIFT = SK_TI - 1;       // == SK_TJ - 1
-    static_assert(SK_TI == SK_TJ, "square tiles");
-    const int tix = UPPER ? ti + 1 : ti - 1, tjy = UPPER ? tj + 1 : tj - 1;
-    const bool tilex = tix >= 0 && tix < g.ntx, tiley = tjy >= 0 && tjy < g.nty;
-
-    if (t >= SK_THREADS + 32) {
-        // ---- sync warp: everything that talks to other tiles, one chunk ahead of the compute threads ----
-        //   prepare(ch): wait until the upstream tiles are far enough, stage their boundary values of chunk ch in shared memory
-        //   publish(ch): once the compute threads finished chunk ch, make their results visible and advance this tile's progress
-        const int lane = t - (SK_THREADS + 32);
-        const unsigned long long* progx = prog + (tilex ? tix + g.ntx * tj : 0);
-        const unsigned long long* progy = prog + (tiley ? ti + g.ntx * tjy : 0);
-        auto upstream_ready = [&](int ch) {       // lane 0 only: one non-blocking look at the upstream tiles' progress words
-            const int s0 = ch * SK_C;
-            if (tilex && ld_acquire(progx) < epoch + (unsigned long long)min(s0 + SK_C + SK_TI - 1, NS)) return false;
-            if (tiley && ld_acquire(progy) < epoch + (unsigned long long)min(s0 + SK_C + SK_TJ - 1, NS)) return false;
-            return true;
-        };
-        auto stage_halo = [&](int ch) {           // all lanes
-            const int s0 = ch * SK_C;
-            double* hb = hbuf + (ch & 1) * HBUF_DOUBLES;
-#pragma unroll
-            for (int m = 0; m < SK_C * (SK_TI + SK_TJ) / 32; ++m) {
-                const int v = lane + 32 * m;
-                // values [0, C*TJ): x halo (step hc, row hl), the rest: y halo (step hc, column hl); hl mirrored for UPPER
-                const bool hx_duty = v < SK_C * SK_TJ;
-                const int hc = hx_duty ? v / SK_TJ : (v - SK_C * SK_TJ) / SK_TI;
-                const int hl = hx_duty ? v % SK_TJ : (v - SK_C * SK_TJ) % SK_TI;
-                // the upstream tile computed the wanted value TI-1 (TJ-1) steps after my step; lane on its far edge
-                const int lane_lo = hx_duty ? (SK_TI - 1) + SK_TI * hl : hl + SK_TI * (SK_TJ - 1);
-                const int hlane = UPPER ? SK_THREADS - 1 - lane_lo : lane_lo;
-                const int htile = hx_duty ? tix + g.ntx * tj : ti + g.ntx * tjy;
-                const int other = hx_duty ? tj * SK_TJ + (UPPER ? SK_TJ - 1 - hl : hl) : ti * SK_TI + (UPPER ? SK_TI - 1 - hl : hl);
-                const bool hvalid = (hx_duty ? tilex : tiley) && other < (hx_duty ? g.ny : g.nx);
-                const int s = s0 + hc;
-                const int kk = s - hl;
-                const bool ok = hvalid && kk >= 0 && kk < g.nz;
-                const int sl = UPPER ? NS - 1 - (s + HSHIFT) : s + HSHIFT;       // lower-step index of the upstream tile's step
-                const double* src = out + ((size_t)(hvalid ? htile : 0) * NS + (size_t)(ok ? out_step_index(sl) : 0)) * OUT_STEP + OUT_OFF +
-                                    (size_t)hlane * B;
-#pragma unroll
-                for (int e = 0; e < B; ++e) hb[v * B + e] = ok ? __ldcg(src + e) : 0.0;
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&ready[ch & 1]);
-        };
-        // Event loop: publish a chunk as soon as the compute threads are done with it, stage the next chunk's halo as soon as
-        // the upstream tiles allow (at most two chunks ahead of the last published one: the halo buffer is double-buffered).
-        int next_prep = 0, next_pub = 0;
-        while (next_pub < nchunks) {
-            int act = 0;       // bit 0: publish next_pub, bit 1: stage next_prep
-            if (lane == 0) {
-                if (mbar_test(&done[next_pub & 1], (uint32_t)((next_pub >> 1) & 1))) act |= 1;
-                if (next_prep < nchunks && next_prep <= next_pub + 1 && upstream_ready(next_prep)) act |= 2;
-            }
-            act = __shfl_sync(0xffffffffu, act, 0);
-            if (act & 2) { stage_halo(next_prep); ++next_prep; }
-            if (act & 1) {
-                if (lane == 0) st_release(prog + tile, epoch + (unsigned long long)min((next_pub + 1) * SK_C, NS));
-                ++next_pub;
-            }
-            if (!act) __nanosleep(SK_POLL_NS);
-        }
-        return;
-    }
-    if (t >= SK_THREADS) {
-        // ---- producer: one bulk copy per step, as far ahead as the ring allows ----
-        if (t == SK_THREADS) {
-            constexpr uint32_t BYTES = LY::STEP_DOUBLES * sizeof(double);
-            for (int s = 0; s < NS; ++s) {
-                const int q = s % S;
-                if (s >= S) mbar_wait(&empty[q], (uint32_t)(((s / S) - 1) & 1));
-                mbar_expect_tx(&full[q], BYTES);
-                bulk_g2s(stages + (size_t)q * LY::STEP_DOUBLES, stream_tile + (size_t)s * LY::STEP_DOUBLES, BYTES, &full[q]);
-            }
-        }
-        return;
-    }
-
-    // ---- compute threads: actual cell line of this thread ----
-    const int i = ti * SK_TI + (UPPER ? SK_TI - 1 - a : a);
-    const int j = tj * SK_TJ + (UPPER ? SK_TJ - 1 - b : b);
-    const bool line = i < g.nx && j < g.ny;
-    const bool depx = UPPER ? (i + 1 < g.nx) : (i > 0);          // a -x (+x) neighbour cell exists
-    const bool depy = UPPER ? (j + 1 < g.ny) : (j > 0);
-
-    double vprev[B];
-#pragma unroll
-    for (int e = 0; e < B; ++e) vprev[e] = 0.0;
-    // natural-layout index of this thread's cell at wavefront distance kk (layer kk for the lower sweep, nz-1-kk for the upper)
-    auto cell_index = [&](int kk) { return (size_t)i + (size_t)g.nx * ((size_t)j + (size_t)g.ny * (size_t)(UPPER ? g.nz - 1 - kk : kk)); };
-    static_assert(SK_C % SK_PF == 0, "prefetch slots are indexed statically inside the unrolled chunk");
-    double rq[SK_PF][B];       // LOWER: right-hand sides of the next SK_PF steps
-#pragma unroll
-    for (int q = 0; q < SK_PF; ++q) {
-#pragma unroll
-        for (int e = 0; e < B; ++e) rq[q][e] = 0.0;
-        if (!UPPER && SK_NAT_RHS) {
-            const int kn = q - a - b;
-            if (line && kn >= 0 && kn < g.nz) {
-#pragma unroll
-                for (int e = 0; e < B; ++e) rq[q][e] = __ldg(nat + cell_index(kn) * B + e);
-            }
-        }
-    }
-
-    long long* tr = nullptr;       // optional timeline (developer diagnostic): tiles ticketed 0 and ntiles/2
-    if (trace && t == 0) {
-        if (tile == order[0]) tr = trace;
-        else if (tile == order[g.ntiles / 2]) tr = trace + 24 * 64;
-    }
-#define SK_STAMP(slot) do { if (tr && s0 / SK_C < 64) tr[(s0 / SK_C) * 24 + (slot)] = clock64(); } while (0)
-    for (int s0 = 0; s0 < NS; s0 += SK_C) {
-        // ---- chunk head: the sync warp has staged the upstream tiles' boundary values of this chunk ----
-        const int ch = s0 / SK_C;
-        SK_STAMP(0);
-        mbar_wait(&ready[ch & 1], (uint32_t)((ch >> 1) & 1));
-        SK_STAMP(1);
-        const double* hx = hbuf + (ch & 1) * HBUF_DOUBLES;
-        const double* hy = hx + SK_C * SK_TJ * B;
-        SK_STAMP(2);
-
-#pragma unroll
-        for (int c = 0; c < SK_C; ++c) {
-            const int s = s0 + c;
-            if (s < NS) {       // uniform
-                const int stage = s % S;
-                mbar_wait(&full[stage], (uint32_t)((s / S) & 1));
-                SK_STAMP(3 + 2 * c);
-                const double* f = stages + (size_t)stage * LY::STEP_DOUBLES;
-                const int kk = s - a - b;
-                const bool active = line && kk >= 0 && kk < g.nz;
-                const int rb = (s + 1) & 1, wb = s & 1;       // buffer written at step s-1 / written now
-                double* svw = sv + ((wb * (SK_TJ + 1) + (b + 1)) * (SK_TI + 1) + (a + 1)) * B;
-                if (active) {
-                    double r[B];
-#pragma unroll
-                    for (int e = 0; e < B; ++e) r[e] = (UPPER || !SK_NAT_RHS) ? f[LY::STAGE_DOUBLES + tl * B + e] : rq[c % SK_PF][e];
-                    double xv[B], yv[B];
-                    const double* xs = (a == 0) ? hx + (c * SK_TJ + b) * B : sv + ((rb * (SK_TJ + 1) + (b + 1)) * (SK_TI + 1) + a) * B;
-                    const double* ys = (b == 0) ? hy + (c * SK_TI + a) * B : sv + ((rb * (SK_TJ + 1) + b) * (SK_TI + 1) + (a + 1)) * B;
-#pragma unroll
-                    for (int e = 0; e < B; ++e) { xv[e] = xs[e]; yv[e] = ys[e]; }
-                    double blk[LY::NBLK][B * B];
-                    if (B == 2) {
-#pragma unroll
-                        for (int q = 0; q < LY::NBLK; ++q)
-#pragma unroll
-                            for (int rr = 0; rr < 2; ++rr) {
-                                const double2 w = reinterpret_cast<const double2*>(f)[(q * 2 + rr) * SK_THREADS + t];
-                                blk[q][rr * 2] = w.x;
-                                blk[q][rr * 2 + 1] = w.y;
-                            }
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < LY::NBLK; ++q) blk[q][0] = f[q * SK_THREADS + t];
-                    }
-                    const bool depz = kk > 0;
-                    if (!UPPER) {
-                        // columns ascending: -z, -y, -x   (rhs -= A_ij v_j, FieldMatrix::mmv order)
-                        if (depz) {
-#pragma unroll
-                            for (int rr = 0; rr < B; ++rr)
-#pragma unroll
-                                for (int cc = 0; cc < B; ++cc) r[rr] -= blk[0][rr * B + cc] * vprev[cc];
-                        }
-                        if (depy) {
-#pragma unroll
-                            for (int rr = 0; rr < B; ++rr)
-#pragma unroll
-                                for (int cc = 0; cc < B; ++cc) r[rr] -= blk[1][rr * B + cc] * yv[cc];
-                        }
-                        if (depx) {
-#pragma unroll
-                            for (int rr = 0; rr < B; ++rr)
-#pragma unroll
-                                for (int cc = 0; cc < B; ++cc) r[rr] -= blk[2][rr * B + cc] * xv[cc];
-                        }
-                    } else {
-                        // columns ascending: +x, +y, +z, then v = Dinv * rhs (sum from 0)
-                        if (depx) {
-#pragma unroll
-                            for (int rr = 0; rr < B; ++rr)
-#pragma unroll
-                                for (int cc = 0; cc < B; ++cc) r[rr] -= blk[0][rr * B + cc] * xv[cc];
-                        }
-                        if (depy) {
-#pragma unroll
-                            for (int rr = 0; rr < B; ++rr)
-#pragma unroll
-                                for (int cc = 0; cc < B; ++cc) r[rr] -= blk[1][rr * B + cc] * yv[cc];
-                        }
-                        if (depz) {
-#pragma unroll
-                            for (int rr = 0; rr < B; ++rr)
-#pragma unroll
-                                for (int cc = 0; cc < B; ++cc) r[rr] -= blk[2][rr * B + cc] * vprev[cc];
-                        }
-                        double o[B];
-#pragma unroll
-                        for (int rr = 0; rr < B; ++rr) {
-                            double acc = 0.0;
-#pragma unroll
-                            for (int cc = 0; cc < B; ++cc) acc += blk[3][rr * B + cc] * r[cc];
-                            o[rr] = acc;
-                        }
-#pragma unroll
-                        for (int e = 0; e < B; ++e) r[e] = o[e];
-                    }
-#pragma unroll
-                    for (int e = 0; e < B; ++e) { vprev[e] = r[e]; svw[e] = r[e]; }
-                    const int sl = UPPER ? NS - 1 - s : s;
-                    if (!UPPER || !SK_NAT_OUT || a == SK_TI - 1 || b == SK_TJ - 1) {
-                        double* dstp = out_tile + (size_t)out_step_index(sl) * OUT_STEP + (size_t)tl * B;
-                        if (B == 2) __stcg(reinterpret_cast<double2*>(dstp), make_double2(r[0], r[B - 1]));
-                        else __stcg(dstp, r[0]);
-                    }
-                    if (UPPER && SK_NAT_OUT) {
-                        double* dn = nat + cell_index(kk) * B;
-                        if (B == 2) *reinterpret_cast<double2*>(dn) = make_double2(r[0], r[B - 1]);
-                        else dn[0] = r[0];
-                    }
-                }
-                if (!UPPER && SK_NAT_RHS) {
-                    // right-hand side of step s + SK_PF
-                    const int kn = s + SK_PF - a - b;
-#pragma unroll
-                    for (int e = 0; e < B; ++e) rq[c % SK_PF][e] = 0.0;
-                    if (line && kn >= 0 && kn < g.nz) {
-                        const double* sn = nat + cell_index(kn) * B;
-                        if (B == 2) {
-                            const double2 wv = __ldg(reinterpret_cast<const double2*>(sn));
-                            rq[c % SK_PF][0] = wv.x; rq[c % SK_PF][B - 1] = wv.y;
-                        } else rq[c % SK_PF][0] = __ldg(sn);
-                    }
-                }
-                compute_barrier();
-                SK_STAMP(4 + 2 * c);
-                if (t == 0) {
-                    mbar_arrive(&empty[stage]);
-                    if (c == SK_C - 1 || s == NS - 1) mbar_arrive(&done[ch & 1]);
-                }
-            }
-        }
-        SK_STAMP(19);
-    }
-#undef SK_STAMP
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// Variant with flag-in-data halo exchange (SK_LL): the edge threads of a tile publish their values as 64-bit words that carry a
-// tag next to half a double (8-byte stores are single-copy atomic, so a word is valid as soon as its tag matches); the sync warp
-// of the downstream tile polls exactly the words it needs, step by step.  No progress counters, no release fences, and the
-// tile-to-tile lag is the geometric minimum of 16 steps instead of 23.
+// One triangular sweep.  LOWER: L^-1 rhs (unit lower); the right-hand side sits in the vector slots of the lower stream
+// (vec_skew_kernel), the result goes into the vector slots of the UPPER stream (`out`).  UPPER: U^-1 rhs, result scattered
+// into the natural-layout vector (`out`; 16-byte stores -- the two halves of a 32-byte sector are written one step apart and
+// merge in L2, which replaces a separate un-skew pass).
+//
+// Tile-to-tile halo exchange is flag-in-data: the two edge lines of a tile publish every value as 64-bit words that carry a
+// 32-bit tag next to half a double (strong 8-byte stores are single-copy atomic, so a word is valid as soon as its tag
+// matches; the tag changes with every sweep); the sync warp of the downstream tile polls exactly the words it needs, two steps
+// per batch.  No progress counters, no release fences, and the tile-to-tile lag is the geometric minimum of 16 steps.
+// Measured and rejected on the way (B200, 256^3, ms per ILU application): progress words + st.release published by thread 0
+// every 8 steps with the TMA ring issued by thread 0: 1.92; + producer thread: 1.81; + sync warp (polling, halo staging,
+// publication off the compute threads): 1.68; 4-step chunks: slower (the release fence cannot keep up); lower sweep gathering
+// its right-hand side from the natural layout: slower than the skew pass; flag-in-data with dependent polls: 2.79; with
+// batched polls: 1.39.
 // ------------------------------------------------------------------------------------------------------------
 #ifndef SK_RING
 #define SK_RING 8
@@ -574,19 +228,19 @@ __global__ void __launch_bounds__(SK_THREADS + 64, 1) ilu_sweep_kernel(SkewGrid 
 #define SK_BATCH 2       // measured at 256^3: 2 -> 1.39 ms per apply, 4 -> 1.42, 8 -> 1.57
 #endif
 constexpr int SK_R = SK_RING;                // halo ring depth in steps
-constexpr int SK_NB = SK_BATCH;                     // steps whose halo words the sync warp requests together
+constexpr int SK_NB = SK_BATCH;              // steps whose halo words the sync warp requests together
 template <int B, bool UPPER>
-__global__ void __launch_bounds__(SK_THREADS + 64, 1) ilu_sweep_ll_kernel(SkewGrid g, const double* __restrict__ stream, double* out,
-                                                                           double* nat, unsigned long long* ll, unsigned int tag,
+__global__ void __launch_bounds__(SK_THREADS + 64, 1) ilu_sweep_kernel(SkewGrid g, const double* __restrict__ stream, double* out,
+                                                                        unsigned long long* ll, unsigned int tag,
                                                                            const int* __restrict__ order, unsigned long long* ticket_ctr,
                                                                            unsigned long long ticket_base, long long* trace)
 {
     using LY = SkewLayout<B, UPPER>;
     using LYU = SkewLayout<B, true>;
     constexpr int S = LY::S;
-    // where results live: LOWER -> vector slots of the upper stream (step stride STEP_U, offset FAC_U); UPPER -> xsk
-    constexpr size_t OUT_STEP = UPPER ? (size_t)LY::VEC_DOUBLES : (size_t)LYU::STEP_DOUBLES;
-    constexpr size_t OUT_OFF = UPPER ? 0 : (size_t)LYU::STAGE_DOUBLES;
+    // LOWER: results go to the vector slots of the upper stream (step stride STEP_U, offset FAC_U)
+    constexpr size_t OUT_STEP = (size_t)LYU::STEP_DOUBLES;
+    constexpr size_t OUT_OFF = (size_t)LYU::STAGE_DOUBLES;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* stages = reinterpret_cast<double*>(smem_raw);                              // [S][factors | rhs]
     double* sv = stages + (size_t)S * LY::STEP_DOUBLES;                                // [2][TJ+1][TI+1][B]
@@ -615,9 +269,8 @@ __global__ void __launch_bounds__(SK_THREADS + 64, 1) ilu_sweep_ll_kernel(SkewGr
     const double* stream_tile = stream + (size_t)tile * NS * LY::STEP_DOUBLES;
     // results of step s (this sweep's step index) go to "lower step" sl = UPPER ? NS-1-s : s; the LOWER sweep stores them where
     // the upper sweep will fetch them: upper step NS-1-sl
-    auto out_step_index = [&](int sl) { return UPPER ? sl : NS - 1 - sl; };
+    auto out_step_index = [&](int sl) { return NS - 1 - sl; };
     double* out_tile = out + (size_t)tile * NS * OUT_STEP + OUT_OFF;
-    const int nchunks = (NS + SK_C - 1) / SK_C;
     constexpr int HSHIFT = SK_TI - 1;       // == SK_TJ - 1
     static_assert(SK_TI == SK_TJ, "square tiles");
     const int tix = UPPER ? ti + 1 : ti - 1, tjy = UPPER ? tj + 1 : tj - 1;
@@ -706,21 +359,6 @@ __global__ void __launch_bounds__(SK_THREADS + 64, 1) ilu_sweep_ll_kernel(SkewGr
     for (int e = 0; e < B; ++e) vprev[e] = 0.0;
     // natural-layout index of this thread's cell at wavefront distance kk (layer kk for the lower sweep, nz-1-kk for the upper)
     auto cell_index = [&](int kk) { return (size_t)i + (size_t)g.nx * ((size_t)j + (size_t)g.ny * (size_t)(UPPER ? g.nz - 1 - kk : kk)); };
-    static_assert(SK_C % SK_PF == 0, "prefetch slots are indexed statically inside the unrolled chunk");
-    double rq[SK_PF][B];       // LOWER: right-hand sides of the next SK_PF steps
-#pragma unroll
-    for (int q = 0; q < SK_PF; ++q) {
-#pragma unroll
-        for (int e = 0; e < B; ++e) rq[q][e] = 0.0;
-        if (!UPPER && SK_NAT_RHS) {
-            const int kn = q - a - b;
-            if (line && kn >= 0 && kn < g.nz) {
-#pragma unroll
-                for (int e = 0; e < B; ++e) rq[q][e] = __ldg(nat + cell_index(kn) * B + e);
-            }
-        }
-    }
-
     long long* tr = nullptr;       // optional timeline (developer diagnostic): tiles ticketed 0 and ntiles/2
     if (trace && t == 0) {
         if (tile == order[0]) tr = trace;
@@ -754,7 +392,7 @@ __global__ void __launch_bounds__(SK_THREADS + 64, 1) ilu_sweep_ll_kernel(SkewGr
                 if (active) {
                     double r[B];
 #pragma unroll
-                    for (int e = 0; e < B; ++e) r[e] = (UPPER || !SK_NAT_RHS) ? f[LY::STAGE_DOUBLES + tl * B + e] : rq[c % SK_PF][e];
+                    for (int e = 0; e < B; ++e) r[e] = f[LY::STAGE_DOUBLES + tl * B + e];
                     double xv[B], yv[B];
                     const double* xs = (a == 0) ? hx + b * B : sv + ((rb * (SK_TJ + 1) + (b + 1)) * (SK_TI + 1) + a) * B;
                     const double* ys = (b == 0) ? hy + a * B : sv + ((rb * (SK_TJ + 1) + b) * (SK_TI + 1) + (a + 1)) * B;
@@ -855,22 +493,9 @@ __global__ void __launch_bounds__(SK_THREADS + 64, 1) ilu_sweep_ll_kernel(SkewGr
                         }
                     }
                     if (UPPER) {
-                        double* dn = nat + cell_index(kk) * B;
+                        double* dn = out + cell_index(kk) * B;
                         if (B == 2) *reinterpret_cast<double2*>(dn) = make_double2(r[0], r[B - 1]);
                         else dn[0] = r[0];
-                    }
-                }
-                if (!UPPER && SK_NAT_RHS) {
-                    // right-hand side of step s + SK_PF
-                    const int kn = s + SK_PF - a - b;
-#pragma unroll
-                    for (int e = 0; e < B; ++e) rq[c % SK_PF][e] = 0.0;
-                    if (line && kn >= 0 && kn < g.nz) {
-                        const double* sn = nat + cell_index(kn) * B;
-                        if (B == 2) {
-                            const double2 wv = __ldg(reinterpret_cast<const double2*>(sn));
-                            rq[c % SK_PF][0] = wv.x; rq[c % SK_PF][B - 1] = wv.y;
-                        } else rq[c % SK_PF][0] = __ldg(sn);
                     }
                 }
                 compute_barrier();
@@ -892,48 +517,26 @@ __global__ void __launch_bounds__(SK_THREADS + 64, 1) ilu_sweep_ll_kernel(SkewGr
 struct SkewState {
     SkewGrid g{};
     int b = 0;
-    double *Lsk = nullptr, *Usk = nullptr, *xsk = nullptr;
+    double *Lsk = nullptr, *Usk = nullptr;
     int *order_lo = nullptr, *order_up = nullptr;
-    unsigned long long* ctl = nullptr;       // [0],[1]: tickets lower/upper; [2 .. 2+ntiles): prog lower; then prog upper
+    unsigned long long* ctl = nullptr;       // [0],[1]: tile tickets of the lower / upper sweep
     unsigned long long seq_lo = 0, seq_up = 0;
     long long* trace = nullptr;            // 2 kernels x 2 tiles x 64 chunks x 24 stamps (DMX_SK_TRACE=1)
     unsigned long long* ll = nullptr;      // flag-in-data halo words [tile][step][dir 2][edge 16][2*b]
     unsigned int ll_seq = 0;               // tag counter of the flag-in-data sweeps
-    int use_ll = 3;                        // DMX_SK_LL: bit 0 lower / bit 1 upper sweep with flag-in-data halos (0: progress counters)
 };
 
 template <int B, bool UPPER>
-static size_t sweep_smem()
-{
-    using LY = SkewLayout<B, UPPER>;
-    return ((size_t)LY::S * LY::STEP_DOUBLES + 2 * (SK_TJ + 1) * (SK_TI + 1) * B + 2 * SK_C * (SK_TI + SK_TJ) * B) * sizeof(double) +
-           (2 * LY::S + 4) * sizeof(uint64_t);
-}
-
-template <int B, bool UPPER>
-static int sweep_launch(dmx_ctx* ctx, SkewState* st, const double* stream, double* out, double* nat, const int* order, unsigned long long* tick,
-                        unsigned long long base, unsigned long long* prog, unsigned long long epoch, long long* trace)
-{
-    const SkewGrid& g = st->g;
-    auto kern = ilu_sweep_kernel<B, UPPER>;
-    const size_t smem = sweep_smem<B, UPPER>();
-    DMX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<g.ntiles, SK_THREADS + 64, smem, ctx->stream>>>(g, stream, out, nat, order, tick, base, prog, epoch, trace);
-    DMX_CHECK_LAUNCH();
-    return 0;
-}
-
-template <int B, bool UPPER>
-static int sweep_launch_ll(dmx_ctx* ctx, SkewState* st, const double* stream, double* out, double* nat, unsigned int tag, const int* order,
+static int sweep_launch_ll(dmx_ctx* ctx, SkewState* st, const double* stream, double* out, unsigned int tag, const int* order,
                            unsigned long long* tick, unsigned long long base, long long* trace)
 {
     using LY = SkewLayout<B, UPPER>;
     const SkewGrid& g = st->g;
-    auto kern = ilu_sweep_ll_kernel<B, UPPER>;
+    auto kern = ilu_sweep_kernel<B, UPPER>;
     const size_t smem = ((size_t)LY::S * LY::STEP_DOUBLES + 2 * (SK_TJ + 1) * (SK_TI + 1) * B + SK_R * (SK_TI + SK_TJ) * B) * sizeof(double) +
                         (2 * LY::S + 2 * SK_R) * sizeof(uint64_t);
     DMX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<g.ntiles, SK_THREADS + 64, smem, ctx->stream>>>(g, stream, out, nat, st->ll, tag, order, tick, base, trace);
+    kern<<<g.ntiles, SK_THREADS + 64, smem, ctx->stream>>>(g, stream, out, st->ll, tag, order, tick, base, trace);
     DMX_CHECK_LAUNCH();
     return 0;
 }
@@ -950,7 +553,7 @@ void sk_free(dmx_ctx* ctx)
 {
     SkewState* st = static_cast<SkewState*>(ctx->skew);
     if (!st) return;
-    cudaFree(st->Lsk); cudaFree(st->Usk); cudaFree(st->xsk); cudaFree(st->ll); cudaFree(st->order_lo); cudaFree(st->order_up); cudaFree(st->ctl);
+    cudaFree(st->Lsk); cudaFree(st->Usk); cudaFree(st->ll); cudaFree(st->order_lo); cudaFree(st->order_up); cudaFree(st->ctl);
     if (st->trace) cudaFree(st->trace);
     delete st;
     ctx->skew = nullptr;
@@ -971,14 +574,11 @@ int sk_setup(dmx_ctx* ctx)
     const int BB = ctx->b * ctx->b;
     const size_t slots = (size_t)g.ntiles * g.NS * SK_THREADS;
     // streams [factors | vector] per step: the vector slots of Lsk hold the right-hand side, those of Usk the lower sweep's result
-    DMX_CUDA(cudaMalloc((void**)&st->Lsk, slots * (3 * BB + (SK_NAT_RHS ? 0 : ctx->b)) * sizeof(double)));
+    DMX_CUDA(cudaMalloc((void**)&st->Lsk, slots * (3 * BB + ctx->b) * sizeof(double)));
     DMX_CUDA(cudaMalloc((void**)&st->Usk, slots * (4 * BB + ctx->b) * sizeof(double)));
-    DMX_CUDA(cudaMemsetAsync(st->Lsk, 0, slots * (3 * BB + (SK_NAT_RHS ? 0 : ctx->b)) * sizeof(double), ctx->stream));
+    DMX_CUDA(cudaMemsetAsync(st->Lsk, 0, slots * (3 * BB + ctx->b) * sizeof(double), ctx->stream));
     DMX_CUDA(cudaMemsetAsync(st->Usk, 0, slots * (4 * BB + ctx->b) * sizeof(double), ctx->stream));
-    DMX_CUDA(cudaMalloc((void**)&st->xsk, slots * ctx->b * sizeof(double)));
     {
-        const char* env = getenv("DMX_SK_LL");
-        st->use_ll = env ? atoi(env) : 3;      // bit 0: lower sweep, bit 1: upper sweep
         const size_t words = (size_t)g.ntiles * g.NS * 2 * SK_TI * 2 * ctx->b;
         DMX_CUDA(cudaMalloc((void**)&st->ll, words * sizeof(unsigned long long)));
         DMX_CUDA(cudaMemsetAsync(st->ll, 0, words * sizeof(unsigned long long), ctx->stream));
@@ -992,8 +592,8 @@ int sk_setup(dmx_ctx* ctx)
     DMX_CUDA(cudaMalloc((void**)&st->order_up, g.ntiles * sizeof(int)));
     DMX_CUDA(cudaMemcpy(st->order_lo, lo.data(), g.ntiles * sizeof(int), cudaMemcpyHostToDevice));
     DMX_CUDA(cudaMemcpy(st->order_up, up.data(), g.ntiles * sizeof(int), cudaMemcpyHostToDevice));
-    DMX_CUDA(cudaMalloc((void**)&st->ctl, (2 + 2 * (size_t)g.ntiles) * sizeof(unsigned long long)));
-    DMX_CUDA(cudaMemset(st->ctl, 0, (2 + 2 * (size_t)g.ntiles) * sizeof(unsigned long long)));
+    DMX_CUDA(cudaMalloc((void**)&st->ctl, 2 * sizeof(unsigned long long)));
+    DMX_CUDA(cudaMemset(st->ctl, 0, 2 * sizeof(unsigned long long)));
     {
         const char* env = getenv("DMX_SK_TRACE");
         if (env && env[0] == '1') {
@@ -1022,38 +622,17 @@ static int sk_apply_t(dmx_ctx* ctx, SkewState* st, const double* d, double* v)
     const SkewGrid& g = st->g;
     unsigned long long* tick_lo = st->ctl;
     unsigned long long* tick_up = st->ctl + 1;
-    unsigned long long* prog_lo = st->ctl + 2;
-    unsigned long long* prog_up = st->ctl + 2 + g.ntiles;
-    const unsigned long long base_lo = st->seq_lo * (unsigned long long)g.ntiles, ep_lo = (st->seq_lo + 1) * SK_EPOCH;
-    const unsigned long long base_up = st->seq_up * (unsigned long long)g.ntiles, ep_up = (st->seq_up + 1) * SK_EPOCH;
+    const unsigned long long base_lo = st->seq_lo * (unsigned long long)g.ntiles;
+    const unsigned long long base_up = st->seq_up * (unsigned long long)g.ntiles;
     st->seq_lo++;
     st->seq_up++;
-    if (!SK_NAT_RHS) {
-        vec_skew_kernel<B><<<(unsigned)((size_t)g.ntiles * g.NS), SK_THREADS, 0, ctx->stream>>>(g, d, st->Lsk);
-        DMX_CHECK_LAUNCH();
-    }
-    // tags of the flag-in-data sweeps: never 0 (the buffer starts zeroed), different for every sweep
+    // tags of the halo words: never 0 (the buffer starts zeroed), different for every sweep
     const unsigned int tag_lo = 2 * st->ll_seq + 1, tag_up = 2 * st->ll_seq + 2;
     st->ll_seq = (st->ll_seq + 1) % 0x7ffffff0u;
-    const bool ll_lo = (st->use_ll & 1) != 0, ll_up = (st->use_ll & 2) != 0 && SK_NAT_OUT;
-    if (ll_lo) {
-        if (int rc = sweep_launch_ll<B, false>(ctx, st, st->Lsk, st->Usk, const_cast<double*>(d), tag_lo, st->order_lo, tick_lo, base_lo, st->trace))
-            return rc;
-    } else if (int rc = sweep_launch<B, false>(ctx, st, st->Lsk, st->Usk, const_cast<double*>(d), st->order_lo, tick_lo, base_lo, prog_lo, ep_lo,
-                                               st->trace))
-        return rc;
-    if (ll_up) {
-        if (int rc = sweep_launch_ll<B, true>(ctx, st, st->Usk, st->xsk, v, tag_up, st->order_up, tick_up, base_up,
-                                              st->trace ? st->trace + 2 * 64 * 24 : nullptr))
-            return rc;
-    } else if (int rc = sweep_launch<B, true>(ctx, st, st->Usk, st->xsk, v, st->order_up, tick_up, base_up, prog_up, ep_up,
-                                              st->trace ? st->trace + 2 * 64 * 24 : nullptr))
-        return rc;
-    if (!SK_NAT_OUT) {
-        vec_unskew_kernel<B><<<(unsigned)((ctx->n + 255) / 256), 256, 0, ctx->stream>>>(g, st->xsk, v);
-        DMX_CHECK_LAUNCH();
-    }
-    return 0;
+    vec_skew_kernel<B><<<(unsigned)((size_t)g.ntiles * g.NS), SK_THREADS, 0, ctx->stream>>>(g, d, st->Lsk);
+    DMX_CHECK_LAUNCH();
+    if (int rc = sweep_launch_ll<B, false>(ctx, st, st->Lsk, st->Usk, tag_lo, st->order_lo, tick_lo, base_lo, st->trace)) return rc;
+    return sweep_launch_ll<B, true>(ctx, st, st->Usk, v, tag_up, st->order_up, tick_up, base_up, st->trace ? st->trace + 2 * 64 * 24 : nullptr);
 }
 
 int sk_apply(dmx_ctx* ctx, const double* d, double* v)
