@@ -250,9 +250,8 @@ class Engine:
         if spec.source is not None:
             self._check(L.dmx_set_source(self.h, self.localize_cells(spec.source)))
         if getattr(spec, "volume_flux", None) is not None:
-            if self.nranks != 1:
-                raise DmxError("tracer transport: single-GPU only in this round")
-            self._check(L.dmx_set_volume_flux(self.h, np.ascontiguousarray(spec.volume_flux, dtype=np.float64).reshape(-1)))
+            # slab-decomposed runs: per-cell fluxes of the local box incl. overlap, like every other per-cell array
+            self._check(L.dmx_set_volume_flux(self.h, np.ascontiguousarray(self.localize_cells(spec.volume_flux), dtype=np.float64).reshape(-1)))
             self._check(L.dmx_set_tracer(self.h, int(spec.implicit)))
 
     def localize_cells(self, a):

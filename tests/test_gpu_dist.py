@@ -122,3 +122,85 @@ def test_slab_decomposed_newton_step_matches_cpu_reference(world):
     # global norm = sqrt(sum of owned squares)
     owned = D.gather_owned([ref[r]["res"] for r in range(world)], CELLS, world, 2)
     assert abs(got[0]["norm"] - np.linalg.norm(owned)) <= 1e-12 * np.linalg.norm(owned)
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# tracer transport (BASELINE config 5), slab-decomposed: explicit steps on 2 GPUs against the single-domain CPU oracle
+# ------------------------------------------------------------------------------------------------------------------------
+TRACER_CELLS = (18, 14, 20)
+TRACER_STEPS = 12
+
+
+def _tracer_problem():
+    from dumux_b200 import problems
+    from oracle.oracle_py import Oracle
+    ps = problems.onep_tracer_pressure(TRACER_CELLS)
+    n = int(np.prod(TRACER_CELLS))
+    rng = np.random.RandomState(11)
+    ctr = problems.cell_centers(TRACER_CELLS, ps.lower, ps.upper)
+    p = 1.0e5 * (1.1 - 0.1 * ctr[:, 2]) + rng.uniform(-20.0, 20.0, size=n)       # mostly upward flow + noise
+    vf = Oracle(ps).volume_flux(p)
+    ts = problems.tracer_transport(TRACER_CELLS, vf, dt=0.01)      # explicit Euler: below the CFL limit of the noisy field
+    ts.initial[:, 0] = rng.uniform(0.0, 2e-11, size=n)
+    return ts
+
+
+def _tracer_worker(rank, world, uid, q):
+    try:
+        from dumux_b200 import binding as B
+        from dumux_b200 import problems
+        ts = _tracer_problem()
+        eng = B.Engine(ts, device=rank, nccl_uid=uid, rank=rank, nranks=world)
+        lo, hi, b0, b1 = problems.slab_partition(TRACER_CELLS[2], world, rank)
+        nf = TRACER_CELLS[0] * TRACER_CELLS[1]
+        x0 = ts.initial.reshape(TRACER_CELLS[2], nf)[lo:hi].reshape(-1)
+        eng.upload(B.VEC_CUR, x0)
+        eng.upload(B.VEC_PREV, x0)
+        prm = eng.newton_params(lin_reduction=1e-13)
+        for _ in range(TRACER_STEPS):
+            st, its, shift, a, s, u = eng.newton_step(prm)
+            assert st == 0
+            eng.advance_timestep()
+        x = eng.download(B.VEC_CUR).reshape(hi - lo, nf)
+        q.put((rank, {"x": x[b0 - lo:b1 - lo].copy(), "overlap_lo": x[0].copy(), "range": (lo, hi, b0, b1)}))
+        eng.close()
+    except BaseException:      # noqa: BLE001
+        import traceback
+        q.put((rank, {"error": traceback.format_exc()}))
+        raise
+
+
+def test_slab_decomposed_tracer_matches_single_domain_oracle():
+    import torch
+    world = 2
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs (run under gpurun --gpus {world})")
+    import torch.multiprocessing as mp
+    from dumux_b200 import binding as B
+    from oracle.oracle_py import Oracle
+    ts = _tracer_problem()
+    o = Oracle(ts)
+    x = ts.initial.ravel().copy()
+    for _ in range(TRACER_STEPS):
+        r, j = o.assemble(x, x)
+        dx, st, its, red = o.solve(j, r, reduction=1e-13)
+        assert st == 0
+        x = x - dx
+    uid = B.Engine.nccl_unique_id()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_tracer_worker, args=(r, world, uid, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=600) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+    nf = TRACER_CELLS[0] * TRACER_CELLS[1]
+    ref = x.reshape(TRACER_CELLS[2], nf)
+    for r in range(world):
+        assert "error" not in got[r], got[r].get("error")
+        lo, hi, b0, b1 = got[r]["range"]
+        assert np.abs(got[r]["x"] - ref[b0:b1]).max() <= 1e-12 * np.abs(ref).max()
+        # the overlap layer carries the owner's values after every step (copyOwnerToAll inside the solve)
+        assert np.abs(got[r]["overlap_lo"] - ref[lo]).max() <= 1e-12 * np.abs(ref).max()
+    assert np.abs(ref - ts.initial.reshape(TRACER_CELLS[2], nf)).max() > 1e-13       # the field really moved
