@@ -130,3 +130,17 @@ def test_tile_kernel_chunks_bit_identical(engine_factory, cells, law):
     assert rerr <= 1e-13 and jerr <= RTOL, (rerr, jerr)
     assert np.array_equal(res_g, res_o)
     assert np.array_equal(jac_g, jac_o), int((jac_g != jac_o).sum())
+
+
+def test_one_dimensional_grid(engine_factory):
+    """dim = 1 instantiation of the tile kernel and the structured solver path (YaspGrid<1>): assembly bit-identical, the
+    stationary solve reproduces the oracle."""
+    spec = problems.onep_incompressible((40,))
+    cur = _perturbed(spec, 6, dp=1e4)
+    rerr, jerr, (res_o, jac_o, res_g, jac_g) = _compare(spec, engine_factory, cur, None)
+    assert np.array_equal(res_g, res_o) and np.array_equal(jac_g, jac_o)
+    o = Oracle(spec)
+    xo, sto, ito, redo = o.solve(jac_o, res_o, reduction=1e-12)
+    e = engine_factory(spec)
+    xg, stg, itg, redg = e.solve(jac_o, res_o, reduction=1e-12)
+    assert sto == 0 and stg == 0 and np.linalg.norm(xg - xo) <= 1e-10 * np.linalg.norm(xo)
