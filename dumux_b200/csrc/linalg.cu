@@ -192,11 +192,22 @@ __global__ void __launch_bounds__(RED_THREADS) axpy2_norm_kernel(size_t len, int
 }
 // first half step of BiCGSTAB: r += -alpha*v ; partial ||r||^2.  The matching x += alpha*y is deferred to the second half
 // step (x is not needed in between), which saves one read and one write of x per iteration.
-__global__ void __launch_bounds__(RED_THREADS) axpy_r_norm_kernel(size_t len, int b, double alpha, const double* v, double* r,
+// Device-resident Krylov scalars (ctx->d_scalars): [0..2] reduction results, [3] rho, [4] alpha, [5] omega, [6] h.  alpha and
+// omega are derived on the device right after their dot products (derive_kernel), so the update kernels can be queued
+// without a host round trip; the host reads all of them together with the residual norm, once per half step.
+enum { SC_RED = 0, SC_RHO = 3, SC_ALPHA = 4, SC_OMEGA = 5, SC_H = 6 };
+__global__ void derive_kernel(double* sc, int op)
+{
+    if (op == 0) { sc[SC_H] = sc[0]; sc[SC_ALPHA] = sc[SC_RHO] / sc[0]; }       // alpha = rho / <rt, v>
+    else if (op == 1) sc[SC_OMEGA] = sc[0] / sc[1];                               // omega = <t, r> / <t, t>
+    else if (op == 2) sc[SC_RHO] = sc[1];                                         // rho of the next iteration (fused update)
+    else sc[SC_RHO] = sc[0];                                                      // rho from the stand-alone dot
+}
+__global__ void __launch_bounds__(RED_THREADS) axpy_r_norm_kernel(size_t len, int b, const double* sc, const double* v, double* r,
                                                                   const unsigned char* owner, double* partials)
 {
     double s = 0.0;
-    const double malpha = -alpha;
+    const double malpha = -sc[SC_ALPHA];
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (size_t)gridDim.x * blockDim.x) {
         const double ri = r[i] + malpha * v[i];
         r[i] = ri;
@@ -206,11 +217,12 @@ __global__ void __launch_bounds__(RED_THREADS) axpy_r_norm_kernel(size_t len, in
     if (threadIdx.x == 0) partials[blockIdx.x] = s;
 }
 // second half step: x = (x + alpha*y) + omega*z ; r += -omega*t ; partial ||r||^2 and partial <rt, r> (the next iteration's rho)
-__global__ void __launch_bounds__(RED_THREADS) axpy3_norm_dot_kernel(size_t len, int b, double alpha, double omega, const double* y,
+__global__ void __launch_bounds__(RED_THREADS) axpy3_norm_dot_kernel(size_t len, int b, const double* sc, const double* y,
                                                                      const double* z, const double* t, const double* rt, double* x,
                                                                      double* r, const unsigned char* owner, double* partials)
 {
     double s = 0.0, d = 0.0;
+    const double alpha = sc[SC_ALPHA], omega = sc[SC_OMEGA];
     const double momega = -omega;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (size_t)gridDim.x * blockDim.x) {
         double xi = x[i];
@@ -295,6 +307,29 @@ static int reduce_to_host(dmx_ctx* ctx, int nq, bool max, double* out)
     return 0;
 }
 
+// reduction of the per-block partials into d_scalars[0..nq) (+ all-reduce), then a derived scalar; no host round trip
+static int reduce_on_device(dmx_ctx* ctx, int nq, int derive_op)
+{
+    final_reduce_kernel<false><<<1, RED_THREADS, 0, ctx->stream>>>(RED_BLOCKS, nq, ctx->d_partials, ctx->d_scalars);
+    DMX_CHECK_LAUNCH();
+    if (ctx->nranks > 1) {
+        if (int rc = allreduce_sum(ctx, ctx->d_scalars, nq)) return rc;
+    }
+    if (derive_op >= 0) {
+        derive_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d_scalars, derive_op);
+        DMX_CHECK_LAUNCH();
+    }
+    return 0;
+}
+static int read_scalars(dmx_ctx* ctx, double* out8)
+{
+    DMX_CUDA(cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    DMX_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->prof_pending.size() > 512) prof_drain(ctx);
+    for (int q = 0; q < 8; ++q) out8[q] = ctx->h_scalars[q];
+    return 0;
+}
+
 int dot(dmx_ctx* ctx, const double* a, const double* b, double* out)
 {
     const size_t len = (size_t)ctx->n * ctx->b;
@@ -303,15 +338,6 @@ int dot(dmx_ctx* ctx, const double* a, const double* b, double* out)
     DMX_CHECK_LAUNCH();
     return reduce_to_host(ctx, 1, false, out);
 }
-static int dot2(dmx_ctx* ctx, const double* a0, const double* b0, const double* a1, const double* b1, double* out)
-{
-    const size_t len = (size_t)ctx->n * ctx->b;
-    ProfScope ps(ctx, DMX_K_BLAS1);
-    dot_kernel<2><<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>>(len, ctx->b, a0, b0, a1, b1, nullptr, nullptr, ctx->d_owner, ctx->d_partials);
-    DMX_CHECK_LAUNCH();
-    return reduce_to_host(ctx, 2, false, out);
-}
-
 int newton_update(dmx_ctx* ctx, double* shift)
 {
     const size_t len = (size_t)ctx->n * ctx->b;
@@ -737,8 +763,20 @@ int bicgstab(dmx_ctx* ctx, double reduction, int maxit, int precond, int* iterat
         DMX_CHECK_LAUNCH();
         return 0;
     };
+    double sc[8];
     for (it = 0.5; it < maxit; it += .5) {
-        if (!have_rho && (rc = dot(ctx, rt, r, &rho_new))) return rc;
+        if (!have_rho) {
+            // <rt, r> of the first iteration: stand-alone dot, kept on the device as rho and read back
+            {
+                ProfScope ps(ctx, DMX_K_BLAS1);
+                dot_kernel<1><<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>>(len, ctx->b, rt, r, nullptr, nullptr, nullptr, nullptr, ctx->d_owner,
+                                                                            ctx->d_partials);
+                DMX_CHECK_LAUNCH();
+            }
+            if ((rc = reduce_on_device(ctx, 1, 3))) return rc;
+            if ((rc = read_scalars(ctx, sc))) return rc;
+            rho_new = sc[SC_RHO];
+        }
         if (std::fabs(rho) <= EPSILON || std::fabs(omega) <= EPSILON) { status = DMX_STATUS_BREAKDOWN; break; }
         if (it < 1)
             DMX_CUDA(cudaMemcpyAsync(p, r, len * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
@@ -750,34 +788,44 @@ int bicgstab(dmx_ctx* ctx, double reduction, int maxit, int precond, int* iterat
         }
         if ((rc = precond_apply(ctx, precond, p, y))) return rc;
         if ((rc = launch_spmv(ctx, y, v))) return rc;
-        if ((rc = dot(ctx, rt, v, &h))) return rc;
-        if (std::fabs(h) < EPSILON) { status = DMX_STATUS_BREAKDOWN; break; }
-        alpha = rho_new / h;
         {
+            // h = <rt, v>, alpha = rho / h on the device; r -= alpha v and ||r||^2 queued behind it; ONE host read for both
             ProfScope ps(ctx, DMX_K_BLAS1);
-            axpy_r_norm_kernel<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>>(len, ctx->b, alpha, v, r, ctx->d_owner, ctx->d_partials);
+            dot_kernel<1><<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>>(len, ctx->b, rt, v, nullptr, nullptr, nullptr, nullptr, ctx->d_owner,
+                                                                        ctx->d_partials);
             DMX_CHECK_LAUNCH();
+            if ((rc = reduce_on_device(ctx, 1, 0))) return rc;
+            axpy_r_norm_kernel<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>>(len, ctx->b, ctx->d_scalars, v, r, ctx->d_owner, ctx->d_partials);
+            DMX_CHECK_LAUNCH();
+            if ((rc = reduce_on_device(ctx, 1, -1))) return rc;
         }
-        if ((rc = reduce_to_host(ctx, 1, false, s))) return rc;
-        norm = std::sqrt(s[0]);
+        if ((rc = read_scalars(ctx, sc))) return rc;
+        h = sc[SC_H];
+        if (std::fabs(h) < EPSILON) { status = DMX_STATUS_BREAKDOWN; break; }
+        alpha = sc[SC_ALPHA];
+        norm = std::sqrt(sc[0]);
         if (!(norm == norm) || std::isinf(norm)) { if ((rc = flush_x())) return rc; status = DMX_STATUS_NONFINITE; break; }
         if (converged(norm)) { if ((rc = flush_x())) return rc; status = 0; break; }
         it += .5;
         if ((rc = precond_apply(ctx, precond, r, z))) return rc;
         if ((rc = launch_spmv(ctx, z, t))) return rc;
-        if ((rc = dot2(ctx, t, r, t, t, s))) return rc;
-        omega = s[0] / s[1];
         {
+            // omega = <t, r> / <t, t> on the device; x, r update with ||r||^2 and the next rho queued behind it
             ProfScope ps(ctx, DMX_K_BLAS1);
-            axpy3_norm_dot_kernel<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>>(len, ctx->b, alpha, omega, y, z, t, rt, x, r, ctx->d_owner,
+            dot_kernel<2><<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>>(len, ctx->b, t, r, t, t, nullptr, nullptr, ctx->d_owner, ctx->d_partials);
+            DMX_CHECK_LAUNCH();
+            if ((rc = reduce_on_device(ctx, 2, 1))) return rc;
+            axpy3_norm_dot_kernel<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>>(len, ctx->b, ctx->d_scalars, y, z, t, rt, x, r, ctx->d_owner,
                                                                                  ctx->d_partials);
             DMX_CHECK_LAUNCH();
+            if ((rc = reduce_on_device(ctx, 2, 2))) return rc;
         }
-        if ((rc = reduce_to_host(ctx, 2, false, s))) return rc;
+        if ((rc = read_scalars(ctx, sc))) return rc;
+        omega = sc[SC_OMEGA];
         rho = rho_new;
-        rho_new = s[1];
+        rho_new = sc[SC_RHO];
         have_rho = true;
-        norm = std::sqrt(s[0]);
+        norm = std::sqrt(sc[0]);
         if (!(norm == norm) || std::isinf(norm)) { status = DMX_STATUS_NONFINITE; break; }
         if (converged(norm)) { status = 0; break; }
     }
