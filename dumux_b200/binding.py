@@ -44,13 +44,18 @@ class DmxOptions(C.Structure):
 
 class DmxNewtonParams(C.Structure):
     _fields_ = [("max_relative_shift", C.c_double), ("min_steps", C.c_int), ("max_steps", C.c_int),
-                ("lin_reduction", C.c_double), ("lin_maxit", C.c_int), ("preconditioner", C.c_int)]
+                ("lin_reduction", C.c_double), ("lin_maxit", C.c_int), ("preconditioner", C.c_int),
+                ("use_line_search", C.c_int), ("line_search_min_relaxation", C.c_double),
+                ("enable_shift_criterion", C.c_int), ("enable_residual_criterion", C.c_int),
+                ("enable_absolute_residual_criterion", C.c_int), ("satisfy_residual_and_shift", C.c_int),
+                ("residual_reduction", C.c_double), ("max_absolute_residual", C.c_double)]
 
 
 class DmxNewtonReport(C.Structure):
     _fields_ = [("newton_iterations", C.c_int), ("converged", C.c_int), ("linear_iterations_total", C.c_int),
                 ("last_shift", C.c_double), ("t_assemble", C.c_double), ("t_solve", C.c_double),
-                ("t_update", C.c_double), ("linear_iterations", C.c_int * 64), ("shifts", C.c_double * 64)]
+                ("t_update", C.c_double), ("linear_iterations", C.c_int * 64), ("shifts", C.c_double * 64),
+                ("last_reduction", C.c_double), ("last_residual_norm", C.c_double), ("relaxation", C.c_double * 64)]
 
 
 class DmxError(RuntimeError):

@@ -212,6 +212,9 @@ void dmx_default_newton_params(dmx_newton_params* p)
 {
     p->max_relative_shift = 1e-8; p->min_steps = 2; p->max_steps = 18; p->lin_reduction = 1e-6; p->lin_maxit = 250;
     p->preconditioner = DMX_PRECOND_ILU0;
+    p->use_line_search = 0; p->line_search_min_relaxation = 0.125;
+    p->enable_shift_criterion = 1; p->enable_residual_criterion = 0; p->enable_absolute_residual_criterion = 0;
+    p->satisfy_residual_and_shift = 0; p->residual_reduction = 1e-5; p->max_absolute_residual = 1e-5;
 }
 
 int dmx_create_distributed(dmx_ctx** out, int device, const void* uid, int rank, int nranks)
@@ -604,7 +607,7 @@ int dmx_dot(dmx_ctx* ctx, int a, int b, double* out)
     if (int rc = vec_ok(ctx, b)) return rc;
     return dot(ctx, ctx->d_vec[a], ctx->d_vec[b], out);
 }
-int dmx_newton_update(dmx_ctx* ctx, double* shift) { return newton_update(ctx, shift); }
+int dmx_newton_update(dmx_ctx* ctx, double* shift) { return newton_update(ctx, 1.0, shift); }
 int dmx_advance_timestep(dmx_ctx* ctx) { return dmx_vec_copy(ctx, DMX_VEC_PREV, DMX_VEC_CUR); }
 int dmx_reset_timestep(dmx_ctx* ctx) { return dmx_vec_copy(ctx, DMX_VEC_CUR, DMX_VEC_PREV); }
 
@@ -623,7 +626,7 @@ int dmx_newton_step(dmx_ctx* ctx, const dmx_newton_params* prm, int* linear_iter
     rc = bicgstab(ctx, prm->lin_reduction, prm->lin_maxit, prm->preconditioner, linear_iterations, &red);
     if (rc) return rc;
     DMX_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
-    if ((rc = newton_update(ctx, shift))) return rc;
+    if ((rc = newton_update(ctx, 1.0, shift))) return rc;
     DMX_CUDA(cudaEventRecord(ctx->ev[3], ctx->stream));
     DMX_CUDA(cudaEventSynchronize(ctx->ev[3]));
     float a = 0, s = 0, u = 0;
@@ -661,34 +664,84 @@ int dmx_timer_stop(dmx_ctx* ctx, float* ms)
 
 // NewtonSolver::solveImpl_ (newtonsolver.hh:976-1072) with newtonProceed (:428-446), newtonConverged (:657-666, shift
 // criterion), on the device-resident CUR/PREV.  Returns 0 if converged, DMX_STATUS_* otherwise.
+// NewtonSolver::solveImpl_ (newtonsolver.hh:976-1072) with newtonBeginStep (:448-461), newtonUpdate (:543-566),
+// lineSearchUpdate_ (:1154-1178), computeResidualReduction_ (:869-881), newtonConverged (:657-701), newtonProceed (:428-446)
 int dmx_newton_solve(dmx_ctx* ctx, const dmx_newton_params* prm, dmx_newton_report* rep)
 {
     std::memset(rep, 0, sizeof(*rep));
+    const bool shiftCrit = prm->enable_shift_criterion != 0;
+    const bool absResCrit = prm->enable_absolute_residual_criterion != 0;
+    const bool resCrit = prm->enable_residual_criterion != 0 || absResCrit;
+    if (!shiftCrit && !resCrit) return fail(ctx, DMX_ERR_USAGE, "Newton: at least one of the shift / residual criteria has to be enabled");
+    const bool lineSearch = prm->use_line_search != 0;
+    const bool needResidual = lineSearch || resCrit;
     int numSteps = 0;
-    double shift = 0.0, lastShift = 0.0;
+    double shift = 0.0, lastShift = 0.0, reduction = 1.0, lastReduction = 1.0, residualNorm = 0.0, initialResidual = 0.0;
     bool converged = false;
     auto proceed = [&]() {
         if (numSteps < prm->min_steps) return true;
         else if (converged) return false;
-        else if (numSteps >= prm->max_steps) return shift * 4.0 < lastShift;
+        else if (numSteps >= prm->max_steps) return shiftCrit ? shift * 4.0 < lastShift : reduction * 4.0 < lastReduction;
         return true;
     };
-    while (proceed()) {
-        lastShift = shift;
-        int its = 0;
-        float a = 0, s = 0, u = 0;
-        const int rc = dmx_newton_step(ctx, prm, &its, &shift, &a, &s, &u);
-        if (numSteps < 64) rep->linear_iterations[numSteps] = its;
-        rep->linear_iterations_total += its;
-        if (rc) { rep->newton_iterations = numSteps; rep->converged = 0; return rc; }
-        rep->t_assemble += a * 1e-3; rep->t_solve += s * 1e-3; rep->t_update += u * 1e-3;
-        if (numSteps < 64) rep->shifts[numSteps] = shift;
-        ++numSteps;
-        converged = shift <= prm->max_relative_shift;
+    auto isConverged = [&]() {
+        const bool resOk = absResCrit ? residualNorm <= prm->max_absolute_residual : reduction <= prm->residual_reduction;
+        if (shiftCrit && !resCrit) return shift <= prm->max_relative_shift;
+        if (!shiftCrit && resCrit) return resOk;
+        if (prm->satisfy_residual_and_shift) return shift <= prm->max_relative_shift && resOk;
+        return shift <= prm->max_relative_shift || resOk;
+    };
+    if (!needResidual) {
+        // default path: one fused step per iteration
+        while (proceed()) {
+            lastShift = shift;
+            int its = 0;
+            float a = 0, s = 0, u = 0;
+            const int rc = dmx_newton_step(ctx, prm, &its, &shift, &a, &s, &u);
+            if (numSteps < 64) rep->linear_iterations[numSteps] = its;
+            rep->linear_iterations_total += its;
+            if (rc) { rep->newton_iterations = numSteps; rep->converged = 0; return rc; }
+            rep->t_assemble += a * 1e-3; rep->t_solve += s * 1e-3; rep->t_update += u * 1e-3;
+            if (numSteps < 64) { rep->shifts[numSteps] = shift; rep->relaxation[numSteps] = 1.0; }
+            ++numSteps;
+            converged = isConverged();
+        }
+    } else {
+        DMX_CUDA(cudaSetDevice(ctx->device));
+        const size_t bytes = (size_t)ctx->n * ctx->b * sizeof(double);
+        while (proceed()) {
+            lastShift = shift;
+            lastReduction = numSteps == 0 ? 1.0 : reduction;
+            int rc, its = 0;
+            if ((rc = dmx_vec_copy(ctx, DMX_VEC_ULAST, DMX_VEC_CUR))) return rc;
+            if ((rc = dmx_assemble(ctx, 1))) { rep->newton_iterations = numSteps; return rc; }
+            if (numSteps == 0 && (rc = dmx_norm2(ctx, DMX_VEC_RESIDUAL, &initialResidual))) return rc;     // solveLinearSystem :495
+            DMX_CUDA(cudaMemsetAsync(ctx->d_vec[DMX_VEC_DELTA], 0, bytes, ctx->stream));
+            double red = 0;
+            rc = bicgstab(ctx, prm->lin_reduction, prm->lin_maxit, prm->preconditioner, &its, &red);
+            if (numSteps < 64) rep->linear_iterations[numSteps] = its;
+            rep->linear_iterations_total += its;
+            if (rc) { rep->newton_iterations = numSteps; rep->converged = 0; return rc; }
+            double lambda = 1.0;
+            while (true) {
+                // uCurrentIter = uLastIter; axpy(-lambda, deltaU); residual and its norm at the trial point
+                if ((rc = newton_update(ctx, lambda, &shift))) return rc;
+                if ((rc = dmx_assemble(ctx, 0))) { rep->newton_iterations = numSteps; return rc; }
+                if ((rc = dmx_norm2(ctx, DMX_VEC_RESIDUAL, &residualNorm))) return rc;
+                reduction = residualNorm / initialResidual;
+                if (!lineSearch || reduction < lastReduction || lambda <= prm->line_search_min_relaxation) break;
+                lambda *= 0.5;
+            }
+            if (numSteps < 64) { rep->shifts[numSteps] = shift; rep->relaxation[numSteps] = lambda; }
+            ++numSteps;
+            converged = isConverged();
+        }
     }
     rep->newton_iterations = numSteps;
     rep->converged = converged ? 1 : 0;
     rep->last_shift = shift;
+    rep->last_reduction = reduction;
+    rep->last_residual_norm = residualNorm;
     return converged ? 0 : DMX_STATUS_NOT_CONVERGED;
 }
 int dmx_newton_solve_host(dmx_ctx* ctx, double* u, const double* prev, const dmx_newton_params* prm, dmx_newton_report* rep)

@@ -229,7 +229,7 @@ int block_jacobi_setup(dmx_ctx* ctx);
 int block_jacobi_apply(dmx_ctx* ctx, const double* d, double* v);
 int dot(dmx_ctx* ctx, const double* a, const double* b, double* out);
 int bicgstab(dmx_ctx* ctx, double reduction, int maxit, int precond, int* iterations, double* achieved);
-int newton_update(dmx_ctx* ctx, double* shift);
+int newton_update(dmx_ctx* ctx, double lambda, double* shift);
 int check_finite(dmx_ctx* ctx, const double* v, size_t len, bool* ok);
 // implemented in ilu_structured.cu
 int sk_setup(dmx_ctx* ctx);

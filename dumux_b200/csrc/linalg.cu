@@ -269,14 +269,14 @@ __global__ void __launch_bounds__(RED_THREADS) residual_init_kernel(size_t len, 
     if (threadIdx.x == 0) partials[blockIdx.x] = s;
 }
 
-// u = uLast + (-1)*delta ; shift = max_i |u - uLast| / max(1, |u + uLast|/2)   (newtonsolver.hh:111-129,556-557)
-__global__ void __launch_bounds__(RED_THREADS) newton_update_kernel(size_t len, int b, const double* uLast, const double* delta, double* u,
+// u = uLast + (-lambda)*delta ; shift = max_i |u - uLast| / max(1, |u + uLast|/2)   (newtonsolver.hh:111-129,556-557,1163)
+__global__ void __launch_bounds__(RED_THREADS) newton_update_kernel(size_t len, int b, double mlambda, const double* uLast, const double* delta, double* u,
                                                                     const unsigned char* owner, double* partials)
 {
     double s = 0.0;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (size_t)gridDim.x * blockDim.x) {
         const double ul = uLast[i];
-        const double un = ul + (-1.0) * delta[i];
+        const double un = ul + mlambda * delta[i];
         u[i] = un;
         const double sh = fabs(un - ul) / fmax(1.0, fabs(un + ul) * 0.5);
         if (!owner || owner[i / b]) s = fmax(s, sh);
@@ -338,11 +338,11 @@ int dot(dmx_ctx* ctx, const double* a, const double* b, double* out)
     DMX_CHECK_LAUNCH();
     return reduce_to_host(ctx, 1, false, out);
 }
-int newton_update(dmx_ctx* ctx, double* shift)
+int newton_update(dmx_ctx* ctx, double lambda, double* shift)
 {
     const size_t len = (size_t)ctx->n * ctx->b;
     ProfScope ps(ctx, DMX_K_BLAS1);
-    newton_update_kernel<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>>(len, ctx->b, ctx->d_vec[DMX_VEC_ULAST], ctx->d_vec[DMX_VEC_DELTA],
+    newton_update_kernel<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>>(len, ctx->b, -lambda, ctx->d_vec[DMX_VEC_ULAST], ctx->d_vec[DMX_VEC_DELTA],
                                                                       ctx->d_vec[DMX_VEC_CUR], ctx->d_owner, ctx->d_partials);
     DMX_CHECK_LAUNCH();
     return reduce_to_host(ctx, 1, true, shift);

@@ -63,6 +63,15 @@ typedef struct {
     double lin_reduction;        /* LinearSolver.ResidualReduction 1e-6 (newtonsolver.hh:232) */
     int    lin_maxit;            /* LinearSolver.MaxIterations 250 */
     int    preconditioner;       /* DMX_PRECOND_* */
+    /* update strategy and convergence criteria (newtonsolver.hh:1213-1232, 543-566, 657-701, 1154-1178) */
+    int    use_line_search;               /* Newton.UseLineSearch 0: halve the update until the residual norm decreases */
+    double line_search_min_relaxation;    /* Newton.LineSearchMinRelaxationFactor 0.125 */
+    int    enable_shift_criterion;        /* Newton.EnableShiftCriterion 1 */
+    int    enable_residual_criterion;     /* Newton.EnableResidualCriterion 0 */
+    int    enable_absolute_residual_criterion;   /* Newton.EnableAbsoluteResidualCriterion 0 (implies the residual criterion) */
+    int    satisfy_residual_and_shift;    /* Newton.SatisfyResidualAndShiftCriterion 0 */
+    double residual_reduction;            /* Newton.ResidualReduction 1e-5 */
+    double max_absolute_residual;         /* Newton.MaxAbsoluteResidual 1e-5 */
 } dmx_newton_params;
 
 typedef struct {
@@ -73,6 +82,9 @@ typedef struct {
     double t_assemble, t_solve, t_update;   /* seconds, CUDA-event timed; buckets of newtonsolver.hh:950-955 */
     int    linear_iterations[64];
     double shifts[64];
+    double last_reduction;       /* residual norm / initial residual norm (line search or residual criterion only) */
+    double last_residual_norm;
+    double relaxation[64];       /* line search: the accepted lambda of every iteration */
 } dmx_newton_report;
 
 /* ---- lifetime ------------------------------------------------------------------------------------------ */

@@ -331,7 +331,20 @@ public:
     void setMinSteps(int n) { params_.min_steps = n; }
     void setMaxSteps(int n) { params_.max_steps = n; }
     void setTargetSteps(int n) { targetSteps_ = n; }
-    void setResidualReduction(double r) { params_.lin_reduction = r; }
+    void setMaxAbsoluteResidual(double r) { params_.max_absolute_residual = r; }                 // newtonsolver.hh:259
+    void setResidualReduction(double r) { params_.residual_reduction = r; }                      // :268 (Newton.ResidualReduction)
+    void setUseLineSearch(bool v = true) { params_.use_line_search = v ? 1 : 0; }               // :815
+    //! Newton.EnableShiftCriterion / EnableResidualCriterion / EnableAbsoluteResidualCriterion /
+    //! SatisfyResidualAndShiftCriterion (:1220-1223)
+    void setConvergenceCriteria(bool shift, bool residual, bool absoluteResidual = false, bool satisfyBoth = false)
+    {
+        params_.enable_shift_criterion = shift ? 1 : 0;
+        params_.enable_residual_criterion = residual ? 1 : 0;
+        params_.enable_absolute_residual_criterion = absoluteResidual ? 1 : 0;
+        params_.satisfy_residual_and_shift = satisfyBoth ? 1 : 0;
+    }
+    //! LinearSolver.ResidualReduction as set by the NewtonSolver constructor (:232) / LinearSolver.MaxIterations
+    void setLinearResidualReduction(double r) { params_.lin_reduction = r; }
     void setLinearMaxIterations(int n) { params_.lin_maxit = n; }
 
     //! NewtonSolver::solve(vars) at fixed dt (newtonsolver.hh:362-372): throws NumericalProblem if not converged.

@@ -1173,6 +1173,84 @@ int orc_newton_solve(orc_problem* p, double* u, const double* prev, double lin_r
     return converged ? 0 : 1;
 }
 
+void orc_default_newton_options(orc_newton_options* o)
+{
+    o->use_line_search = 0; o->line_search_min_relaxation = 0.125;
+    o->enable_shift_criterion = 1; o->enable_residual_criterion = 0; o->enable_absolute_residual_criterion = 0;
+    o->satisfy_residual_and_shift = 0; o->residual_reduction = 1e-5; o->max_absolute_residual = 1e-5;
+}
+
+// NewtonSolver::solveImpl_ with the non-default update strategies and criteria: newtonBeginStep (newtonsolver.hh:448-461),
+// solveLinearSystem's initial residual (:495), newtonUpdate (:543-566), lineSearchUpdate_ (:1154-1178),
+// computeResidualReduction_ (:869-881), newtonConverged (:657-701), newtonProceed (:428-446)
+int orc_newton_solve_ex(orc_problem* p, double* u, const double* prev, double lin_reduction, int lin_maxit,
+                        double max_rel_shift, int min_steps, int max_steps, const orc_newton_options* opt,
+                        orc_newton_report* rep, double* relaxation, double* reduction_out)
+{
+    const int n = p->n, b = p->b;
+    const size_t N = (size_t)n * b;
+    const size_t nnz = p->colidx.size();
+    std::vector<double> J(nnz * b * b), r(N), delta(N), uLast(u, u + N);
+    const bool shiftCrit = opt->enable_shift_criterion != 0;
+    const bool absResCrit = opt->enable_absolute_residual_criterion != 0;
+    const bool resCrit = opt->enable_residual_criterion != 0 || absResCrit;
+    const bool lineSearch = opt->use_line_search != 0;
+    int numSteps = 0;
+    double shift = 0.0, lastShift = 0.0, reduction = 1.0, lastReduction = 1.0, residualNorm = 0.0, initialResidual = 0.0;
+    bool converged = false;
+    std::memset(rep, 0, sizeof(*rep));
+    auto proceed = [&]() {
+        if (numSteps < min_steps) return true;
+        else if (converged) return false;
+        else if (numSteps >= max_steps) return shiftCrit ? shift * 4.0 < lastShift : reduction * 4.0 < lastReduction;
+        return true;
+    };
+    auto isConverged = [&]() {
+        const bool resOk = absResCrit ? residualNorm <= opt->max_absolute_residual : reduction <= opt->residual_reduction;
+        if (shiftCrit && !resCrit) return shift <= max_rel_shift;
+        if (!shiftCrit && resCrit) return resOk;
+        if (opt->satisfy_residual_and_shift) return shift <= max_rel_shift && resOk;
+        return shift <= max_rel_shift || resOk;
+    };
+    while (proceed()) {
+        lastShift = shift;
+        lastReduction = numSteps == 0 ? 1.0 : reduction;
+        uLast.assign(u, u + N);
+        orc_assemble(p, u, prev, r.data(), J.data());
+        for (size_t i = 0; i < N; ++i)
+            if (!(r[i] == r[i]) || std::isinf(r[i])) return 3;
+        if (numSteps == 0) initialResidual = std::sqrt(dot(N, r.data(), r.data()));
+        std::fill(delta.begin(), delta.end(), 0.0);
+        int its = 0;
+        double red = 0;
+        const int st = orc_ilu0_bicgstab(n, b, p->rowptr.data(), p->colidx.data(), J.data(), delta.data(), r.data(),
+                                         lin_reduction, lin_maxit, &its, &red);
+        if (numSteps < 64) rep->linear_iterations[numSteps] = its;
+        rep->linear_iterations_total += its;
+        if (st != 0) { rep->newton_iterations = numSteps; rep->converged = 0; return st; }
+        double lambda = 1.0;
+        while (true) {
+            for (size_t i = 0; i < N; ++i) u[i] = uLast[i] + (-lambda) * delta[i];     // axpy(-lambda, deltaU, uCurrentIter)
+            if (lineSearch || resCrit) {
+                orc_assemble(p, u, prev, r.data(), nullptr);
+                residualNorm = std::sqrt(dot(N, r.data(), r.data()));
+                reduction = residualNorm / initialResidual;
+            }
+            if (!lineSearch || reduction < lastReduction || lambda <= opt->line_search_min_relaxation) break;
+            lambda *= 0.5;
+        }
+        if (shiftCrit) shift = orc_max_relative_shift((int)N, u, uLast.data());
+        if (numSteps < 64) { rep->shifts[numSteps] = shift; if (relaxation) relaxation[numSteps] = lambda; }
+        ++numSteps;
+        converged = isConverged();
+    }
+    rep->newton_iterations = numSteps;
+    rep->converged = converged ? 1 : 0;
+    rep->last_shift = shift;
+    if (reduction_out) *reduction_out = reduction;
+    return converged ? 0 : 1;
+}
+
 // test/porousmediumflow/2p/incompressible/main.cc:126-163 with dumux/common/timeloop.hh:239-252,320-332,385-411
 // and NewtonSolver::solve(vars,timeLoop) retry logic newtonsolver.hh:309-355, suggestTimeStepSize :784-798
 int orc_run_timeloop(orc_problem* p, double* u, double t_end, double dt_initial, double max_dt,

@@ -94,6 +94,24 @@ typedef struct {
     double shifts[64];
 } orc_newton_report;
 
+/* update strategy and convergence criteria of the Newton solver (newtonsolver.hh:1213-1232) */
+typedef struct {
+    int    use_line_search;               /* Newton.UseLineSearch */
+    double line_search_min_relaxation;    /* Newton.LineSearchMinRelaxationFactor 0.125 */
+    int    enable_shift_criterion;        /* 1 */
+    int    enable_residual_criterion;     /* 0 */
+    int    enable_absolute_residual_criterion;
+    int    satisfy_residual_and_shift;
+    double residual_reduction;            /* Newton.ResidualReduction 1e-5 */
+    double max_absolute_residual;         /* Newton.MaxAbsoluteResidual 1e-5 */
+} orc_newton_options;
+void orc_default_newton_options(orc_newton_options* o);
+/* as orc_newton_solve with lineSearchUpdate_ (:1154-1178), computeResidualReduction_ (:869-881), newtonConverged (:657-701);
+   relaxation[64] receives the accepted lambda per iteration, reduction the last residual reduction */
+int  orc_newton_solve_ex(orc_problem* p, double* u, const double* prev, double lin_reduction, int lin_maxit,
+                         double max_rel_shift, int min_steps, int max_steps, const orc_newton_options* opt,
+                         orc_newton_report* rep, double* relaxation, double* reduction_out);
+
 /* One Newton solve at fixed dt (newtonsolver.hh:976-1072); u in/out, prev = previous time level */
 int  orc_newton_solve(orc_problem* p, double* u, const double* prev, double lin_reduction, int lin_maxit,
                       double max_rel_shift, int min_steps, int max_steps, orc_newton_report* rep);

@@ -31,6 +31,13 @@ class OrcOptions(C.Structure):
                 ("use_std_pow", C.c_int), ("num_threads", C.c_int)]
 
 
+class OrcNewtonOptions(C.Structure):
+    _fields_ = [("use_line_search", C.c_int), ("line_search_min_relaxation", C.c_double),
+                ("enable_shift_criterion", C.c_int), ("enable_residual_criterion", C.c_int),
+                ("enable_absolute_residual_criterion", C.c_int), ("satisfy_residual_and_shift", C.c_int),
+                ("residual_reduction", C.c_double), ("max_absolute_residual", C.c_double)]
+
+
 class OrcNewtonReport(C.Structure):
     _fields_ = [("newton_iterations", C.c_int), ("converged", C.c_int), ("linear_iterations_total", C.c_int),
                 ("last_shift", C.c_double), ("t_assemble", C.c_double), ("t_solve", C.c_double),
@@ -68,6 +75,9 @@ def lib():
         L.orc_pattern.argtypes = [vp, _ip, _ip]
         L.orc_assemble.argtypes = [vp, _dp, vp, vp, vp]
         L.orc_volvars.argtypes = [vp, _dp, _dp]
+        L.orc_default_newton_options.argtypes = [C.c_void_p]
+        L.orc_newton_solve_ex.argtypes = [vp, _dp, vp, C.c_double, C.c_int, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p, _dp, C.c_void_p]
+        L.orc_newton_solve_ex.restype = C.c_int
         L.orc_volume_flux.argtypes = [vp, _dp, _dp]
         L.orc_tracer_assemble.argtypes = [vp, _dp, _dp, _dp, C.c_int, C.c_double, C.c_void_p, C.c_void_p]
         L.orc_ilu0_bicgstab.argtypes = [C.c_int, C.c_int, _ip, _ip, _dp, _dp, _dp, C.c_double, C.c_int,
@@ -214,6 +224,23 @@ class Oracle:
         st = lib().orc_newton_solve(self.h, u, _ptr(prev_a), lin_reduction, lin_maxit, max_rel_shift, min_steps,
                                     max_steps, C.byref(rep))
         return u, st, rep
+
+    def newton_ex(self, u, prev, lin_reduction=1e-6, lin_maxit=250, max_rel_shift=1e-8, min_steps=2, max_steps=18, **opts):
+        """Newton solve with line search / residual criteria (orc_newton_solve_ex); opts = fields of orc_newton_options.
+        Returns (u, status, report, relaxation factors per iteration, last residual reduction)."""
+        L = lib()
+        o = OrcNewtonOptions()
+        L.orc_default_newton_options(C.byref(o))
+        for k, v in opts.items():
+            setattr(o, k, v)
+        u = np.ascontiguousarray(u, dtype=np.float64).reshape(-1).copy()
+        prev_a = None if prev is None else np.ascontiguousarray(prev, dtype=np.float64).reshape(-1)
+        rep = OrcNewtonReport()
+        relax = np.zeros(64)
+        red = C.c_double(0)
+        st = L.orc_newton_solve_ex(self.h, u, _ptr(prev_a), lin_reduction, lin_maxit, max_rel_shift, min_steps, max_steps,
+                                   C.byref(o), C.byref(rep), relax, C.byref(red))
+        return u, st, rep, relax[:rep.newton_iterations].copy(), red.value
 
     def run_instationary(self, u0, loop, **newton_kw):
         """The same driver as Engine.run_instationary (dumux_b200.timeloop decides dt), Newton steps on the CPU."""

@@ -78,3 +78,30 @@ def test_block_jacobi_newton_same_count(engine_factory):
     assert st1 == 0 and st2 == 0
     assert rep1.newton_iterations == rep2.newton_iterations
     assert _rel_l2(u2.reshape(-1, 2)[:, 0], u1.reshape(-1, 2)[:, 0]) <= 1e-8
+
+
+def test_line_search_and_residual_criteria_match_oracle(engine_factory):
+    """Newton.UseLineSearch (lineSearchUpdate_, newtonsolver.hh:1154-1178) and the residual-based convergence criteria
+    (:657-701, computeResidualReduction_ :869-881): same iteration counts, same accepted relaxation factors, same fields."""
+    spec = problems.twop_lens((24, 16), law="vg")
+    rng = np.random.RandomState(0)
+    hard = spec.initial.copy()
+    hard[:, 1] = rng.uniform(0.0, 0.6, size=hard.shape[0])          # far from the solution: the first update gets damped
+    o = Oracle(spec)
+    e = engine_factory(spec)
+    for start, opts in ((hard, dict(use_line_search=1)),
+                        (spec.initial, dict(use_line_search=1)),
+                        (spec.initial, dict(enable_residual_criterion=1, enable_shift_criterion=0, residual_reduction=1e-6)),
+                        (spec.initial, dict(enable_residual_criterion=1, satisfy_residual_and_shift=1, residual_reduction=1e-4)),
+                        (spec.initial, dict(enable_absolute_residual_criterion=1, enable_shift_criterion=0, max_absolute_residual=1e-7))):
+        uo, sto, repo, relax_o, red_o = o.newton_ex(start, spec.initial, **opts)
+        ug, stg, repg = e.newton(start, spec.initial, **opts)
+        assert stg == sto == 0, (opts, stg, sto)
+        assert repg.newton_iterations == repo.newton_iterations, (opts, repg.newton_iterations, repo.newton_iterations)
+        assert list(repg.relaxation[:repg.newton_iterations]) == list(relax_o), opts
+        # the converged residual reduction sits at round-off level: same order of magnitude, or both negligible
+        assert (repg.last_reduction < 1e-12 and red_o < 1e-12) or 0.1 < repg.last_reduction / red_o < 10.0, (opts, repg.last_reduction, red_o)
+        assert np.linalg.norm(ug - uo) <= 1e-8 * np.linalg.norm(uo), opts
+    # the damped first step really happened
+    uo, sto, repo, relax_o, red_o = o.newton_ex(hard, spec.initial, use_line_search=1)
+    assert relax_o[0] < 1.0
