@@ -773,6 +773,12 @@ int dmx_ilu0_apply(dmx_ctx* ctx, int d_vec, int v_vec)
 int dmx_ilu0_download(dmx_ctx* ctx, double* values)
 {
     if (!ctx->ilu_valid) return fail(ctx, DMX_ERR_USAGE, "no ILU factorisation");
+    if (!ctx->ilu_bcrs_valid) {
+        // structured path: the factors live in the sweep streams; rebuild the BCRS view from (J, Dinv) -- J must be unchanged
+        if (!ctx->d_ilu) DMX_CUDA(cudaMalloc((void**)&ctx->d_ilu, (size_t)ctx->nnzb * ctx->b * ctx->b * sizeof(double)));
+        if (int rc = sk_export_bcrs(ctx, ctx->d_ilu)) return rc;
+        ctx->ilu_bcrs_valid = true;
+    }
     DMX_CUDA(cudaMemcpyAsync(values, ctx->d_ilu, (size_t)ctx->nnzb * ctx->b * ctx->b * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     DMX_CUDA(cudaStreamSynchronize(ctx->stream));
     return 0;

@@ -120,6 +120,7 @@ struct dmx_ctx {
     int *d_rowptr = nullptr, *d_colidx = nullptr, *d_diag = nullptr;
     double *d_J = nullptr, *d_ilu = nullptr;
     bool ilu_valid = false;
+    bool ilu_bcrs_valid = false;      // d_ilu holds the factorised BCRS values (generic path; structured path: on download only)
 
     // vectors
     double* d_vec[DMX_NUM_VECS] = {};
@@ -215,6 +216,44 @@ inline void prof_drain(dmx_ctx* c)
     c->prof_pending.clear();
 }
 
+#ifdef __CUDACC__
+// FieldMatrix::invert for 1x1 / 2x2 blocks (dune-common densematrix.hh, the 2x2 closed form); false: singular
+template <int B>
+__device__ __forceinline__ bool invert_block(double* A)
+{
+    if (B == 1) {
+        if (A[0] == 0.0) return false;
+        A[0] = 1.0 / A[0];
+        return true;
+    } else {
+        double detinv = A[0] * A[3] - A[1] * A[2];
+        if (detinv == 0.0 || detinv != detinv) return false;
+        detinv = 1.0 / detinv;
+        const double temp = A[0];
+        A[0] = A[3] * detinv;
+        A[1] = -A[1] * detinv;
+        A[2] = -A[2] * detinv;
+        A[3] = temp * detinv;
+        return true;
+    }
+}
+
+// grid-wide barrier for the persistent level loops (all CTAs co-resident: cooperative launch)
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int& epoch)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        epoch += gridDim.x;
+        __threadfence();
+        atomicAdd(counter, 1u);
+        while (*((volatile unsigned int*)counter) < epoch) { }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+#endif
+
 // implemented in assembly.cu
 int prepare(dmx_ctx* ctx);
 int launch_assemble(dmx_ctx* ctx, bool with_jacobian);
@@ -224,6 +263,7 @@ int launch_volume_flux(dmx_ctx* ctx, double* d_out);
 int build_level_schedule(dmx_ctx* ctx);
 int launch_spmv(dmx_ctx* ctx, const double* x, double* y);
 int ilu0_factor(dmx_ctx* ctx);
+int ilu0_factor_bcrs(dmx_ctx* ctx);
 int ilu0_apply(dmx_ctx* ctx, const double* d, double* v);
 int block_jacobi_setup(dmx_ctx* ctx);
 int block_jacobi_apply(dmx_ctx* ctx, const double* d, double* v);
@@ -234,7 +274,8 @@ int check_finite(dmx_ctx* ctx, const double* v, size_t len, bool* ok);
 // implemented in ilu_structured.cu
 int sk_setup(dmx_ctx* ctx);
 void sk_free(dmx_ctx* ctx);
-int sk_skew(dmx_ctx* ctx);
+int sk_factor(dmx_ctx* ctx);
+int sk_export_bcrs(dmx_ctx* ctx, double* out);
 int sk_apply(dmx_ctx* ctx, const double* d, double* v);
 int sk_trace_read(dmx_ctx* ctx, long long* out);
 // implemented in dist.cu

@@ -109,13 +109,116 @@ __host__ __device__ __forceinline__ int sk_pos(int blk, int r, int c, int t)
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// BCRS (factorised, ctx->d_ilu) -> tile-skewed L and U arrays.  One thread per (tile, step, thread slot).
+// Structured block ILU(0) factorisation (ILU::blockILU0Decomposition, dune-istl ilu.hh, restated in oracle/oracle.cpp).
+// On the 7-point pattern no product L_ij U_jk with k != i falls inside the pattern (boxes with >= 3 cells per axis, see
+// sk_supported), so the elimination only ever updates the DIAGONAL block:
+//     L_ij = A_ij Dinv_j                       (rightmultiply, j in {-z,-y,-x} in ascending column order)
+//     D_i  = A_ii - sum_j L_ij A_ji            (per j: T[r][c] -= L[r][k] A_ji[k][c], k ascending)
+//     Dinv_i = D_i^-1                          (FieldMatrix::invert)
+// and U_ij = A_ij.  The recurrence runs through Dinv only, so it is split in two kernels:
+//   ilu_diag_kernel   the recurrence over the nx+ny+nz-2 hyperplanes x+y+z = l (cooperative launch, one grid barrier per
+//                     hyperplane, rows addressed from the grid instead of through a level schedule; reads J, writes n blocks);
+//   ilu_skew_kernel   embarrassingly parallel: forms L_ij = A_ij Dinv_j and writes L, U and Dinv straight into the two
+//                     tile-skewed streams of the sweeps -- no factorised BCRS copy of the Jacobian is made at all.
+// Same operation sequence per block as factor_row (linalg.cu) -> bit-identical factors.
+// ------------------------------------------------------------------------------------------------------------
+// C = L * D (FieldMatrix::rightmultiply: sums start from 0)
+template <int B>
+__device__ __forceinline__ void block_rmul(const double* L, const double* D, double* C)
+{
+#pragma unroll
+    for (int r = 0; r < B; ++r)
+#pragma unroll
+        for (int c = 0; c < B; ++c) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < B; ++k) s += L[r * B + k] * D[k * B + c];
+            C[r * B + c] = s;
+        }
+}
+template <int B>
+__device__ __forceinline__ void load_block(const double* p, double* out)
+{
+    if (B == 2) {
+        const double2 lo = *reinterpret_cast<const double2*>(p), hi = *reinterpret_cast<const double2*>(p + 2);
+        out[0] = lo.x; out[B - 1] = lo.y; out[B * B - 2] = hi.x; out[B * B - 1] = hi.y;
+    } else out[0] = p[0];
+}
+template <int B>
+__device__ __forceinline__ void load_block_cg(const double* p, double* out)
+{
+    if (B == 2) {
+        const double2 lo = __ldcg(reinterpret_cast<const double2*>(p)), hi = __ldcg(reinterpret_cast<const double2*>(p + 2));
+        out[0] = lo.x; out[B - 1] = lo.y; out[B * B - 2] = hi.x; out[B * B - 1] = hi.y;
+    } else out[0] = __ldcg(p);
+}
+
+template <int B>
+__global__ void __launch_bounds__(256) ilu_diag_kernel(SkewGrid g, const int* __restrict__ diag, const double* __restrict__ A,
+                                                        double* Dinv, int* flag, unsigned int* barrier)
+{
+    constexpr int BB = B * B;
+    unsigned int epoch = 0;
+    const int nlev = g.nx + g.ny + g.nz - 2;
+    const int nthreads = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t sy = (size_t)g.nx, sz = (size_t)g.nx * g.ny;
+    for (int l = 0; l < nlev; ++l) {
+        const int zmin = max(0, l - (g.nx - 1) - (g.ny - 1)), zmax = min(g.nz - 1, l);
+        const int cand = (zmax - zmin + 1) * g.ny;
+        for (int q = tid; q < cand; q += nthreads) {
+            const int zz = q / g.ny;
+            const int z = zmin + zz, y = q - zz * g.ny, x = l - y - z;
+            if (x < 0 || x >= g.nx) continue;
+            const size_t I = (size_t)x + sy * y + sz * z;
+            const int kd = __ldg(diag + I);
+            const bool ex[3] = {z > 0, y > 0, x > 0};
+            const size_t J[3] = {I - sz, I - sy, I - 1};
+            // position of A_ji in row j behind its diagonal: the upper neighbours of j with a smaller column than i
+            const int up[3] = {1 + (x + 1 < g.nx ? 1 : 0) + (y + 1 < g.ny ? 1 : 0), 1 + (x + 1 < g.nx ? 1 : 0), 1};
+            double D[BB], Lb[3][BB], Ub[3][BB], Dj[3][BB];
+            int p = kd - (int)ex[0] - (int)ex[1] - (int)ex[2];
+            load_block<B>(A + (size_t)kd * BB, D);
+#pragma unroll
+            for (int s = 0; s < 3; ++s)
+                if (ex[s]) {
+                    load_block<B>(A + (size_t)p * BB, Lb[s]);
+                    load_block<B>(A + ((size_t)__ldg(diag + J[s]) + up[s]) * BB, Ub[s]);
+                    load_block_cg<B>(Dinv + J[s] * BB, Dj[s]);
+                    ++p;
+                }
+#pragma unroll
+            for (int s = 0; s < 3; ++s)
+                if (ex[s]) {
+                    double C[BB];
+                    block_rmul<B>(Lb[s], Dj[s], C);
+#pragma unroll
+                    for (int r = 0; r < B; ++r)
+#pragma unroll
+                        for (int c = 0; c < B; ++c) {
+                            double t = D[r * B + c];
+#pragma unroll
+                            for (int k = 0; k < B; ++k) t -= C[r * B + k] * Ub[s][k * B + c];
+                            D[r * B + c] = t;
+                        }
+                }
+            if (!invert_block<B>(D)) atomicOr(flag, 1);
+            if (B == 2) {
+                __stcg(reinterpret_cast<double2*>(Dinv + I * BB), make_double2(D[0], D[B - 1]));
+                __stcg(reinterpret_cast<double2*>(Dinv + I * BB + 2), make_double2(D[BB - 2], D[BB - 1]));
+            } else __stcg(Dinv + I, D[0]);
+        }
+        if (l + 1 < nlev) grid_barrier(barrier, epoch);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// (J, Dinv) -> tile-skewed L and U streams.  One thread per (tile, step, thread slot).
 // Mirrored thread coordinates: slot t = a + 16*b; lower: il = a, jl = b, k = s - a - b;
 //                              upper: il = 15-a, jl = 15-b, k = nz-1 - (s - a - b).
 // ------------------------------------------------------------------------------------------------------------
 template <int B>
-__global__ void __launch_bounds__(SK_THREADS) ilu_skew_kernel(SkewGrid g, const int* __restrict__ rowptr, const int* __restrict__ diag,
-                                                               const double* __restrict__ ilu, double* __restrict__ Lsk,
+__global__ void __launch_bounds__(SK_THREADS) ilu_skew_kernel(SkewGrid g, const int* __restrict__ diag, const double* __restrict__ A,
+                                                               const double* __restrict__ Dinv, double* __restrict__ Lsk,
                                                                double* __restrict__ Usk)
 {
     constexpr int BB = B * B;
@@ -124,6 +227,7 @@ __global__ void __launch_bounds__(SK_THREADS) ilu_skew_kernel(SkewGrid g, const 
     const int s = blockIdx.x % g.NS;
     const int tile = blockIdx.x / g.NS;
     const int ti = tile % g.ntx, tj = tile / g.ntx;
+    const size_t sy = (size_t)g.nx, sz = (size_t)g.nx * g.ny;
     {
         // lower
         const int i = ti * SK_TI + a, j = tj * SK_TJ + b, k = s - a - b;
@@ -135,11 +239,19 @@ __global__ void __launch_bounds__(SK_THREADS) ilu_skew_kernel(SkewGrid g, const 
 #pragma unroll
             for (int e = 0; e < BB; ++e) blk[q][e] = 0.0;
         if (valid) {
-            const int I = i + g.nx * (j + g.ny * k);
-            int p = rowptr[I];
-            if (k > 0) { for (int e = 0; e < BB; ++e) blk[0][e] = ilu[(size_t)p * BB + e]; ++p; }
-            if (j > 0) { for (int e = 0; e < BB; ++e) blk[1][e] = ilu[(size_t)p * BB + e]; ++p; }
-            if (i > 0) { for (int e = 0; e < BB; ++e) blk[2][e] = ilu[(size_t)p * BB + e]; ++p; }
+            const size_t I = (size_t)i + sy * j + sz * k;
+            const bool ex[3] = {k > 0, j > 0, i > 0};
+            const size_t J[3] = {I - sz, I - sy, I - 1};
+            int p = diag[I] - (int)ex[0] - (int)ex[1] - (int)ex[2];
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+                if (ex[q]) {
+                    double Lb[BB], Dj[BB];
+                    load_block<B>(A + (size_t)p * BB, Lb);
+                    load_block<B>(Dinv + J[q] * BB, Dj);
+                    block_rmul<B>(Lb, Dj, blk[q]);
+                    ++p;
+                }
         }
 #pragma unroll
         for (int q = 0; q < 3; ++q)
@@ -159,13 +271,13 @@ __global__ void __launch_bounds__(SK_THREADS) ilu_skew_kernel(SkewGrid g, const 
 #pragma unroll
             for (int e = 0; e < BB; ++e) blk[q][e] = 0.0;
         if (valid) {
-            const int I = i + g.nx * (j + g.ny * k);
+            const size_t I = (size_t)i + sy * j + sz * k;
             int p = diag[I];
-            for (int e = 0; e < BB; ++e) blk[3][e] = ilu[(size_t)p * BB + e];
+            load_block<B>(Dinv + I * BB, blk[3]);
             ++p;
-            if (i + 1 < g.nx) { for (int e = 0; e < BB; ++e) blk[0][e] = ilu[(size_t)p * BB + e]; ++p; }
-            if (j + 1 < g.ny) { for (int e = 0; e < BB; ++e) blk[1][e] = ilu[(size_t)p * BB + e]; ++p; }
-            if (k + 1 < g.nz) { for (int e = 0; e < BB; ++e) blk[2][e] = ilu[(size_t)p * BB + e]; ++p; }
+            if (i + 1 < g.nx) { load_block<B>(A + (size_t)p * BB, blk[0]); ++p; }
+            if (j + 1 < g.ny) { load_block<B>(A + (size_t)p * BB, blk[1]); ++p; }
+            if (k + 1 < g.nz) { load_block<B>(A + (size_t)p * BB, blk[2]); ++p; }
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q)
@@ -173,6 +285,29 @@ __global__ void __launch_bounds__(SK_THREADS) ilu_skew_kernel(SkewGrid g, const 
             for (int r = 0; r < B; ++r)
 #pragma unroll
                 for (int c = 0; c < B; ++c) dst[sk_pos<B>(q, r, c, t)] = blk[q][r * B + c];
+    }
+}
+
+// factorised BCRS values (what the generic ilu0_factor_kernel leaves in ctx->d_ilu) from (J, Dinv): for dmx_ilu0_download only
+template <int B>
+__global__ void __launch_bounds__(256) ilu_export_kernel(int n, const int* __restrict__ rowptr, const int* __restrict__ colidx,
+                                                          const double* __restrict__ A, const double* __restrict__ Dinv, double* out)
+{
+    constexpr int BB = B * B;
+    const int I = blockIdx.x * blockDim.x + threadIdx.x;
+    if (I >= n) return;
+    for (int k = rowptr[I]; k < rowptr[I + 1]; ++k) {
+        const int j = colidx[k];
+        double blk[BB], r[BB];
+        load_block<B>(A + (size_t)k * BB, blk);
+        if (j < I) {
+            double Dj[BB];
+            load_block<B>(Dinv + (size_t)j * BB, Dj);
+            block_rmul<B>(blk, Dj, r);
+        } else if (j == I) load_block<B>(Dinv + (size_t)I * BB, r);
+        else
+            for (int e = 0; e < BB; ++e) r[e] = blk[e];
+        for (int e = 0; e < BB; ++e) out[(size_t)k * BB + e] = r[e];
     }
 }
 
@@ -518,6 +653,8 @@ struct SkewState {
     SkewGrid g{};
     int b = 0;
     double *Lsk = nullptr, *Usk = nullptr;
+    double* Dinv = nullptr;                // inverted diagonal blocks of the ILU(0) factorisation, natural layout [n][b*b]
+    int diag_grid = 0;                     // co-resident CTAs of ilu_diag_kernel
     int *order_lo = nullptr, *order_up = nullptr;
     unsigned long long* ctl = nullptr;       // [0],[1]: tile tickets of the lower / upper sweep
     unsigned long long seq_lo = 0, seq_up = 0;
@@ -553,7 +690,7 @@ void sk_free(dmx_ctx* ctx)
 {
     SkewState* st = static_cast<SkewState*>(ctx->skew);
     if (!st) return;
-    cudaFree(st->Lsk); cudaFree(st->Usk); cudaFree(st->ll); cudaFree(st->order_lo); cudaFree(st->order_up); cudaFree(st->ctl);
+    cudaFree(st->Lsk); cudaFree(st->Usk); cudaFree(st->Dinv); cudaFree(st->ll); cudaFree(st->order_lo); cudaFree(st->order_up); cudaFree(st->ctl);
     if (st->trace) cudaFree(st->trace);
     delete st;
     ctx->skew = nullptr;
@@ -576,6 +713,7 @@ int sk_setup(dmx_ctx* ctx)
     // streams [factors | vector] per step: the vector slots of Lsk hold the right-hand side, those of Usk the lower sweep's result
     DMX_CUDA(cudaMalloc((void**)&st->Lsk, slots * (3 * BB + ctx->b) * sizeof(double)));
     DMX_CUDA(cudaMalloc((void**)&st->Usk, slots * (4 * BB + ctx->b) * sizeof(double)));
+    DMX_CUDA(cudaMalloc((void**)&st->Dinv, (size_t)ctx->n * BB * sizeof(double)));
     DMX_CUDA(cudaMemsetAsync(st->Lsk, 0, slots * (3 * BB + ctx->b) * sizeof(double), ctx->stream));
     DMX_CUDA(cudaMemsetAsync(st->Usk, 0, slots * (4 * BB + ctx->b) * sizeof(double), ctx->stream));
     {
@@ -604,14 +742,47 @@ int sk_setup(dmx_ctx* ctx)
     return 0;
 }
 
-// after ilu0_factor(): re-layout the factors
-int sk_skew(dmx_ctx* ctx)
+// ILU(0) factorisation of ctx->d_J on the structured pattern: diagonal recurrence, then the two sweep streams
+template <int B>
+static int sk_factor_t(dmx_ctx* ctx, SkewState* st)
+{
+    const SkewGrid& g = st->g;
+    auto kern = ilu_diag_kernel<B>;
+    if (!st->diag_grid) {
+        int perSm = 0;
+        DMX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kern, 256, 0));
+        st->diag_grid = std::max(1, std::min(perSm, 2)) * ctx->num_sms;
+    }
+    DMX_CUDA(cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream));
+    DMX_CUDA(cudaMemsetAsync(ctx->d_barrier, 0, sizeof(unsigned int), ctx->stream));
+    SkewGrid gg = g;
+    const int* diag = ctx->d_diag;
+    const double* A = ctx->d_J;
+    double* Dinv = st->Dinv;
+    int* flag = ctx->d_flag;
+    unsigned int* barrier = ctx->d_barrier;
+    void* params[] = {(void*)&gg, (void*)&diag, (void*)&A, (void*)&Dinv, (void*)&flag, (void*)&barrier};
+    DMX_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(st->diag_grid), dim3(256), params, 0, ctx->stream));
+    ctx->launches++;
+    const unsigned grid = (unsigned)((size_t)g.ntiles * g.NS);
+    ilu_skew_kernel<B><<<grid, SK_THREADS, 0, ctx->stream>>>(g, ctx->d_diag, ctx->d_J, st->Dinv, st->Lsk, st->Usk);
+    DMX_CHECK_LAUNCH();
+    return 0;
+}
+
+int sk_factor(dmx_ctx* ctx)
 {
     SkewState* st = static_cast<SkewState*>(ctx->skew);
-    const SkewGrid& g = st->g;
-    const unsigned grid = (unsigned)((size_t)g.ntiles * g.NS);
-    if (ctx->b == 2) ilu_skew_kernel<2><<<grid, SK_THREADS, 0, ctx->stream>>>(g, ctx->d_rowptr, ctx->d_diag, ctx->d_ilu, st->Lsk, st->Usk);
-    else ilu_skew_kernel<1><<<grid, SK_THREADS, 0, ctx->stream>>>(g, ctx->d_rowptr, ctx->d_diag, ctx->d_ilu, st->Lsk, st->Usk);
+    return ctx->b == 2 ? sk_factor_t<2>(ctx, st) : sk_factor_t<1>(ctx, st);
+}
+
+// factorised BCRS values into `out` (device, nnzb*b*b doubles), the layout of the generic path
+int sk_export_bcrs(dmx_ctx* ctx, double* out)
+{
+    SkewState* st = static_cast<SkewState*>(ctx->skew);
+    const unsigned grid = (unsigned)((ctx->n + 255) / 256);
+    if (ctx->b == 2) ilu_export_kernel<2><<<grid, 256, 0, ctx->stream>>>(ctx->n, ctx->d_rowptr, ctx->d_colidx, ctx->d_J, st->Dinv, out);
+    else ilu_export_kernel<1><<<grid, 256, 0, ctx->stream>>>(ctx->n, ctx->d_rowptr, ctx->d_colidx, ctx->d_J, st->Dinv, out);
     DMX_CHECK_LAUNCH();
     return 0;
 }

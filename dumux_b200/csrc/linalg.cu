@@ -417,40 +417,6 @@ int build_level_schedule(dmx_ctx* ctx)
 }
 
 template <int B>
-__device__ __forceinline__ bool invert_block(double* A)
-{
-    if (B == 1) {
-        if (A[0] == 0.0) return false;
-        A[0] = 1.0 / A[0];
-        return true;
-    } else {
-        double detinv = A[0] * A[3] - A[1] * A[2];
-        if (detinv == 0.0 || detinv != detinv) return false;
-        detinv = 1.0 / detinv;
-        const double temp = A[0];
-        A[0] = A[3] * detinv;
-        A[1] = -A[1] * detinv;
-        A[2] = -A[2] * detinv;
-        A[3] = temp * detinv;
-        return true;
-    }
-}
-
-// grid-wide barrier for the persistent level loops (all CTAs co-resident: cooperative launch)
-__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int& epoch)
-{
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        epoch += gridDim.x;
-        __threadfence();
-        atomicAdd(counter, 1u);
-        while (*((volatile unsigned int*)counter) < epoch) { }
-        __threadfence();
-    }
-    __syncthreads();
-}
-
-template <int B>
 __device__ __forceinline__ void factor_row(int i, const int* rowptr, const int* colidx, const int* diag, double* A, int* flag)
 {
     constexpr int BB = B * B;
@@ -606,29 +572,37 @@ static int coop_launch(dmx_ctx* ctx, void (*kernel)(Args...), int threads, Args.
     return 0;
 }
 
-int ilu0_factor(dmx_ctx* ctx)
+// generic pattern: level-scheduled factorisation of a copy of J (ctx->d_ilu); sets ctx->d_flag on a singular block
+int ilu0_factor_bcrs(dmx_ctx* ctx)
 {
-    ProfScope ps(ctx, DMX_K_ILU_FACTOR);
     const size_t bytes = (size_t)ctx->nnzb * ctx->b * ctx->b * sizeof(double);
     if (!ctx->d_ilu) DMX_CUDA(cudaMalloc((void**)&ctx->d_ilu, bytes));
     DMX_CUDA(cudaMemcpyAsync(ctx->d_ilu, ctx->d_J, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
     DMX_CUDA(cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream));
     const int nlev = (int)ctx->l_ptr.size() - 1;
-    int rc;
     if (ctx->b == 2)
-        rc = coop_launch(ctx, ilu0_factor_kernel<2>, 128, nlev, (const int*)ctx->d_lptr, (const int*)ctx->d_lrows, (const int*)ctx->d_rowptr,
-                         (const int*)ctx->d_colidx, (const int*)ctx->d_diag, ctx->d_ilu, ctx->d_flag, ctx->d_barrier);
-    else
-        rc = coop_launch(ctx, ilu0_factor_kernel<1>, 128, nlev, (const int*)ctx->d_lptr, (const int*)ctx->d_lrows, (const int*)ctx->d_rowptr,
-                         (const int*)ctx->d_colidx, (const int*)ctx->d_diag, ctx->d_ilu, ctx->d_flag, ctx->d_barrier);
-    if (rc) return rc;
+        return coop_launch(ctx, ilu0_factor_kernel<2>, 128, nlev, (const int*)ctx->d_lptr, (const int*)ctx->d_lrows, (const int*)ctx->d_rowptr,
+                           (const int*)ctx->d_colidx, (const int*)ctx->d_diag, ctx->d_ilu, ctx->d_flag, ctx->d_barrier);
+    return coop_launch(ctx, ilu0_factor_kernel<1>, 128, nlev, (const int*)ctx->d_lptr, (const int*)ctx->d_lrows, (const int*)ctx->d_rowptr,
+                       (const int*)ctx->d_colidx, (const int*)ctx->d_diag, ctx->d_ilu, ctx->d_flag, ctx->d_barrier);
+}
+
+int ilu0_factor(dmx_ctx* ctx)
+{
+    ProfScope ps(ctx, DMX_K_ILU_FACTOR);
+    ctx->ilu_valid = false;
+    ctx->ilu_bcrs_valid = false;
+    if (ctx->skew) {
+        // structured box: diagonal recurrence + sweep streams straight from J (ilu_structured.cu), no factorised BCRS copy
+        if (int rc = sk_factor(ctx)) return rc;
+    } else {
+        if (int rc = ilu0_factor_bcrs(ctx)) return rc;
+    }
     DMX_CUDA(cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     DMX_CUDA(cudaStreamSynchronize(ctx->stream));
     if (*ctx->h_flag) { ctx->err = "ILU0: singular diagonal block"; return DMX_STATUS_BREAKDOWN; }
-    if (ctx->skew) {
-        if (int rc2 = sk_skew(ctx)) return rc2;
-    }
     ctx->ilu_valid = true;
+    ctx->ilu_bcrs_valid = !ctx->skew;
     return 0;
 }
 
