@@ -31,8 +31,9 @@ EXPORTS = [
     "dmx_ilu0_factor", "dmx_ilu0_apply", "dmx_ilu0_download", "dmx_dot", "dmx_halo_exchange", "dmx_time_kernel",
     "dmx_kernel_launch_count", "dmx_synchronize", "dmx_profile", "dmx_profile_read",
     "dmx_newton_step_host", "dmx_timer_start", "dmx_timer_stop", "dmx_debug_sweep_trace",
-    "dmx_volume_flux", "dmx_set_volume_flux", "dmx_set_tracer",
+    "dmx_volume_flux", "dmx_set_volume_flux", "dmx_set_tracer", "dmx_set_wetting_phase", "dmx_set_linear_solver",
 ]
+SOLVER_BICGSTAB, SOLVER_RESTARTED_GMRES = 0, 1
 K_ASSEMBLY, K_SPMV, K_ILU_APPLY, K_ILU_FACTOR, K_VOLVARS, K_BLAS1, K_HALO, K_JACOBI = range(8)
 
 
@@ -104,6 +105,8 @@ def load_library():
     L.dmx_volume_flux.argtypes = [vp, _dp]
     L.dmx_set_volume_flux.argtypes = [vp, _dp]
     L.dmx_set_tracer.argtypes = [vp, C.c_int]
+    L.dmx_set_wetting_phase.argtypes = [vp, C.c_int, C.c_int]
+    L.dmx_set_linear_solver.argtypes = [vp, C.c_int, C.c_int]
     L.dmx_set_boundary.argtypes = [vp, C.c_int, _ip, _dp]
     L.dmx_vec_upload.argtypes = [vp, C.c_int, C.c_void_p]
     L.dmx_vec_download.argtypes = [vp, C.c_int, C.c_void_p]
@@ -241,6 +244,8 @@ class Engine:
             reg = np.ascontiguousarray(m.reg if len(m.reg) else [0.01, 0.99, 0.1, 0.9], dtype=np.float64)
             self._check(L.dmx_set_material(self.h, r, m.law, np.ascontiguousarray(m.params, dtype=np.float64),
                                            m.swr, m.snr, int(m.regularize), reg))
+            if getattr(m, "wetting", 0):
+                self._check(L.dmx_set_wetting_phase(self.h, r, int(m.wetting)))
         if spec.fluid_table is not None:
             t = spec.fluid_table
             self._check(L.dmx_set_fluid_table(self.h, t["nT"], t["nP"], t["Tmin"], t["Tmax"],
@@ -357,6 +362,10 @@ class Engine:
         st = self._check(self.L.dmx_linear_solve_host(self.h, _hostptr(values), _hostptr(x), _hostptr(rhs), reduction,
                                                       maxit, precond, C.byref(its), C.byref(red)), allow_status=True)
         return x, st, its.value, red.value
+
+    def set_linear_solver(self, kind, restart=10):
+        """'bicgstab' = ILUBiCGSTABIstlSolver (default), 'gmres' = ILURestartedGMResIstlSolver (LinearSolver.GMResRestart)."""
+        self._check(self.L.dmx_set_linear_solver(self.h, {"bicgstab": SOLVER_BICGSTAB, "gmres": SOLVER_RESTARTED_GMRES}[kind], restart))
 
     def solve_device(self, reduction=1e-6, maxit=250, precond=PRECOND_ILU0):
         its, red = C.c_int(0), C.c_double(0)

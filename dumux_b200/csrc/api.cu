@@ -259,7 +259,7 @@ int dmx_destroy(dmx_ctx* ctx)
     if (ctx->nccl_comm) nccl_destroy(ctx);
     void* ptrs[] = {ctx->d_geom, ctx->d_K, ctx->d_phi, ctx->d_q, ctx->d_region, ctx->d_tij[0], ctx->d_tij[1], ctx->d_tij[2], ctx->d_laws,
                     ctx->d_tab_buf, ctx->d_rowptr, ctx->d_colidx, ctx->d_diag, ctx->d_J, ctx->d_ilu, ctx->d_rt, ctx->d_p, ctx->d_v, ctx->d_t,
-                    ctx->d_y, ctx->d_z, ctx->d_dinv, ctx->d_vf, ctx->d_lrows, ctx->d_urows, ctx->d_lptr, ctx->d_uptr, ctx->d_barrier, ctx->d_partials,
+                    ctx->d_y, ctx->d_z, ctx->d_dinv, ctx->d_gm, ctx->d_vf, ctx->d_lrows, ctx->d_urows, ctx->d_lptr, ctx->d_uptr, ctx->d_barrier, ctx->d_partials,
                     ctx->d_scalars, ctx->d_flag, ctx->d_owner, ctx->d_send_lo, ctx->d_send_hi, ctx->d_recv_lo, ctx->d_recv_hi};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int v = 0; v < DMX_NUM_VECS; ++v) if (ctx->d_vec[v]) cudaFree(ctx->d_vec[v]);
@@ -387,6 +387,15 @@ int dmx_set_material(dmx_ctx* ctx, int region, int law, const double* params, do
         l.alpha = params[0]; l.n = params[1]; l.m = 1.0 - 1.0 / l.n; l.l = params[2];
         if (reg) { l.pcLowSwe = reg[0]; l.pcHighSwe = reg[1]; l.krnLowSwe = reg[2]; l.krwHighSwe = reg[3]; }
     } else return fail(ctx, DMX_ERR_USAGE, "unknown material law");
+    ctx->prepared = false;
+    return 0;
+}
+int dmx_set_wetting_phase(dmx_ctx* ctx, int region, int phase)
+{
+    if (region < 0 || region >= DMX_MAX_REGIONS) return fail(ctx, DMX_ERR_USAGE, "region id out of range");
+    if (phase != 0 && phase != 1) return fail(ctx, DMX_ERR_USAGE, "wetting phase must be 0 or 1");
+    if ((int)ctx->laws.size() <= region) return fail(ctx, DMX_ERR_USAGE, "set_wetting_phase: call dmx_set_material for the region first");
+    ctx->laws[region].wetting = phase;
     ctx->prepared = false;
     return 0;
 }
@@ -575,11 +584,18 @@ int dmx_assemble_host(dmx_ctx* ctx, const double* cur, const double* prev, doubl
     if (jacobian && (rc = dmx_jacobian_download(ctx, jacobian))) return rc;
     return 0;
 }
+int dmx_set_linear_solver(dmx_ctx* ctx, int solver, int restart)
+{
+    if (solver != DMX_SOLVER_BICGSTAB && solver != DMX_SOLVER_RESTARTED_GMRES) return fail(ctx, DMX_ERR_USAGE, "unknown linear solver");
+    ctx->linear_solver = solver;
+    ctx->gmres_restart = restart > 0 ? restart : 10;
+    return 0;
+}
 int dmx_linear_solve(dmx_ctx* ctx, double reduction, int maxit, int preconditioner, int* iterations, double* achieved)
 {
     if (!ctx->d_J) return fail(ctx, DMX_ERR_USAGE, "linear_solve: no pattern");
     DMX_CUDA(cudaSetDevice(ctx->device));
-    return bicgstab(ctx, reduction, maxit, preconditioner, iterations, achieved);
+    return linear_solve(ctx, reduction, maxit, preconditioner, iterations, achieved);
 }
 int dmx_linear_solve_host(dmx_ctx* ctx, const double* values, double* x, const double* b, double reduction, int maxit, int preconditioner,
                           int* iterations, double* achieved)
@@ -623,7 +639,7 @@ int dmx_newton_step(dmx_ctx* ctx, const dmx_newton_params* prm, int* linear_iter
     DMX_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
     DMX_CUDA(cudaMemsetAsync(ctx->d_vec[DMX_VEC_DELTA], 0, (size_t)ctx->n * ctx->b * sizeof(double), ctx->stream));   // deltaU = 0 (:1032)
     double red = 0;
-    rc = bicgstab(ctx, prm->lin_reduction, prm->lin_maxit, prm->preconditioner, linear_iterations, &red);
+    rc = linear_solve(ctx, prm->lin_reduction, prm->lin_maxit, prm->preconditioner, linear_iterations, &red);
     if (rc) return rc;
     DMX_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
     if ((rc = newton_update(ctx, 1.0, shift))) return rc;
@@ -718,7 +734,7 @@ int dmx_newton_solve(dmx_ctx* ctx, const dmx_newton_params* prm, dmx_newton_repo
             if (numSteps == 0 && (rc = dmx_norm2(ctx, DMX_VEC_RESIDUAL, &initialResidual))) return rc;     // solveLinearSystem :495
             DMX_CUDA(cudaMemsetAsync(ctx->d_vec[DMX_VEC_DELTA], 0, bytes, ctx->stream));
             double red = 0;
-            rc = bicgstab(ctx, prm->lin_reduction, prm->lin_maxit, prm->preconditioner, &its, &red);
+            rc = linear_solve(ctx, prm->lin_reduction, prm->lin_maxit, prm->preconditioner, &its, &red);
             if (numSteps < 64) rep->linear_iterations[numSteps] = its;
             rep->linear_iterations_total += its;
             if (rc) { rep->newton_iterations = numSteps; rep->converged = 0; return rc; }

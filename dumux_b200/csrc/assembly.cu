@@ -178,11 +178,14 @@ __device__ __forceinline__ void fill_cell(const AsmParams& P, const MaterialLaw*
         const double2 u = __ldg(reinterpret_cast<const double2*>(P.cur) + C);
         rec[(L::U + 0) * AT_HC] = u.x;
         rec[(L::U + 1) * AT_HC] = u.y;
+        // p0s1 formulation with a per-region wetting phase w (2p/volumevariables.hh:87-96,132-152): the law is evaluated at the
+        // saturation of phase w, krw belongs to phase w, and p1 = p0 + pc (w = 0) or p0 - pc (w = 1; stored as -pc: x - y == x + (-y))
         const MaterialLaw& law = slaws[__ldg(P.region + C)];
-        Law3 c = law_eval3_call(&law, 1 - u.y);
-        rec[(L::ST + 0) * AT_HC] = c.pc;
-        rec[(L::ST + 1) * AT_HC] = P.rho[0] * div_by(c.krw, P.mu[0], P.rmu[0]);
-        rec[(L::ST + 2) * AT_HC] = P.rho[1] * div_by(c.krn, P.mu[1], P.rmu[1]);
+        const bool w1 = law.wetting != 0;
+        Law3 c = law_eval3_call(&law, w1 ? u.y : 1 - u.y);
+        rec[(L::ST + 0) * AT_HC] = w1 ? -c.pc : c.pc;
+        rec[(L::ST + 1) * AT_HC] = P.rho[0] * div_by(w1 ? c.krn : c.krw, P.mu[0], P.rmu[0]);
+        rec[(L::ST + 2) * AT_HC] = P.rho[1] * div_by(w1 ? c.krw : c.krn, P.mu[1], P.rmu[1]);
         if constexpr (JAC) {
             const double epsP = fd_step<ND>(P, u.x, 0), epsS = fd_step<ND>(P, u.y, 1);
             rec[(L::EPS + 0) * AT_HC] = epsP;
@@ -192,10 +195,10 @@ __device__ __forceinline__ void fill_cell(const AsmParams& P, const MaterialLaw*
 #pragma unroll
             for (int k = 0; k < ND; ++k) {
                 const double Snk = fd_defl<ND>(P, k, u.y, epsS);
-                c = law_eval3_call(&law, 1 - Snk);
-                rec[(L::ST + 3 * (1 + k) + 0) * AT_HC] = c.pc;
-                rec[(L::ST + 3 * (1 + k) + 1) * AT_HC] = P.rho[0] * div_by(c.krw, P.mu[0], P.rmu[0]);
-                rec[(L::ST + 3 * (1 + k) + 2) * AT_HC] = P.rho[1] * div_by(c.krn, P.mu[1], P.rmu[1]);
+                c = law_eval3_call(&law, w1 ? Snk : 1 - Snk);
+                rec[(L::ST + 3 * (1 + k) + 0) * AT_HC] = w1 ? -c.pc : c.pc;
+                rec[(L::ST + 3 * (1 + k) + 1) * AT_HC] = P.rho[0] * div_by(w1 ? c.krn : c.krw, P.mu[0], P.rmu[0]);
+                rec[(L::ST + 3 * (1 + k) + 2) * AT_HC] = P.rho[1] * div_by(w1 ? c.krw : c.krn, P.mu[1], P.rmu[1]);
             }
         }
     } else {
@@ -888,12 +891,13 @@ static void dirichlet_state(const dmx_ctx* ctx, int cell, const double* pv, doub
     if (ctx->model == DMX_MODEL_2P) {
         const MaterialLaw& law = ctx->laws[ctx->h_region[cell]];
         const double Sn = pv[1];
-        const double sw = 1 - Sn;
+        const int w = law.wetting ? 1 : 0, nw = 1 - w;
+        const double sw = w ? Sn : 1 - Sn;                     // saturation of the wetting phase
         const double pc = law_pc(law, sw);
         p[0] = pv[0];
-        p[1] = pv[0] + pc;
-        up[0] = ctx->rho[0] * (law_krw(law, sw) / ctx->mu[0]);
-        up[1] = ctx->rho[1] * (law_krn(law, sw) / ctx->mu[1]);
+        p[1] = w ? pv[0] - pc : pv[0] + pc;
+        up[w] = ctx->rho[w] * (law_krw(law, sw) / ctx->mu[w]);
+        up[nw] = ctx->rho[nw] * (law_krn(law, sw) / ctx->mu[nw]);
         rho[0] = ctx->rho[0];
         rho[1] = ctx->rho[1];
     } else {

@@ -131,6 +131,9 @@ struct dmx_ctx {
     std::vector<int> l_ptr, u_ptr;
     int *d_lptr = nullptr, *d_uptr = nullptr;
     unsigned int* d_barrier = nullptr;
+    int linear_solver = DMX_SOLVER_BICGSTAB, gmres_restart = 10;     // dmx_set_linear_solver
+    double* d_gm = nullptr;           // GMRes basis: restart+1 vectors, w, defect
+    int gm_vectors = 0;
     void* skew = nullptr;             // SkewState of ilu_structured.cu (structured-grid ILU sweeps), null: generic kernels
 
     // reductions
@@ -269,6 +272,8 @@ int block_jacobi_setup(dmx_ctx* ctx);
 int block_jacobi_apply(dmx_ctx* ctx, const double* d, double* v);
 int dot(dmx_ctx* ctx, const double* a, const double* b, double* out);
 int bicgstab(dmx_ctx* ctx, double reduction, int maxit, int precond, int* iterations, double* achieved);
+int gmres(dmx_ctx* ctx, double reduction, int maxit, int restart, int precond, int* iterations, double* achieved);
+int linear_solve(dmx_ctx* ctx, double reduction, int maxit, int precond, int* iterations, double* achieved);
 int newton_update(dmx_ctx* ctx, double lambda, double* shift);
 int check_finite(dmx_ctx* ctx, const double* v, size_t len, bool* ok);
 // implemented in ilu_structured.cu

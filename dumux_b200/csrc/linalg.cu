@@ -810,4 +810,164 @@ int bicgstab(dmx_ctx* ctx, double reduction, int maxit, int precond, int* iterat
     return status;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Restarted GMRes: Dune::RestartedGMResSolver::apply restated (what ILURestartedGMResIstlSolver runs,
+// dumux/linear/istlsolvers.hh:660-667; the reference's 2p test uses it, test/porousmediumflow/2p/incompressible/main.cc:134).
+// LEFT-preconditioned GMRes(m): the monitored norm is ||M^-1 (b - A x)||, Arnoldi with modified Gram-Schmidt, Givens rotations
+// on the host (an (m+1) x m Hessenberg matrix), update by back substitution, restart from the recomputed defect.
+// x = DELTA, b = RESIDUAL (not modified).  The basis lives in ctx->d_gm: m+1 basis vectors, w, and the defect.
+// Every Gram-Schmidt coefficient is needed on the host for the QR update, so each dot is one host read.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gm_sub_kernel(size_t len, int b, const double* rhs, const double* Ax, double* out,
+                                                     const unsigned char* __restrict__ owner)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (size_t)gridDim.x * blockDim.x) {
+        const bool own = !owner || owner[i / b];
+        out[i] = own ? rhs[i] - Ax[i] : 0.0;
+    }
+}
+__global__ void __launch_bounds__(256) gm_scale_kernel(size_t len, double f, const double* src, double* dst)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i] * f;
+}
+static void gm_generate_rotation(double dx, double dy, double& cs, double& sn)
+{
+    const double eps = 1e-15;
+    const double ndx = std::fabs(dx), ndy = std::fabs(dy);
+    const double nmax = std::max(ndx, ndy), nmin = std::min(ndx, ndy);
+    const double temp = nmin / nmax;
+    if (ndy < eps) { cs = 1.0; sn = 0.0; }
+    else if (ndx < eps) { cs = 0.0; sn = 1.0; }
+    else if (ndy > ndx) { cs = 1.0 / std::sqrt(1.0 + temp * temp) * temp; sn = 1.0 / std::sqrt(1.0 + temp * temp) * dx * dy / ndx / ndy; }
+    else { cs = 1.0 / std::sqrt(1.0 + temp * temp); sn = 1.0 / std::sqrt(1.0 + temp * temp) * dy / dx; }
+}
+static void gm_apply_rotation(double& dx, double& dy, double cs, double sn)
+{
+    const double temp = cs * dx + sn * dy;
+    dy = -sn * dx + cs * dy;
+    dx = temp;
+}
+
+int gmres(dmx_ctx* ctx, double reduction, int maxit, int restart, int precond, int* iterations, double* achieved)
+{
+    if (ctx->nranks > 1) return fail(ctx, DMX_ERR_USAGE, "restarted GMRes runs on a single domain in this version (use BiCGSTAB for slab-decomposed runs)");
+    const size_t len = (size_t)ctx->n * ctx->b;
+    const int m = restart > 0 ? restart : 10;
+    if (!ctx->d_gm || ctx->gm_vectors < m + 3) {
+        if (ctx->d_gm) cudaFree(ctx->d_gm);
+        ctx->d_gm = nullptr;
+        DMX_CUDA(cudaMalloc((void**)&ctx->d_gm, (size_t)(m + 3) * len * sizeof(double)));
+        ctx->gm_vectors = m + 3;
+    }
+    auto V = [&](int k) { return ctx->d_gm + (size_t)k * len; };
+    double* w = V(m + 1);
+    double* bdef = V(m + 2);
+    double* x = ctx->d_vec[DMX_VEC_DELTA];
+    const double* rhs = ctx->d_vec[DMX_VEC_RESIDUAL];
+    double* t = ctx->d_t;
+    int rc;
+    *iterations = 0;
+    *achieved = 1.0;
+    if (precond == DMX_PRECOND_ILU0) { if ((rc = ilu0_factor(ctx))) return rc; }
+    else if ((rc = block_jacobi_setup(ctx))) return rc;
+
+    auto axpy = [&](double alpha, const double* y, double* xx) -> int {
+        ProfScope ps(ctx, DMX_K_BLAS1);
+        axpy_kernel<<<RED_BLOCKS, 256, 0, ctx->stream>>>(len, alpha, y, xx);
+        DMX_CHECK_LAUNCH();
+        return 0;
+    };
+    auto defect = [&](double* nrm) -> int {          // bdef = b - A x ; v[0] = M^-1 bdef ; ||v[0]||
+        int r;
+        if ((r = launch_spmv(ctx, x, t))) return r;
+        {
+            ProfScope ps(ctx, DMX_K_BLAS1);
+            gm_sub_kernel<<<RED_BLOCKS, 256, 0, ctx->stream>>>(len, ctx->b, rhs, t, bdef, ctx->d_owner);
+            DMX_CHECK_LAUNCH();
+        }
+        if ((r = precond_apply(ctx, precond, bdef, V(0)))) return r;
+        double s2;
+        if ((r = dot(ctx, V(0), V(0), &s2))) return r;
+        *nrm = std::sqrt(s2);
+        return 0;
+    };
+    double norm;
+    if ((rc = defect(&norm))) return rc;
+    const double norm0 = norm;
+    if (!(norm0 == norm0) || std::isinf(norm0)) return DMX_STATUS_NONFINITE;
+    auto conv = [&](double nrm) { return nrm < reduction * norm0 || nrm < 1e-30; };
+    if (conv(norm0)) { *achieved = norm0 > 0 ? 1.0 : 0.0; return 0; }
+
+    const double EPSILON = 1e-80;
+    std::vector<double> s(m + 1), sn(m), cs(m), H((size_t)(m + 1) * (m + 1), 0.0);
+    auto Hm = [&](int r, int c) -> double& { return H[(size_t)r * (m + 1) + c]; };
+    int j = 1;
+    bool converged = false;
+    int status = DMX_STATUS_NOT_CONVERGED;
+    while (j <= maxit && !converged) {
+        int i = 0;
+        {
+            ProfScope ps(ctx, DMX_K_BLAS1);
+            gm_scale_kernel<<<RED_BLOCKS, 256, 0, ctx->stream>>>(len, norm == 0.0 ? 0.0 : 1.0 / norm, V(0), V(0));
+            DMX_CHECK_LAUNCH();
+        }
+        s[0] = norm;
+        for (i = 1; i < m + 1; ++i) s[i] = 0.0;
+        for (i = 0; i < m && j <= maxit && !converged; ++i, ++j) {
+            if ((rc = launch_spmv(ctx, V(i), V(i + 1)))) return rc;
+            if ((rc = precond_apply(ctx, precond, V(i + 1), w))) return rc;
+            for (int k = 0; k < i + 1; ++k) {
+                double h;
+                if ((rc = dot(ctx, V(k), w, &h))) return rc;
+                Hm(k, i) = h;
+                if ((rc = axpy(-h, V(k), w))) return rc;
+            }
+            double ww;
+            if ((rc = dot(ctx, w, w, &ww))) return rc;
+            Hm(i + 1, i) = std::sqrt(ww);
+            *iterations = j;
+            if (!(Hm(i + 1, i) == Hm(i + 1, i)) || std::isinf(Hm(i + 1, i))) return DMX_STATUS_NONFINITE;
+            if (std::fabs(Hm(i + 1, i)) < EPSILON) {
+                *achieved = norm / norm0;
+                ctx->err = "GMRes breakdown (|w| == 0)";
+                return DMX_STATUS_BREAKDOWN;
+            }
+            {
+                ProfScope ps(ctx, DMX_K_BLAS1);
+                gm_scale_kernel<<<RED_BLOCKS, 256, 0, ctx->stream>>>(len, norm == 0.0 ? 0.0 : 1.0 / Hm(i + 1, i), w, V(i + 1));
+                DMX_CHECK_LAUNCH();
+            }
+            for (int k = 0; k < i; ++k) gm_apply_rotation(Hm(k, i), Hm(k + 1, i), cs[k], sn[k]);
+            gm_generate_rotation(Hm(i, i), Hm(i + 1, i), cs[i], sn[i]);
+            gm_apply_rotation(Hm(i, i), Hm(i + 1, i), cs[i], sn[i]);
+            gm_apply_rotation(s[i], s[i + 1], cs[i], sn[i]);
+            norm = std::fabs(s[i + 1]);
+            if (conv(norm)) { converged = true; status = 0; }
+        }
+        // update(): y from the triangular system, x += sum_a y_a v_a accumulated from the last basis vector to the first
+        DMX_CUDA(cudaMemsetAsync(w, 0, len * sizeof(double), ctx->stream));
+        {
+            std::vector<double> y(s);
+            for (int a = i - 1; a >= 0; --a) {
+                double r = s[a];
+                for (int c = a + 1; c < i; ++c) r -= Hm(a, c) * y[c];
+                y[a] = (r == 0.0) ? 0.0 : r / Hm(a, a);
+                if ((rc = axpy(y[a], V(a), w))) return rc;
+            }
+        }
+        if ((rc = axpy(1.0, w, x))) return rc;
+        if (!converged && j < maxit && (rc = defect(&norm))) return rc;
+    }
+    *achieved = norm0 > 0 ? norm / norm0 : 0.0;
+    if (status == DMX_STATUS_NOT_CONVERGED) ctx->err = "GMRes: maximum iterations reached";
+    return status;
+}
+
+// the solver selected with dmx_set_linear_solver (what NewtonSolver::solveLinearSystem calls)
+int linear_solve(dmx_ctx* ctx, double reduction, int maxit, int precond, int* iterations, double* achieved)
+{
+    if (ctx->linear_solver == DMX_SOLVER_RESTARTED_GMRES) return gmres(ctx, reduction, maxit, ctx->gmres_restart, precond, iterations, achieved);
+    return bicgstab(ctx, reduction, maxit, precond, iterations, achieved);
+}
+
 } // namespace dmx

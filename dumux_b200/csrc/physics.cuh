@@ -54,6 +54,8 @@ DMX_HD double spline_eval_derivative(const Spline2& s, double x)
 struct MaterialLaw {
     int kind;
     int regularized;
+    int wetting;                   // wetting phase index (spatialParams.wettingPhase, 2p/volumevariables.hh:132): 0 or 1
+    int pad_;
     double swr, snr;
     double pcEntry, lambda;        // Brooks-Corey
     double alpha, n, m, l;         // van Genuchten

@@ -28,6 +28,7 @@ class Material:
     snr: float = 0.0
     regularize: bool = True
     reg: Tuple[float, ...] = ()        # BC: (pcLowSwe,), VG: (pcLowSwe, pcHighSwe, krnLowSwe, krwHighSwe)
+    wetting: int = 0                   # wetting phase index (spatialParams.wettingPhase): 0 = phase 0 (water), 1 = phase 1
 
 
 @dataclasses.dataclass
@@ -298,9 +299,11 @@ def onep_compressible(cells=(10, 10), lower=None, upper=None, dt=0.002, lognorma
 # spatialparams.hh:46-140).  2-D: y vertical.  `vertical_axis` = dim-1 always (gravity acts along -e_{dim-1}).
 # ------------------------------------------------------------------------------------------------------
 def twop_lens(cells=(48, 32), law="vg", lower=None, upper=None, lens_lower=None, lens_upper=None,
-              dt=250.0, heterogeneity_sigma=0.0, seed=0, bc_params=None, slab=None, plane_rng=False) -> ProblemSpec:
+              dt=250.0, heterogeneity_sigma=0.0, seed=0, bc_params=None, slab=None, plane_rng=False, oilwet=False) -> ProblemSpec:
     """`slab` = (lo, hi): build only those layers of the last axis (see ProblemSpec.slab); `plane_rng`: per-layer
-    heterogeneity streams (implied by `slab`)."""
+    heterogeneity streams (implied by `slab`).  `oilwet`: test_2p_incompressible_tpfa_oilwet (SpatialParams.LensIsOilWet,
+    Problem.EnableGravity false): the lens keeps the outer permeability and pc-kr-Sw parameters but phase 1 wets it
+    (spatialparams.hh:76,105,117-122) and the injection rate is ten times higher (problem.hh:112-113)."""
     dim = len(cells)
     if dim == 2:
         lower = (0.0, 0.0) if lower is None else lower
@@ -319,7 +322,7 @@ def twop_lens(cells=(48, 32), law="vg", lower=None, upper=None, lens_lower=None,
     va = dim - 1
     ctr = cell_centers(cells, lower, upper, slab)
     lens = _in_box(ctr, lens_lower, lens_upper, 1.5e-7)
-    K = np.where(lens, 9.05e-12, 4.6e-10)
+    K = np.where(lens, 9.05e-12, 4.6e-10) if not oilwet else np.full(n, 4.6e-10)
     if heterogeneity_sigma > 0.0:
         if slab is not None or plane_rng:
             K = K * plane_lognormal_multiplier(cells, heterogeneity_sigma, seed, slab)
@@ -333,7 +336,9 @@ def twop_lens(cells=(48, 32), law="vg", lower=None, upper=None, lens_lower=None,
         bp = bc_params or ((500.0, 2.0), (2000.0, 2.0))
         mats = [Material(LAW_BC, bp[0], swr=0.05, reg=(0.01,)),
                 Material(LAW_BC, bp[1], swr=0.18, reg=(0.01,))]
-    rho_w, g = 1000.0, -9.81
+    if oilwet:
+        mats[1] = dataclasses.replace(mats[0], wetting=1)
+    rho_w, g = 1000.0, (0.0 if oilwet else -9.81)
     height = upper[va] - lower[va]
     width = upper[0] - lower[0]
     alpha = 1 + 1.5 / height
@@ -354,14 +359,15 @@ def twop_lens(cells=(48, 32), law="vg", lower=None, upper=None, lens_lower=None,
         vals[dirichlet, 1] = 0.0
         lam = (upper[0] - x) / width
         inlet = (y > upper[va] - eps) & (0.5 < lam) & (lam < 2.0 / 3.0) & ~dirichlet
-        vals[inlet, 1] = -0.04
+        vals[inlet, 1] = -0.04 * 10 if oilwet else -0.04
         bc_type[side], bc_values[side] = t, vals
     init = np.zeros((n, 2))
     init[:, 0] = 1e5 - rho_w * g * (upper[va] - ctr[:, va])
     return ProblemSpec(
         name=f"2p_lens_{dim}d_{law}", model=MODEL_2P, dim=dim, cells=tuple(cells), lower=tuple(lower), upper=tuple(upper),
         K=K, phi=np.full(n, 0.4), region=region, materials=mats, rho=(1000.0, 1460.0), mu=(1e-3, 5.7e-4),
-        bc_type=bc_type, bc_values=bc_values, options=Options(stationary=False, dt=dt), initial=init, slab=slab)
+        bc_type=bc_type, bc_values=bc_values, options=Options(stationary=False, dt=dt, enable_gravity=not oilwet), initial=init,
+        slab=slab)
 
 
 # ------------------------------------------------------------------------------------------------------

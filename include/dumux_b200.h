@@ -30,6 +30,9 @@ enum { DMX_LAW_BROOKSCOREY = 0, DMX_LAW_VANGENUCHTEN = 1 };
    examples/1ptracer/problem_tracer.hh:92-115 */
 enum { DMX_BC_NEUMANN = 0, DMX_BC_DIRICHLET = 1, DMX_BC_NONE = 2, DMX_BC_OUTFLOW = 3 };
 enum { DMX_PRECOND_ILU0 = 0, DMX_PRECOND_BLOCKJACOBI = 1 };
+/* Krylov method behind dmx_linear_solve / dmx_newton_*: ILUBiCGSTABIstlSolver (linear/istlsolvers.hh:636-642, default) or
+   ILURestartedGMResIstlSolver (:660-667) */
+enum { DMX_SOLVER_BICGSTAB = 0, DMX_SOLVER_RESTARTED_GMRES = 1 };
 enum { DMX_STATUS_OK = 0, DMX_STATUS_NOT_CONVERGED = 1, DMX_STATUS_BREAKDOWN = 2, DMX_STATUS_NONFINITE = 3 };
 /* device-resident vectors of a ctx */
 enum {
@@ -122,6 +125,10 @@ int  dmx_set_source(dmx_ctx* ctx, const double* q);
 /* BC: params {pcEntry, lambda}, reg {pcLowSwe}; VG: params {alpha, n, l}, reg {pcLowSwe, pcHighSwe, krnLowSwe, krwHighSwe} */
 int  dmx_set_material(dmx_ctx* ctx, int region, int law, const double* params, double swr, double snr,
                       int regularize, const double* reg);
+/* FVSpatialParams::wettingPhase of a region (porousmediumflow/2p/volumevariables.hh:87-96,132-152; e.g. the oil-wet lens of
+   test_2p_incompressible_tpfa_oilwet, test/porousmediumflow/2p/incompressible/spatialparams.hh:117-122): 0 (default) = phase 0
+   wets, 1 = phase 1 wets.  Call after dmx_set_material(region, ...). */
+int  dmx_set_wetting_phase(dmx_ctx* ctx, int region, int phase);
 int  dmx_set_fluids(dmx_ctx* ctx, const double* density, const double* viscosity);
 int  dmx_set_fluid_table(dmx_ctx* ctx, int nT, int nP, double Tmin, double Tmax, const double* pmin, const double* pmax,
                          const double* density, const double* viscosity, double temperature);
@@ -155,6 +162,9 @@ int  dmx_assemble(dmx_ctx* ctx, int with_jacobian);
 int  dmx_assemble_host(dmx_ctx* ctx, const double* cur, const double* prev, double* residual, double* jacobian);
 /* IstlIterativeLinearSolver::solve(A, x, b) (linear/istlsolvers.hh:273,457-464): fresh preconditioner + BiCGSTAB,
    Jacobian * DELTA = RESIDUAL, DELTA zeroed first (newtonsolver.hh:1032). */
+/* selects the Krylov method (DMX_SOLVER_*); restart = LinearSolver.GMResRestart (<= 0: 10, linearsolverparameters.hh:115,138).
+   For GMRes `achieved_reduction` refers to the preconditioned defect, as in Dune::RestartedGMResSolver. */
+int  dmx_set_linear_solver(dmx_ctx* ctx, int solver, int restart);
 int  dmx_linear_solve(dmx_ctx* ctx, double reduction, int maxit, int preconditioner, int* iterations, double* achieved_reduction);
 /* host-buffer form: A values, x (in: initial guess, out: solution), b */
 int  dmx_linear_solve_host(dmx_ctx* ctx, const double* values, double* x, const double* b, double reduction, int maxit,

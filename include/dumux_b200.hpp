@@ -269,7 +269,8 @@ class GpuILUBiCGSTABSolver {
 public:
     //! LinearSolverParameters defaults (linearsolverparameters.hh:56-73): maxit 250, reduction 1e-13 -- NewtonSolver
     //! overrides the reduction with LinearSolver.ResidualReduction = 1e-6 through setResidualReduction (newtonsolver.hh:232)
-    explicit GpuILUBiCGSTABSolver(std::shared_ptr<Context> ctx) : ctx_(std::move(ctx)) {}
+    explicit GpuILUBiCGSTABSolver(std::shared_ptr<Context> ctx) : GpuILUBiCGSTABSolver(std::move(ctx), DMX_SOLVER_BICGSTAB, 0) {}
+    virtual ~GpuILUBiCGSTABSolver() = default;
 
     //! istlsolvers.hh:273: host matrix and vectors; x is the initial guess and the result
     IstlSolverResult solve(BCRSMatrix& A, BlockVector& x, BlockVector& b)
@@ -305,7 +306,14 @@ public:
     void setResidualReduction(double r) { reduction_ = r; }       // :350
     void setMaxIter(std::size_t i) { maxIter_ = static_cast<int>(i); }
     void setPreconditioner(int p) { precond_ = p; }               // DMX_PRECOND_ILU0 (default) or DMX_PRECOND_BLOCKJACOBI
-    std::string name() const { return "ILU0 preconditioned BiCGSTAB solver (B200)"; }
+    virtual std::string name() const { return "ILU0 preconditioned BiCGSTAB solver (B200)"; }
+
+protected:
+    //! the Krylov method is a property of the context (dmx_set_linear_solver): one solver object per context
+    GpuILUBiCGSTABSolver(std::shared_ptr<Context> ctx, int solver, int restart) : ctx_(std::move(ctx))
+    {
+        ctx_->check(dmx_set_linear_solver(ctx_->get(), solver, restart));
+    }
 
 private:
     void ensurePattern_(const BCRSMatrix& A)
@@ -317,6 +325,16 @@ private:
     std::shared_ptr<Context> ctx_;
     double reduction_ = 1e-13;
     int maxIter_ = 250, precond_ = DMX_PRECOND_ILU0;
+};
+
+// =====================================================================================================================
+//! ILURestartedGMResIstlSolver (linear/istlsolvers.hh:660-667; what test/porousmediumflow/2p/incompressible/main.cc:134 uses):
+//! same interface, Dune::RestartedGMResSolver instead of BiCGSTAB; restart = LinearSolver.GMResRestart (default 10)
+class GpuILURestartedGMResSolver : public GpuILUBiCGSTABSolver {
+public:
+    explicit GpuILURestartedGMResSolver(std::shared_ptr<Context> ctx, int restart = 10)
+    : GpuILUBiCGSTABSolver(std::move(ctx), DMX_SOLVER_RESTARTED_GMRES, restart) {}
+    std::string name() const override { return "ILU0 preconditioned restarted GMRes solver (B200)"; }
 };
 
 // =====================================================================================================================

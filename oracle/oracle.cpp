@@ -98,6 +98,7 @@ struct Law {
            pcDerivativeHighSweThreshold = 0;
     Spline2 pcSpline, krwSpline, krnSpline;
     pow_fn pw = det_pow_;
+    int wetting = 0;               // wetting phase index (spatialParams.wettingPhase, 2p/volumevariables.hh:132)
 
     // efftoabsdefaultpolicy.hh:106-152
     double swToSwe(double sw) const { return (sw - swr) / (1.0 - swr - snr); }
@@ -337,6 +338,7 @@ struct orc_problem {
     std::vector<int> bcType[6];
     std::vector<double> bcVal[6];
     std::vector<int> rowptr, colidx;
+    int linearSolver = ORC_SOLVER_BICGSTAB, gmresRestart = 10;   // orc_set_linear_solver
     bool volumeFluxMode = false;               // upwind term = mobility only (examples/1ptracer/main.cc:170)
 
     // ---- grid geometry: YaspGrid equidistant / tensor coordinates, AxisAlignedCubeGeometry [DUNE-ext] ----
@@ -406,19 +408,22 @@ struct orc_problem {
             v.rho[1] = v.mu[1] = v.mob[1] = 0.0; v.pc = 0.0;
             return;
         }
+        // p0s1 formulation (2p/volumevariables.hh:133-152): priVars = (p of phase 0, S of phase 1); the law is evaluated at
+        // the saturation of the WETTING phase; p1 = p0 + pc if phase 0 wets, p0 - pc if phase 1 wets
         const Law& law = laws[region[cell]];
+        const int w = law.wetting, nw = 1 - w;
         const double Sn = priVars[1];
         v.p[0] = priVars[0];
         v.S[1] = Sn;
         v.S[0] = 1 - Sn;
-        v.pc = law.pc(v.S[0]);
-        v.p[1] = priVars[0] + v.pc;
+        v.pc = law.pc(v.S[w]);
+        v.p[1] = (w == 1) ? priVars[0] - v.pc : priVars[0] + v.pc;
         for (int ph = 0; ph < 2; ++ph) {
             v.mu[ph] = fluids.viscosity(ph, v.p[ph]);
             v.rho[ph] = fluids.density(ph, v.p[ph]);
         }
-        v.mob[0] = law.krw(v.S[0]) / v.mu[0];
-        v.mob[1] = law.krn(v.S[0]) / v.mu[1];
+        v.mob[w] = law.krw(v.S[w]) / v.mu[w];                           // :90-96
+        v.mob[nw] = law.krn(v.S[w]) / v.mu[nw];
     }
 
     // ---- TPFA transmissibility: dumux/discretization/cellcentered/tpfa/computetransmissibility.hh:69-80 ----
@@ -911,6 +916,102 @@ int bicgstab(size_t N, Op&& op, Prec&& prec, Dot&& sp, double* x, const double* 
     return status;
 }
 
+// Dune::RestartedGMResSolver::apply (dune-istl solvers.hh) [DUNE-ext, restated from the published algorithm]: LEFT-preconditioned
+// GMRes(m) -- the monitored norm is that of the PRECONDITIONED defect M^-1(b - A x) --, Arnoldi with modified Gram-Schmidt,
+// Givens rotations (generatePlaneRotation / applyPlaneRotation), update() by back substitution with the correction added on
+// the fly from the last basis vector to the first, restart from the recomputed defect.  Iterations count operator applications.
+inline void gmresGenerateRotation(double dx, double dy, double& cs, double& sn)
+{
+    const double eps = 1e-15;
+    const double ndx = std::fabs(dx), ndy = std::fabs(dy);
+    const double nmax = std::max(ndx, ndy), nmin = std::min(ndx, ndy);
+    const double temp = nmin / nmax;
+    if (ndy < eps) { cs = 1.0; sn = 0.0; }
+    else if (ndx < eps) { cs = 0.0; sn = 1.0; }
+    else if (ndy > ndx) { cs = 1.0 / std::sqrt(1.0 + temp * temp) * temp; sn = 1.0 / std::sqrt(1.0 + temp * temp) * dx * dy / ndx / ndy; }
+    else { cs = 1.0 / std::sqrt(1.0 + temp * temp); sn = 1.0 / std::sqrt(1.0 + temp * temp) * dy / dx; }
+}
+inline void gmresApplyRotation(double& dx, double& dy, double cs, double sn)
+{
+    const double temp = cs * dx + sn * dy;
+    dy = -sn * dx + cs * dy;
+    dx = temp;
+}
+template <class Op, class Prec, class Dot>
+int restartedGmres(size_t N, Op&& op, Prec&& prec, Dot&& sp, double* x, const double* rhs, double reduction, int maxit, int restart,
+                   int* iterations, double* achieved)
+{
+    const int m = restart;
+    const double EPSILON = 1e-80;
+    std::vector<double> s(m + 1), sn(m), cs(m), b(rhs, rhs + N), w(N), tmp(N);
+    std::vector<std::vector<double>> H(m + 1, std::vector<double>(m + 1, 0.0)), v(m + 1, std::vector<double>(N, 0.0));
+    auto defect = [&]() {                                   // b = rhs - A x ; v[0] = M^-1 b
+        op(x, tmp.data());
+        for (size_t i = 0; i < N; ++i) b[i] = rhs[i] - tmp[i];
+        std::fill(v[0].begin(), v[0].end(), 0.0);
+        prec(v[0].data(), b.data());
+        return std::sqrt(sp(v[0].data(), v[0].data()));
+    };
+    double norm = defect();
+    const double norm0 = norm;
+    *iterations = 0;
+    *achieved = 1.0;
+    if (!(norm0 == norm0) || std::isinf(norm0)) return 3;
+    auto conv = [&](double nrm) { return nrm < reduction * norm0 || nrm < 1e-30; };
+    if (conv(norm0)) { *achieved = norm0 > 0 ? 1.0 : 0.0; return 0; }
+    int j = 1;
+    bool converged = false;
+    int status = 1;
+    while (j <= maxit && !converged) {
+        int i = 0;
+        {
+            const double f = (norm == 0.0) ? 0.0 : 1.0 / norm;
+            for (size_t q = 0; q < N; ++q) v[0][q] *= f;
+        }
+        s[0] = norm;
+        for (i = 1; i < m + 1; ++i) s[i] = 0.0;
+        for (i = 0; i < m && j <= maxit && !converged; ++i, ++j) {
+            std::fill(w.begin(), w.end(), 0.0);
+            op(v[i].data(), v[i + 1].data());
+            prec(w.data(), v[i + 1].data());
+            for (int k = 0; k < i + 1; ++k) {
+                H[k][i] = sp(v[k].data(), w.data());
+                const double mh = -H[k][i];
+                for (size_t q = 0; q < N; ++q) w[q] += mh * v[k][q];
+            }
+            H[i + 1][i] = std::sqrt(sp(w.data(), w.data()));
+            if (!(H[i + 1][i] == H[i + 1][i]) || std::isinf(H[i + 1][i])) { *iterations = j; return 3; }
+            if (std::fabs(H[i + 1][i]) < EPSILON) { *iterations = j; *achieved = norm / norm0; return 2; }
+            {
+                const double f = (norm == 0.0) ? 0.0 : 1.0 / H[i + 1][i];
+                for (size_t q = 0; q < N; ++q) v[i + 1][q] = w[q] * f;
+            }
+            for (int k = 0; k < i; ++k) gmresApplyRotation(H[k][i], H[k + 1][i], cs[k], sn[k]);
+            gmresGenerateRotation(H[i][i], H[i + 1][i], cs[i], sn[i]);
+            gmresApplyRotation(H[i][i], H[i + 1][i], cs[i], sn[i]);
+            gmresApplyRotation(s[i], s[i + 1], cs[i], sn[i]);
+            norm = std::fabs(s[i + 1]);
+            *iterations = j;
+            if (conv(norm)) { converged = true; status = 0; }
+        }
+        // update(w, i, H, s, v): back substitution, x += sum_a y_a v_a accumulated from a = i-1 down to 0
+        std::fill(w.begin(), w.end(), 0.0);
+        {
+            std::vector<double> y(s);
+            for (int a = i - 1; a >= 0; --a) {
+                double r = s[a];
+                for (int c = a + 1; c < i; ++c) r -= H[a][c] * y[c];
+                y[a] = (r == 0.0) ? 0.0 : r / H[a][a];
+                for (size_t q = 0; q < N; ++q) w[q] += y[a] * v[a][q];
+            }
+        }
+        for (size_t q = 0; q < N; ++q) x[q] += w[q];
+        if (!converged && j < maxit) norm = defect();
+    }
+    *achieved = norm0 > 0 ? norm / norm0 : 0.0;
+    return status;
+}
+
 double nowSec()
 {
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -1018,6 +1119,11 @@ void orc_set_material(orc_problem* p, int region, int law, const double* params,
     }
     l.init();
 }
+void orc_set_wetting_phase(orc_problem* p, int region, int phase)
+{
+    if ((int)p->laws.size() <= region) p->laws.resize(region + 1);
+    p->laws[region].wetting = phase ? 1 : 0;
+}
 void orc_set_fluids(orc_problem* p, const double* rho, const double* mu)
 {
     p->fluids.tabulated = false;
@@ -1123,6 +1229,35 @@ int orc_ilu0_bicgstab(int n, int b, const int* rowptr, const int* colidx, const 
         [&](const double* a, const double* c) { return dot(N, a, c); }, x, rhs, reduction, maxit, iterations, achieved);
 }
 
+// ILURestartedGMResIstlSolver (dumux/linear/istlsolvers.hh:660-667): SeqILU(0) + Dune::RestartedGMResSolver,
+// restart = LinearSolver.GMResRestart (default 10, linearsolverparameters.hh:115-116,138)
+int orc_ilu0_gmres(int n, int b, const int* rowptr, const int* colidx, const double* values, double* x, const double* rhs,
+                   double reduction, int maxit, int restart, int* iterations, double* achieved)
+{
+    const size_t N = (size_t)n * b;
+    std::vector<double> ilu((size_t)rowptr[n] * b * b);
+    std::memcpy(ilu.data(), values, sizeof(double) * ilu.size());
+    if (ilu0Factor(n, b, rowptr, colidx, ilu.data())) return 2;
+    return restartedGmres(
+        N, [&](const double* in, double* out) { spmv(n, b, rowptr, colidx, values, in, out); },
+        [&](double* v, const double* d) { ilu0Apply(n, b, rowptr, colidx, ilu.data(), v, d); },
+        [&](const double* a, const double* c) { return dot(N, a, c); }, x, rhs, reduction, maxit, restart, iterations, achieved);
+}
+void orc_set_linear_solver(orc_problem* p, int kind, int restart)
+{
+    p->linearSolver = kind;
+    p->gmresRestart = restart > 0 ? restart : 10;
+}
+// the solver selected with orc_set_linear_solver (what NewtonSolver::solveLinearSystem calls)
+static int orcLinearSolve(orc_problem* p, const double* values, double* x, const double* rhs, double reduction, int maxit, int* iterations,
+                          double* achieved)
+{
+    if (p->linearSolver == ORC_SOLVER_GMRES)
+        return orc_ilu0_gmres(p->n, p->b, p->rowptr.data(), p->colidx.data(), values, x, rhs, reduction, maxit, p->gmresRestart, iterations,
+                              achieved);
+    return orc_ilu0_bicgstab(p->n, p->b, p->rowptr.data(), p->colidx.data(), values, x, rhs, reduction, maxit, iterations, achieved);
+}
+
 // Newton loop at fixed dt: dumux/nonlinear/newtonsolver.hh:976-1072 (solveImpl_), newtonProceed :428-446,
 // newtonUpdate :543-557, shift :1138-1144, newtonConverged :657-666 (shift criterion only, defaults :1213-1247)
 int orc_newton_solve(orc_problem* p, double* u, const double* prev, double lin_reduction, int lin_maxit,
@@ -1153,8 +1288,7 @@ int orc_newton_solve(orc_problem* p, double* u, const double* prev, double lin_r
         std::fill(delta.begin(), delta.end(), 0.0);
         int its = 0;
         double red = 0;
-        const int st = orc_ilu0_bicgstab(n, b, p->rowptr.data(), p->colidx.data(), J.data(), delta.data(), r.data(),
-                                         lin_reduction, lin_maxit, &its, &red);
+        const int st = orcLinearSolve(p, J.data(), delta.data(), r.data(), lin_reduction, lin_maxit, &its, &red);
         double t2 = nowSec();
         if (numSteps < 64) rep->linear_iterations[numSteps] = its;
         rep->linear_iterations_total += its;
@@ -1223,8 +1357,7 @@ int orc_newton_solve_ex(orc_problem* p, double* u, const double* prev, double li
         std::fill(delta.begin(), delta.end(), 0.0);
         int its = 0;
         double red = 0;
-        const int st = orc_ilu0_bicgstab(n, b, p->rowptr.data(), p->colidx.data(), J.data(), delta.data(), r.data(),
-                                         lin_reduction, lin_maxit, &its, &red);
+        const int st = orcLinearSolve(p, J.data(), delta.data(), r.data(), lin_reduction, lin_maxit, &its, &red);
         if (numSteps < 64) rep->linear_iterations[numSteps] = its;
         rep->linear_iterations_total += its;
         if (st != 0) { rep->newton_iterations = numSteps; rep->converged = 0; return st; }

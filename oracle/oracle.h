@@ -38,6 +38,7 @@ typedef struct {
 
 enum { ORC_MODEL_1P = 1, ORC_MODEL_2P = 2 };
 enum { ORC_LAW_BROOKSCOREY = 0, ORC_LAW_VANGENUCHTEN = 1 };
+enum { ORC_SOLVER_BICGSTAB = 0, ORC_SOLVER_GMRES = 1 };   /* ILUBiCGSTABIstlSolver / ILURestartedGMResIstlSolver */
 enum { ORC_BC_NEUMANN = 0, ORC_BC_DIRICHLET = 1, ORC_BC_NONE = 2, ORC_BC_OUTFLOW = 3 };
 /* sides: 0 -x, 1 +x, 2 -y, 3 +y, 4 -z, 5 +z (YaspGrid indexInInside) */
 
@@ -54,6 +55,8 @@ void orc_set_source(orc_problem* p, const double* q);
 /* BC: params = {pcEntry, lambda}, reg = {pcLowSwe}; VG: params = {alpha, n, l}, reg = {pcLowSwe, pcHighSwe, krnLowSwe, krwHighSwe} */
 void orc_set_material(orc_problem* p, int region, int law, const double* params, double swr, double snr,
                       int regularize, const double* reg);
+/* FVSpatialParams::wettingPhase per region (2p/volumevariables.hh:132; 0 = phase 0 wets, the default) */
+void orc_set_wetting_phase(orc_problem* p, int region, int phase);
 void orc_set_fluids(orc_problem* p, const double* rho, const double* mu);
 /* tabulated liquid (dumux/material/components/tabulatedcomponent.hh): tables values[iT + iP*nT], per-temperature pressure range pmin[nT], pmax[nT] */
 void orc_set_fluid_table(orc_problem* p, int nT, int nP, double Tmin, double Tmax, const double* pmin, const double* pmax,
@@ -76,6 +79,12 @@ void orc_volvars(orc_problem* p, const double* cur, double* out);
 int  orc_ilu0_bicgstab(int n, int b, const int* rowptr, const int* colidx, const double* values,
                        double* x, const double* rhs, double reduction, int maxit,
                        int* iterations, double* achieved_reduction);
+/* ILURestartedGMResIstlSolver (istlsolvers.hh:660-667): left-preconditioned GMRes(restart); `achieved` refers to the
+   PRECONDITIONED defect, which is what Dune::RestartedGMResSolver monitors */
+int  orc_ilu0_gmres(int n, int b, const int* rowptr, const int* colidx, const double* values, double* x, const double* rhs,
+                    double reduction, int maxit, int restart, int* iterations, double* achieved_reduction);
+/* linear solver used by orc_newton_solve(_ex) / orc_run_timeloop: ORC_SOLVER_*; restart <= 0: 10 (LinearSolver.GMResRestart) */
+void orc_set_linear_solver(orc_problem* p, int kind, int restart);
 /* standalone pieces for kernel-level parity */
 int  orc_ilu0_factor(int n, int b, const int* rowptr, const int* colidx, const double* values, double* ilu);
 void orc_ilu0_apply(int n, int b, const int* rowptr, const int* colidx, const double* ilu, double* v, const double* d);

@@ -65,6 +65,7 @@ def lib():
         L.orc_set_cell_fields.argtypes = [vp, _dp, _dp, _ip]
         L.orc_set_source.argtypes = [vp, _dp]
         L.orc_set_material.argtypes = [vp, C.c_int, C.c_int, _dp, C.c_double, C.c_double, C.c_int, _dp]
+        L.orc_set_wetting_phase.argtypes = [vp, C.c_int, C.c_int]
         L.orc_set_fluids.argtypes = [vp, _dp, _dp]
         L.orc_set_fluid_table.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_double, _dp, _dp, _dp, _dp, C.c_double]
         L.orc_side_faces.argtypes = [vp, C.c_int]
@@ -83,6 +84,10 @@ def lib():
         L.orc_ilu0_bicgstab.argtypes = [C.c_int, C.c_int, _ip, _ip, _dp, _dp, _dp, C.c_double, C.c_int,
                                         C.POINTER(C.c_int), C.POINTER(C.c_double)]
         L.orc_ilu0_bicgstab.restype = C.c_int
+        L.orc_ilu0_gmres.argtypes = [C.c_int, C.c_int, _ip, _ip, _dp, _dp, _dp, C.c_double, C.c_int, C.c_int,
+                                     C.POINTER(C.c_int), C.POINTER(C.c_double)]
+        L.orc_ilu0_gmres.restype = C.c_int
+        L.orc_set_linear_solver.argtypes = [vp, C.c_int, C.c_int]
         L.orc_ilu0_factor.argtypes = [C.c_int, C.c_int, _ip, _ip, _dp, _dp]
         L.orc_ilu0_factor.restype = C.c_int
         L.orc_ilu0_apply.argtypes = [C.c_int, C.c_int, _ip, _ip, _dp, _dp, _dp]
@@ -151,6 +156,7 @@ class Oracle:
             reg = np.ascontiguousarray(m.reg if len(m.reg) else [0.01, 0.99, 0.1, 0.9], dtype=np.float64)
             L.orc_set_material(self.h, r, m.law, np.ascontiguousarray(m.params, dtype=np.float64), m.swr, m.snr,
                                int(m.regularize), reg)
+            L.orc_set_wetting_phase(self.h, r, int(m.wetting))
         if spec.fluid_table is not None:
             t = spec.fluid_table
             L.orc_set_fluid_table(self.h, t["nT"], t["nP"], t["Tmin"], t["Tmax"],
@@ -209,6 +215,17 @@ class Oracle:
         out = np.zeros((self.n, 12))
         lib().orc_volvars(self.h, cur, out)
         return out
+
+    def set_linear_solver(self, kind, restart=10):
+        """kind: 'bicgstab' (ILUBiCGSTABIstlSolver) or 'gmres' (ILURestartedGMResIstlSolver); used by newton()/run_timeloop()."""
+        lib().orc_set_linear_solver(self.h, {"bicgstab": 0, "gmres": 1}[kind], restart)
+
+    def solve_gmres(self, values, rhs, reduction=1e-6, maxit=250, restart=10, x0=None):
+        x = np.zeros(self.n * self.b) if x0 is None else np.ascontiguousarray(x0, dtype=np.float64).copy()
+        its, red = C.c_int(0), C.c_double(0)
+        st = lib().orc_ilu0_gmres(self.n, self.b, self.rowptr, self.colidx, np.ascontiguousarray(values),
+                                  x, np.ascontiguousarray(rhs), reduction, maxit, restart, C.byref(its), C.byref(red))
+        return x, st, its.value, red.value
 
     def solve(self, values, rhs, reduction=1e-6, maxit=250, x0=None):
         x = np.zeros(self.n * self.b) if x0 is None else np.ascontiguousarray(x0, dtype=np.float64).copy()

@@ -66,6 +66,24 @@ def test_2p_lens(engine_factory, law, cells):
     assert rerr <= 1e-13 and jerr <= RTOL, (rerr, jerr)
 
 
+@pytest.mark.parametrize("cells", [(48, 32), (20, 12, 9)])
+def test_2p_oilwet_lens(engine_factory, cells):
+    """Per-region wetting phase (2p/volumevariables.hh:87-96,132-152; test_2p_incompressible_tpfa_oilwet): in the lens phase 1
+    wets, p1 = p0 - pc, krw belongs to phase 1.  Saturations span the regularised branches on both sides; bit-identical."""
+    spec = problems.twop_lens(cells, law="vg", oilwet=True, dt=130.0)
+    rng = np.random.RandomState(11)
+    cur = _perturbed(spec, 4)
+    cur[:, 1] = rng.choice([-0.01, 0.0, 1e-9, 0.03, 0.3, 0.6, 0.9, 0.97, 1.0, 1.02], size=cur.shape[0])
+    prev = _perturbed(spec, 5, ds=0.9)
+    rerr, jerr, (res_o, jac_o, res_g, jac_g) = _compare(spec, engine_factory, cur, prev)
+    assert np.array_equal(res_g, res_o) and np.array_equal(jac_g, jac_o), (rerr, jerr)
+    # the wetting phase matters: the same state with a water-wet lens gives another residual
+    spec_ww = problems.twop_lens(cells, law="vg", oilwet=True, dt=130.0)
+    spec_ww.materials[1] = spec_ww.materials[0]
+    res_ww, _ = Oracle(spec_ww).assemble(cur, prev)
+    assert np.abs(res_ww - res_o).max() > 1e-6 * np.abs(res_o).max()
+
+
 def test_2p_saturation_extremes(engine_factory):
     """Regularised branches: S_n < 0, S_n = 0, S_w below the low-saturation threshold, S_w > 1."""
     spec = problems.twop_lens((16, 8, 6), law="vg")

@@ -96,6 +96,34 @@ def test_ilu_bicgstab_matches_oracle(engine_factory, spec):
     assert np.linalg.norm(r) <= 1.01e-8 * np.linalg.norm(res)
 
 
+@pytest.mark.parametrize("restart", [10, 4])
+@pytest.mark.parametrize("spec", [problems.onep_incompressible((40, 40)), problems.twop_lens((48, 32), law="vg"),
+                                  problems.twop_lens((16, 12, 10), law="bc", heterogeneity_sigma=0.5)],
+                         ids=["1p2d", "2p2d", "2p3d"])
+def test_ilu_gmres_matches_oracle(engine_factory, spec, restart):
+    """ILURestartedGMResIstlSolver (istlsolvers.hh:660-667): same iteration count, same achieved (preconditioned) reduction and the
+    same solution as the Dune::RestartedGMResSolver restatement; only the dot-product reduction tree differs."""
+    o, res, jac = _system(spec)
+    e = engine_factory(spec)
+    e.set_linear_solver("gmres", restart)
+    xo, sto, ito, redo = o.solve_gmres(jac, res, reduction=1e-8, maxit=400, restart=restart)
+    xg, stg, itg, redg = e.solve(jac, res, reduction=1e-8, maxit=400)
+    assert sto == 0 and stg == 0
+    assert itg == ito, (itg, ito)
+    assert redg == pytest.approx(redo, rel=1e-6)
+    assert np.linalg.norm(xg - xo) <= 1e-9 * np.linalg.norm(xo)
+    # stopping rules: iteration limit -> status 1 with exactly maxit operator applications
+    xg, stg, itg, redg = e.solve(jac, res, reduction=1e-30, maxit=7)
+    xo, sto, ito, redo = o.solve_gmres(jac, res, reduction=1e-30, maxit=7, restart=restart)
+    assert (stg, itg) == (sto, ito) == (1, 7)
+    assert np.linalg.norm(xg - xo) <= 1e-9 * np.linalg.norm(xo)
+    # back to the default solver on the same context
+    e.set_linear_solver("bicgstab")
+    xb, stb, itb, redb = e.solve(jac, res, reduction=1e-8)
+    xob, stob, itob, redob = o.solve(jac, res, reduction=1e-8)
+    assert stb == 0 and itb == itob
+
+
 def test_generic_bcrs_2x2_laplacian(engine_factory):
     """test/linear/test_linearsolver.cc: 2x2-block Laplacian (dune-istl setupLaplacian), asserts convergence."""
     N = 20

@@ -69,6 +69,27 @@ def test_2p_lens_timeloop_golden(engine_factory):
         assert np.all((d <= 1.5e-7) | (d <= 1e-2 * np.abs(ref))), name
 
 
+def test_2p_oilwet_timeloop_golden(engine_factory):
+    """test_2p_incompressible_tpfa_oilwet: oil-wet lens, no gravity, dt0 = 130 s, ILU0-GMRes(10) as in the reference's main.cc:134
+    -> nine time steps to t = 3000 s (the golden file is output number 9), same Newton counts and time steps as the oracle,
+    fields vs the oracle (1e-8) and vs test_2p_incompressible_tpfa_oilwet-reference.vtu."""
+    spec = problems.twop_lens((48, 32), law="vg", oilwet=True, dt=130.0)
+    o = Oracle(spec)
+    o.set_linear_solver("gmres", 10)
+    uo, nso, itso, dtso = o.run_timeloop(spec.initial, 3000.0, 130.0)
+    e = engine_factory(spec)
+    e.set_linear_solver("gmres", 10)
+    ug, itsg, dtsg = e.run_timeloop(spec.initial, 3000.0, 130.0)
+    assert len(itsg) == 9 and list(itsg) == list(itso), (itsg, itso)
+    assert np.allclose(dtsg, dtso, rtol=0, atol=0)
+    uo2, ug2 = uo.reshape(-1, 2), ug.reshape(-1, 2)
+    assert _rel_l2(ug2[:, 0], uo2[:, 0]) <= 1e-8
+    assert _rel_l2(ug2[:, 1], uo2[:, 1]) <= 1e-8
+    g = np.load(os.path.join(GOLDEN, "test_2p_incompressible_tpfa_oilwet.npz"))
+    assert np.abs(ug2[:, 1] - g["S_napl"]).max() < 5e-6
+    assert np.abs(ug2[:, 0] / g["p_aq"] - 1).max() < 2e-5
+
+
 def test_block_jacobi_newton_same_count(engine_factory):
     """A different preconditioner changes BiCGSTAB counts but must not change the Newton count or the fields."""
     spec = problems.twop_lens((24, 16), law="bc")

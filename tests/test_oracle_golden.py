@@ -103,6 +103,38 @@ def test_2p_lens_48x32_reference_vtu(lens_run):
     assert np.abs(u[:, 0] / g["p_aq"] - 1).max() < 1e-5
 
 
+def test_2p_oilwet_lens_reference_vtu():
+    """test_2p_incompressible_tpfa_oilwet (SpatialParams.LensIsOilWet, no gravity, DtInitial 130, ILURestartedGMResIstlSolver as in
+    main.cc:134) -> test_2p_incompressible_tpfa_oilwet-reference.vtu, which is the NINTH output file: the run must reach
+    t = 3000 s in exactly nine time steps, which pins the per-region wetting phase of TwoPVolumeVariables
+    (2p/volumevariables.hh:87-96,132-152), the Newton counts and the time-step control together.  (ILU0-BiCGSTAB breaks down in
+    the very first Newton iteration of this run -- rho == 0 exactly, the non-wetting rows are solved by the ILU sweep -- which
+    is why the reference's test uses GMRes.)"""
+    spec = problems.twop_lens((48, 32), law="vg", oilwet=True, dt=130.0)
+    o = Oracle(spec)
+    o.set_linear_solver("gmres", 10)
+    u, nsteps, its, dts = o.run_timeloop(spec.initial, 3000.0, 130.0)
+    assert nsteps == 9 and dts[0] == 130.0 and abs(sum(dts) - 3000.0) < 1e-9
+    g = np.load(os.path.join(GOLDEN, "test_2p_incompressible_tpfa_oilwet.npz"))
+    vv = o.volvars(u)
+    cols = {"S_aq": 0, "S_napl": 1, "p_aq": 2, "p_napl": 3, "rho_aq": 4, "rho_napl": 5, "mob_aq": 6, "mob_napl": 7, "pc": 8,
+            "porosity": 9}
+    for name, c in cols.items():
+        assert _fuzzy_ok(vv[:, c], g[name].astype(np.float64)), name
+    # far tighter than the reference's bar: Float32 storage is the limit
+    u2 = u.reshape(-1, 2)
+    assert np.abs(u2[:, 1] - g["S_napl"]).max() < 5e-6
+    assert np.abs(u2[:, 0] / g["p_aq"] - 1).max() < 2e-5
+    assert np.abs(vv[:, 8] - g["pc"]).max() < 0.05                 # Pa, of up to 2530
+    # inside the oil-wet lens the non-wetting (water) pressure exceeds the oil pressure: p_napl = p_aq - pc
+    lens = spec.region == 1
+    assert np.all(vv[lens, 3] <= vv[lens, 2]) and np.all(vv[~lens, 3] >= vv[~lens, 2])
+    # BiCGSTAB on the same run: breakdown in the first linear solve -> the time step is halved until it is tiny
+    ob = Oracle(spec)
+    ub, nb, itsb, dtsb = ob.run_timeloop(spec.initial, 3000.0, 130.0)
+    assert dtsb[0] < 130.0
+
+
 def test_2p_lens_newton_counts_are_stable(lens_run):
     """The time-step / Newton control (newtonsolver.hh:784-798, timeloop.hh) is deterministic: pin the sequence so that a
     change in the oracle's control flow is noticed."""

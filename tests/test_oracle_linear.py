@@ -155,6 +155,55 @@ def test_bicgstab_stopping_rules():
     assert L.orc_ilu0_bicgstab(n, 2, rp, ci, v, x, bad, 1e-6, 250, C.byref(its), C.byref(red)) == 3
 
 
+@pytest.mark.parametrize("b,N,restart", [(1, 12, 10), (2, 2, 10), (2, 15, 10), (2, 15, 3), (2, 15, 40)])
+def test_gmres_converges_to_direct_solution(b, N, restart):
+    """ILURestartedGMResIstlSolver restatement: converges to the direct solution for every restart length; the reported
+    reduction is that of the PRECONDITIONED defect (left preconditioning), monotone in the iteration limit."""
+    n, rp, ci, v = _block_laplacian(N, b)
+    A = _to_scipy(n, b, rp, ci, v)
+    rhs = np.random.RandomState(4).uniform(-1, 1, n * b)
+    import ctypes as C
+    L = O.lib()
+    x = np.zeros(n * b); its, red = C.c_int(0), C.c_double(0)
+    st = L.orc_ilu0_gmres(n, b, rp, ci, v, x, rhs, 1e-13, 400, restart, C.byref(its), C.byref(red))
+    assert st == 0 and red.value < 1e-13 and 1 <= its.value < 400
+    assert np.allclose(x, spla.spsolve(A.tocsc(), rhs), rtol=1e-9, atol=1e-11)
+    # preconditioned defect: ||M^-1 (b - A x)|| / ||M^-1 b||
+    ilu, _ = O.ilu0_factor(n, b, rp, ci, v)
+    pd = lambda r: np.linalg.norm(O.ilu0_apply(n, b, rp, ci, ilu, r))
+    assert pd(rhs - A @ x) / pd(rhs) <= 5e-13
+    # residual norms are non-increasing in the iteration limit (minimal-residual property inside a cycle, restarts keep x)
+    last = 1.0
+    for maxit in (1, 2, 4, 8):
+        x = np.zeros(n * b)
+        stm = L.orc_ilu0_gmres(n, b, rp, ci, v, x, rhs, 1e-13, maxit, restart, C.byref(its), C.byref(red))
+        assert stm in (0, 1) and its.value <= maxit and red.value <= last * (1 + 1e-12)
+        last = red.value
+
+
+def test_gmres_full_cycle_matches_scipy_gmres():
+    """One un-restarted cycle of left-preconditioned GMRes minimises ||M^-1(b - A x)|| over the Krylov space: compare the iterate
+    after k steps with scipy's GMRes on the explicitly preconditioned system."""
+    n, rp, ci, v = _block_laplacian(8, 2)
+    A = _to_scipy(n, 2, rp, ci, v)
+    rhs = np.random.RandomState(9).uniform(-1, 1, n * 2)
+    ilu, _ = O.ilu0_factor(n, 2, rp, ci, v)
+    Minv = np.column_stack([O.ilu0_apply(n, 2, rp, ci, ilu, e) for e in np.eye(n * 2)])
+    import ctypes as C
+    x = np.zeros(n * 2); its, red = C.c_int(0), C.c_double(0)
+    k = 6
+    O.lib().orc_ilu0_gmres(n, 2, rp, ci, v, x, rhs, 1e-30, k, 50, C.byref(its), C.byref(red))
+    # minimiser over span{M^-1 b, (M^-1 A) M^-1 b, ...} by dense least squares
+    B = Minv @ A.toarray()
+    c = Minv @ rhs
+    Kry = [c]
+    for _ in range(k - 1):
+        Kry.append(B @ Kry[-1])
+    Q, _ = np.linalg.qr(np.column_stack(Kry))
+    y, *_ = np.linalg.lstsq(B @ Q, c, rcond=None)
+    assert np.linalg.norm(x - Q @ y) <= 1e-8 * np.linalg.norm(x)
+
+
 def test_assembled_jacobian_solve_against_scipy():
     """The real thing: 2p lens Jacobian + residual, ILU0-BiCGSTAB at Newton's reduction vs a sparse direct solve."""
     spec = problems.twop_lens((24, 16), law="vg")
