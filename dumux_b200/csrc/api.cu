@@ -41,7 +41,7 @@ int upload_pattern(dmx_ctx* ctx)
     DMX_CUDA(cudaMalloc((void**)&ctx->d_colidx, ctx->h_colidx.size() * sizeof(int)));
     DMX_CUDA(cudaMemcpy(ctx->d_rowptr, ctx->h_rowptr.data(), ctx->h_rowptr.size() * sizeof(int), cudaMemcpyHostToDevice));
     DMX_CUDA(cudaMemcpy(ctx->d_colidx, ctx->h_colidx.data(), ctx->h_colidx.size() * sizeof(int), cudaMemcpyHostToDevice));
-    return build_level_schedule(ctx);
+    return build_diag(ctx);
 }
 
 // Jacobian pattern of the CCTpfa scheme on the local box: (I,I) and (I,J) for all face neighbours, columns ascending

@@ -363,21 +363,43 @@ int check_finite(dmx_ctx* ctx, const double* v, size_t len, bool* ok)
 // block ILU(0), level scheduled.  Level of row i (lower) = 1 + max level of rows j<i in its pattern; for the
 // 7-point stencil that is the hyperplane i+j+k.  Rows of one level are independent.
 // ---------------------------------------------------------------------------------------------
+// position of the diagonal block of every row (uploaded with the pattern); the level schedule itself is built lazily, only when
+// the generic (non-structured) ILU kernels are actually used
+int build_diag(dmx_ctx* ctx)
+{
+    const int n = ctx->n;
+    const std::vector<int>& rp = ctx->h_rowptr;
+    const std::vector<int>& ci = ctx->h_colidx;
+    std::vector<int> diag(n, -1);
+    for (int i = 0; i < n; ++i) {
+        for (int k = rp[i]; k < rp[i + 1]; ++k)
+            if (ci[k] == i) { diag[i] = k; break; }
+        if (diag[i] < 0) return fail(ctx, DMX_ERR_USAGE, "pattern without diagonal entry");
+    }
+    if (ctx->d_diag) cudaFree(ctx->d_diag);
+    ctx->d_diag = nullptr;
+    DMX_CUDA(cudaMalloc((void**)&ctx->d_diag, diag.size() * sizeof(int)));
+    DMX_CUDA(cudaMemcpy(ctx->d_diag, diag.data(), diag.size() * sizeof(int), cudaMemcpyHostToDevice));
+    ctx->l_ptr.clear();
+    ctx->u_ptr.clear();
+    ctx->ilu_valid = false;
+    ctx->ilu_bcrs_valid = false;
+    return 0;
+}
+
 int build_level_schedule(dmx_ctx* ctx)
 {
     const int n = ctx->n;
     const std::vector<int>& rp = ctx->h_rowptr;
     const std::vector<int>& ci = ctx->h_colidx;
-    std::vector<int> lev(n, 0), diag(n, -1);
+    std::vector<int> lev(n, 0);
     int nl = 0;
     for (int i = 0; i < n; ++i) {
         int l = 0;
         for (int k = rp[i]; k < rp[i + 1]; ++k) {
             const int j = ci[k];
             if (j < i) l = std::max(l, lev[j] + 1);
-            else if (j == i) diag[i] = k;
         }
-        if (diag[i] < 0) return fail(ctx, DMX_ERR_USAGE, "pattern without diagonal entry");
         lev[i] = l;
         nl = std::max(nl, l + 1);
     }
@@ -410,7 +432,6 @@ int build_level_schedule(dmx_ctx* ctx)
     };
     if (int rc = up(&ctx->d_lrows, lrows)) return rc;
     if (int rc = up(&ctx->d_urows, urows)) return rc;
-    if (int rc = up(&ctx->d_diag, diag)) return rc;
     if (int rc = up(&ctx->d_lptr, ctx->l_ptr)) return rc;
     if (int rc = up(&ctx->d_uptr, ctx->u_ptr)) return rc;
     return 0;
@@ -579,6 +600,7 @@ int ilu0_factor_bcrs(dmx_ctx* ctx)
     if (!ctx->d_ilu) DMX_CUDA(cudaMalloc((void**)&ctx->d_ilu, bytes));
     DMX_CUDA(cudaMemcpyAsync(ctx->d_ilu, ctx->d_J, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
     DMX_CUDA(cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream));
+    if (ctx->l_ptr.empty()) { if (int rc = build_level_schedule(ctx)) return rc; }
     const int nlev = (int)ctx->l_ptr.size() - 1;
     if (ctx->b == 2)
         return coop_launch(ctx, ilu0_factor_kernel<2>, 128, nlev, (const int*)ctx->d_lptr, (const int*)ctx->d_lrows, (const int*)ctx->d_rowptr,
@@ -610,6 +632,7 @@ int ilu0_apply(dmx_ctx* ctx, const double* d, double* v)
 {
     ProfScope ps(ctx, DMX_K_ILU_APPLY);
     if (ctx->skew) return sk_apply(ctx, d, v);
+    if (ctx->l_ptr.empty()) { if (int rc0 = build_level_schedule(ctx)) return rc0; }
     const int nl = (int)ctx->l_ptr.size() - 1, nu = (int)ctx->u_ptr.size() - 1;
     int rc;
     if (ctx->b == 2) {
