@@ -94,7 +94,7 @@ def projected_step(list_csv, out, iterations):
     rows = list(csv.DictReader(open(list_csv)))
     avg = {r["kernel"]: float(r["avg_ms"]) for r in rows}
     it = iterations
-    per_step = {"assemble_tile_kernel": 1, "ilu0_factor_kernel": 1, "ilu_skew_kernel": 1, "vec_skew_kernel": 2 * it,
+    per_step = {"assemble_tile_kernel": 1, "ilu0_factor_kernel": 1, "ilu_diag_kernel": 1, "ilu_skew_kernel": 1, "vec_skew_kernel": 2 * it,
                 "ilu_sweep_kernel<2, 0>": 2 * it, "ilu_sweep_kernel<2, 1>": 2 * it, "stencil_spmv_kernel": 2 * it + 1,
                 "dot_kernel<1>": it + 1, "dot_kernel<2>": it, "p_update_kernel": it - 1, "axpy_r_norm_kernel": it,
                 "axpy3_norm_dot_kernel": it, "residual_init_kernel": 1, "final_reduce_kernel": 4 * it + 2, "newton_update_kernel": 1}
