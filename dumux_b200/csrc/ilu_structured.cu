@@ -32,9 +32,16 @@
 
 namespace dmx {
 
-constexpr int SK_TI = 16, SK_TJ = 16, SK_THREADS = SK_TI * SK_TJ;
+#ifndef SK_TILE
+#define SK_TILE 16       // edge of the square (i,j) tile of a CTA (power of two, <= 16)
+#endif
+constexpr int SK_TI = SK_TILE, SK_TJ = SK_TILE, SK_THREADS = SK_TI * SK_TJ;
+#ifndef SK_CTAS_PER_SM
+#define SK_CTAS_PER_SM ((SK_TILE == 16) ? 1 : 4)
+#endif
+constexpr int SK_CTAS = SK_CTAS_PER_SM;     // resident CTAs per SM the sweep kernel is built for
 constexpr int SK_C = 8;                      // unroll factor of the step loop (and granularity of the developer timeline)
-static_assert(SK_TI + SK_TJ == 32, "one sync-warp lane per halo value of a step");
+static_assert(SK_TI + SK_TJ <= 32 && (SK_TI & (SK_TI - 1)) == 0, "one sync-warp lane per halo value of a step");
 
 struct SkewGrid {
     int nx, ny, nz, ntx, nty, ntiles, NS;
@@ -74,7 +81,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar)
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // barrier among the 256 compute threads only (the producer warp does not take part)
-__device__ __forceinline__ void compute_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void compute_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(SK_THREADS) : "memory"); }
 __device__ __forceinline__ unsigned long long ld_relaxed(const unsigned long long* p)
 {
     unsigned long long v;
@@ -223,7 +230,7 @@ __global__ void __launch_bounds__(SK_THREADS) ilu_skew_kernel(SkewGrid g, const 
 {
     constexpr int BB = B * B;
     const int t = threadIdx.x;
-    const int a = t & (SK_TI - 1), b = t >> 4;
+    const int a = t & (SK_TI - 1), b = t / SK_TI;
     const int s = blockIdx.x % g.NS;
     const int tile = blockIdx.x / g.NS;
     const int ti = tile % g.ntx, tj = tile / g.ntx;
@@ -320,7 +327,7 @@ template <int B>
 __global__ void __launch_bounds__(SK_THREADS) vec_skew_kernel(SkewGrid g, const double* __restrict__ x, double* __restrict__ xsk)
 {
     const int t = threadIdx.x;
-    const int a = t & (SK_TI - 1), b = t >> 4;
+    const int a = t & (SK_TI - 1), b = t / SK_TI;
     const int s = blockIdx.x % g.NS;
     const int tile = blockIdx.x / g.NS;
     const int i = (tile % g.ntx) * SK_TI + a, j = (tile / g.ntx) * SK_TJ + b, k = s - a - b;
@@ -365,7 +372,7 @@ __global__ void __launch_bounds__(SK_THREADS) vec_skew_kernel(SkewGrid g, const 
 constexpr int SK_R = SK_RING;                // halo ring depth in steps
 constexpr int SK_NB = SK_BATCH;              // steps whose halo words the sync warp requests together
 template <int B, bool UPPER>
-__global__ void __launch_bounds__(SK_THREADS + 64, 1) ilu_sweep_kernel(SkewGrid g, const double* __restrict__ stream, double* out,
+__global__ void __launch_bounds__(SK_THREADS + 64, SK_CTAS) ilu_sweep_kernel(SkewGrid g, const double* __restrict__ stream, double* out,
                                                                         unsigned long long* ll, unsigned int tag,
                                                                            const int* __restrict__ order, unsigned long long* ticket_ctr,
                                                                            unsigned long long ticket_base, long long* trace)
@@ -388,7 +395,7 @@ __global__ void __launch_bounds__(SK_THREADS + 64, 1) ilu_sweep_kernel(SkewGrid 
     __shared__ int s_tile;
 
     const int t = threadIdx.x;
-    const int a = t & (SK_TI - 1), b = t >> 4;          // mirrored coordinates for UPPER
+    const int a = t & (SK_TI - 1), b = t / SK_TI;          // mirrored coordinates for UPPER
     const int tl = UPPER ? SK_THREADS - 1 - t : t;      // lane in LOWER indexing (storage)
     if (t == 0) {
         const unsigned long long ticket = atomicAdd(ticket_ctr, 1ull) - ticket_base;
@@ -422,7 +429,8 @@ __global__ void __launch_bounds__(SK_THREADS + 64, 1) ilu_sweep_kernel(SkewGrid 
         const int dir = lane / SK_TI, hl = lane % SK_TI;        // lanes 0-15: x halo (row hl), 16-31: y halo (column hl)
         const int htile = dir == 0 ? tix + g.ntx * tj : ti + g.ntx * tjy;
         const int other = dir == 0 ? tj * SK_TJ + (UPPER ? SK_TJ - 1 - hl : hl) : ti * SK_TI + (UPPER ? SK_TI - 1 - hl : hl);
-        const bool hvalid = (dir == 0 ? tilex : tiley) && other < (dir == 0 ? g.ny : g.nx);
+        const bool hlane = lane < SK_TI + SK_TJ;               // lanes beyond the two edges idle (tiles smaller than 16 x 16)
+        const bool hvalid = hlane && (dir == 0 ? tilex : tiley) && other < (dir == 0 ? g.ny : g.nx);
         // Batches of SK_NB steps: all words of a batch are requested at once (one L2 round trip per batch instead of 2*B
         // dependent round trips per step); a word whose tag does not match yet is polled again when its step is due.
         for (int s0 = 0; s0 < NS; s0 += SK_NB) {
@@ -461,7 +469,8 @@ __global__ void __launch_bounds__(SK_THREADS + 64, 1) ilu_sweep_kernel(SkewGrid 
                 }
                 __syncwarp();
 #pragma unroll
-                for (int e = 0; e < B; ++e) hring[q * HSTEP_DOUBLES + lane * B + e] = val[e];
+                for (int e = 0; e < B; ++e)
+                    if (hlane) hring[q * HSTEP_DOUBLES + lane * B + e] = val[e];
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&hready[q]);
             }
