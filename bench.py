@@ -42,6 +42,18 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# The contract is ONE JSON line on stdout.  Libraries write banners to file descriptor 1 (NCCL prints "NCCL version ..." at
+# communicator creation when NCCL_DEBUG=VERSION is set in the environment), so fd 1 is pointed at stderr for the whole run and
+# the result line goes to a duplicate of the original stdout.
+_RESULT_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line):
+    _RESULT_OUT.write(json.dumps(line) + "\n")
+    _RESULT_OUT.flush()
+
+
 # ----------------------------------------------------------------------------------------------------------
 # algorithmic bytes per launch (DESIGN.md "Kernels")
 # ----------------------------------------------------------------------------------------------------------
@@ -162,7 +174,7 @@ def run_reference(args):
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -369,7 +381,7 @@ def run_b200(args):
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

@@ -342,8 +342,8 @@ int dmx_set_options(dmx_ctx* ctx, const dmx_options* o)
 {
     const bool structural = (o->fd_method != ctx->opt.fd_method) || (o->extrusion != ctx->opt.extrusion);
     ctx->opt = *o;
-    if (o->fd_method != 1 && o->fd_method != 0 && o->fd_method != -1 && o->fd_method != 5)
-        return fail(ctx, DMX_ERR_USAGE, "Assembly.NumericDifferenceMethod must be 1, 0, -1 or 5");
+    if (o->fd_method != 1 && o->fd_method != 0 && o->fd_method != -1 && o->fd_method != 5 && o->fd_method != DMX_DIFF_ANALYTIC)
+        return fail(ctx, DMX_ERR_USAGE, "Assembly.NumericDifferenceMethod must be 1, 0, -1 or 5 (or DMX_DIFF_ANALYTIC)");
     if (structural) ctx->prepared = false;
     return 0;
 }

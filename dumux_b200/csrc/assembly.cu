@@ -647,6 +647,65 @@ __global__ void __launch_bounds__(AT_THREADS, (ND == 1) ? 2 : 1) assemble_tile_k
 }
 
 // ================================================================================================
+// DiffMethod::analytic for the incompressible 1p model: CCLocalAssembler<analytic, implicit> (assembly/cclocalassembler.hh:
+// 490-600) + OnePIncompressibleLocalResidual::addFluxDerivatives / addCCDirichletFluxDerivatives
+// (porousmediumflow/1p/incompressiblelocalresidual.hh:76-123,204-221): A[I][I] += tij*up over interior and Dirichlet faces
+// (-x,+x,-y,+y,-z,+z), A[I][J] -= tij*up, up = density/viscosity; no storage derivative (:51-60), Neumann faces contribute
+// nothing.  One thread per row, rows written whole; the residual comes from the JAC = false instantiation of the tile kernel.
+// HBM-bound stream: 3 transmissibilities + rowptr in, 7 entries out per row.
+// ================================================================================================
+template <int DIM>
+__global__ void __launch_bounds__(256) onep_analytic_jacobian_kernel(const AsmParams P, double up)
+{
+    const size_t I = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (I >= (size_t)P.n) return;
+    const int nx = P.nc[0], ny = P.nc[1];
+    const int ci[3] = {(int)(I % nx), (int)((I / nx) % ny), (int)(I / ((size_t)nx * ny))};
+    const size_t stride[3] = {1, (size_t)nx, (size_t)nx * ny};
+    bool ex[6];
+    int pos[6];
+#pragma unroll
+    for (int s = 0; s < 6; ++s) ex[s] = (s >> 1) < DIM && ((s & 1) ? ci[s >> 1] + 1 < P.nc[s >> 1] : ci[s >> 1] > 0);
+    const int rowStart = P.rowptr[I];
+    const int posDiag = rowStart + (ex[4] ? 1 : 0) + (ex[2] ? 1 : 0) + (ex[0] ? 1 : 0);
+    pos[4] = rowStart;
+    pos[2] = rowStart + (ex[4] ? 1 : 0);
+    pos[0] = pos[2] + (ex[2] ? 1 : 0);
+    pos[1] = posDiag + 1;
+    pos[3] = pos[1] + (ex[1] ? 1 : 0);
+    pos[5] = pos[3] + (ex[3] ? 1 : 0);
+    double diag = 0.0;
+#pragma unroll
+    for (int s = 0; s < 2 * DIM; ++s) {
+        const int a = s >> 1;
+        const bool hi = (s & 1);
+        if (ex[s]) {
+            const double tij = hi ? P.tij[a][I] : P.tij[a][I - stride[a]];
+            const double deriv = tij * up;
+            diag += deriv;
+            double off = 0.0;
+            off -= deriv;
+            P.jac[pos[s]] = off;
+        } else {
+            int f;
+            if (a == 0) f = ci[1] + ny * ci[2];
+            else if (a == 1) f = ci[0] + nx * ci[2];
+            else f = ci[0] + nx * ci[1];
+            const int type = P.bc_type[s] ? P.bc_type[s][f] : DMX_BC_NEUMANN;
+            if (type == DMX_BC_DIRICHLET) {
+                double area = 1.0;
+                if (a != 0) area *= P.width[0][ci[0]];
+                if (a != 1 && DIM > 1) area *= P.width[1][ci[1]];
+                if (a != 2 && DIM > 2) area *= P.width[2][ci[2]];
+                const double ti = P.K[I] * P.extrusion * (hi ? P.gf_hi[a][ci[a]] : P.gf_lo[a][ci[a]]);
+                diag += (area * ti) * up;
+            }
+        }
+    }
+    P.jac[posDiag] = diag;
+}
+
+// ================================================================================================
 // Tracer transport on a frozen velocity field (BASELINE config 5, examples/1ptracer)
 // ================================================================================================
 // Volume fluxes over all scvfs from the 1p pressure field in CUR: examples/1ptracer/main.cc:162-199
@@ -1041,6 +1100,20 @@ static int launch_impl(dmx_ctx* ctx, bool with_jac, bool volvars_only)
         else if (ctx->dim == 2) DMX_TRACER(2);
         else DMX_TRACER(1);
 #undef DMX_TRACER
+        DMX_CHECK_LAUNCH();
+        return 0;
+    }
+    if (ctx->opt.fd_method == DMX_DIFF_ANALYTIC) {
+        if (ctx->model != DMX_MODEL_1P || ctx->tabulated)
+            return fail(ctx, DMX_ERR_USAGE, "DiffMethod::analytic is available for the incompressible 1p model only");
+        if (int rc = launch_tile<DMX_MODEL_1P, false>(ctx, P, false)) return rc;          // residual
+        if (!with_jac) return 0;
+        const unsigned grid = (unsigned)((ctx->n + 255) / 256);
+        const double up = ctx->rho[0] / ctx->mu[0];               // volVars.density() / volVars.viscosity()
+        ProfScope ps__(ctx, DMX_K_ASSEMBLY);
+        if (ctx->dim == 3) onep_analytic_jacobian_kernel<3><<<grid, 256, 0, ctx->stream>>>(P, up);
+        else if (ctx->dim == 2) onep_analytic_jacobian_kernel<2><<<grid, 256, 0, ctx->stream>>>(P, up);
+        else onep_analytic_jacobian_kernel<1><<<grid, 256, 0, ctx->stream>>>(P, up);
         DMX_CHECK_LAUNCH();
         return 0;
     }

@@ -20,6 +20,9 @@ LAW_BC, LAW_VG = 0, 1
 BC_NEUMANN, BC_DIRICHLET, BC_NONE, BC_OUTFLOW = 0, 1, 2, 3
 
 
+DIFF_ANALYTIC = 100     # Options.fd_method value for DiffMethod::analytic (DMX_DIFF_ANALYTIC / ORC_DIFF_ANALYTIC)
+
+
 @dataclasses.dataclass
 class Material:
     law: int
@@ -223,7 +226,8 @@ def fast_lognormal_multiplier(n: int, sigma: float, seed: int = 0) -> np.ndarray
 # ------------------------------------------------------------------------------------------------------
 # C1: test/porousmediumflow/1p/incompressible (params.input, problem.hh:41-100, spatialparams.hh:44-106)
 # ------------------------------------------------------------------------------------------------------
-def onep_incompressible(cells=(10, 10), lower=None, upper=None, numdiff_params=True) -> ProblemSpec:
+def onep_incompressible(cells=(10, 10), lower=None, upper=None, numdiff_params=True, analytic=False) -> ProblemSpec:
+    """`analytic`: DiffMethod::analytic (test_1p_incompressible_tpfa, the reference's default) instead of numeric differentiation."""
     dim = len(cells)
     lower = tuple([0.0] * dim) if lower is None else lower
     upper = tuple([1.0] * dim) if upper is None else upper
@@ -245,6 +249,8 @@ def onep_incompressible(cells=(10, 10), lower=None, upper=None, numdiff_params=T
     if numdiff_params:
         opt.base_eps = 0.1
         opt.privar_magnitude = (1e5, -1.0)
+    if analytic:
+        opt.fd_method = DIFF_ANALYTIC
     return ProblemSpec(
         name="1p_incompressible", model=MODEL_1P, dim=dim, cells=tuple(cells), lower=tuple(lower), upper=tuple(upper),
         K=K, phi=np.full(n, 0.4), region=np.zeros(n, dtype=np.int32), materials=[],

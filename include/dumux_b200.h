@@ -29,6 +29,10 @@ enum { DMX_LAW_BROOKSCOREY = 0, DMX_LAW_VANGENUCHTEN = 1 };
 /* DMX_BC_OUTFLOW (tracer model only): the solution-dependent Neumann flux volumeFlux * X * rho / area of
    examples/1ptracer/problem_tracer.hh:92-115 */
 enum { DMX_BC_NEUMANN = 0, DMX_BC_DIRICHLET = 1, DMX_BC_NONE = 2, DMX_BC_OUTFLOW = 3 };
+/* dmx_options.fd_method value selecting DiffMethod::analytic instead of numeric differentiation: CCLocalAssembler<analytic,
+   implicit> (assembly/cclocalassembler.hh:490-600) with OnePIncompressibleLocalResidual (porousmediumflow/1p/
+   incompressiblelocalresidual.hh:76-123,204-221).  Incompressible 1p model only (constant density and viscosity). */
+enum { DMX_DIFF_ANALYTIC = 100 };
 enum { DMX_PRECOND_ILU0 = 0, DMX_PRECOND_BLOCKJACOBI = 1 };
 /* Krylov method behind dmx_linear_solve / dmx_newton_*: ILUBiCGSTABIstlSolver (linear/istlsolvers.hh:636-642, default) or
    ILURestartedGMResIstlSolver (:660-667) */

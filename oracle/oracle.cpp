@@ -579,6 +579,63 @@ struct orc_problem {
         }
     }
 
+    // advectionTij of the flux-variables cache (flux/cctpfa/darcyslaw.hh:218-259): what computeFlux uses, factored out for the
+    // analytic flux derivatives
+    double advectionTij(const int* cI, int side, double KI, double extrI, bool boundary, const int* cJ, double KJ, double extrJ) const
+    {
+        const double area = faceArea(side / 2, cI);
+        const double ti = computeTpfaTransmissibility(cI, side, cI, KI, extrI);
+        if (boundary) return area * ti;
+        const double tj = -1.0 * computeTpfaTransmissibility(cI, side, cJ, KJ, extrJ);
+        if (ti * tj <= 0.0) return 0;
+        return area * (ti * tj) / (ti + tj);
+    }
+
+    // ---------------------------------------------------------------------------------------------
+    // DiffMethod::analytic for the incompressible 1p model: CCLocalAssembler<analytic, implicit>
+    // (dumux/assembly/cclocalassembler.hh:490-600) with OnePIncompressibleLocalResidual
+    // (dumux/porousmediumflow/1p/incompressiblelocalresidual.hh:51-60 no storage derivative, :76-123 flux derivatives
+    // A[I][I] += tij*up, A[I][J] -= tij*up with up = density/viscosity, :204-221 Dirichlet faces A[I][I] += tij*up;
+    // Neumann faces: addRobinFluxDerivatives is empty).  What test_1p_incompressible_tpfa runs by default.
+    // ---------------------------------------------------------------------------------------------
+    void assembleElementAnalytic1p(int I, const double* cur, const double* prev, double* residual, double* jac) const
+    {
+        int cI[3];
+        ijk(I, cI);
+        VolVars vvI, prevVV, nb[6];
+        updateVolVars(vvI, cur + (size_t)I * b, I);
+        if (!opt.stationary) updateVolVars(prevVV, prev + (size_t)I * b, I);
+        int nbIdx[6], nbC[6][3];
+        for (int side = 0; side < 6; ++side) {
+            nbIdx[side] = (side < 2 * dim) ? neighbor(cI, side) : -1;
+            if (nbIdx[side] >= 0) {
+                ijk(nbIdx[side], nbC[side]);
+                updateVolVars(nb[side], cur + (size_t)nbIdx[side] * b, nbIdx[side]);
+            }
+        }
+        double orig0[2];
+        evalLocalResidual(orig0, I, cI, vvI, nb, &prevVV);
+        if (residual) residual[I] = orig0[0];
+        if (!jac) return;
+        const double up = vvI.rho[0] / vvI.mu[0];
+        const int kd = findEntry(I, I);
+        for (int side = 0; side < 2 * dim; ++side) {
+            const int J = nbIdx[side];
+            if (J >= 0) {
+                const double deriv = advectionTij(cI, side, vvI.K, vvI.extr, false, nbC[side], nb[side].K, nb[side].extr) * up;
+                jac[kd] += deriv;
+                jac[findEntry(I, J)] -= deriv;
+            } else {
+                const int fidx = sideFaceIndex(side, cI);
+                const int type = bcType[side].empty() ? ORC_BC_NEUMANN : bcType[side][fidx];
+                if (type == ORC_BC_DIRICHLET) {
+                    const double deriv = advectionTij(cI, side, vvI.K, vvI.extr, true, nullptr, 0.0, 0.0) * up;
+                    jac[kd] += deriv;
+                }
+            }
+        }
+    }
+
     // FD epsilon: dumux/assembly/numericepsilon.hh:47-51, dumux/common/numericdifferentiation.hh:36-41
     double fdEps(double priVar, int pvIdx) const
     {
@@ -1173,7 +1230,10 @@ void orc_assemble(orc_problem* p, const double* cur, const double* prev, double*
     const int nt = p->opt.num_threads > 0 ? p->opt.num_threads : omp_get_max_threads();
 #pragma omp parallel for schedule(static) num_threads(nt)
 #endif
-    for (int I = 0; I < p->n; ++I) p->assembleElement(I, cur, prev, residual, jac);
+    for (int I = 0; I < p->n; ++I) {
+        if (p->opt.fd_method == ORC_DIFF_ANALYTIC) p->assembleElementAnalytic1p(I, cur, prev, residual, jac);
+        else p->assembleElement(I, cur, prev, residual, jac);
+    }
 }
 
 void orc_volvars(orc_problem* p, const double* cur, double* out)

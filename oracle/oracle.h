@@ -38,6 +38,8 @@ typedef struct {
 
 enum { ORC_MODEL_1P = 1, ORC_MODEL_2P = 2 };
 enum { ORC_LAW_BROOKSCOREY = 0, ORC_LAW_VANGENUCHTEN = 1 };
+/* fd_method value selecting DiffMethod::analytic (incompressible 1p only: 1p/incompressiblelocalresidual.hh) */
+enum { ORC_DIFF_ANALYTIC = 100 };
 enum { ORC_SOLVER_BICGSTAB = 0, ORC_SOLVER_GMRES = 1 };   /* ILUBiCGSTABIstlSolver / ILURestartedGMResIstlSolver */
 enum { ORC_BC_NEUMANN = 0, ORC_BC_DIRICHLET = 1, ORC_BC_NONE = 2, ORC_BC_OUTFLOW = 3 };
 /* sides: 0 -x, 1 +x, 2 -y, 3 +y, 4 -z, 5 +z (YaspGrid indexInInside) */

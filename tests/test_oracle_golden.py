@@ -44,6 +44,27 @@ def test_1p_incompressible_10x10_reference_vtu():
     assert np.linalg.norm(r2) <= 1e-9 * np.linalg.norm(r0)
 
 
+def test_1p_incompressible_analytic_reference_vtu():
+    """test_1p_incompressible_tpfa (DiffMethod::analytic, the reference's default for this test) -> the same
+    test_1p_cc-reference.vtu; the analytic Jacobian (1p/incompressiblelocalresidual.hh:76-123,204-221) is exact, so it equals the
+    FD Jacobian of the linear problem up to the FD rounding."""
+    spec = problems.onep_incompressible((10, 10), analytic=True)
+    x, o, its = _one_linear_step(spec)
+    g = np.load(os.path.join(GOLDEN, "test_1p_cc.npz"))["p"].astype(np.float64)
+    assert _fuzzy_ok(x, g) and np.abs(x / g - 1).max() < 5e-6
+    _, ja = o.assemble(np.zeros(100))
+    _, jn = Oracle(problems.onep_incompressible((10, 10), numdiff_params=True)).assemble(np.zeros(100))
+    assert np.abs(ja - jn).max() <= 1e-9 * np.abs(ja).max()
+    # closed form on the 10x10 grid: interior face tij = K (h = 0.1, area 0.1, two half distances 0.05), up = rho/mu = 1e6
+    K = 1e-10
+    assert ja[o.rowptr[0] + 1] == pytest.approx(-K * 1e6, rel=1e-14)           # A[0][1]
+    # cell 0 touches the Dirichlet bottom (t = area*K/0.05 = 2K) and two interior faces: diagonal = (2K + K + K) * up
+    assert ja[o.rowptr[0]] == pytest.approx(4 * K * 1e6, rel=1e-14)
+    # row sums vanish away from Dirichlet faces (pure flux balance, no storage term)
+    I = 45
+    assert abs(ja[o.rowptr[I]:o.rowptr[I + 1]].sum()) <= 1e-12 * abs(ja[o.rowptr[I]:o.rowptr[I + 1]]).max()
+
+
 def test_1p_analytic_and_numeric_jacobian_agree():
     """For the linear 1p problem the FD Jacobian is exact for any eps (test_1p_incompressible_tpfa vs _numdiff)."""
     a = problems.onep_incompressible((10, 10), numdiff_params=True)
