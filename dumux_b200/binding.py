@@ -31,9 +31,10 @@ EXPORTS = [
     "dmx_ilu0_factor", "dmx_ilu0_apply", "dmx_ilu0_download", "dmx_dot", "dmx_halo_exchange", "dmx_time_kernel",
     "dmx_kernel_launch_count", "dmx_synchronize", "dmx_profile", "dmx_profile_read",
     "dmx_newton_step_host", "dmx_timer_start", "dmx_timer_stop", "dmx_debug_sweep_trace",
-    "dmx_volume_flux", "dmx_set_volume_flux", "dmx_set_tracer", "dmx_set_wetting_phase", "dmx_set_linear_solver",
+    "dmx_volume_flux", "dmx_set_volume_flux", "dmx_set_tracer", "dmx_set_wetting_phase", "dmx_set_linear_solver", "dmx_ssor_apply",
 ]
-SOLVER_BICGSTAB, SOLVER_RESTARTED_GMRES = 0, 1
+SOLVER_BICGSTAB, SOLVER_RESTARTED_GMRES, SOLVER_CG = 0, 1, 2
+PRECOND_SSOR = 2
 K_ASSEMBLY, K_SPMV, K_ILU_APPLY, K_ILU_FACTOR, K_VOLVARS, K_BLAS1, K_HALO, K_JACOBI = range(8)
 
 
@@ -107,6 +108,7 @@ def load_library():
     L.dmx_set_tracer.argtypes = [vp, C.c_int]
     L.dmx_set_wetting_phase.argtypes = [vp, C.c_int, C.c_int]
     L.dmx_set_linear_solver.argtypes = [vp, C.c_int, C.c_int]
+    L.dmx_ssor_apply.argtypes = [vp, C.c_int, C.c_int]
     L.dmx_set_boundary.argtypes = [vp, C.c_int, _ip, _dp]
     L.dmx_vec_upload.argtypes = [vp, C.c_int, C.c_void_p]
     L.dmx_vec_download.argtypes = [vp, C.c_int, C.c_void_p]
@@ -365,7 +367,10 @@ class Engine:
 
     def set_linear_solver(self, kind, restart=10):
         """'bicgstab' = ILUBiCGSTABIstlSolver (default), 'gmres' = ILURestartedGMResIstlSolver (LinearSolver.GMResRestart)."""
-        self._check(self.L.dmx_set_linear_solver(self.h, {"bicgstab": SOLVER_BICGSTAB, "gmres": SOLVER_RESTARTED_GMRES}[kind], restart))
+        self._check(self.L.dmx_set_linear_solver(self.h, {"bicgstab": SOLVER_BICGSTAB, "gmres": SOLVER_RESTARTED_GMRES, "cg": SOLVER_CG}[kind], restart))
+
+    def ssor_apply(self, d_vec, v_vec):
+        self._check(self.L.dmx_ssor_apply(self.h, d_vec, v_vec))
 
     def solve_device(self, reduction=1e-6, maxit=250, precond=PRECOND_ILU0):
         its, red = C.c_int(0), C.c_double(0)

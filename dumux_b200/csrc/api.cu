@@ -482,6 +482,7 @@ int dmx_vec_copy(dmx_ctx* ctx, int dst, int src)
 }
 int dmx_jacobian_upload(dmx_ctx* ctx, const double* values)
 {
+    ctx->jac_diagonal = false;
     if (!ctx->d_J) return fail(ctx, DMX_ERR_USAGE, "no pattern set");
     DMX_CUDA(cudaMemcpyAsync(ctx->d_J, values, (size_t)ctx->nnzb * ctx->b * ctx->b * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     DMX_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -495,7 +496,7 @@ int dmx_jacobian_download(dmx_ctx* ctx, double* values)
     return 0;
 }
 void* dmx_vec_device_ptr(dmx_ctx* ctx, int vec) { return (vec >= 0 && vec < DMX_NUM_VECS) ? ctx->d_vec[vec] : nullptr; }
-void* dmx_jacobian_device_ptr(dmx_ctx* ctx) { return ctx->d_J; }
+void* dmx_jacobian_device_ptr(dmx_ctx* ctx) { ctx->jac_diagonal = false; return ctx->d_J; }   /* the caller may write through it */
 int dmx_synchronize(dmx_ctx* ctx)
 {
     DMX_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -586,7 +587,7 @@ int dmx_assemble_host(dmx_ctx* ctx, const double* cur, const double* prev, doubl
 }
 int dmx_set_linear_solver(dmx_ctx* ctx, int solver, int restart)
 {
-    if (solver != DMX_SOLVER_BICGSTAB && solver != DMX_SOLVER_RESTARTED_GMRES) return fail(ctx, DMX_ERR_USAGE, "unknown linear solver");
+    if (solver != DMX_SOLVER_BICGSTAB && solver != DMX_SOLVER_RESTARTED_GMRES && solver != DMX_SOLVER_CG) return fail(ctx, DMX_ERR_USAGE, "unknown linear solver");
     ctx->linear_solver = solver;
     ctx->gmres_restart = restart > 0 ? restart : 10;
     return 0;
@@ -785,6 +786,14 @@ int dmx_ilu0_apply(dmx_ctx* ctx, int d_vec, int v_vec)
     if (int rc = vec_ok(ctx, d_vec)) return rc;
     if (int rc = vec_ok(ctx, v_vec)) return rc;
     return ilu0_apply(ctx, ctx->d_vec[d_vec], ctx->d_vec[v_vec]);
+}
+int dmx_ssor_apply(dmx_ctx* ctx, int d_vec, int v_vec)
+{
+    if (!ctx->d_J) return fail(ctx, DMX_ERR_USAGE, "ssor_apply: no pattern");
+    if (ctx->nranks > 1) return fail(ctx, DMX_ERR_USAGE, "SSOR runs on a single domain in this version");
+    if (int rc = vec_ok(ctx, d_vec)) return rc;
+    if (int rc = vec_ok(ctx, v_vec)) return rc;
+    return ssor_apply(ctx, ctx->d_vec[d_vec], ctx->d_vec[v_vec]);
 }
 int dmx_ilu0_download(dmx_ctx* ctx, double* values)
 {

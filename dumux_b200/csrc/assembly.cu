@@ -1136,7 +1136,13 @@ int launch_volume_flux(dmx_ctx* ctx, double* d_out)
     return 0;
 }
 
-int launch_assemble(dmx_ctx* ctx, bool with_jacobian) { return launch_impl(ctx, with_jacobian, false); }
+int launch_assemble(dmx_ctx* ctx, bool with_jacobian)
+{
+    const int rc = launch_impl(ctx, with_jacobian, false);
+    // explicit tracer steps assemble the storage derivative only (tracer/localresidual.hh:193-214): off-diagonal blocks are +0.0
+    if (with_jacobian) ctx->jac_diagonal = (rc == 0 && ctx->model == DMX_MODEL_TRACER && !ctx->tracer_implicit);
+    return rc;
+}
 int launch_volvars_only(dmx_ctx* ctx) { return fail(ctx, DMX_ERR_USAGE, "the secondary variables are evaluated inside the assembly kernel"); }
 
 } // namespace dmx

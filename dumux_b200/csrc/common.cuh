@@ -120,6 +120,7 @@ struct dmx_ctx {
     int *d_rowptr = nullptr, *d_colidx = nullptr, *d_diag = nullptr;
     double *d_J = nullptr, *d_ilu = nullptr;
     bool ilu_valid = false;
+    bool jac_diagonal = false;        // every off-diagonal block of d_J is exactly zero (explicit tracer assembly): ILU0 = D^-1
     bool ilu_bcrs_valid = false;      // d_ilu holds the factorised BCRS values (generic path; structured path: on download only)
 
     // vectors
@@ -269,6 +270,7 @@ int launch_spmv(dmx_ctx* ctx, const double* x, double* y);
 int ilu0_factor(dmx_ctx* ctx);
 int ilu0_factor_bcrs(dmx_ctx* ctx);
 int ilu0_apply(dmx_ctx* ctx, const double* d, double* v);
+int ssor_apply(dmx_ctx* ctx, const double* d, double* v);
 int block_jacobi_setup(dmx_ctx* ctx);
 int block_jacobi_apply(dmx_ctx* ctx, const double* d, double* v);
 int dot(dmx_ctx* ctx, const double* a, const double* b, double* out);

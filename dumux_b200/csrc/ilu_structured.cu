@@ -218,6 +218,21 @@ __global__ void __launch_bounds__(256) ilu_diag_kernel(SkewGrid g, const int* __
     }
 }
 
+// Jacobian with all off-diagonal blocks exactly zero (explicit tracer step): every L_ij is 0 * Dinv_j = 0 and the diagonal is
+// never updated, so the recurrence degenerates to Dinv_i = A_ii^-1 for all rows at once -- same bits, no hyperplane loop.
+template <int B>
+__global__ void __launch_bounds__(256) ilu_diag_only_kernel(int n, const int* __restrict__ diag, const double* __restrict__ A, double* Dinv,
+                                                             int* flag)
+{
+    constexpr int BB = B * B;
+    const int I = blockIdx.x * blockDim.x + threadIdx.x;
+    if (I >= n) return;
+    double D[BB];
+    load_block<B>(A + (size_t)diag[I] * BB, D);
+    if (!invert_block<B>(D)) atomicOr(flag, 1);
+    for (int e = 0; e < BB; ++e) Dinv[(size_t)I * BB + e] = D[e];
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // (J, Dinv) -> tile-skewed L and U streams.  One thread per (tile, step, thread slot).
 // Mirrored thread coordinates: slot t = a + 16*b; lower: il = a, jl = b, k = s - a - b;
@@ -763,6 +778,14 @@ static int sk_factor_t(dmx_ctx* ctx, SkewState* st)
         st->diag_grid = std::max(1, std::min(perSm, 2)) * ctx->num_sms;
     }
     DMX_CUDA(cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream));
+    if (ctx->jac_diagonal) {
+        ilu_diag_only_kernel<B><<<(unsigned)((ctx->n + 255) / 256), 256, 0, ctx->stream>>>(ctx->n, ctx->d_diag, ctx->d_J, st->Dinv, ctx->d_flag);
+        DMX_CHECK_LAUNCH();
+        const unsigned grid = (unsigned)((size_t)g.ntiles * g.NS);
+        ilu_skew_kernel<B><<<grid, SK_THREADS, 0, ctx->stream>>>(g, ctx->d_diag, ctx->d_J, st->Dinv, st->Lsk, st->Usk);
+        DMX_CHECK_LAUNCH();
+        return 0;
+    }
     DMX_CUDA(cudaMemsetAsync(ctx->d_barrier, 0, sizeof(unsigned int), ctx->stream));
     SkewGrid gg = g;
     const int* diag = ctx->d_diag;

@@ -573,6 +573,57 @@ __global__ void __launch_bounds__(128) ilu0_upper_kernel(int nlev, const int* up
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Dune::SeqSSOR(1 iteration, w = 1) (what SSORCGIstlSolver / SSORBiCGSTABIstlSolver use, dumux/linear/istlsolvers.hh:686-714):
+// one forward and one backward block Gauss-Seidel sweep (dune-istl gsetc.hh bsorf / bsorb).  Per row, columns ascending INCLUDING
+// the diagonal: rhs = d_i - sum_j A_ij x_j (newest values), v = A_ii^-1 rhs (FieldMatrix::solve), x_i += v.  Level-scheduled like
+// the generic ILU0 sweeps: rows of one level are independent, lower (upper) neighbours belong to earlier levels and upper
+// (lower) ones to later levels, so "newest value" is well defined with one grid barrier per level.
+// ---------------------------------------------------------------------------------------------
+template <int B>
+__device__ __forceinline__ void gs_row(int i, const int* rowptr, const int* colidx, const int* diag, const double* A, const double* d, double* x)
+{
+    constexpr int BB = B * B;
+    double rhs[B];
+#pragma unroll
+    for (int e = 0; e < B; ++e) rhs[e] = d[(size_t)i * B + e];
+    const int kend = rowptr[i + 1];
+    for (int k = rowptr[i]; k < kend; ++k) {
+        const int c = colidx[k];
+        double xv[B];
+#pragma unroll
+        for (int e = 0; e < B; ++e) xv[e] = __ldcg(x + (size_t)c * B + e);
+#pragma unroll
+        for (int r = 0; r < B; ++r)
+#pragma unroll
+            for (int cc = 0; cc < B; ++cc) rhs[r] -= A[(size_t)k * BB + r * B + cc] * xv[cc];
+    }
+    const double* D = A + (size_t)diag[i] * BB;
+    double v[B];
+    if (B == 1) v[0] = rhs[0] / D[0];
+    else {
+        double detinv = D[0] * D[3] - D[1] * D[2];
+        detinv = 1 / detinv;
+        v[0] = detinv * (D[3] * rhs[0] - D[1] * rhs[B - 1]);
+        v[B - 1] = detinv * (D[0] * rhs[B - 1] - D[2] * rhs[0]);
+    }
+#pragma unroll
+    for (int e = 0; e < B; ++e) __stcg(x + (size_t)i * B + e, __ldcg(x + (size_t)i * B + e) + 1.0 * v[e]);
+}
+template <int B>
+__global__ void __launch_bounds__(128) gs_sweep_kernel(int nlev, const int* lptr, const int* lrows, const int* rowptr, const int* colidx,
+                                                       const int* diag, const double* A, const double* d, double* x, unsigned int* barrier)
+{
+    unsigned int epoch = 0;
+    for (int l = 0; l < nlev; ++l) {
+        const int r0 = lptr[l], r1 = lptr[l + 1];
+        for (int q = r0 + blockIdx.x * blockDim.x + threadIdx.x; q < r1; q += gridDim.x * blockDim.x)
+            gs_row<B>(lrows[q], rowptr, colidx, diag, A, d, x);
+        if (l + 1 < nlev) grid_barrier(barrier, epoch);
+    }
+}
+
 static int coop_grid(dmx_ctx* ctx, const void* kernel, int threads)
 {
     int perSm = 0;
@@ -651,6 +702,31 @@ int ilu0_apply(dmx_ctx* ctx, const double* d, double* v)
     return rc;
 }
 
+// v = SeqSSOR(J)(d), starting from v = 0 (the Krylov solvers clear the correction before Preconditioner::apply)
+int ssor_apply(dmx_ctx* ctx, const double* d, double* v)
+{
+    ProfScope ps(ctx, DMX_K_ILU_APPLY);
+    if (ctx->l_ptr.empty()) { if (int rc0 = build_level_schedule(ctx)) return rc0; }
+    const size_t len = (size_t)ctx->n * ctx->b;
+    DMX_CUDA(cudaMemsetAsync(v, 0, len * sizeof(double), ctx->stream));
+    const int nl = (int)ctx->l_ptr.size() - 1, nu = (int)ctx->u_ptr.size() - 1;
+    int rc;
+    if (ctx->b == 2) {
+        rc = coop_launch(ctx, gs_sweep_kernel<2>, 128, nl, (const int*)ctx->d_lptr, (const int*)ctx->d_lrows, (const int*)ctx->d_rowptr,
+                         (const int*)ctx->d_colidx, (const int*)ctx->d_diag, (const double*)ctx->d_J, d, v, ctx->d_barrier);
+        if (rc) return rc;
+        rc = coop_launch(ctx, gs_sweep_kernel<2>, 128, nu, (const int*)ctx->d_uptr, (const int*)ctx->d_urows, (const int*)ctx->d_rowptr,
+                         (const int*)ctx->d_colidx, (const int*)ctx->d_diag, (const double*)ctx->d_J, d, v, ctx->d_barrier);
+    } else {
+        rc = coop_launch(ctx, gs_sweep_kernel<1>, 128, nl, (const int*)ctx->d_lptr, (const int*)ctx->d_lrows, (const int*)ctx->d_rowptr,
+                         (const int*)ctx->d_colidx, (const int*)ctx->d_diag, (const double*)ctx->d_J, d, v, ctx->d_barrier);
+        if (rc) return rc;
+        rc = coop_launch(ctx, gs_sweep_kernel<1>, 128, nu, (const int*)ctx->d_uptr, (const int*)ctx->d_urows, (const int*)ctx->d_rowptr,
+                         (const int*)ctx->d_colidx, (const int*)ctx->d_diag, (const double*)ctx->d_J, d, v, ctx->d_barrier);
+    }
+    return rc;
+}
+
 // ---------------------------------------------------------------------------------------------
 // block-Jacobi alternative: v = D^-1 d
 // ---------------------------------------------------------------------------------------------
@@ -707,9 +783,20 @@ int block_jacobi_apply(dmx_ctx* ctx, const double* d, double* v)
 // b = RESIDUAL (not modified).  In a distributed ctx: operator = local SpMV + project, preconditioner = local
 // ILU0 + copyOwnerToAll, scalar product = owner-masked dot + all-reduce (OverlappingSchwarz*, BlockPreconditioner).
 // ---------------------------------------------------------------------------------------------
+// fresh preconditioner per solve (istlsolvers.hh:457-463); SeqSSOR has no set-up
+static int precond_setup(dmx_ctx* ctx, int precond)
+{
+    if (precond == DMX_PRECOND_ILU0) return ilu0_factor(ctx);
+    if (precond == DMX_PRECOND_SSOR) {
+        if (ctx->nranks > 1) return fail(ctx, DMX_ERR_USAGE, "SSOR runs on a single domain in this version");
+        return 0;
+    }
+    if (precond == DMX_PRECOND_BLOCKJACOBI) return block_jacobi_setup(ctx);
+    return fail(ctx, DMX_ERR_USAGE, "unknown preconditioner");
+}
 static int precond_apply(dmx_ctx* ctx, int precond, const double* d, double* v)
 {
-    int rc = (precond == DMX_PRECOND_ILU0) ? ilu0_apply(ctx, d, v) : block_jacobi_apply(ctx, d, v);
+    int rc = (precond == DMX_PRECOND_ILU0) ? ilu0_apply(ctx, d, v) : (precond == DMX_PRECOND_SSOR ? ssor_apply(ctx, d, v) : block_jacobi_apply(ctx, d, v));
     if (rc) return rc;
     if (ctx->nranks > 1) return halo_exchange(ctx, v);
     return 0;
@@ -728,8 +815,7 @@ int bicgstab(dmx_ctx* ctx, double reduction, int maxit, int precond, int* iterat
     *achieved = 1.0;
 
     // fresh preconditioner per call (istlsolvers.hh:457-463)
-    if (precond == DMX_PRECOND_ILU0) { if ((rc = ilu0_factor(ctx))) return rc; }
-    else if ((rc = block_jacobi_setup(ctx))) return rc;
+    if ((rc = precond_setup(ctx, precond))) return rc;
 
     if (ctx->nranks > 1 && (rc = halo_exchange(ctx, x))) return rc;       // BlockPreconditioner::pre: copyOwnerToAll(x)
     if ((rc = launch_spmv(ctx, x, t))) return rc;
@@ -891,8 +977,7 @@ int gmres(dmx_ctx* ctx, double reduction, int maxit, int restart, int precond, i
     int rc;
     *iterations = 0;
     *achieved = 1.0;
-    if (precond == DMX_PRECOND_ILU0) { if ((rc = ilu0_factor(ctx))) return rc; }
-    else if ((rc = block_jacobi_setup(ctx))) return rc;
+    if ((rc = precond_setup(ctx, precond))) return rc;
 
     auto axpy = [&](double alpha, const double* y, double* xx) -> int {
         ProfScope ps(ctx, DMX_K_BLAS1);
@@ -986,9 +1071,78 @@ int gmres(dmx_ctx* ctx, double reduction, int maxit, int restart, int precond, i
     return status;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Conjugate gradients: Dune::CGSolver::apply restated (SSORCGIstlSolver, dumux/linear/istlsolvers.hh:701-714 -- the linear solver
+// of the reference's 1p incompressible test).  x = DELTA, b = RESIDUAL (not modified); the defect lives in WORK0.
+// ---------------------------------------------------------------------------------------------
+int cg(dmx_ctx* ctx, double reduction, int maxit, int precond, int* iterations, double* achieved)
+{
+    if (ctx->nranks > 1) return fail(ctx, DMX_ERR_USAGE, "CG runs on a single domain in this version");
+    const size_t len = (size_t)ctx->n * ctx->b;
+    double* x = ctx->d_vec[DMX_VEC_DELTA];
+    const double* rhs = ctx->d_vec[DMX_VEC_RESIDUAL];
+    double* b = ctx->d_vec[DMX_VEC_WORK0];
+    double *p = ctx->d_p, *q = ctx->d_v;
+    int rc;
+    *iterations = 0;
+    *achieved = 1.0;
+    if ((rc = precond_setup(ctx, precond))) return rc;
+    auto axpy = [&](double alpha, const double* y, double* xx) -> int {
+        ProfScope ps(ctx, DMX_K_BLAS1);
+        axpy_kernel<<<RED_BLOCKS, 256, 0, ctx->stream>>>(len, alpha, y, xx);
+        DMX_CHECK_LAUNCH();
+        return 0;
+    };
+    if ((rc = launch_spmv(ctx, x, q))) return rc;
+    {
+        ProfScope ps(ctx, DMX_K_BLAS1);
+        gm_sub_kernel<<<RED_BLOCKS, 256, 0, ctx->stream>>>(len, ctx->b, rhs, q, b, ctx->d_owner);
+        DMX_CHECK_LAUNCH();
+    }
+    double s2;
+    if ((rc = dot(ctx, b, b, &s2))) return rc;
+    double def = std::sqrt(s2);
+    const double def0 = def;
+    if (!(def0 == def0) || std::isinf(def0)) return DMX_STATUS_NONFINITE;
+    auto conv = [&](double nrm) { return nrm < reduction * def0 || nrm < 1e-30; };
+    if (conv(def0)) { *achieved = def0 > 0 ? 1.0 : 0.0; return 0; }
+    if ((rc = precond_apply(ctx, precond, b, p))) return rc;
+    double rholast, rho, lambda, alpha, beta;
+    if ((rc = dot(ctx, p, b, &rholast))) return rc;
+    int status = DMX_STATUS_NOT_CONVERGED, i = 1;
+    for (; i <= maxit; ++i) {
+        if ((rc = launch_spmv(ctx, p, q))) return rc;
+        if ((rc = dot(ctx, p, q, &alpha))) return rc;
+        lambda = rholast / alpha;
+        if ((rc = axpy(lambda, p, x))) return rc;
+        if ((rc = axpy(-lambda, q, b))) return rc;
+        if ((rc = dot(ctx, b, b, &s2))) return rc;
+        def = std::sqrt(s2);
+        *iterations = i;
+        if (!(def == def) || std::isinf(def)) { status = DMX_STATUS_NONFINITE; break; }
+        if (conv(def)) { status = 0; break; }
+        if ((rc = precond_apply(ctx, precond, b, q))) return rc;
+        if ((rc = dot(ctx, q, b, &rho))) return rc;
+        beta = rho / rholast;
+        {
+            // p = p*beta + q (p *= beta; p += q)
+            ProfScope ps(ctx, DMX_K_BLAS1);
+            gm_scale_kernel<<<RED_BLOCKS, 256, 0, ctx->stream>>>(len, beta, p, p);
+            DMX_CHECK_LAUNCH();
+        }
+        if ((rc = axpy(1.0, q, p))) return rc;
+        rholast = rho;
+    }
+    if (i > maxit) *iterations = maxit;
+    *achieved = def0 > 0 ? def / def0 : 0.0;
+    if (status == DMX_STATUS_NOT_CONVERGED) ctx->err = "CG: maximum iterations reached";
+    return status;
+}
+
 // the solver selected with dmx_set_linear_solver (what NewtonSolver::solveLinearSystem calls)
 int linear_solve(dmx_ctx* ctx, double reduction, int maxit, int precond, int* iterations, double* achieved)
 {
+    if (ctx->linear_solver == DMX_SOLVER_CG) return cg(ctx, reduction, maxit, precond, iterations, achieved);
     if (ctx->linear_solver == DMX_SOLVER_RESTARTED_GMRES) return gmres(ctx, reduction, maxit, ctx->gmres_restart, precond, iterations, achieved);
     return bicgstab(ctx, reduction, maxit, precond, iterations, achieved);
 }

@@ -33,10 +33,12 @@ enum { DMX_BC_NEUMANN = 0, DMX_BC_DIRICHLET = 1, DMX_BC_NONE = 2, DMX_BC_OUTFLOW
    implicit> (assembly/cclocalassembler.hh:490-600) with OnePIncompressibleLocalResidual (porousmediumflow/1p/
    incompressiblelocalresidual.hh:76-123,204-221).  Incompressible 1p model only (constant density and viscosity). */
 enum { DMX_DIFF_ANALYTIC = 100 };
-enum { DMX_PRECOND_ILU0 = 0, DMX_PRECOND_BLOCKJACOBI = 1 };
+/* SSOR = Dune::SeqSSOR(1 iteration, relaxation 1): the preconditioner of SSORCGIstlSolver / SSORBiCGSTABIstlSolver
+   (linear/istlsolvers.hh:686-714) */
+enum { DMX_PRECOND_ILU0 = 0, DMX_PRECOND_BLOCKJACOBI = 1, DMX_PRECOND_SSOR = 2 };
 /* Krylov method behind dmx_linear_solve / dmx_newton_*: ILUBiCGSTABIstlSolver (linear/istlsolvers.hh:636-642, default) or
    ILURestartedGMResIstlSolver (:660-667) */
-enum { DMX_SOLVER_BICGSTAB = 0, DMX_SOLVER_RESTARTED_GMRES = 1 };
+enum { DMX_SOLVER_BICGSTAB = 0, DMX_SOLVER_RESTARTED_GMRES = 1, DMX_SOLVER_CG = 2 };   /* CG: Dune::CGSolver (SSORCGIstlSolver :701-714) */
 enum { DMX_STATUS_OK = 0, DMX_STATUS_NOT_CONVERGED = 1, DMX_STATUS_BREAKDOWN = 2, DMX_STATUS_NONFINITE = 3 };
 /* device-resident vectors of a ctx */
 enum {
@@ -197,6 +199,8 @@ int  dmx_spmv(dmx_ctx* ctx, int x_vec, int y_vec);                       /* y = 
 int  dmx_ilu0_factor(dmx_ctx* ctx);                                      /* ILU copy of J, in place */
 int  dmx_ilu0_apply(dmx_ctx* ctx, int d_vec, int v_vec);                 /* v = (LU)^-1 d */
 int  dmx_ilu0_download(dmx_ctx* ctx, double* values);
+/* v = SeqSSOR(J)(d) from v = 0: one forward + one backward block Gauss-Seidel sweep (dune-istl gsetc.hh bsorf/bsorb, w = 1) */
+int  dmx_ssor_apply(dmx_ctx* ctx, int d_vec, int v_vec);
 int  dmx_dot(dmx_ctx* ctx, int a_vec, int b_vec, double* out);
 int  dmx_halo_exchange(dmx_ctx* ctx, int vec);                           /* copyOwnerToAll */
 /* average device time in ms of `reps` back-to-back launches of one kernel, CUDA-event timed on the ctx stream.

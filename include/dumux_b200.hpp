@@ -337,6 +337,20 @@ public:
     std::string name() const override { return "ILU0 preconditioned restarted GMRes solver (B200)"; }
 };
 
+//! SSORCGIstlSolver (linear/istlsolvers.hh:701-714; the linear solver of test/porousmediumflow/1p/incompressible/main.cc):
+//! Dune::CGSolver preconditioned with one SeqSSOR iteration
+class GpuSSORCGSolver : public GpuILUBiCGSTABSolver {
+public:
+    explicit GpuSSORCGSolver(std::shared_ptr<Context> ctx) : GpuILUBiCGSTABSolver(std::move(ctx), DMX_SOLVER_CG, 0) { setPreconditioner(DMX_PRECOND_SSOR); }
+    std::string name() const override { return "SSOR preconditioned CG solver (B200)"; }
+};
+//! SSORBiCGSTABIstlSolver (linear/istlsolvers.hh:686-699)
+class GpuSSORBiCGSTABSolver : public GpuILUBiCGSTABSolver {
+public:
+    explicit GpuSSORBiCGSTABSolver(std::shared_ptr<Context> ctx) : GpuILUBiCGSTABSolver(std::move(ctx), DMX_SOLVER_BICGSTAB, 0) { setPreconditioner(DMX_PRECOND_SSOR); }
+    std::string name() const override { return "SSOR preconditioned BiCGSTAB solver (B200)"; }
+};
+
 // =====================================================================================================================
 class GpuNewtonSolver {
 public:

@@ -973,6 +973,78 @@ int bicgstab(size_t N, Op&& op, Prec&& prec, Dot&& sp, double* x, const double* 
     return status;
 }
 
+// Dune::SeqSSOR(n=1, w) [DUNE-ext, restated from dune-istl preconditioners.hh / gsetc.hh]: one bsorf + one bsorb per apply.
+// Per row (forward: ascending rows, backward: descending), columns ascending INCLUDING the diagonal:
+//   rhs = d_i - sum_j A_ij x_j (newest values) ; v = A_ii^-1 rhs (FieldMatrix::solve: 1x1 division, 2x2 closed form) ; x_i += w v
+// Restated for w = 1 (LinearSolver.PreconditionerRelaxation default), where the two nested relaxation factors of gsetc.hh coincide.
+inline void blockSolve(const double* A, const double* rhs, double* x, int b)
+{
+    if (b == 1) { x[0] = rhs[0] / A[0]; return; }
+    double detinv = A[0] * A[3] - A[1] * A[2];
+    detinv = 1 / detinv;
+    x[0] = detinv * (A[3] * rhs[0] - A[1] * rhs[1]);
+    x[1] = detinv * (A[0] * rhs[1] - A[2] * rhs[0]);
+}
+void ssorApply(int n, int b, const int* rowptr, const int* colidx, const double* A, double* x, const double* d)
+{
+    const int bb = b * b;
+    auto row = [&](int i) {
+        double rhs[2], v[2];
+        for (int e = 0; e < b; ++e) rhs[e] = d[(size_t)i * b + e];
+        int kd = -1;
+        for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+            if (colidx[k] == i) kd = k;
+            mmv(A + (size_t)k * bb, x + (size_t)colidx[k] * b, rhs, b);
+        }
+        blockSolve(A + (size_t)kd * bb, rhs, v, b);
+        for (int e = 0; e < b; ++e) x[(size_t)i * b + e] += 1.0 * v[e];
+    };
+    for (int i = 0; i < n; ++i) row(i);
+    for (int i = n - 1; i >= 0; --i) row(i);
+}
+
+// Dune::CGSolver::apply (dune-istl solvers.hh) [DUNE-ext]: preconditioned conjugate gradients, the defect norm is that of b - A x
+template <class Op, class Prec, class Dot>
+int cgSolve(size_t N, Op&& op, Prec&& prec, Dot&& sp, double* x, const double* rhs, double reduction, int maxit, int* iterations,
+            double* achieved)
+{
+    std::vector<double> b(rhs, rhs + N), p(N, 0.0), q(N, 0.0);
+    op(x, q.data());
+    for (size_t i = 0; i < N; ++i) b[i] -= q[i];                 // applyscaleadd(-1, x, b)
+    double def = std::sqrt(sp(b.data(), b.data()));
+    const double def0 = def;
+    *iterations = 0;
+    *achieved = 1.0;
+    if (!(def0 == def0) || std::isinf(def0)) return 3;
+    auto conv = [&](double nrm) { return nrm < reduction * def0 || nrm < 1e-30; };
+    if (conv(def0)) { *achieved = def0 > 0 ? 1.0 : 0.0; return 0; }
+    std::fill(p.begin(), p.end(), 0.0);
+    prec(p.data(), b.data());
+    double rholast = sp(p.data(), b.data()), rho, lambda, alpha, beta;
+    int status = 1, i = 1;
+    for (; i <= maxit; ++i) {
+        op(p.data(), q.data());
+        alpha = sp(p.data(), q.data());
+        lambda = rholast / alpha;
+        for (size_t k = 0; k < N; ++k) x[k] += lambda * p[k];
+        for (size_t k = 0; k < N; ++k) b[k] += -lambda * q[k];
+        def = std::sqrt(sp(b.data(), b.data()));
+        *iterations = i;
+        if (!(def == def) || std::isinf(def)) { status = 3; break; }
+        if (conv(def)) { status = 0; break; }
+        std::fill(q.begin(), q.end(), 0.0);
+        prec(q.data(), b.data());
+        rho = sp(q.data(), b.data());
+        beta = rho / rholast;
+        for (size_t k = 0; k < N; ++k) p[k] *= beta;
+        for (size_t k = 0; k < N; ++k) p[k] += q[k];
+        rholast = rho;
+    }
+    if (i > maxit) *iterations = maxit;
+    *achieved = def0 > 0 ? def / def0 : 0.0;
+    return status;
+}
+
 // Dune::RestartedGMResSolver::apply (dune-istl solvers.hh) [DUNE-ext, restated from the published algorithm]: LEFT-preconditioned
 // GMRes(m) -- the monitored norm is that of the PRECONDITIONED defect M^-1(b - A x) --, Arnoldi with modified Gram-Schmidt,
 // Givens rotations (generatePlaneRotation / applyPlaneRotation), update() by back substitution with the correction added on
@@ -1302,6 +1374,23 @@ int orc_ilu0_gmres(int n, int b, const int* rowptr, const int* colidx, const dou
         N, [&](const double* in, double* out) { spmv(n, b, rowptr, colidx, values, in, out); },
         [&](double* v, const double* d) { ilu0Apply(n, b, rowptr, colidx, ilu.data(), v, d); },
         [&](const double* a, const double* c) { return dot(N, a, c); }, x, rhs, reduction, maxit, restart, iterations, achieved);
+}
+// SSORCGIstlSolver / SSORBiCGSTABIstlSolver (dumux/linear/istlsolvers.hh:686-714): Dune::SeqSSOR(1 iteration, w = 1) with
+// Dune::CGSolver (kind 0) or Dune::BiCGSTABSolver (kind 1).  SSORCG is the linear solver of the reference's 1p incompressible test.
+int orc_ssor_solve(int n, int b, const int* rowptr, const int* colidx, const double* values, double* x, const double* rhs, int krylov,
+                   double reduction, int maxit, int* iterations, double* achieved)
+{
+    const size_t N = (size_t)n * b;
+    auto op = [&](const double* in, double* out) { spmv(n, b, rowptr, colidx, values, in, out); };
+    auto prec = [&](double* v, const double* d) { ssorApply(n, b, rowptr, colidx, values, v, d); };
+    auto sp = [&](const double* a, const double* c) { return dot(N, a, c); };
+    if (krylov == 0) return cgSolve(N, op, prec, sp, x, rhs, reduction, maxit, iterations, achieved);
+    return bicgstab(N, op, prec, sp, x, rhs, reduction, maxit, iterations, achieved);
+}
+void orc_ssor_apply(int n, int b, const int* rowptr, const int* colidx, const double* values, double* v, const double* d)
+{
+    std::fill(v, v + (size_t)n * b, 0.0);
+    ssorApply(n, b, rowptr, colidx, values, v, d);
 }
 void orc_set_linear_solver(orc_problem* p, int kind, int restart)
 {

@@ -85,6 +85,11 @@ int  orc_ilu0_bicgstab(int n, int b, const int* rowptr, const int* colidx, const
    PRECONDITIONED defect, which is what Dune::RestartedGMResSolver monitors */
 int  orc_ilu0_gmres(int n, int b, const int* rowptr, const int* colidx, const double* values, double* x, const double* rhs,
                     double reduction, int maxit, int restart, int* iterations, double* achieved_reduction);
+/* SSORCGIstlSolver (krylov 0) / SSORBiCGSTABIstlSolver (krylov 1), istlsolvers.hh:686-714: SeqSSOR(1, w = 1) preconditioner */
+int  orc_ssor_solve(int n, int b, const int* rowptr, const int* colidx, const double* values, double* x, const double* rhs, int krylov,
+                    double reduction, int maxit, int* iterations, double* achieved_reduction);
+/* v = SeqSSOR(A)(d) from v = 0 (one forward + one backward block Gauss-Seidel sweep) */
+void orc_ssor_apply(int n, int b, const int* rowptr, const int* colidx, const double* values, double* v, const double* d);
 /* linear solver used by orc_newton_solve(_ex) / orc_run_timeloop: ORC_SOLVER_*; restart <= 0: 10 (LinearSolver.GMResRestart) */
 void orc_set_linear_solver(orc_problem* p, int kind, int restart);
 /* standalone pieces for kernel-level parity */

@@ -88,6 +88,10 @@ def lib():
                                      C.POINTER(C.c_int), C.POINTER(C.c_double)]
         L.orc_ilu0_gmres.restype = C.c_int
         L.orc_set_linear_solver.argtypes = [vp, C.c_int, C.c_int]
+        L.orc_ssor_solve.argtypes = [C.c_int, C.c_int, _ip, _ip, _dp, _dp, _dp, C.c_int, C.c_double, C.c_int,
+                                     C.POINTER(C.c_int), C.POINTER(C.c_double)]
+        L.orc_ssor_solve.restype = C.c_int
+        L.orc_ssor_apply.argtypes = [C.c_int, C.c_int, _ip, _ip, _dp, _dp, _dp]
         L.orc_ilu0_factor.argtypes = [C.c_int, C.c_int, _ip, _ip, _dp, _dp]
         L.orc_ilu0_factor.restype = C.c_int
         L.orc_ilu0_apply.argtypes = [C.c_int, C.c_int, _ip, _ip, _dp, _dp, _dp]
@@ -290,6 +294,21 @@ class Oracle:
 
     def law(self, region, which, sw):
         return lib().orc_law_eval(self.h, region, which, float(sw))
+
+
+def ssor_apply(n, b, rowptr, colidx, values, d):
+    v = np.zeros(n * b)
+    lib().orc_ssor_apply(n, b, rowptr, colidx, np.ascontiguousarray(values), v, np.ascontiguousarray(d))
+    return v
+
+
+def ssor_solve(n, b, rowptr, colidx, values, rhs, krylov="cg", reduction=1e-6, maxit=250, x0=None):
+    """SSORCGIstlSolver ('cg') / SSORBiCGSTABIstlSolver ('bicgstab'); returns (x, status, iterations, reduction)."""
+    x = np.zeros(n * b) if x0 is None else np.ascontiguousarray(x0, dtype=np.float64).copy()
+    its, red = C.c_int(0), C.c_double(0)
+    st = lib().orc_ssor_solve(n, b, rowptr, colidx, np.ascontiguousarray(values), x, np.ascontiguousarray(rhs),
+                              {"cg": 0, "bicgstab": 1}[krylov], reduction, maxit, C.byref(its), C.byref(red))
+    return x, st, its.value, red.value
 
 
 def ilu0_factor(n, b, rowptr, colidx, values):

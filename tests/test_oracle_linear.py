@@ -204,6 +204,53 @@ def test_gmres_full_cycle_matches_scipy_gmres():
     assert np.linalg.norm(x - Q @ y) <= 1e-8 * np.linalg.norm(x)
 
 
+@pytest.mark.parametrize("b", [1, 2])
+def test_ssor_is_the_symmetric_gauss_seidel_splitting(b):
+    """SeqSSOR(1, w = 1) from v = 0 equals (D+U)^-1 D (D+L)^-1 d with BLOCK diagonal D (dune-istl bsorf/bsorb)."""
+    n, rp, ci, v = _block_laplacian(7, b)
+    A = _to_scipy(n, b, rp, ci, v).toarray()
+    N = n * b
+    blk = np.arange(N) // b
+    D = np.where(blk[:, None] == blk[None, :], A, 0.0)
+    Lo = np.where(blk[:, None] > blk[None, :], A, 0.0)
+    Up = np.where(blk[:, None] < blk[None, :], A, 0.0)
+    d = np.random.RandomState(3).standard_normal(N)
+    ref = np.linalg.solve(D + Up, D @ np.linalg.solve(D + Lo, d))
+    assert np.allclose(O.ssor_apply(n, b, rp, ci, v, d), ref, rtol=1e-12, atol=1e-14)
+
+
+@pytest.mark.parametrize("krylov", ["cg", "bicgstab"])
+@pytest.mark.parametrize("b,N", [(1, 12), (2, 15)])
+def test_ssor_krylov_converges_to_direct_solution(krylov, b, N):
+    """SSORCGIstlSolver / SSORBiCGSTABIstlSolver restatements on the SPD block Laplacian of test_linearsolver.cc."""
+    n, rp, ci, v = _block_laplacian(N, b)
+    if krylov == "cg":
+        # CG needs a symmetric positive definite operator: symmetrise the randomly perturbed blocks (the pattern is symmetric)
+        Ad = _to_scipy(n, b, rp, ci, v).toarray()
+        Ad = 0.5 * (Ad + Ad.T)
+        vb = np.empty((len(ci), b, b))
+        for i in range(n):
+            for k in range(rp[i], rp[i + 1]):
+                vb[k] = Ad[i * b:(i + 1) * b, ci[k] * b:(ci[k] + 1) * b]
+        v = vb.reshape(-1)
+    A = _to_scipy(n, b, rp, ci, v)
+    rhs = np.random.RandomState(4).uniform(-1, 1, n * b)
+    x, st, its, red = O.ssor_solve(n, b, rp, ci, v, rhs, krylov, 1e-13, 400)
+    assert st == 0 and red < 1e-13 and 1 <= its < 200
+    assert np.allclose(x, spla.spsolve(A.tocsc(), rhs), rtol=1e-9, atol=1e-11)
+    assert np.linalg.norm(rhs - A @ x) / np.linalg.norm(rhs) == pytest.approx(red, rel=1e-3, abs=1e-15)
+    # CG: the energy-norm error decreases monotonically with the iteration limit
+    if krylov == "cg":
+        xs = spla.spsolve(A.tocsc(), rhs)
+        last = np.inf
+        for maxit in (1, 2, 4, 8, 16):
+            xm, stm, itm, _ = O.ssor_solve(n, b, rp, ci, v, rhs, "cg", 1e-30, maxit)
+            e = xm - xs
+            en = float(e @ (A @ e))
+            assert itm == maxit and en <= last * (1 + 1e-12)
+            last = en
+
+
 def test_assembled_jacobian_solve_against_scipy():
     """The real thing: 2p lens Jacobian + residual, ILU0-BiCGSTAB at Newton's reduction vs a sparse direct solve."""
     spec = problems.twop_lens((24, 16), law="vg")
