@@ -706,6 +706,166 @@ __global__ void __launch_bounds__(256) onep_analytic_jacobian_kernel(const AsmPa
 }
 
 // ================================================================================================
+// DiffMethod::analytic for the incompressible 2p model (p0-s1, phase 0 wetting): CCLocalAssembler<analytic, implicit>
+// (assembly/cclocalassembler.hh:490-600) + TwoPIncompressibleLocalResidual (porousmediumflow/2p/incompressiblelocalresidual.hh:
+// 80-101 storage derivatives, :137-234 TPFA flux derivatives, :420-481 Dirichlet faces; Neumann faces contribute nothing).
+// One thread per block row, rows written whole, blocks [eq][priVar] with priVars (p_w, S_n); the residual comes from the
+// JAC = false instantiation of the tile kernel.  Same operation sequence as the oracle (bit-identical); not tuned -- the
+// numerically differentiated tile kernel stays the benchmarked path.
+// ================================================================================================
+struct TwoPState {
+    double p[2], mob[2], Sw, K;
+    int region;
+};
+__device__ __forceinline__ TwoPState twop_state(const AsmParams& P, size_t C)
+{
+    TwoPState s;
+    const double2 u = reinterpret_cast<const double2*>(P.cur)[C];
+    s.region = P.region[C];
+    s.K = P.K[C];
+    const MaterialLaw& law = P.laws[s.region];
+    s.Sw = 1 - u.y;
+    const double pc = law_pc(law, s.Sw);
+    s.p[0] = u.x;
+    s.p[1] = u.x + pc;
+    s.mob[0] = law_krw(law, s.Sw) / P.mu[0];
+    s.mob[1] = law_krn(law, s.Sw) / P.mu[1];
+    return s;
+}
+template <int DIM>
+__global__ void __launch_bounds__(128) twop_analytic_jacobian_kernel(const AsmParams P)
+{
+    const size_t I = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (I >= (size_t)P.n) return;
+    const int nx = P.nc[0], ny = P.nc[1];
+    const int ci[3] = {(int)(I % nx), (int)((I / nx) % ny), (int)(I / ((size_t)nx * ny))};
+    const size_t stride[3] = {1, (size_t)nx, (size_t)nx * ny};
+    bool ex[6];
+    int pos[6];
+#pragma unroll
+    for (int s = 0; s < 6; ++s) ex[s] = (s >> 1) < DIM && ((s & 1) ? ci[s >> 1] + 1 < P.nc[s >> 1] : ci[s >> 1] > 0);
+    const int rowStart = P.rowptr[I];
+    const int posDiag = rowStart + (ex[4] ? 1 : 0) + (ex[2] ? 1 : 0) + (ex[0] ? 1 : 0);
+    pos[4] = rowStart;
+    pos[2] = rowStart + (ex[4] ? 1 : 0);
+    pos[0] = pos[2] + (ex[2] ? 1 : 0);
+    pos[1] = posDiag + 1;
+    pos[3] = pos[1] + (ex[1] ? 1 : 0);
+    pos[5] = pos[3] + (ex[3] ? 1 : 0);
+
+    const TwoPState sI = twop_state(P, I);
+    const MaterialLaw& lawI = P.laws[sI.region];
+    const double w = P.upwind_weight, extr = P.extrusion;
+    const double rho_w = P.rho[0], rho_n = P.rho[1];
+    const double rhow_muw = rho_w / P.mu[0], rhon_mun = rho_n / P.mu[1];
+    const double dKrw_dSn_inside = -1.0 * law_dkrw_dsw(lawI, sI.Sw);
+    const double dKrn_dSn_inside = -1.0 * law_dkrn_dsw(lawI, sI.Sw);
+    const double dpc_dSn_inside = -1.0 * law_dpc_dsw(lawI, sI.Sw);
+    double wdt[3] = {P.width[0][ci[0]], DIM > 1 ? P.width[1][ci[1]] : 1.0, DIM > 2 ? P.width[2][ci[2]] : 1.0};
+    double AII[4] = {0.0, 0.0, 0.0, 0.0};
+    if (!P.stationary) {
+        double vol = 1.0;
+        vol *= wdt[0];
+        if (DIM > 1) vol *= wdt[1];
+        if (DIM > 2) vol *= wdt[2];
+        const double phiI = P.phi[I];
+        const double porosity = 1.0 - (1.0 - phiI);
+        const double poreVolume = vol * porosity;
+        AII[1] -= poreVolume * rho_w / P.dt;
+        AII[3] += poreVolume * rho_n / P.dt;
+    }
+#pragma unroll
+    for (int s = 0; s < 2 * DIM; ++s) {
+        const int a = s >> 1;
+        const bool hi = (s & 1);
+        double area = 1.0;
+        if (a != 0) area *= wdt[0];
+        if (a != 1 && DIM > 1) area *= wdt[1];
+        if (a != 2 && DIM > 2) area *= wdt[2];
+        const bool grav = P.enable_gravity && (a == DIM - 1);
+        const double ng = hi ? -P.gravity : P.gravity;
+        const double alphaI = sI.K * ng * extr;
+        double pJ[2], upJ[2], tij, flux[2];
+        double dKrw_dSn_outside = 0.0, dKrn_dSn_outside = 0.0, dpc_dSn_outside = 0.0;
+        bool boundary = false;
+        if (ex[s]) {
+            const size_t J = hi ? I + stride[a] : I - stride[a];
+            const int cj = hi ? ci[a] + 1 : ci[a] - 1;
+            const TwoPState sJ = twop_state(P, J);
+            const MaterialLaw& lawJ = P.laws[sJ.region];
+            tij = hi ? P.tij[a][I] : P.tij[a][J];
+            pJ[0] = sJ.p[0]; pJ[1] = sJ.p[1];
+            upJ[0] = rho_w * sJ.mob[0]; upJ[1] = rho_n * sJ.mob[1];
+            const double tJ = sJ.K * extr * (hi ? P.gf_lo[a][cj] : P.gf_hi[a][cj]);
+            const double alphaJ = sJ.K * ng * extr;
+#pragma unroll
+            for (int ph = 0; ph < 2; ++ph) {
+                double f = tij * (sI.p[ph] - pJ[ph]);
+                if (grav) {
+                    const double rho = (P.rho[ph] + P.rho[ph]) * 0.5;
+                    f = f + rho * area * alphaI;
+                    f -= rho * tij / tJ * (alphaI - alphaJ);
+                }
+                flux[ph] = f;
+            }
+            dKrw_dSn_outside = -1.0 * law_dkrw_dsw(lawJ, sJ.Sw);
+            dKrn_dSn_outside = -1.0 * law_dkrn_dsw(lawJ, sJ.Sw);
+            dpc_dSn_outside = -1.0 * law_dpc_dsw(lawJ, sJ.Sw);
+        } else {
+            int f_;
+            if (a == 0) f_ = ci[1] + ny * ci[2];
+            else if (a == 1) f_ = ci[0] + nx * ci[2];
+            else f_ = ci[0] + nx * ci[1];
+            const int type = P.bc_type[s] ? P.bc_type[s][f_] : DMX_BC_NEUMANN;
+            if (type != DMX_BC_DIRICHLET) continue;
+            boundary = true;
+            const double ti = sI.K * extr * (hi ? P.gf_hi[a][ci[a]] : P.gf_lo[a][ci[a]]);
+            tij = area * ti;
+#pragma unroll
+            for (int ph = 0; ph < 2; ++ph) {
+                pJ[ph] = P.bc_p[s][(size_t)f_ * 2 + ph];
+                upJ[ph] = P.bc_up[s][(size_t)f_ * 2 + ph];
+                double f = tij * (sI.p[ph] - pJ[ph]);
+                if (grav) f = f + P.bc_rho[s][(size_t)f_ * 2 + ph] * area * alphaI;
+                flux[ph] = f;
+            }
+        }
+        const double flux_w = flux[0], flux_n = flux[1];
+        const double insideWeight_w = signbit(flux_w) ? (1.0 - w) : w;
+        const double outsideWeight_w = 1.0 - insideWeight_w;
+        const double insideWeight_n = signbit(flux_n) ? (1.0 - w) : w;
+        const double outsideWeight_n = 1.0 - insideWeight_n;
+        const double up_w = (rho_w * sI.mob[0]) * insideWeight_w + upJ[0] * outsideWeight_w;
+        const double up_n = (rho_n * sI.mob[1]) * insideWeight_n + upJ[1] * outsideWeight_n;
+        if (boundary) {
+            AII[0] += tij * up_w;
+            AII[1] += rhow_muw * flux_w * dKrw_dSn_inside * insideWeight_w;
+            AII[2] += tij * up_n;
+            AII[3] += rhon_mun * flux_n * dKrn_dSn_inside * insideWeight_n;
+            AII[3] += tij * dpc_dSn_inside * up_n;
+            continue;
+        }
+        const double rho_mu_flux_w = rhow_muw * flux_w, rho_mu_flux_n = rhon_mun * flux_n;
+        const double tij_up_w = tij * up_w, tij_up_n = tij * up_n;
+        double AIJ[4] = {0.0, 0.0, 0.0, 0.0};
+        AII[0] += tij_up_w;
+        AIJ[0] -= tij_up_w;
+        AII[1] += rho_mu_flux_w * dKrw_dSn_inside * insideWeight_w;
+        AIJ[1] += rho_mu_flux_w * dKrw_dSn_outside * outsideWeight_w;
+        AII[2] += tij_up_n;
+        AIJ[2] -= tij_up_n;
+        AII[3] += rho_mu_flux_n * dKrn_dSn_inside * insideWeight_n;
+        AIJ[3] += rho_mu_flux_n * dKrn_dSn_outside * outsideWeight_n;
+        AII[3] += tij_up_n * dpc_dSn_inside;
+        AIJ[3] -= tij_up_n * dpc_dSn_outside;
+        double* dst = P.jac + (size_t)pos[s] * 4;
+        dst[0] = AIJ[0]; dst[1] = AIJ[1]; dst[2] = AIJ[2]; dst[3] = AIJ[3];
+    }
+    double* dst = P.jac + (size_t)posDiag * 4;
+    dst[0] = AII[0]; dst[1] = AII[1]; dst[2] = AII[2]; dst[3] = AII[3];
+}
+
+// ================================================================================================
 // Tracer transport on a frozen velocity field (BASELINE config 5, examples/1ptracer)
 // ================================================================================================
 // Volume fluxes over all scvfs from the 1p pressure field in CUR: examples/1ptracer/main.cc:162-199
@@ -1104,16 +1264,28 @@ static int launch_impl(dmx_ctx* ctx, bool with_jac, bool volvars_only)
         return 0;
     }
     if (ctx->opt.fd_method == DMX_DIFF_ANALYTIC) {
-        if (ctx->model != DMX_MODEL_1P || ctx->tabulated)
-            return fail(ctx, DMX_ERR_USAGE, "DiffMethod::analytic is available for the incompressible 1p model only");
+        if (ctx->tabulated) return fail(ctx, DMX_ERR_USAGE, "DiffMethod::analytic is available for incompressible fluids only");
+        const unsigned grid = (unsigned)((ctx->n + 127) / 128);
+        if (ctx->model == DMX_MODEL_2P) {
+            for (const auto& l : ctx->laws)
+                if (l.wetting != 0)
+                    return fail(ctx, DMX_ERR_USAGE, "DiffMethod::analytic (2p/incompressiblelocalresidual.hh) assumes that phase 0 is the wetting phase");
+            if (int rc = launch_tile<DMX_MODEL_2P, false>(ctx, P, false)) return rc;      // residual
+            if (!with_jac) return 0;
+            ProfScope ps__(ctx, DMX_K_ASSEMBLY);
+            if (ctx->dim == 3) twop_analytic_jacobian_kernel<3><<<grid, 128, 0, ctx->stream>>>(P);
+            else if (ctx->dim == 2) twop_analytic_jacobian_kernel<2><<<grid, 128, 0, ctx->stream>>>(P);
+            else twop_analytic_jacobian_kernel<1><<<grid, 128, 0, ctx->stream>>>(P);
+            DMX_CHECK_LAUNCH();
+            return 0;
+        }
         if (int rc = launch_tile<DMX_MODEL_1P, false>(ctx, P, false)) return rc;          // residual
         if (!with_jac) return 0;
-        const unsigned grid = (unsigned)((ctx->n + 255) / 256);
         const double up = ctx->rho[0] / ctx->mu[0];               // volVars.density() / volVars.viscosity()
         ProfScope ps__(ctx, DMX_K_ASSEMBLY);
-        if (ctx->dim == 3) onep_analytic_jacobian_kernel<3><<<grid, 256, 0, ctx->stream>>>(P, up);
-        else if (ctx->dim == 2) onep_analytic_jacobian_kernel<2><<<grid, 256, 0, ctx->stream>>>(P, up);
-        else onep_analytic_jacobian_kernel<1><<<grid, 256, 0, ctx->stream>>>(P, up);
+        if (ctx->dim == 3) onep_analytic_jacobian_kernel<3><<<grid, 128, 0, ctx->stream>>>(P, up);
+        else if (ctx->dim == 2) onep_analytic_jacobian_kernel<2><<<grid, 128, 0, ctx->stream>>>(P, up);
+        else onep_analytic_jacobian_kernel<1><<<grid, 128, 0, ctx->stream>>>(P, up);
         DMX_CHECK_LAUNCH();
         return 0;
     }

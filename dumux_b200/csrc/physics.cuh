@@ -159,6 +159,39 @@ DMX_HD double law_krn(const MaterialLaw& p, double sw)
     return base_krn(p, swe);
 }
 
+// regularised derivatives w.r.t. the absolute wetting saturation (materiallaw.hh dpc_dsw / dkrw_dsw / dkrn_dsw with the
+// regularisation of brookscorey.hh / vangenuchten.hh): what the analytic 2p Jacobian (2p/incompressiblelocalresidual.hh) calls
+DMX_HD double law_dpc_dsw(const MaterialLaw& p, double sw)
+{
+    const double swe = swToSwe(p, sw);
+    if (p.regularized) {
+        if (swe <= p.pcLowSwe) return p.pcDerivativeLowSw * dswe_dsw(p);
+        else if (swe >= 1.0) return p.pcDerivativeHighSwEnd * dswe_dsw(p);
+        else if (p.kind == LAW_VANGENUCHTEN && swe > p.pcHighSwe) return spline_eval_derivative(p.pcSpline, swe) * dswe_dsw(p);
+    }
+    return base_dpc_dswe(p, swe) * dswe_dsw(p);
+}
+DMX_HD double law_dkrw_dsw(const MaterialLaw& p, double sw)
+{
+    const double swe = swToSwe(p, sw);
+    if (p.regularized) {
+        if (swe <= 0.0) return 0.0;
+        else if (swe >= 1.0) return 0.0;
+        else if (p.kind == LAW_VANGENUCHTEN && swe >= p.krwHighSwe) return spline_eval_derivative(p.krwSpline, swe) * dswe_dsw(p);
+    }
+    return base_dkrw_dswe(p, swe) * dswe_dsw(p);
+}
+DMX_HD double law_dkrn_dsw(const MaterialLaw& p, double sw)
+{
+    const double swe = swToSwe(p, sw);
+    if (p.regularized) {
+        if (swe <= 0.0) return 0.0;
+        else if (swe >= 1.0) return 0.0;
+        else if (p.kind == LAW_VANGENUCHTEN && swe <= p.krnLowSwe) return spline_eval_derivative(p.krnSpline, swe) * dswe_dsw(p);
+    }
+    return base_dkrn_dswe(p, swe) * dswe_dsw(p);
+}
+
 // derived regularisation constants: brookscorey.hh:481-489; vangenuchten.hh initPcParameters_/initKrParameters_
 inline void law_init(MaterialLaw& p)
 {

@@ -305,11 +305,13 @@ def onep_compressible(cells=(10, 10), lower=None, upper=None, dt=0.002, lognorma
 # spatialparams.hh:46-140).  2-D: y vertical.  `vertical_axis` = dim-1 always (gravity acts along -e_{dim-1}).
 # ------------------------------------------------------------------------------------------------------
 def twop_lens(cells=(48, 32), law="vg", lower=None, upper=None, lens_lower=None, lens_upper=None,
-              dt=250.0, heterogeneity_sigma=0.0, seed=0, bc_params=None, slab=None, plane_rng=False, oilwet=False) -> ProblemSpec:
+              dt=250.0, heterogeneity_sigma=0.0, seed=0, bc_params=None, slab=None, plane_rng=False, oilwet=False,
+              analytic=False) -> ProblemSpec:
     """`slab` = (lo, hi): build only those layers of the last axis (see ProblemSpec.slab); `plane_rng`: per-layer
     heterogeneity streams (implied by `slab`).  `oilwet`: test_2p_incompressible_tpfa_oilwet (SpatialParams.LensIsOilWet,
     Problem.EnableGravity false): the lens keeps the outer permeability and pc-kr-Sw parameters but phase 1 wets it
-    (spatialparams.hh:76,105,117-122) and the injection rate is ten times higher (problem.hh:112-113)."""
+    (spatialparams.hh:76,105,117-122) and the injection rate is ten times higher (problem.hh:112-113).
+    `analytic`: DiffMethod::analytic (test_2p_incompressible_tpfa_analytic)."""
     dim = len(cells)
     if dim == 2:
         lower = (0.0, 0.0) if lower is None else lower
@@ -372,7 +374,8 @@ def twop_lens(cells=(48, 32), law="vg", lower=None, upper=None, lens_lower=None,
     return ProblemSpec(
         name=f"2p_lens_{dim}d_{law}", model=MODEL_2P, dim=dim, cells=tuple(cells), lower=tuple(lower), upper=tuple(upper),
         K=K, phi=np.full(n, 0.4), region=region, materials=mats, rho=(1000.0, 1460.0), mu=(1e-3, 5.7e-4),
-        bc_type=bc_type, bc_values=bc_values, options=Options(stationary=False, dt=dt, enable_gravity=not oilwet), initial=init,
+        bc_type=bc_type, bc_values=bc_values, options=Options(stationary=False, dt=dt, enable_gravity=not oilwet, fd_method=DIFF_ANALYTIC if analytic else 1),
+        initial=init,
         slab=slab)
 
 

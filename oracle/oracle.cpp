@@ -450,7 +450,8 @@ struct orc_problem {
     // ---- advective TPFA flux of one phase over the face `side` of `cI`: flux/cctpfa/darcyslaw.hh:154-213,
     //      transmissibility :218-259, upwinding flux/upwindscheme.hh:36-54,
     //      phase mass flux porousmediumflow/immiscible/localresidual.hh:98-127 ----
-    void computeFlux(double* flux, const int* cI, int side, const VolVars& in, const VolVars& out, bool boundary, const int* cJ) const
+    void computeFlux(double* flux, const int* cI, int side, const VolVars& in, const VolVars& out, bool boundary, const int* cJ,
+                     double* darcy = nullptr) const
     {
         const int a = side / 2;
         const double area = faceArea(a, cI);
@@ -486,6 +487,7 @@ struct orc_problem {
             } else {
                 f = tij * (in.p[ph] - out.p[ph]);
             }
+            if (darcy) darcy[ph] = f;        // AdvectionType::flux (darcyslaw.hh:154-213): what the analytic derivatives upwind with
             // upwindscheme.hh:43-53, upwind term = density*mobility (immiscible/localresidual.hh:113-114)
             const double w = opt.upwind_weight;
             const double upIn = volumeFluxMode ? in.mob[ph] : in.rho[ph] * in.mob[ph];
@@ -633,6 +635,105 @@ struct orc_problem {
                     jac[kd] += deriv;
                 }
             }
+        }
+    }
+
+    // ---------------------------------------------------------------------------------------------
+    // DiffMethod::analytic for the incompressible 2p model (p0-s1, phase 0 wetting): CCLocalAssembler<analytic, implicit>
+    // (dumux/assembly/cclocalassembler.hh:490-600) with TwoPIncompressibleLocalResidual
+    // (dumux/porousmediumflow/2p/incompressiblelocalresidual.hh:80-101 storage, :137-234 TPFA flux derivatives,
+    // :420-481 Dirichlet faces; Neumann faces contribute nothing).  Blocks are [eq][priVar], priVars = (p_w, S_n).
+    // What test_2p_incompressible_tpfa_analytic runs.
+    // ---------------------------------------------------------------------------------------------
+    void assembleElementAnalytic2p(int I, const double* cur, const double* prev, double* residual, double* jac) const
+    {
+        int cI[3];
+        ijk(I, cI);
+        VolVars vvI, prevVV, nb[6];
+        updateVolVars(vvI, cur + (size_t)I * b, I);
+        if (!opt.stationary) updateVolVars(prevVV, prev + (size_t)I * b, I);
+        int nbIdx[6], nbC[6][3];
+        for (int side = 0; side < 6; ++side) {
+            nbIdx[side] = (side < 2 * dim) ? neighbor(cI, side) : -1;
+            if (nbIdx[side] >= 0) {
+                ijk(nbIdx[side], nbC[side]);
+                updateVolVars(nb[side], cur + (size_t)nbIdx[side] * b, nbIdx[side]);
+            }
+        }
+        double orig0[2];
+        evalLocalResidual(orig0, I, cI, vvI, nb, &prevVV);
+        if (residual)
+            for (int e = 0; e < 2; ++e) residual[(size_t)I * 2 + e] = orig0[e];
+        if (!jac) return;
+        double* AII = jac + (size_t)findEntry(I, I) * 4;
+        if (!opt.stationary) {
+            // :96-101 (Extrusion::volume of the default NoExtrusion: the scv volume)
+            const double poreVolume = volume(cI) * vvI.porosity;
+            AII[0 * 2 + 1] -= poreVolume * vvI.rho[0] / opt.dt;
+            AII[1 * 2 + 1] += poreVolume * vvI.rho[1] / opt.dt;
+        }
+        const Law& lawI = laws[region[I]];
+        const double w = opt.upwind_weight;
+        const double rho_w = vvI.rho[0], rho_n = vvI.rho[1];
+        const double rhow_muw = rho_w / vvI.mu[0], rhon_mun = rho_n / vvI.mu[1];
+        const double insideSw = vvI.S[0];
+        const double dKrw_dSn_inside = -1.0 * lawI.dkrw_dsw(insideSw);
+        const double dKrn_dSn_inside = -1.0 * lawI.dkrn_dsw(insideSw);
+        const double dpc_dSn_inside = -1.0 * lawI.dpc_dsw(insideSw);
+        for (int side = 0; side < 2 * dim; ++side) {
+            const int J = nbIdx[side];
+            VolVars bv;
+            const VolVars* out = nullptr;
+            bool boundary = false;
+            if (J >= 0) out = &nb[side];
+            else {
+                const int fidx = sideFaceIndex(side, cI);
+                const int type = bcType[side].empty() ? ORC_BC_NEUMANN : bcType[side][fidx];
+                if (type != ORC_BC_DIRICHLET) continue;
+                double pv[2] = {bcVal[side][(size_t)fidx * 2], bcVal[side][(size_t)fidx * 2 + 1]};
+                updateVolVars(bv, pv, I);
+                out = &bv;
+                boundary = true;
+            }
+            double fl[2], darcy[2];
+            computeFlux(fl, cI, side, vvI, *out, boundary, boundary ? nullptr : nbC[side], darcy);
+            const double flux_w = darcy[0], flux_n = darcy[1];
+            const double insideWeight_w = std::signbit(flux_w) ? (1.0 - w) : w;
+            const double outsideWeight_w = 1.0 - insideWeight_w;
+            const double insideWeight_n = std::signbit(flux_n) ? (1.0 - w) : w;
+            const double outsideWeight_n = 1.0 - insideWeight_n;
+            const double rhowKrw_muw_inside = rho_w * vvI.mob[0], rhonKrn_mun_inside = rho_n * vvI.mob[1];
+            const double rhowKrw_muw_outside = rho_w * out->mob[0], rhonKrn_mun_outside = rho_n * out->mob[1];
+            const double tij = boundary ? advectionTij(cI, side, vvI.K, vvI.extr, true, nullptr, 0.0, 0.0)
+                                        : advectionTij(cI, side, vvI.K, vvI.extr, false, nbC[side], out->K, out->extr);
+            const double up_w = rhowKrw_muw_inside * insideWeight_w + rhowKrw_muw_outside * outsideWeight_w;
+            const double up_n = rhonKrn_mun_inside * insideWeight_n + rhonKrn_mun_outside * outsideWeight_n;
+            if (boundary) {
+                AII[0] += tij * up_w;
+                AII[1] += rhow_muw * flux_w * dKrw_dSn_inside * insideWeight_w;
+                AII[2] += tij * up_n;
+                AII[3] += rhon_mun * flux_n * dKrn_dSn_inside * insideWeight_n;
+                AII[3] += tij * dpc_dSn_inside * up_n;
+                continue;
+            }
+            const Law& lawJ = laws[region[J]];
+            const double outsideSw = out->S[0];
+            const double dKrw_dSn_outside = -1.0 * lawJ.dkrw_dsw(outsideSw);
+            const double dKrn_dSn_outside = -1.0 * lawJ.dkrn_dsw(outsideSw);
+            const double dpc_dSn_outside = -1.0 * lawJ.dpc_dsw(outsideSw);
+            const double rho_mu_flux_w = rhow_muw * flux_w, rho_mu_flux_n = rhon_mun * flux_n;
+            const double tij_up_w = tij * up_w, tij_up_n = tij * up_n;
+            double* AIJ = jac + (size_t)findEntry(I, J) * 4;
+            AII[0] += tij_up_w;
+            AIJ[0] -= tij_up_w;
+            AII[1] += rho_mu_flux_w * dKrw_dSn_inside * insideWeight_w;
+            AIJ[1] += rho_mu_flux_w * dKrw_dSn_outside * outsideWeight_w;
+            AII[2] += tij_up_n;
+            AIJ[2] -= tij_up_n;
+            AII[3] += rho_mu_flux_n * dKrn_dSn_inside * insideWeight_n;
+            AIJ[3] += rho_mu_flux_n * dKrn_dSn_outside * outsideWeight_n;
+            AII[3] += tij_up_n * dpc_dSn_inside;
+            AIJ[3] -= tij_up_n * dpc_dSn_outside;
         }
     }
 
@@ -1303,7 +1404,8 @@ void orc_assemble(orc_problem* p, const double* cur, const double* prev, double*
 #pragma omp parallel for schedule(static) num_threads(nt)
 #endif
     for (int I = 0; I < p->n; ++I) {
-        if (p->opt.fd_method == ORC_DIFF_ANALYTIC) p->assembleElementAnalytic1p(I, cur, prev, residual, jac);
+        if (p->opt.fd_method == ORC_DIFF_ANALYTIC && p->model == ORC_MODEL_2P) p->assembleElementAnalytic2p(I, cur, prev, residual, jac);
+        else if (p->opt.fd_method == ORC_DIFF_ANALYTIC) p->assembleElementAnalytic1p(I, cur, prev, residual, jac);
         else p->assembleElement(I, cur, prev, residual, jac);
     }
 }

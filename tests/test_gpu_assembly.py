@@ -83,6 +83,20 @@ def test_2p_lens(engine_factory, law, cells):
     assert rerr <= 1e-13 and jerr <= RTOL, (rerr, jerr)
 
 
+@pytest.mark.parametrize("law", ["vg", "bc"])
+@pytest.mark.parametrize("cells", [(48, 32), (20, 12, 9)])
+def test_2p_analytic_jacobian(engine_factory, law, cells):
+    """DiffMethod::analytic for the incompressible 2p model (2p/incompressiblelocalresidual.hh:80-234,420-481): bit-identical to
+    the oracle, saturations spanning the regularised branches."""
+    spec = problems.twop_lens(cells, law=law, heterogeneity_sigma=0.5 if len(cells) == 3 else 0.0, analytic=True)
+    rng = np.random.RandomState(12)
+    cur = _perturbed(spec, 6)
+    cur[:, 1] = rng.choice([-0.01, 0.0, 1e-9, 0.03, 0.3, 0.6, 0.9, 0.97, 1.0, 1.02], size=cur.shape[0])
+    prev = _perturbed(spec, 7)
+    rerr, jerr, (res_o, jac_o, res_g, jac_g) = _compare(spec, engine_factory, cur, prev)
+    assert np.array_equal(res_g, res_o) and np.array_equal(jac_g, jac_o), (rerr, jerr)
+
+
 @pytest.mark.parametrize("cells", [(48, 32), (20, 12, 9)])
 def test_2p_oilwet_lens(engine_factory, cells):
     """Per-region wetting phase (2p/volumevariables.hh:87-96,132-152; test_2p_incompressible_tpfa_oilwet): in the lens phase 1

@@ -69,6 +69,25 @@ def test_2p_lens_timeloop_golden(engine_factory):
         assert np.all((d <= 1.5e-7) | (d <= 1e-2 * np.abs(ref))), name
 
 
+def test_2p_lens_analytic_timeloop_golden(engine_factory):
+    """test_2p_incompressible_tpfa_analytic: analytic Jacobian + ILU0-GMRes(10), seven time steps to t = 3000 s, same Newton counts
+    as the oracle, fields vs oracle (1e-8) and vs test_2p_incompressible_cc-reference.vtu."""
+    spec = problems.twop_lens((48, 32), law="vg", analytic=True)
+    o = Oracle(spec)
+    o.set_linear_solver("gmres", 10)
+    uo, nso, itso, dtso = o.run_timeloop(spec.initial, 3000.0, 250.0)
+    e = engine_factory(spec)
+    e.set_linear_solver("gmres", 10)
+    ug, itsg, dtsg = e.run_timeloop(spec.initial, 3000.0, 250.0)
+    assert len(itsg) == 7 and list(itsg) == list(itso), (itsg, itso)
+    assert np.allclose(dtsg, dtso, rtol=0, atol=0)
+    uo2, ug2 = uo.reshape(-1, 2), ug.reshape(-1, 2)
+    assert _rel_l2(ug2[:, 0], uo2[:, 0]) <= 1e-8
+    assert _rel_l2(ug2[:, 1], uo2[:, 1]) <= 1e-8
+    g = np.load(os.path.join(GOLDEN, "test_2p_incompressible_cc.npz"))
+    assert np.abs(ug2[:, 1] - g["S_napl"]).max() < 5e-6
+
+
 def test_2p_oilwet_timeloop_golden(engine_factory):
     """test_2p_incompressible_tpfa_oilwet: oil-wet lens, no gravity, dt0 = 130 s, ILU0-GMRes(10) as in the reference's main.cc:134
     -> nine time steps to t = 3000 s (the golden file is output number 9), same Newton counts and time steps as the oracle,

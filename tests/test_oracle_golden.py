@@ -111,7 +111,8 @@ def test_2p_lens_48x32_reference_vtu(lens_run):
     """test_2p_incompressible_tpfa (van Genuchten lens, tEnd 3000 s, dt0 250 s) -> test_2p_incompressible_cc-reference.vtu.
     All ten stored fields are compared at the reference's fuzzy tolerance."""
     spec, o, u, nsteps, its, dts = lens_run
-    assert nsteps > 0 and abs(sum(dts) - 3000.0) < 1e-6
+    # the golden file is output number 7 of the reference run (CMakeLists.txt: test_2p_incompressible_tpfa-00007.vtu)
+    assert nsteps == 7 and abs(sum(dts) - 3000.0) < 1e-6
     g = np.load(os.path.join(GOLDEN, "test_2p_incompressible_cc.npz"))
     vv = o.volvars(u.reshape(-1))
     cols = {"S_aq": 0, "S_napl": 1, "p_aq": 2, "p_napl": 3, "rho_aq": 4, "rho_napl": 5, "mob_aq": 6, "mob_napl": 7, "pc": 8,
@@ -122,6 +123,36 @@ def test_2p_lens_48x32_reference_vtu(lens_run):
     # tighter than the reference's own bar: saturations to 2e-4 absolute, pressures to 1e-5 relative
     assert np.abs(u[:, 1] - g["S_napl"]).max() < 2e-4
     assert np.abs(u[:, 0] / g["p_aq"] - 1).max() < 1e-5
+
+
+def test_2p_lens_analytic_jacobian_reference_vtu(lens_run):
+    """test_2p_incompressible_tpfa_analytic (DiffMethod::analytic, 2p/incompressiblelocalresidual.hh:80-234,420-481; ILU0-GMRes) is
+    compared by the reference against the SAME golden file, again output number 7: seven time steps, the Newton counts of the
+    numeric run, S_n to Float32 precision.  The analytic Jacobian equals a central-difference one except where the finite
+    difference straddles an upwind switch."""
+    import dataclasses
+    spec = problems.twop_lens((48, 32), law="vg", analytic=True)
+    o = Oracle(spec)
+    o.set_linear_solver("gmres", 10)
+    u, nsteps, its, dts = o.run_timeloop(spec.initial, 3000.0, 250.0)
+    assert nsteps == 7 and list(its) == list(lens_run[4])
+    g = np.load(os.path.join(GOLDEN, "test_2p_incompressible_cc.npz"))
+    u2 = u.reshape(-1, 2)
+    assert np.abs(u2[:, 1] - g["S_napl"]).max() < 5e-6
+    assert np.abs(u2[:, 0] / g["p_aq"] - 1).max() < 1e-5
+    rng = np.random.RandomState(0)
+    small = problems.twop_lens((24, 16), law="vg", analytic=True)
+    cur = small.initial.copy()
+    cur[:, 0] += rng.uniform(-50, 50, cur.shape[0])
+    cur[:, 1] = rng.uniform(0.02, 0.6, cur.shape[0])
+    prev = small.initial.copy()
+    prev[:, 1] = rng.uniform(0, 0.3, cur.shape[0])
+    ra, ja = Oracle(small).assemble(cur, prev)
+    central = dataclasses.replace(small, options=dataclasses.replace(small.options, fd_method=0, base_eps=1e-6))
+    rc, jc = Oracle(central).assemble(cur, prev)
+    assert np.array_equal(ra, rc)
+    rel = np.abs(ja - jc).reshape(-1, 4) / np.abs(jc).reshape(-1, 4).max(axis=0)
+    assert np.mean(rel.max(axis=1) < 1e-7) > 0.99 and np.median(rel) < 1e-10
 
 
 def test_2p_oilwet_lens_reference_vtu():
