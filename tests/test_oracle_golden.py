@@ -120,8 +120,8 @@ def test_2p_lens_48x32_reference_vtu(lens_run):
     for name, c in cols.items():
         ref = g[name].astype(np.float64)
         assert _fuzzy_ok(vv[:, c], ref), name
-    # tighter than the reference's own bar: saturations to 2e-4 absolute, pressures to 1e-5 relative
-    assert np.abs(u[:, 1] - g["S_napl"]).max() < 2e-4
+    # far tighter than the reference's own bar (Float32 storage is the limit): saturations to 5e-6 absolute, pressures to 1e-5 relative
+    assert np.abs(u[:, 1] - g["S_napl"]).max() < 5e-6
     assert np.abs(u[:, 0] / g["p_aq"] - 1).max() < 1e-5
 
 
