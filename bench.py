@@ -397,7 +397,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cells", type=int, default=256, help="cube edge per GPU")
     ap.add_argument("--global-z", type=int, default=0, help="fix the global number of z layers (strong scaling)")
-    ap.add_argument("--cpu-edge", type=int, default=64, help="cube edge of the bounded CPU sample")
+    ap.add_argument("--cpu-edge", type=int, default=96, help="cube edge of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
