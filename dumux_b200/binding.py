@@ -31,7 +31,7 @@ EXPORTS = [
     "dmx_ilu0_factor", "dmx_ilu0_apply", "dmx_ilu0_download", "dmx_dot", "dmx_halo_exchange", "dmx_time_kernel",
     "dmx_kernel_launch_count", "dmx_synchronize", "dmx_profile", "dmx_profile_read",
     "dmx_newton_step_host", "dmx_timer_start", "dmx_timer_stop", "dmx_debug_sweep_trace",
-    "dmx_volume_flux", "dmx_set_volume_flux", "dmx_set_tracer", "dmx_set_wetting_phase", "dmx_set_linear_solver", "dmx_ssor_apply",
+    "dmx_volume_flux", "dmx_set_volume_flux", "dmx_set_tracer", "dmx_set_wetting_phase", "dmx_set_linear_solver", "dmx_ssor_apply", "dmx_num_output_fields", "dmx_output_fields",
 ]
 SOLVER_BICGSTAB, SOLVER_RESTARTED_GMRES, SOLVER_CG = 0, 1, 2
 PRECOND_SSOR = 2
@@ -109,6 +109,8 @@ def load_library():
     L.dmx_set_wetting_phase.argtypes = [vp, C.c_int, C.c_int]
     L.dmx_set_linear_solver.argtypes = [vp, C.c_int, C.c_int]
     L.dmx_ssor_apply.argtypes = [vp, C.c_int, C.c_int]
+    L.dmx_num_output_fields.argtypes = [vp]
+    L.dmx_output_fields.argtypes = [vp, C.c_void_p]
     L.dmx_set_boundary.argtypes = [vp, C.c_int, _ip, _dp]
     L.dmx_vec_upload.argtypes = [vp, C.c_int, C.c_void_p]
     L.dmx_vec_download.argtypes = [vp, C.c_int, C.c_void_p]
@@ -368,6 +370,20 @@ class Engine:
     def set_linear_solver(self, kind, restart=10):
         """'bicgstab' = ILUBiCGSTABIstlSolver (default), 'gmres' = ILURestartedGMResIstlSolver (LinearSolver.GMResRestart)."""
         self._check(self.L.dmx_set_linear_solver(self.h, {"bicgstab": SOLVER_BICGSTAB, "gmres": SOLVER_RESTARTED_GMRES, "cg": SOLVER_CG}[kind], restart))
+
+    def output_fields(self, phase_names=("aq", "napl")):
+        """Output fields of the state in CUR with the reference's names (IOName::saturation/pressure/density/mobility<FluidSystem>,
+        capillaryPressure, porosity; dumux/io/name.hh): an ordered dict name -> array[n]."""
+        nf = self.L.dmx_num_output_fields(self.h)
+        out = np.zeros((nf, self.n_local if hasattr(self, "n_local") else self.n))
+        self._check(self.L.dmx_output_fields(self.h, _hostptr(out)))
+        if nf == 1:
+            return {"p": out[0]}
+        names = []
+        for ph in phase_names:
+            names += [f"S_{ph}", f"p_{ph}", f"rho_{ph}", f"mob_{ph}"]
+        names += ["pc", "porosity"]
+        return dict(zip(names, out))
 
     def ssor_apply(self, d_vec, v_vec):
         self._check(self.L.dmx_ssor_apply(self.h, d_vec, v_vec))

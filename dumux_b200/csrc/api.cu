@@ -787,6 +787,23 @@ int dmx_ilu0_apply(dmx_ctx* ctx, int d_vec, int v_vec)
     if (int rc = vec_ok(ctx, v_vec)) return rc;
     return ilu0_apply(ctx, ctx->d_vec[d_vec], ctx->d_vec[v_vec]);
 }
+int dmx_num_output_fields(const dmx_ctx* ctx) { return ctx->model == DMX_MODEL_2P ? 10 : 1; }
+int dmx_output_fields(dmx_ctx* ctx, double* out)
+{
+    if (!ctx->has_grid) return fail(ctx, DMX_ERR_USAGE, "output_fields: set grid first");
+    DMX_CUDA(cudaSetDevice(ctx->device));
+    const size_t len = (size_t)dmx_num_output_fields(ctx) * ctx->n;
+    double* d = nullptr;
+    DMX_CUDA(cudaMalloc((void**)&d, len * sizeof(double)));
+    int rc = launch_output_fields(ctx, d);
+    if (!rc) {
+        cudaError_t e = cudaMemcpyAsync(out, d, len * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = fail(ctx, DMX_ERR_CUDA, std::string("output_fields: ") + cudaGetErrorString(e));
+    }
+    cudaFree(d);
+    return rc;
+}
 int dmx_ssor_apply(dmx_ctx* ctx, int d_vec, int v_vec)
 {
     if (!ctx->d_J) return fail(ctx, DMX_ERR_USAGE, "ssor_apply: no pattern");

@@ -1308,6 +1308,53 @@ int launch_volume_flux(dmx_ctx* ctx, double* d_out)
     return 0;
 }
 
+// ================================================================================================
+// Output fields of the device-resident solution (what VtkOutputModule asks the volume variables for):
+// TwoPIOFields (porousmediumflow/2p/iofields.hh:31-50): per phase S, p, rho, mobility, then pc and porosity;
+// OnePIOFields (1p/iofields.hh:30-33): p.  out[field][cell] (SoA), computed from CUR with the same secondary-variable
+// evaluation as the assembly (TwoPVolumeVariables::update incl. the per-region wetting phase).
+// ================================================================================================
+__global__ void __launch_bounds__(256) output_fields_2p_kernel(const AsmParams P, double* __restrict__ out)
+{
+    const size_t I = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t n = (size_t)P.n;
+    if (I >= n) return;
+    const double2 u = reinterpret_cast<const double2*>(P.cur)[I];
+    const MaterialLaw& law = P.laws[P.region[I]];
+    const int w = law.wetting ? 1 : 0, nw = 1 - w;
+    double S[2], p[2], mob[2];
+    S[1] = u.y;
+    S[0] = 1 - u.y;
+    const double pc = law_pc(law, S[w]);
+    p[0] = u.x;
+    p[1] = w ? u.x - pc : u.x + pc;
+    mob[w] = law_krw(law, S[w]) / P.mu[w];
+    mob[nw] = law_krn(law, S[w]) / P.mu[nw];
+#pragma unroll
+    for (int ph = 0; ph < 2; ++ph) {
+        out[(size_t)(4 * ph + 0) * n + I] = S[ph];
+        out[(size_t)(4 * ph + 1) * n + I] = p[ph];
+        out[(size_t)(4 * ph + 2) * n + I] = P.rho[ph];
+        out[(size_t)(4 * ph + 3) * n + I] = mob[ph];
+    }
+    out[(size_t)8 * n + I] = pc;
+    out[(size_t)9 * n + I] = 1.0 - (1.0 - P.phi[I]);
+}
+
+int launch_output_fields(dmx_ctx* ctx, double* d_out)
+{
+    if (int rc = prepare(ctx)) return rc;
+    AsmParams P;
+    fill_params(ctx, P);
+    if (ctx->model == DMX_MODEL_2P) {
+        output_fields_2p_kernel<<<(unsigned)((ctx->n + 255) / 256), 256, 0, ctx->stream>>>(P, d_out);
+        DMX_CHECK_LAUNCH();
+        return 0;
+    }
+    DMX_CUDA(cudaMemcpyAsync(d_out, ctx->d_vec[DMX_VEC_CUR], (size_t)ctx->n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    return 0;
+}
+
 int launch_assemble(dmx_ctx* ctx, bool with_jacobian)
 {
     const int rc = launch_impl(ctx, with_jacobian, false);

@@ -263,6 +263,7 @@ int prepare(dmx_ctx* ctx);
 int launch_assemble(dmx_ctx* ctx, bool with_jacobian);
 int launch_volvars_only(dmx_ctx* ctx);
 int launch_volume_flux(dmx_ctx* ctx, double* d_out);
+int launch_output_fields(dmx_ctx* ctx, double* d_out);
 // implemented in linalg.cu
 int build_diag(dmx_ctx* ctx);
 int build_level_schedule(dmx_ctx* ctx);

@@ -199,6 +199,11 @@ int  dmx_spmv(dmx_ctx* ctx, int x_vec, int y_vec);                       /* y = 
 int  dmx_ilu0_factor(dmx_ctx* ctx);                                      /* ILU copy of J, in place */
 int  dmx_ilu0_apply(dmx_ctx* ctx, int d_vec, int v_vec);                 /* v = (LU)^-1 d */
 int  dmx_ilu0_download(dmx_ctx* ctx, double* values);
+/* Output fields of the solution in CUR as VtkOutputModule collects them from the volume variables (io/vtkoutputmodule.hh):
+   2p: TwoPIOFields (porousmediumflow/2p/iofields.hh:31-50) S_0, p_0, rho_0, mob_0, S_1, p_1, rho_1, mob_1, pc, porosity;
+   1p / tracer: the primary variable (1p/iofields.hh:30-33).  out: host buffer [dmx_num_output_fields][num_cells]. */
+int  dmx_num_output_fields(const dmx_ctx* ctx);
+int  dmx_output_fields(dmx_ctx* ctx, double* out);
 /* v = SeqSSOR(J)(d) from v = 0: one forward + one backward block Gauss-Seidel sweep (dune-istl gsetc.hh bsorf/bsorb, w = 1) */
 int  dmx_ssor_apply(dmx_ctx* ctx, int d_vec, int v_vec);
 int  dmx_dot(dmx_ctx* ctx, int a_vec, int b_vec, double* out);
