@@ -81,10 +81,14 @@ int main(int argc, char** argv)
     const std::string mode = argc > 1 ? argv[1] : "1p";
     try {
         auto ctx = std::make_shared<Context>(0);
-        if (mode == "1p") {
+        if (mode == "1p" || mode == "1p-ssorcg") {
             const int nx = 10, ny = 10;
             auto assembler = std::make_shared<GpuFVAssembler>(ctx, onepIncompressible(nx, ny));
-            auto linearSolver = std::make_shared<GpuILUBiCGSTABSolver>(ctx);
+            // test/porousmediumflow/1p/incompressible/main.cc uses SSORCGIstlSolver; the ILU-BiCGSTAB variant is the bench solver
+            std::shared_ptr<GpuILUBiCGSTABSolver> linearSolver;
+            if (mode == "1p-ssorcg") linearSolver = std::make_shared<GpuSSORCGSolver>(ctx);
+            else linearSolver = std::make_shared<GpuILUBiCGSTABSolver>(ctx);
+            std::fprintf(stderr, "linear solver: %s\n", linearSolver->name().c_str());
             GpuFVAssembler::SolutionVector x(assembler->numDofs(), 1, 0.0);
             assembler->setLinearSystem();
             assembler->assembleJacobian(x);
@@ -111,7 +115,11 @@ int main(int argc, char** argv)
                 }
             auto xOld = x;
             auto assembler = std::make_shared<GpuFVAssembler>(ctx, pd, dtInitial, xOld);
-            auto linearSolver = std::make_shared<GpuILUBiCGSTABSolver>(ctx);
+            // test/porousmediumflow/2p/incompressible/main.cc:134 uses ILURestartedGMResIstlSolver
+            std::shared_ptr<GpuILUBiCGSTABSolver> linearSolver;
+            if (mode == "2p-gmres") linearSolver = std::make_shared<GpuILURestartedGMResSolver>(ctx);
+            else linearSolver = std::make_shared<GpuILUBiCGSTABSolver>(ctx);
+            std::fprintf(stderr, "linear solver: %s\n", linearSolver->name().c_str());
             GpuNewtonSolver nonLinearSolver(assembler, linearSolver);
             // plain TimeLoop (common/timeloop.hh:239-252,320-332,385-411)
             double time = 0.0, dt = dtInitial;

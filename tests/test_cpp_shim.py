@@ -64,6 +64,24 @@ def test_shim_1p_main_reproduces_golden(shim_exe):
 
 
 @pytest.mark.gpu
+def test_shim_reference_solver_aliases(shim_exe):
+    """The solvers the reference mains actually instantiate: SSORCGIstlSolver for the 1p test (1p/incompressible/main.cc) and
+    ILURestartedGMResIstlSolver for the 2p test (2p/incompressible/main.cc:134), through their C++ mirrors."""
+    p = subprocess.run([shim_exe, "1p-ssorcg"], capture_output=True, text=True, check=True)
+    assert "SSOR preconditioned CG" in p.stderr
+    x = np.array([float(v) for v in p.stdout.split()])
+    g = np.load(os.path.join(GOLDEN, "test_1p_cc.npz"))["p"].astype(np.float64)
+    assert x.shape == g.shape and np.abs(x / g - 1).max() < 5e-6
+    p = subprocess.run([shim_exe, "2p-gmres"], capture_output=True, text=True, check=True)
+    assert "restarted GMRes" in p.stderr
+    u = np.array([float(v) for v in p.stdout.split()]).reshape(-1, 2)
+    steps = [l for l in p.stderr.splitlines() if l.startswith("step")]
+    assert len(steps) == 7                                   # the golden file is output number 7
+    g = np.load(os.path.join(GOLDEN, "test_2p_incompressible_cc.npz"))
+    assert np.abs(u[:, 1] - g["S_napl"]).max() < 5e-6 and np.abs(u[:, 0] / g["p_aq"] - 1).max() < 1e-5
+
+
+@pytest.mark.gpu
 def test_shim_2p_timeloop_reproduces_oracle_and_golden(shim_exe):
     from dumux_b200 import problems
     from oracle.oracle_py import Oracle
