@@ -935,6 +935,12 @@ __global__ void __launch_bounds__(256) gm_sub_kernel(size_t len, int b, const do
         out[i] = own ? rhs[i] - Ax[i] : 0.0;
     }
 }
+// x += (-h[0]) * y with the coefficient taken from device memory (the Gram-Schmidt chain runs without host round trips)
+__global__ void __launch_bounds__(256) gm_axpy_neg_dev_kernel(size_t len, const double* __restrict__ h, const double* y, double* x)
+{
+    const double mh = -h[0];
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (size_t)gridDim.x * blockDim.x) x[i] += mh * y[i];
+}
 __global__ void __launch_bounds__(256) gm_scale_kernel(size_t len, double f, const double* src, double* dst)
 {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i] * f;
@@ -965,9 +971,11 @@ int gmres(dmx_ctx* ctx, double reduction, int maxit, int restart, int precond, i
     if (!ctx->d_gm || ctx->gm_vectors < m + 3) {
         if (ctx->d_gm) cudaFree(ctx->d_gm);
         ctx->d_gm = nullptr;
-        DMX_CUDA(cudaMalloc((void**)&ctx->d_gm, (size_t)(m + 3) * len * sizeof(double)));
+        DMX_CUDA(cudaMalloc((void**)&ctx->d_gm, ((size_t)(m + 3) * len + (size_t)(m + 2)) * sizeof(double)));
         ctx->gm_vectors = m + 3;
     }
+    double* d_h = ctx->d_gm + (size_t)ctx->gm_vectors * len;      // Gram-Schmidt coefficients of one Arnoldi step + ||w||^2
+    std::vector<double> h_h(m + 2);
     auto V = [&](int k) { return ctx->d_gm + (size_t)k * len; };
     double* w = V(m + 1);
     double* bdef = V(m + 2);
@@ -1024,15 +1032,30 @@ int gmres(dmx_ctx* ctx, double reduction, int maxit, int restart, int precond, i
         for (i = 0; i < m && j <= maxit && !converged; ++i, ++j) {
             if ((rc = launch_spmv(ctx, V(i), V(i + 1)))) return rc;
             if ((rc = precond_apply(ctx, precond, V(i + 1), w))) return rc;
-            for (int k = 0; k < i + 1; ++k) {
-                double h;
-                if ((rc = dot(ctx, V(k), w, &h))) return rc;
-                Hm(k, i) = h;
-                if ((rc = axpy(-h, V(k), w))) return rc;
+            {
+                // modified Gram-Schmidt, chained on the device: h_k = <v_k, w> is reduced into d_h[k] and consumed by the next
+                // update from there; the host reads all coefficients of the step (and ||w||^2) once
+                ProfScope ps(ctx, DMX_K_BLAS1);
+                for (int k = 0; k < i + 1; ++k) {
+                    dot_kernel<1><<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>>(len, ctx->b, V(k), w, nullptr, nullptr, nullptr, nullptr,
+                                                                                ctx->d_owner, ctx->d_partials);
+                    DMX_CHECK_LAUNCH();
+                    final_reduce_kernel<false><<<1, RED_THREADS, 0, ctx->stream>>>(RED_BLOCKS, 1, ctx->d_partials, d_h + k);
+                    DMX_CHECK_LAUNCH();
+                    gm_axpy_neg_dev_kernel<<<RED_BLOCKS, 256, 0, ctx->stream>>>(len, d_h + k, V(k), w);
+                    DMX_CHECK_LAUNCH();
+                }
+                dot_kernel<1><<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>>(len, ctx->b, w, w, nullptr, nullptr, nullptr, nullptr, ctx->d_owner,
+                                                                            ctx->d_partials);
+                DMX_CHECK_LAUNCH();
+                final_reduce_kernel<false><<<1, RED_THREADS, 0, ctx->stream>>>(RED_BLOCKS, 1, ctx->d_partials, d_h + i + 1);
+                DMX_CHECK_LAUNCH();
             }
-            double ww;
-            if ((rc = dot(ctx, w, w, &ww))) return rc;
-            Hm(i + 1, i) = std::sqrt(ww);
+            DMX_CUDA(cudaMemcpyAsync(h_h.data(), d_h, (size_t)(i + 2) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+            DMX_CUDA(cudaStreamSynchronize(ctx->stream));
+            if (ctx->prof_pending.size() > 512) prof_drain(ctx);
+            for (int k = 0; k < i + 1; ++k) Hm(k, i) = h_h[k];
+            Hm(i + 1, i) = std::sqrt(h_h[i + 1]);
             *iterations = j;
             if (!(Hm(i + 1, i) == Hm(i + 1, i)) || std::isinf(Hm(i + 1, i))) return DMX_STATUS_NONFINITE;
             if (std::fabs(Hm(i + 1, i)) < EPSILON) {
