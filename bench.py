@@ -168,8 +168,12 @@ def run_reference(args):
         "impl": "reference", "metric": f"{METRIC} {args.cells}^3", "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["sec_per_step"] * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"2p immiscible CCTpfa lens {args.cells}^3 per GPU, Brooks-Corey, numeric differentiation, ILU0-BiCGSTAB 1e-6",
-                   "sample_cells": edge ** 3},
+        # the arm's workload (same wording as the B200 arm's `config`), timed on a bounded sample of it
+        "config": {"workload": f"2p immiscible CCTpfa lens/infiltration, {args.cells}x{args.cells}x{args.cells} cells ({args.cells}^3 per GPU), "
+                               f"Brooks-Corey, lognormal K multiplier sigma 0.5, numeric differentiation (forward, eps 1e-10), 2x2 BCRS blocks",
+                   "step": "one Newton iteration: assemble + ILU0 factor + BiCGSTAB(1e-6) + update, from the hydrostatic initial state, dt 250 s",
+                   "linear_solver": f"ILU0-BiCGSTAB, reduction 1e-6, maxit {LIN_MAXIT}", "bicgstab_iterations_per_step": r["bicgstab_iterations"],
+                   "parallelism": "host cores of the GPU box", "sample_cells": edge ** 3},
         "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
