@@ -31,7 +31,7 @@ EXPORTS = [
     "dmx_ilu0_factor", "dmx_ilu0_apply", "dmx_ilu0_download", "dmx_dot", "dmx_halo_exchange", "dmx_time_kernel",
     "dmx_kernel_launch_count", "dmx_synchronize", "dmx_profile", "dmx_profile_read",
     "dmx_newton_step_host", "dmx_timer_start", "dmx_timer_stop", "dmx_debug_sweep_trace",
-    "dmx_volume_flux", "dmx_set_volume_flux", "dmx_set_tracer", "dmx_set_wetting_phase", "dmx_set_linear_solver", "dmx_ssor_apply", "dmx_num_output_fields", "dmx_output_fields",
+    "dmx_volume_flux", "dmx_set_volume_flux", "dmx_set_tracer", "dmx_set_wetting_phase", "dmx_set_linear_solver", "dmx_ssor_apply", "dmx_num_output_fields", "dmx_output_fields", "dmx_set_tracer_diffusion",
 ]
 SOLVER_BICGSTAB, SOLVER_RESTARTED_GMRES, SOLVER_CG = 0, 1, 2
 PRECOND_SSOR = 2
@@ -106,6 +106,7 @@ def load_library():
     L.dmx_volume_flux.argtypes = [vp, _dp]
     L.dmx_set_volume_flux.argtypes = [vp, _dp]
     L.dmx_set_tracer.argtypes = [vp, C.c_int]
+    L.dmx_set_tracer_diffusion.argtypes = [vp, C.c_double, C.c_double]
     L.dmx_set_wetting_phase.argtypes = [vp, C.c_int, C.c_int]
     L.dmx_set_linear_solver.argtypes = [vp, C.c_int, C.c_int]
     L.dmx_ssor_apply.argtypes = [vp, C.c_int, C.c_int]
@@ -267,6 +268,7 @@ class Engine:
             # slab-decomposed runs: per-cell fluxes of the local box incl. overlap, like every other per-cell array
             self._check(L.dmx_set_volume_flux(self.h, np.ascontiguousarray(self.localize_cells(spec.volume_flux), dtype=np.float64).reshape(-1)))
             self._check(L.dmx_set_tracer(self.h, int(spec.implicit)))
+            self._check(L.dmx_set_tracer_diffusion(self.h, float(spec.tracer_diffusion[0]), float(spec.tracer_diffusion[1])))
 
     def localize_cells(self, a):
         """Cut the local slab (incl. overlap) out of a global per-cell array (x fastest)."""

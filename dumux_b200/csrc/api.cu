@@ -557,6 +557,13 @@ int dmx_set_volume_flux(dmx_ctx* ctx, const double* vf)
     DMX_CUDA(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
+int dmx_set_tracer_diffusion(dmx_ctx* ctx, double D, double tortuosity)
+{
+    if (ctx->model != DMX_MODEL_TRACER) return fail(ctx, DMX_ERR_USAGE, "set_tracer_diffusion: not a tracer context");
+    ctx->tracer_D = D;
+    ctx->tracer_tau = tortuosity;
+    return 0;
+}
 int dmx_set_tracer(dmx_ctx* ctx, int implicit)
 {
     if (ctx->model != DMX_MODEL_TRACER) return fail(ctx, DMX_ERR_USAGE, "set_tracer: not a tracer ctx");

@@ -1006,17 +1006,33 @@ __global__ void __launch_bounds__(256) tracer_assemble_kernel(const AsmParams P)
             double mult;
             if (signbit(vflux)) mult = w * upOut + (1.0 - w) * upIn;
             else mult = w * upIn + (1.0 - w) * upOut;
+            // Fick's law, TPFA (flux/cctpfa/fickslaw.hh) with D_eff = porosity * S * tau * D (S = 1): harmonic transmissibility of
+            // the two half-cell values, flux = rho_avg * tij * (X_I - X_J); D = 0 gives tij = 0
+            const int cj = hi ? ci[a] + 1 : ci[a] - 1;
+            const double porosityJ = 1.0 - (1.0 - P.phi[J]);
+            const double DeffI = porosity * 1.0 * P.tracer_tau * P.tracer_D;
+            const double DeffJ = porosityJ * 1.0 * P.tracer_tau * P.tracer_D;
+            double areaF = 1.0;
+            for (int d = 0; d < DIM; ++d)
+                if (d != a) areaF *= P.width[d][ci[d]];
+            const double ti = DeffI * extr * (hi ? P.gf_hi[a][ci[a]] : P.gf_lo[a][ci[a]]);
+            const double tj = DeffJ * extr * (hi ? P.gf_lo[a][cj] : P.gf_hi[a][cj]);
+            double dTij;
+            if (ti * tj <= 0.0) dTij = 0;
+            else dTij = areaF * (ti * tj) / (ti + tj);
+            const double rhoAvg = 0.5 * (rho + rho);
             double flux = 0.0;
             flux += vflux * mult;
-            flux += 0.0;       // diffusive flux, D = 0
+            flux += rhoAvg * dTij * (XI - X[J]);
             res += flux;
             if constexpr (JAC) {
                 double offdiag = 0.0;
                 if (implicit) {
                     const double insideWeight = signbit(vflux) ? (1.0 - w) : w;
                     const double outsideWeight = 1.0 - insideWeight;
-                    diag += vflux * rho * insideWeight;
-                    offdiag += vflux * rho * outsideWeight;
+                    const double diffDeriv = rhoAvg * dTij;
+                    diag += (vflux * rho * insideWeight + diffDeriv);
+                    offdiag += (vflux * rho * outsideWeight - diffDeriv);
                 }
                 P.jac[pos[s]] = offdiag;
             }
@@ -1099,6 +1115,7 @@ static void fill_params(dmx_ctx* ctx, AsmParams& P)
     }
     P.cur = ctx->d_vec[DMX_VEC_CUR]; P.prev = ctx->d_vec[DMX_VEC_PREV];
     P.vf = ctx->d_vf; P.tracer_implicit = ctx->tracer_implicit;
+    P.tracer_D = ctx->tracer_D; P.tracer_tau = ctx->tracer_tau;
     P.rowptr = ctx->d_rowptr; P.residual = ctx->d_vec[DMX_VEC_RESIDUAL]; P.jac = ctx->d_J;
     P.flag_nonfinite = ctx->d_flag;
 }

@@ -38,6 +38,7 @@ struct AsmParams {
     const double* tij[3];     // transmissibility of the + face of each cell along axis a
     const double* vf;         // tracer: frozen volume fluxes [n][2*dim]
     int tracer_implicit;
+    double tracer_D, tracer_tau;          // Fick's law: binary diffusion coefficient, constant tortuosity
     // fluids
     double rho[2], mu[2];
     double rmu[2], rdt;       // correctly rounded 1/mu, 1/dt (host IEEE division) for div_by
@@ -99,6 +100,7 @@ struct dmx_ctx {
     double* d_tij[3] = {nullptr, nullptr, nullptr};
     double* d_vf = nullptr;             // tracer: frozen volume fluxes [n][2*dim]
     int tracer_implicit = 0;
+    double tracer_D = 0.0, tracer_tau = 0.5;
 
     std::vector<dmx::MaterialLaw> laws;
     dmx::MaterialLaw* d_laws = nullptr;

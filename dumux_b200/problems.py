@@ -71,6 +71,8 @@ class ProblemSpec:
     # time discretisation (False: explicit Euler as in examples/1ptracer/main.cc:236, True: implicit)
     volume_flux: Optional[np.ndarray] = None
     implicit: bool = False
+    # tracer: (binary diffusion coefficient D, SpatialParams.Tortuosity) of Fick's law with DiffusivityConstantTortuosity; D = 0: off
+    tracer_diffusion: Tuple[float, float] = (0.0, 0.5)
     # slab-local spec (multi-GPU set-up without materialising the global arrays): the per-cell / per-face arrays above
     # cover only the layers [slab[0], slab[1]) of the last axis (overlap included); cells/lower/upper stay GLOBAL.
     slab: Optional[Tuple[int, int]] = None
@@ -434,3 +436,47 @@ def tracer_transport(cells, volume_flux, dt=10.0, implicit=False) -> ProblemSpec
         K=np.ones(n), phi=np.full(n, 0.2), region=np.zeros(n, dtype=np.int32), materials=[],
         rho=(1000.0,), mu=(1e-3,), bc_type=bc_type, bc_values=bc_values,
         options=Options(stationary=False, dt=dt, enable_gravity=False), initial=init, volume_flux=vf, implicit=implicit)
+
+
+# ------------------------------------------------------------------------------------------------------
+# test/porousmediumflow/tracer/constvel (params.input, problem.hh:60-120, spatialparams.hh:40-100): analytic divergence-free
+# velocity field sampled at the face centres (volumeFlux = v(ipGlobal) . n * area), porosity 0.2, fluid density 1000, all
+# boundaries no-flow Neumann, initial band 0.4 <= y <= 0.6 with X = 1e-9 * M_tracer / M_fluid (0.3 / 18), dt = 1e4 s to 1e6 s.
+# The test carries two decoupled components: D = 1e-8 (Problem.D) for the first, D2 = 0 (pure advection) for the second; one
+# spec describes one of them (`D`).
+# ------------------------------------------------------------------------------------------------------
+def tracer_constvel(cells=(50, 50), dt=1.0e4, implicit=False, D=0.0) -> ProblemSpec:
+    dim = 2
+    lower, upper = (0.0, 0.0), (1.0, 1.0)
+    n = int(np.prod(cells))
+    ctr = cell_centers(cells, lower, upper)
+    xn = node_coords(cells, lower, upper)
+    hx, hy = np.diff(xn[0]), np.diff(xn[1])
+    i = np.arange(n) % cells[0]
+    j = np.arange(n) // cells[0]
+
+    def vel(x, y):
+        vx = 1e-5 * (x * x * (1.0 - x) * (1.0 - x) * (2.0 * y - 6.0 * y * y + 4.0 * y * y * y))
+        vy = 1e-5 * (-1.0 * y * y * (1.0 - y) * (1.0 - y) * (2.0 * x - 6.0 * x * x + 4.0 * x * x * x))
+        return vx, vy
+
+    vf = np.zeros((n, 4))
+    yc, xc = ctr[:, 1], ctr[:, 0]
+    vf[:, 0] = -vel(xn[0][i], yc)[0] * hy[j]            # -x face: outer normal (-1, 0), area = hy
+    vf[:, 1] = vel(xn[0][i + 1], yc)[0] * hy[j]
+    vf[:, 2] = -vel(xc, xn[1][j])[1] * hx[i]
+    vf[:, 3] = vel(xc, xn[1][j + 1])[1] * hx[i]
+    bc_type, bc_values = {}, {}
+    for side in range(4):
+        nf = cells[1] if side < 2 else cells[0]
+        bc_type[side] = np.full(nf, BC_NEUMANN, dtype=np.int32)
+        bc_values[side] = np.zeros((nf, 1))
+    init = np.zeros((n, 1))
+    band = (ctr[:, 1] > 0.4 - 1e-6) & (ctr[:, 1] < 0.6 + 1e-6)
+    init[band, 0] = 1e-9 * 0.300 / 18.0
+    return ProblemSpec(
+        name="tracer_constvel", model=MODEL_TRACER, dim=dim, cells=tuple(cells), lower=lower, upper=upper,
+        K=np.ones(n), phi=np.full(n, 0.2), region=np.zeros(n, dtype=np.int32), materials=[],
+        rho=(1000.0,), mu=(1e-3,), bc_type=bc_type, bc_values=bc_values,
+        options=Options(stationary=False, dt=dt, enable_gravity=False), initial=init, volume_flux=vf, implicit=implicit,
+        tracer_diffusion=(D, 0.5))

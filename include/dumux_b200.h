@@ -148,6 +148,10 @@ int  dmx_set_volume_flux(dmx_ctx* ctx, const double* volume_flux);
    Fluid density = density[0] of dmx_set_fluids, porosity from dmx_set_cell_fields, dt / extrusion / upwind weight from
    dmx_options.  dmx_assemble / dmx_newton_step then run TracerLocalResidual (porousmediumflow/tracer/localresidual.hh). */
 int  dmx_set_tracer(dmx_ctx* ctx, int implicit);
+/* tracer ctx: Fick's law (flux/cctpfa/fickslaw.hh) with DiffusivityConstantTortuosity (material/fluidmatrixinteractions/
+   diffusivityconstanttortuosity.hh:55-63): D = FluidSystem::binaryDiffusionCoefficient (constant), tortuosity =
+   SpatialParams.Tortuosity (default 0.5); mass fractions, mass-averaged reference system.  D = 0 (default): no diffusion. */
+int  dmx_set_tracer_diffusion(dmx_ctx* ctx, double D, double tortuosity);
 int  dmx_side_faces(const dmx_ctx* ctx, int side);
 int  dmx_set_boundary(dmx_ctx* ctx, int side, const int* type, const double* values);
 

@@ -339,6 +339,7 @@ struct orc_problem {
     std::vector<double> bcVal[6];
     std::vector<int> rowptr, colidx;
     int linearSolver = ORC_SOLVER_BICGSTAB, gmresRestart = 10;   // orc_set_linear_solver
+    double tracerD = 0.0, tracerTau = 0.5;     // binary diffusion coefficient of the tracer and SpatialParams.Tortuosity
     bool volumeFluxMode = false;               // upwind term = mobility only (examples/1ptracer/main.cc:170)
 
     // ---- grid geometry: YaspGrid equidistant / tensor coordinates, AxisAlignedCubeGeometry [DUNE-ext] ----
@@ -1494,6 +1495,11 @@ void orc_ssor_apply(int n, int b, const int* rowptr, const int* colidx, const do
     std::fill(v, v + (size_t)n * b, 0.0);
     ssorApply(n, b, rowptr, colidx, values, v, d);
 }
+void orc_set_tracer_diffusion(orc_problem* p, double D, double tortuosity)
+{
+    p->tracerD = D;
+    p->tracerTau = tortuosity;
+}
 void orc_set_linear_solver(orc_problem* p, int kind, int restart)
 {
     p->linearSolver = kind;
@@ -1774,15 +1780,26 @@ void orc_tracer_assemble(orc_problem* p, const double* vf, const double* cur, co
                 double mult;
                 if (std::signbit(vflux)) mult = w * upOut + (1.0 - w) * upIn;
                 else mult = w * upIn + (1.0 - w) * upOut;
+                // Fick's law, TPFA (flux/cctpfa/fickslaw.hh:120-175 flux_, :177-230 calculateTransmissibility) with
+                // DiffusivityConstantTortuosity (diffusivityconstanttortuosity.hh:55-63): D_eff = porosity * S * tau * D, S = 1;
+                // mass-averaged reference system with mass fractions: flux = rho_avg * tij * (X_I - X_J)
+                int cJ[3];
+                p->ijk(J, cJ);
+                const double porosityJ = 1.0 - (1.0 - p->phi[J]);
+                const double DeffI = porosity * 1.0 * p->tracerTau * p->tracerD;
+                const double DeffJ = porosityJ * 1.0 * p->tracerTau * p->tracerD;
+                const double dTij = p->advectionTij(cI, side, DeffI, extr, false, cJ, DeffJ, extr);
+                const double rhoAvg = 0.5 * (rho + rho);
                 double flux = 0.0;
                 flux += vflux * mult;
-                flux += 0.0;       // diffusive flux, D = 0 (examples/1ptracer/properties_tracer.hh binaryDiffusionCoefficient)
+                flux += rhoAvg * dTij * (X[I] - X[J]);
                 res += flux;
                 if (jac && implicit) {
                     const double insideWeight = std::signbit(vflux) ? (1.0 - w) : w;
                     const double outsideWeight = 1.0 - insideWeight;
-                    diag += vflux * rho * insideWeight;
-                    jac[pos(J)] += vflux * rho * outsideWeight;
+                    const double diffDeriv = rhoAvg * dTij;           // tracer/localresidual.hh:268-291
+                    diag += (vflux * rho * insideWeight + diffDeriv);
+                    jac[pos(J)] += (vflux * rho * outsideWeight - diffDeriv);
                 }
             } else {
                 const int fidx = p->sideFaceIndex(side, cI);

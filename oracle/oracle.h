@@ -90,6 +90,9 @@ int  orc_ssor_solve(int n, int b, const int* rowptr, const int* colidx, const do
                     double reduction, int maxit, int* iterations, double* achieved_reduction);
 /* v = SeqSSOR(A)(d) from v = 0 (one forward + one backward block Gauss-Seidel sweep) */
 void orc_ssor_apply(int n, int b, const int* rowptr, const int* colidx, const double* values, double* v, const double* d);
+/* tracer: binary diffusion coefficient D (FluidSystem::binaryDiffusionCoefficient) and SpatialParams.Tortuosity (default 0.5) of
+   DiffusivityConstantTortuosity; D = 0 (the default) switches Fick's law off */
+void orc_set_tracer_diffusion(orc_problem* p, double D, double tortuosity);
 /* linear solver used by orc_newton_solve(_ex) / orc_run_timeloop: ORC_SOLVER_*; restart <= 0: 10 (LinearSolver.GMResRestart) */
 void orc_set_linear_solver(orc_problem* p, int kind, int restart);
 /* standalone pieces for kernel-level parity */

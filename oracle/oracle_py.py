@@ -88,6 +88,7 @@ def lib():
                                      C.POINTER(C.c_int), C.POINTER(C.c_double)]
         L.orc_ilu0_gmres.restype = C.c_int
         L.orc_set_linear_solver.argtypes = [vp, C.c_int, C.c_int]
+        L.orc_set_tracer_diffusion.argtypes = [vp, C.c_double, C.c_double]
         L.orc_ssor_solve.argtypes = [C.c_int, C.c_int, _ip, _ip, _dp, _dp, _dp, C.c_int, C.c_double, C.c_int,
                                      C.POINTER(C.c_int), C.POINTER(C.c_double)]
         L.orc_ssor_solve.restype = C.c_int
@@ -161,6 +162,8 @@ class Oracle:
             L.orc_set_material(self.h, r, m.law, np.ascontiguousarray(m.params, dtype=np.float64), m.swr, m.snr,
                                int(m.regularize), reg)
             L.orc_set_wetting_phase(self.h, r, int(m.wetting))
+        if spec.model == 3:
+            L.orc_set_tracer_diffusion(self.h, float(spec.tracer_diffusion[0]), float(spec.tracer_diffusion[1]))
         if spec.fluid_table is not None:
             t = spec.fluid_table
             L.orc_set_fluid_table(self.h, t["nT"], t["nP"], t["Tmin"], t["Tmax"],

@@ -5,6 +5,7 @@ Source files (reference tree, test/references/):
   test_1p_cc-reference.vtu                    1p incompressible/compressible CCTpfa, 10x10   (field p)
   test_2p_incompressible_cc-reference.vtu     2p lens, 48x32, t = 3000 s                      (10 fields)
   test_2p_incompressible_tpfa_oilwet-reference.vtu  2p, oil-wet lens, no gravity, 9th output file    (10 fields)
+  test_tracer_{explicit,implicit}_tpfa-reference.vtu  tracer/constvel, 50x50, t = 1e6 s (output 10), two components (D = 1e-8, 0)
   test_1ptracer_pressure-reference.vtu        1p on log-normal K, 50x50                       (p, permeability)
   test_1ptracer_transport-reference.vtu       tracer after 5000 s                             (x, X, rho, velocity)
 All are Float32 ASCII cell data in element (x-fastest) order; the reference's own comparison is
@@ -24,6 +25,8 @@ FILES = {
     "test_1p_cc": "test/references/test_1p_cc-reference.vtu",
     "test_2p_incompressible_cc": "test/references/test_2p_incompressible_cc-reference.vtu",
     "test_2p_incompressible_tpfa_oilwet": "test/references/test_2p_incompressible_tpfa_oilwet-reference.vtu",
+    "test_tracer_explicit_tpfa": "test/references/test_tracer_explicit_tpfa-reference.vtu",
+    "test_tracer_implicit_tpfa": "test/references/test_tracer_implicit_tpfa-reference.vtu",
     "test_1ptracer_pressure": "test/references/test_1ptracer_pressure-reference.vtu",
     "test_1ptracer_transport": "test/references/test_1ptracer_transport-reference.vtu",
 }

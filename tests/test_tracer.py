@@ -71,6 +71,72 @@ def test_oracle_implicit_tracer_is_consistent_with_its_jacobian():
     assert np.abs((r1 - r0) - Jd).max() <= 1e-12 * np.abs(Jd).max()
 
 
+CONSTVEL = [(False, "test_tracer_explicit_tpfa", 1e-8, "X_tracer_0"), (False, "test_tracer_explicit_tpfa", 0.0, "X_tracer_1"),
+            (True, "test_tracer_implicit_tpfa", 1e-8, "X_tracer_0"), (True, "test_tracer_implicit_tpfa", 0.0, "X_tracer_1")]
+
+
+@pytest.mark.parametrize("implicit,golden,D,field", CONSTVEL)
+def test_oracle_constvel_tracer_matches_reference_vtu(implicit, golden, D, field):
+    """test/porousmediumflow/tracer/constvel (test_tracer_explicit_tpfa / test_tracer_implicit_tpfa): 100 steps of 1e4 s on the
+    analytic divergence-free velocity field.  The files hold two decoupled components: Problem.D = 1e-8 (Fick's law with
+    DiffusivityConstantTortuosity, flux/cctpfa/fickslaw.hh) and D2 = 0 (pure advection); both must be reproduced by the explicit
+    AND the implicit TracerLocalResidual restatement (the implicit assembler and Fick's law have no other golden).  Mass is
+    conserved (all boundaries no-flow)."""
+    ts = problems.tracer_constvel((50, 50), implicit=implicit, D=D)
+    assert np.abs(ts.volume_flux.sum(axis=1)).max() <= 1e-4 * np.abs(ts.volume_flux).max()      # discretely divergence-free
+    o = Oracle(ts)
+    x = ts.initial.ravel().copy()
+    for _ in range(100):
+        r, j = o.assemble(x, x)
+        dx, st, its, red = o.solve(j, r, reduction=1e-13, maxit=500)
+        assert st == 0
+        x = x - dx
+    g = np.load(os.path.join(GOLDEN, golden + ".npz"))
+    X = g[field].astype(np.float64)
+    assert np.abs(x - X).max() <= 1e-5 * X.max() and np.linalg.norm(x - X) <= 5e-6 * np.linalg.norm(X)
+    assert x.sum() == pytest.approx(ts.initial.sum(), rel=1e-11)
+    # diffusion matters: the two components of the file differ visibly
+    assert np.abs(g["X_tracer_0"] - g["X_tracer_1"]).max() > 0.1 * g["X_tracer_1"].max()
+
+
+def test_oracle_fick_jacobian_is_the_derivative_of_the_implicit_residual():
+    ts = problems.tracer_constvel((12, 9), implicit=True, D=3e-7)
+    o = Oracle(ts)
+    rng = np.random.RandomState(2)
+    cur, prev = rng.uniform(0, 2e-11, size=(108, 1)), rng.uniform(0, 2e-11, size=(108, 1))
+    r0, j = o.assemble(cur, prev)
+    import scipy.sparse as sp
+    A = sp.csr_matrix((j, o.colidx, o.rowptr), shape=(108, 108))
+    d = rng.uniform(-1e-12, 1e-12, size=(108, 1))
+    r1, _ = o.assemble(cur + d, prev, jacobian=False)
+    assert np.linalg.norm((r1 - r0) - A @ d.ravel()) <= 1e-9 * np.linalg.norm(A @ d.ravel())      # the residual is linear in X
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("implicit,golden,D,field", CONSTVEL)
+def test_gpu_constvel_tracer_matches_reference_vtu(engine_factory, implicit, golden, D, field):
+    """The same 100 steps on the device (state resident; explicit steps take the diagonal fast path of the ILU0 factorisation),
+    and the assembly with Fick's law bit-identical to the oracle."""
+    from dumux_b200 import binding as B
+    ts = problems.tracer_constvel((50, 50), implicit=implicit, D=D)
+    rng = np.random.RandomState(8)
+    cur, prev = rng.uniform(0, 2e-11, size=(2500, 1)), rng.uniform(0, 2e-11, size=(2500, 1))
+    ro, jo = Oracle(ts).assemble(cur, prev)
+    et = engine_factory(ts)
+    rg, jg = et.assemble(cur, prev)
+    assert np.array_equal(rg, ro) and np.array_equal(jg, jo)
+    et.upload(B.VEC_CUR, ts.initial)
+    et.upload(B.VEC_PREV, ts.initial)
+    prm = et.newton_params(lin_reduction=1e-13, lin_maxit=500)
+    for _ in range(100):
+        st, its, shift, a, s, upd = et.newton_step(prm)
+        assert st == 0
+        et.advance_timestep()
+    x = et.download(B.VEC_CUR).ravel()
+    X = np.load(os.path.join(GOLDEN, golden + ".npz"))[field].astype(np.float64)
+    assert np.abs(x - X).max() <= 1e-5 * X.max() and np.linalg.norm(x - X) <= 5e-6 * np.linalg.norm(X)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("cells", [(50, 50), (21, 13, 17)])
 def test_gpu_volume_flux_bit_identical(engine_factory, cells):
