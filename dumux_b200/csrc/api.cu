@@ -28,6 +28,9 @@ int alloc_vectors(dmx_ctx* ctx)
     if (ctx->d_J) cudaFree(ctx->d_J);
     if (ctx->d_ilu) { cudaFree(ctx->d_ilu); ctx->d_ilu = nullptr; }
     if (ctx->d_dinv) { cudaFree(ctx->d_dinv); ctx->d_dinv = nullptr; }
+    if (ctx->d_gm) { cudaFree(ctx->d_gm); ctx->d_gm = nullptr; ctx->gm_vectors = 0; }      // sized by the old vector length
+    ctx->ilu_valid = false;
+    ctx->jac_diagonal = false;
     DMX_CUDA(cudaMalloc((void**)&ctx->d_J, (size_t)ctx->nnzb * ctx->b * ctx->b * sizeof(double)));
     DMX_CUDA(cudaMemset(ctx->d_J, 0, (size_t)ctx->nnzb * ctx->b * ctx->b * sizeof(double)));
     return 0;
