@@ -965,7 +965,6 @@ static void gm_apply_rotation(double& dx, double& dy, double cs, double sn)
 
 int gmres(dmx_ctx* ctx, double reduction, int maxit, int restart, int precond, int* iterations, double* achieved)
 {
-    if (ctx->nranks > 1) return fail(ctx, DMX_ERR_USAGE, "restarted GMRes runs on a single domain in this version (use BiCGSTAB for slab-decomposed runs)");
     const size_t len = (size_t)ctx->n * ctx->b;
     const int m = restart > 0 ? restart : 10;
     if (!ctx->d_gm || ctx->gm_vectors < m + 3) {
@@ -1007,6 +1006,11 @@ int gmres(dmx_ctx* ctx, double reduction, int maxit, int restart, int precond, i
         *nrm = std::sqrt(s2);
         return 0;
     };
+    // slab-decomposed context: the same overlapping-Schwarz pieces as bicgstab() -- operator = local SpMV + project (launch_spmv),
+    // preconditioner = local ILU0 + copyOwnerToAll (precond_apply), scalar product = owner-masked dot + all-reduce (dot_kernel,
+    // final reduction + allreduce_sum below); the basis vectors stay consistent on the overlap because every one of them is a
+    // linear combination of preconditioner outputs
+    if (ctx->nranks > 1 && (rc = halo_exchange(ctx, x))) return rc;       // BlockPreconditioner::pre: copyOwnerToAll(x)
     double norm;
     if ((rc = defect(&norm))) return rc;
     const double norm0 = norm;
@@ -1042,6 +1046,7 @@ int gmres(dmx_ctx* ctx, double reduction, int maxit, int restart, int precond, i
                     DMX_CHECK_LAUNCH();
                     final_reduce_kernel<false><<<1, RED_THREADS, 0, ctx->stream>>>(RED_BLOCKS, 1, ctx->d_partials, d_h + k);
                     DMX_CHECK_LAUNCH();
+                    if (ctx->nranks > 1 && (rc = allreduce_sum(ctx, d_h + k, 1))) return rc;
                     gm_axpy_neg_dev_kernel<<<RED_BLOCKS, 256, 0, ctx->stream>>>(len, d_h + k, V(k), w);
                     DMX_CHECK_LAUNCH();
                 }
@@ -1050,6 +1055,7 @@ int gmres(dmx_ctx* ctx, double reduction, int maxit, int restart, int precond, i
                 DMX_CHECK_LAUNCH();
                 final_reduce_kernel<false><<<1, RED_THREADS, 0, ctx->stream>>>(RED_BLOCKS, 1, ctx->d_partials, d_h + i + 1);
                 DMX_CHECK_LAUNCH();
+                if (ctx->nranks > 1 && (rc = allreduce_sum(ctx, d_h + i + 1, 1))) return rc;
             }
             DMX_CUDA(cudaMemcpyAsync(h_h.data(), d_h, (size_t)(i + 2) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
             DMX_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -228,6 +228,98 @@ class SlabRank:
             it += 0.5
         return x, status, int(math.ceil(min(it, maxit))), (norm / norm0 if norm0 > 0 else 0.0)
 
+    def gmres(self, jac, rhs, reduction=1e-6, maxit=250, restart=10):
+        """Dune::RestartedGMResSolver::apply (left preconditioned, see oracle.cpp restartedGmres) with the overlapping-Schwarz
+        operator / scalar product / BlockPreconditioner; x0 = 0.  Returns (x, status, iterations, achieved reduction)."""
+        ilu, st = O.ilu0_factor(self.n, self.b, self.o.rowptr, self.o.colidx, jac)
+        st = int(self.comm.allreduce(float(st), "max"))
+        if st != 0:
+            return np.zeros_like(rhs), 2, 0, 1.0
+
+        def prec(d):
+            v = O.ilu0_apply(self.n, self.b, self.o.rowptr, self.o.colidx, ilu, d)
+            self.copy_owner_to_all(v)
+            return v
+
+        def rotation(dx, dy):
+            eps = 1e-15
+            ndx, ndy = abs(dx), abs(dy)
+            if ndy < eps:
+                return 1.0, 0.0
+            if ndx < eps:
+                return 0.0, 1.0
+            temp = min(ndx, ndy) / max(ndx, ndy)
+            if ndy > ndx:
+                return 1.0 / math.sqrt(1.0 + temp * temp) * temp, 1.0 / math.sqrt(1.0 + temp * temp) * dx * dy / ndx / ndy
+            return 1.0 / math.sqrt(1.0 + temp * temp), 1.0 / math.sqrt(1.0 + temp * temp) * dy / dx
+
+        m = restart
+        x = np.zeros_like(rhs)
+        self.copy_owner_to_all(x)                                    # BlockPreconditioner::pre
+
+        def defect():
+            b = rhs - O.spmv(self.n, self.b, self.o.rowptr, self.o.colidx, jac, x)
+            b[~self.owner] = 0.0                                     # applyscaleadd projects
+            v0 = prec(b)
+            return v0, math.sqrt(self.dot(v0, v0))
+
+        v = [None] * (m + 1)
+        v[0], norm = defect()
+        norm0 = norm
+        if not math.isfinite(norm0):
+            return x, 3, 0, 1.0
+        conv = lambda nrm: nrm < reduction * norm0 or nrm < 1e-30
+        if conv(norm0):
+            return x, 0, 0, (1.0 if norm0 > 0 else 0.0)
+        H = np.zeros((m + 1, m + 1))
+        cs, sn, s = np.zeros(m), np.zeros(m), np.zeros(m + 1)
+        j, converged, status, its = 1, False, 1, 0
+        while j <= maxit and not converged:
+            v[0] = v[0] * (0.0 if norm == 0.0 else 1.0 / norm)
+            s[:] = 0.0
+            s[0] = norm
+            i = 0
+            while i < m and j <= maxit and not converged:
+                w = prec(self.apply_operator(jac, v[i]))
+                for k in range(i + 1):
+                    H[k, i] = self.dot(v[k], w)
+                    w = w + (-H[k, i]) * v[k]
+                H[i + 1, i] = math.sqrt(self.dot(w, w))
+                its = j
+                if not math.isfinite(H[i + 1, i]):
+                    return x, 3, its, 1.0
+                if abs(H[i + 1, i]) < 1e-80:
+                    return x, 2, its, norm / norm0
+                v[i + 1] = w * (0.0 if norm == 0.0 else 1.0 / H[i + 1, i])
+                for k in range(i):
+                    t = cs[k] * H[k, i] + sn[k] * H[k + 1, i]
+                    H[k + 1, i] = -sn[k] * H[k, i] + cs[k] * H[k + 1, i]
+                    H[k, i] = t
+                cs[i], sn[i] = rotation(H[i, i], H[i + 1, i])
+                t = cs[i] * H[i, i] + sn[i] * H[i + 1, i]
+                H[i + 1, i] = -sn[i] * H[i, i] + cs[i] * H[i + 1, i]
+                H[i, i] = t
+                t = cs[i] * s[i] + sn[i] * s[i + 1]
+                s[i + 1] = -sn[i] * s[i] + cs[i] * s[i + 1]
+                s[i] = t
+                norm = abs(s[i + 1])
+                if conv(norm):
+                    converged, status = True, 0
+                i += 1
+                j += 1
+            y = s.copy()
+            w = np.zeros_like(rhs)
+            for a in range(i - 1, -1, -1):
+                r = s[a]
+                for c in range(a + 1, i):
+                    r -= H[a, c] * y[c]
+                y[a] = 0.0 if r == 0.0 else r / H[a, a]
+                w = w + y[a] * v[a]
+            x = x + w
+            if not converged and j < maxit:
+                v[0], norm = defect()
+        return x, status, its, (norm / norm0 if norm0 > 0 else 0.0)
+
     def newton(self, u0, prev, lin_reduction=1e-6, lin_maxit=250, max_rel_shift=1e-8, min_steps=2, max_steps=18):
         """NewtonSolver::solveImpl_ (nonlinear/newtonsolver.hh:976-1072) on the local slab; u0/prev are LOCAL arrays."""
         u = np.ascontiguousarray(u0, dtype=np.float64).reshape(-1).copy()

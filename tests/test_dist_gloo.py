@@ -46,9 +46,10 @@ def _rank_job(rank_obj):
     prev = rank_obj.spec.initial.reshape(-1)
     res, jac = rank_obj.o.assemble(cur, prev)
     x, st, its, red = rank_obj.bicgstab(jac, res, reduction=1e-11, maxit=500)
+    xg, stg, itsg, redg = rank_obj.gmres(jac, res, reduction=1e-11, maxit=500, restart=10)
     u, nst, nsteps, lin_its = rank_obj.newton(rank_obj.spec.initial, rank_obj.spec.initial)
     return {"x": x, "st": st, "its": its, "red": red, "res": res, "u": u, "nst": nst, "nsteps": nsteps, "lin_its": lin_its,
-            "owner": rank_obj.owner.copy()}
+            "owner": rank_obj.owner.copy(), "xg": xg, "stg": stg, "itsg": itsg, "redg": redg, "jac": jac}
 
 
 def _gloo_worker(rank, world, port, q):
@@ -115,6 +116,28 @@ def test_schwarz_bicgstab_converges_to_single_domain_solution(reference_runs, P)
 
 
 @pytest.mark.parametrize("P", [2, 3])
+def test_schwarz_gmres_converges_to_single_domain_solution(reference_runs, P):
+    """ILURestartedGMResIstlSolver on the overlapping decomposition: the single-rank run equals the sequential C++ restatement, the
+    P-rank runs converge to the same global solution with overlap copies consistent."""
+    single, two, three = reference_runs
+    runs = two if P == 2 else three
+    assert single["stg"] == 0 and all(o["stg"] == 0 for o in runs)
+    o1 = O.Oracle(_make_spec(None))
+    xs, sts, itss, reds = o1.solve_gmres(single["jac"], single["res"], reduction=1e-11, maxit=500, restart=10)
+    assert sts == 0 and itss == single["itsg"] and np.linalg.norm(xs - single["xg"]) <= 1e-12 * np.linalg.norm(xs)
+    x = D.gather_owned([o["xg"] for o in runs], CELLS, P, 2)
+    assert np.linalg.norm(x - single["x"]) <= 1e-7 * np.linalg.norm(single["x"])
+    assert len({o["itsg"] for o in runs}) == 1 and runs[0]["itsg"] >= single["itsg"]
+    nf = CELLS[0] * CELLS[1] * 2
+    for r in range(P - 1):
+        lo0, hi0, b00, b10 = problems.slab_partition(CELLS[2], P, r)
+        lo1, hi1, b01, b11 = problems.slab_partition(CELLS[2], P, r + 1)
+        a = runs[r]["xg"].reshape(hi0 - lo0, nf)
+        b = runs[r + 1]["xg"].reshape(hi1 - lo1, nf)
+        assert np.allclose(a[b10 - lo0], b[b10 - lo1], rtol=1e-12, atol=0) and np.allclose(a[b10 - 1 - lo0], b[b10 - 1 - lo1], rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("P", [2, 3])
 def test_newton_iteration_count_independent_of_partition(reference_runs, P):
     """north_star: same Newton iteration count, fields to 1e-8 relative L2 (BiCGSTAB counts may depend on P)."""
     single, two, three = reference_runs
@@ -144,5 +167,6 @@ def test_two_processes_over_gloo_match_reference(reference_runs):
     for r in range(2):
         assert got[r]["st"] == 0 and got[r]["its"] == two[r]["its"]
         assert np.array_equal(got[r]["x"], two[r]["x"])
+        assert got[r]["stg"] == 0 and got[r]["itsg"] == two[r]["itsg"] and np.array_equal(got[r]["xg"], two[r]["xg"])
         assert got[r]["nsteps"] == two[r]["nsteps"] and got[r]["lin_its"] == two[r]["lin_its"]
         assert np.array_equal(got[r]["u"], two[r]["u"])

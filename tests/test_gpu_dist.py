@@ -42,8 +42,10 @@ def _cpu_rank_job(rank_obj):
     prev = rank_obj.spec.initial.reshape(-1)
     res, jac = rank_obj.o.assemble(cur, prev)
     x, st, its, red = rank_obj.bicgstab(jac, res, reduction=1e-10, maxit=500)
+    xg, stg, itsg, redg = rank_obj.gmres(jac, res, reduction=1e-10, maxit=500, restart=10)
     u, nst, nsteps, lin_its = rank_obj.newton(rank_obj.spec.initial, rank_obj.spec.initial)
-    return {"res": res, "jac": jac, "x": x, "st": st, "its": its, "u": u, "nst": nst, "nsteps": nsteps, "lin_its": lin_its}
+    return {"res": res, "jac": jac, "x": x, "st": st, "its": its, "u": u, "nst": nst, "nsteps": nsteps, "lin_its": lin_its,
+            "xg": xg, "stg": stg, "itsg": itsg, "redg": redg}
 
 
 def _gpu_worker(rank, world, uid, q):
@@ -57,6 +59,9 @@ def _gpu_worker(rank, world, uid, q):
         cur = _perturb(spec, (lo, hi))
         res, jac = eng.assemble(cur, spec.initial)
         x, st, its, red = eng.solve(jac, res, reduction=1e-10, maxit=500)
+        eng.set_linear_solver("gmres", 10)
+        xg, stg, itsg, redg = eng.solve(jac, res, reduction=1e-10, maxit=500)
+        eng.set_linear_solver("bicgstab")
         # halo exchange primitive: fill a vector with the rank id, exchange, look at the overlap planes
         v = np.full(eng.n * eng.b, float(rank))
         eng.upload(B.VEC_WORK1, v)
@@ -66,7 +71,7 @@ def _gpu_worker(rank, world, uid, q):
         u, nst, rep = eng.newton(spec.initial, spec.initial)
         q.put((rank, {"res": res, "jac": jac, "x": x, "st": st, "its": its, "halo": halo, "norm": nrm, "u": u, "nst": nst,
                       "nsteps": rep.newton_iterations, "lin_its": [rep.linear_iterations[i] for i in range(rep.newton_iterations)],
-                      "launches": eng.launches()}))
+                      "launches": eng.launches(), "xg": xg, "stg": stg, "itsg": itsg, "redg": redg}))
         eng.close()
     except BaseException as e:      # noqa: BLE001
         import traceback
@@ -113,6 +118,11 @@ def test_slab_decomposed_newton_step_matches_cpu_reference(world):
         # Schwarz-BiCGSTAB: same iteration count, solution at the solver tolerance
         assert g["st"] == 0 and c["st"] == 0 and g["its"] == c["its"], (g["its"], c["its"])
         assert np.linalg.norm(g["x"] - c["x"]) <= 1e-7 * np.linalg.norm(c["x"])
+        # Schwarz-GMRes(10) (ILURestartedGMResIstlSolver on the overlapping decomposition): same count, reduction and solution
+        assert g["stg"] == 0 and c["stg"] == 0 and g["itsg"] == c["itsg"], (g["itsg"], c["itsg"])
+        assert g["redg"] == pytest.approx(c["redg"], rel=1e-5)
+        assert np.linalg.norm(g["xg"] - c["xg"]) <= 1e-7 * np.linalg.norm(c["xg"])
+        assert np.linalg.norm(g["xg"] - g["x"]) <= 1e-6 * np.linalg.norm(g["x"])          # both solve the same global system
         # Newton: same iteration count, fields to 1e-8
         assert g["nst"] == 0 and g["nsteps"] == c["nsteps"]
         ug, uc = g["u"].reshape(-1, 2), c["u"].reshape(-1, 2)
