@@ -10,7 +10,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O
 for s in $STEPS; do
   case $s in
     tests) timeout 1500 python -m pytest tests -m gpu -x -q > $OUT/tests.log 2>&1; echo "tests exit $?" >> $OUT/tests.log; tail -5 $OUT/tests.log;;
-    probe) timeout 600 python scripts/gpu_probe.py 256 > $OUT/probe_tile.log 2>&1; tail -25 $OUT/probe_tile.log
+    probe) timeout 600 python tests/tools/gpu_probe.py 256 > $OUT/probe_tile.log 2>&1; tail -25 $OUT/probe_tile.log
            DMX_ASM_LEGACY=1 timeout 600 python scripts/ilu_probe.py 256 5 > $OUT/probe_legacy.log 2>&1; tail -5 $OUT/probe_legacy.log;;
     list)  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv \
              python scripts/profile_step.py 256 6 > $OUT/list.log 2>&1; tail -2 $OUT/list.log;;

@@ -1,6 +1,6 @@
 """Development probe (not a test): prints parity error magnitudes and kernel timings on the GPU box."""
 import sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from dumux_b200 import problems
 from dumux_b200 import binding as B
