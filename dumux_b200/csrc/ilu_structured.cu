@@ -384,8 +384,12 @@ __global__ void __launch_bounds__(SK_THREADS) vec_skew_kernel(SkewGrid g, const 
 #ifndef SK_BATCH
 #define SK_BATCH 2       // measured at 256^3: 2 -> 1.39 ms per apply, 4 -> 1.42, 8 -> 1.57
 #endif
-constexpr int SK_R = SK_RING;                // halo ring depth in steps
-constexpr int SK_NB = SK_BATCH;              // steps whose halo words the sync warp requests together
+// halo ring depth in steps / steps whose halo words the sync warp requests together.  1x1 blocks move four times less data per
+// step, their sweeps are pure latency: a deeper ring with 4-step batches measured 0.924 -> 0.869 ms per application at 256^3
+template <int B> struct SkHalo {
+    static constexpr int R = (B == 1) ? 2 * SK_RING : SK_RING;
+    static constexpr int NB = (B == 1) ? 2 * SK_BATCH : SK_BATCH;
+};
 template <int B, bool UPPER>
 __global__ void __launch_bounds__(SK_THREADS + 64, SK_CTAS) ilu_sweep_kernel(SkewGrid g, const double* __restrict__ stream, double* out,
                                                                         unsigned long long* ll, unsigned int tag,
@@ -395,6 +399,7 @@ __global__ void __launch_bounds__(SK_THREADS + 64, SK_CTAS) ilu_sweep_kernel(Ske
     using LY = SkewLayout<B, UPPER>;
     using LYU = SkewLayout<B, true>;
     constexpr int S = LY::S;
+    constexpr int SK_R = SkHalo<B>::R, SK_NB = SkHalo<B>::NB;
     // LOWER: results go to the vector slots of the upper stream (step stride STEP_U, offset FAC_U)
     constexpr size_t OUT_STEP = (size_t)LYU::STEP_DOUBLES;
     constexpr size_t OUT_OFF = (size_t)LYU::STAGE_DOUBLES;
@@ -694,6 +699,7 @@ static int sweep_launch_ll(dmx_ctx* ctx, SkewState* st, const double* stream, do
     using LY = SkewLayout<B, UPPER>;
     const SkewGrid& g = st->g;
     auto kern = ilu_sweep_kernel<B, UPPER>;
+    constexpr int SK_R = SkHalo<B>::R;
     const size_t smem = ((size_t)LY::S * LY::STEP_DOUBLES + 2 * (SK_TJ + 1) * (SK_TI + 1) * B + SK_R * (SK_TI + SK_TJ) * B) * sizeof(double) +
                         (2 * LY::S + 2 * SK_R) * sizeof(uint64_t);
     DMX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
