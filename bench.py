@@ -316,11 +316,14 @@ def run_b200(args):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     ab = algorithmic_bytes(n_local, eng.nnzb, b)
+    # DRAM traffic per launch from the committed `ncu --set full` capture (profiles/traffic.json), which was taken on the default
+    # 256^3 single-GPU workload: reported only when this run has that per-GPU size, null otherwise
     traffic = {}
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-    except Exception:
-        pass
+    if edge == 256 and n_local == 256 ** 3:
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        except Exception:
+            pass
     kernels = {}
     for name, (ms, units) in prof.items():
         if units == 0:
