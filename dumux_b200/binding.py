@@ -17,11 +17,12 @@ LIB_PATH = os.environ.get("DMX_LIB") or os.path.join(_HERE, "libdumux_b200.so") 
 VEC_CUR, VEC_PREV, VEC_RESIDUAL, VEC_DELTA, VEC_ULAST, VEC_WORK0, VEC_WORK1 = range(7)
 PRECOND_ILU0, PRECOND_BLOCKJACOBI = 0, 1
 STATUS_OK, STATUS_NOT_CONVERGED, STATUS_BREAKDOWN, STATUS_NONFINITE = 0, 1, 2, 3
-KERNEL_ASSEMBLY, KERNEL_SPMV, KERNEL_ILU_APPLY, KERNEL_ILU_FACTOR, KERNEL_VOLVARS = range(5)
+KERNEL_ASSEMBLY, KERNEL_SPMV, KERNEL_ILU_APPLY, KERNEL_ILU_FACTOR = range(4)
 
 EXPORTS = [
     "dmx_default_options", "dmx_default_newton_params", "dmx_create", "dmx_create_distributed", "dmx_get_nccl_unique_id",
     "dmx_destroy", "dmx_last_error", "dmx_version", "dmx_grid_structured", "dmx_grid_tensor", "dmx_local_box",
+    "dmx_local_box3", "dmx_set_partitioning",
     "dmx_num_cells", "dmx_num_eq", "dmx_nnz_blocks", "dmx_pattern", "dmx_bcrs_pattern", "dmx_set_options",
     "dmx_set_cell_fields", "dmx_set_source", "dmx_set_material", "dmx_set_fluids", "dmx_set_fluid_table",
     "dmx_side_faces", "dmx_set_boundary", "dmx_vec_upload", "dmx_vec_download", "dmx_vec_copy", "dmx_jacobian_upload",
@@ -35,7 +36,7 @@ EXPORTS = [
 ]
 SOLVER_BICGSTAB, SOLVER_RESTARTED_GMRES, SOLVER_CG = 0, 1, 2
 PRECOND_SSOR = 2
-K_ASSEMBLY, K_SPMV, K_ILU_APPLY, K_ILU_FACTOR, K_VOLVARS, K_BLAS1, K_HALO, K_JACOBI = range(8)
+K_ASSEMBLY, K_SPMV, K_ILU_APPLY, K_ILU_FACTOR, K_AMG, K_BLAS1, K_HALO, K_JACOBI = range(8)
 
 
 class DmxOptions(C.Structure):
@@ -90,6 +91,8 @@ def load_library():
     L.dmx_default_newton_params.argtypes = [C.POINTER(DmxNewtonParams)]
     L.dmx_grid_structured.argtypes = [vp, C.c_int, C.c_int, _ip, _dp, _dp]
     L.dmx_local_box.argtypes = [vp, _ip, _ip, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.dmx_local_box3.argtypes = [vp, _ip, _ip, _ip, _ip, _ip, _ip]
+    L.dmx_set_partitioning.argtypes = [vp, C.c_void_p]
     L.dmx_num_cells.argtypes = [vp]
     L.dmx_num_eq.argtypes = [vp]
     L.dmx_nnz_blocks.argtypes = [vp]
@@ -166,9 +169,10 @@ def _hostptr(a):
 
 class Engine:
     """One dmx_ctx (one GPU).  `spec` is a dumux_b200.problems.ProblemSpec describing the GLOBAL problem; in a
-    distributed engine (`nccl_uid`, `rank`, `nranks`) the per-rank slabs are cut out here."""
+    distributed engine (`nccl_uid`, `rank`, `nranks`) the per-rank blocks are cut out here.  `part` = Grid.Partitioning
+    (ranks per axis, product = nranks; default: slabs along the last axis)."""
 
-    def __init__(self, spec=None, device: int = 0, nccl_uid: bytes | None = None, rank: int = 0, nranks: int = 1):
+    def __init__(self, spec=None, device: int = 0, nccl_uid: bytes | None = None, rank: int = 0, nranks: int = 1, part=None):
         self.L = load_library()
         self.h = C.c_void_p()
         if nranks > 1:
@@ -179,6 +183,9 @@ class Engine:
         if rc != 0 or not self.h:
             raise DmxError(f"dmx_create failed with code {rc} (is a CUDA device visible? there is no CPU fallback)")
         self.rank, self.nranks = rank, nranks
+        if part is not None:
+            p3 = np.ascontiguousarray(list(part) + [1] * (3 - len(part)), dtype=np.int32)
+            self._check(self.L.dmx_set_partitioning(self.h, p3.ctypes.data_as(C.c_void_p)))
         self.spec = None
         self.n = self.b = 0
         self.opt = DmxOptions()
@@ -222,16 +229,14 @@ class Engine:
         self.n = L.dmx_num_cells(self.h)
         self.b = L.dmx_num_eq(self.h)
         self.nnzb = L.dmx_nnz_blocks(self.h)
-        lc = np.zeros(3, dtype=np.int32)
-        off = np.zeros(3, dtype=np.int32)
-        ob, oe = C.c_int(0), C.c_int(0)
-        L.dmx_local_box(self.h, lc, off, C.byref(ob), C.byref(oe))
-        self.local_cells, self.offset, self.own_begin, self.own_end = lc, off, ob.value, oe.value
-        if getattr(spec, "slab", None) is not None:
-            sa = spec.dim - 1
-            if (int(off[sa]), int(off[sa] + lc[sa])) != tuple(spec.slab):
-                raise DmxError(f"slab-local spec covers layers {spec.slab}, this rank holds "
-                               f"{(int(off[sa]), int(off[sa] + lc[sa]))}")
+        lc, off, ob, oe, pp, pc = (np.zeros(3, dtype=np.int32) for _ in range(6))
+        L.dmx_local_box3(self.h, lc, off, ob, oe, pp, pc)
+        self.local_cells, self.offset, self.own_lo, self.own_hi, self.part, self.coord = lc, off, ob, oe, pp, pc
+        self.own_begin, self.own_end = int(ob[spec.dim - 1]), int(oe[spec.dim - 1])      # slab view: the last axis
+        self.local_box = [(int(off[a]), int(off[a] + lc[a])) for a in range(spec.dim)]
+        sb = spec.local_box
+        if sb is not None and [tuple(x) for x in sb] != self.local_box:
+            raise DmxError(f"box-local spec covers {sb}, this rank holds {self.local_box}")
         o = spec.options
         self.opt.enable_gravity = int(o.enable_gravity)
         self.opt.gravity = o.gravity
@@ -270,36 +275,40 @@ class Engine:
             self._check(L.dmx_set_tracer(self.h, int(spec.implicit)))
             self._check(L.dmx_set_tracer_diffusion(self.h, float(spec.tracer_diffusion[0]), float(spec.tracer_diffusion[1])))
 
+    def owner_mask(self):
+        """bool[n]: cells this rank owns (interior partition), x fastest"""
+        m = np.ones((int(self.local_cells[2]), int(self.local_cells[1]), int(self.local_cells[0])), dtype=bool)
+        for a in range(3):
+            idx = np.arange(int(self.local_cells[a]))
+            ok = (idx >= self.own_lo[a]) & (idx < self.own_hi[a])
+            shp = [1, 1, 1]
+            shp[2 - a] = -1
+            m &= ok.reshape(shp)
+        return m.reshape(-1)
+
     def localize_cells(self, a):
-        """Cut the local slab (incl. overlap) out of a global per-cell array (x fastest)."""
+        """Cut the local box (incl. overlap) out of a global per-cell array (x fastest)."""
         a = np.asarray(a)
-        if self.nranks == 1 or getattr(self.spec, "slab", None) is not None:
+        if self.nranks == 1 or self.spec.local_box is not None:
             return np.ascontiguousarray(a)
         gc = self.spec.cells3
-        sa = self.spec.dim - 1
-        shape = (gc[2], gc[1], gc[0]) + a.shape[1:]
-        g = a.reshape(shape)
-        sl = [slice(None)] * 3
-        sl[2 - sa] = slice(int(self.offset[sa]), int(self.offset[sa] + self.local_cells[sa]))
-        loc = g[tuple(sl)]
-        return np.ascontiguousarray(loc.reshape((-1,) + a.shape[1:]))
+        g = a.reshape((gc[2], gc[1], gc[0]) + a.shape[1:])
+        sl = tuple(slice(int(self.offset[d]), int(self.offset[d] + self.local_cells[d])) for d in (2, 1, 0))
+        return np.ascontiguousarray(g[sl].reshape((-1,) + a.shape[1:]))
 
     def localize_side(self, side, t, v):
         t = np.asarray(t, dtype=np.int32)
         v = np.asarray(v, dtype=np.float64)
-        if self.nranks == 1 or getattr(self.spec, "slab", None) is not None:
+        if self.nranks == 1 or self.spec.local_box is not None:
             return np.ascontiguousarray(t), np.ascontiguousarray(v)
         gc = self.spec.cells3
-        sa = self.spec.dim - 1
         a = side // 2
-        if a == sa:   # faces normal to the split axis: the full plane (ignored by the library on processor boundaries)
-            return np.ascontiguousarray(t), np.ascontiguousarray(v)
-        # side plane axes: remaining axes ascending, lower fastest; the split axis is the slowest of them
+        # side plane axes: remaining axes ascending, lower fastest (ignored by the library on processor boundaries)
         rem = [d for d in range(3) if d != a]
         shape = (gc[rem[1]], gc[rem[0]])
-        lo, hi = int(self.offset[sa]), int(self.offset[sa] + self.local_cells[sa])
-        tt = t.reshape(shape)[lo:hi]
-        vv = v.reshape(shape + (v.shape[-1],))[lo:hi]
+        sl = tuple(slice(int(self.offset[d]), int(self.offset[d] + self.local_cells[d])) for d in (rem[1], rem[0]))
+        tt = t.reshape(shape)[sl]
+        vv = v.reshape(shape + (v.shape[-1],))[sl]
         return np.ascontiguousarray(tt.reshape(-1)), np.ascontiguousarray(vv.reshape(-1, v.shape[-1]))
 
     def set_bcrs_pattern(self, n, b, rowptr, colidx):

@@ -119,23 +119,34 @@ int finish_grid(dmx_ctx* ctx, int model, int dim, const int* cells, const std::v
     ctx->b = (model == DMX_MODEL_2P) ? 2 : 1;
     ctx->dim = dim;
     for (int a = 0; a < 3; ++a) { ctx->gcells[a] = (a < dim) ? cells[a] : 1; ctx->nc[a] = ctx->gcells[a]; ctx->off[a] = 0; }
-    ctx->split_axis = dim - 1;
-    // slab decomposition along the last axis, overlap 1 (Grid.Partitioning "1 .. P", Grid.Overlap 1)
-    const int sa = ctx->split_axis;
-    int lo = 0, hi = ctx->gcells[sa];
+    // Block decomposition with overlap 1 (Grid.Partitioning "px py pz" -> Dune::Yasp::FixedSizePartitioning, Grid.Overlap 1;
+    // io/grid/gridmanager_yasp.hh:129,194-203).  Default: slabs along the last axis ("1 .. P").  Rank -> torus coordinate with x
+    // fastest and, per axis, n/P cells for the first P - n%P processes and one more for the rest (dune-grid torus.hh
+    // Torus::rank_to_coord / Torus::partition) [DUNE-ext].
+    for (int a = 0; a < 3; ++a) { ctx->part[a] = 1; ctx->pcoord[a] = 0; ctx->own_lo[a] = 0; ctx->own_hi[a] = ctx->gcells[a]; }
     if (ctx->nranks > 1) {
-        const int N = ctx->gcells[sa], P = ctx->nranks, r = ctx->rank;
-        if (N < P) return fail(ctx, DMX_ERR_USAGE, "fewer cell layers than ranks along the split axis");
-        const int base = N / P, rem = N % P;
-        const int b0 = r * base + std::min(r, rem);
-        const int b1 = b0 + base + (r < rem ? 1 : 0);
-        lo = std::max(0, b0 - 1);
-        hi = std::min(N, b1 + 1);
-        ctx->own_begin = b0 - lo;
-        ctx->own_end = b1 - lo;
-    } else { ctx->own_begin = 0; ctx->own_end = hi; }
-    ctx->off[sa] = lo;
-    ctx->nc[sa] = hi - lo;
+        if (ctx->part_req[0] > 0) {
+            for (int a = 0; a < 3; ++a) ctx->part[a] = ctx->part_req[a];
+            for (int a = dim; a < 3; ++a)
+                if (ctx->part[a] != 1) return fail(ctx, DMX_ERR_USAGE, "Grid.Partitioning: more than one rank along an axis the grid does not have");
+        } else ctx->part[dim - 1] = ctx->nranks;
+        if (ctx->part[0] * ctx->part[1] * ctx->part[2] != ctx->nranks)
+            return fail(ctx, DMX_ERR_USAGE, "Grid.Partitioning: the product of the per-axis rank counts must equal the number of ranks");
+        int r = ctx->rank;
+        for (int a = 0; a < 3; ++a) { ctx->pcoord[a] = r % ctx->part[a]; r /= ctx->part[a]; }
+        for (int a = 0; a < 3; ++a) {
+            const int N = ctx->gcells[a], P = ctx->part[a], c = ctx->pcoord[a];
+            if (N < P) return fail(ctx, DMX_ERR_USAGE, "fewer cell layers than ranks along a partitioned axis");
+            const int m = N / P, rem = N % P;
+            const int b0 = (c < P - rem) ? c * m : (P - rem) * m + (c - (P - rem)) * (m + 1);
+            const int b1 = b0 + ((c < P - rem) ? m : m + 1);
+            const int lo = std::max(0, b0 - 1), hi = std::min(N, b1 + 1);
+            ctx->off[a] = lo;
+            ctx->nc[a] = hi - lo;
+            ctx->own_lo[a] = b0 - lo;
+            ctx->own_hi[a] = b1 - lo;
+        }
+    }
     for (int a = 0; a < 3; ++a) {
         ctx->xn[a].assign(gx[a].begin() + ctx->off[a], gx[a].begin() + ctx->off[a] + ctx->nc[a] + 1);
     }
@@ -146,12 +157,12 @@ int finish_grid(dmx_ctx* ctx, int model, int dim, const int* cells, const std::v
     ctx->h_phi.assign(ctx->n, 0.4);
     ctx->h_region.assign(ctx->n, 0);
     for (int s = 0; s < 6; ++s) { ctx->h_bc_type[s].clear(); ctx->h_bc_val[s].clear(); }
-    // processor boundaries: outer faces of overlap layers carry no scvf
-    if (ctx->nranks > 1) {
+    // processor boundaries: outer faces of overlap layers carry no scvf (tpfa/fvgridgeometry.hh:272-320)
+    for (int a = 0; a < 3 && ctx->nranks > 1; ++a) {
         int nf = 1;
-        for (int d = 0; d < 3; ++d) if (d != sa) nf *= ctx->nc[d];
-        if (lo > 0) { ctx->h_bc_type[2 * sa].assign(nf, DMX_BC_NONE); ctx->h_bc_val[2 * sa].assign((size_t)nf * ctx->b, 0.0); }
-        if (hi < ctx->gcells[sa]) { ctx->h_bc_type[2 * sa + 1].assign(nf, DMX_BC_NONE); ctx->h_bc_val[2 * sa + 1].assign((size_t)nf * ctx->b, 0.0); }
+        for (int d = 0; d < 3; ++d) if (d != a) nf *= ctx->nc[d];
+        if (ctx->off[a] > 0) { ctx->h_bc_type[2 * a].assign(nf, DMX_BC_NONE); ctx->h_bc_val[2 * a].assign((size_t)nf * ctx->b, 0.0); }
+        if (ctx->off[a] + ctx->nc[a] < ctx->gcells[a]) { ctx->h_bc_type[2 * a + 1].assign(nf, DMX_BC_NONE); ctx->h_bc_val[2 * a + 1].assign((size_t)nf * ctx->b, 0.0); }
     }
     build_grid_pattern(ctx);
     if (int rc = setup_geometry(ctx)) return rc;
@@ -177,19 +188,48 @@ int finish_grid(dmx_ctx* ctx, int model, int dim, const int* cells, const std::v
     }
     // owner mask (distributed): a cell is owner where it is interior (parallelhelpers.hh:485-497)
     if (ctx->d_owner) { cudaFree(ctx->d_owner); ctx->d_owner = nullptr; }
+    if (ctx->d_send) { cudaFree(ctx->d_send); ctx->d_send = nullptr; }
+    if (ctx->d_recv) { cudaFree(ctx->d_recv); ctx->d_recv = nullptr; }
+    ctx->halo_nb.clear();
+    ctx->halo_total = 0;
     if (ctx->nranks > 1) {
         std::vector<unsigned char> own(ctx->n, 0);
-        const int stride = (sa == 0) ? 1 : (sa == 1 ? ctx->nc[0] : ctx->nc[0] * ctx->nc[1]);
-        for (int I = 0; I < ctx->n; ++I) {
-            const int c = (I / stride) % ctx->nc[sa];
-            own[I] = (c >= ctx->own_begin && c < ctx->own_end) ? 1 : 0;
-        }
+        size_t I = 0;
+        for (int k = 0; k < ctx->nc[2]; ++k)
+            for (int j = 0; j < ctx->nc[1]; ++j)
+                for (int i = 0; i < ctx->nc[0]; ++i, ++I)
+                    own[I] = (i >= ctx->own_lo[0] && i < ctx->own_hi[0] && j >= ctx->own_lo[1] && j < ctx->own_hi[1] && k >= ctx->own_lo[2] &&
+                              k < ctx->own_hi[2]) ? 1 : 0;
         if (int rc = up(&ctx->d_owner, own)) return rc;
-        const size_t plane = (size_t)(ctx->n / ctx->nc[sa]) * ctx->b;
-        double** bufs[] = {&ctx->d_send_lo, &ctx->d_send_hi, &ctx->d_recv_lo, &ctx->d_recv_hi};
-        for (double** p : bufs) {
-            if (*p) cudaFree(*p);
-            DMX_CUDA(cudaMalloc((void**)p, plane * sizeof(double)));
+        // copyOwnerToAll neighbour table: direction (dx,dy,dz) in {-1,0,1}^3 \ 0, z slowest.  Along an axis with d = -1 my first
+        // owned layer goes out and my low overlap layer comes in, d = +1 likewise at the high end, d = 0: the owned range.
+        for (int dz = -1; dz <= 1; ++dz)
+            for (int dy = -1; dy <= 1; ++dy)
+                for (int dx = -1; dx <= 1; ++dx) {
+                    const int d[3] = {dx, dy, dz};
+                    if (!dx && !dy && !dz) continue;
+                    bool ok = true;
+                    for (int a = 0; a < 3; ++a) { const int c = ctx->pcoord[a] + d[a]; if (c < 0 || c >= ctx->part[a]) ok = false; }
+                    if (!ok) continue;
+                    dmx_ctx::HaloNb nb;
+                    nb.rank = (ctx->pcoord[0] + dx) + ctx->part[0] * ((ctx->pcoord[1] + dy) + ctx->part[1] * (ctx->pcoord[2] + dz));
+                    long long cnt = ctx->b;
+                    for (int a = 0; a < 3; ++a) {
+                        if (d[a] < 0) { nb.slo[a] = ctx->own_lo[a]; nb.rlo[a] = ctx->own_lo[a] - 1; nb.size[a] = 1; }
+                        else if (d[a] > 0) { nb.slo[a] = ctx->own_hi[a] - 1; nb.rlo[a] = ctx->own_hi[a]; nb.size[a] = 1; }
+                        else { nb.slo[a] = nb.rlo[a] = ctx->own_lo[a]; nb.size[a] = ctx->own_hi[a] - ctx->own_lo[a]; }
+                        cnt *= nb.size[a];
+                    }
+                    nb.count = cnt;
+                    nb.off = ctx->halo_total;
+                    // a region that spans the full local extent of every faster axis is one contiguous range of the vector
+                    nb.contiguous = nb.size[0] == ctx->nc[0] && (nb.size[1] == ctx->nc[1] || nb.size[2] == 1);
+                    ctx->halo_total += cnt;
+                    ctx->halo_nb.push_back(nb);
+                }
+        if (ctx->halo_total > 0) {
+            DMX_CUDA(cudaMalloc((void**)&ctx->d_send, (size_t)ctx->halo_total * sizeof(double)));
+            DMX_CUDA(cudaMalloc((void**)&ctx->d_recv, (size_t)ctx->halo_total * sizeof(double)));
         }
     }
     return 0;
@@ -263,7 +303,7 @@ int dmx_destroy(dmx_ctx* ctx)
     void* ptrs[] = {ctx->d_geom, ctx->d_K, ctx->d_phi, ctx->d_q, ctx->d_region, ctx->d_tij[0], ctx->d_tij[1], ctx->d_tij[2], ctx->d_laws,
                     ctx->d_tab_buf, ctx->d_rowptr, ctx->d_colidx, ctx->d_diag, ctx->d_J, ctx->d_ilu, ctx->d_rt, ctx->d_p, ctx->d_v, ctx->d_t,
                     ctx->d_y, ctx->d_z, ctx->d_dinv, ctx->d_gm, ctx->d_vf, ctx->d_lrows, ctx->d_urows, ctx->d_lptr, ctx->d_uptr, ctx->d_barrier, ctx->d_partials,
-                    ctx->d_scalars, ctx->d_flag, ctx->d_owner, ctx->d_send_lo, ctx->d_send_hi, ctx->d_recv_lo, ctx->d_recv_hi};
+                    ctx->d_scalars, ctx->d_flag, ctx->d_owner, ctx->d_send, ctx->d_recv};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int v = 0; v < DMX_NUM_VECS; ++v) if (ctx->d_vec[v]) cudaFree(ctx->d_vec[v]);
     for (int s = 0; s < 6; ++s) {
@@ -309,8 +349,27 @@ int dmx_grid_tensor(dmx_ctx* ctx, int model, int dim, const int* cells, const do
 int dmx_local_box(const dmx_ctx* ctx, int* cells, int* offset, int* owned_begin, int* owned_end)
 {
     for (int a = 0; a < 3; ++a) { cells[a] = ctx->nc[a]; offset[a] = ctx->off[a]; }
-    *owned_begin = ctx->own_begin;
-    *owned_end = ctx->own_end;
+    // owned range along the last grid axis (the slab axis of the default partitioning)
+    *owned_begin = ctx->own_lo[ctx->dim > 0 ? ctx->dim - 1 : 0];
+    *owned_end = ctx->own_hi[ctx->dim > 0 ? ctx->dim - 1 : 0];
+    return 0;
+}
+int dmx_set_partitioning(dmx_ctx* ctx, const int* ranks_per_axis)
+{
+    if (!ranks_per_axis) { ctx->part_req[0] = ctx->part_req[1] = ctx->part_req[2] = 0; return 0; }
+    for (int a = 0; a < 3; ++a) {
+        if (ranks_per_axis[a] < 1) return fail(ctx, DMX_ERR_USAGE, "set_partitioning: ranks per axis must be >= 1");
+        ctx->part_req[a] = ranks_per_axis[a];
+    }
+    return 0;
+}
+int dmx_local_box3(const dmx_ctx* ctx, int* cells, int* offset, int* owned_begin, int* owned_end, int* ranks_per_axis, int* coord)
+{
+    for (int a = 0; a < 3; ++a) {
+        cells[a] = ctx->nc[a]; offset[a] = ctx->off[a]; owned_begin[a] = ctx->own_lo[a]; owned_end[a] = ctx->own_hi[a];
+        if (ranks_per_axis) ranks_per_axis[a] = ctx->part[a];
+        if (coord) coord[a] = ctx->pcoord[a];
+    }
     return 0;
 }
 int dmx_num_cells(const dmx_ctx* ctx) { return ctx->n; }
@@ -446,8 +505,8 @@ int dmx_set_boundary(dmx_ctx* ctx, int side, const int* type, const double* valu
     if (!ctx->has_grid) return fail(ctx, DMX_ERR_USAGE, "set grid first");
     if (side < 0 || side >= 2 * ctx->dim) return fail(ctx, DMX_ERR_USAGE, "side out of range");
     // a processor boundary keeps its DMX_BC_NONE marking
-    const int sa = ctx->split_axis;
-    if (ctx->nranks > 1 && ((side == 2 * sa && ctx->off[sa] > 0) || (side == 2 * sa + 1 && ctx->off[sa] + ctx->nc[sa] < ctx->gcells[sa])))
+    const int sa = side / 2;
+    if (ctx->nranks > 1 && (((side & 1) == 0 && ctx->off[sa] > 0) || ((side & 1) == 1 && ctx->off[sa] + ctx->nc[sa] < ctx->gcells[sa])))
         return 0;
     const int nf = dmx_side_faces(ctx, side);
     ctx->h_bc_type[side].assign(type, type + nf);
@@ -579,9 +638,9 @@ int dmx_assemble(dmx_ctx* ctx, int with_jacobian)
     DMX_CUDA(cudaSetDevice(ctx->device));
     DMX_CUDA(cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream));
     if (int rc = launch_assemble(ctx, with_jacobian != 0)) return rc;
-    DMX_CUDA(cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    DMX_CUDA(cudaStreamSynchronize(ctx->stream));
-    int bad = *ctx->h_flag;
+    // comm().min(succeeded) (assembly/fvassembler.hh:504-509): all ranks see the same flag
+    int bad = 0;
+    if (int rc = agree_flag(ctx, &bad)) return rc;
     if (bad) { ctx->err = "assemble: non-finite residual"; return DMX_STATUS_NONFINITE; }
     return 0;
 }
@@ -850,7 +909,7 @@ int dmx_time_kernel(dmx_ctx* ctx, int which, int reps, float* ms_avg)
     if (reps < 1) reps = 1;
     int rc = 0;
     if (which == 2 && !ctx->ilu_valid) return fail(ctx, DMX_ERR_USAGE, "time ILU apply: factor first");
-    if ((which == 0 || which == 4) && (rc = prepare(ctx))) return rc;
+    if (which == 0 && (rc = prepare(ctx))) return rc;
     DMX_CUDA(cudaStreamSynchronize(ctx->stream));
     DMX_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
     for (int i = 0; i < reps && !rc; ++i) {
@@ -859,7 +918,6 @@ int dmx_time_kernel(dmx_ctx* ctx, int which, int reps, float* ms_avg)
             case 1: rc = launch_spmv(ctx, ctx->d_vec[DMX_VEC_WORK0], ctx->d_vec[DMX_VEC_WORK1]); break;
             case 2: rc = ilu0_apply(ctx, ctx->d_vec[DMX_VEC_WORK0], ctx->d_vec[DMX_VEC_WORK1]); break;
             case 3: rc = ilu0_factor(ctx); break;
-            case 4: rc = launch_volvars_only(ctx); break;
             default: return fail(ctx, DMX_ERR_USAGE, "unknown kernel id");
         }
     }

@@ -1379,6 +1379,5 @@ int launch_assemble(dmx_ctx* ctx, bool with_jacobian)
     if (with_jacobian) ctx->jac_diagonal = (rc == 0 && ctx->model == DMX_MODEL_TRACER && !ctx->tracer_implicit);
     return rc;
 }
-int launch_volvars_only(dmx_ctx* ctx) { return fail(ctx, DMX_ERR_USAGE, "the secondary variables are evaluated inside the assembly kernel"); }
 
 } // namespace dmx

@@ -75,8 +75,16 @@ struct dmx_ctx {
     // distributed
     int rank = 0, nranks = 1;
     void* nccl_comm = nullptr;
-    int split_axis = 2;
-    int own_begin = 0, own_end = 0;     // owned index range along split axis (local indices)
+    // Grid.Partitioning (io/grid/gridmanager_yasp.hh:194-203): ranks per axis, 0 = not set (slabs along the last axis);
+    // pcoord = this rank's position in the process torus (x fastest); own_lo/own_hi = owned index range per axis (LOCAL indices)
+    int part_req[3] = {0, 0, 0};
+    int part[3] = {1, 1, 1}, pcoord[3] = {0, 0, 0};
+    int own_lo[3] = {0, 0, 0}, own_hi[3] = {1, 1, 1};
+    // copyOwnerToAll neighbours (up to 26 directions): owned cells that lie in the neighbour's overlap go out, my overlap
+    // cells the neighbour owns come in.  Regions are boxes in local indices; buffers are packed in neighbour order.
+    struct HaloNb { int rank; int slo[3], rlo[3], size[3]; long long off, count; bool contiguous; };
+    std::vector<HaloNb> halo_nb;
+    long long halo_total = 0;           // doubles per exchange (all neighbours)
 
     // grid
     int model = 0, b = 0, dim = 0;
@@ -148,7 +156,7 @@ struct dmx_ctx {
     unsigned char* d_owner = nullptr;  // 1 = owner (null in single-GPU mode)
 
     // halo (distributed)
-    double *d_send_lo = nullptr, *d_send_hi = nullptr, *d_recv_lo = nullptr, *d_recv_hi = nullptr;
+    double *d_send = nullptr, *d_recv = nullptr;
 
     cudaEvent_t ev[6] = {};
 
@@ -263,7 +271,6 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
 // implemented in assembly.cu
 int prepare(dmx_ctx* ctx);
 int launch_assemble(dmx_ctx* ctx, bool with_jacobian);
-int launch_volvars_only(dmx_ctx* ctx);
 int launch_volume_flux(dmx_ctx* ctx, double* d_out);
 int launch_output_fields(dmx_ctx* ctx, double* d_out);
 // implemented in linalg.cu
@@ -281,7 +288,6 @@ int bicgstab(dmx_ctx* ctx, double reduction, int maxit, int precond, int* iterat
 int gmres(dmx_ctx* ctx, double reduction, int maxit, int restart, int precond, int* iterations, double* achieved);
 int linear_solve(dmx_ctx* ctx, double reduction, int maxit, int precond, int* iterations, double* achieved);
 int newton_update(dmx_ctx* ctx, double lambda, double* shift);
-int check_finite(dmx_ctx* ctx, const double* v, size_t len, bool* ok);
 // implemented in ilu_structured.cu
 int sk_setup(dmx_ctx* ctx);
 void sk_free(dmx_ctx* ctx);
@@ -297,5 +303,7 @@ int halo_exchange(dmx_ctx* ctx, double* v);
 int allreduce_sum(dmx_ctx* ctx, double* d_buf, int count);
 int allreduce_max(dmx_ctx* ctx, double* d_buf, int count);
 int allreduce_min_int(dmx_ctx* ctx, int* d_buf, int count);
+int allreduce_max_int(dmx_ctx* ctx, int* d_buf, int count);
+int agree_flag(dmx_ctx* ctx, int* flag_out);
 
 } // namespace dmx

@@ -67,36 +67,29 @@ bool load_nccl()
             return fail(ctx, DMX_ERR_NCCL, std::string(#call) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r__) : "nccl error")); \
     } while (0)
 
-// gather / scatter one plane (index `layer` along the split axis) of a block vector
-__global__ void __launch_bounds__(256) plane_pack_kernel(int nx, int ny, int nz, int b, int axis, int layer, const double* v, double* buf)
+// gather / scatter the copyOwnerToAll regions of all neighbours in one launch: region q = box lo[q] + [0, size[q]) of the local
+// grid, packed x fastest at buf + off[q]
+struct HaloRegions {
+    int nreg;
+    int lo[26][3], size[26][3];
+    long long off[27];         // in doubles; off[nreg] = total
+};
+template <bool PACK>
+__global__ void __launch_bounds__(256) halo_pack_kernel(HaloRegions R, int nx, int ny, int b, double* v, double* buf)
 {
-    const int nc[3] = {nx, ny, nz};
-    int m = 1;
-    for (int d = 0; d < 3; ++d) if (d != axis) m *= nc[d];
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= m * b) return;
-    const int f = t / b, e = t % b;
-    int c[3];
-    if (axis == 0) { c[0] = layer; c[1] = f % ny; c[2] = f / ny; }
-    else if (axis == 1) { c[0] = f % nx; c[1] = layer; c[2] = f / nx; }
-    else { c[0] = f % nx; c[1] = f / nx; c[2] = layer; }
-    const size_t I = c[0] + (size_t)nx * (c[1] + (size_t)ny * c[2]);
-    buf[t] = v[I * b + e];
-}
-__global__ void __launch_bounds__(256) plane_unpack_kernel(int nx, int ny, int nz, int b, int axis, int layer, double* v, const double* buf)
-{
-    const int nc[3] = {nx, ny, nz};
-    int m = 1;
-    for (int d = 0; d < 3; ++d) if (d != axis) m *= nc[d];
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= m * b) return;
-    const int f = t / b, e = t % b;
-    int c[3];
-    if (axis == 0) { c[0] = layer; c[1] = f % ny; c[2] = f / ny; }
-    else if (axis == 1) { c[0] = f % nx; c[1] = layer; c[2] = f / nx; }
-    else { c[0] = f % nx; c[1] = f / nx; c[2] = layer; }
-    const size_t I = c[0] + (size_t)nx * (c[1] + (size_t)ny * c[2]);
-    v[I * b + e] = buf[t];
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= R.off[R.nreg]) return;
+    int q = 0;
+    while (t >= R.off[q + 1]) ++q;
+    long long f = (t - R.off[q]) / b;
+    const int e = (int)((t - R.off[q]) % b);
+    const int i = R.lo[q][0] + (int)(f % R.size[q][0]);
+    f /= R.size[q][0];
+    const int j = R.lo[q][1] + (int)(f % R.size[q][1]);
+    const int k = R.lo[q][2] + (int)(f / R.size[q][1]);
+    const size_t I = i + (size_t)nx * (j + (size_t)ny * k);
+    if (PACK) buf[t] = v[I * b + e];
+    else v[I * b + e] = buf[t];
 }
 } // namespace
 
@@ -127,33 +120,41 @@ int nccl_destroy(dmx_ctx* ctx)
     return 0;
 }
 
-// copyOwnerToAll for a slab decomposition with overlap 1: my first/last OWNED plane goes to the neighbour's
-// overlap plane; my overlap planes are overwritten with the neighbours' owned planes.
+// copyOwnerToAll for a block decomposition with overlap 1 (BlockPreconditioner::apply / pre): every overlap
+// cell receives the value of the rank that owns it -- up to 26 neighbours (faces, edges, corners), ONE grouped NCCL exchange.
+// Regions that are contiguous in the vector (the planes of a slab decomposition along the last axis) are sent from and received
+// into the vector directly; the others go through one pack and one unpack launch.
 int halo_exchange(dmx_ctx* ctx, double* v)
 {
-    if (ctx->nranks == 1) return 0;
+    if (ctx->nranks == 1 || ctx->halo_nb.empty()) return 0;
     ProfScope ps(ctx, DMX_K_HALO);
     ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
-    const int sa = ctx->split_axis;
-    const int nx = ctx->nc[0], ny = ctx->nc[1], nz = ctx->nc[2], b = ctx->b;
-    const int m = (ctx->n / ctx->nc[sa]) * b;
-    const int grid = (m + 255) / 256;
-    const bool hasLo = ctx->off[sa] > 0;
-    const bool hasHi = ctx->off[sa] + ctx->nc[sa] < ctx->gcells[sa];
-    if (hasLo) { plane_pack_kernel<<<grid, 256, 0, ctx->stream>>>(nx, ny, nz, b, sa, ctx->own_begin, v, ctx->d_send_lo); DMX_CHECK_LAUNCH(); }
-    if (hasHi) { plane_pack_kernel<<<grid, 256, 0, ctx->stream>>>(nx, ny, nz, b, sa, ctx->own_end - 1, v, ctx->d_send_hi); DMX_CHECK_LAUNCH(); }
-    DMX_NCCL(g_nccl.GroupStart());
-    if (hasLo) {
-        DMX_NCCL(g_nccl.Send(ctx->d_send_lo, m, ncclFloat64, ctx->rank - 1, comm, ctx->stream));
-        DMX_NCCL(g_nccl.Recv(ctx->d_recv_lo, m, ncclFloat64, ctx->rank - 1, comm, ctx->stream));
+    const int nx = ctx->nc[0], ny = ctx->nc[1], b = ctx->b;
+    HaloRegions S, R;
+    S.nreg = R.nreg = 0;
+    long long so = 0;
+    for (const auto& nb : ctx->halo_nb) {
+        if (nb.contiguous) continue;
+        for (int a = 0; a < 3; ++a) { S.lo[S.nreg][a] = nb.slo[a]; S.size[S.nreg][a] = nb.size[a]; R.lo[R.nreg][a] = nb.rlo[a]; R.size[R.nreg][a] = nb.size[a]; }
+        S.off[S.nreg] = R.off[R.nreg] = so;
+        so += nb.count;
+        ++S.nreg; ++R.nreg;
     }
-    if (hasHi) {
-        DMX_NCCL(g_nccl.Send(ctx->d_send_hi, m, ncclFloat64, ctx->rank + 1, comm, ctx->stream));
-        DMX_NCCL(g_nccl.Recv(ctx->d_recv_hi, m, ncclFloat64, ctx->rank + 1, comm, ctx->stream));
+    S.off[S.nreg] = R.off[R.nreg] = so;
+    const int grid = (int)((so + 255) / 256);
+    if (so > 0) { halo_pack_kernel<true><<<grid, 256, 0, ctx->stream>>>(S, nx, ny, b, v, ctx->d_send); DMX_CHECK_LAUNCH(); }
+    auto at = [&](const int* lo) { return ((size_t)lo[0] + (size_t)nx * (lo[1] + (size_t)ny * lo[2])) * b; };
+    DMX_NCCL(g_nccl.GroupStart());
+    long long po = 0;
+    for (const auto& nb : ctx->halo_nb) {
+        const double* sp = nb.contiguous ? v + at(nb.slo) : ctx->d_send + po;
+        double* rp = nb.contiguous ? v + at(nb.rlo) : ctx->d_recv + po;
+        if (!nb.contiguous) po += nb.count;
+        DMX_NCCL(g_nccl.Send(sp, (size_t)nb.count, ncclFloat64, nb.rank, comm, ctx->stream));
+        DMX_NCCL(g_nccl.Recv(rp, (size_t)nb.count, ncclFloat64, nb.rank, comm, ctx->stream));
     }
     DMX_NCCL(g_nccl.GroupEnd());
-    if (hasLo) { plane_unpack_kernel<<<grid, 256, 0, ctx->stream>>>(nx, ny, nz, b, sa, ctx->own_begin - 1, v, ctx->d_recv_lo); DMX_CHECK_LAUNCH(); }
-    if (hasHi) { plane_unpack_kernel<<<grid, 256, 0, ctx->stream>>>(nx, ny, nz, b, sa, ctx->own_end, v, ctx->d_recv_hi); DMX_CHECK_LAUNCH(); }
+    if (so > 0) { halo_pack_kernel<false><<<grid, 256, 0, ctx->stream>>>(R, nx, ny, b, v, ctx->d_recv); DMX_CHECK_LAUNCH(); }
     return 0;
 }
 
@@ -173,6 +174,26 @@ int allreduce_min_int(dmx_ctx* ctx, int* d_buf, int count)
 {
     if (ctx->nranks == 1) return 0;
     DMX_NCCL(g_nccl.AllReduce(d_buf, d_buf, count, ncclInt32, ncclMin, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+    return 0;
+}
+
+int allreduce_max_int(dmx_ctx* ctx, int* d_buf, int count)
+{
+    if (ctx->nranks == 1) return 0;
+    DMX_NCCL(g_nccl.AllReduce(d_buf, d_buf, count, ncclInt32, ncclMax, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+    return 0;
+}
+
+// The failure word ctx->d_flag (non-finite residual, singular diagonal block) agreed over all ranks before any of them acts on
+// it: what `comm.min(succeeded)` does in FVAssembler::assemble_ (assembly/fvassembler.hh:504-509) and
+// NewtonSolver::solveLinearSystem (nonlinear/newtonsolver.hh:510-523) -- every rank returns the same status, so a
+// NumericalProblem on one rank becomes a dt-halving retry on all of them instead of a hang in the next collective.
+int agree_flag(dmx_ctx* ctx, int* flag_out)
+{
+    if (int rc = allreduce_max_int(ctx, ctx->d_flag, 1)) return rc;
+    DMX_CUDA(cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    DMX_CUDA(cudaStreamSynchronize(ctx->stream));
+    *flag_out = *ctx->h_flag;
     return 0;
 }
 

@@ -284,14 +284,6 @@ __global__ void __launch_bounds__(RED_THREADS) newton_update_kernel(size_t len, 
     s = block_reduce<true>(s);
     if (threadIdx.x == 0) partials[blockIdx.x] = s;
 }
-__global__ void __launch_bounds__(RED_THREADS) finite_check_kernel(size_t len, const double* v, int* flag)
-{
-    bool bad = false;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (size_t)gridDim.x * blockDim.x)
-        bad = bad || !(fabs(v[i]) <= DBL_MAX);
-    if (bad) atomicOr(flag, 1);
-}
-
 static int reduce_to_host(dmx_ctx* ctx, int nq, bool max, double* out)
 {
     if (max) final_reduce_kernel<true><<<1, RED_THREADS, 0, ctx->stream>>>(RED_BLOCKS, nq, ctx->d_partials, ctx->d_scalars);
@@ -346,17 +338,6 @@ int newton_update(dmx_ctx* ctx, double lambda, double* shift)
                                                                       ctx->d_vec[DMX_VEC_CUR], ctx->d_owner, ctx->d_partials);
     DMX_CHECK_LAUNCH();
     return reduce_to_host(ctx, 1, true, shift);
-}
-
-int check_finite(dmx_ctx* ctx, const double* v, size_t len, bool* ok)
-{
-    DMX_CUDA(cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream));
-    finite_check_kernel<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>>(len, v, ctx->d_flag);
-    DMX_CHECK_LAUNCH();
-    DMX_CUDA(cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    DMX_CUDA(cudaStreamSynchronize(ctx->stream));
-    *ok = (*ctx->h_flag == 0);
-    return 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -671,9 +652,10 @@ int ilu0_factor(dmx_ctx* ctx)
     } else {
         if (int rc = ilu0_factor_bcrs(ctx)) return rc;
     }
-    DMX_CUDA(cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    DMX_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (*ctx->h_flag) { ctx->err = "ILU0: singular diagonal block"; return DMX_STATUS_BREAKDOWN; }
+    // agreed over all ranks (the reference: the solver construction throws on one rank, newtonsolver.hh:510-523 comm.min)
+    int bad = 0;
+    if (int rc = agree_flag(ctx, &bad)) return rc;
+    if (bad) { ctx->err = "ILU0: singular diagonal block"; return DMX_STATUS_BREAKDOWN; }
     ctx->ilu_valid = true;
     ctx->ilu_bcrs_valid = !ctx->skew;
     return 0;
@@ -763,9 +745,9 @@ int block_jacobi_setup(dmx_ctx* ctx)
     if (ctx->b == 2) jacobi_setup_kernel<2><<<grid, 256, 0, ctx->stream>>>(ctx->n, ctx->d_diag, ctx->d_J, ctx->d_dinv, ctx->d_flag);
     else jacobi_setup_kernel<1><<<grid, 256, 0, ctx->stream>>>(ctx->n, ctx->d_diag, ctx->d_J, ctx->d_dinv, ctx->d_flag);
     DMX_CHECK_LAUNCH();
-    DMX_CUDA(cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    DMX_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (*ctx->h_flag) { ctx->err = "block-Jacobi: singular diagonal block"; return DMX_STATUS_BREAKDOWN; }
+    int bad = 0;
+    if (int rc = agree_flag(ctx, &bad)) return rc;
+    if (bad) { ctx->err = "block-Jacobi: singular diagonal block"; return DMX_STATUS_BREAKDOWN; }
     return 0;
 }
 int block_jacobi_apply(dmx_ctx* ctx, const double* d, double* v)

@@ -76,6 +76,13 @@ class ProblemSpec:
     # slab-local spec (multi-GPU set-up without materialising the global arrays): the per-cell / per-face arrays above
     # cover only the layers [slab[0], slab[1]) of the last axis (overlap included); cells/lower/upper stay GLOBAL.
     slab: Optional[Tuple[int, int]] = None
+    # box-local spec: the arrays cover the box [box[a][0], box[a][1]) of every axis (block decomposition, overlap included)
+    box: Optional[Tuple[Tuple[int, int], ...]] = None
+
+    @property
+    def local_box(self):
+        """per-axis (lo, hi) the per-cell arrays cover, or None if they are global"""
+        return _as_box(self.cells, self.slab, self.box)
 
     @property
     def num_eq(self) -> int:
@@ -102,37 +109,80 @@ def node_coords(cells, lower, upper):
     return out
 
 
+def axis_partition(n_layers: int, nparts: int, coord: int, overlap: int = 1):
+    """Layers [lo, hi) of one axis held by the block at torus coordinate `coord` (overlap included) and its owned range
+    [b0, b1).  YaspGrid's tensor-product partitioning (dune-grid torus.hh Torus::partition [DUNE-ext]): n/P layers for the
+    first P - n%P blocks, one more for the others; Grid.Overlap 1 (io/grid/gridmanager_yasp.hh:129)."""
+    if nparts == 1:
+        return 0, n_layers, 0, n_layers
+    m, rem = divmod(n_layers, nparts)
+    if coord < nparts - rem:
+        b0, b1 = coord * m, coord * m + m
+    else:
+        b0 = (nparts - rem) * m + (coord - (nparts - rem)) * (m + 1)
+        b1 = b0 + m + 1
+    return max(0, b0 - overlap), min(n_layers, b1 + overlap), b0, b1
+
+
 def slab_partition(n_layers: int, nranks: int, rank: int, overlap: int = 1):
     """Layers [lo, hi) of the split axis held by `rank` (overlap included) and its owned range [b0, b1): the
     Yasp-style fixed-size partitioning "1 1 P" with Grid.Overlap 1 (io/grid/gridmanager_yasp.hh:129,194-203) as
     dmx_grid_structured cuts it."""
-    base, rem = divmod(n_layers, nranks)
-    b0 = rank * base + min(rank, rem)
-    b1 = b0 + base + (1 if rank < rem else 0)
-    if nranks == 1:
-        return 0, n_layers, 0, n_layers
-    return max(0, b0 - overlap), min(n_layers, b1 + overlap), b0, b1
+    return axis_partition(n_layers, nranks, rank, overlap)
 
 
-def cell_centers(cells, lower, upper, slab=None):
-    """float64[n, dim], x fastest; `slab` = (lo, hi) restricts the last axis to those layers."""
-    xs = node_coords(cells, lower, upper)
-    ctr = [0.5 * (x[:-1] + x[1:]) for x in xs]
+def default_partitioning(dim: int, nranks: int):
+    """Grid.Partitioning used when none is given: slabs along the last axis ("1 .. P")."""
+    return tuple([1] * (dim - 1) + [nranks])
+
+
+def rank_coord(part, rank: int):
+    """Torus coordinate of `rank`, x fastest (dune-grid torus.hh Torus::rank_to_coord [DUNE-ext])."""
+    c = []
+    for p in part:
+        c.append(rank % p)
+        rank //= p
+    return tuple(c)
+
+
+def box_partition(cells, part, rank: int, overlap: int = 1):
+    """Per axis (lo, hi, b0, b1) of the block of `rank` in a `part` = (px, py[, pz]) decomposition (Grid.Partitioning,
+    io/grid/gridmanager_yasp.hh:194-203): the local box incl. overlap and the owned (interior) range, global indices."""
+    coord = rank_coord(part, rank)
+    return [axis_partition(cells[a], part[a], coord[a], overlap) for a in range(len(cells))]
+
+
+def _cut(arrs, box):
+    if box is None:
+        return arrs
+    return [a[lo:hi] for a, (lo, hi) in zip(arrs, box)]
+
+
+def _as_box(cells, slab=None, box=None):
+    """normalise the (slab | box) arguments to a per-axis list of (lo, hi) or None"""
+    if box is not None:
+        return [tuple(b) for b in box]
     if slab is not None:
-        ctr[-1] = ctr[-1][slab[0]:slab[1]]
+        return [(0, c) for c in cells[:-1]] + [tuple(slab)]
+    return None
+
+
+def cell_centers(cells, lower, upper, slab=None, box=None):
+    """float64[n, dim], x fastest; `slab` = (lo, hi) restricts the last axis to those layers, `box` = per-axis (lo, hi)."""
+    xs = node_coords(cells, lower, upper)
+    ctr = _cut([0.5 * (x[:-1] + x[1:]) for x in xs], _as_box(cells, slab, box))
     grids = np.meshgrid(*ctr, indexing="ij")
     # x fastest: flatten in Fortran order
     return np.stack([g.reshape(-1, order="F") for g in grids], axis=1)
 
 
-def side_face_centers(cells, lower, upper, side, slab=None):
-    """float64[nf, dim] centres of the boundary faces of `side` (lower remaining axis fastest)."""
+def side_face_centers(cells, lower, upper, side, slab=None, box=None):
+    """float64[nf, dim] centres of the boundary faces of `side` (lower remaining axis fastest) of the GLOBAL boundary,
+    restricted to the local box in the other axes."""
     dim = len(cells)
     a = side // 2
     xs = node_coords(cells, lower, upper)
-    ctr = [0.5 * (x[:-1] + x[1:]) for x in xs]
-    if slab is not None and a != dim - 1:
-        ctr[-1] = ctr[-1][slab[0]:slab[1]]
+    ctr = _cut([0.5 * (x[:-1] + x[1:]) for x in xs], _as_box(cells, slab, box))
     ctr[a] = np.array([xs[a][-1] if side & 1 else xs[a][0]])
     grids = np.meshgrid(*ctr, indexing="ij")
     return np.stack([g.reshape(-1, order="F") for g in grids], axis=1)[:, :dim]
@@ -207,15 +257,21 @@ def lognormal_permeability(n: int, kmean: float, seed: int = 0, in_lens: Optiona
     return out
 
 
-def plane_lognormal_multiplier(cells, sigma: float, seed: int = 0, slab=None) -> np.ndarray:
+def plane_lognormal_multiplier(cells, sigma: float, seed: int = 0, slab=None, box=None) -> np.ndarray:
     """exp(N(0, sigma)) per cell with one MT19937 stream per layer of the last axis (seeded seed*1000003 + layer), so
-    that any slab of a slab-decomposed grid can be generated without the global field."""
-    per_layer = int(np.prod(cells[:-1]))
-    lo, hi = (0, cells[-1]) if slab is None else slab
-    out = np.empty((hi - lo, per_layer))
+    that any slab / block of a decomposed grid can be generated without the global field."""
+    bx = _as_box(cells, slab, box)
+    lo, hi = (0, cells[-1]) if bx is None else bx[-1]
+    inner = tuple(cells[:-1])
+    per_layer = int(np.prod(inner))
+    sl = tuple(slice(*b) for b in reversed(bx[:-1])) if bx is not None else None
+    out = []
     for k in range(lo, hi):
-        out[k - lo] = np.exp(np.random.RandomState(seed * 1000003 + k).normal(0.0, sigma, size=per_layer))
-    return out.reshape(-1)
+        layer = np.exp(np.random.RandomState(seed * 1000003 + k).normal(0.0, sigma, size=per_layer))
+        if sl is not None:
+            layer = layer.reshape(tuple(reversed(inner)))[sl].reshape(-1)
+        out.append(layer)
+    return np.concatenate(out)
 
 
 def fast_lognormal_multiplier(n: int, sigma: float, seed: int = 0) -> np.ndarray:
@@ -308,9 +364,9 @@ def onep_compressible(cells=(10, 10), lower=None, upper=None, dt=0.002, lognorma
 # ------------------------------------------------------------------------------------------------------
 def twop_lens(cells=(48, 32), law="vg", lower=None, upper=None, lens_lower=None, lens_upper=None,
               dt=250.0, heterogeneity_sigma=0.0, seed=0, bc_params=None, slab=None, plane_rng=False, oilwet=False,
-              analytic=False) -> ProblemSpec:
-    """`slab` = (lo, hi): build only those layers of the last axis (see ProblemSpec.slab); `plane_rng`: per-layer
-    heterogeneity streams (implied by `slab`).  `oilwet`: test_2p_incompressible_tpfa_oilwet (SpatialParams.LensIsOilWet,
+              analytic=False, box=None) -> ProblemSpec:
+    """`slab` = (lo, hi): build only those layers of the last axis (see ProblemSpec.slab), `box` = per-axis (lo, hi): build only
+    that block (ProblemSpec.box); `plane_rng`: per-layer heterogeneity streams (implied by `slab` / `box`).  `oilwet`: test_2p_incompressible_tpfa_oilwet (SpatialParams.LensIsOilWet,
     Problem.EnableGravity false): the lens keeps the outer permeability and pc-kr-Sw parameters but phase 1 wets it
     (spatialparams.hh:76,105,117-122) and the injection rate is ten times higher (problem.hh:112-113).
     `analytic`: DiffMethod::analytic (test_2p_incompressible_tpfa_analytic)."""
@@ -327,15 +383,16 @@ def twop_lens(cells=(48, 32), law="vg", lower=None, upper=None, lens_lower=None,
         lens_lower = (1.0, 1.0, 2.0) if lens_lower is None else lens_lower
         lens_upper = (4.0, 3.0, 3.0) if lens_upper is None else lens_upper
     n = int(np.prod(cells))
-    if slab is not None:
-        n = int(np.prod(cells[:-1])) * (slab[1] - slab[0])
+    bx = _as_box(cells, slab, box)
+    if bx is not None:
+        n = int(np.prod([hi - lo for lo, hi in bx]))
     va = dim - 1
-    ctr = cell_centers(cells, lower, upper, slab)
+    ctr = cell_centers(cells, lower, upper, box=bx)
     lens = _in_box(ctr, lens_lower, lens_upper, 1.5e-7)
     K = np.where(lens, 9.05e-12, 4.6e-10) if not oilwet else np.full(n, 4.6e-10)
     if heterogeneity_sigma > 0.0:
-        if slab is not None or plane_rng:
-            K = K * plane_lognormal_multiplier(cells, heterogeneity_sigma, seed, slab)
+        if bx is not None or plane_rng:
+            K = K * plane_lognormal_multiplier(cells, heterogeneity_sigma, seed, box=bx)
         else:
             K = K * fast_lognormal_multiplier(n, heterogeneity_sigma, seed)
     region = lens.astype(np.int32)
@@ -355,7 +412,7 @@ def twop_lens(cells=(48, 32), law="vg", lower=None, upper=None, lens_lower=None,
     bc_type, bc_values = {}, {}
     eps = 1e-6
     for side in range(2 * dim):
-        fc = side_face_centers(cells, lower, upper, side, slab)
+        fc = side_face_centers(cells, lower, upper, side, box=bx)
         nf = fc.shape[0]
         x, y = fc[:, 0], fc[:, va]
         left = x < lower[0] + eps
@@ -378,7 +435,7 @@ def twop_lens(cells=(48, 32), law="vg", lower=None, upper=None, lens_lower=None,
         K=K, phi=np.full(n, 0.4), region=region, materials=mats, rho=(1000.0, 1460.0), mu=(1e-3, 5.7e-4),
         bc_type=bc_type, bc_values=bc_values, options=Options(stationary=False, dt=dt, enable_gravity=not oilwet, fd_method=DIFF_ANALYTIC if analytic else 1),
         initial=init,
-        slab=slab)
+        slab=slab, box=None if box is None else tuple(tuple(b) for b in box))
 
 
 # ------------------------------------------------------------------------------------------------------

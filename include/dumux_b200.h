@@ -110,12 +110,19 @@ const char* dmx_version(void);
 
 /* ---- grid + pattern (GridManager<YaspGrid>, io/grid/gridmanager_yasp.hh:84-135; CCTpfaFVGridGeometry::update_,
         discretization/cellcentered/tpfa/fvgridgeometry.hh:216-345; getJacobianPattern, assembly/jacobianpattern.hh:27-52) ---- */
-/* cells/lower/upper describe the GLOBAL grid.  In a distributed ctx the grid is slab-decomposed along the last
-   axis (Grid.Partitioning "1 1 P") with overlap 1 (Grid.Overlap default, gridmanager_yasp.hh:129). */
+/* cells/lower/upper describe the GLOBAL grid.  In a distributed ctx the grid is block-decomposed with overlap 1
+   (Grid.Overlap default, gridmanager_yasp.hh:129): dmx_set_partitioning gives the ranks per axis (Grid.Partitioning
+   "px py pz" -> Yasp::FixedSizePartitioning, gridmanager_yasp.hh:194-203; product = nranks; rank -> block with x fastest);
+   without it the grid is cut into slabs along the last axis ("1 1 P").  Call before dmx_grid_*; NULL restores the default. */
+int  dmx_set_partitioning(dmx_ctx* ctx, const int* ranks_per_axis);
 int  dmx_grid_structured(dmx_ctx* ctx, int model, int dim, const int* cells, const double* lower, const double* upper);
 int  dmx_grid_tensor(dmx_ctx* ctx, int model, int dim, const int* cells, const double* x, const double* y, const double* z);
-/* local box (incl. overlap) of this rank: cells[3], offset[3] in the global index space; owned range of the split axis */
+/* local box (incl. overlap) of this rank: cells[3], offset[3] in the global index space; owned range of the last grid axis */
 int  dmx_local_box(const dmx_ctx* ctx, int* cells, int* offset, int* owned_begin, int* owned_end);
+/* the same with the owned range [owned_begin[a], owned_end[a]) of every axis (local indices), the ranks per axis and this
+   rank's block coordinate (either may be NULL): the interior / overlap partition types of the YaspGrid piece
+   (linear/parallelhelpers.hh:434-458,485-497 turn them into owner / copy attributes) */
+int  dmx_local_box3(const dmx_ctx* ctx, int* cells, int* offset, int* owned_begin, int* owned_end, int* ranks_per_axis, int* coord);
 int  dmx_num_cells(const dmx_ctx* ctx);
 int  dmx_num_eq(const dmx_ctx* ctx);
 long long dmx_nnz_blocks(const dmx_ctx* ctx);
@@ -213,7 +220,7 @@ int  dmx_ssor_apply(dmx_ctx* ctx, int d_vec, int v_vec);
 int  dmx_dot(dmx_ctx* ctx, int a_vec, int b_vec, double* out);
 int  dmx_halo_exchange(dmx_ctx* ctx, int vec);                           /* copyOwnerToAll */
 /* average device time in ms of `reps` back-to-back launches of one kernel, CUDA-event timed on the ctx stream.
-   which: 0 assembly (residual+Jacobian), 1 SpMV, 2 ILU0 apply, 3 ILU0 factor, 4 secondary-variable pass only */
+   which: 0 assembly (residual+Jacobian), 1 SpMV, 2 ILU0 apply, 3 ILU0 factor */
 int  dmx_time_kernel(dmx_ctx* ctx, int which, int reps, float* ms_avg);
 /* developer diagnostic: clock64 timeline of the structured ILU sweeps (enabled by DMX_SK_TRACE=1 at grid set-up):
    out[kernel 2][tile 2][chunk 64][stamp 24] */
@@ -223,7 +230,7 @@ int  dmx_kernel_launch_count(const dmx_ctx* ctx, long long* launches);
    kernel granularity): CUDA-event pairs on the ctx stream around every launch of the class while enabled.
    dmx_profile(ctx, 1) resets and enables, dmx_profile(ctx, 0) disables; dmx_profile_read returns the accumulated
    device milliseconds and the number of timed units of one DMX_K_* class. */
-enum { DMX_K_ASSEMBLY = 0, DMX_K_SPMV = 1, DMX_K_ILU_APPLY = 2, DMX_K_ILU_FACTOR = 3, DMX_K_VOLVARS = 4, DMX_K_BLAS1 = 5,
+enum { DMX_K_ASSEMBLY = 0, DMX_K_SPMV = 1, DMX_K_ILU_APPLY = 2, DMX_K_ILU_FACTOR = 3, DMX_K_AMG = 4, DMX_K_BLAS1 = 5,
        DMX_K_HALO = 6, DMX_K_JACOBI = 7 };
 int  dmx_profile(dmx_ctx* ctx, int enable);
 int  dmx_profile_read(dmx_ctx* ctx, int kclass, double* ms_total, long long* units);

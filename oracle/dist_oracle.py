@@ -1,7 +1,8 @@
-"""Slab-decomposed (overlapping Schwarz) restatement of the Newton step on the CPU oracle.  TEST INFRASTRUCTURE ONLY.
+"""Block-decomposed (overlapping Schwarz) restatement of the Newton step on the CPU oracle.  TEST INFRASTRUCTURE ONLY.
 
 What DuMux does for a cell-centred scheme on P MPI ranks (SURVEY 2.2, 8e, Appendix A "Overlapping variant"):
-  * YaspGrid cuts the structured box into slabs (Grid.Partitioning "1 1 P") and adds `Grid.Overlap 1` layers; every rank
+  * YaspGrid cuts the structured box into px x py x pz blocks (Grid.Partitioning, io/grid/gridmanager_yasp.hh:194-203; slabs
+    "1 1 P" by default here) and adds `Grid.Overlap 1` layers; every rank
     assembles the rows of ALL its cells (interior + overlap); the outer face of an overlap cell carries no scvf
     (discretization/cellcentered/tpfa/fvgridgeometry.hh:272-320), so those rows are incomplete;
   * linear/linearsolvertraits.hh:79-91 + linear/istlsolvers.hh:550-566 wire dune-istl's
@@ -52,15 +53,14 @@ class ThreadComm:
             return acc
         return max(vals) if op == "max" else min(vals)
 
-    def exchange(self, to_lo, to_hi):
-        """send `to_lo` to rank-1 and `to_hi` to rank+1 (None: no neighbour); returns (from_lo, from_hi)."""
-        self.s.mail[(self.rank, -1)] = None if to_lo is None else to_lo.copy()
-        self.s.mail[(self.rank, +1)] = None if to_hi is None else to_hi.copy()
+    def exchange(self, sends):
+        """`sends`: {neighbour rank: array}; returns {neighbour rank: the array that neighbour sent to me}."""
+        for dst, a in sends.items():
+            self.s.mail[(self.rank, dst)] = a.copy()
         self.s.barrier.wait()
-        from_lo = self.s.mail.get((self.rank - 1, +1)) if self.rank > 0 else None
-        from_hi = self.s.mail.get((self.rank + 1, -1)) if self.rank + 1 < self.nranks else None
+        out = {src: self.s.mail[(src, self.rank)] for src in sends}
         self.s.barrier.wait()
-        return from_lo, from_hi
+        return out
 
 
 class TorchComm:
@@ -78,75 +78,122 @@ class TorchComm:
         out = t.numpy()
         return float(out[0]) if np.ndim(value) == 0 else out
 
-    def exchange(self, to_lo, to_hi):
+    def exchange(self, sends):
         import torch
-        reqs, from_lo, from_hi = [], None, None
-        if to_lo is not None:
-            from_lo = torch.empty(to_lo.size, dtype=torch.float64)
-            reqs.append(self.dist.isend(torch.from_numpy(np.ascontiguousarray(to_lo)), self.rank - 1))
-            reqs.append(self.dist.irecv(from_lo, self.rank - 1))
-        if to_hi is not None:
-            from_hi = torch.empty(to_hi.size, dtype=torch.float64)
-            reqs.append(self.dist.isend(torch.from_numpy(np.ascontiguousarray(to_hi)), self.rank + 1))
-            reqs.append(self.dist.irecv(from_hi, self.rank + 1))
+        reqs, recv = [], {}
+        for nb in sorted(sends):
+            recv[nb] = torch.empty(sends[nb].size, dtype=torch.float64)
+            reqs.append(self.dist.isend(torch.from_numpy(np.ascontiguousarray(sends[nb])), nb))
+            reqs.append(self.dist.irecv(recv[nb], nb))
         for r in reqs:
             r.wait()
-        return (None if from_lo is None else from_lo.numpy()), (None if from_hi is None else from_hi.numpy())
+        return {nb: t.numpy() for nb, t in recv.items()}
 
 
 # ----------------------------------------------------------------------------------------------------------
 # one rank
 # ----------------------------------------------------------------------------------------------------------
-class SlabRank:
-    """Local problem of one rank: slab [lo, hi) of the last axis incl. overlap, owned layers [b0, b1)."""
+class BoxRank:
+    """Local problem of one rank: block [lo, hi) per axis incl. overlap, owned (interior) range [b0, b1) per axis.
+    `part` = Grid.Partitioning (ranks per axis); None = slabs along the last axis.  `make_spec(box)` builds the box-local
+    ProblemSpec (box = per-axis (lo, hi), None for the single-domain run)."""
 
-    def __init__(self, make_spec, cells, comm):
+    def __init__(self, make_spec, cells, comm, part=None):
+        import copy
+        import itertools
         self.comm = comm
         dim = len(cells)
-        self.layers = cells[-1]
-        self.lo, self.hi, self.b0, self.b1 = problems.slab_partition(self.layers, comm.nranks, comm.rank)
-        self.spec = make_spec((self.lo, self.hi)) if comm.nranks > 1 else make_spec(None)
+        self.cells = tuple(cells)
+        self.part = tuple(part) if part is not None else problems.default_partitioning(dim, comm.nranks)
+        assert int(np.prod(self.part)) == comm.nranks
+        self.ranges = problems.box_partition(cells, self.part, comm.rank)          # per axis (lo, hi, b0, b1)
+        self.box = [(r[0], r[1]) for r in self.ranges]
+        # slab view of the last axis (kept for the slab tests)
+        self.lo, self.hi, self.b0, self.b1 = self.ranges[-1]
+        self.spec = make_spec(self.box) if comm.nranks > 1 else make_spec(None)
         spec = self.spec
         # the local oracle works on the local box: cut the geometry, mark processor boundaries as "no scvf"
-        import copy
         loc = copy.copy(spec)
-        h = (spec.upper[-1] - spec.lower[-1]) / cells[-1]
-        loc.cells = tuple(cells[:-1]) + (self.hi - self.lo,)
-        loc.lower = tuple(spec.lower[:-1]) + (spec.lower[-1] + self.lo * h,)
-        loc.upper = tuple(spec.upper[:-1]) + (spec.lower[-1] + self.hi * h,)
+        loc.cells = tuple(hi - lo for lo, hi in self.box)
+        nodes = problems.node_coords(cells, spec.lower, spec.upper)
+        loc.node_coords = [nodes[a][self.box[a][0]:self.box[a][1] + 1] for a in range(dim)]
+        loc.lower = tuple(float(loc.node_coords[a][0]) for a in range(dim))
+        loc.upper = tuple(float(loc.node_coords[a][-1]) for a in range(dim))
         loc.bc_type = dict(spec.bc_type)
         loc.bc_values = dict(spec.bc_values)
-        nf = int(np.prod(cells[:-1]))
-        if self.lo > 0:
-            loc.bc_type[2 * (dim - 1)] = np.full(nf, problems.BC_NONE, dtype=np.int32)
-            loc.bc_values[2 * (dim - 1)] = np.zeros((nf, spec.num_eq))
-        if self.hi < self.layers:
-            loc.bc_type[2 * (dim - 1) + 1] = np.full(nf, problems.BC_NONE, dtype=np.int32)
-            loc.bc_values[2 * (dim - 1) + 1] = np.zeros((nf, spec.num_eq))
+        for a in range(dim):
+            nf = int(np.prod([loc.cells[d] for d in range(dim) if d != a]))
+            if self.box[a][0] > 0:
+                loc.bc_type[2 * a] = np.full(nf, problems.BC_NONE, dtype=np.int32)
+                loc.bc_values[2 * a] = np.zeros((nf, spec.num_eq))
+            if self.box[a][1] < cells[a]:
+                loc.bc_type[2 * a + 1] = np.full(nf, problems.BC_NONE, dtype=np.int32)
+                loc.bc_values[2 * a + 1] = np.zeros((nf, spec.num_eq))
         loc.slab = None
-        nodes = problems.node_coords(cells, spec.lower, spec.upper)
-        nodes[-1] = nodes[-1][self.lo:self.hi + 1]
-        loc.node_coords = nodes
+        loc.box = None
         self.local = loc
         self.o = O.Oracle(loc)
         self.b = self.o.b
         self.n = self.o.n
-        self.plane = nf
-        own = np.zeros(self.hi - self.lo, dtype=bool)
-        own[self.b0 - self.lo:self.b1 - self.lo] = True
-        self.owner = np.repeat(np.repeat(own, nf), self.b)          # per scalar dof
+        lc3 = tuple(loc.cells) + (1,) * (3 - dim)
+        self.shape = (lc3[2], lc3[1], lc3[0], self.b)            # local block vector viewed [z, y, x, eq]
+        own = np.ones(self.shape[:3], dtype=bool)
+        self.own_rng = []
+        for a in range(3):
+            if a < dim:
+                lo, hi, b0, b1 = self.ranges[a]
+                self.own_rng.append((b0 - lo, b1 - lo))
+            else:
+                self.own_rng.append((0, 1))
+            idx = np.arange(lc3[a])
+            ok = (idx >= self.own_rng[a][0]) & (idx < self.own_rng[a][1])
+            shp = [1, 1, 1]
+            shp[2 - a] = -1
+            own &= ok.reshape(shp)
+        self.owner = np.repeat(own.reshape(-1), self.b)           # per scalar dof
+        # copyOwnerToAll neighbours: direction d in {-1,0,1}^3 \ 0 -> (rank, send slices, recv slices), [z, y, x] order
+        coord = problems.rank_coord(tuple(self.part) + (1,) * (3 - dim), comm.rank)
+        part3 = tuple(self.part) + (1,) * (3 - dim)
+        self.neighbours = []
+        for dz, dy, dx in itertools.product((-1, 0, 1), repeat=3):
+            d = (dx, dy, dz)
+            if d == (0, 0, 0):
+                continue
+            c = [coord[a] + d[a] for a in range(3)]
+            if any(c[a] < 0 or c[a] >= part3[a] for a in range(3)):
+                continue
+            nb = c[0] + part3[0] * (c[1] + part3[1] * c[2])
+            snd, rcv = [], []
+            for a in range(3):
+                o0, o1 = self.own_rng[a]
+                if d[a] < 0:
+                    snd.append(slice(o0, o0 + 1)); rcv.append(slice(o0 - 1, o0))
+                elif d[a] > 0:
+                    snd.append(slice(o1 - 1, o1)); rcv.append(slice(o1, o1 + 1))
+                else:
+                    snd.append(slice(o0, o1)); rcv.append(slice(o0, o1))
+            self.neighbours.append((nb, tuple(reversed(snd)), tuple(reversed(rcv))))
 
-    # copyOwnerToAll for slabs with overlap 1: my first / last OWNED plane -> neighbour's overlap plane
+    # copyOwnerToAll with overlap 1: owned cells inside a neighbour's overlap go out, my overlap cells come in from their owner
     def copy_owner_to_all(self, v):
-        pb = self.plane * self.b
-        o0, o1 = (self.b0 - self.lo) * pb, (self.b1 - self.lo) * pb
-        to_lo = v[o0:o0 + pb] if self.lo > 0 else None
-        to_hi = v[o1 - pb:o1] if self.hi < self.layers else None
-        from_lo, from_hi = self.comm.exchange(to_lo, to_hi)
-        if from_lo is not None:
-            v[o0 - pb:o0] = from_lo
-        if from_hi is not None:
-            v[o1:o1 + pb] = from_hi
+        if not self.neighbours:
+            return
+        g = v.reshape(self.shape)
+        got = self.comm.exchange({nb: np.ascontiguousarray(g[snd]).reshape(-1) for nb, snd, _ in self.neighbours})
+        for nb, _, rcv in self.neighbours:
+            g[rcv] = got[nb].reshape(g[rcv].shape)
+
+    def gather_box(self):
+        """(global slices [z, y, x] of my owned block, local slices of it)"""
+        dim = len(self.cells)
+        gs, ls = [], []
+        for a in range(3):
+            if a < dim:
+                lo, hi, b0, b1 = self.ranges[a]
+                gs.append(slice(b0, b1)); ls.append(slice(b0 - lo, b1 - lo))
+            else:
+                gs.append(slice(0, 1)); ls.append(slice(0, 1))
+        return tuple(reversed(gs)), tuple(reversed(ls))
 
     def dot(self, a, b):
         return self.comm.allreduce(float(np.dot(a[self.owner], b[self.owner])), "sum")
@@ -347,15 +394,18 @@ class SlabRank:
         return u, (0 if converged else 1), steps, lin_its
 
 
-def run_threads(make_spec, cells, nranks, fn):
-    """Runs fn(SlabRank) on `nranks` threads; returns the per-rank results."""
+SlabRank = BoxRank      # the slab decomposition is the default partitioning of BoxRank
+
+
+def run_threads(make_spec, cells, nranks, fn, part=None):
+    """Runs fn(BoxRank) on `nranks` threads; returns the per-rank results."""
     shared = ThreadComm.Shared(nranks)
     out = [None] * nranks
     err = []
 
     def work(r):
         try:
-            out[r] = fn(SlabRank(make_spec, cells, ThreadComm(shared, r)))
+            out[r] = fn(BoxRank(make_spec, cells, ThreadComm(shared, r), part))
         except BaseException as e:       # noqa: BLE001
             err.append(e)
             shared.barrier.abort()
@@ -370,11 +420,16 @@ def run_threads(make_spec, cells, nranks, fn):
     return out
 
 
-def gather_owned(results, cells, nranks, b):
-    """Concatenate the owned layers of per-rank local vectors (x fastest) into the global vector."""
-    nf = int(np.prod(cells[:-1]))
-    parts = []
+def gather_owned(results, cells, nranks, b, part=None):
+    """Assemble the owned blocks of per-rank local vectors (x fastest) into the global vector."""
+    dim = len(cells)
+    part = tuple(part) if part is not None else problems.default_partitioning(dim, nranks)
+    c3 = tuple(cells) + (1,) * (3 - dim)
+    out = np.zeros((c3[2], c3[1], c3[0], b))
     for r, v in enumerate(results):
-        lo, hi, b0, b1 = problems.slab_partition(cells[-1], nranks, r)
-        parts.append(np.asarray(v).reshape(hi - lo, nf * b)[b0 - lo:b1 - lo].reshape(-1))
-    return np.concatenate(parts)
+        rng = problems.box_partition(cells, part, r) + [(0, 1, 0, 1)] * (3 - dim)
+        shape = tuple(rng[a][1] - rng[a][0] for a in (2, 1, 0)) + (b,)
+        gs = tuple(slice(rng[a][2], rng[a][3]) for a in (2, 1, 0))
+        ls = tuple(slice(rng[a][2] - rng[a][0], rng[a][3] - rng[a][0]) for a in (2, 1, 0))
+        out[gs] = np.asarray(v).reshape(shape)[ls]
+    return out.reshape(-1)

@@ -19,20 +19,20 @@ from oracle import oracle_py as O
 CELLS = (12, 10, 14)
 
 
-def _make_spec(slab):
-    return problems.twop_lens(CELLS, law="bc", heterogeneity_sigma=0.4, slab=slab, plane_rng=True)
+def _make_spec(box):
+    return problems.twop_lens(CELLS, law="bc", heterogeneity_sigma=0.4, box=box, plane_rng=True)
 
 
-def _perturb(spec, slab, seed=3):
-    """deterministic global perturbation, cut to the slab"""
+def _perturb(spec, box, seed=3):
+    """deterministic global perturbation, cut to the local box"""
     n = int(np.prod(CELLS))
     rng = np.random.RandomState(seed)
     sn = rng.uniform(0.0, 0.25, size=n)
     dp = rng.uniform(-40.0, 40.0, size=n)
-    if slab is not None:
-        nf = CELLS[0] * CELLS[1]
-        sn = sn.reshape(CELLS[2], nf)[slab[0]:slab[1]].reshape(-1)
-        dp = dp.reshape(CELLS[2], nf)[slab[0]:slab[1]].reshape(-1)
+    if box is not None:
+        sl = tuple(slice(*box[a]) for a in (2, 1, 0))
+        sn = sn.reshape(CELLS[2], CELLS[1], CELLS[0])[sl].reshape(-1)
+        dp = dp.reshape(CELLS[2], CELLS[1], CELLS[0])[sl].reshape(-1)
     u = spec.initial.copy()
     u[:, 0] += dp
     u[:, 1] = sn
@@ -41,8 +41,8 @@ def _perturb(spec, slab, seed=3):
 
 def _rank_job(rank_obj):
     """what every rank does: assemble its slab, solve to a tight tolerance, take one Newton solve"""
-    slab = (rank_obj.lo, rank_obj.hi) if rank_obj.comm.nranks > 1 else None
-    cur = _perturb(rank_obj.spec, slab).reshape(-1)
+    box = rank_obj.box if rank_obj.comm.nranks > 1 else None
+    cur = _perturb(rank_obj.spec, box).reshape(-1)
     prev = rank_obj.spec.initial.reshape(-1)
     res, jac = rank_obj.o.assemble(cur, prev)
     x, st, its, red = rank_obj.bicgstab(jac, res, reduction=1e-11, maxit=500)
@@ -52,12 +52,12 @@ def _rank_job(rank_obj):
             "owner": rank_obj.owner.copy(), "xg": xg, "stg": stg, "itsg": itsg, "redg": redg, "jac": jac}
 
 
-def _gloo_worker(rank, world, port, q):
+def _gloo_worker(rank, world, port, q, part=None):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     import torch.distributed as dist
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        out = _rank_job(D.SlabRank(_make_spec, CELLS, D.TorchComm()))
+        out = _rank_job(D.BoxRank(_make_spec, CELLS, D.TorchComm(), part))
         q.put((rank, out))
     finally:
         dist.barrier()
@@ -170,3 +170,83 @@ def test_two_processes_over_gloo_match_reference(reference_runs):
         assert got[r]["stg"] == 0 and got[r]["itsg"] == two[r]["itsg"] and np.array_equal(got[r]["xg"], two[r]["xg"])
         assert got[r]["nsteps"] == two[r]["nsteps"] and got[r]["lin_its"] == two[r]["lin_its"]
         assert np.array_equal(got[r]["u"], two[r]["u"])
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# general Grid.Partitioning "px py pz" (io/grid/gridmanager_yasp.hh:194-203): blocks with face, edge and corner neighbours
+# ------------------------------------------------------------------------------------------------------------------------
+BLOCK_PARTS = [(2, 1, 2), (2, 2, 2), (1, 3, 2)]
+
+
+def test_block_partition_layout():
+    """every cell has exactly one owner; a block holds its owned range plus one layer towards every neighbour; ranks are
+    numbered x fastest"""
+    for part in BLOCK_PARTS + [(3, 2, 1)]:
+        P = int(np.prod(part))
+        owners = np.zeros(CELLS[::-1], dtype=int)
+        for r in range(P):
+            rng = problems.box_partition(CELLS, part, r)
+            coord = problems.rank_coord(part, r)
+            assert r == coord[0] + part[0] * (coord[1] + part[1] * coord[2])
+            for a in range(3):
+                lo, hi, b0, b1 = rng[a]
+                assert lo == max(0, b0 - 1) and hi == min(CELLS[a], b1 + 1)
+                assert (b1 - b0) in (CELLS[a] // part[a], CELLS[a] // part[a] + 1)
+            owners[tuple(slice(rng[a][2], rng[a][3]) for a in (2, 1, 0))] += 1
+        assert np.all(owners == 1)
+
+
+@pytest.fixture(scope="module")
+def block_runs(reference_runs):
+    return {part: D.run_threads(_make_spec, CELLS, int(np.prod(part)), _rank_job, part) for part in BLOCK_PARTS}
+
+
+@pytest.mark.parametrize("part", BLOCK_PARTS)
+def test_block_decomposition_owned_rows_and_solution(reference_runs, block_runs, part):
+    """Owned residual rows equal the single-domain rows bit for bit; Schwarz-BiCGSTAB / GMRes converge to the single-domain
+    solution; after copyOwnerToAll every overlap copy (faces, edges, corners) equals its owner's value; same Newton count."""
+    single = reference_runs[0]
+    runs = block_runs[part]
+    P = int(np.prod(part))
+    assert np.array_equal(D.gather_owned([o["res"] for o in runs], CELLS, P, 2, part), single["res"])
+    assert single["st"] == 0 and all(o["st"] == 0 for o in runs)
+    x = D.gather_owned([o["x"] for o in runs], CELLS, P, 2, part)
+    assert np.linalg.norm(x - single["x"]) <= 1e-8 * np.linalg.norm(single["x"])
+    assert len({o["its"] for o in runs}) == 1 and runs[0]["its"] >= single["its"]
+    xg = D.gather_owned([o["xg"] for o in runs], CELLS, P, 2, part)
+    assert np.linalg.norm(xg - single["x"]) <= 1e-7 * np.linalg.norm(single["x"])
+    # overlap copies == owner values: every rank's FULL local box equals the gathered global vector there
+    glob = x.reshape(CELLS[2], CELLS[1], CELLS[0], 2)
+    for r, o in enumerate(runs):
+        rng = problems.box_partition(CELLS, part, r)
+        sl = tuple(slice(rng[a][0], rng[a][1]) for a in (2, 1, 0))
+        assert np.array_equal(o["x"].reshape(glob[sl].shape), glob[sl])
+    assert all(o["nst"] == 0 and o["nsteps"] == single["nsteps"] for o in runs)
+    u = D.gather_owned([o["u"] for o in runs], CELLS, P, 2, part).reshape(-1, 2)
+    us = single["u"].reshape(-1, 2)
+    assert np.linalg.norm(u[:, 0] - us[:, 0]) <= 1e-8 * np.linalg.norm(us[:, 0])
+    assert np.linalg.norm(u[:, 1] - us[:, 1]) <= 1e-8 * max(1.0, np.linalg.norm(us[:, 1]))
+
+
+def test_four_processes_over_gloo_block_partition(block_runs):
+    """world_size 4 over gloo with Grid.Partitioning "2 1 2": identical to the in-process reference (real messages to face and
+    edge neighbours)."""
+    import torch.multiprocessing as mp
+    part = (2, 1, 2)
+    ref = block_runs[part]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29870 + os.getpid() % 100
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 4, port, q, part)) for r in range(4)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=300) for _ in range(4))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # (gloo sums the four contributions of an all-reduce in its own order, so the iterates agree to rounding, not bit for bit)
+    for r in range(4):
+        assert got[r]["st"] == 0 and got[r]["its"] == ref[r]["its"]
+        assert np.linalg.norm(got[r]["x"] - ref[r]["x"]) <= 1e-9 * np.linalg.norm(ref[r]["x"])
+        assert got[r]["nsteps"] == ref[r]["nsteps"] and all(abs(a - b) <= 1 for a, b in zip(got[r]["lin_its"], ref[r]["lin_its"]))
+        assert np.linalg.norm(got[r]["u"] - ref[r]["u"]) <= 1e-8 * np.linalg.norm(ref[r]["u"])

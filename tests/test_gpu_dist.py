@@ -16,20 +16,20 @@ pytestmark = pytest.mark.gpu
 CELLS = (20, 18, 22)
 
 
-def _make_spec(slab):
+def _make_spec(box):
     from dumux_b200 import problems
-    return problems.twop_lens(CELLS, law="bc", heterogeneity_sigma=0.4, slab=slab, plane_rng=True)
+    return problems.twop_lens(CELLS, law="bc", heterogeneity_sigma=0.4, box=box, plane_rng=True)
 
 
-def _perturb(spec, slab, seed=3):
+def _perturb(spec, box, seed=3):
     n = int(np.prod(CELLS))
     rng = np.random.RandomState(seed)
     sn = rng.uniform(0.0, 0.25, size=n)
     dp = rng.uniform(-40.0, 40.0, size=n)
-    if slab is not None:
-        nf = CELLS[0] * CELLS[1]
-        sn = sn.reshape(CELLS[2], nf)[slab[0]:slab[1]].reshape(-1)
-        dp = dp.reshape(CELLS[2], nf)[slab[0]:slab[1]].reshape(-1)
+    if box is not None:
+        sl = tuple(slice(*box[a]) for a in (2, 1, 0))
+        sn = sn.reshape(CELLS[2], CELLS[1], CELLS[0])[sl].reshape(-1)
+        dp = dp.reshape(CELLS[2], CELLS[1], CELLS[0])[sl].reshape(-1)
     u = spec.initial.copy()
     u[:, 0] += dp
     u[:, 1] = sn
@@ -37,8 +37,8 @@ def _perturb(spec, slab, seed=3):
 
 
 def _cpu_rank_job(rank_obj):
-    slab = (rank_obj.lo, rank_obj.hi) if rank_obj.comm.nranks > 1 else None
-    cur = _perturb(rank_obj.spec, slab).reshape(-1)
+    box = rank_obj.box if rank_obj.comm.nranks > 1 else None
+    cur = _perturb(rank_obj.spec, box).reshape(-1)
     prev = rank_obj.spec.initial.reshape(-1)
     res, jac = rank_obj.o.assemble(cur, prev)
     x, st, its, red = rank_obj.bicgstab(jac, res, reduction=1e-10, maxit=500)
@@ -48,30 +48,45 @@ def _cpu_rank_job(rank_obj):
             "xg": xg, "stg": stg, "itsg": itsg, "redg": redg}
 
 
-def _gpu_worker(rank, world, uid, q):
+def _gpu_worker(rank, world, uid, q, part=None):
     try:
         from dumux_b200 import binding as B
         from dumux_b200 import problems
-        lo, hi, b0, b1 = problems.slab_partition(CELLS[2], world, rank)
-        spec = _make_spec((lo, hi))
-        eng = B.Engine(spec, device=rank, nccl_uid=uid, rank=rank, nranks=world)
-        assert (eng.own_begin, eng.own_end) == (b0 - lo, b1 - lo)
-        cur = _perturb(spec, (lo, hi))
+        part_ = part if part is not None else problems.default_partitioning(3, world)
+        rng = problems.box_partition(CELLS, part_, rank)
+        box = [(r[0], r[1]) for r in rng]
+        spec = _make_spec(box)
+        eng = B.Engine(spec, device=rank, nccl_uid=uid, rank=rank, nranks=world, part=part)
+        assert [(int(eng.own_lo[a]), int(eng.own_hi[a])) for a in range(3)] == [(r[2] - r[0], r[3] - r[0]) for r in rng]
+        cur = _perturb(spec, box)
         res, jac = eng.assemble(cur, spec.initial)
         x, st, its, red = eng.solve(jac, res, reduction=1e-10, maxit=500)
         eng.set_linear_solver("gmres", 10)
         xg, stg, itsg, redg = eng.solve(jac, res, reduction=1e-10, maxit=500)
         eng.set_linear_solver("bicgstab")
-        # halo exchange primitive: fill a vector with the rank id, exchange, look at the overlap planes
+        # halo exchange primitive: fill a vector with the rank id, exchange: every cell then carries its OWNER's rank id
         v = np.full(eng.n * eng.b, float(rank))
         eng.upload(B.VEC_WORK1, v)
         eng.halo_exchange(B.VEC_WORK1)
-        halo = eng.download(B.VEC_WORK1).reshape(hi - lo, -1)[:, 0].copy()
+        halo = eng.download(B.VEC_WORK1).reshape(-1, eng.b)[:, 0].copy()
         nrm = eng.norm(B.VEC_RESIDUAL)
         u, nst, rep = eng.newton(spec.initial, spec.initial)
+        # cross-rank failure agreement (assembly/fvassembler.hh:504-509 comm.min): a NaN on ONE rank makes EVERY rank
+        # return DMX_STATUS_NONFINITE from the assembly instead of leaving the others in the next collective
+        bad = spec.initial.copy()
+        if rank == world - 1:
+            bad[eng.n // 2, 0] = np.nan
+        eng.upload(B.VEC_CUR, bad)
+        st_bad = eng.assemble_device(True)
+        p = eng.newton_params()
+        st_step = eng.newton_step(p)[0]
+        # ... and the engine is usable afterwards (the dt-halving retry of NewtonSolver::solve)
+        eng.upload(B.VEC_CUR, spec.initial)
+        st_ok = eng.assemble_device(True)
         q.put((rank, {"res": res, "jac": jac, "x": x, "st": st, "its": its, "halo": halo, "norm": nrm, "u": u, "nst": nst,
                       "nsteps": rep.newton_iterations, "lin_its": [rep.linear_iterations[i] for i in range(rep.newton_iterations)],
-                      "launches": eng.launches(), "xg": xg, "stg": stg, "itsg": itsg, "redg": redg}))
+                      "launches": eng.launches(), "xg": xg, "stg": stg, "itsg": itsg, "redg": redg,
+                      "st_bad": st_bad, "st_step": st_step, "st_ok": st_ok}))
         eng.close()
     except BaseException as e:      # noqa: BLE001
         import traceback
@@ -79,8 +94,8 @@ def _gpu_worker(rank, world, uid, q):
         raise
 
 
-@pytest.mark.parametrize("world", [2])
-def test_slab_decomposed_newton_step_matches_cpu_reference(world):
+@pytest.mark.parametrize("world,part", [(2, None), (2, (2, 1, 1)), (4, (2, 1, 2)), (8, (2, 2, 2))])
+def test_decomposed_newton_step_matches_cpu_reference(world, part):
     import torch
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs (run under gpurun --gpus {world})")
@@ -88,11 +103,11 @@ def test_slab_decomposed_newton_step_matches_cpu_reference(world):
     from dumux_b200 import binding as B
     from dumux_b200 import problems
     from oracle import dist_oracle as D
-    ref = D.run_threads(_make_spec, CELLS, world, _cpu_rank_job)
+    ref = D.run_threads(_make_spec, CELLS, world, _cpu_rank_job, part)
     uid = B.Engine.nccl_unique_id()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_gpu_worker, args=(r, world, uid, q)) for r in range(world)]
+    procs = [ctx.Process(target=_gpu_worker, args=(r, world, uid, q, part)) for r in range(world)]
     for p in procs:
         p.start()
     got = dict(q.get(timeout=600) for _ in range(world))
@@ -100,27 +115,28 @@ def test_slab_decomposed_newton_step_matches_cpu_reference(world):
         p.join(timeout=120)
     for r in range(world):
         assert "error" not in got[r], got[r].get("error")
-    nf2 = CELLS[0] * CELLS[1] * 2
+    part_ = part if part is not None else problems.default_partitioning(3, world)
+    # owner rank of every global cell
+    owner_of = np.zeros(CELLS[::-1])
+    for r in range(world):
+        rng = problems.box_partition(CELLS, part_, r)
+        owner_of[tuple(slice(rng[a][2], rng[a][3]) for a in (2, 1, 0))] = r
     for r in range(world):
         g, c = got[r], ref[r]
-        lo, hi, b0, b1 = problems.slab_partition(CELLS[2], world, r)
+        rng = problems.box_partition(CELLS, part_, r)
         # assembly of the local box incl. overlap rows (no scvf on the processor boundary): bit-exact
         assert np.array_equal(g["res"], c["res"]) and np.array_equal(g["jac"], c["jac"])
-        # halo: overlap planes carry the neighbour's rank id, owned planes mine
-        expect = np.full(hi - lo, float(r))
-        if lo > 0:
-            expect[0] = r - 1
-        if hi < CELLS[2]:
-            expect[-1] = r + 1
-        assert np.array_equal(g["halo"], expect)
+        # halo: after copyOwnerToAll every local cell (faces, edges, corners of the overlap included) carries its owner's id
+        assert np.array_equal(g["halo"], owner_of[tuple(slice(rng[a][0], rng[a][1]) for a in (2, 1, 0))].reshape(-1))
         # owner-masked, all-reduced norm is the same number on every rank
         assert g["norm"] == got[0]["norm"]
         # Schwarz-BiCGSTAB: same iteration count, solution at the solver tolerance
-        assert g["st"] == 0 and c["st"] == 0 and g["its"] == c["its"], (g["its"], c["its"])
+        assert g["st"] == 0 and c["st"] == 0 and abs(g["its"] - c["its"]) <= (0 if world == 2 else 1), (g["its"], c["its"])
         assert np.linalg.norm(g["x"] - c["x"]) <= 1e-7 * np.linalg.norm(c["x"])
         # Schwarz-GMRes(10) (ILURestartedGMResIstlSolver on the overlapping decomposition): same count, reduction and solution
-        assert g["stg"] == 0 and c["stg"] == 0 and g["itsg"] == c["itsg"], (g["itsg"], c["itsg"])
-        assert g["redg"] == pytest.approx(c["redg"], rel=1e-5)
+        assert g["stg"] == 0 and c["stg"] == 0 and abs(g["itsg"] - c["itsg"]) <= (0 if world == 2 else 1), (g["itsg"], c["itsg"])
+        if g["itsg"] == c["itsg"]:
+            assert g["redg"] == pytest.approx(c["redg"], rel=1e-5)
         assert np.linalg.norm(g["xg"] - c["xg"]) <= 1e-7 * np.linalg.norm(c["xg"])
         assert np.linalg.norm(g["xg"] - g["x"]) <= 1e-6 * np.linalg.norm(g["x"])          # both solve the same global system
         # Newton: same iteration count, fields to 1e-8
@@ -129,8 +145,10 @@ def test_slab_decomposed_newton_step_matches_cpu_reference(world):
         assert np.linalg.norm(ug[:, 0] - uc[:, 0]) <= 1e-8 * np.linalg.norm(uc[:, 0])
         assert np.linalg.norm(ug[:, 1] - uc[:, 1]) <= 1e-8 * max(1.0, np.linalg.norm(uc[:, 1]))
         assert g["launches"] > 0
+        # failure agreement: every rank reports the NaN that only the last rank holds, and recovers
+        assert g["st_bad"] == B.STATUS_NONFINITE and g["st_step"] == B.STATUS_NONFINITE and g["st_ok"] == 0
     # global norm = sqrt(sum of owned squares)
-    owned = D.gather_owned([ref[r]["res"] for r in range(world)], CELLS, world, 2)
+    owned = D.gather_owned([ref[r]["res"] for r in range(world)], CELLS, world, 2, part)
     assert abs(got[0]["norm"] - np.linalg.norm(owned)) <= 1e-12 * np.linalg.norm(owned)
 
 
