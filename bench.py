@@ -12,11 +12,16 @@ all K steps do identical work.  metric = degrees of freedom (cells x 2) / second
 
 N = 1: 256^3 cells (the configuration the metric is quoted on).  N > 1: weak scaling, 256 x 256 x (256 N) cells slab-
 decomposed along z with overlap 1 (Grid.Partitioning "1 1 N"), per-rank ILU0 (overlapping Schwarz) -- pass --cells to
-change the per-GPU cube edge, --global-z to fix the total number of layers instead (strong scaling).
+change the per-GPU cube edge, --global-cells / --part to run any global box on any Grid.Partitioning.
 
-The JSON line also carries: `roofline` (dominant roofline-graded kernel, CUDA-event timed inside the timed region),
-`kernels` (every kernel class the same way), `e2e` (the same step through the host-buffer C-ABI call: pinned host
-curSol -> H2D -> step -> D2H), `cpu_baseline` (the oracle port on this box's host cores, bounded sample), `clocks`.
+Besides the headline the JSON line carries
+  `parity_check`  a small decomposed Newton solve on the SAME N ranks against the CPU multi-rank oracle, run before the timed
+                  region (Newton count, BiCGSTAB counts, fields; N > 1: slabs and blocks, NaN-injection failure agreement);
+                  the run aborts if it is off
+  `strong_512`    BASELINE config 4: the 512^3 problem on these N GPUs (block decomposition, strong scaling), its own timed region
+  `roofline` / `kernels`  CUDA-event timers of every kernel class inside the timed region
+  `e2e`           the same step through the host-buffer C-ABI call (pinned host curSol -> H2D -> step -> D2H)
+  `cpu_baseline`  the oracle port on this box's host cores (bounded, labelled sample), `clocks`.
 """
 from __future__ import annotations
 
@@ -36,6 +41,7 @@ if ROOT not in sys.path:
 METRIC = "Newton-step MDOF/s (assembly+BiCGSTAB) 2p CCTpfa"
 UNIT = "MDOF/s"
 LIN_MAXIT = 2000          # LinearSolver.MaxIterations: ILU0-BiCGSTAB needs > 250 iterations at 256^3 (no AMG on this path)
+STRONG_PART = {1: (1, 1, 1), 2: (1, 1, 2), 4: (1, 2, 2), 8: (2, 2, 2)}      # Grid.Partitioning of the strong-scaling region
 
 
 def log(*a):
@@ -52,6 +58,14 @@ os.dup2(2, 1)
 def emit(line):
     _RESULT_OUT.write(json.dumps(line) + "\n")
     _RESULT_OUT.flush()
+
+
+def workload_config(cells, edge):
+    """`config` of a line: the workload only, worded identically by both arms (run-specific facts go into `run`)."""
+    return {"workload": f"2p immiscible CCTpfa lens/infiltration, {cells[0]}x{cells[1]}x{cells[2]} cells ({edge}^3 per GPU), Brooks-Corey, "
+                        f"lognormal K multiplier sigma 0.5, numeric differentiation (forward, eps 1e-10), 2x2 BCRS blocks",
+            "step": "one Newton iteration: assemble + ILU0 factor + BiCGSTAB(1e-6) + update, from the hydrostatic initial state, dt 250 s",
+            "linear_solver": f"ILU0-BiCGSTAB, reduction 1e-6, maxit {LIN_MAXIT}"}
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -125,11 +139,38 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------------------
-# CPU side: the oracle port (reference algorithm restated), bounded sample of the same workload
+# CPU side: the oracle port (reference algorithm restated).  Timing legs use the -O3 -march=native build of the oracle
+# (the reference's own flags, cmake.opts:17-27), compiled on the machine that runs it.
 # ----------------------------------------------------------------------------------------------------------
+def use_fast_oracle():
+    """Build oracle/_fast/liboracle_fast.so here and make oracle_py load it; falls back to the canonical -O2 build."""
+    if "oracle.oracle_py" in sys.modules:
+        return "canonical -O2 build (already loaded)"
+    try:
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-s", "fast"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        path = os.path.join(ROOT, "oracle", "_fast", "liboracle_fast.so")
+        if os.path.exists(path):
+            os.environ["ORACLE_LIB"] = path
+            return "g++ -O3 -march=native"
+    except Exception:
+        pass
+    return "canonical -O2 build"
+
+
+def balanced_partition(nranks):
+    """nranks (a power of two) as px*py*pz with the factors as equal as possible, z largest"""
+    p = [1, 1, 1]
+    a = 2
+    while nranks > 1:
+        p[a] *= 2
+        nranks //= 2
+        a = (a - 1) % 3
+    return tuple(p)
+
+
 def cpu_newton_step(edge, steps, warmup, threads):
     """Times `steps` Newton iterations (assemble + ILU0 + BiCGSTAB + update) of the 2p lens problem at edge^3 cells with
-    the oracle.  Assembly runs on `threads` OpenMP threads (DuMux's coloured parallelFor), the linear solve is the
+    the oracle on ONE rank.  Assembly runs on `threads` OpenMP threads (DuMux's coloured parallelFor), the linear solve is the
     sequential dune-istl algorithm (one thread per rank, as in the reference)."""
     import numpy as np
     from dumux_b200 import problems
@@ -154,27 +195,90 @@ def cpu_newton_step(edge, steps, warmup, threads):
     return {"value": dofs / sec / 1e6, "sec_per_step": sec, "bicgstab_iterations": its_seen[-1], "dofs": dofs}
 
 
+def cpu_newton_step_ranks(edge, ranks):
+    """ONE Newton iteration of the edge^3 problem the way DuMux runs it under `mpirun -np ranks`: block decomposition with
+    overlap 1, every rank assembles its box and the Krylov solve is dune-istl's overlapping Schwarz (per-rank ILU0, owner-masked
+    dots, copyOwnerToAll) -- oracle/dist_oracle.py with one thread per rank."""
+    import numpy as np
+    from dumux_b200 import problems
+    from oracle import dist_oracle as D
+    cells = (edge, edge, edge)
+    part = balanced_partition(ranks)
+
+    def make(box):
+        return problems.twop_lens(cells, law="bc", heterogeneity_sigma=0.5, box=box, plane_rng=True)
+
+    def job(ro):
+        u0 = ro.spec.initial.reshape(-1).copy()
+        ro.comm.allreduce(0.0)                       # all ranks set up: start the clock together
+        t0 = time.perf_counter()
+        res, jac = ro.o.assemble(u0, u0)
+        t1 = time.perf_counter()
+        dx, st, its, red = ro.bicgstab(jac, res, 1e-6, LIN_MAXIT)
+        u = u0 + (-1.0) * dx
+        sh = np.abs(u - u0) / np.maximum(1.0, np.abs(u + u0) * 0.5)
+        shift = ro.comm.allreduce(float(sh[ro.owner].max()), "max")
+        t2 = time.perf_counter()
+        return {"st": st, "its": its, "t_assemble": t1 - t0, "t_total": t2 - t0, "shift": shift}
+
+    out = D.run_threads(make, cells, ranks, job, part if ranks > 1 else None, num_threads=1 if ranks > 1 else 0)
+    assert all(o["st"] == 0 for o in out) and out[0]["shift"] > 0
+    sec = max(o["t_total"] for o in out)
+    dofs = 2 * edge ** 3
+    return {"value": dofs / sec / 1e6, "sec_per_step": sec, "bicgstab_iterations": out[0]["its"], "dofs": dofs, "part": part,
+            "sec_assemble": max(o["t_assemble"] for o in out)}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
-    edge = args.cpu_edge
-    r = cpu_newton_step(edge, args.steps, args.warmup, cores)
-    sample = (f"2p lens {edge}^3 cells (bounded sample of the {args.cells}^3 workload), one Newton iteration per step, "
-              f"{r['bicgstab_iterations']} BiCGSTAB iterations; oracle port of the DuMux/dune-istl algorithm: assembly on {cores} "
-              f"OpenMP threads, ILU0/BiCGSTAB sequential (1 rank, no MPI in this image)")
+    flags = use_fast_oracle()
+    edge = args.cpu_edge if args.cpu_edge else args.cells          # default: the configuration itself, not a sample
+    ranks = 1
+    while ranks * 2 <= min(cores, args.cpu_ranks):
+        ranks *= 2
+    if edge < 24:
+        ranks = 1
+    t0 = time.time()
+    # The whole run is ONE step whatever --steps says: a 256^3 Newton iteration is minutes of CPU time, and every step would be
+    # the same work (steps/warmup of the line say what was done).  The driver calls this arm once per N of the scaling run with
+    # identical CPU work, so the measurement is kept under gpurun_out/ (scratch of THIS box, never shipped) and re-used there.
+    cache = os.path.join(ROOT, "gpurun_out", f"reference_arm_{edge}_{ranks}.json")
+    r = None
+    if not args.no_cache:
+        try:
+            r = json.load(open(cache))
+            r["part"] = tuple(r["part"])
+            r["cached"] = True
+        except Exception:
+            r = None
+    if r is None:
+        r = cpu_newton_step_ranks(edge, ranks)
+        try:
+            os.makedirs(os.path.dirname(cache), exist_ok=True)
+            json.dump(r, open(cache, "w"))
+        except Exception:
+            pass
+    log(f"[bench] reference arm: {edge}^3 on {ranks} Schwarz ranks {r['part']}: {r['sec_per_step']:.1f} s per Newton iteration, "
+        f"{r['bicgstab_iterations']} BiCGSTAB iterations (total {time.time() - t0:.0f} s incl. set-up)")
+    whole = edge == args.cells
+    sample = (f"{'the full configuration' if whole else 'bounded sample'}: one Newton iteration of the 2p lens problem at {edge}^3 cells, "
+              f"{r['bicgstab_iterations']} BiCGSTAB iterations, {r['sec_per_step']:.1f} s; oracle port of the DuMux/dune-istl algorithm ({flags}) run as "
+              f"{ranks} overlapping-Schwarz ranks (Grid.Partitioning {r['part']}, overlap 1, per-rank ILU0 -- what `mpirun -np {ranks}` does in "
+              f"DuMux; one thread per rank, no MPI in this image), {cores} host cores visible"
+              + ("" if args.gpus == 1 else f"; the N-GPU arm runs {args.gpus}x this many cells, the CPU arm the per-GPU share"))
+    cells = (edge, edge, edge)
     line = {
-        "impl": "reference", "metric": f"{METRIC} {args.cells}^3", "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["sec_per_step"] * 1e3, "higher_is_better": True,
+        "impl": "reference", "metric": f"{METRIC} {edge}^3", "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": 1, "warmup": 0, "ms_per_step": r["sec_per_step"] * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        # the arm's workload (same wording as the B200 arm's `config`), timed on a bounded sample of it
-        "config": {"workload": f"2p immiscible CCTpfa lens/infiltration, {args.cells}x{args.cells}x{args.cells} cells ({args.cells}^3 per GPU), "
-                               f"Brooks-Corey, lognormal K multiplier sigma 0.5, numeric differentiation (forward, eps 1e-10), 2x2 BCRS blocks",
-                   "step": "one Newton iteration: assemble + ILU0 factor + BiCGSTAB(1e-6) + update, from the hydrostatic initial state, dt 250 s",
-                   "linear_solver": f"ILU0-BiCGSTAB, reduction 1e-6, maxit {LIN_MAXIT}", "bicgstab_iterations_per_step": r["bicgstab_iterations"],
-                   "parallelism": "host cores of the GPU box", "sample_cells": edge ** 3},
-        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": workload_config(cells, edge),
+        "run": {"bicgstab_iterations_per_step": r["bicgstab_iterations"], "parallelism": f"{ranks} CPU ranks {r['part']}, overlap 1",
+                "assemble_s": r["sec_assemble"], "requested_steps": args.steps, "requested_warmup": args.warmup,
+                "reused_measurement_of_an_earlier_invocation_on_this_box": bool(r.get("cached", False))},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": ranks, "kind": "port", "sample": sample},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -185,68 +289,165 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------------------
-def run_b200(args):
+class Comm:
+    """torch.distributed plumbing of the bench (NCCL): barrier, max-reduce of timings, object gather, fresh ncclUniqueIds"""
+
+    def __init__(self):
+        import torch
+        self.torch = torch
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local_rank)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+            self.dist = dist
+
+    def uid(self):
+        """a fresh ncclUniqueId for one engine's communicator, broadcast from rank 0"""
+        if self.dist is None:
+            return None
+        from dumux_b200 import binding as B
+        torch = self.torch
+        buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if self.rank == 0:
+            buf.copy_(torch.frombuffer(bytearray(B.Engine.nccl_unique_id()), dtype=torch.uint8))
+        self.dist.broadcast(buf, 0)
+        return bytes(buf.cpu().numpy().tobytes())
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.dist is not None:
+            self.dist.barrier()
+
+    def maxreduce(self, x):
+        if self.dist is None:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def gather(self, obj):
+        if self.dist is None:
+            return [obj]
+        out = [None] * self.world
+        self.dist.all_gather_object(out, obj)
+        return out
+
+    def close(self):
+        if self.dist is not None:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+def parity_check(comm):
+    """A small decomposed Newton solve on these N ranks against the CPU multi-rank oracle (oracle/dist_oracle.py, N threads on
+    rank 0): Newton count, BiCGSTAB counts per Newton iteration, fields of the owned cells.  N > 1: the slab layout of the headline
+    AND the block layout of the strong-scaling region, plus the failure agreement (a NaN on one rank -> DMX_STATUS_NONFINITE on
+    every rank, no hang).  Matches newtonsolver.hh:976-1072, linearsolvertraits.hh:79-91, fvassembler.hh:504-509."""
+    import numpy as np
+    from dumux_b200 import binding as B
+    from dumux_b200 import problems
+    world, rank = comm.world, comm.rank
+    out = {"ranks": world, "layouts": []}
+    layouts = [None] if world == 1 else [None, STRONG_PART.get(world, balanced_partition(world))]
+    ok_all = True
+    for part in layouts:
+        part_ = part if part is not None else problems.default_partitioning(3, world)
+        cells = tuple(24 * p if p > 1 else 32 for p in part_) if part is not None else (32, 32, 16 * world)
+
+        def make(box):
+            return problems.twop_lens(cells, law="bc", heterogeneity_sigma=0.4, box=box, plane_rng=True)
+
+        rng = problems.box_partition(cells, part_, rank)
+        box = [(r[0], r[1]) for r in rng] if world > 1 else None
+        spec = make(box)
+        eng = B.Engine(spec, device=comm.local_rank, nccl_uid=comm.uid(), rank=rank, nranks=world, part=part)
+        u, st, rep = eng.newton(spec.initial, spec.initial)
+        mine = {"st": st, "nsteps": rep.newton_iterations, "lin_its": [rep.linear_iterations[i] for i in range(rep.newton_iterations)],
+                "u": u}
+        agree = None
+        if world > 1:
+            bad = spec.initial.copy()
+            if rank == world - 1:
+                bad[eng.n // 2, 0] = np.nan
+            eng.upload(B.VEC_CUR, bad)
+            mine["st_bad"] = eng.assemble_device(True)
+            eng.upload(B.VEC_CUR, spec.initial)
+            mine["st_after"] = eng.assemble_device(True)
+        eng.close()
+        got = comm.gather(mine)
+        entry = None
+        if rank == 0:
+            from oracle import dist_oracle as D
+
+            def job(ro):
+                uu, nst, nsteps, lin_its = ro.newton(ro.spec.initial, ro.spec.initial)
+                return {"u": uu, "st": nst, "nsteps": nsteps, "lin_its": lin_its}
+
+            ref = D.run_threads(make, cells, world, job, part)
+            ug = D.gather_owned([g["u"] for g in got], cells, world, 2, part).reshape(-1, 2)
+            uc = D.gather_owned([c["u"] for c in ref], cells, world, 2, part).reshape(-1, 2)
+            relp = float(np.linalg.norm(ug[:, 0] - uc[:, 0]) / np.linalg.norm(uc[:, 0]))
+            rels = float(np.linalg.norm(ug[:, 1] - uc[:, 1]) / max(1.0, np.linalg.norm(uc[:, 1])))
+            its_g, its_c = got[0]["lin_its"], ref[0]["lin_its"]
+            if world > 1:
+                agree = all(g["st_bad"] == B.STATUS_NONFINITE and g["st_after"] == 0 for g in got)
+            entry = {"cells": list(cells), "partitioning": list(part_), "newton_its": got[0]["nsteps"], "newton_its_oracle": ref[0]["nsteps"],
+                     "newton_its_equal": all(g["st"] == 0 and g["nsteps"] == c["nsteps"] for g, c in zip(got, ref)),
+                     "bicgstab_its": its_g, "bicgstab_its_oracle": its_c,
+                     "bicgstab_its_equal": its_g == its_c,
+                     "bicgstab_its_max_diff": max([abs(a - b) for a, b in zip(its_g, its_c)] + [abs(len(its_g) - len(its_c)) * 999]),
+                     "field_rel_l2": max(relp, rels), "failure_agreement": agree}
+            # BiCGSTAB counts may move by one where the reduction order of the all-reduced dots differs (N > 2); fields 1e-8
+            ok = entry["newton_its_equal"] and entry["bicgstab_its_max_diff"] <= (0 if world <= 2 else 1) and entry["field_rel_l2"] <= 1e-8 \
+                and (agree is None or agree)
+            entry["ok"] = bool(ok)
+            ok_all = ok_all and ok
+            out["layouts"].append(entry)
+    verdict = comm.gather(ok_all if rank == 0 else None)[0]
+    if rank == 0:
+        first = out["layouts"][0]
+        out.update(newton_its_equal=all(e["newton_its_equal"] for e in out["layouts"]),
+                   bicgstab_its_equal=all(e["bicgstab_its_equal"] for e in out["layouts"]),
+                   field_rel_l2=max(e["field_rel_l2"] for e in out["layouts"]),
+                   failure_agreement=first["failure_agreement"], ok=bool(verdict))
+        log(f"[bench] parity_check: {json.dumps(out)}")
+    if not verdict:
+        raise SystemExit("bench.py: parity_check against the CPU oracle FAILED -- not timing a wrong result")
+    return out
+
+
+def measure(comm, cells, upper, part, steps, warmup, e2e=True, label="bench"):
+    """One timed region: `steps` device-resident Newton iterations of the lens problem on `cells` (global), decomposed by
+    `part`; returns the numbers of the JSON line."""
     import numpy as np
     import torch
     from dumux_b200 import problems
     from dumux_b200 import binding as B
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.gpus > 1 and world == 1:
-        # convenience: re-launch under torchrun
-        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
-               "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + sys.argv[1:]
-        return subprocess.call(cmd)
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device visible; the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local_rank)
-    dist = None
-    uid = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            buf.copy_(torch.frombuffer(bytearray(B.Engine.nccl_unique_id()), dtype=torch.uint8))
-        dist.broadcast(buf, 0)
-        uid = bytes(buf.cpu().numpy().tobytes())
-
-    edge = args.cells
-    nz_global = args.global_z if args.global_z else edge * world
-    cells = (edge, edge, nz_global)
-    # physical domain: the C3 box [0,6]x[0,4]x[0,4] per 256-layer cube, stretched in z with the number of layers
-    upper = (6.0, 4.0, 4.0 * nz_global / edge)
-    lo, hi, b0, b1 = problems.slab_partition(nz_global, world, rank)
+    world, rank = comm.world, comm.rank
+    part_ = part if part is not None else problems.default_partitioning(3, world)
+    rng = problems.box_partition(cells, part_, rank)
+    box = [(r[0], r[1]) for r in rng] if world > 1 else None
     t0 = time.time()
-    spec = problems.twop_lens(cells, law="bc", upper=upper, lower=(0.0, 0.0, 0.0), heterogeneity_sigma=0.5, dt=250.0,
-                              slab=(lo, hi) if world > 1 else None, plane_rng=True)
-    eng = B.Engine(spec, device=local_rank, nccl_uid=uid, rank=rank, nranks=world)
+    spec = problems.twop_lens(cells, law="bc", upper=upper, lower=(0.0, 0.0, 0.0), heterogeneity_sigma=0.5, dt=250.0, box=box, plane_rng=True)
+    eng = B.Engine(spec, device=comm.local_rank, nccl_uid=comm.uid(), rank=rank, nranks=world, part=part)
     n_local, b = eng.n, eng.b
-    n_owned = edge * edge * (b1 - b0)
-    dofs_global = edge * edge * nz_global * b
+    dofs_global = int(np.prod(cells)) * b
     if rank == 0:
-        log(f"[bench] set-up {time.time() - t0:.1f} s: global cells {cells}, rank 0 holds {n_local} cells ({n_owned} owned), nnzb {eng.nnzb}")
-
+        log(f"[{label}] set-up {time.time() - t0:.1f} s: global cells {cells}, partitioning {part_}, rank 0 holds {n_local} cells, nnzb {eng.nnzb}")
     u0 = torch.from_numpy(np.ascontiguousarray(spec.initial.reshape(-1))).pin_memory()
     uh = torch.empty_like(u0).pin_memory()
+    del spec
     eng.upload(B.VEC_PREV, u0)
     eng.upload(B.VEC_WORK1, u0)          # device copy of the start state
     prm = eng.newton_params(lin_maxit=LIN_MAXIT)
 
     def barrier():
         eng.synchronize()
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-
-    def maxreduce(x):
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        comm.barrier()
 
     def device_step():
         eng.copy(B.VEC_CUR, B.VEC_WORK1)
@@ -262,14 +463,13 @@ def run_b200(args):
             raise SystemExit(f"bench.py: host Newton step failed with status {st}")
         return its, shift
 
-    # ---- warm-up ----
-    for _ in range(args.warmup):
+    its = shift = 0
+    for _ in range(warmup):
         its, shift, *_ = device_step()
     if rank == 0:
-        log(f"[bench] warm-up done: {its} BiCGSTAB iterations per step, shift {shift:.3e}")
+        log(f"[{label}] warm-up done: {its} BiCGSTAB iterations per step, shift {shift:.3e}")
 
-    # ---- timed region: K device-resident steps ----
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(comm.local_rank)
     barrier()
     launches0 = eng.launches()
     eng.profile(True)
@@ -278,7 +478,7 @@ def run_b200(args):
     eng.timer_start()
     wall0 = time.perf_counter()
     buckets = [0.0, 0.0, 0.0]
-    for _ in range(args.steps):
+    for _ in range(steps):
         its, shift, a, s, u = device_step()
         buckets[0] += a; buckets[1] += s; buckets[2] += u
     ms_total = eng.timer_stop()
@@ -290,46 +490,39 @@ def run_b200(args):
                                                 ("ilu0_apply", B.K_ILU_APPLY), ("ilu0_factor", B.K_ILU_FACTOR),
                                                 ("blas1", B.K_BLAS1), ("halo", B.K_HALO))}
     eng.profile(False)
-    ms_total = maxreduce(ms_total)
-    ms_per_step = ms_total / args.steps
-    value = dofs_global / (ms_per_step * 1e-3) / 1e6
+    ms_total = comm.maxreduce(ms_total)
+    ms_per_step = ms_total / steps
+    res = {"cells": cells, "part": part_, "n_local": n_local, "nnzb": eng.nnzb, "b": b, "dofs_global": dofs_global, "its": its,
+           "ms_per_step": ms_per_step, "value": dofs_global / (ms_per_step * 1e-3) / 1e6, "buckets": [x / steps for x in buckets],
+           "wall_ms_per_step": wall * 1e3 / steps, "launches": int(launches), "clocks": clocks, "prof": prof, "ms_total": ms_total,
+           "vec_bytes": int(u0.numel() * 8)}
+    if e2e:
+        for _ in range(2):
+            host_step()
+        barrier()
+        eng.timer_start()
+        e2e_steps = max(2, min(steps, 3))
+        for _ in range(e2e_steps):
+            host_step()
+        ms_e2e = comm.maxreduce(eng.timer_stop()) / e2e_steps
+        barrier()
+        assert float((uh - u0).abs().max()) > 0.0           # the step really came back to the host
+        res["e2e_ms"] = ms_e2e
+        res["e2e_value"] = dofs_global / (ms_e2e * 1e-3) / 1e6
+    eng.close()
+    del eng, u0, uh
+    torch.cuda.empty_cache()
+    return res
 
-    # ---- e2e: the same step through the host-buffer ABI call ----
-    for _ in range(2):
-        host_step()
-    barrier()
-    eng.timer_start()
-    e2e_steps = max(2, min(args.steps, 3))
-    for _ in range(e2e_steps):
-        host_step()
-    ms_e2e = maxreduce(eng.timer_stop()) / e2e_steps
-    barrier()
-    e2e_value = dofs_global / (ms_e2e * 1e-3) / 1e6
-    assert float((uh - u0).abs().max()) > 0.0           # the step really came back to the host
 
-    # ---- roofline of the graded kernels, from the in-region event timers ----
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    ab = algorithmic_bytes(n_local, eng.nnzb, b)
-    # DRAM traffic per launch from the committed `ncu --set full` capture (profiles/traffic.json), which was taken on the default
-    # 256^3 single-GPU workload: reported only when this run has that per-GPU size, null otherwise
-    traffic = {}
-    if edge == 256 and n_local == 256 ** 3:
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        except Exception:
-            pass
+def kernel_table(res, peak, traffic):
+    ab = algorithmic_bytes(res["n_local"], res["nnzb"], res["b"])
     kernels = {}
-    for name, (ms, units) in prof.items():
+    for name, (ms, units) in res["prof"].items():
         if units == 0:
             continue
         avg = ms / units
-        k = {"launches_timed": units, "avg_ms": avg, "share_of_step": ms / ms_total if ms_total > 0 else None}
+        k = {"launches_timed": units, "avg_ms": avg, "share_of_step": ms / res["ms_total"] if res["ms_total"] > 0 else None}
         if name in ab:
             ach = ab[name] / (avg * 1e-3) / 1e9
             k.update(bound="hbm", achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, algorithmic_bytes=ab[name],
@@ -340,7 +533,50 @@ def run_b200(args):
                          note="read-dominated stream: the peak is the measured COPY bandwidth (half writes), pure reads run above it; "
                               "against the nominal 8000 GB/s the fraction is %.2f" % (ach / 8000.0))
         kernels[name] = k
-    # the dominant kernel of the step (largest share of the timed region) among the HBM-bound kernel classes
+    return kernels
+
+
+def run_b200(args):
+    import torch
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+               "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device visible; the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
+    comm = Comm()
+    rank = comm.rank
+
+    parity = None if args.no_parity_check else parity_check(comm)
+
+    edge = args.cells
+    if args.global_cells:
+        cells = tuple(args.global_cells)
+    else:
+        cells = (edge, edge, args.global_z if args.global_z else edge * world)
+    part = tuple(args.part) if args.part else None
+    # physical domain: the C3 box [0,6]x[0,4]x[0,4] per edge^3 cube, stretched with the number of cells
+    upper = (6.0 * cells[0] / edge, 4.0 * cells[1] / edge, 4.0 * cells[2] / edge)
+    res = measure(comm, cells, upper, part, args.steps, args.warmup, e2e=True)
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    # DRAM traffic per launch from the committed `ncu --set full` capture (profiles/traffic.json), which was taken on the default
+    # 256^3 single-GPU workload: reported only when this run has that per-GPU size, null otherwise
+    traffic = {}
+    if res["n_local"] == 256 ** 3:
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        except Exception:
+            pass
+    kernels = kernel_table(res, peak, traffic)
     graded = [k for k in ("ilu0_apply", "spmv", "assembly") if k in kernels]
     dom = max(graded, key=lambda k: kernels[k]["share_of_step"]) if graded else None
     roofline = None
@@ -352,47 +588,87 @@ def run_b200(args):
                     "note": ("one ILU0 application = vec_skew + lower sweep + upper sweep (3 launches timed as one unit); "
                              "algorithmic bytes are the BCRS-equivalent figure of SURVEY 8d" if dom == "ilu0_apply" else None)}
 
+    # ---- BASELINE config 4: 512^3 strong scaling on these N GPUs (its own timed region) ----
+    strong = None
+    if not args.no_strong and not args.global_cells and not args.global_z:
+        sc = args.strong_cells
+        spart = STRONG_PART.get(world, balanced_partition(world))
+        try:
+            sres = measure(comm, (sc, sc, sc), (6.0, 4.0, 4.0), spart if world > 1 else None, args.strong_steps, 1, e2e=False,
+                           label=f"strong_{sc}")
+            sk = kernel_table(sres, peak, {})
+            strong = {"cells": [sc, sc, sc], "partitioning": list(spart), "scaling": "strong", "steps": args.strong_steps, "warmup": 1,
+                      "ms_per_step": sres["ms_per_step"], "bicgstab_iterations_per_step": sres["its"], "value": sres["value"], "unit": UNIT,
+                      "ms_per_bicgstab_iteration": sres["buckets"][1] / max(1, sres["its"]),
+                      "local_cells_rank0": sres["n_local"],
+                      "kernels": {k: {kk: v[kk] for kk in ("avg_ms", "share_of_step", "frac") if kk in v} for k, v in sk.items()}}
+            # the 1-GPU time of the same problem: measured by the N = 1 run of this bench on the same box (kept under gpurun_out/),
+            # else the committed measurement of this round (profiles/), said which
+            ref_path = os.path.join(ROOT, "gpurun_out", f"strong{sc}_n1.json")
+            if rank == 0:
+                if world == 1:
+                    try:
+                        os.makedirs(os.path.dirname(ref_path), exist_ok=True)
+                        json.dump({"ms_per_step": sres["ms_per_step"], "its": sres["its"]}, open(ref_path, "w"))
+                    except Exception:
+                        pass
+                    strong["speedup_vs_1gpu"] = 1.0
+                else:
+                    for src, pth in (("N=1 run of this bench on this box", ref_path),
+                                     ("committed 1-GPU measurement profiles/strong%d_n1.json" % sc, os.path.join(ROOT, "profiles", f"strong{sc}_n1.json"))):
+                        try:
+                            one = json.load(open(pth))
+                            strong["speedup_vs_1gpu"] = one["ms_per_step"] / sres["ms_per_step"]
+                            strong["one_gpu_ms_per_step"] = one["ms_per_step"]
+                            strong["one_gpu_bicgstab_iterations"] = one["its"]
+                            strong["one_gpu_source"] = src
+                            break
+                        except Exception:
+                            continue
+        except SystemExit:
+            raise
+        except Exception as e:      # noqa: BLE001  (e.g. not enough memory for the requested size: report, keep the headline)
+            strong = {"error": f"{type(e).__name__}: {e}"}
+
     if rank != 0:
-        if dist is not None:
-            dist.barrier()
-            dist.destroy_process_group()
-        eng.close()
+        comm.close()
         return 0
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
+        flags = use_fast_oracle()
+        ce = args.cpu_edge if args.cpu_edge else 96
         t0 = time.time()
-        r = cpu_newton_step(args.cpu_edge, 1, 0, cores)
-        cpu = {"value": r["value"], "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"one Newton iteration of the same 2p lens problem at {args.cpu_edge}^3 cells ({r['bicgstab_iterations']} BiCGSTAB "
-                         f"iterations, {r['sec_per_step']:.1f} s): oracle port, assembly on {cores} OpenMP threads, ILU0/BiCGSTAB sequential"}
+        r = cpu_newton_step(ce, 1, 0, cores)
+        cpu = {"value": r["value"], "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"bounded sample: one Newton iteration of the same 2p lens problem at {ce}^3 cells ({r['bicgstab_iterations']} BiCGSTAB "
+                         f"iterations, {r['sec_per_step']:.1f} s): oracle port ({flags}), ONE rank -- ILU0/BiCGSTAB sequential as one dune-istl rank, "
+                         f"assembly on {cores} OpenMP threads; the multi-rank CPU number on the full {edge}^3 configuration is the "
+                         f"`--impl reference` arm"}
         log(f"[bench] cpu baseline {time.time() - t0:.1f} s")
 
     line = {
-        "metric": f"{METRIC} {edge}^3", "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if args.global_z else "weak", "vs_baseline": None,
+        "metric": f"{METRIC} {edge}^3", "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+        "scaling": "strong" if (args.global_z or args.global_cells) else "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"2p immiscible CCTpfa lens/infiltration, {cells[0]}x{cells[1]}x{cells[2]} cells ({edge}^3 per GPU), Brooks-Corey, "
-                               f"lognormal K multiplier sigma 0.5, numeric differentiation (forward, eps 1e-10), 2x2 BCRS blocks",
-                   "step": "one Newton iteration: assemble + ILU0 factor + BiCGSTAB(1e-6) + update, from the hydrostatic initial state, dt 250 s",
-                   "linear_solver": f"ILU0-BiCGSTAB, reduction 1e-6, maxit {LIN_MAXIT}", "bicgstab_iterations_per_step": its,
-                   "parallelism": f"slab z x{world}, overlap 1" if world > 1 else "single GPU",
-                   "l2_policy": "inputs larger than L2 (Jacobian 3.75 GB, vectors 268 MB per GPU at 256^3)"},
-        "buckets_ms_per_step": {"assemble": buckets[0] / args.steps, "solve": buckets[1] / args.steps, "update": buckets[2] / args.steps},
-        "wall_ms_per_step": wall * 1e3 / args.steps,
+        "config": workload_config(cells, edge),
+        "run": {"bicgstab_iterations_per_step": res["its"],
+                "parallelism": f"Grid.Partitioning {list(res['part'])}, overlap 1" if world > 1 else "single GPU",
+                "l2_policy": "inputs larger than L2 (Jacobian 3.75 GB, vectors 268 MB per GPU at 256^3)"},
+        "buckets_ms_per_step": {"assemble": res["buckets"][0], "solve": res["buckets"][1], "update": res["buckets"][2]},
+        "wall_ms_per_step": res["wall_ms_per_step"],
         "roofline": roofline, "kernels": kernels,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(u0.numel() * 8), "d2h_bytes_per_step": int(u0.numel() * 8),
-                "ms_per_step": ms_e2e},
-        "gpu_launches": int(launches), "clocks": clocks,
+        "e2e": {"value": res["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": res["vec_bytes"], "d2h_bytes_per_step": res["vec_bytes"],
+                "ms_per_step": res["e2e_ms"]},
+        "gpu_launches": res["launches"], "clocks": res["clocks"],
+        "parity_check": parity, "strong_512": strong,
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu
     emit(line)
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
-    eng.close()
+    comm.close()
     return 0
 
 
@@ -403,9 +679,17 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cells", type=int, default=256, help="cube edge per GPU")
-    ap.add_argument("--global-z", type=int, default=0, help="fix the global number of z layers (strong scaling)")
-    ap.add_argument("--cpu-edge", type=int, default=96, help="cube edge of the bounded CPU sample")
+    ap.add_argument("--global-z", type=int, default=0, help="fix the global number of z layers (strong scaling along z)")
+    ap.add_argument("--global-cells", type=int, nargs=3, default=None, help="global box nx ny nz (with --part)")
+    ap.add_argument("--part", type=int, nargs=3, default=None, help="Grid.Partitioning px py pz (default: slabs 1 1 N)")
+    ap.add_argument("--cpu-edge", type=int, default=0, help="cube edge of the CPU run (reference arm: default --cells; cpu_baseline leg: 96)")
+    ap.add_argument("--cpu-ranks", type=int, default=16, help="reference arm: at most this many overlapping-Schwarz CPU ranks")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cache", action="store_true", help="reference arm: time again even if this box already holds the measurement")
+    ap.add_argument("--no-parity-check", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="skip the 512^3 strong-scaling region")
+    ap.add_argument("--strong-cells", type=int, default=512)
+    ap.add_argument("--strong-steps", type=int, default=2)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -98,7 +98,7 @@ class BoxRank:
     `part` = Grid.Partitioning (ranks per axis); None = slabs along the last axis.  `make_spec(box)` builds the box-local
     ProblemSpec (box = per-axis (lo, hi), None for the single-domain run)."""
 
-    def __init__(self, make_spec, cells, comm, part=None):
+    def __init__(self, make_spec, cells, comm, part=None, num_threads=0):
         import copy
         import itertools
         self.comm = comm
@@ -132,7 +132,7 @@ class BoxRank:
         loc.slab = None
         loc.box = None
         self.local = loc
-        self.o = O.Oracle(loc)
+        self.o = O.Oracle(loc, num_threads=num_threads)
         self.b = self.o.b
         self.n = self.o.n
         lc3 = tuple(loc.cells) + (1,) * (3 - dim)
@@ -397,7 +397,7 @@ class BoxRank:
 SlabRank = BoxRank      # the slab decomposition is the default partitioning of BoxRank
 
 
-def run_threads(make_spec, cells, nranks, fn, part=None):
+def run_threads(make_spec, cells, nranks, fn, part=None, num_threads=0):
     """Runs fn(BoxRank) on `nranks` threads; returns the per-rank results."""
     shared = ThreadComm.Shared(nranks)
     out = [None] * nranks
@@ -405,7 +405,7 @@ def run_threads(make_spec, cells, nranks, fn, part=None):
 
     def work(r):
         try:
-            out[r] = fn(BoxRank(make_spec, cells, ThreadComm(shared, r), part))
+            out[r] = fn(BoxRank(make_spec, cells, ThreadComm(shared, r), part, num_threads))
         except BaseException as e:       # noqa: BLE001
             err.append(e)
             shared.barrier.abort()
