@@ -26,6 +26,54 @@ from oracle import oracle_py as O
 
 
 # ----------------------------------------------------------------------------------------------------------
+# The summation tree of the CUDA reductions (dumux_b200/csrc/linalg.cu: dot_kernel / axpy*_norm* / residual_init ->
+# block_reduce -> final_reduce_kernel), restated so that a scalar product here returns the SAME BITS as on the device:
+# 1184 x 256 threads each add their grid-stride elements in order, a warp adds lane l and l+16, l+8, l+4, l+2, l+1, the
+# 8 warp sums of a block go through the same tree (padded with zeros), and the 1184 block partials are summed by 256
+# threads in stride order followed by one more block tree.  dune-istl's SeqScalarProduct sums sequentially instead
+# (`BoxRank(gpu_reduction=False)`, the default); the two differ in the last bits of every dot product, which BiCGSTAB
+# amplifies into iteration counts that wander by a few -- with this tree the device and the oracle run the identical
+# iteration, so the counts can be compared exactly.
+# ----------------------------------------------------------------------------------------------------------
+RED_BLOCKS, RED_THREADS = 1184, 256
+
+
+def _tree32(v):
+    """lane 0 of `for o in 16,8,4,2,1: v += shfl_down(v, o)` over the last axis (length 32)"""
+    for o in (16, 8, 4, 2, 1):
+        v = v[..., :o] + v[..., o:2 * o]
+    return v[..., 0]
+
+
+def _block_tree(v):
+    """block_reduce<false> of linalg.cu: v[..., 256] -> 8 warp sums -> one more warp tree with lanes 8..31 = 0"""
+    w = _tree32(v.reshape(v.shape[:-1] + (RED_THREADS // 32, 32)))
+    pad = np.zeros(w.shape[:-1] + (32,))
+    pad[..., :w.shape[-1]] = w
+    return _tree32(pad)
+
+
+def gpu_sum(terms):
+    """sum of `terms` (one per vector entry, non-owner entries already zero) in the device's summation order"""
+    G = RED_BLOCKS * RED_THREADS
+    L = terms.size
+    nch = max(1, -(-L // G))
+    pad = np.zeros(nch * G)
+    pad[:L] = terms
+    acc = np.zeros(G)
+    for k in range(nch):                                      # each thread: s += term, grid-stride order
+        acc = acc + pad[k * G:(k + 1) * G]
+    partials = _block_tree(acc.reshape(RED_BLOCKS, RED_THREADS))
+    nch2 = -(-RED_BLOCKS // RED_THREADS)
+    pad2 = np.zeros(nch2 * RED_THREADS)
+    pad2[:RED_BLOCKS] = partials
+    acc2 = np.zeros(RED_THREADS)
+    for k in range(nch2):                                     # final_reduce_kernel: thread t adds partials[t], [t+256], ...
+        acc2 = acc2 + pad2[k * RED_THREADS:(k + 1) * RED_THREADS]
+    return float(_block_tree(acc2))
+
+
+# ----------------------------------------------------------------------------------------------------------
 # communicators
 # ----------------------------------------------------------------------------------------------------------
 class ThreadComm:
@@ -98,10 +146,11 @@ class BoxRank:
     `part` = Grid.Partitioning (ranks per axis); None = slabs along the last axis.  `make_spec(box)` builds the box-local
     ProblemSpec (box = per-axis (lo, hi), None for the single-domain run)."""
 
-    def __init__(self, make_spec, cells, comm, part=None, num_threads=0):
+    def __init__(self, make_spec, cells, comm, part=None, num_threads=0, gpu_reduction=False):
         import copy
         import itertools
         self.comm = comm
+        self.gpu_reduction = gpu_reduction
         dim = len(cells)
         self.cells = tuple(cells)
         self.part = tuple(part) if part is not None else problems.default_partitioning(dim, comm.nranks)
@@ -196,6 +245,8 @@ class BoxRank:
         return tuple(reversed(gs)), tuple(reversed(ls))
 
     def dot(self, a, b):
+        if self.gpu_reduction:
+            return self.comm.allreduce(gpu_sum(np.where(self.owner, a * b, 0.0)), "sum")
         return self.comm.allreduce(float(np.dot(a[self.owner], b[self.owner])), "sum")
 
     def apply_operator(self, jac, x):
@@ -397,7 +448,13 @@ class BoxRank:
 SlabRank = BoxRank      # the slab decomposition is the default partitioning of BoxRank
 
 
-def run_threads(make_spec, cells, nranks, fn, part=None, num_threads=0):
+def single_rank(spec, gpu_reduction=True, num_threads=0):
+    """The one-rank case as a BoxRank: the same BiCGSTAB / Newton loops as the multi-rank reference, with the device's summation
+    tree for the scalar products by default -- what a single-GPU run is compared with when iteration COUNTS must match exactly."""
+    return BoxRank(lambda box: spec, spec.cells, ThreadComm(ThreadComm.Shared(1), 0), None, num_threads, gpu_reduction)
+
+
+def run_threads(make_spec, cells, nranks, fn, part=None, num_threads=0, gpu_reduction=False):
     """Runs fn(BoxRank) on `nranks` threads; returns the per-rank results."""
     shared = ThreadComm.Shared(nranks)
     out = [None] * nranks
@@ -405,7 +462,7 @@ def run_threads(make_spec, cells, nranks, fn, part=None, num_threads=0):
 
     def work(r):
         try:
-            out[r] = fn(BoxRank(make_spec, cells, ThreadComm(shared, r), part, num_threads))
+            out[r] = fn(BoxRank(make_spec, cells, ThreadComm(shared, r), part, num_threads, gpu_reduction))
         except BaseException as e:       # noqa: BLE001
             err.append(e)
             shared.barrier.abort()

@@ -103,7 +103,8 @@ def test_decomposed_newton_step_matches_cpu_reference(world, part):
     from dumux_b200 import binding as B
     from dumux_b200 import problems
     from oracle import dist_oracle as D
-    ref = D.run_threads(_make_spec, CELLS, world, _cpu_rank_job, part)
+    # the oracle adds every scalar product in the device's reduction tree -> identical Krylov iterations for 2 ranks
+    ref = D.run_threads(_make_spec, CELLS, world, _cpu_rank_job, part, gpu_reduction=True)
     uid = B.Engine.nccl_unique_id()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -131,16 +132,18 @@ def test_decomposed_newton_step_matches_cpu_reference(world, part):
         # owner-masked, all-reduced norm is the same number on every rank
         assert g["norm"] == got[0]["norm"]
         # Schwarz-BiCGSTAB: same iteration count, solution at the solver tolerance
-        assert g["st"] == 0 and c["st"] == 0 and abs(g["its"] - c["its"]) <= (0 if world == 2 else 1), (g["its"], c["its"])
+        assert g["st"] == 0 and c["st"] == 0 and abs(g["its"] - c["its"]) <= (0 if world == 2 else 2), (g["its"], c["its"])
         assert np.linalg.norm(g["x"] - c["x"]) <= 1e-7 * np.linalg.norm(c["x"])
         # Schwarz-GMRes(10) (ILURestartedGMResIstlSolver on the overlapping decomposition): same count, reduction and solution
-        assert g["stg"] == 0 and c["stg"] == 0 and abs(g["itsg"] - c["itsg"]) <= (0 if world == 2 else 1), (g["itsg"], c["itsg"])
+        assert g["stg"] == 0 and c["stg"] == 0 and abs(g["itsg"] - c["itsg"]) <= (0 if world == 2 else 2), (g["itsg"], c["itsg"])
         if g["itsg"] == c["itsg"]:
             assert g["redg"] == pytest.approx(c["redg"], rel=1e-5)
         assert np.linalg.norm(g["xg"] - c["xg"]) <= 1e-7 * np.linalg.norm(c["xg"])
         assert np.linalg.norm(g["xg"] - g["x"]) <= 1e-6 * np.linalg.norm(g["x"])          # both solve the same global system
         # Newton: same iteration count, fields to 1e-8
         assert g["nst"] == 0 and g["nsteps"] == c["nsteps"]
+        if world == 2:
+            assert g["lin_its"] == c["lin_its"], (g["lin_its"], c["lin_its"])
         ug, uc = g["u"].reshape(-1, 2), c["u"].reshape(-1, 2)
         assert np.linalg.norm(ug[:, 0] - uc[:, 0]) <= 1e-8 * np.linalg.norm(uc[:, 0])
         assert np.linalg.norm(ug[:, 1] - uc[:, 1]) <= 1e-8 * max(1.0, np.linalg.norm(uc[:, 1]))
