@@ -1185,6 +1185,19 @@ int prepare(dmx_ctx* ctx)
     DMX_CUDA(cudaSetDevice(ctx->device));
     // material laws
     if (ctx->model == DMX_MODEL_2P && ctx->laws.empty()) return fail(ctx, DMX_ERR_USAGE, "2p model without material law");
+    if (ctx->model == DMX_MODEL_2P) {
+        // every region id a cell refers to needs its dmx_set_material call (spatialParams.fluidMatrixInteraction of that cell)
+        int maxRegion = 0;
+        for (int r : ctx->h_region) maxRegion = std::max(maxRegion, r);
+        if (maxRegion >= (int)ctx->laws.size())
+            return fail(ctx, DMX_ERR_USAGE, "a cell refers to material region " + std::to_string(maxRegion) + " but only " +
+                                                std::to_string(ctx->laws.size()) + " regions were given to dmx_set_material");
+        std::vector<char> used(ctx->laws.size(), 0);
+        for (int r : ctx->h_region) used[r] = 1;
+        for (size_t r = 0; r < ctx->laws.size(); ++r)
+            if (used[r] && ctx->laws[r].kind == DMX_LAW_BROOKSCOREY && ctx->laws[r].lambda == 0.0)      // value-initialised slot
+                return fail(ctx, DMX_ERR_USAGE, "material region " + std::to_string(r) + " is used by cells but was never set");
+    }
     for (auto& l : ctx->laws) law_init(l);
     if (int rc = upload(ctx, &ctx->d_laws, ctx->laws)) return rc;
     // boundary data

@@ -831,17 +831,31 @@ static int sk_apply_t(dmx_ctx* ctx, SkewState* st, const double* d, double* v)
     const SkewGrid& g = st->g;
     unsigned long long* tick_lo = st->ctl;
     unsigned long long* tick_up = st->ctl + 1;
+    // The device ticket counters advance by ntiles per sweep; the host mirrors (seq_lo / seq_up) advance only once the sweep
+    // that consumes the tickets has been enqueued.  If a launch is refused the counters are re-zeroed on both sides, so a
+    // recoverable launch error can never leave a later sweep with a ticket base the device does not share.
     const unsigned long long base_lo = st->seq_lo * (unsigned long long)g.ntiles;
     const unsigned long long base_up = st->seq_up * (unsigned long long)g.ntiles;
-    st->seq_lo++;
-    st->seq_up++;
     // tags of the halo words: never 0 (the buffer starts zeroed), different for every sweep
     const unsigned int tag_lo = 2 * st->ll_seq + 1, tag_up = 2 * st->ll_seq + 2;
     st->ll_seq = (st->ll_seq + 1) % 0x7ffffff0u;
+    auto resync = [&](int rc) {
+        cudaMemsetAsync(st->ctl, 0, 2 * sizeof(unsigned long long), ctx->stream);
+        st->seq_lo = st->seq_up = 0;
+        return rc;
+    };
     vec_skew_kernel<B><<<(unsigned)((size_t)g.ntiles * g.NS), SK_THREADS, 0, ctx->stream>>>(g, d, st->Lsk);
-    DMX_CHECK_LAUNCH();
-    if (int rc = sweep_launch_ll<B, false>(ctx, st, st->Lsk, st->Usk, tag_lo, st->order_lo, tick_lo, base_lo, st->trace)) return rc;
-    return sweep_launch_ll<B, true>(ctx, st, st->Usk, v, tag_up, st->order_up, tick_up, base_up, st->trace ? st->trace + 2 * 64 * 24 : nullptr);
+    {
+        ctx->launches++;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return resync(fail(ctx, DMX_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e)));
+    }
+    if (int rc = sweep_launch_ll<B, false>(ctx, st, st->Lsk, st->Usk, tag_lo, st->order_lo, tick_lo, base_lo, st->trace)) return resync(rc);
+    st->seq_lo++;
+    if (int rc = sweep_launch_ll<B, true>(ctx, st, st->Usk, v, tag_up, st->order_up, tick_up, base_up, st->trace ? st->trace + 2 * 64 * 24 : nullptr))
+        return resync(rc);
+    st->seq_up++;
+    return 0;
 }
 
 int sk_apply(dmx_ctx* ctx, const double* d, double* v)

@@ -93,6 +93,10 @@ struct BCRSMatrix {
     std::size_t nonzeroes() const { return colidx.size(); }
 };
 
+//! stands for Dumux::PartialReassembler<Assembler> (assembly/partialreassembler.hh): partial reassembly is not implemented on
+//! the device (parity runs set Newton.EnablePartialReassembly = false), so the only value accepted is nullptr
+struct PartialReassembler;
+
 //! what GridGeometry + Problem + SpatialParams provide, sampled into flat arrays (common/fvproblem.hh:126-283,
 //! porousmediumflow/fvspatialparams.hh:83-99); cells numbered x fastest, boundary faces per side lower axis fastest
 struct ProblemData {
@@ -115,6 +119,12 @@ struct ProblemData {
     //! discretisation of FVAssembler<TracerTypeTag, DiffMethod::analytic, implicit> (examples/1ptracer/main.cc:236)
     std::vector<double> volumeFlux;
     bool tracerImplicit = false;
+    //! The adapter that samples a DuMux Problem sets these when the problem overrides the solution-dependent interfaces
+    //! neumann(element, fvGeometry, elemVolVars, elemFluxVarsCache, scvf) / source(element, fvGeometry, elemVolVars, scv)
+    //! (common/fvproblem.hh:262-283,307-331) instead of neumannAtPos / sourceAtPos, or returns a tensor from
+    //! SpatialParams::permeability (porousmediumflow/fvspatialparams.hh:83-99): the kernels take sampled arrays and a scalar K,
+    //! so the assembler refuses such a problem instead of silently freezing the values (DESIGN.md "Out of scope").
+    bool solutionDependentNeumann = false, solutionDependentSource = false, tensorPermeability = false;
     dmx_options options;
     ProblemData() { dmx_default_options(&options); }
 };
@@ -133,6 +143,7 @@ public:
     using JacobianMatrix = BCRSMatrix;
     using SolutionVector = BlockVector;
     using ResidualType = BlockVector;
+    using Variables = BlockVector;          // assemblers that do not export grid variables: Variables = SolutionVector (newtonsolver.hh:199)
 
     //! stationary problems (fvassembler.hh:131)
     GpuFVAssembler(std::shared_ptr<Context> ctx, const ProblemData& problem) : ctx_(std::move(ctx)), stationary_(true) { init_(problem); }
@@ -144,9 +155,11 @@ public:
         setTimeStepSize(dt);
     }
 
-    //! fvassembler.hh:179-207: throws NumericalProblem if the residual is not finite (all ranks agree, :504-509)
-    void assembleJacobianAndResidual(const SolutionVector& curSol)
+    //! fvassembler.hh:179-207: throws NumericalProblem if the residual is not finite (all ranks agree, :504-509).
+    //! `partialReassembler` must be null (see PartialReassembler above).
+    void assembleJacobianAndResidual(const SolutionVector& curSol, const PartialReassembler* partialReassembler = nullptr)
     {
+        if (partialReassembler) throw InvalidState("GpuFVAssembler: partial reassembly is not supported (Newton.EnablePartialReassembly must be false)");
         upload_(curSol);
         ctx_->check(dmx_assemble(ctx_->get(), 1));
         hostJacobianValid_ = hostResidualValid_ = false;
@@ -214,6 +227,9 @@ public:
 private:
     void init_(const ProblemData& p)
     {
+        if (p.solutionDependentNeumann || p.solutionDependentSource)
+            throw InvalidState("GpuFVAssembler: solution-dependent Neumann fluxes / sources are not supported (only the tracer outflow, DMX_BC_OUTFLOW)");
+        if (p.tensorPermeability) throw InvalidState("GpuFVAssembler: tensor-valued permeability is not supported (scalar K only)");
         dmx_ctx* c = ctx_->get();
         ctx_->check(dmx_grid_structured(c, p.model, p.dim, p.cells.data(), p.lower.data(), p.upper.data()));
         numEq_ = dmx_num_eq(c);
@@ -276,6 +292,7 @@ public:
     IstlSolverResult solve(BCRSMatrix& A, BlockVector& x, BlockVector& b)
     {
         ensurePattern_(A);
+        select();
         IstlSolverResult r;
         const int st = ctx_->check(dmx_linear_solve_host(ctx_->get(), A.values.data(), x.data(), b.data(), reduction_, maxIter_, precond_,
                                                           &r.iterations, &r.reduction),
@@ -287,6 +304,7 @@ public:
     IstlSolverResult solve(GpuFVAssembler& assembler, BlockVector& x)
     {
         dmx_ctx* c = ctx_->get();
+        select();
         ctx_->check(dmx_vec_upload(c, DMX_VEC_DELTA, x.data()));
         IstlSolverResult r;
         const int st = ctx_->check(dmx_linear_solve(c, reduction_, maxIter_, precond_, &r.iterations, &r.reduction), true);
@@ -306,13 +324,18 @@ public:
     void setResidualReduction(double r) { reduction_ = r; }       // :350
     void setMaxIter(std::size_t i) { maxIter_ = static_cast<int>(i); }
     void setPreconditioner(int p) { precond_ = p; }               // DMX_PRECOND_ILU0 (default) or DMX_PRECOND_BLOCKJACOBI
+    double residualReduction() const { return reduction_; }
+    int maxIter() const { return maxIter_; }
+    int preconditioner() const { return precond_; }
+    //! makes this object's Krylov method the one the context runs (a property of the context, dmx_set_linear_solver); called
+    //! before every solve so that several solver objects can share a context
+    void select() const { ctx_->check(dmx_set_linear_solver(ctx_->get(), solver_, restart_)); }
     virtual std::string name() const { return "ILU0 preconditioned BiCGSTAB solver (B200)"; }
 
 protected:
-    //! the Krylov method is a property of the context (dmx_set_linear_solver): one solver object per context
-    GpuILUBiCGSTABSolver(std::shared_ptr<Context> ctx, int solver, int restart) : ctx_(std::move(ctx))
+    GpuILUBiCGSTABSolver(std::shared_ptr<Context> ctx, int solver, int restart) : ctx_(std::move(ctx)), solver_(solver), restart_(restart)
     {
-        ctx_->check(dmx_set_linear_solver(ctx_->get(), solver, restart));
+        select();
     }
 
 private:
@@ -323,6 +346,7 @@ private:
         ctx_->check(dmx_bcrs_pattern(c, A.n, A.b, A.rowptr.data(), A.colidx.data()));
     }
     std::shared_ptr<Context> ctx_;
+    int solver_ = DMX_SOLVER_BICGSTAB, restart_ = 0;
     double reduction_ = 1e-13;
     int maxIter_ = 250, precond_ = DMX_PRECOND_ILU0;
 };
@@ -358,6 +382,8 @@ public:
     : assembler_(std::move(assembler)), linearSolver_(std::move(linearSolver))
     {
         dmx_default_newton_params(&params_);      // newtonsolver.hh:1213-1247
+        // the NewtonSolver constructor sets the linear solver's reduction to LinearSolver.ResidualReduction (default 1e-6), :232
+        linearSolver_->setResidualReduction(params_.lin_reduction);
     }
     void setMaxRelativeShift(double s) { params_.max_relative_shift = s; }
     void setMinSteps(int n) { params_.min_steps = n; }
@@ -376,8 +402,10 @@ public:
         params_.satisfy_residual_and_shift = satisfyBoth ? 1 : 0;
     }
     //! LinearSolver.ResidualReduction as set by the NewtonSolver constructor (:232) / LinearSolver.MaxIterations
-    void setLinearResidualReduction(double r) { params_.lin_reduction = r; }
-    void setLinearMaxIterations(int n) { params_.lin_maxit = n; }
+    void setLinearResidualReduction(double r) { linearSolver_->setResidualReduction(r); }
+    void setLinearMaxIterations(int n) { linearSolver_->setMaxIter(static_cast<std::size_t>(n)); }
+    GpuILUBiCGSTABSolver& linearSolver() { return *linearSolver_; }
+    GpuFVAssembler& assembler() { return *assembler_; }
 
     //! NewtonSolver::solve(vars) at fixed dt (newtonsolver.hh:362-372): throws NumericalProblem if not converged.
     //! The whole loop (assemble, solve, update, shift) runs on the device; u is uploaded once and downloaded once.
@@ -385,6 +413,12 @@ public:
     {
         const auto& ctx = assembler_->context();
         const double* prev = assembler_->isStationaryProblem() ? nullptr : assembler_->prevSol().data();
+        // the linear solve inside the device loop is the one `linearSolver_` describes: Krylov method, preconditioner,
+        // reduction and iteration limit (solveLinearSystem calls linearSolver().solve, newtonsolver.hh:1201-1210)
+        linearSolver_->select();
+        params_.preconditioner = linearSolver_->preconditioner();
+        params_.lin_reduction = linearSolver_->residualReduction();
+        params_.lin_maxit = linearSolver_->maxIter();
         const int st = ctx->check(dmx_newton_solve_host(ctx->get(), u.data(), prev, &params_, &report_), true);
         if (st != DMX_STATUS_OK) throw NumericalProblem("Newton solver didn't converge after " + std::to_string(report_.newton_iterations) + " iterations");
     }

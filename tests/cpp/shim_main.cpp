@@ -81,7 +81,23 @@ int main(int argc, char** argv)
     const std::string mode = argc > 1 ? argv[1] : "1p";
     try {
         auto ctx = std::make_shared<Context>(0);
-        if (mode == "1p" || mode == "1p-ssorcg") {
+        if (mode == "1p-newton-ssor" || mode == "1p-newton-ilu") {
+            // stationary Newton solve through GpuNewtonSolver with the solver object the caller chose: the preconditioner,
+            // Krylov method, reduction and iteration limit of `linearSolver` must be the ones the device loop runs
+            const int nx = 10, ny = 10;
+            auto assembler = std::make_shared<GpuFVAssembler>(ctx, onepIncompressible(nx, ny));
+            std::shared_ptr<GpuILUBiCGSTABSolver> linearSolver;
+            if (mode == "1p-newton-ssor") linearSolver = std::make_shared<GpuSSORBiCGSTABSolver>(ctx);
+            else linearSolver = std::make_shared<GpuILUBiCGSTABSolver>(ctx);
+            auto other = std::make_shared<GpuILURestartedGMResSolver>(ctx);      // a second solver object on the same context must not leak into the solve
+            (void)other;
+            GpuNewtonSolver newton(assembler, linearSolver);
+            GpuFVAssembler::SolutionVector x(assembler->numDofs(), 1, 0.0);
+            newton.solve(x);
+            std::fprintf(stderr, "newton %d linear %d %d\n", newton.report().newton_iterations, newton.report().linear_iterations[0],
+                         newton.report().linear_iterations[1]);
+            for (std::size_t i = 0; i < x.size(); ++i) std::printf("%.17g\n", x[i][0]);
+        } else if (mode == "1p" || mode == "1p-ssorcg") {
             const int nx = 10, ny = 10;
             auto assembler = std::make_shared<GpuFVAssembler>(ctx, onepIncompressible(nx, ny));
             // test/porousmediumflow/1p/incompressible/main.cc uses SSORCGIstlSolver; the ILU-BiCGSTAB variant is the bench solver

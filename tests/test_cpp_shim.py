@@ -100,3 +100,65 @@ def test_shim_2p_timeloop_reproduces_oracle_and_golden(shim_exe):
         ref = g[name].astype(np.float64)
         d = np.abs(u[:, col] - ref)
         assert np.all((d <= 1.5e-7) | (d <= 1e-2 * np.abs(ref))), name
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# NewtonSolver's duck-typed contract (test/nonlinear/newton/test_newton.cc:31-78) and the linear-solver hand-over
+# ------------------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def contract_exe(tmp_path_factory):
+    import __graft_entry__ as g
+    from dumux_b200 import binding
+    if not os.path.exists(binding.LIB_PATH):
+        g.build()
+    exe = str(tmp_path_factory.mktemp("contract") / "newton_contract")
+    libdir = os.path.join(ROOT, "dumux_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "newton_contract.cpp"), "-o", exe, "-L", libdir, "-ldumux_b200",
+                           f"-Wl,-rpath,{libdir}"])
+    return exe
+
+
+def test_gpu_classes_satisfy_the_newton_solver_contract(contract_exe):
+    """A Newton loop written against exactly the members the reference's mock assembler / linear solver provide compiles with
+    the Gpu classes (that is the check) and finds sqrt(5) with the restated mocks, as test_newton.cc does."""
+    p = subprocess.run([contract_exe], capture_output=True, text=True, check=True)
+    tag, steps, x = p.stdout.split()
+    assert tag == "mock" and abs(float(x) - 5 ** 0.5) <= 1e-13 * 5 ** 0.5
+
+
+@pytest.mark.gpu
+def test_contract_loop_runs_on_the_device_with_every_solver_alias(contract_exe):
+    p = subprocess.run([contract_exe, "gpu"], capture_output=True, text=True, check=True)
+    line = [l for l in p.stdout.splitlines() if l.startswith("gpu")][0].split()
+    s1, s2, s3 = (int(v) for v in line[1:4])
+    x, y, z = (float(v) for v in line[4:7])
+    assert s1 >= 2 and s2 >= 2 and s3 >= 2
+    assert abs(x / y - 1) < 1e-8 and abs(x / z - 1) < 1e-8 and 1.0e5 < x < 2.0e5
+
+
+@pytest.mark.gpu
+def test_newton_solver_runs_the_linear_solver_it_was_given(shim_exe):
+    """GpuNewtonSolver(assembler, GpuSSORBiCGSTABSolver) must run SSOR-BiCGSTAB inside the device loop (the
+    preconditioner of the solver object was dropped): first-iteration counts equal the oracle's for SSOR and for ILU0, and differ."""
+    from dumux_b200 import problems
+    from oracle import oracle_py as O
+    spec = problems.onep_incompressible((10, 10))
+    o = O.Oracle(spec)
+    r, j = o.assemble(np.zeros(100))
+    xs, sts, its_ssor, _ = O.ssor_solve(o.n, o.b, o.rowptr, o.colidx, j, r, krylov="bicgstab", reduction=1e-6, maxit=250)
+    xi, sti, its_ilu, _ = o.solve(j, r, reduction=1e-6, maxit=250)
+    assert sts == 0 and sti == 0 and its_ssor != its_ilu
+    g = np.load(os.path.join(GOLDEN, "test_1p_cc.npz"))["p"].astype(np.float64)
+    for mode, its in (("1p-newton-ssor", its_ssor), ("1p-newton-ilu", its_ilu)):
+        p = subprocess.run([shim_exe, mode], capture_output=True, text=True, check=True)
+        lin = [l for l in p.stderr.splitlines() if l.startswith("newton")][0].split()
+        assert int(lin[3]) == its, (mode, lin, its)
+        x = np.array([float(v) for v in p.stdout.split()])
+        assert np.abs(x / g - 1).max() < 5e-6
+
+
+def test_shim_rejects_what_the_kernels_cannot_represent():
+    src = open(os.path.join(ROOT, "include", "dumux_b200.hpp")).read()
+    for needle in ("solutionDependentNeumann", "tensorPermeability", "const PartialReassembler* partialReassembler = nullptr", "using Variables"):
+        assert needle in src, needle
