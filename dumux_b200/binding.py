@@ -22,7 +22,7 @@ KERNEL_ASSEMBLY, KERNEL_SPMV, KERNEL_ILU_APPLY, KERNEL_ILU_FACTOR = range(4)
 EXPORTS = [
     "dmx_default_options", "dmx_default_newton_params", "dmx_create", "dmx_create_distributed", "dmx_get_nccl_unique_id",
     "dmx_destroy", "dmx_last_error", "dmx_version", "dmx_grid_structured", "dmx_grid_tensor", "dmx_local_box",
-    "dmx_local_box3", "dmx_set_partitioning",
+    "dmx_local_box3", "dmx_set_partitioning", "dmx_set_preconditioner_params", "dmx_precond_apply",
     "dmx_num_cells", "dmx_num_eq", "dmx_nnz_blocks", "dmx_pattern", "dmx_bcrs_pattern", "dmx_set_options",
     "dmx_set_cell_fields", "dmx_set_source", "dmx_set_material", "dmx_set_fluids", "dmx_set_fluid_table",
     "dmx_side_faces", "dmx_set_boundary", "dmx_vec_upload", "dmx_vec_download", "dmx_vec_copy", "dmx_jacobian_upload",
@@ -36,6 +36,7 @@ EXPORTS = [
 ]
 SOLVER_BICGSTAB, SOLVER_RESTARTED_GMRES, SOLVER_CG = 0, 1, 2
 PRECOND_SSOR = 2
+PRECOND_PARMT_JAC, PRECOND_PARMT_SOR, PRECOND_PARMT_SSOR = 3, 4, 5
 K_ASSEMBLY, K_SPMV, K_ILU_APPLY, K_ILU_FACTOR, K_AMG, K_BLAS1, K_HALO, K_JACOBI = range(8)
 
 
@@ -113,6 +114,8 @@ def load_library():
     L.dmx_set_wetting_phase.argtypes = [vp, C.c_int, C.c_int]
     L.dmx_set_linear_solver.argtypes = [vp, C.c_int, C.c_int]
     L.dmx_ssor_apply.argtypes = [vp, C.c_int, C.c_int]
+    L.dmx_set_preconditioner_params.argtypes = [vp, C.c_int, C.c_double]
+    L.dmx_precond_apply.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     L.dmx_num_output_fields.argtypes = [vp]
     L.dmx_output_fields.argtypes = [vp, C.c_void_p]
     L.dmx_set_boundary.argtypes = [vp, C.c_int, _ip, _dp]
@@ -398,6 +401,12 @@ class Engine:
 
     def ssor_apply(self, d_vec, v_vec):
         self._check(self.L.dmx_ssor_apply(self.h, d_vec, v_vec))
+
+    def set_preconditioner_params(self, iterations=1, relaxation=1.0):
+        self._check(self.L.dmx_set_preconditioner_params(self.h, iterations, relaxation))
+
+    def precond_apply(self, precond, d_vec=VEC_WORK0, v_vec=VEC_WORK1):
+        self._check(self.L.dmx_precond_apply(self.h, precond, d_vec, v_vec))
 
     def solve_device(self, reduction=1e-6, maxit=250, precond=PRECOND_ILU0):
         its, red = C.c_int(0), C.c_double(0)

@@ -29,6 +29,7 @@ int alloc_vectors(dmx_ctx* ctx)
     if (ctx->d_ilu) { cudaFree(ctx->d_ilu); ctx->d_ilu = nullptr; }
     if (ctx->d_dinv) { cudaFree(ctx->d_dinv); ctx->d_dinv = nullptr; }
     if (ctx->d_gm) { cudaFree(ctx->d_gm); ctx->d_gm = nullptr; ctx->gm_vectors = 0; }      // sized by the old vector length
+    if (ctx->d_xold) { cudaFree(ctx->d_xold); ctx->d_xold = nullptr; }
     ctx->ilu_valid = false;
     ctx->jac_diagonal = false;
     DMX_CUDA(cudaMalloc((void**)&ctx->d_J, (size_t)ctx->nnzb * ctx->b * ctx->b * sizeof(double)));
@@ -302,7 +303,7 @@ int dmx_destroy(dmx_ctx* ctx)
     if (ctx->nccl_comm) nccl_destroy(ctx);
     void* ptrs[] = {ctx->d_geom, ctx->d_K, ctx->d_phi, ctx->d_q, ctx->d_region, ctx->d_tij[0], ctx->d_tij[1], ctx->d_tij[2], ctx->d_laws,
                     ctx->d_tab_buf, ctx->d_rowptr, ctx->d_colidx, ctx->d_diag, ctx->d_J, ctx->d_ilu, ctx->d_rt, ctx->d_p, ctx->d_v, ctx->d_t,
-                    ctx->d_y, ctx->d_z, ctx->d_dinv, ctx->d_gm, ctx->d_vf, ctx->d_lrows, ctx->d_urows, ctx->d_lptr, ctx->d_uptr, ctx->d_barrier, ctx->d_partials,
+                    ctx->d_y, ctx->d_z, ctx->d_dinv, ctx->d_gm, ctx->d_vf, ctx->d_color_rows, ctx->d_xold, ctx->d_lrows, ctx->d_urows, ctx->d_lptr, ctx->d_uptr, ctx->d_barrier, ctx->d_partials,
                     ctx->d_scalars, ctx->d_flag, ctx->d_owner, ctx->d_send, ctx->d_recv};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int v = 0; v < DMX_NUM_VECS; ++v) if (ctx->d_vec[v]) cudaFree(ctx->d_vec[v]);
@@ -876,10 +877,25 @@ int dmx_output_fields(dmx_ctx* ctx, double* out)
 int dmx_ssor_apply(dmx_ctx* ctx, int d_vec, int v_vec)
 {
     if (!ctx->d_J) return fail(ctx, DMX_ERR_USAGE, "ssor_apply: no pattern");
-    if (ctx->nranks > 1) return fail(ctx, DMX_ERR_USAGE, "SSOR runs on a single domain in this version");
     if (int rc = vec_ok(ctx, d_vec)) return rc;
     if (int rc = vec_ok(ctx, v_vec)) return rc;
     return ssor_apply(ctx, ctx->d_vec[d_vec], ctx->d_vec[v_vec]);
+}
+int dmx_set_preconditioner_params(dmx_ctx* ctx, int iterations, double relaxation)
+{
+    if (iterations < 1) return fail(ctx, DMX_ERR_USAGE, "LinearSolver.PreconditionerIterations must be >= 1");
+    ctx->precond_iterations = iterations;
+    ctx->precond_relaxation = relaxation;
+    return 0;
+}
+int dmx_precond_apply(dmx_ctx* ctx, int preconditioner, int d_vec, int v_vec)
+{
+    if (!ctx->d_J) return fail(ctx, DMX_ERR_USAGE, "precond_apply: no pattern");
+    if (int rc = vec_ok(ctx, d_vec)) return rc;
+    if (int rc = vec_ok(ctx, v_vec)) return rc;
+    DMX_CUDA(cudaSetDevice(ctx->device));
+    if (int rc = precond_setup(ctx, preconditioner)) return rc;
+    return precond_apply_local(ctx, preconditioner, ctx->d_vec[d_vec], ctx->d_vec[v_vec]);
 }
 int dmx_ilu0_download(dmx_ctx* ctx, double* values)
 {

@@ -143,6 +143,11 @@ struct dmx_ctx {
     int *d_lptr = nullptr, *d_uptr = nullptr;
     unsigned int* d_barrier = nullptr;
     int linear_solver = DMX_SOLVER_BICGSTAB, gmres_restart = 10;     // dmx_set_linear_solver
+    int precond_iterations = 1;       // LinearSolver.PreconditionerIterations (ParMT* smoothers)
+    double precond_relaxation = 1.0;  // LinearSolver.PreconditionerRelaxation
+    int* d_color_rows = nullptr;      // ParMTSOR/SSOR: rows sorted by colour (computeColorsForMatrixSweep_)
+    std::vector<int> color_ptr;       // host: first row of every colour in d_color_rows (+ end)
+    double* d_xold = nullptr;         // ParMTJac: previous iterate
     double* d_gm = nullptr;           // GMRes basis: restart+1 vectors, w, defect
     int gm_vectors = 0;
     void* skew = nullptr;             // SkewState of ilu_structured.cu (structured-grid ILU sweeps), null: generic kernels
@@ -283,6 +288,9 @@ int ilu0_apply(dmx_ctx* ctx, const double* d, double* v);
 int ssor_apply(dmx_ctx* ctx, const double* d, double* v);
 int block_jacobi_setup(dmx_ctx* ctx);
 int block_jacobi_apply(dmx_ctx* ctx, const double* d, double* v);
+int parmt_apply(dmx_ctx* ctx, int precond, const double* d, double* v);
+int precond_apply_local(dmx_ctx* ctx, int precond, const double* d, double* v);
+int precond_setup(dmx_ctx* ctx, int precond);
 int dot(dmx_ctx* ctx, const double* a, const double* b, double* out);
 int bicgstab(dmx_ctx* ctx, double reduction, int maxit, int precond, int* iterations, double* achieved);
 int gmres(dmx_ctx* ctx, double reduction, int maxit, int restart, int precond, int* iterations, double* achieved);

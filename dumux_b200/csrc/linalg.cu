@@ -363,6 +363,7 @@ int build_diag(dmx_ctx* ctx)
     DMX_CUDA(cudaMemcpy(ctx->d_diag, diag.data(), diag.size() * sizeof(int), cudaMemcpyHostToDevice));
     ctx->l_ptr.clear();
     ctx->u_ptr.clear();
+    ctx->color_ptr.clear();
     ctx->ilu_valid = false;
     ctx->ilu_bcrs_valid = false;
     return 0;
@@ -761,25 +762,159 @@ int block_jacobi_apply(dmx_ctx* ctx, const double* d, double* v)
 }
 
 // ---------------------------------------------------------------------------------------------
+// Dumux::ParMTJac / ParMTSOR / ParMTSSOR (dumux/linear/preconditioners.hh:330-400, 442-620), DuMux's own multi-threaded
+// smoothers ("par_mt_jac", "par_mt_sor", "par_mt_ssor").  Rows are coloured like computeColorsForMatrixSweep_ (:408-440: in
+// index order, smallest colour no matrix neighbour has -- the checkerboard on the 7-point pattern); a sweep visits the
+// colours in order (backward: descending), all rows of a colour in parallel: rhs = d_i - sum_j A_ij x_j over ALL columns
+// ascending (diagonal included), v = A_ii^-1 rhs (FieldMatrix::solve), x_i += w v.  ParMTJac uses the previous iterate for
+// every row.  One thread per block row; no wavefront, so these are plain HBM-streaming kernels.
+// ---------------------------------------------------------------------------------------------
+template <int B>
+__global__ void __launch_bounds__(256) parmt_row_kernel(int nrows, const int* __restrict__ rows, const int* __restrict__ rowptr,
+                                                        const int* __restrict__ colidx, const int* __restrict__ diag,
+                                                        const double* __restrict__ A, const double* __restrict__ d, const double* xin,
+                                                        double* xout, double w)
+{
+    constexpr int BB = B * B;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nrows) return;
+    const int i = rows ? rows[q] : q;
+    double rhs[B];
+#pragma unroll
+    for (int e = 0; e < B; ++e) rhs[e] = d[(size_t)i * B + e];
+    const int kend = rowptr[i + 1];
+    for (int k = rowptr[i]; k < kend; ++k) {
+        const int c = colidx[k];
+        double xv[B];
+#pragma unroll
+        for (int e = 0; e < B; ++e) xv[e] = xin[(size_t)c * B + e];
+#pragma unroll
+        for (int r = 0; r < B; ++r)
+#pragma unroll
+            for (int cc = 0; cc < B; ++cc) rhs[r] -= A[(size_t)k * BB + r * B + cc] * xv[cc];
+    }
+    const double* D = A + (size_t)diag[i] * BB;
+    double v[B];
+    if (B == 1) v[0] = rhs[0] / D[0];
+    else {
+        double detinv = D[0] * D[3] - D[1] * D[2];
+        detinv = 1 / detinv;
+        v[0] = detinv * (D[3] * rhs[0] - D[1] * rhs[B - 1]);
+        v[B - 1] = detinv * (D[0] * rhs[B - 1] - D[2] * rhs[0]);
+    }
+#pragma unroll
+    for (int e = 0; e < B; ++e) xout[(size_t)i * B + e] = xin[(size_t)i * B + e] + w * v[e];
+}
+
+static int parmt_build_colors(dmx_ctx* ctx)
+{
+    const int n = ctx->n;
+    const std::vector<int>& rp = ctx->h_rowptr;
+    const std::vector<int>& ci = ctx->h_colidx;
+    std::vector<int> colors(n, -1), nb;
+    std::vector<char> used;
+    int ncol = 0;
+    for (int i = 0; i < n; ++i) {
+        nb.clear();
+        for (int k = rp[i]; k < rp[i + 1]; ++k) nb.push_back(colors[ci[k]]);
+        const int m = (int)nb.size();
+        used.assign(m, 0);
+        for (int q = 0; q < m; ++q)
+            if (nb[q] >= 0 && nb[q] < m) used[nb[q]] = 1;
+        int c = m;
+        for (int q = 0; q < m; ++q)
+            if (!used[q]) { c = q; break; }
+        colors[i] = c;
+        ncol = std::max(ncol, c + 1);
+    }
+    ctx->color_ptr.assign(ncol + 1, 0);
+    for (int i = 0; i < n; ++i) ctx->color_ptr[colors[i] + 1]++;
+    for (int c = 0; c < ncol; ++c) ctx->color_ptr[c + 1] += ctx->color_ptr[c];
+    std::vector<int> rows(n), cur(ctx->color_ptr.begin(), ctx->color_ptr.end() - 1);
+    for (int i = 0; i < n; ++i) rows[cur[colors[i]]++] = i;
+    if (ctx->d_color_rows) cudaFree(ctx->d_color_rows);
+    ctx->d_color_rows = nullptr;
+    DMX_CUDA(cudaMalloc((void**)&ctx->d_color_rows, (size_t)n * sizeof(int)));
+    DMX_CUDA(cudaMemcpy(ctx->d_color_rows, rows.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// v = ParMT{Jac,SOR,SSOR}(J)(d) from v = 0
+int parmt_apply(dmx_ctx* ctx, int precond, const double* d, double* v)
+{
+    ProfScope ps(ctx, DMX_K_JACOBI);
+    const size_t len = (size_t)ctx->n * ctx->b;
+    DMX_CUDA(cudaMemsetAsync(v, 0, len * sizeof(double), ctx->stream));
+    const double w = ctx->precond_relaxation;
+    auto launch = [&](int nrows, const int* rows, const double* xin, double* xout) -> int {
+        if (nrows <= 0) return 0;
+        const int grid = (nrows + 255) / 256;
+        if (ctx->b == 2)
+            parmt_row_kernel<2><<<grid, 256, 0, ctx->stream>>>(nrows, rows, ctx->d_rowptr, ctx->d_colidx, ctx->d_diag, ctx->d_J, d, xin, xout, w);
+        else
+            parmt_row_kernel<1><<<grid, 256, 0, ctx->stream>>>(nrows, rows, ctx->d_rowptr, ctx->d_colidx, ctx->d_diag, ctx->d_J, d, xin, xout, w);
+        DMX_CHECK_LAUNCH();
+        return 0;
+    };
+    if (precond == DMX_PRECOND_PARMT_JAC) {
+        if (!ctx->d_xold) DMX_CUDA(cudaMalloc((void**)&ctx->d_xold, len * sizeof(double)));
+        for (int it = 0; it < ctx->precond_iterations; ++it) {
+            DMX_CUDA(cudaMemcpyAsync(ctx->d_xold, v, len * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+            if (int rc = launch(ctx->n, nullptr, ctx->d_xold, v)) return rc;
+        }
+        return 0;
+    }
+    const int ncol = (int)ctx->color_ptr.size() - 1;
+    auto sweep = [&](bool forward) -> int {
+        for (int cc = 0; cc < ncol; ++cc) {
+            const int c = forward ? cc : ncol - 1 - cc;
+            if (int rc = launch(ctx->color_ptr[c + 1] - ctx->color_ptr[c], ctx->d_color_rows + ctx->color_ptr[c], v, v)) return rc;
+        }
+        return 0;
+    };
+    for (int it = 0; it < ctx->precond_iterations; ++it) {
+        if (int rc = sweep(true)) return rc;
+        if (precond == DMX_PRECOND_PARMT_SSOR)
+            if (int rc = sweep(false)) return rc;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // BiCGSTAB: Dune::BiCGSTABSolver::apply restated.  x = DELTA (initial guess as given),
 // b = RESIDUAL (not modified).  In a distributed ctx: operator = local SpMV + project, preconditioner = local
 // ILU0 + copyOwnerToAll, scalar product = owner-masked dot + all-reduce (OverlappingSchwarz*, BlockPreconditioner).
 // ---------------------------------------------------------------------------------------------
 // fresh preconditioner per solve (istlsolvers.hh:457-463); SeqSSOR has no set-up
-static int precond_setup(dmx_ctx* ctx, int precond)
+int precond_setup(dmx_ctx* ctx, int precond)
 {
     if (precond == DMX_PRECOND_ILU0) return ilu0_factor(ctx);
-    if (precond == DMX_PRECOND_SSOR) {
-        if (ctx->nranks > 1) return fail(ctx, DMX_ERR_USAGE, "SSOR runs on a single domain in this version");
+    if (precond == DMX_PRECOND_SSOR) return 0;
+    if (precond == DMX_PRECOND_BLOCKJACOBI) return block_jacobi_setup(ctx);
+    if (precond == DMX_PRECOND_PARMT_JAC) return 0;
+    if (precond == DMX_PRECOND_PARMT_SOR || precond == DMX_PRECOND_PARMT_SSOR) {
+        if (ctx->color_ptr.empty()) return parmt_build_colors(ctx);
         return 0;
     }
-    if (precond == DMX_PRECOND_BLOCKJACOBI) return block_jacobi_setup(ctx);
     return fail(ctx, DMX_ERR_USAGE, "unknown preconditioner");
 }
+// the sequential preconditioner on this rank's (interior + overlap) matrix
+int precond_apply_local(dmx_ctx* ctx, int precond, const double* d, double* v)
+{
+    switch (precond) {
+        case DMX_PRECOND_ILU0: return ilu0_apply(ctx, d, v);
+        case DMX_PRECOND_SSOR: return ssor_apply(ctx, d, v);
+        case DMX_PRECOND_BLOCKJACOBI: return block_jacobi_apply(ctx, d, v);
+        case DMX_PRECOND_PARMT_JAC:
+        case DMX_PRECOND_PARMT_SOR:
+        case DMX_PRECOND_PARMT_SSOR: return parmt_apply(ctx, precond, d, v);
+    }
+    return fail(ctx, DMX_ERR_USAGE, "unknown preconditioner");
+}
+// BlockPreconditioner::apply: the sequential preconditioner, then copyOwnerToAll
 static int precond_apply(dmx_ctx* ctx, int precond, const double* d, double* v)
 {
-    int rc = (precond == DMX_PRECOND_ILU0) ? ilu0_apply(ctx, d, v) : (precond == DMX_PRECOND_SSOR ? ssor_apply(ctx, d, v) : block_jacobi_apply(ctx, d, v));
-    if (rc) return rc;
+    if (int rc = precond_apply_local(ctx, precond, d, v)) return rc;
     if (ctx->nranks > 1) return halo_exchange(ctx, v);
     return 0;
 }
@@ -1088,7 +1223,8 @@ int gmres(dmx_ctx* ctx, double reduction, int maxit, int restart, int precond, i
 // ---------------------------------------------------------------------------------------------
 int cg(dmx_ctx* ctx, double reduction, int maxit, int precond, int* iterations, double* achieved)
 {
-    if (ctx->nranks > 1) return fail(ctx, DMX_ERR_USAGE, "CG runs on a single domain in this version");
+    // distributed ctx: the overlapping-Schwarz pieces as in bicgstab() (operator projects, dots are owner-masked + all-reduced,
+    // the preconditioner is followed by copyOwnerToAll)
     const size_t len = (size_t)ctx->n * ctx->b;
     double* x = ctx->d_vec[DMX_VEC_DELTA];
     const double* rhs = ctx->d_vec[DMX_VEC_RESIDUAL];
@@ -1104,6 +1240,7 @@ int cg(dmx_ctx* ctx, double reduction, int maxit, int precond, int* iterations, 
         DMX_CHECK_LAUNCH();
         return 0;
     };
+    if (ctx->nranks > 1 && (rc = halo_exchange(ctx, x))) return rc;       // BlockPreconditioner::pre: copyOwnerToAll(x)
     if ((rc = launch_spmv(ctx, x, q))) return rc;
     {
         ProfScope ps(ctx, DMX_K_BLAS1);

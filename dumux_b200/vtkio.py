@@ -91,3 +91,81 @@ def load_solution(path, pv_names):
     if missing:
         raise KeyError(f"{path}: no cell data named {missing} (available: {list(data)})")
     return np.stack([data[nm].astype(np.float64) for nm in pv_names], axis=1)
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# Parallel output / restart (dumux/io/vtkoutputmodule.hh:346 with Dune's parallel VTKWriter; dumux/io/loadsolution.hh:43,332)
+# ------------------------------------------------------------------------------------------------------------------------
+def piece_name(name, index, nranks, rank):
+    """Dune's parallel file names: s<P>-p<r>-<name>-<index>.vtu (the reference's parallel tests compare exactly these files,
+    e.g. s0002-p0000-test_richards_lens_tpfa_parallel_yasp-00007.vtu, test/porousmediumflow/richards/lens/CMakeLists.txt:91-112)"""
+    return f"s{nranks:04d}-p{rank:04d}-{name}-{index:05d}.vtu"
+
+
+def pvtu_name(name, index, nranks):
+    return f"s{nranks:04d}-{name}-{index:05d}.pvtu"
+
+
+def write_piece(dirpath, name, index, nranks, rank, node_coords, own_lo, own_hi, fields):
+    """This rank's <Piece>: the cells it OWNS (interior partition -- what Dune's VTKWriter iterates over; the rank-0 piece of
+    test_richards_lens_tpfa_parallel-reference.vtu holds 12x16 of the 24x16 cells) with their vertices.  `node_coords`: the node
+    coordinates of the local box (overlap included), `own_lo/own_hi`: owned index range per axis (local), `fields`: name ->
+    array over ALL local cells (x fastest); the overlap cells are cut away here.  Returns the path."""
+    import os
+    dim = len(node_coords)
+    lc = [len(c) - 1 for c in node_coords]
+    sl = tuple(slice(int(own_lo[a]), int(own_hi[a])) for a in range(dim - 1, -1, -1))
+    owned = {}
+    for k, v in fields.items():
+        v = np.asarray(v)
+        shp = tuple(lc[::-1]) + v.shape[1:]
+        w = v.reshape(shp)[sl]
+        owned[k] = w.reshape((-1,) + v.shape[1:])
+    nodes = [np.asarray(node_coords[a])[int(own_lo[a]):int(own_hi[a]) + 1] for a in range(dim)]
+    path = os.path.join(dirpath, piece_name(name, index, nranks, rank))
+    write_vtu(path, nodes, owned, rank=rank)
+    return path
+
+
+def write_pvtu(dirpath, name, index, nranks, field_components):
+    """The master file rank 0 writes: one <Piece Source=.../> per rank and the declarations of the cell data
+    (`field_components`: ordered mapping name -> number of components; `process rank` is appended as in the pieces)."""
+    import os
+    root = ET.Element("VTKFile", type="PUnstructuredGrid", version="0.1", byte_order="LittleEndian")
+    grid = ET.SubElement(root, "PUnstructuredGrid", GhostLevel="0")
+    names = list(field_components.keys())
+    cd = ET.SubElement(grid, "PCellData", Scalars=names[0] if names else "process rank")
+    for nm in names + ["process rank"]:
+        ET.SubElement(cd, "PDataArray", type="Float32", Name=nm, NumberOfComponents=str(field_components.get(nm, 1)))
+    ET.SubElement(ET.SubElement(grid, "PPoints"), "PDataArray", type="Float32", NumberOfComponents="3")
+    for r in range(nranks):
+        ET.SubElement(grid, "Piece", Source=piece_name(name, index, nranks, r))
+    ET.indent(root, space="  ")
+    path = os.path.join(dirpath, pvtu_name(name, index, nranks))
+    with open(path, "wb") as f:
+        f.write(b'<?xml version="1.0"?>\n')
+        ET.ElementTree(root).write(f, encoding="utf-8", xml_declaration=False)
+        f.write(b"\n")
+    return path
+
+
+def read_pvtu(path):
+    """(list of piece paths, list of cell-data names) of a .pvtu master file"""
+    import os
+    grid = ET.parse(path).getroot().find("PUnstructuredGrid")
+    pieces = [os.path.join(os.path.dirname(path), p.get("Source")) for p in grid.findall("Piece")]
+    names = [d.get("Name") for d in grid.find("PCellData")]
+    return pieces, names
+
+
+def load_solution_piece(pvtu_path, rank, pv_names, local_cells, own_lo, own_hi):
+    """loadSolution on rank `rank` of a parallel run (dumux/io/loadsolution.hh:332 reads the rank's own piece of the .pvtu; the
+    overlap entries are then filled from their owners by the communication of :43 -- here: Engine.halo_exchange after the
+    upload).  Returns the LOCAL vector [n_local, numEq] with the owned cells filled and the overlap cells zero."""
+    pieces, _ = read_pvtu(pvtu_path)
+    own = load_solution(pieces[rank], pv_names)
+    dim = len(local_cells)
+    out = np.zeros(tuple(int(c) for c in local_cells[::-1]) + (len(pv_names),))
+    sl = tuple(slice(int(own_lo[a]), int(own_hi[a])) for a in range(dim - 1, -1, -1))
+    out[sl] = own.reshape(out[sl].shape)
+    return out.reshape(-1, len(pv_names))

@@ -35,7 +35,11 @@ enum { DMX_BC_NEUMANN = 0, DMX_BC_DIRICHLET = 1, DMX_BC_NONE = 2, DMX_BC_OUTFLOW
 enum { DMX_DIFF_ANALYTIC = 100 };
 /* SSOR = Dune::SeqSSOR(1 iteration, relaxation 1): the preconditioner of SSORCGIstlSolver / SSORBiCGSTABIstlSolver
    (linear/istlsolvers.hh:686-714) */
-enum { DMX_PRECOND_ILU0 = 0, DMX_PRECOND_BLOCKJACOBI = 1, DMX_PRECOND_SSOR = 2 };
+/* PARMT_*: DuMux's own multi-threaded smoothers Dumux::ParMTJac / ParMTSOR / ParMTSSOR ("par_mt_jac", "par_mt_sor", "par_mt_ssor";
+   dumux/linear/preconditioners.hh:330-400, 489-620): Jacobi, and (S)SOR colour by colour with the greedy colouring of
+   computeColorsForMatrixSweep_ (:408-440); iterations / relaxation from dmx_set_preconditioner_params */
+enum { DMX_PRECOND_ILU0 = 0, DMX_PRECOND_BLOCKJACOBI = 1, DMX_PRECOND_SSOR = 2, DMX_PRECOND_PARMT_JAC = 3, DMX_PRECOND_PARMT_SOR = 4,
+       DMX_PRECOND_PARMT_SSOR = 5 };
 /* Krylov method behind dmx_linear_solve / dmx_newton_*: ILUBiCGSTABIstlSolver (linear/istlsolvers.hh:636-642, default) or
    ILURestartedGMResIstlSolver (:660-667) */
 enum { DMX_SOLVER_BICGSTAB = 0, DMX_SOLVER_RESTARTED_GMRES = 1, DMX_SOLVER_CG = 2 };   /* CG: Dune::CGSolver (SSORCGIstlSolver :701-714) */
@@ -217,6 +221,11 @@ int  dmx_num_output_fields(const dmx_ctx* ctx);
 int  dmx_output_fields(dmx_ctx* ctx, double* out);
 /* v = SeqSSOR(J)(d) from v = 0: one forward + one backward block Gauss-Seidel sweep (dune-istl gsetc.hh bsorf/bsorb, w = 1) */
 int  dmx_ssor_apply(dmx_ctx* ctx, int d_vec, int v_vec);
+/* LinearSolver.PreconditionerIterations / PreconditionerRelaxation (linear/linearsolverparameters.hh:61-62,121-122; defaults 1 / 1.0):
+   honoured by the DMX_PRECOND_PARMT_* smoothers */
+int  dmx_set_preconditioner_params(dmx_ctx* ctx, int iterations, double relaxation);
+/* v = M^-1 d for any DMX_PRECOND_* on this rank's matrix (sets the preconditioner up first; no halo exchange) */
+int  dmx_precond_apply(dmx_ctx* ctx, int preconditioner, int d_vec, int v_vec);
 int  dmx_dot(dmx_ctx* ctx, int a_vec, int b_vec, double* out);
 int  dmx_halo_exchange(dmx_ctx* ctx, int vec);                           /* copyOwnerToAll */
 /* average device time in ms of `reps` back-to-back launches of one kernel, CUDA-event timed on the ctx stream.

@@ -254,15 +254,29 @@ class BoxRank:
         y[~self.owner] = 0.0                                         # project()
         return y
 
-    def bicgstab(self, jac, rhs, reduction=1e-6, maxit=250):
+    def local_preconditioner(self, jac, precond="ilu0", iterations=1, relaxation=1.0):
+        """The sequential preconditioner of this rank's (interior + overlap) matrix: d -> M^-1 d, or None if the set-up fails
+        on any rank.  "ilu0" = SeqILU(0), "ssor" = SeqSSOR, "par_mt_jac" / "par_mt_sor" / "par_mt_ssor" = Dumux::ParMT*."""
+        n, b, rp, ci = self.n, self.b, self.o.rowptr, self.o.colidx
+        if precond == "ilu0":
+            ilu, st = O.ilu0_factor(n, b, rp, ci, jac)
+            st = int(self.comm.allreduce(float(st), "max"))
+            if st != 0:
+                return None
+            return lambda d: O.ilu0_apply(n, b, rp, ci, ilu, d)
+        if precond == "ssor":
+            return lambda d: O.ssor_apply(n, b, rp, ci, jac, d)
+        kind = {"par_mt_jac": O.PARMT_JAC, "par_mt_sor": O.PARMT_SOR, "par_mt_ssor": O.PARMT_SSOR}[precond]
+        return lambda d: O.parmt_apply(kind, n, b, rp, ci, jac, d, iterations, relaxation)
+
+    def bicgstab(self, jac, rhs, reduction=1e-6, maxit=250, precond="ilu0", iterations=1, relaxation=1.0):
         """Dune::BiCGSTABSolver::apply with the overlapping-Schwarz operator / scalar product / BlockPreconditioner; x0 = 0."""
-        ilu, st = O.ilu0_factor(self.n, self.b, self.o.rowptr, self.o.colidx, jac)
-        st = int(self.comm.allreduce(float(st), "max"))
-        if st != 0:
+        local = self.local_preconditioner(jac, precond, iterations, relaxation)
+        if local is None:
             return np.zeros_like(rhs), 2, 0, 1.0
 
         def prec(d):
-            v = O.ilu0_apply(self.n, self.b, self.o.rowptr, self.o.colidx, ilu, d)
+            v = local(d)
             self.copy_owner_to_all(v)
             return v
 
@@ -325,6 +339,56 @@ class BoxRank:
                 break
             it += 0.5
         return x, status, int(math.ceil(min(it, maxit))), (norm / norm0 if norm0 > 0 else 0.0)
+
+    def cg(self, jac, rhs, reduction=1e-6, maxit=250, precond="ssor", iterations=1, relaxation=1.0):
+        """Dune::CGSolver::apply (see oracle.cpp cgSolve) with the overlapping-Schwarz operator / scalar product /
+        BlockPreconditioner; x0 = 0.  Returns (x, status, iterations, achieved reduction)."""
+        local = self.local_preconditioner(jac, precond, iterations, relaxation)
+        if local is None:
+            return np.zeros_like(rhs), 2, 0, 1.0
+
+        def prec(d):
+            v = local(d)
+            self.copy_owner_to_all(v)
+            return v
+
+        x = np.zeros_like(rhs)
+        self.copy_owner_to_all(x)
+        b = rhs - O.spmv(self.n, self.b, self.o.rowptr, self.o.colidx, jac, x)
+        b[~self.owner] = 0.0
+        def0 = math.sqrt(self.dot(b, b))
+        if not math.isfinite(def0):
+            return x, 3, 0, 1.0
+        conv = lambda nrm: nrm < reduction * def0 or nrm < 1e-30
+        if conv(def0):
+            return x, 0, 0, (1.0 if def0 > 0 else 0.0)
+        p = prec(b)
+        rholast = self.dot(p, b)
+        deff, status, i = def0, 1, 1
+        while i <= maxit:
+            q = self.apply_operator(jac, p)
+            alpha = self.dot(p, q)
+            lam = rholast / alpha
+            x += lam * p
+            b += (-lam) * q
+            deff = math.sqrt(self.dot(b, b))
+            its = i
+            if not math.isfinite(deff):
+                status = 3
+                break
+            if conv(deff):
+                status = 0
+                break
+            q = prec(b)
+            rho = self.dot(q, b)
+            beta = rho / rholast
+            p = p * beta
+            p += q
+            rholast = rho
+            i += 1
+        else:
+            its = maxit
+        return x, status, its, (deff / def0 if def0 > 0 else 0.0)
 
     def gmres(self, jac, rhs, reduction=1e-6, maxit=250, restart=10):
         """Dune::RestartedGMResSolver::apply (left preconditioned, see oracle.cpp restartedGmres) with the overlapping-Schwarz

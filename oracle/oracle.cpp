@@ -1105,6 +1105,73 @@ void ssorApply(int n, int b, const int* rowptr, const int* colidx, const double*
     for (int i = n - 1; i >= 0; --i) row(i);
 }
 
+// Dumux::ParMTJac / ParMTSOR / ParMTSSOR (dumux/linear/preconditioners.hh:330-400, 442-620): DuMux's own multi-threaded smoothers.
+// Colours: computeColorsForMatrixSweep_ (:408-440) -- rows in index order take the smallest colour none of their matrix
+// neighbours has (Detail::smallestAvailableColor, dumux/assembly/coloring.hh:195-215; the row's own, still unset colour -1 is
+// in the list); the 7-point stencil in lexicographic order gets the two checkerboard colours.  Sweeps: parallelBlockSOR_
+// (:442-476) colour by colour (backward: colours descending), per row rhs = b_i - sum_j A_ij update_j over ALL columns in
+// ascending order (diagonal included, newest values), v = A_ii^-1 rhs (bsorf/bsorb at block level 0: FieldMatrix::solve),
+// update_i += w v.  ParMTJac::apply (:364-393): the same row formula against the PREVIOUS iterate, all rows at once.
+void parmtColors(int n, const int* rowptr, const int* colidx, std::vector<int>& colors, int& ncolors)
+{
+    colors.assign(n, -1);
+    ncolors = 0;
+    std::vector<int> nb;
+    std::vector<char> used;
+    for (int i = 0; i < n; ++i) {
+        nb.clear();
+        for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) nb.push_back(colors[colidx[k]]);
+        const int m = (int)nb.size();
+        used.assign(m, 0);
+        for (int q = 0; q < m; ++q)
+            if (nb[q] >= 0 && nb[q] < m) used[nb[q]] = 1;
+        int c = m;
+        for (int q = 0; q < m; ++q)
+            if (!used[q]) { c = q; break; }
+        colors[i] = c;
+        ncolors = std::max(ncolors, c + 1);
+    }
+}
+// kind 0: ParMTJac, 1: ParMTSOR (forward sweeps), 2: ParMTSSOR (forward + backward per iteration)
+void parmtApply(int kind, int n, int b, const int* rowptr, const int* colidx, const double* A, double* update, const double* defect,
+                int iterations, double w)
+{
+    const int bb = b * b;
+    auto row = [&](int i, const double* xin) {
+        double rhs[2], v[2];
+        for (int e = 0; e < b; ++e) rhs[e] = defect[(size_t)i * b + e];
+        int kd = -1;
+        for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+            if (colidx[k] == i) kd = k;
+            mmv(A + (size_t)k * bb, xin + (size_t)colidx[k] * b, rhs, b);
+        }
+        blockSolve(A + (size_t)kd * bb, rhs, v, b);
+        for (int e = 0; e < b; ++e) update[(size_t)i * b + e] += w * v[e];
+    };
+    if (kind == 0) {
+        std::vector<double> xOld(update, update + (size_t)n * b);
+        for (int it = 0; it < iterations; ++it) {
+            if (it > 0) std::copy(update, update + (size_t)n * b, xOld.begin());
+            for (int i = 0; i < n; ++i) row(i, xOld.data());
+        }
+        return;
+    }
+    std::vector<int> colors;
+    int nc = 0;
+    parmtColors(n, rowptr, colidx, colors, nc);
+    auto sweep = [&](bool forward) {
+        for (int cc = 0; cc < nc; ++cc) {
+            const int c = forward ? cc : nc - 1 - cc;
+            for (int i = 0; i < n; ++i)
+                if (colors[i] == c) row(i, update);
+        }
+    };
+    for (int it = 0; it < iterations; ++it) {
+        sweep(true);
+        if (kind == 2) sweep(false);
+    }
+}
+
 // Dune::CGSolver::apply (dune-istl solvers.hh) [DUNE-ext]: preconditioned conjugate gradients, the defect norm is that of b - A x
 template <class Op, class Prec, class Dot>
 int cgSolve(size_t N, Op&& op, Prec&& prec, Dot&& sp, double* x, const double* rhs, double reduction, int maxit, int* iterations,
@@ -1494,6 +1561,31 @@ void orc_ssor_apply(int n, int b, const int* rowptr, const int* colidx, const do
 {
     std::fill(v, v + (size_t)n * b, 0.0);
     ssorApply(n, b, rowptr, colidx, values, v, d);
+}
+// the "par_mt_jac" / "par_mt_sor" / "par_mt_ssor" preconditioners (preconditioners.hh:400,540,618) under CG (krylov 0) or BiCGSTAB
+int orc_parmt_solve(int kind, int iterations, double relaxation, int n, int b, const int* rowptr, const int* colidx, const double* values,
+                    double* x, const double* rhs, int krylov, double reduction, int maxit, int* its, double* achieved)
+{
+    const size_t N = (size_t)n * b;
+    auto op = [&](const double* in, double* out) { spmv(n, b, rowptr, colidx, values, in, out); };
+    auto prec = [&](double* v, const double* d) { parmtApply(kind, n, b, rowptr, colidx, values, v, d, iterations, relaxation); };
+    auto sp = [&](const double* a, const double* c) { return dot(N, a, c); };
+    if (krylov == 0) return cgSolve(N, op, prec, sp, x, rhs, reduction, maxit, its, achieved);
+    return bicgstab(N, op, prec, sp, x, rhs, reduction, maxit, its, achieved);
+}
+void orc_parmt_apply(int kind, int iterations, double relaxation, int n, int b, const int* rowptr, const int* colidx, const double* values,
+                     double* v, const double* d)
+{
+    std::fill(v, v + (size_t)n * b, 0.0);
+    parmtApply(kind, n, b, rowptr, colidx, values, v, d, iterations, relaxation);
+}
+int orc_parmt_colors(int n, const int* rowptr, const int* colidx, int* colors)
+{
+    std::vector<int> c;
+    int nc = 0;
+    parmtColors(n, rowptr, colidx, c, nc);
+    std::copy(c.begin(), c.end(), colors);
+    return nc;
 }
 void orc_set_tracer_diffusion(orc_problem* p, double D, double tortuosity)
 {

@@ -90,6 +90,12 @@ int  orc_ssor_solve(int n, int b, const int* rowptr, const int* colidx, const do
                     double reduction, int maxit, int* iterations, double* achieved_reduction);
 /* v = SeqSSOR(A)(d) from v = 0 (one forward + one backward block Gauss-Seidel sweep) */
 void orc_ssor_apply(int n, int b, const int* rowptr, const int* colidx, const double* values, double* v, const double* d);
+/* Dumux::ParMTJac (kind 0) / ParMTSOR (1) / ParMTSSOR (2), dumux/linear/preconditioners.hh:330-620 */
+int  orc_parmt_solve(int kind, int iterations, double relaxation, int n, int b, const int* rowptr, const int* colidx, const double* values,
+                     double* x, const double* rhs, int krylov, double reduction, int maxit, int* its, double* achieved);
+void orc_parmt_apply(int kind, int iterations, double relaxation, int n, int b, const int* rowptr, const int* colidx, const double* values,
+                     double* v, const double* d);
+int  orc_parmt_colors(int n, const int* rowptr, const int* colidx, int* colors);
 /* tracer: binary diffusion coefficient D (FluidSystem::binaryDiffusionCoefficient) and SpatialParams.Tortuosity (default 0.5) of
    DiffusivityConstantTortuosity; D = 0 (the default) switches Fick's law off */
 void orc_set_tracer_diffusion(orc_problem* p, double D, double tortuosity);

@@ -97,6 +97,12 @@ def lib():
                                      C.POINTER(C.c_int), C.POINTER(C.c_double)]
         L.orc_ssor_solve.restype = C.c_int
         L.orc_ssor_apply.argtypes = [C.c_int, C.c_int, _ip, _ip, _dp, _dp, _dp]
+        L.orc_parmt_solve.argtypes = [C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, _ip, _ip, _dp, _dp, _dp, C.c_int, C.c_double, C.c_int,
+                                      C.POINTER(C.c_int), C.POINTER(C.c_double)]
+        L.orc_parmt_solve.restype = C.c_int
+        L.orc_parmt_apply.argtypes = [C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, _ip, _ip, _dp, _dp, _dp]
+        L.orc_parmt_colors.argtypes = [C.c_int, _ip, _ip, _ip]
+        L.orc_parmt_colors.restype = C.c_int
         L.orc_ilu0_factor.argtypes = [C.c_int, C.c_int, _ip, _ip, _dp, _dp]
         L.orc_ilu0_factor.restype = C.c_int
         L.orc_ilu0_apply.argtypes = [C.c_int, C.c_int, _ip, _ip, _dp, _dp, _dp]
@@ -316,6 +322,32 @@ def ssor_solve(n, b, rowptr, colidx, values, rhs, krylov="cg", reduction=1e-6, m
     st = lib().orc_ssor_solve(n, b, rowptr, colidx, np.ascontiguousarray(values), x, np.ascontiguousarray(rhs),
                               {"cg": 0, "bicgstab": 1}[krylov], reduction, maxit, C.byref(its), C.byref(red))
     return x, st, its.value, red.value
+
+
+PARMT_JAC, PARMT_SOR, PARMT_SSOR = 0, 1, 2
+
+
+def parmt_apply(kind, n, b, rowptr, colidx, values, d, iterations=1, relaxation=1.0):
+    """v = ParMTJac / ParMTSOR / ParMTSSOR (dumux/linear/preconditioners.hh:330-620) applied to d from v = 0"""
+    v = np.zeros(n * b)
+    lib().orc_parmt_apply(kind, iterations, relaxation, n, b, rowptr, colidx, np.ascontiguousarray(values, dtype=np.float64),
+                          v, np.ascontiguousarray(d, dtype=np.float64))
+    return v
+
+
+def parmt_solve(kind, n, b, rowptr, colidx, values, rhs, krylov="bicgstab", reduction=1e-6, maxit=250, iterations=1, relaxation=1.0, x0=None):
+    x = np.zeros(n * b) if x0 is None else np.ascontiguousarray(x0, dtype=np.float64).copy()
+    its, red = C.c_int(0), C.c_double(0)
+    st = lib().orc_parmt_solve(kind, iterations, relaxation, n, b, rowptr, colidx, np.ascontiguousarray(values, dtype=np.float64), x,
+                               np.ascontiguousarray(rhs, dtype=np.float64), 0 if krylov == "cg" else 1, reduction, maxit,
+                               C.byref(its), C.byref(red))
+    return x, st, its.value, red.value
+
+
+def parmt_colors(n, rowptr, colidx):
+    colors = np.zeros(n, dtype=np.int32)
+    nc = lib().orc_parmt_colors(n, rowptr, colidx, colors)
+    return colors, nc
 
 
 def ilu0_factor(n, b, rowptr, colidx, values):

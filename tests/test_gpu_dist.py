@@ -44,8 +44,10 @@ def _cpu_rank_job(rank_obj):
     x, st, its, red = rank_obj.bicgstab(jac, res, reduction=1e-10, maxit=500)
     xg, stg, itsg, redg = rank_obj.gmres(jac, res, reduction=1e-10, maxit=500, restart=10)
     u, nst, nsteps, lin_its = rank_obj.newton(rank_obj.spec.initial, rank_obj.spec.initial)
+    # BlockPreconditioner<SeqSSOR> (SSORBiCGSTABIstlSolver) and <ParMTSSOR> on the overlapping decomposition
+    other = {pc: rank_obj.bicgstab(jac, res, reduction=1e-8, maxit=2000, precond=pc) for pc in ("ssor", "par_mt_ssor")}
     return {"res": res, "jac": jac, "x": x, "st": st, "its": its, "u": u, "nst": nst, "nsteps": nsteps, "lin_its": lin_its,
-            "xg": xg, "stg": stg, "itsg": itsg, "redg": redg}
+            "xg": xg, "stg": stg, "itsg": itsg, "redg": redg, "other": other}
 
 
 def _gpu_worker(rank, world, uid, q, part=None):
@@ -64,6 +66,8 @@ def _gpu_worker(rank, world, uid, q, part=None):
         eng.set_linear_solver("gmres", 10)
         xg, stg, itsg, redg = eng.solve(jac, res, reduction=1e-10, maxit=500)
         eng.set_linear_solver("bicgstab")
+        other = {name: eng.solve(jac, res, reduction=1e-8, maxit=2000, precond=pc)
+                 for name, pc in (("ssor", B.PRECOND_SSOR), ("par_mt_ssor", B.PRECOND_PARMT_SSOR))}
         # halo exchange primitive: fill a vector with the rank id, exchange: every cell then carries its OWNER's rank id
         v = np.full(eng.n * eng.b, float(rank))
         eng.upload(B.VEC_WORK1, v)
@@ -71,6 +75,26 @@ def _gpu_worker(rank, world, uid, q, part=None):
         halo = eng.download(B.VEC_WORK1).reshape(-1, eng.b)[:, 0].copy()
         nrm = eng.norm(B.VEC_RESIDUAL)
         u, nst, rep = eng.newton(spec.initial, spec.initial)
+        # parallel output + restart: my piece holds my OWNED cells; a restart reads it back and the overlap is filled from the
+        # owners by copyOwnerToAll (io/vtkoutputmodule.hh:346, io/loadsolution.hh:43,332)
+        import tempfile
+        from dumux_b200 import vtkio
+        outdir = tempfile.mkdtemp(prefix=f"dmx_pvtu_r{rank}_")
+        u2 = u.reshape(-1, 2)
+        nodes = [problems.node_coords(CELLS, spec.lower, spec.upper)[a][box[a][0]:box[a][1] + 1] for a in range(3)]
+        vtkio.write_piece(outdir, "restart", 1, world, rank, nodes, eng.own_lo, eng.own_hi, {"p_aq": u2[:, 0], "S_napl": u2[:, 1]})
+        master = vtkio.write_pvtu(outdir, "restart", 1, world, {"p_aq": 1, "S_napl": 1})
+        pieces, _ = vtkio.read_pvtu(master)
+        own = vtkio.load_solution(pieces[rank], ["p_aq", "S_napl"])
+        lc = [int(c) for c in eng.local_cells]
+        loc = np.zeros((lc[2], lc[1], lc[0], 2))
+        loc[tuple(slice(int(eng.own_lo[a]), int(eng.own_hi[a])) for a in (2, 1, 0))] = own.reshape(
+            tuple(int(eng.own_hi[a] - eng.own_lo[a]) for a in (2, 1, 0)) + (2,))
+        eng.upload(B.VEC_WORK1, loc.reshape(-1))
+        eng.halo_exchange(B.VEC_WORK1)
+        restarted = eng.download(B.VEC_WORK1)
+        stored = np.array([float("%.6g" % v) for v in u.astype(np.float32)])          # what a %.6g Float32 file keeps of u
+        restart_ok = bool(np.array_equal(restarted.astype(np.float32), stored.astype(np.float32)))
         # cross-rank failure agreement (assembly/fvassembler.hh:504-509 comm.min): a NaN on ONE rank makes EVERY rank
         # return DMX_STATUS_NONFINITE from the assembly instead of leaving the others in the next collective
         bad = spec.initial.copy()
@@ -86,7 +110,8 @@ def _gpu_worker(rank, world, uid, q, part=None):
         q.put((rank, {"res": res, "jac": jac, "x": x, "st": st, "its": its, "halo": halo, "norm": nrm, "u": u, "nst": nst,
                       "nsteps": rep.newton_iterations, "lin_its": [rep.linear_iterations[i] for i in range(rep.newton_iterations)],
                       "launches": eng.launches(), "xg": xg, "stg": stg, "itsg": itsg, "redg": redg,
-                      "st_bad": st_bad, "st_step": st_step, "st_ok": st_ok}))
+                      "st_bad": st_bad, "st_step": st_step, "st_ok": st_ok, "other": other,
+                      "restart_ok": restart_ok}))
         eng.close()
     except BaseException as e:      # noqa: BLE001
         import traceback
@@ -140,6 +165,11 @@ def test_decomposed_newton_step_matches_cpu_reference(world, part):
             assert g["redg"] == pytest.approx(c["redg"], rel=1e-5)
         assert np.linalg.norm(g["xg"] - c["xg"]) <= 1e-7 * np.linalg.norm(c["xg"])
         assert np.linalg.norm(g["xg"] - g["x"]) <= 1e-6 * np.linalg.norm(g["x"])          # both solve the same global system
+        # the other block preconditioners on the decomposition: same counts (2 ranks: identical iteration), same solution
+        for name in ("ssor", "par_mt_ssor"):
+            (xa, sta, ita, _), (xb, stb, itb, _) = g["other"][name], c["other"][name]
+            assert sta == 0 and stb == 0 and abs(ita - itb) <= (0 if world == 2 else 2), (name, ita, itb)
+            assert np.linalg.norm(xa - xb) <= 1e-6 * np.linalg.norm(xb)
         # Newton: same iteration count, fields to 1e-8
         assert g["nst"] == 0 and g["nsteps"] == c["nsteps"]
         if world == 2:
@@ -150,6 +180,7 @@ def test_decomposed_newton_step_matches_cpu_reference(world, part):
         assert g["launches"] > 0
         # failure agreement: every rank reports the NaN that only the last rank holds, and recovers
         assert g["st_bad"] == B.STATUS_NONFINITE and g["st_step"] == B.STATUS_NONFINITE and g["st_ok"] == 0
+        assert g["restart_ok"]
     # global norm = sqrt(sum of owned squares)
     owned = D.gather_owned([ref[r]["res"] for r in range(world)], CELLS, world, 2, part)
     assert abs(got[0]["norm"] - np.linalg.norm(owned)) <= 1e-12 * np.linalg.norm(owned)

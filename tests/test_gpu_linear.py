@@ -215,3 +215,51 @@ def test_singular_block_reports_breakdown(engine_factory):
     e = engine_factory(spec)
     e.upload_jacobian(jac)
     assert e.ilu0_factor() == B.STATUS_BREAKDOWN
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# Dumux::ParMTJac / ParMTSOR / ParMTSSOR (dumux/linear/preconditioners.hh:330-620): DuMux's own multi-threaded smoothers
+# ------------------------------------------------------------------------------------------------------------------------
+_PARMT = [(B.PRECOND_PARMT_JAC, O.PARMT_JAC), (B.PRECOND_PARMT_SOR, O.PARMT_SOR), (B.PRECOND_PARMT_SSOR, O.PARMT_SSOR)]
+
+
+@pytest.mark.parametrize("spec", [problems.onep_incompressible((10, 10)), problems.twop_lens((13, 9, 7), law="bc", heterogeneity_sigma=0.3)],
+                         ids=["1p-2d", "2p-3d"])
+@pytest.mark.parametrize("iterations,relaxation", [(1, 1.0), (3, 0.8)])
+def test_parmt_smoothers_bit_exact(engine_factory, spec, iterations, relaxation):
+    """One application from v = 0 equals the restated reference loops bit for bit (same per-row operation order, same colours)."""
+    o, res, jac = _system(spec)
+    colors, nc = O.parmt_colors(o.n, o.rowptr, o.colidx)
+    assert nc == 2                                            # the checkerboard on the 5-/7-point stencil
+    e = engine_factory(spec)
+    e.upload_jacobian(jac)
+    e.upload(B.VEC_WORK0, res)
+    e.set_preconditioner_params(iterations, relaxation)
+    for pg, po in _PARMT:
+        e.precond_apply(pg, B.VEC_WORK0, B.VEC_WORK1)
+        vg = e.download(B.VEC_WORK1)
+        vo = O.parmt_apply(po, o.n, o.b, o.rowptr, o.colidx, jac, res, iterations, relaxation)
+        assert np.array_equal(vg, vo), (pg, iterations, relaxation)
+    e.set_preconditioner_params(1, 1.0)
+
+
+def test_parmt_preconditioned_solves_match_oracle(engine_factory):
+    """BiCGSTAB (and CG where the smoother is symmetric) preconditioned with the ParMT smoothers: the oracle's iteration counts"""
+    spec = problems.twop_lens((13, 9, 7), law="bc", heterogeneity_sigma=0.3)
+    o, res, jac = _system(spec)
+    e = engine_factory(spec)
+    for pg, po in _PARMT:
+        xo, sto, ito, redo = O.parmt_solve(po, o.n, o.b, o.rowptr, o.colidx, jac, res, krylov="bicgstab", reduction=1e-8, maxit=2000)
+        xg, stg, itg, redg = e.solve(jac, res, reduction=1e-8, maxit=2000, precond=pg)
+        assert sto == 0 and stg == 0 and abs(itg - ito) <= 1, (pg, itg, ito)
+        assert np.linalg.norm(xg - xo) <= 1e-6 * np.linalg.norm(xo)
+    spec = problems.onep_incompressible((10, 10))
+    o, res, jac = _system(spec)
+    e = engine_factory(spec)
+    e.set_linear_solver("cg")
+    for pg, po in (_PARMT[0], _PARMT[2]):
+        xo, sto, ito, redo = O.parmt_solve(po, o.n, 1, o.rowptr, o.colidx, jac, res, krylov="cg", reduction=1e-12, maxit=500)
+        xg, stg, itg, redg = e.solve(jac, res, reduction=1e-12, maxit=500, precond=pg)
+        assert sto == 0 and stg == 0 and itg == ito, (pg, itg, ito)
+        assert np.linalg.norm(xg - xo) <= 1e-9 * np.linalg.norm(xo)
+    e.set_linear_solver("bicgstab")

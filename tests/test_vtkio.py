@@ -100,3 +100,54 @@ def test_device_output_fields_equal_oracle_volvars(engine_factory, oilwet, tmp_p
         a, ref = back[nm].astype(np.float64), g[nm].astype(np.float64)
         d = np.abs(a - ref)
         assert np.all((d <= 1.5e-7) | (d <= 1e-2 * np.maximum(np.abs(a), np.abs(ref)))), nm
+
+
+def test_parallel_pieces_and_pvtu(tmp_path):
+    """Per-rank pieces hold the OWNED cells only (as the reference's s0002-p0000-*.vtu pieces do: the rank-0 piece of
+    test_richards_lens_tpfa_parallel-reference.vtu has half of the 24x16 cells), carry `process rank`, follow Dune's parallel file
+    names, and together reproduce the single-domain field; a rank restarts from its own piece (loadSolution) with the overlap
+    left for the owner -> copy communication."""
+    cells, part = (9, 7, 6), (2, 1, 2)
+    P = int(np.prod(part))
+    coords = problems.node_coords(cells, (0.0, 0.0, 0.0), (3.0, 2.0, 1.0))
+    n = int(np.prod(cells))
+    rng = np.random.RandomState(4)
+    # values with at most six significant digits: the ASCII writer prints %.6g like Dune's
+    glob = {"p_aq": (1e5 + rng.randint(0, 1000, size=n)).astype(np.float32).astype(np.float64),
+            "S_napl": np.round(rng.uniform(0, 0.5, size=n), 3).astype(np.float32).astype(np.float64)}
+    g3 = {k: v.reshape(cells[::-1]) for k, v in glob.items()}
+    merged = {k: np.full(cells[::-1], np.nan) for k in glob}
+    for r in range(P):
+        rngs = problems.box_partition(cells, part, r)
+        box = tuple(slice(rngs[a][0], rngs[a][1]) for a in (2, 1, 0))
+        local = {k: v[box].reshape(-1) for k, v in g3.items()}
+        nodes = [coords[a][rngs[a][0]:rngs[a][1] + 1] for a in range(3)]
+        own_lo = [rngs[a][2] - rngs[a][0] for a in range(3)]
+        own_hi = [rngs[a][3] - rngs[a][0] for a in range(3)]
+        path = vtkio.write_piece(str(tmp_path), "run", 3, P, r, nodes, own_lo, own_hi, local)
+        assert os.path.basename(path) == f"s{P:04d}-p{r:04d}-run-00003.vtu"
+        m, back = vtkio.read_vtu(path)
+        assert m == int(np.prod([rngs[a][3] - rngs[a][2] for a in range(3)]))
+        assert np.all(back["process rank"] == r)
+        own = tuple(slice(rngs[a][2], rngs[a][3]) for a in (2, 1, 0))
+        for k in glob:
+            merged[k][own] = back[k].reshape(merged[k][own].shape)
+    master = vtkio.write_pvtu(str(tmp_path), "run", 3, P, {"p_aq": 1, "S_napl": 1})
+    assert os.path.basename(master) == f"s{P:04d}-run-00003.pvtu"
+    pieces, names = vtkio.read_pvtu(master)
+    assert len(pieces) == P and names == ["p_aq", "S_napl", "process rank"] and all(os.path.exists(p) for p in pieces)
+    for k in glob:
+        assert np.array_equal(merged[k].reshape(-1), glob[k])
+    # restart of rank 1: owned cells from its piece, overlap cells untouched (zero) until the halo exchange
+    r = 1
+    rngs = problems.box_partition(cells, part, r)
+    lc = [rngs[a][1] - rngs[a][0] for a in range(3)]
+    own_lo = [rngs[a][2] - rngs[a][0] for a in range(3)]
+    own_hi = [rngs[a][3] - rngs[a][0] for a in range(3)]
+    u = vtkio.load_solution_piece(master, r, ["p_aq", "S_napl"], lc, own_lo, own_hi).reshape(lc[2], lc[1], lc[0], 2)
+    own = tuple(slice(own_lo[a], own_hi[a]) for a in (2, 1, 0))
+    gl = tuple(slice(rngs[a][2], rngs[a][3]) for a in (2, 1, 0))
+    assert np.array_equal(u[own][..., 0], g3["p_aq"][gl]) and np.array_equal(u[own][..., 1], g3["S_napl"][gl])
+    mask = np.ones(u.shape[:3], dtype=bool)
+    mask[own] = False
+    assert mask.any() and np.all(u[mask] == 0.0)
