@@ -60,8 +60,17 @@ def emit(line):
     _RESULT_OUT.flush()
 
 
-def workload_config(cells, edge):
+SOLVER_TEXT = {"ilu0": "ILU0-BiCGSTAB", "amg": "AMG-BiCGSTAB (V-cycle, SSOR smoother, 2+2 steps, damping 1.6)",
+               "amg-ilu": "AMG-BiCGSTAB (V-cycle, ILU0 smoother, 1+1 steps, damping 1.6)"}
+
+
+def workload_config(cells, edge, solver="ilu0"):
     """`config` of a line: the workload only, worded identically by both arms (run-specific facts go into `run`)."""
+    if solver != "ilu0":
+        c = workload_config(cells, edge)
+        c["step"] = c["step"].replace("ILU0 factor", "AMG set-up")
+        c["linear_solver"] = f"{SOLVER_TEXT[solver]}, reduction 1e-6, maxit {LIN_MAXIT}"
+        return c
     return {"workload": f"2p immiscible CCTpfa lens/infiltration, {cells[0]}x{cells[1]}x{cells[2]} cells ({edge}^3 per GPU), Brooks-Corey, "
                         f"lognormal K multiplier sigma 0.5, numeric differentiation (forward, eps 1e-10), 2x2 BCRS blocks",
             "step": "one Newton iteration: assemble + ILU0 factor + BiCGSTAB(1e-6) + update, from the hydrostatic initial state, dt 250 s",
@@ -425,7 +434,7 @@ def parity_check(comm):
     return out
 
 
-def measure(comm, cells, upper, part, steps, warmup, e2e=True, label="bench"):
+def measure(comm, cells, upper, part, steps, warmup, e2e=True, label="bench", solver="ilu0"):
     """One timed region: `steps` device-resident Newton iterations of the lens problem on `cells` (global), decomposed by
     `part`; returns the numbers of the JSON line."""
     import numpy as np
@@ -449,6 +458,10 @@ def measure(comm, cells, upper, part, steps, warmup, e2e=True, label="bench"):
     eng.upload(B.VEC_PREV, u0)
     eng.upload(B.VEC_WORK1, u0)          # device copy of the start state
     prm = eng.newton_params(lin_maxit=LIN_MAXIT)
+    if solver.startswith("amg"):
+        prm.preconditioner = B.PRECOND_AMG
+        if solver == "amg-ilu":
+            eng.set_amg_params(smoother=B.PRECOND_ILU0, pre_steps=1, post_steps=1)
 
     def barrier():
         eng.synchronize()
@@ -493,7 +506,7 @@ def measure(comm, cells, upper, part, steps, warmup, e2e=True, label="bench"):
     launches = eng.launches() - launches0
     prof = {k: eng.profile_read(v) for k, v in (("assembly", B.K_ASSEMBLY), ("spmv", B.K_SPMV),
                                                 ("ilu0_apply", B.K_ILU_APPLY), ("ilu0_factor", B.K_ILU_FACTOR),
-                                                ("blas1", B.K_BLAS1), ("halo", B.K_HALO))}
+                                                ("blas1", B.K_BLAS1), ("halo", B.K_HALO), ("amg_transfer", B.K_AMG))}
     eng.profile(False)
     ms_total = comm.maxreduce(ms_total)
     ms_per_step = ms_total / steps
@@ -564,7 +577,7 @@ def run_b200(args):
     part = tuple(args.part) if args.part else None
     # physical domain: the C3 box [0,6]x[0,4]x[0,4] per edge^3 cube, stretched with the number of cells
     upper = (6.0 * cells[0] / edge, 4.0 * cells[1] / edge, 4.0 * cells[2] / edge)
-    res = measure(comm, cells, upper, part, args.steps, args.warmup, e2e=True)
+    res = measure(comm, cells, upper, part, args.steps, args.warmup, e2e=True, solver=args.solver)
 
     peaks = {}
     try:
@@ -658,7 +671,7 @@ def run_b200(args):
         "ms_per_step": res["ms_per_step"], "higher_is_better": True,
         "scaling": "strong" if (args.global_z or args.global_cells) else "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": workload_config(cells, edge),
+        "config": workload_config(cells, edge, args.solver),
         "run": {"bicgstab_iterations_per_step": res["its"],
                 "parallelism": f"Grid.Partitioning {list(res['part'])}, overlap 1" if world > 1 else "single GPU",
                 "l2_policy": "inputs larger than L2 (Jacobian 3.75 GB, vectors 268 MB per GPU at 256^3)"},
@@ -689,6 +702,9 @@ def main():
     ap.add_argument("--part", type=int, nargs=3, default=None, help="Grid.Partitioning px py pz (default: slabs 1 1 N)")
     ap.add_argument("--cpu-edge", type=int, default=0, help="cube edge of the CPU run (reference arm: default --cells; cpu_baseline leg: 96)")
     ap.add_argument("--cpu-ranks", type=int, default=16, help="reference arm: at most this many overlapping-Schwarz CPU ranks")
+    ap.add_argument("--solver", default="ilu0", choices=["ilu0", "amg", "amg-ilu"],
+                    help="preconditioner of the timed step: ilu0 (the headline, north_star), amg (AMGBiCGSTABIstlSolver with dune-istl's default "
+                         "cycle: SSOR smoother, 2 pre + 2 post steps), amg-ilu (ILU0 smoother, 1 + 1 steps)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cache", action="store_true", help="reference arm: time again even if this box already holds the measurement")
     ap.add_argument("--no-parity-check", action="store_true")

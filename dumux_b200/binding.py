@@ -23,6 +23,7 @@ EXPORTS = [
     "dmx_default_options", "dmx_default_newton_params", "dmx_create", "dmx_create_distributed", "dmx_get_nccl_unique_id",
     "dmx_destroy", "dmx_last_error", "dmx_version", "dmx_grid_structured", "dmx_grid_tensor", "dmx_local_box",
     "dmx_local_box3", "dmx_set_partitioning", "dmx_set_preconditioner_params", "dmx_precond_apply",
+    "dmx_default_amg_params", "dmx_set_amg_params", "dmx_amg_levels", "dmx_amg_level_cells", "dmx_amg_level_nnz_blocks", "dmx_amg_level_matrix",
     "dmx_num_cells", "dmx_num_eq", "dmx_nnz_blocks", "dmx_pattern", "dmx_bcrs_pattern", "dmx_set_options",
     "dmx_set_cell_fields", "dmx_set_source", "dmx_set_material", "dmx_set_fluids", "dmx_set_fluid_table",
     "dmx_side_faces", "dmx_set_boundary", "dmx_vec_upload", "dmx_vec_download", "dmx_vec_copy", "dmx_jacobian_upload",
@@ -37,6 +38,7 @@ EXPORTS = [
 SOLVER_BICGSTAB, SOLVER_RESTARTED_GMRES, SOLVER_CG = 0, 1, 2
 PRECOND_SSOR = 2
 PRECOND_PARMT_JAC, PRECOND_PARMT_SOR, PRECOND_PARMT_SSOR = 3, 4, 5
+PRECOND_AMG = 6
 K_ASSEMBLY, K_SPMV, K_ILU_APPLY, K_ILU_FACTOR, K_AMG, K_BLAS1, K_HALO, K_JACOBI = range(8)
 
 
@@ -53,6 +55,11 @@ class DmxNewtonParams(C.Structure):
                 ("enable_shift_criterion", C.c_int), ("enable_residual_criterion", C.c_int),
                 ("enable_absolute_residual_criterion", C.c_int), ("satisfy_residual_and_shift", C.c_int),
                 ("residual_reduction", C.c_double), ("max_absolute_residual", C.c_double)]
+
+
+class DmxAmgParams(C.Structure):
+    _fields_ = [("pre_steps", C.c_int), ("post_steps", C.c_int), ("prolongation_damping", C.c_double), ("smoother", C.c_int),
+                ("coarsest_cells", C.c_int), ("coarsest_steps", C.c_int), ("max_levels", C.c_int)]
 
 
 class DmxNewtonReport(C.Structure):
@@ -115,6 +122,13 @@ def load_library():
     L.dmx_set_linear_solver.argtypes = [vp, C.c_int, C.c_int]
     L.dmx_ssor_apply.argtypes = [vp, C.c_int, C.c_int]
     L.dmx_set_preconditioner_params.argtypes = [vp, C.c_int, C.c_double]
+    L.dmx_default_amg_params.argtypes = [C.POINTER(DmxAmgParams)]
+    L.dmx_set_amg_params.argtypes = [vp, C.POINTER(DmxAmgParams)]
+    L.dmx_amg_levels.argtypes = [vp]
+    L.dmx_amg_level_cells.argtypes = [vp, C.c_int, _ip]
+    L.dmx_amg_level_nnz_blocks.argtypes = [vp, C.c_int]
+    L.dmx_amg_level_nnz_blocks.restype = C.c_longlong
+    L.dmx_amg_level_matrix.argtypes = [vp, C.c_int, C.c_void_p]
     L.dmx_precond_apply.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     L.dmx_num_output_fields.argtypes = [vp]
     L.dmx_output_fields.argtypes = [vp, C.c_void_p]
@@ -404,6 +418,29 @@ class Engine:
 
     def set_preconditioner_params(self, iterations=1, relaxation=1.0):
         self._check(self.L.dmx_set_preconditioner_params(self.h, iterations, relaxation))
+
+    def set_amg_params(self, **kw):
+        """dune-istl's AMG parameter names: pre_steps, post_steps, prolongation_damping, smoother (PRECOND_SSOR | PRECOND_ILU0),
+        coarsest_cells, coarsest_steps, max_levels; unspecified ones keep dune's defaults"""
+        p = DmxAmgParams()
+        self.L.dmx_default_amg_params(C.byref(p))
+        for k, v in kw.items():
+            setattr(p, k, v)
+        self._check(self.L.dmx_set_amg_params(self.h, C.byref(p)))
+
+    def amg_levels(self):
+        out = []
+        for l in range(self.L.dmx_amg_levels(self.h)):
+            c = np.zeros(3, dtype=np.int32)
+            self._check(self.L.dmx_amg_level_cells(self.h, l, c))
+            out.append(tuple(int(x) for x in c))
+        return out
+
+    def amg_level_matrix(self, level):
+        nnzb = self.L.dmx_amg_level_nnz_blocks(self.h, level)
+        out = np.empty(nnzb * self.b * self.b)
+        self._check(self.L.dmx_amg_level_matrix(self.h, level, _hostptr(out)))
+        return out
 
     def precond_apply(self, precond, d_vec=VEC_WORK0, v_vec=VEC_WORK1):
         self._check(self.L.dmx_precond_apply(self.h, precond, d_vec, v_vec))

@@ -1,0 +1,300 @@
+// amg.cu -- aggregation AMG preconditioner on the structured grid hierarchy (AMGBiCGSTABIstlSolver / AMGCGIstlSolver,
+// dumux/linear/istlsolvers.hh:716-757: Dune::Amg::AMG built by Dune::AMGCreator with dune-istl's default parameters).
+//
+// What dune-istl's AMG does [DUNE-ext, paamg/amg.hh, parameters.hh, solverfactory defaults]: aggregates of strongly connected
+// unknowns (default aggregate size 4..8, "isotropic" with diameter 2), piecewise-constant prolongation, Galerkin coarse
+// matrices P^T A P (blocks summed), coarse-grid correction damped by prolongationDampingFactor = 1.6, a V-cycle (gamma 1)
+// with preSteps = postSteps = 2 smoothing steps of SeqSSOR (1 iteration, relaxation 1), where a smoothing step is
+// "update = 0; smoother.apply(update, defect); lhs += update; defect -= A update", and a direct solve on the coarsest level.
+// Its aggregation is a graph heuristic that cannot be restated from memory, so this is NOT a bit-for-bit port of dune's
+// hierarchy.  It is the same cycle on the hierarchy the heuristic degenerates to on a 7-point structured box: aggregates
+// = 2 x 2 x 2 cell blocks (8 unknowns, the upper end of dune's default range).  With those the coarse pattern stays the
+// 7-point stencil of the coarse box, so EVERY level runs the structured kernels of this library (stencil SpMV, tile-wavefront
+// sweeps); the hierarchy ends at <= coarsest_cells cells, where coarsest_steps smoothing steps stand in for the direct solve.
+// The smoother is SeqSSOR in its factorised form M = (D + L) D^-1 (D + U) -- one forward and one backward block Gauss-Seidel
+// sweep started from zero, which is what a smoothing step applies -- executed by the ILU sweep kernels with Dinv_i = A_ii^-1
+// (L~ = L D^-1, U = D + U); SeqILU(0) is the alternative (dune: smoother "ilu").  oracle/amg_oracle.py restates this cycle
+// operation by operation (same summation orders), so device and oracle agree bit for bit.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace dmx {
+
+struct AmgLevel {
+    dmx_ctx* c = nullptr;        // level 0: the parent context; coarser levels: child contexts sharing its stream
+    double *x = nullptr, *r = nullptr, *u = nullptr, *t = nullptr;
+};
+struct AmgState {
+    std::vector<AmgLevel> levels;
+    double* own[3] = {nullptr, nullptr, nullptr};      // r, u, t of level 0
+};
+
+// ---------------------------------------------------------------------------------------------
+// Galerkin product for 2x2x2 box aggregates and piecewise-constant prolongation: coarse block (I,J) = sum of the fine blocks
+// (i,j) with i in aggregate I, j in aggregate J.  One thread per coarse row.  Canonical summation order (restated by
+// oracle.cpp orc_amg_galerkin): children in lexicographic order (x fastest), per child its entries in column order
+// -z,-y,-x,diag,+x,+y,+z, every coarse slot accumulated from 0 in that visiting order.
+// ---------------------------------------------------------------------------------------------
+template <int B>
+__global__ void __launch_bounds__(128) amg_galerkin_kernel(int fx, int fy, int fz, int cx, int cy, int cz, int dim,
+                                                           const int* __restrict__ f_rowptr, const double* __restrict__ fA,
+                                                           const int* __restrict__ c_rowptr, double* __restrict__ cA)
+{
+    constexpr int BB = B * B;
+    const int Ic = blockIdx.x * blockDim.x + threadIdx.x;
+    if (Ic >= cx * cy * cz) return;
+    const int I = Ic % cx, J = (Ic / cx) % cy, K = Ic / (cx * cy);
+    double acc[7][BB];
+#pragma unroll
+    for (int s = 0; s < 7; ++s)
+#pragma unroll
+        for (int q = 0; q < BB; ++q) acc[s][q] = 0.0;
+    auto add = [&](int slot, const double* blk) {
+#pragma unroll
+        for (int s = 0; s < 7; ++s)
+            if (s == slot) {
+#pragma unroll
+                for (int q = 0; q < BB; ++q) acc[s][q] += blk[q];
+            }
+    };
+    for (int dz = 0; dz < 2; ++dz)
+        for (int dy = 0; dy < 2; ++dy)
+            for (int dx = 0; dx < 2; ++dx) {
+                const int i = 2 * I + dx, j = 2 * J + dy, k = 2 * K + dz;
+                if (i >= fx || j >= fy || k >= fz) continue;
+                const size_t row = (size_t)i + (size_t)fx * (j + (size_t)fy * k);
+                const double* p = fA + (size_t)f_rowptr[row] * BB;
+                if (dim > 2 && k > 0) { add(dz == 0 ? 0 : 3, p); p += BB; }
+                if (dim > 1 && j > 0) { add(dy == 0 ? 1 : 3, p); p += BB; }
+                if (i > 0) { add(dx == 0 ? 2 : 3, p); p += BB; }
+                add(3, p); p += BB;
+                if (i + 1 < fx) { add(dx == 0 ? 3 : 4, p); p += BB; }
+                if (dim > 1 && j + 1 < fy) { add(dy == 0 ? 3 : 5, p); p += BB; }
+                if (dim > 2 && k + 1 < fz) { add(dz == 0 ? 3 : 6, p); p += BB; }
+            }
+    double* out = cA + (size_t)c_rowptr[Ic] * BB;
+    const bool ex[7] = {dim > 2 && K > 0, dim > 1 && J > 0, I > 0, true, I + 1 < cx, dim > 1 && J + 1 < cy, dim > 2 && K + 1 < cz};
+#pragma unroll
+    for (int s = 0; s < 7; ++s)
+        if (ex[s]) {
+#pragma unroll
+            for (int q = 0; q < BB; ++q) out[q] = acc[s][q];
+            out += BB;
+        }
+}
+
+// restriction with P^T: r_c[I] = sum of the children's entries, lexicographic child order, from 0
+template <int B>
+__global__ void __launch_bounds__(256) amg_restrict_kernel(int fx, int fy, int fz, int cx, int cy, int cz, const double* __restrict__ rf,
+                                                           double* __restrict__ rc)
+{
+    const int Ic = blockIdx.x * blockDim.x + threadIdx.x;
+    if (Ic >= cx * cy * cz) return;
+    const int I = Ic % cx, J = (Ic / cx) % cy, K = Ic / (cx * cy);
+    double s[B];
+#pragma unroll
+    for (int e = 0; e < B; ++e) s[e] = 0.0;
+    for (int dz = 0; dz < 2; ++dz)
+        for (int dy = 0; dy < 2; ++dy)
+            for (int dx = 0; dx < 2; ++dx) {
+                const int i = 2 * I + dx, j = 2 * J + dy, k = 2 * K + dz;
+                if (i >= fx || j >= fy || k >= fz) continue;
+                const size_t row = (size_t)i + (size_t)fx * (j + (size_t)fy * k);
+#pragma unroll
+                for (int e = 0; e < B; ++e) s[e] += rf[row * B + e];
+            }
+#pragma unroll
+    for (int e = 0; e < B; ++e) rc[(size_t)Ic * B + e] = s[e];
+}
+
+// prolongation of the coarse correction, damped: u_i = damp * x_c[aggregate(i)];  x_i += u_i (x_i = u_i if `first`)
+template <int B>
+__global__ void __launch_bounds__(256) amg_prolong_kernel(int fx, int fy, int fz, int cx, int cy, double damp, const double* __restrict__ xc,
+                                                          double* __restrict__ u, double* __restrict__ x, int first)
+{
+    const size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= (size_t)fx * fy * fz) return;
+    const int i = (int)(row % fx), j = (int)((row / fx) % fy), k = (int)(row / ((size_t)fx * fy));
+    const size_t Ic = (size_t)(i >> 1) + (size_t)cx * ((j >> 1) + (size_t)cy * (k >> 1));
+#pragma unroll
+    for (int e = 0; e < B; ++e) {
+        const double v = damp * xc[Ic * B + e];
+        u[row * B + e] = v;
+        x[row * B + e] = first ? v : x[row * B + e] + v;
+    }
+}
+
+// after a smoothing step / the coarse-grid correction: lhs += update (lhs = update if `first`), defect -= A update (t = A update)
+__global__ void __launch_bounds__(256) amg_update_kernel(size_t len, const double* __restrict__ u, const double* __restrict__ t, double* x,
+                                                         double* r, int first, int with_x, int with_r)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (size_t)gridDim.x * blockDim.x) {
+        if (with_x) x[i] = first ? u[i] : x[i] + u[i];
+        if (with_r) r[i] -= t[i];
+    }
+}
+
+static AmgState* amg_of(dmx_ctx* ctx) { return static_cast<AmgState*>(ctx->amg); }
+
+void amg_free(dmx_ctx* ctx)
+{
+    AmgState* st = amg_of(ctx);
+    if (!st) return;
+    for (size_t l = 1; l < st->levels.size(); ++l) destroy_child_ctx(st->levels[l].c);
+    for (double* p : st->own) if (p) cudaFree(p);
+    delete st;
+    ctx->amg = nullptr;
+}
+
+// hierarchy of boxes: halve every axis (ceil) until <= coarsest_cells cells remain (or max_levels)
+static int amg_build(dmx_ctx* ctx)
+{
+    amg_free(ctx);
+    if (!ctx->has_grid) return fail(ctx, DMX_ERR_USAGE, "AMG: needs a structured grid (dmx_grid_structured / dmx_grid_tensor)");
+    AmgState* st = new AmgState;
+    ctx->amg = st;
+    const size_t len = (size_t)ctx->n * ctx->b;
+    for (double*& p : st->own) DMX_CUDA(cudaMalloc((void**)&p, len * sizeof(double)));
+    AmgLevel l0;
+    l0.c = ctx; l0.r = st->own[0]; l0.u = st->own[1]; l0.t = st->own[2];
+    st->levels.push_back(l0);
+    int nc[3] = {ctx->nc[0], ctx->nc[1], ctx->nc[2]};
+    while ((int)st->levels.size() < ctx->amg_prm.max_levels) {
+        const long long n = (long long)nc[0] * nc[1] * nc[2];
+        if (n <= ctx->amg_prm.coarsest_cells) break;
+        bool can = false;
+        for (int a = 0; a < ctx->dim; ++a) {
+            if (nc[a] > 1) can = true;
+            nc[a] = (nc[a] + 1) / 2;
+        }
+        if (!can) break;
+        dmx_ctx* child = nullptr;
+        if (int rc = make_child_ctx(ctx, nc, &child)) return rc;
+        AmgLevel lv;
+        lv.c = child;
+        lv.x = child->d_vec[DMX_VEC_DELTA]; lv.r = child->d_vec[DMX_VEC_RESIDUAL];
+        lv.u = child->d_vec[DMX_VEC_WORK0]; lv.t = child->d_vec[DMX_VEC_WORK1];
+        st->levels.push_back(lv);
+    }
+    return 0;
+}
+
+int amg_num_levels(dmx_ctx* ctx) { return amg_of(ctx) ? (int)amg_of(ctx)->levels.size() : 0; }
+dmx_ctx* amg_level_ctx(dmx_ctx* ctx, int level)
+{
+    AmgState* st = amg_of(ctx);
+    return (st && level >= 0 && level < (int)st->levels.size()) ? st->levels[level].c : nullptr;
+}
+
+// Galerkin coarse matrices from the current Jacobian, then the smoother of every level
+int amg_setup(dmx_ctx* ctx)
+{
+    AmgState* st = amg_of(ctx);
+    if (!st || ctx->amg_dirty) {
+        if (int rc = amg_build(ctx)) return rc;
+        ctx->amg_dirty = false;
+        st = amg_of(ctx);
+    }
+    const int smoother = ctx->amg_prm.smoother;
+    if (smoother != DMX_PRECOND_SSOR && smoother != DMX_PRECOND_ILU0) return fail(ctx, DMX_ERR_USAGE, "AMG smoother must be DMX_PRECOND_SSOR or DMX_PRECOND_ILU0");
+    for (size_t l = 0; l < st->levels.size(); ++l) {
+        dmx_ctx* c = st->levels[l].c;
+        if (l > 0) {
+            dmx_ctx* f = st->levels[l - 1].c;
+            ProfScope ps(ctx, DMX_K_AMG);
+            const int grid = (c->n + 127) / 128;
+            if (ctx->b == 2)
+                amg_galerkin_kernel<2><<<grid, 128, 0, ctx->stream>>>(f->nc[0], f->nc[1], f->nc[2], c->nc[0], c->nc[1], c->nc[2], ctx->dim, f->d_rowptr,
+                                                                      f->d_J, c->d_rowptr, c->d_J);
+            else
+                amg_galerkin_kernel<1><<<grid, 128, 0, ctx->stream>>>(f->nc[0], f->nc[1], f->nc[2], c->nc[0], c->nc[1], c->nc[2], ctx->dim, f->d_rowptr,
+                                                                      f->d_J, c->d_rowptr, c->d_J);
+            DMX_CHECK_LAUNCH();
+            c->jac_diagonal = false;
+        }
+        // smoother set-up: the ILU machinery with Dinv = A_ii^-1 (factorised SSOR) or the ILU(0) recurrence
+        c->ssor_factorised = (smoother == DMX_PRECOND_SSOR);
+        const int rc = ilu0_factor(c);
+        if (rc) {
+            if (c != ctx) ctx->err = c->err;
+            return rc;
+        }
+    }
+    return 0;
+}
+
+static int amg_smooth_step(dmx_ctx* ctx, AmgLevel& L, bool first, bool need_defect)
+{
+    dmx_ctx* c = L.c;
+    const size_t len = (size_t)c->n * c->b;
+    if (int rc = ilu0_apply(c, L.r, L.u)) return rc;                          // update = M^-1 defect (from update = 0)
+    if (need_defect)
+        if (int rc = launch_spmv_local(c, L.u, L.t)) return rc;               // A update
+    ProfScope ps(ctx, DMX_K_AMG);
+    const int grid = (int)std::min<size_t>((len + 255) / 256, 148 * 8);
+    amg_update_kernel<<<grid, 256, 0, ctx->stream>>>(len, L.u, L.t, L.x, L.r, first ? 1 : 0, 1, need_defect ? 1 : 0);
+    DMX_CHECK_LAUNCH();
+    return 0;
+}
+
+static int amg_cycle(dmx_ctx* ctx, AmgState* st, int l)
+{
+    AmgLevel& L = st->levels[l];
+    dmx_ctx* c = L.c;
+    const auto& prm = ctx->amg_prm;
+    if (l + 1 == (int)st->levels.size()) {
+        // coarsest level: coarsest_steps smoothing steps instead of dune's direct solve
+        const int ns = std::max(1, prm.coarsest_steps);
+        for (int s = 0; s < ns; ++s)
+            if (int rc = amg_smooth_step(ctx, L, s == 0, s + 1 < ns)) return rc;
+        return 0;
+    }
+    AmgLevel& C = st->levels[l + 1];
+    dmx_ctx* cc = C.c;
+    for (int s = 0; s < prm.pre_steps; ++s)
+        if (int rc = amg_smooth_step(ctx, L, s == 0, true)) return rc;
+    {
+        ProfScope ps(ctx, DMX_K_AMG);
+        const int grid = (cc->n + 255) / 256;
+        if (ctx->b == 2) amg_restrict_kernel<2><<<grid, 256, 0, ctx->stream>>>(c->nc[0], c->nc[1], c->nc[2], cc->nc[0], cc->nc[1], cc->nc[2], L.r, C.r);
+        else amg_restrict_kernel<1><<<grid, 256, 0, ctx->stream>>>(c->nc[0], c->nc[1], c->nc[2], cc->nc[0], cc->nc[1], cc->nc[2], L.r, C.r);
+        DMX_CHECK_LAUNCH();
+    }
+    if (int rc = amg_cycle(ctx, st, l + 1)) return rc;
+    {
+        ProfScope ps(ctx, DMX_K_AMG);
+        const int grid = (c->n + 255) / 256;
+        const int first = prm.pre_steps == 0 ? 1 : 0;
+        if (ctx->b == 2)
+            amg_prolong_kernel<2><<<grid, 256, 0, ctx->stream>>>(c->nc[0], c->nc[1], c->nc[2], cc->nc[0], cc->nc[1], prm.prolongation_damping, C.x, L.u, L.x, first);
+        else
+            amg_prolong_kernel<1><<<grid, 256, 0, ctx->stream>>>(c->nc[0], c->nc[1], c->nc[2], cc->nc[0], cc->nc[1], prm.prolongation_damping, C.x, L.u, L.x, first);
+        DMX_CHECK_LAUNCH();
+    }
+    if (prm.post_steps > 0) {
+        if (int rc = launch_spmv_local(c, L.u, L.t)) return rc;
+        ProfScope ps(ctx, DMX_K_AMG);
+        const size_t len = (size_t)c->n * c->b;
+        const int grid = (int)std::min<size_t>((len + 255) / 256, 148 * 8);
+        amg_update_kernel<<<grid, 256, 0, ctx->stream>>>(len, L.u, L.t, L.x, L.r, 0, 0, 1);
+        DMX_CHECK_LAUNCH();
+    }
+    for (int s = 0; s < prm.post_steps; ++s)
+        if (int rc = amg_smooth_step(ctx, L, false, s + 1 < prm.post_steps)) return rc;
+    return 0;
+}
+
+// v = AMG(J)(d): one V-cycle from v = 0
+int amg_apply(dmx_ctx* ctx, const double* d, double* v)
+{
+    AmgState* st = amg_of(ctx);
+    if (!st) return fail(ctx, DMX_ERR_USAGE, "AMG apply before set-up");
+    AmgLevel& L0 = st->levels[0];
+    const size_t len = (size_t)ctx->n * ctx->b;
+    DMX_CUDA(cudaMemcpyAsync(L0.r, d, len * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    L0.x = v;
+    return amg_cycle(ctx, st, 0);
+}
+
+} // namespace dmx

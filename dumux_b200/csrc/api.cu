@@ -154,6 +154,8 @@ int finish_grid(dmx_ctx* ctx, int model, int dim, const int* cells, const std::v
     ctx->n = ctx->nc[0] * ctx->nc[1] * ctx->nc[2];
     ctx->has_grid = true;
     ctx->prepared = false;
+    amg_free(ctx);
+    ctx->amg_dirty = true;
     ctx->h_K.assign(ctx->n, 1e-10);
     ctx->h_phi.assign(ctx->n, 0.4);
     ctx->h_region.assign(ctx->n, 0);
@@ -252,6 +254,11 @@ void dmx_default_options(dmx_options* o)
     o->enable_gravity = 1; o->gravity = 9.81; o->upwind_weight = 1.0; o->fd_method = 1; o->base_eps = 1e-10;
     o->privar_magnitude[0] = o->privar_magnitude[1] = -1.0; o->stationary = 0; o->dt = 1.0; o->extrusion = 1.0;
 }
+void dmx_default_amg_params(dmx_amg_params* p)
+{
+    p->pre_steps = 2; p->post_steps = 2; p->prolongation_damping = 1.6; p->smoother = DMX_PRECOND_SSOR;
+    p->coarsest_cells = 8; p->coarsest_steps = 8; p->max_levels = 15;
+}
 void dmx_default_newton_params(dmx_newton_params* p)
 {
     p->max_relative_shift = 1e-8; p->min_steps = 2; p->max_steps = 18; p->lin_reduction = 1e-6; p->lin_maxit = 250;
@@ -259,6 +266,18 @@ void dmx_default_newton_params(dmx_newton_params* p)
     p->use_line_search = 0; p->line_search_min_relaxation = 0.125;
     p->enable_shift_criterion = 1; p->enable_residual_criterion = 0; p->enable_absolute_residual_criterion = 0;
     p->satisfy_residual_and_shift = 0; p->residual_reduction = 1e-5; p->max_absolute_residual = 1e-5;
+}
+
+static int alloc_ctx_scratch(dmx_ctx* ctx)
+{
+    cudaMalloc((void**)&ctx->d_partials, 3 * 1184 * sizeof(double));
+    cudaMalloc((void**)&ctx->d_scalars, 8 * sizeof(double));
+    cudaMallocHost((void**)&ctx->h_scalars, 8 * sizeof(double));
+    cudaMalloc((void**)&ctx->d_flag, sizeof(int));
+    cudaMallocHost((void**)&ctx->h_flag, sizeof(int));
+    cudaMalloc((void**)&ctx->d_barrier, sizeof(unsigned int));
+    for (auto& e : ctx->ev) cudaEventCreate(&e);
+    return cudaGetLastError() == cudaSuccess ? 0 : DMX_ERR_CUDA;
 }
 
 int dmx_create_distributed(dmx_ctx** out, int device, const void* uid, int rank, int nranks)
@@ -272,19 +291,13 @@ int dmx_create_distributed(dmx_ctx** out, int device, const void* uid, int rank,
     ctx->rank = rank;
     ctx->nranks = nranks;
     dmx_default_options(&ctx->opt);
+    dmx_default_amg_params(&ctx->amg_prm);
     if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return DMX_ERR_CUDA; }
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, device);
     ctx->num_sms = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return DMX_ERR_CUDA; }
-    cudaMalloc((void**)&ctx->d_partials, 3 * 1184 * sizeof(double));
-    cudaMalloc((void**)&ctx->d_scalars, 8 * sizeof(double));
-    cudaMallocHost((void**)&ctx->h_scalars, 8 * sizeof(double));
-    cudaMalloc((void**)&ctx->d_flag, sizeof(int));
-    cudaMallocHost((void**)&ctx->h_flag, sizeof(int));
-    cudaMalloc((void**)&ctx->d_barrier, sizeof(unsigned int));
-    for (auto& e : ctx->ev) cudaEventCreate(&e);
-    if (cudaGetLastError() != cudaSuccess) { delete ctx; return DMX_ERR_CUDA; }
+    if (alloc_ctx_scratch(ctx)) { delete ctx; return DMX_ERR_CUDA; }
     if (nranks > 1) {
         if (int rc = nccl_init(ctx, uid)) { delete ctx; return rc; }
     }
@@ -299,6 +312,7 @@ int dmx_destroy(dmx_ctx* ctx)
     if (!ctx) return 0;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    amg_free(ctx);
     sk_free(ctx);
     if (ctx->nccl_comm) nccl_destroy(ctx);
     void* ptrs[] = {ctx->d_geom, ctx->d_K, ctx->d_phi, ctx->d_q, ctx->d_region, ctx->d_tij[0], ctx->d_tij[1], ctx->d_tij[2], ctx->d_laws,
@@ -316,7 +330,7 @@ int dmx_destroy(dmx_ctx* ctx)
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
     for (auto& r : ctx->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto& e : ctx->prof_pool) cudaEventDestroy(e);
-    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->stream && ctx->owns_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return 0;
 }
@@ -387,6 +401,8 @@ int dmx_bcrs_pattern(dmx_ctx* ctx, int n, int b, const int* rowptr, const int* c
     if (b != 1 && b != 2) return fail(ctx, DMX_ERR_USAGE, "block size must be 1 or 2");
     DMX_CUDA(cudaSetDevice(ctx->device));
     sk_free(ctx);
+    amg_free(ctx);
+    ctx->amg_dirty = true;
     ctx->has_grid = false;
     ctx->model = 0;
     ctx->n = n;
@@ -567,7 +583,9 @@ int dmx_synchronize(dmx_ctx* ctx)
 }
 int dmx_kernel_launch_count(const dmx_ctx* ctx, long long* launches)
 {
-    *launches = ctx->launches;
+    long long total = ctx->launches;
+    for (const dmx_ctx* c : ctx->children) total += c->launches;
+    *launches = total;
     return 0;
 }
 
@@ -881,6 +899,37 @@ int dmx_ssor_apply(dmx_ctx* ctx, int d_vec, int v_vec)
     if (int rc = vec_ok(ctx, v_vec)) return rc;
     return ssor_apply(ctx, ctx->d_vec[d_vec], ctx->d_vec[v_vec]);
 }
+int dmx_set_amg_params(dmx_ctx* ctx, const dmx_amg_params* p)
+{
+    if (p->pre_steps < 0 || p->post_steps < 0 || p->pre_steps + p->post_steps < 1) return fail(ctx, DMX_ERR_USAGE, "AMG: preSteps + postSteps must be >= 1");
+    if (p->smoother != DMX_PRECOND_SSOR && p->smoother != DMX_PRECOND_ILU0) return fail(ctx, DMX_ERR_USAGE, "AMG smoother must be DMX_PRECOND_SSOR or DMX_PRECOND_ILU0");
+    if (p->coarsest_cells < 1 || p->coarsest_steps < 1 || p->max_levels < 1) return fail(ctx, DMX_ERR_USAGE, "AMG: coarsest_cells, coarsest_steps, max_levels must be >= 1");
+    if (p->coarsest_cells != ctx->amg_prm.coarsest_cells || p->max_levels != ctx->amg_prm.max_levels) ctx->amg_dirty = true;
+    ctx->amg_prm = *p;
+    return 0;
+}
+int dmx_amg_levels(dmx_ctx* ctx) { return amg_num_levels(ctx); }
+int dmx_amg_level_cells(dmx_ctx* ctx, int level, int* cells)
+{
+    dmx_ctx* c = amg_level_ctx(ctx, level);
+    if (!c) return fail(ctx, DMX_ERR_USAGE, "no such AMG level");
+    for (int a = 0; a < 3; ++a) cells[a] = c->nc[a];
+    return 0;
+}
+long long dmx_amg_level_nnz_blocks(dmx_ctx* ctx, int level)
+{
+    dmx_ctx* c = amg_level_ctx(ctx, level);
+    return c ? c->nnzb : -1;
+}
+int dmx_amg_level_matrix(dmx_ctx* ctx, int level, double* values)
+{
+    dmx_ctx* c = amg_level_ctx(ctx, level);
+    if (!c) return fail(ctx, DMX_ERR_USAGE, "no such AMG level");
+    DMX_CUDA(cudaSetDevice(ctx->device));
+    DMX_CUDA(cudaMemcpyAsync(values, c->d_J, (size_t)c->nnzb * c->b * c->b * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    DMX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
 int dmx_set_preconditioner_params(dmx_ctx* ctx, int iterations, double relaxation)
 {
     if (iterations < 1) return fail(ctx, DMX_ERR_USAGE, "LinearSolver.PreconditionerIterations must be >= 1");
@@ -948,3 +997,40 @@ int dmx_time_kernel(dmx_ctx* ctx, int which, int reps, float* ms_avg)
 }
 
 } // extern "C"
+
+namespace dmx {
+
+int make_child_ctx(dmx_ctx* parent, const int* cells, dmx_ctx** out)
+{
+    dmx_ctx* ctx = parent;       // for the error macros
+    dmx_ctx* c = new dmx_ctx;
+    c->device = parent->device;
+    c->num_sms = parent->num_sms;
+    c->stream = parent->stream;
+    c->owns_stream = false;
+    c->prof_parent = parent;
+    dmx_default_options(&c->opt);
+    dmx_default_amg_params(&c->amg_prm);
+    if (alloc_ctx_scratch(c)) { dmx_destroy(c); return fail(ctx, DMX_ERR_CUDA, "AMG: cannot allocate a level context"); }
+    const double lower[3] = {0.0, 0.0, 0.0}, upper[3] = {1.0, 1.0, 1.0};
+    const int rc = dmx_grid_structured(c, parent->b == 2 ? DMX_MODEL_2P : DMX_MODEL_1P, parent->dim, cells, lower, upper);
+    if (rc) {
+        parent->err = "AMG level context: " + c->err;
+        dmx_destroy(c);
+        return rc;
+    }
+    parent->children.push_back(c);
+    *out = c;
+    return 0;
+}
+void destroy_child_ctx(dmx_ctx* child)
+{
+    if (!child) return;
+    if (child->prof_parent) {
+        auto& v = child->prof_parent->children;
+        v.erase(std::remove(v.begin(), v.end(), child), v.end());
+    }
+    dmx_destroy(child);
+}
+
+} // namespace dmx

@@ -151,6 +151,13 @@ struct dmx_ctx {
     double* d_gm = nullptr;           // GMRes basis: restart+1 vectors, w, defect
     int gm_vectors = 0;
     void* skew = nullptr;             // SkewState of ilu_structured.cu (structured-grid ILU sweeps), null: generic kernels
+    bool ssor_factorised = false;     // the "ILU" machinery holds SeqSSOR in factorised form: Dinv_i = A_ii^-1 instead of the ILU(0) recurrence
+    void* amg = nullptr;              // AmgState of amg.cu
+    dmx_amg_params amg_prm;
+    bool amg_dirty = true;            // hierarchy has to be (re)built: new grid or new parameters
+    bool owns_stream = true;          // false: a level context of an AMG hierarchy running on its parent's stream
+    dmx_ctx* prof_parent = nullptr;   // kernel-class timers of a level context are booked on the parent
+    std::vector<dmx_ctx*> children;   // level contexts (for the launch count)
 
     // reductions
     double* d_partials = nullptr;
@@ -210,7 +217,7 @@ struct ProfScope {
         else cudaEventCreate(&e);
         return e;
     }
-    ProfScope(dmx_ctx* ctx, int k) : c(ctx), cls(k)
+    ProfScope(dmx_ctx* ctx, int k) : c(ctx->prof_parent ? ctx->prof_parent : ctx), cls(k)
     {
         if (!c->prof_on) return;
         a = get(c); b = get(c);
@@ -282,6 +289,7 @@ int launch_output_fields(dmx_ctx* ctx, double* d_out);
 int build_diag(dmx_ctx* ctx);
 int build_level_schedule(dmx_ctx* ctx);
 int launch_spmv(dmx_ctx* ctx, const double* x, double* y);
+int launch_spmv_local(dmx_ctx* ctx, const double* x, double* y);     // without the owner projection
 int ilu0_factor(dmx_ctx* ctx);
 int ilu0_factor_bcrs(dmx_ctx* ctx);
 int ilu0_apply(dmx_ctx* ctx, const double* d, double* v);
@@ -303,6 +311,15 @@ int sk_factor(dmx_ctx* ctx);
 int sk_export_bcrs(dmx_ctx* ctx, double* out);
 int sk_apply(dmx_ctx* ctx, const double* d, double* v);
 int sk_trace_read(dmx_ctx* ctx, long long* out);
+// implemented in amg.cu
+void amg_free(dmx_ctx* ctx);
+int amg_setup(dmx_ctx* ctx);
+int amg_apply(dmx_ctx* ctx, const double* d, double* v);
+int amg_num_levels(dmx_ctx* ctx);
+dmx_ctx* amg_level_ctx(dmx_ctx* ctx, int level);
+// implemented in api.cu: level contexts of a hierarchy (own grid, matrix and vectors; the parent's device and stream)
+int make_child_ctx(dmx_ctx* parent, const int* cells, dmx_ctx** out);
+void destroy_child_ctx(dmx_ctx* child);
 // implemented in dist.cu
 int nccl_init(dmx_ctx* ctx, const void* uid);
 int nccl_get_unique_id(void* out);

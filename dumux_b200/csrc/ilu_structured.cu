@@ -784,7 +784,8 @@ static int sk_factor_t(dmx_ctx* ctx, SkewState* st)
         st->diag_grid = std::max(1, std::min(perSm, 2)) * ctx->num_sms;
     }
     DMX_CUDA(cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream));
-    if (ctx->jac_diagonal) {
+    if (ctx->jac_diagonal || ctx->ssor_factorised) {
+        // Dinv_i = A_ii^-1: exact ILU(0) of a block-diagonal matrix, or SeqSSOR in factorised form (L~ = L D^-1, U = D + U)
         ilu_diag_only_kernel<B><<<(unsigned)((ctx->n + 255) / 256), 256, 0, ctx->stream>>>(ctx->n, ctx->d_diag, ctx->d_J, st->Dinv, ctx->d_flag);
         DMX_CHECK_LAUNCH();
         const unsigned grid = (unsigned)((size_t)g.ntiles * g.NS);

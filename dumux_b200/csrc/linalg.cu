@@ -87,16 +87,16 @@ __global__ void __launch_bounds__(128) stencil_spmv_kernel(int nx, int ny, int n
     y[(size_t)row * B + e] = acc;
 }
 
-int launch_spmv(dmx_ctx* ctx, const double* x, double* y)
+static int launch_spmv_owner(dmx_ctx* ctx, const double* x, double* y, const unsigned char* owner)
 {
     ProfScope ps(ctx, DMX_K_SPMV);
     if (ctx->has_grid && ctx->nc[1] <= 65535 && ctx->nc[2] <= 65535) {
         const int bs = 128;
         const dim3 grid((unsigned)((ctx->nc[0] * ctx->b + bs - 1) / bs), (unsigned)ctx->nc[1], (unsigned)ctx->nc[2]);
         if (ctx->b == 2)
-            stencil_spmv_kernel<2><<<grid, bs, 0, ctx->stream>>>(ctx->nc[0], ctx->nc[1], ctx->nc[2], ctx->dim, ctx->d_rowptr, ctx->d_J, x, y, ctx->d_owner);
+            stencil_spmv_kernel<2><<<grid, bs, 0, ctx->stream>>>(ctx->nc[0], ctx->nc[1], ctx->nc[2], ctx->dim, ctx->d_rowptr, ctx->d_J, x, y, owner);
         else
-            stencil_spmv_kernel<1><<<grid, bs, 0, ctx->stream>>>(ctx->nc[0], ctx->nc[1], ctx->nc[2], ctx->dim, ctx->d_rowptr, ctx->d_J, x, y, ctx->d_owner);
+            stencil_spmv_kernel<1><<<grid, bs, 0, ctx->stream>>>(ctx->nc[0], ctx->nc[1], ctx->nc[2], ctx->dim, ctx->d_rowptr, ctx->d_J, x, y, owner);
         DMX_CHECK_LAUNCH();
         return 0;
     }
@@ -104,12 +104,16 @@ int launch_spmv(dmx_ctx* ctx, const double* x, double* y)
     const int bs = 256;
     const int grid = (int)((threads + bs - 1) / bs);
     if (ctx->b == 2)
-        bcrs_spmv_kernel<2><<<grid, bs, 0, ctx->stream>>>(ctx->n, ctx->d_rowptr, ctx->d_colidx, ctx->d_J, x, y, ctx->d_owner);
+        bcrs_spmv_kernel<2><<<grid, bs, 0, ctx->stream>>>(ctx->n, ctx->d_rowptr, ctx->d_colidx, ctx->d_J, x, y, owner);
     else
-        bcrs_spmv_kernel<1><<<grid, bs, 0, ctx->stream>>>(ctx->n, ctx->d_rowptr, ctx->d_colidx, ctx->d_J, x, y, ctx->d_owner);
+        bcrs_spmv_kernel<1><<<grid, bs, 0, ctx->stream>>>(ctx->n, ctx->d_rowptr, ctx->d_colidx, ctx->d_J, x, y, owner);
     DMX_CHECK_LAUNCH();
     return 0;
 }
+// OverlappingSchwarzOperator::apply: local A.mv, then project (non-owner rows zero)
+int launch_spmv(dmx_ctx* ctx, const double* x, double* y) { return launch_spmv_owner(ctx, x, y, ctx->d_owner); }
+// the plain local product (inside a sequential preconditioner)
+int launch_spmv_local(dmx_ctx* ctx, const double* x, double* y) { return launch_spmv_owner(ctx, x, y, nullptr); }
 
 // ---------------------------------------------------------------------------------------------
 // reductions: fixed grid, per-block partials, single-block final pass in fixed order -> deterministic
@@ -626,11 +630,57 @@ static int coop_launch(dmx_ctx* ctx, void (*kernel)(Args...), int threads, Args.
     return 0;
 }
 
+// SeqSSOR in factorised form on a generic pattern, in the layout of the ILU sweeps: L~_ij = A_ij A_jj^-1 (j < i), A_ii^-1 on the
+// diagonal, U_ij = A_ij (j > i) -- what ilu_skew_kernel builds on a structured box with Dinv_i = A_ii^-1 (same per-block arithmetic)
+template <int B>
+__global__ void __launch_bounds__(128) ssor_factor_bcrs_kernel(int n, const int* rowptr, const int* colidx, const int* diag, const double* A,
+                                                              double* out, int* flag)
+{
+    constexpr int BB = B * B;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+        const int j = colidx[k];
+        double blk[BB];
+#pragma unroll
+        for (int q = 0; q < BB; ++q) blk[q] = A[(size_t)k * BB + q];
+        if (j == i) {
+            if (!invert_block<B>(blk)) atomicOr(flag, 1);
+        } else if (j < i) {
+            double D[BB], C[BB];
+#pragma unroll
+            for (int q = 0; q < BB; ++q) D[q] = A[(size_t)diag[j] * BB + q];
+            invert_block<B>(D);
+#pragma unroll
+            for (int r = 0; r < B; ++r)
+#pragma unroll
+                for (int c = 0; c < B; ++c) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int kk = 0; kk < B; ++kk) s += blk[r * B + kk] * D[kk * B + c];
+                    C[r * B + c] = s;
+                }
+#pragma unroll
+            for (int q = 0; q < BB; ++q) blk[q] = C[q];
+        }
+#pragma unroll
+        for (int q = 0; q < BB; ++q) out[(size_t)k * BB + q] = blk[q];
+    }
+}
+
 // generic pattern: level-scheduled factorisation of a copy of J (ctx->d_ilu); sets ctx->d_flag on a singular block
 int ilu0_factor_bcrs(dmx_ctx* ctx)
 {
     const size_t bytes = (size_t)ctx->nnzb * ctx->b * ctx->b * sizeof(double);
     if (!ctx->d_ilu) DMX_CUDA(cudaMalloc((void**)&ctx->d_ilu, bytes));
+    if (ctx->ssor_factorised) {
+        DMX_CUDA(cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream));
+        const int grid = (ctx->n + 127) / 128;
+        if (ctx->b == 2) ssor_factor_bcrs_kernel<2><<<grid, 128, 0, ctx->stream>>>(ctx->n, ctx->d_rowptr, ctx->d_colidx, ctx->d_diag, ctx->d_J, ctx->d_ilu, ctx->d_flag);
+        else ssor_factor_bcrs_kernel<1><<<grid, 128, 0, ctx->stream>>>(ctx->n, ctx->d_rowptr, ctx->d_colidx, ctx->d_diag, ctx->d_J, ctx->d_ilu, ctx->d_flag);
+        DMX_CHECK_LAUNCH();
+        return 0;
+    }
     DMX_CUDA(cudaMemcpyAsync(ctx->d_ilu, ctx->d_J, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
     DMX_CUDA(cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream));
     if (ctx->l_ptr.empty()) { if (int rc = build_level_schedule(ctx)) return rc; }
@@ -888,7 +938,8 @@ int parmt_apply(dmx_ctx* ctx, int precond, const double* d, double* v)
 // fresh preconditioner per solve (istlsolvers.hh:457-463); SeqSSOR has no set-up
 int precond_setup(dmx_ctx* ctx, int precond)
 {
-    if (precond == DMX_PRECOND_ILU0) return ilu0_factor(ctx);
+    if (precond == DMX_PRECOND_ILU0) { ctx->ssor_factorised = false; return ilu0_factor(ctx); }
+    if (precond == DMX_PRECOND_AMG) return amg_setup(ctx);
     if (precond == DMX_PRECOND_SSOR) return 0;
     if (precond == DMX_PRECOND_BLOCKJACOBI) return block_jacobi_setup(ctx);
     if (precond == DMX_PRECOND_PARMT_JAC) return 0;
@@ -903,6 +954,7 @@ int precond_apply_local(dmx_ctx* ctx, int precond, const double* d, double* v)
 {
     switch (precond) {
         case DMX_PRECOND_ILU0: return ilu0_apply(ctx, d, v);
+        case DMX_PRECOND_AMG: return amg_apply(ctx, d, v);
         case DMX_PRECOND_SSOR: return ssor_apply(ctx, d, v);
         case DMX_PRECOND_BLOCKJACOBI: return block_jacobi_apply(ctx, d, v);
         case DMX_PRECOND_PARMT_JAC:

@@ -38,8 +38,9 @@ enum { DMX_DIFF_ANALYTIC = 100 };
 /* PARMT_*: DuMux's own multi-threaded smoothers Dumux::ParMTJac / ParMTSOR / ParMTSSOR ("par_mt_jac", "par_mt_sor", "par_mt_ssor";
    dumux/linear/preconditioners.hh:330-400, 489-620): Jacobi, and (S)SOR colour by colour with the greedy colouring of
    computeColorsForMatrixSweep_ (:408-440); iterations / relaxation from dmx_set_preconditioner_params */
+/* AMG: aggregation multigrid V-cycle (AMGBiCGSTABIstlSolver / AMGCGIstlSolver, linear/istlsolvers.hh:716-757), see dmx_amg_params */
 enum { DMX_PRECOND_ILU0 = 0, DMX_PRECOND_BLOCKJACOBI = 1, DMX_PRECOND_SSOR = 2, DMX_PRECOND_PARMT_JAC = 3, DMX_PRECOND_PARMT_SOR = 4,
-       DMX_PRECOND_PARMT_SSOR = 5 };
+       DMX_PRECOND_PARMT_SSOR = 5, DMX_PRECOND_AMG = 6 };
 /* Krylov method behind dmx_linear_solve / dmx_newton_*: ILUBiCGSTABIstlSolver (linear/istlsolvers.hh:636-642, default) or
    ILURestartedGMResIstlSolver (:660-667) */
 enum { DMX_SOLVER_BICGSTAB = 0, DMX_SOLVER_RESTARTED_GMRES = 1, DMX_SOLVER_CG = 2 };   /* CG: Dune::CGSolver (SSORCGIstlSolver :701-714) */
@@ -100,9 +101,31 @@ typedef struct {
     double relaxation[64];       /* line search: the accepted lambda of every iteration */
 } dmx_newton_report;
 
+/* Parameters of the AMG preconditioner, named after dune-istl's (Dune::Amg::Parameters / Dune::AMGCreator keys) with its
+   defaults: V-cycle, preSteps = postSteps = 2, prolongationDampingFactor 1.6, smoother SeqSSOR (1 iteration, relaxation 1).
+   Aggregates are 2x2x2 cell blocks of the structured grid (dune's default aggregate size is 4..8); the hierarchy ends at
+   <= coarsest_cells cells where coarsest_steps smoothing steps replace dune's direct coarse solve.  csrc/amg.cu. */
+typedef struct {
+    int    pre_steps;             /* preSteps  2 */
+    int    post_steps;            /* postSteps 2 */
+    double prolongation_damping;  /* prolongationDampingFactor 1.6 */
+    int    smoother;              /* DMX_PRECOND_SSOR (default, "ssor") or DMX_PRECOND_ILU0 ("ilu") */
+    int    coarsest_cells;        /* stop coarsening at <= this many cells (default 8) */
+    int    coarsest_steps;        /* smoothing steps on the coarsest level (default 8) */
+    int    max_levels;            /* maxLevel 15 */
+} dmx_amg_params;
+
 /* ---- lifetime ------------------------------------------------------------------------------------------ */
 void dmx_default_options(dmx_options* o);
 void dmx_default_newton_params(dmx_newton_params* p);
+void dmx_default_amg_params(dmx_amg_params* p);
+int  dmx_set_amg_params(dmx_ctx* ctx, const dmx_amg_params* p);
+/* number of levels of the AMG hierarchy (0 before the first set-up) and the cells per axis of one level */
+int  dmx_amg_levels(dmx_ctx* ctx);
+int  dmx_amg_level_cells(dmx_ctx* ctx, int level, int* cells);
+/* developer / test access: the BCRS values of a coarse level's Galerkin matrix (host buffer, nnz blocks of that level) */
+long long dmx_amg_level_nnz_blocks(dmx_ctx* ctx, int level);
+int  dmx_amg_level_matrix(dmx_ctx* ctx, int level, double* values);
 int  dmx_create(dmx_ctx** out, int device);
 /* One ctx per rank of a slab-decomposed run; nccl_unique_id = the 128-byte ncclUniqueId from rank 0.
    Replaces the MPI communicator DuMux gets from Dune::MPIHelper / gridView.comm() (linear/istlsolvers.hh:192). */

@@ -375,6 +375,26 @@ public:
     std::string name() const override { return "SSOR preconditioned BiCGSTAB solver (B200)"; }
 };
 
+//! AMGBiCGSTABIstlSolver (linear/istlsolvers.hh:716-736): BiCGSTAB preconditioned with one AMG V-cycle (dune-istl's default
+//! cycle parameters, see dmx_amg_params); setAmgParams stands for the LinearSolver.Preconditioner.* keys Dune::AMGCreator reads
+class GpuAMGBiCGSTABSolver : public GpuILUBiCGSTABSolver {
+public:
+    explicit GpuAMGBiCGSTABSolver(std::shared_ptr<Context> ctx) : GpuILUBiCGSTABSolver(ctx, DMX_SOLVER_BICGSTAB, 0), amgCtx_(std::move(ctx))
+    {
+        setPreconditioner(DMX_PRECOND_AMG);
+    }
+    void setAmgParams(const dmx_amg_params& p) { amgCtx_->check(dmx_set_amg_params(amgCtx_->get(), &p)); }
+    std::string name() const override { return "AMG preconditioned BiCGSTAB solver (B200)"; }
+private:
+    std::shared_ptr<Context> amgCtx_;
+};
+//! AMGCGIstlSolver (linear/istlsolvers.hh:738-757)
+class GpuAMGCGSolver : public GpuILUBiCGSTABSolver {
+public:
+    explicit GpuAMGCGSolver(std::shared_ptr<Context> ctx) : GpuILUBiCGSTABSolver(std::move(ctx), DMX_SOLVER_CG, 0) { setPreconditioner(DMX_PRECOND_AMG); }
+    std::string name() const override { return "AMG preconditioned CG solver (B200)"; }
+};
+
 // =====================================================================================================================
 class GpuNewtonSolver {
 public:

@@ -151,6 +151,7 @@ class BoxRank:
         import itertools
         self.comm = comm
         self.gpu_reduction = gpu_reduction
+        self.amg_params = None      # keyword arguments of oracle.amg_oracle.AmgOracle (precond="amg")
         dim = len(cells)
         self.cells = tuple(cells)
         self.part = tuple(part) if part is not None else problems.default_partitioning(dim, comm.nranks)
@@ -266,6 +267,11 @@ class BoxRank:
             return lambda d: O.ilu0_apply(n, b, rp, ci, ilu, d)
         if precond == "ssor":
             return lambda d: O.ssor_apply(n, b, rp, ci, jac, d)
+        if precond == "amg":
+            from oracle.amg_oracle import AmgOracle
+            amg = AmgOracle(self.local.cells, len(self.local.cells), b, rp, ci, jac, **(self.amg_params or {}))
+            st = int(self.comm.allreduce(float(amg.status), "max"))
+            return None if st != 0 else amg.apply
         kind = {"par_mt_jac": O.PARMT_JAC, "par_mt_sor": O.PARMT_SOR, "par_mt_ssor": O.PARMT_SSOR}[precond]
         return lambda d: O.parmt_apply(kind, n, b, rp, ci, jac, d, iterations, relaxation)
 
@@ -482,7 +488,7 @@ class BoxRank:
                 v[0], norm = defect()
         return x, status, its, (norm / norm0 if norm0 > 0 else 0.0)
 
-    def newton(self, u0, prev, lin_reduction=1e-6, lin_maxit=250, max_rel_shift=1e-8, min_steps=2, max_steps=18):
+    def newton(self, u0, prev, lin_reduction=1e-6, lin_maxit=250, max_rel_shift=1e-8, min_steps=2, max_steps=18, precond="ilu0"):
         """NewtonSolver::solveImpl_ (nonlinear/newtonsolver.hh:976-1072) on the local slab; u0/prev are LOCAL arrays."""
         u = np.ascontiguousarray(u0, dtype=np.float64).reshape(-1).copy()
         prev = np.ascontiguousarray(prev, dtype=np.float64).reshape(-1)
@@ -496,7 +502,7 @@ class BoxRank:
                     break
             last_shift = shift
             res, jac = self.o.assemble(u, prev)
-            dx, st, its, red = self.bicgstab(jac, res, lin_reduction, lin_maxit)
+            dx, st, its, red = self.bicgstab(jac, res, lin_reduction, lin_maxit, precond=precond)
             lin_its.append(its)
             if st != 0:
                 return u, st, steps, lin_its

@@ -1587,6 +1587,70 @@ int orc_parmt_colors(int n, const int* rowptr, const int* colidx, int* colors)
     std::copy(c.begin(), c.end(), colors);
     return nc;
 }
+// ---- aggregation AMG on the structured hierarchy (oracle/amg_oracle.py; device: dumux_b200/csrc/amg.cu) ----
+// Galerkin product P^T A P for 2x2x2 box aggregates and piecewise-constant prolongation on the 7-point pattern: coarse block
+// (I,J) = sum of the fine blocks (i,j), i in I, j in J.  Canonical summation order: children of a coarse cell in lexicographic
+// order (x fastest), per child its entries in column order, every coarse slot accumulated from 0 in that visiting order.
+void orc_amg_galerkin(int b, int dim, const int* fcells, const int* f_rowptr, const double* fA, const int* ccells, const int* c_rowptr,
+                      double* cA)
+{
+    const int bb = b * b;
+    const int fx = fcells[0], fy = fcells[1], fz = fcells[2], cx = ccells[0], cy = ccells[1], cz = ccells[2];
+    for (int K = 0; K < cz; ++K)
+        for (int J = 0; J < cy; ++J)
+            for (int I = 0; I < cx; ++I) {
+                const int Ic = I + cx * (J + cy * K);
+                double acc[7][4] = {};
+                auto add = [&](int slot, const double* blk) { for (int q = 0; q < bb; ++q) acc[slot][q] += blk[q]; };
+                for (int dz = 0; dz < 2; ++dz)
+                    for (int dy = 0; dy < 2; ++dy)
+                        for (int dx = 0; dx < 2; ++dx) {
+                            const int i = 2 * I + dx, j = 2 * J + dy, k = 2 * K + dz;
+                            if (i >= fx || j >= fy || k >= fz) continue;
+                            const size_t row = (size_t)i + (size_t)fx * (j + (size_t)fy * k);
+                            const double* p = fA + (size_t)f_rowptr[row] * bb;
+                            if (dim > 2 && k > 0) { add(dz == 0 ? 0 : 3, p); p += bb; }
+                            if (dim > 1 && j > 0) { add(dy == 0 ? 1 : 3, p); p += bb; }
+                            if (i > 0) { add(dx == 0 ? 2 : 3, p); p += bb; }
+                            add(3, p); p += bb;
+                            if (i + 1 < fx) { add(dx == 0 ? 3 : 4, p); p += bb; }
+                            if (dim > 1 && j + 1 < fy) { add(dy == 0 ? 3 : 5, p); p += bb; }
+                            if (dim > 2 && k + 1 < fz) { add(dz == 0 ? 3 : 6, p); p += bb; }
+                        }
+                double* out = cA + (size_t)c_rowptr[Ic] * bb;
+                const bool ex[7] = {dim > 2 && K > 0, dim > 1 && J > 0, I > 0, true, I + 1 < cx, dim > 1 && J + 1 < cy, dim > 2 && K + 1 < cz};
+                for (int s = 0; s < 7; ++s)
+                    if (ex[s]) {
+                        for (int q = 0; q < bb; ++q) out[q] = acc[s][q];
+                        out += bb;
+                    }
+            }
+}
+// SeqSSOR (one forward + one backward block Gauss-Seidel sweep from zero) in factorised form M = (D + L) D^-1 (D + U), stored in
+// the layout blockILUBacksolve consumes: L~_ij = A_ij A_jj^-1 (rightmultiply with the inverted diagonal block), A_ii^-1 on the
+// diagonal, U_ij = A_ij.  Returns 1 if a diagonal block is singular.
+int orc_ssor_factor(int n, int b, const int* rowptr, const int* colidx, const double* A, double* out)
+{
+    const int bb = b * b;
+    int bad = 0;
+    std::vector<double> dinv((size_t)n * bb);
+    for (int i = 0; i < n; ++i) {
+        int kd = -1;
+        for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) if (colidx[k] == i) kd = k;
+        if (kd < 0) return 1;
+        for (int q = 0; q < bb; ++q) dinv[(size_t)i * bb + q] = A[(size_t)kd * bb + q];
+        if (!invertBlock(&dinv[(size_t)i * bb], b)) bad = 1;
+    }
+    for (int i = 0; i < n; ++i)
+        for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+            const int j = colidx[k];
+            double* o = out + (size_t)k * bb;
+            for (int q = 0; q < bb; ++q) o[q] = A[(size_t)k * bb + q];
+            if (j == i) for (int q = 0; q < bb; ++q) o[q] = dinv[(size_t)i * bb + q];
+            else if (j < i) rightMultiply(o, &dinv[(size_t)j * bb], b);
+        }
+    return bad;
+}
 void orc_set_tracer_diffusion(orc_problem* p, double D, double tortuosity)
 {
     p->tracerD = D;

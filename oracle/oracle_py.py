@@ -102,6 +102,9 @@ def lib():
         L.orc_parmt_solve.restype = C.c_int
         L.orc_parmt_apply.argtypes = [C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, _ip, _ip, _dp, _dp, _dp]
         L.orc_parmt_colors.argtypes = [C.c_int, _ip, _ip, _ip]
+        L.orc_amg_galerkin.argtypes = [C.c_int, C.c_int, _ip, _ip, _dp, _ip, _ip, _dp]
+        L.orc_ssor_factor.argtypes = [C.c_int, C.c_int, _ip, _ip, _dp, _dp]
+        L.orc_ssor_factor.restype = C.c_int
         L.orc_parmt_colors.restype = C.c_int
         L.orc_ilu0_factor.argtypes = [C.c_int, C.c_int, _ip, _ip, _dp, _dp]
         L.orc_ilu0_factor.restype = C.c_int
@@ -348,6 +351,13 @@ def parmt_colors(n, rowptr, colidx):
     colors = np.zeros(n, dtype=np.int32)
     nc = lib().orc_parmt_colors(n, rowptr, colidx, colors)
     return colors, nc
+
+
+def ssor_factor(n, b, rowptr, colidx, values):
+    """SeqSSOR in factorised form (D + L) D^-1 (D + U), in the layout ilu0_apply consumes; returns (values, status)"""
+    out = np.empty(len(values))
+    st = lib().orc_ssor_factor(n, b, rowptr, colidx, np.ascontiguousarray(values, dtype=np.float64), out)
+    return out, st
 
 
 def ilu0_factor(n, b, rowptr, colidx, values):

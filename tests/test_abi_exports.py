@@ -60,12 +60,13 @@ def test_struct_layouts_match_ctypes(lib):
     from dumux_b200 import binding
     with tempfile.TemporaryDirectory() as d:
         src = os.path.join(d, "s.c")
-        open(src, "w").write('#include <stdio.h>\n#include "dumux_b200.h"\nint main(void){printf("%zu %zu %zu\\n", sizeof(dmx_options), '
-                             'sizeof(dmx_newton_params), sizeof(dmx_newton_report));return 0;}\n')
+        open(src, "w").write('#include <stdio.h>\n#include "dumux_b200.h"\nint main(void){printf("%zu %zu %zu %zu\\n", sizeof(dmx_options), '
+                             'sizeof(dmx_newton_params), sizeof(dmx_newton_report), sizeof(dmx_amg_params));return 0;}\n')
         exe = os.path.join(d, "s")
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), src, "-o", exe])
         sizes = [int(x) for x in subprocess.check_output([exe]).split()]
-    assert sizes == [ctypes.sizeof(binding.DmxOptions), ctypes.sizeof(binding.DmxNewtonParams), ctypes.sizeof(binding.DmxNewtonReport)]
+    assert sizes == [ctypes.sizeof(binding.DmxOptions), ctypes.sizeof(binding.DmxNewtonParams), ctypes.sizeof(binding.DmxNewtonReport),
+                     ctypes.sizeof(binding.DmxAmgParams)]
 
 
 def test_defaults_match_reference_parameters(lib):
