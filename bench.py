@@ -19,6 +19,7 @@ Besides the headline the JSON line carries
                   region (Newton count, BiCGSTAB counts, fields; N > 1: slabs and blocks, NaN-injection failure agreement);
                   the run aborts if it is off
   `strong_512`    BASELINE config 4: the 512^3 problem on these N GPUs (block decomposition, strong scaling), its own timed region
+  `amg`, `strong_512_amg`  the headline workload and config 4 again with the AMG preconditioner (AMGBiCGSTABIstlSolver)
   `roofline` / `kernels`  CUDA-event timers of every kernel class inside the timed region
   `e2e`           the same step through the host-buffer C-ABI call (pinned host curSol -> H2D -> step -> D2H)
   `cpu_baseline`  the oracle port on this box's host cores (bounded, labelled sample), `clocks`.
@@ -606,23 +607,47 @@ def run_b200(args):
                     "note": ("one ILU0 application = vec_skew + lower sweep + upper sweep (3 launches timed as one unit); "
                              "algorithmic bytes are the BCRS-equivalent figure of SURVEY 8d" if dom == "ilu0_apply" else None)}
 
-    # ---- BASELINE config 4: 512^3 strong scaling on these N GPUs (its own timed region) ----
+    # ---- the same workload with the AMG preconditioner (AMGBiCGSTABIstlSolver, istlsolvers.hh:716-757): its own timed region ----
+    amg_line = None
+    if args.solver == "ilu0" and not args.no_amg:
+        try:
+            ares = measure(comm, cells, upper, part, args.steps, 2, e2e=False, label="amg", solver="amg")
+            ak = kernel_table(ares, peak, {})
+            amg_line = {"linear_solver": SOLVER_TEXT["amg"], "ms_per_step": ares["ms_per_step"], "value": ares["value"], "unit": UNIT,
+                        "bicgstab_iterations_per_step": ares["its"], "speedup_vs_ilu0_step": res["ms_per_step"] / ares["ms_per_step"],
+                        "ilu0_bicgstab_iterations_per_step": res["its"], "gpu_launches": ares["launches"],
+                        "buckets_ms_per_step": {"assemble": ares["buckets"][0], "solve": ares["buckets"][1], "update": ares["buckets"][2]},
+                        "kernels": {k: {kk: v[kk] for kk in ("avg_ms", "share_of_step", "launches_timed") if kk in v} for k, v in ak.items()},
+                        "note": "block-decomposed runs: the GLOBAL hierarchy cut like the grid (aggregates do not cross processor "
+                                "boundaries), smoother BlockPreconditioner<SeqSSOR>; smoothing sweeps are booked under ilu0_apply "
+                                "(same sweep kernels), Galerkin/transfer kernels under amg_transfer"}
+        except SystemExit:
+            raise
+        except Exception as e:      # noqa: BLE001
+            amg_line = {"error": f"{type(e).__name__}: {e}"}
+
+    # ---- BASELINE config 4: 512^3 strong scaling on these N GPUs (its own timed regions: ILU0 and AMG) ----
     strong = None
-    if not args.no_strong and not args.global_cells and not args.global_z:
+    strong_amg = None
+
+    def strong_region(solver, key):
         sc = args.strong_cells
         spart = STRONG_PART.get(world, balanced_partition(world))
         try:
             sres = measure(comm, (sc, sc, sc), (6.0, 4.0, 4.0), spart if world > 1 else None, args.strong_steps, 1, e2e=False,
-                           label=f"strong_{sc}")
+                           label=f"{key}", solver=solver)
             sk = kernel_table(sres, peak, {})
-            strong = {"cells": [sc, sc, sc], "partitioning": list(spart), "scaling": "strong", "steps": args.strong_steps, "warmup": 1,
-                      "ms_per_step": sres["ms_per_step"], "bicgstab_iterations_per_step": sres["its"], "value": sres["value"], "unit": UNIT,
-                      "ms_per_bicgstab_iteration": sres["buckets"][1] / max(1, sres["its"]),
-                      "local_cells_rank0": sres["n_local"],
-                      "kernels": {k: {kk: v[kk] for kk in ("avg_ms", "share_of_step", "frac") if kk in v} for k, v in sk.items()}}
+            out = {"cells": [sc, sc, sc], "partitioning": list(spart), "scaling": "strong", "steps": args.strong_steps, "warmup": 1,
+                   "linear_solver": SOLVER_TEXT[solver],
+                   "ms_per_step": sres["ms_per_step"], "bicgstab_iterations_per_step": sres["its"], "value": sres["value"], "unit": UNIT,
+                   "ms_per_bicgstab_iteration": sres["buckets"][1] / max(1, sres["its"]),
+                   "local_cells_rank0": sres["n_local"],
+                   # (AMG: spmv / sweep launches of all levels are averaged together, so no per-launch roofline fraction there)
+                   "kernels": {k: {kk: v[kk] for kk in (("avg_ms", "share_of_step", "frac") if solver == "ilu0" else ("avg_ms", "share_of_step", "launches_timed"))
+                                   if kk in v} for k, v in sk.items()}}
             # the 1-GPU time of the same problem: measured by the N = 1 run of this bench on the same box (kept under gpurun_out/),
             # else the committed measurement of this round (profiles/), said which
-            ref_path = os.path.join(ROOT, "gpurun_out", f"strong{sc}_n1.json")
+            ref_path = os.path.join(ROOT, "gpurun_out", f"{key}_n1.json")
             if rank == 0:
                 if world == 1:
                     try:
@@ -630,23 +655,29 @@ def run_b200(args):
                         json.dump({"ms_per_step": sres["ms_per_step"], "its": sres["its"]}, open(ref_path, "w"))
                     except Exception:
                         pass
-                    strong["speedup_vs_1gpu"] = 1.0
+                    out["speedup_vs_1gpu"] = 1.0
                 else:
                     for src, pth in (("N=1 run of this bench on this box", ref_path),
-                                     ("committed 1-GPU measurement profiles/strong%d_n1.json" % sc, os.path.join(ROOT, "profiles", f"strong{sc}_n1.json"))):
+                                     (f"committed 1-GPU measurement profiles/{key}_n1.json", os.path.join(ROOT, "profiles", f"{key}_n1.json"))):
                         try:
                             one = json.load(open(pth))
-                            strong["speedup_vs_1gpu"] = one["ms_per_step"] / sres["ms_per_step"]
-                            strong["one_gpu_ms_per_step"] = one["ms_per_step"]
-                            strong["one_gpu_bicgstab_iterations"] = one["its"]
-                            strong["one_gpu_source"] = src
+                            out["speedup_vs_1gpu"] = one["ms_per_step"] / sres["ms_per_step"]
+                            out["one_gpu_ms_per_step"] = one["ms_per_step"]
+                            out["one_gpu_bicgstab_iterations"] = one["its"]
+                            out["one_gpu_source"] = src
                             break
                         except Exception:
                             continue
+            return out
         except SystemExit:
             raise
         except Exception as e:      # noqa: BLE001  (e.g. not enough memory for the requested size: report, keep the headline)
-            strong = {"error": f"{type(e).__name__}: {e}"}
+            return {"error": f"{type(e).__name__}: {e}"}
+
+    if not args.no_strong and not args.global_cells and not args.global_z:
+        strong = strong_region("ilu0", f"strong{args.strong_cells}")
+        if not args.no_amg:
+            strong_amg = strong_region("amg", f"strong{args.strong_cells}_amg")
 
     if rank != 0:
         comm.close()
@@ -681,7 +712,7 @@ def run_b200(args):
         "e2e": {"value": res["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": res["vec_bytes"], "d2h_bytes_per_step": res["vec_bytes"],
                 "ms_per_step": res["e2e_ms"]},
         "gpu_launches": res["launches"], "clocks": res["clocks"],
-        "parity_check": parity, "strong_512": strong,
+        "parity_check": parity, "amg": amg_line, "strong_512": strong, "strong_512_amg": strong_amg,
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu
@@ -708,7 +739,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cache", action="store_true", help="reference arm: time again even if this box already holds the measurement")
     ap.add_argument("--no-parity-check", action="store_true")
-    ap.add_argument("--no-strong", action="store_true", help="skip the 512^3 strong-scaling region")
+    ap.add_argument("--no-strong", action="store_true", help="skip the 512^3 strong-scaling regions")
+    ap.add_argument("--no-amg", action="store_true", help="skip the AMG-preconditioned regions")
     ap.add_argument("--strong-cells", type=int, default=512)
     ap.add_argument("--strong-steps", type=int, default=2)
     args = ap.parse_args()

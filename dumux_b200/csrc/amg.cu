@@ -25,6 +25,28 @@ struct AmgLevel {
     dmx_ctx* c = nullptr;        // level 0: the parent context; coarser levels: child contexts sharing its stream
     double *x = nullptr, *r = nullptr, *u = nullptr, *t = nullptr;
 };
+
+// Block-decomposed context (Grid.Partitioning, overlap 1): the hierarchy is the GLOBAL one and every level is decomposed like the
+// grid.  Aggregates never cross a processor boundary (as in dune-istl's parallel AMG): along every axis the OWNED range
+// [flo, fhi) of the local fine box is cut into pairs starting at its first cell (a last single cell if the length is odd); the
+// overlap cell below / above belongs to the neighbour's last / first aggregate = the coarse overlap cell clo - 1 / chi.  Single
+// domain: the owned range is the box, aggregate = index >> 1.  The cycle then contains the parallel pieces of dune's
+// overlapping AMG: smoother = BlockPreconditioner (local sweeps, copyOwnerToAll), operator = local mv + project; restriction
+// and prolongation need no exchange (children of an owned aggregate are owned; corrections are consistent on the overlap).
+struct AggMap { int flo[3], fhi[3], clo[3]; };
+__device__ __forceinline__ int agg1(int i, int flo, int fhi, int clo)
+{
+    if (i < flo) return clo - 1;
+    if (i >= fhi) return clo + ((fhi - flo + 1) >> 1);
+    return clo + ((i - flo) >> 1);
+}
+__device__ __forceinline__ void children1(int I, int flo, int fhi, int clo, int& c0, int& c1)
+{
+    const int chi = clo + ((fhi - flo + 1) >> 1);
+    if (I < clo) { c0 = flo - 1; c1 = flo; }
+    else if (I >= chi) { c0 = fhi; c1 = fhi + 1; }
+    else { c0 = flo + 2 * (I - clo); c1 = min(c0 + 2, fhi); }
+}
 struct AmgState {
     std::vector<AmgLevel> levels;
     double* own[3] = {nullptr, nullptr, nullptr};      // r, u, t of level 0
@@ -37,7 +59,7 @@ struct AmgState {
 // -z,-y,-x,diag,+x,+y,+z, every coarse slot accumulated from 0 in that visiting order.
 // ---------------------------------------------------------------------------------------------
 template <int B>
-__global__ void __launch_bounds__(128) amg_galerkin_kernel(int fx, int fy, int fz, int cx, int cy, int cz, int dim,
+__global__ void __launch_bounds__(128) amg_galerkin_kernel(int fx, int fy, int fz, int cx, int cy, int cz, int dim, AggMap M,
                                                            const int* __restrict__ f_rowptr, const double* __restrict__ fA,
                                                            const int* __restrict__ c_rowptr, double* __restrict__ cA)
 {
@@ -58,20 +80,22 @@ __global__ void __launch_bounds__(128) amg_galerkin_kernel(int fx, int fy, int f
                 for (int q = 0; q < BB; ++q) acc[s][q] += blk[q];
             }
     };
-    for (int dz = 0; dz < 2; ++dz)
-        for (int dy = 0; dy < 2; ++dy)
-            for (int dx = 0; dx < 2; ++dx) {
-                const int i = 2 * I + dx, j = 2 * J + dy, k = 2 * K + dz;
-                if (i >= fx || j >= fy || k >= fz) continue;
+    int i0, i1, j0, j1, k0, k1;
+    children1(I, M.flo[0], M.fhi[0], M.clo[0], i0, i1);
+    children1(J, M.flo[1], M.fhi[1], M.clo[1], j0, j1);
+    children1(K, M.flo[2], M.fhi[2], M.clo[2], k0, k1);
+    for (int k = k0; k < k1; ++k)
+        for (int j = j0; j < j1; ++j)
+            for (int i = i0; i < i1; ++i) {
                 const size_t row = (size_t)i + (size_t)fx * (j + (size_t)fy * k);
                 const double* p = fA + (size_t)f_rowptr[row] * BB;
-                if (dim > 2 && k > 0) { add(dz == 0 ? 0 : 3, p); p += BB; }
-                if (dim > 1 && j > 0) { add(dy == 0 ? 1 : 3, p); p += BB; }
-                if (i > 0) { add(dx == 0 ? 2 : 3, p); p += BB; }
+                if (dim > 2 && k > 0) { add(agg1(k - 1, M.flo[2], M.fhi[2], M.clo[2]) == K ? 3 : 0, p); p += BB; }
+                if (dim > 1 && j > 0) { add(agg1(j - 1, M.flo[1], M.fhi[1], M.clo[1]) == J ? 3 : 1, p); p += BB; }
+                if (i > 0) { add(agg1(i - 1, M.flo[0], M.fhi[0], M.clo[0]) == I ? 3 : 2, p); p += BB; }
                 add(3, p); p += BB;
-                if (i + 1 < fx) { add(dx == 0 ? 3 : 4, p); p += BB; }
-                if (dim > 1 && j + 1 < fy) { add(dy == 0 ? 3 : 5, p); p += BB; }
-                if (dim > 2 && k + 1 < fz) { add(dz == 0 ? 3 : 6, p); p += BB; }
+                if (i + 1 < fx) { add(agg1(i + 1, M.flo[0], M.fhi[0], M.clo[0]) == I ? 3 : 4, p); p += BB; }
+                if (dim > 1 && j + 1 < fy) { add(agg1(j + 1, M.flo[1], M.fhi[1], M.clo[1]) == J ? 3 : 5, p); p += BB; }
+                if (dim > 2 && k + 1 < fz) { add(agg1(k + 1, M.flo[2], M.fhi[2], M.clo[2]) == K ? 3 : 6, p); p += BB; }
             }
     double* out = cA + (size_t)c_rowptr[Ic] * BB;
     const bool ex[7] = {dim > 2 && K > 0, dim > 1 && J > 0, I > 0, true, I + 1 < cx, dim > 1 && J + 1 < cy, dim > 2 && K + 1 < cz};
@@ -84,9 +108,10 @@ __global__ void __launch_bounds__(128) amg_galerkin_kernel(int fx, int fy, int f
         }
 }
 
-// restriction with P^T: r_c[I] = sum of the children's entries, lexicographic child order, from 0
+// restriction with P^T: r_c[I] = sum of the children's entries, lexicographic child order, from 0 (coarse overlap cells: their
+// local children are fine overlap cells, whose defect is projected to zero)
 template <int B>
-__global__ void __launch_bounds__(256) amg_restrict_kernel(int fx, int fy, int fz, int cx, int cy, int cz, const double* __restrict__ rf,
+__global__ void __launch_bounds__(256) amg_restrict_kernel(int fx, int fy, int fz, int cx, int cy, int cz, AggMap M, const double* __restrict__ rf,
                                                            double* __restrict__ rc)
 {
     const int Ic = blockIdx.x * blockDim.x + threadIdx.x;
@@ -95,11 +120,13 @@ __global__ void __launch_bounds__(256) amg_restrict_kernel(int fx, int fy, int f
     double s[B];
 #pragma unroll
     for (int e = 0; e < B; ++e) s[e] = 0.0;
-    for (int dz = 0; dz < 2; ++dz)
-        for (int dy = 0; dy < 2; ++dy)
-            for (int dx = 0; dx < 2; ++dx) {
-                const int i = 2 * I + dx, j = 2 * J + dy, k = 2 * K + dz;
-                if (i >= fx || j >= fy || k >= fz) continue;
+    int i0, i1, j0, j1, k0, k1;
+    children1(I, M.flo[0], M.fhi[0], M.clo[0], i0, i1);
+    children1(J, M.flo[1], M.fhi[1], M.clo[1], j0, j1);
+    children1(K, M.flo[2], M.fhi[2], M.clo[2], k0, k1);
+    for (int k = k0; k < k1; ++k)
+        for (int j = j0; j < j1; ++j)
+            for (int i = i0; i < i1; ++i) {
                 const size_t row = (size_t)i + (size_t)fx * (j + (size_t)fy * k);
 #pragma unroll
                 for (int e = 0; e < B; ++e) s[e] += rf[row * B + e];
@@ -110,13 +137,14 @@ __global__ void __launch_bounds__(256) amg_restrict_kernel(int fx, int fy, int f
 
 // prolongation of the coarse correction, damped: u_i = damp * x_c[aggregate(i)];  x_i += u_i (x_i = u_i if `first`)
 template <int B>
-__global__ void __launch_bounds__(256) amg_prolong_kernel(int fx, int fy, int fz, int cx, int cy, double damp, const double* __restrict__ xc,
+__global__ void __launch_bounds__(256) amg_prolong_kernel(int fx, int fy, int fz, int cx, int cy, AggMap M, double damp, const double* __restrict__ xc,
                                                           double* __restrict__ u, double* __restrict__ x, int first)
 {
     const size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= (size_t)fx * fy * fz) return;
     const int i = (int)(row % fx), j = (int)((row / fx) % fy), k = (int)(row / ((size_t)fx * fy));
-    const size_t Ic = (size_t)(i >> 1) + (size_t)cx * ((j >> 1) + (size_t)cy * (k >> 1));
+    const size_t Ic = (size_t)agg1(i, M.flo[0], M.fhi[0], M.clo[0]) +
+                      (size_t)cx * (agg1(j, M.flo[1], M.fhi[1], M.clo[1]) + (size_t)cy * agg1(k, M.flo[2], M.fhi[2], M.clo[2]));
 #pragma unroll
     for (int e = 0; e < B; ++e) {
         const double v = damp * xc[Ic * B + e];
@@ -147,7 +175,16 @@ void amg_free(dmx_ctx* ctx)
     ctx->amg = nullptr;
 }
 
-// hierarchy of boxes: halve every axis (ceil) until <= coarsest_cells cells remain (or max_levels)
+static AggMap agg_map(const dmx_ctx* f, const dmx_ctx* c)
+{
+    AggMap M;
+    for (int a = 0; a < 3; ++a) { M.flo[a] = f->own_lo[a]; M.fhi[a] = f->own_hi[a]; M.clo[a] = c->own_lo[a]; }
+    return M;
+}
+
+// hierarchy of boxes: pair the cells of every axis (per owned range) until <= coarsest_cells GLOBAL cells remain, no axis can be
+// coarsened any further (every rank owns one cell along the partitioned axes) or max_levels is reached.  Every rank computes the
+// owned sizes of all torus coordinates, so the boxes of a level need no communication.
 static int amg_build(dmx_ctx* ctx)
 {
     amg_free(ctx);
@@ -159,18 +196,38 @@ static int amg_build(dmx_ctx* ctx)
     AmgLevel l0;
     l0.c = ctx; l0.r = st->own[0]; l0.u = st->own[1]; l0.t = st->own[2];
     st->levels.push_back(l0);
-    int nc[3] = {ctx->nc[0], ctx->nc[1], ctx->nc[2]};
+    const bool dist = ctx->nranks > 1;
+    std::vector<int> sizes[3];                      // owned cells of every torus coordinate, per axis
+    for (int a = 0; a < 3; ++a) {
+        const int N = ctx->gcells[a], P = dist ? ctx->part[a] : 1;
+        const int m = N / P, rem = N % P;
+        for (int c = 0; c < P; ++c) sizes[a].push_back(c < P - rem ? m : m + 1);        // Yasp's partitioning, see finish_grid
+    }
+    int g[3] = {ctx->gcells[0], ctx->gcells[1], ctx->gcells[2]};
     while ((int)st->levels.size() < ctx->amg_prm.max_levels) {
-        const long long n = (long long)nc[0] * nc[1] * nc[2];
-        if (n <= ctx->amg_prm.coarsest_cells) break;
+        if ((long long)g[0] * g[1] * g[2] <= ctx->amg_prm.coarsest_cells) break;
+        int cg[3], off[3], nc[3], olo[3], ohi[3];
         bool can = false;
-        for (int a = 0; a < ctx->dim; ++a) {
-            if (nc[a] > 1) can = true;
-            nc[a] = (nc[a] + 1) / 2;
+        for (int a = 0; a < 3; ++a) {
+            if (a < ctx->dim)
+                for (int& s : sizes[a]) s = (s + 1) / 2;
+            cg[a] = 0;
+            int b0 = 0;
+            const int mine = dist ? ctx->pcoord[a] : 0;
+            for (int c = 0; c < (int)sizes[a].size(); ++c) {
+                if (c == mine) b0 = cg[a];
+                cg[a] += sizes[a][c];
+            }
+            const int b1 = b0 + sizes[a][mine];
+            const int lo = std::max(0, b0 - 1), hi = std::min(cg[a], b1 + 1);
+            off[a] = lo; nc[a] = hi - lo; olo[a] = b0 - lo; ohi[a] = b1 - lo;
+            if (cg[a] != g[a]) can = true;
         }
         if (!can) break;
         dmx_ctx* child = nullptr;
-        if (int rc = make_child_ctx(ctx, nc, &child)) return rc;
+        if (int rc = dist ? make_child_ctx(ctx, cg, off, nc, olo, ohi, &child) : make_child_ctx(ctx, cg, nullptr, nullptr, nullptr, nullptr, &child))
+            return rc;
+        for (int a = 0; a < 3; ++a) g[a] = cg[a];
         AmgLevel lv;
         lv.c = child;
         lv.x = child->d_vec[DMX_VEC_DELTA]; lv.r = child->d_vec[DMX_VEC_RESIDUAL];
@@ -204,12 +261,13 @@ int amg_setup(dmx_ctx* ctx)
             dmx_ctx* f = st->levels[l - 1].c;
             ProfScope ps(ctx, DMX_K_AMG);
             const int grid = (c->n + 127) / 128;
+            const AggMap M = agg_map(f, c);
             if (ctx->b == 2)
-                amg_galerkin_kernel<2><<<grid, 128, 0, ctx->stream>>>(f->nc[0], f->nc[1], f->nc[2], c->nc[0], c->nc[1], c->nc[2], ctx->dim, f->d_rowptr,
-                                                                      f->d_J, c->d_rowptr, c->d_J);
+                amg_galerkin_kernel<2><<<grid, 128, 0, ctx->stream>>>(f->nc[0], f->nc[1], f->nc[2], c->nc[0], c->nc[1], c->nc[2], ctx->dim, M,
+                                                                      f->d_rowptr, f->d_J, c->d_rowptr, c->d_J);
             else
-                amg_galerkin_kernel<1><<<grid, 128, 0, ctx->stream>>>(f->nc[0], f->nc[1], f->nc[2], c->nc[0], c->nc[1], c->nc[2], ctx->dim, f->d_rowptr,
-                                                                      f->d_J, c->d_rowptr, c->d_J);
+                amg_galerkin_kernel<1><<<grid, 128, 0, ctx->stream>>>(f->nc[0], f->nc[1], f->nc[2], c->nc[0], c->nc[1], c->nc[2], ctx->dim, M,
+                                                                      f->d_rowptr, f->d_J, c->d_rowptr, c->d_J);
             DMX_CHECK_LAUNCH();
             c->jac_diagonal = false;
         }
@@ -229,8 +287,10 @@ static int amg_smooth_step(dmx_ctx* ctx, AmgLevel& L, bool first, bool need_defe
     dmx_ctx* c = L.c;
     const size_t len = (size_t)c->n * c->b;
     if (int rc = ilu0_apply(c, L.r, L.u)) return rc;                          // update = M^-1 defect (from update = 0)
+    if (c->nranks > 1)
+        if (int rc = halo_exchange(c, L.u)) return rc;                        // BlockPreconditioner::apply: copyOwnerToAll
     if (need_defect)
-        if (int rc = launch_spmv_local(c, L.u, L.t)) return rc;               // A update
+        if (int rc = launch_spmv(c, L.u, L.t)) return rc;                     // A update (block-decomposed: projected)
     ProfScope ps(ctx, DMX_K_AMG);
     const int grid = (int)std::min<size_t>((len + 255) / 256, 148 * 8);
     amg_update_kernel<<<grid, 256, 0, ctx->stream>>>(len, L.u, L.t, L.x, L.r, first ? 1 : 0, 1, need_defect ? 1 : 0);
@@ -257,8 +317,9 @@ static int amg_cycle(dmx_ctx* ctx, AmgState* st, int l)
     {
         ProfScope ps(ctx, DMX_K_AMG);
         const int grid = (cc->n + 255) / 256;
-        if (ctx->b == 2) amg_restrict_kernel<2><<<grid, 256, 0, ctx->stream>>>(c->nc[0], c->nc[1], c->nc[2], cc->nc[0], cc->nc[1], cc->nc[2], L.r, C.r);
-        else amg_restrict_kernel<1><<<grid, 256, 0, ctx->stream>>>(c->nc[0], c->nc[1], c->nc[2], cc->nc[0], cc->nc[1], cc->nc[2], L.r, C.r);
+        const AggMap M = agg_map(c, cc);
+        if (ctx->b == 2) amg_restrict_kernel<2><<<grid, 256, 0, ctx->stream>>>(c->nc[0], c->nc[1], c->nc[2], cc->nc[0], cc->nc[1], cc->nc[2], M, L.r, C.r);
+        else amg_restrict_kernel<1><<<grid, 256, 0, ctx->stream>>>(c->nc[0], c->nc[1], c->nc[2], cc->nc[0], cc->nc[1], cc->nc[2], M, L.r, C.r);
         DMX_CHECK_LAUNCH();
     }
     if (int rc = amg_cycle(ctx, st, l + 1)) return rc;
@@ -266,14 +327,15 @@ static int amg_cycle(dmx_ctx* ctx, AmgState* st, int l)
         ProfScope ps(ctx, DMX_K_AMG);
         const int grid = (c->n + 255) / 256;
         const int first = prm.pre_steps == 0 ? 1 : 0;
+        const AggMap M = agg_map(c, cc);
         if (ctx->b == 2)
-            amg_prolong_kernel<2><<<grid, 256, 0, ctx->stream>>>(c->nc[0], c->nc[1], c->nc[2], cc->nc[0], cc->nc[1], prm.prolongation_damping, C.x, L.u, L.x, first);
+            amg_prolong_kernel<2><<<grid, 256, 0, ctx->stream>>>(c->nc[0], c->nc[1], c->nc[2], cc->nc[0], cc->nc[1], M, prm.prolongation_damping, C.x, L.u, L.x, first);
         else
-            amg_prolong_kernel<1><<<grid, 256, 0, ctx->stream>>>(c->nc[0], c->nc[1], c->nc[2], cc->nc[0], cc->nc[1], prm.prolongation_damping, C.x, L.u, L.x, first);
+            amg_prolong_kernel<1><<<grid, 256, 0, ctx->stream>>>(c->nc[0], c->nc[1], c->nc[2], cc->nc[0], cc->nc[1], M, prm.prolongation_damping, C.x, L.u, L.x, first);
         DMX_CHECK_LAUNCH();
     }
     if (prm.post_steps > 0) {
-        if (int rc = launch_spmv_local(c, L.u, L.t)) return rc;
+        if (int rc = launch_spmv(c, L.u, L.t)) return rc;
         ProfScope ps(ctx, DMX_K_AMG);
         const size_t len = (size_t)c->n * c->b;
         const int grid = (int)std::min<size_t>((len + 255) / 256, 148 * 8);

@@ -124,8 +124,16 @@ int finish_grid(dmx_ctx* ctx, int model, int dim, const int* cells, const std::v
     // io/grid/gridmanager_yasp.hh:129,194-203).  Default: slabs along the last axis ("1 .. P").  Rank -> torus coordinate with x
     // fastest and, per axis, n/P cells for the first P - n%P processes and one more for the rest (dune-grid torus.hh
     // Torus::rank_to_coord / Torus::partition) [DUNE-ext].
-    for (int a = 0; a < 3; ++a) { ctx->part[a] = 1; ctx->pcoord[a] = 0; ctx->own_lo[a] = 0; ctx->own_hi[a] = ctx->gcells[a]; }
-    if (ctx->nranks > 1) {
+    for (int a = 0; a < 3; ++a) {
+        if (!ctx->explicit_box) { ctx->part[a] = 1; ctx->pcoord[a] = 0; }
+        ctx->own_lo[a] = 0; ctx->own_hi[a] = ctx->gcells[a];
+    }
+    if (ctx->nranks > 1 && ctx->explicit_box) {
+        // level context of a block-decomposed AMG hierarchy: part / pcoord are the parent's, the box is handed in
+        for (int a = 0; a < 3; ++a) {
+            ctx->off[a] = ctx->xb_off[a]; ctx->nc[a] = ctx->xb_nc[a]; ctx->own_lo[a] = ctx->xb_own_lo[a]; ctx->own_hi[a] = ctx->xb_own_hi[a];
+        }
+    } else if (ctx->nranks > 1) {
         if (ctx->part_req[0] > 0) {
             for (int a = 0; a < 3; ++a) ctx->part[a] = ctx->part_req[a];
             for (int a = dim; a < 3; ++a)
@@ -314,7 +322,7 @@ int dmx_destroy(dmx_ctx* ctx)
     cudaStreamSynchronize(ctx->stream);
     amg_free(ctx);
     sk_free(ctx);
-    if (ctx->nccl_comm) nccl_destroy(ctx);
+    if (ctx->nccl_comm && ctx->owns_stream) nccl_destroy(ctx);
     void* ptrs[] = {ctx->d_geom, ctx->d_K, ctx->d_phi, ctx->d_q, ctx->d_region, ctx->d_tij[0], ctx->d_tij[1], ctx->d_tij[2], ctx->d_laws,
                     ctx->d_tab_buf, ctx->d_rowptr, ctx->d_colidx, ctx->d_diag, ctx->d_J, ctx->d_ilu, ctx->d_rt, ctx->d_p, ctx->d_v, ctx->d_t,
                     ctx->d_y, ctx->d_z, ctx->d_dinv, ctx->d_gm, ctx->d_vf, ctx->d_color_rows, ctx->d_xold, ctx->d_lrows, ctx->d_urows, ctx->d_lptr, ctx->d_uptr, ctx->d_barrier, ctx->d_partials,
@@ -1000,7 +1008,7 @@ int dmx_time_kernel(dmx_ctx* ctx, int which, int reps, float* ms_avg)
 
 namespace dmx {
 
-int make_child_ctx(dmx_ctx* parent, const int* cells, dmx_ctx** out)
+int make_child_ctx(dmx_ctx* parent, const int* gcells, const int* off, const int* nc, const int* own_lo, const int* own_hi, dmx_ctx** out)
 {
     dmx_ctx* ctx = parent;       // for the error macros
     dmx_ctx* c = new dmx_ctx;
@@ -1009,11 +1017,19 @@ int make_child_ctx(dmx_ctx* parent, const int* cells, dmx_ctx** out)
     c->stream = parent->stream;
     c->owns_stream = false;
     c->prof_parent = parent;
+    if (parent->nranks > 1 && off) {
+        c->rank = parent->rank; c->nranks = parent->nranks; c->nccl_comm = parent->nccl_comm;
+        c->explicit_box = true;
+        for (int a = 0; a < 3; ++a) {
+            c->part[a] = parent->part[a]; c->pcoord[a] = parent->pcoord[a];
+            c->xb_off[a] = off[a]; c->xb_nc[a] = nc[a]; c->xb_own_lo[a] = own_lo[a]; c->xb_own_hi[a] = own_hi[a];
+        }
+    }
     dmx_default_options(&c->opt);
     dmx_default_amg_params(&c->amg_prm);
     if (alloc_ctx_scratch(c)) { dmx_destroy(c); return fail(ctx, DMX_ERR_CUDA, "AMG: cannot allocate a level context"); }
     const double lower[3] = {0.0, 0.0, 0.0}, upper[3] = {1.0, 1.0, 1.0};
-    const int rc = dmx_grid_structured(c, parent->b == 2 ? DMX_MODEL_2P : DMX_MODEL_1P, parent->dim, cells, lower, upper);
+    const int rc = dmx_grid_structured(c, parent->b == 2 ? DMX_MODEL_2P : DMX_MODEL_1P, parent->dim, gcells, lower, upper);
     if (rc) {
         parent->err = "AMG level context: " + c->err;
         dmx_destroy(c);

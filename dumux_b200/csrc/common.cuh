@@ -155,7 +155,10 @@ struct dmx_ctx {
     void* amg = nullptr;              // AmgState of amg.cu
     dmx_amg_params amg_prm;
     bool amg_dirty = true;            // hierarchy has to be (re)built: new grid or new parameters
-    bool owns_stream = true;          // false: a level context of an AMG hierarchy running on its parent's stream
+    bool owns_stream = true;          // false: a level context of an AMG hierarchy running on its parent's stream (and communicator)
+    // level contexts of a block-decomposed hierarchy get their box handed in instead of Yasp's partitioning formula
+    bool explicit_box = false;
+    int xb_off[3] = {0, 0, 0}, xb_nc[3] = {1, 1, 1}, xb_own_lo[3] = {0, 0, 0}, xb_own_hi[3] = {1, 1, 1};
     dmx_ctx* prof_parent = nullptr;   // kernel-class timers of a level context are booked on the parent
     std::vector<dmx_ctx*> children;   // level contexts (for the launch count)
 
@@ -318,7 +321,9 @@ int amg_apply(dmx_ctx* ctx, const double* d, double* v);
 int amg_num_levels(dmx_ctx* ctx);
 dmx_ctx* amg_level_ctx(dmx_ctx* ctx, int level);
 // implemented in api.cu: level contexts of a hierarchy (own grid, matrix and vectors; the parent's device and stream)
-int make_child_ctx(dmx_ctx* parent, const int* cells, dmx_ctx** out);
+// `gcells`: global cells of the level; distributed parent: off / nc = local box (overlap included), own_lo / own_hi = owned range
+// in local indices (all per axis); single domain: pass nullptr for the four
+int make_child_ctx(dmx_ctx* parent, const int* gcells, const int* off, const int* nc, const int* own_lo, const int* own_hi, dmx_ctx** out);
 void destroy_child_ctx(dmx_ctx* child);
 // implemented in dist.cu
 int nccl_init(dmx_ctx* ctx, const void* uid);

@@ -967,7 +967,8 @@ int precond_apply_local(dmx_ctx* ctx, int precond, const double* d, double* v)
 static int precond_apply(dmx_ctx* ctx, int precond, const double* d, double* v)
 {
     if (int rc = precond_apply_local(ctx, precond, d, v)) return rc;
-    if (ctx->nranks > 1) return halo_exchange(ctx, v);
+    // the block-decomposed AMG cycle already returns a correction that is consistent on the overlap (amg.cu)
+    if (ctx->nranks > 1 && precond != DMX_PRECOND_AMG) return halo_exchange(ctx, v);
     return 0;
 }
 

@@ -141,6 +141,62 @@ class TorchComm:
 # ----------------------------------------------------------------------------------------------------------
 # one rank
 # ----------------------------------------------------------------------------------------------------------
+class RankLayout:
+    """Owner mask and copyOwnerToAll neighbours of one rank's box: per axis (lo, hi, b0, b1) = local box incl. overlap and
+    owned range in GLOBAL indices (3 axes; unused axes (0, 1, 0, 1)), `part3` ranks per axis, block size b."""
+
+    def __init__(self, comm, part3, ranges3, b):
+        import itertools
+        self.comm, self.b = comm, b
+        self.ranges = list(ranges3)
+        lc3 = tuple(r[1] - r[0] for r in ranges3)
+        self.cells3 = lc3
+        self.off3 = tuple(r[0] for r in ranges3)
+        self.n = int(np.prod(lc3))
+        self.shape = (lc3[2], lc3[1], lc3[0], b)               # local block vector viewed [z, y, x, eq]
+        own = np.ones(self.shape[:3], dtype=bool)
+        self.own_rng = []
+        for a in range(3):
+            lo, hi, b0, b1 = ranges3[a]
+            self.own_rng.append((b0 - lo, b1 - lo))
+            idx = np.arange(lc3[a])
+            ok = (idx >= b0 - lo) & (idx < b1 - lo)
+            shp = [1, 1, 1]
+            shp[2 - a] = -1
+            own &= ok.reshape(shp)
+        self.owner_cells = own.reshape(-1)
+        self.owner = np.repeat(self.owner_cells, b)               # per scalar dof
+        coord = problems.rank_coord(part3, comm.rank)
+        self.neighbours = []
+        for dz, dy, dx in itertools.product((-1, 0, 1), repeat=3):
+            d = (dx, dy, dz)
+            if d == (0, 0, 0):
+                continue
+            c = [coord[a] + d[a] for a in range(3)]
+            if any(c[a] < 0 or c[a] >= part3[a] for a in range(3)):
+                continue
+            nb = c[0] + part3[0] * (c[1] + part3[1] * c[2])
+            snd, rcv = [], []
+            for a in range(3):
+                o0, o1 = self.own_rng[a]
+                if d[a] < 0:
+                    snd.append(slice(o0, o0 + 1)); rcv.append(slice(o0 - 1, o0))
+                elif d[a] > 0:
+                    snd.append(slice(o1 - 1, o1)); rcv.append(slice(o1, o1 + 1))
+                else:
+                    snd.append(slice(o0, o1)); rcv.append(slice(o0, o1))
+            self.neighbours.append((nb, tuple(reversed(snd)), tuple(reversed(rcv))))
+
+    # copyOwnerToAll with overlap 1: owned cells inside a neighbour's overlap go out, my overlap cells come in from their owner
+    def copy_owner_to_all(self, v):
+        if not self.neighbours:
+            return
+        g = v.reshape(self.shape)
+        got = self.comm.exchange({nb: np.ascontiguousarray(g[snd]).reshape(-1) for nb, snd, _ in self.neighbours})
+        for nb, _, rcv in self.neighbours:
+            g[rcv] = got[nb].reshape(g[rcv].shape)
+
+
 class BoxRank:
     """Local problem of one rank: block [lo, hi) per axis incl. overlap, owned (interior) range [b0, b1) per axis.
     `part` = Grid.Partitioning (ranks per axis); None = slabs along the last axis.  `make_spec(box)` builds the box-local
@@ -185,53 +241,13 @@ class BoxRank:
         self.o = O.Oracle(loc, num_threads=num_threads)
         self.b = self.o.b
         self.n = self.o.n
-        lc3 = tuple(loc.cells) + (1,) * (3 - dim)
-        self.shape = (lc3[2], lc3[1], lc3[0], self.b)            # local block vector viewed [z, y, x, eq]
-        own = np.ones(self.shape[:3], dtype=bool)
-        self.own_rng = []
-        for a in range(3):
-            if a < dim:
-                lo, hi, b0, b1 = self.ranges[a]
-                self.own_rng.append((b0 - lo, b1 - lo))
-            else:
-                self.own_rng.append((0, 1))
-            idx = np.arange(lc3[a])
-            ok = (idx >= self.own_rng[a][0]) & (idx < self.own_rng[a][1])
-            shp = [1, 1, 1]
-            shp[2 - a] = -1
-            own &= ok.reshape(shp)
-        self.owner = np.repeat(own.reshape(-1), self.b)           # per scalar dof
-        # copyOwnerToAll neighbours: direction d in {-1,0,1}^3 \ 0 -> (rank, send slices, recv slices), [z, y, x] order
-        coord = problems.rank_coord(tuple(self.part) + (1,) * (3 - dim), comm.rank)
         part3 = tuple(self.part) + (1,) * (3 - dim)
-        self.neighbours = []
-        for dz, dy, dx in itertools.product((-1, 0, 1), repeat=3):
-            d = (dx, dy, dz)
-            if d == (0, 0, 0):
-                continue
-            c = [coord[a] + d[a] for a in range(3)]
-            if any(c[a] < 0 or c[a] >= part3[a] for a in range(3)):
-                continue
-            nb = c[0] + part3[0] * (c[1] + part3[1] * c[2])
-            snd, rcv = [], []
-            for a in range(3):
-                o0, o1 = self.own_rng[a]
-                if d[a] < 0:
-                    snd.append(slice(o0, o0 + 1)); rcv.append(slice(o0 - 1, o0))
-                elif d[a] > 0:
-                    snd.append(slice(o1 - 1, o1)); rcv.append(slice(o1, o1 + 1))
-                else:
-                    snd.append(slice(o0, o1)); rcv.append(slice(o0, o1))
-            self.neighbours.append((nb, tuple(reversed(snd)), tuple(reversed(rcv))))
+        self.layout = RankLayout(comm, part3, list(self.ranges) + [(0, 1, 0, 1)] * (3 - dim), self.b)
+        self.part3 = part3
+        self.shape, self.own_rng, self.owner, self.neighbours = self.layout.shape, self.layout.own_rng, self.layout.owner, self.layout.neighbours
 
-    # copyOwnerToAll with overlap 1: owned cells inside a neighbour's overlap go out, my overlap cells come in from their owner
     def copy_owner_to_all(self, v):
-        if not self.neighbours:
-            return
-        g = v.reshape(self.shape)
-        got = self.comm.exchange({nb: np.ascontiguousarray(g[snd]).reshape(-1) for nb, snd, _ in self.neighbours})
-        for nb, _, rcv in self.neighbours:
-            g[rcv] = got[nb].reshape(g[rcv].shape)
+        self.layout.copy_owner_to_all(v)
 
     def gather_box(self):
         """(global slices [z, y, x] of my owned block, local slices of it)"""
@@ -268,8 +284,10 @@ class BoxRank:
         if precond == "ssor":
             return lambda d: O.ssor_apply(n, b, rp, ci, jac, d)
         if precond == "amg":
+            # the GLOBAL hierarchy, block-decomposed like the grid: its cycle contains the owner -> copy exchanges itself
             from oracle.amg_oracle import AmgOracle
-            amg = AmgOracle(self.local.cells, len(self.local.cells), b, rp, ci, jac, **(self.amg_params or {}))
+            amg = AmgOracle(self.local.cells, len(self.local.cells), b, rp, ci, jac, layout=self.layout, part3=self.part3,
+                            gcells=self.cells, **(self.amg_params or {}))
             st = int(self.comm.allreduce(float(amg.status), "max"))
             return None if st != 0 else amg.apply
         kind = {"par_mt_jac": O.PARMT_JAC, "par_mt_sor": O.PARMT_SOR, "par_mt_ssor": O.PARMT_SSOR}[precond]

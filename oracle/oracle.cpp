@@ -1588,34 +1588,56 @@ int orc_parmt_colors(int n, const int* rowptr, const int* colidx, int* colors)
     return nc;
 }
 // ---- aggregation AMG on the structured hierarchy (oracle/amg_oracle.py; device: dumux_b200/csrc/amg.cu) ----
-// Galerkin product P^T A P for 2x2x2 box aggregates and piecewise-constant prolongation on the 7-point pattern: coarse block
-// (I,J) = sum of the fine blocks (i,j), i in I, j in J.  Canonical summation order: children of a coarse cell in lexicographic
-// order (x fastest), per child its entries in column order, every coarse slot accumulated from 0 in that visiting order.
-void orc_amg_galerkin(int b, int dim, const int* fcells, const int* f_rowptr, const double* fA, const int* ccells, const int* c_rowptr,
-                      double* cA)
+// Galerkin product P^T A P for box aggregates (2 cells per axis) and piecewise-constant prolongation on the 7-point pattern:
+// coarse block (I,J) = sum of the fine blocks (i,j), i in I, j in J.  Canonical summation order: children of a coarse cell in
+// lexicographic order (x fastest), per child its entries in column order, every coarse slot accumulated from 0 in that
+// visiting order.
+// Aggregates never cross a processor boundary (as in dune-istl's parallel AMG): along every axis the OWNED range
+// [fown_lo, fown_hi) of the local fine box is cut into pairs starting at its first cell (a last single cell if the length is
+// odd); the overlap cell below / above belongs to the neighbour's last / first aggregate, which is the coarse overlap cell
+// cown_lo - 1 / cown_hi.  Single domain: the owned range is the box, i.e. aggregate = index >> 1.  Rows of coarse overlap
+// cells are partial sums (only the children inside the local fine box), like the incomplete rows of fine overlap cells.
+static inline int amg_agg1(int i, int flo, int fhi, int clo)
+{
+    if (i < flo) return clo - 1;
+    if (i >= fhi) return clo + ((fhi - flo + 1) >> 1);
+    return clo + ((i - flo) >> 1);
+}
+static inline void amg_children1(int I, int flo, int fhi, int clo, int& c0, int& c1)
+{
+    const int chi = clo + ((fhi - flo + 1) >> 1);
+    if (I < clo) { c0 = flo - 1; c1 = flo; }
+    else if (I >= chi) { c0 = fhi; c1 = fhi + 1; }
+    else { c0 = flo + 2 * (I - clo); c1 = c0 + 2 < fhi ? c0 + 2 : fhi; }
+}
+void orc_amg_galerkin(int b, int dim, const int* fcells, const int* fown_lo, const int* fown_hi, const int* f_rowptr, const double* fA,
+                      const int* ccells, const int* cown_lo, const int* c_rowptr, double* cA)
 {
     const int bb = b * b;
     const int fx = fcells[0], fy = fcells[1], fz = fcells[2], cx = ccells[0], cy = ccells[1], cz = ccells[2];
+    auto agg = [&](int a, int i) { return amg_agg1(i, fown_lo[a], fown_hi[a], cown_lo[a]); };
     for (int K = 0; K < cz; ++K)
         for (int J = 0; J < cy; ++J)
             for (int I = 0; I < cx; ++I) {
                 const int Ic = I + cx * (J + cy * K);
                 double acc[7][4] = {};
                 auto add = [&](int slot, const double* blk) { for (int q = 0; q < bb; ++q) acc[slot][q] += blk[q]; };
-                for (int dz = 0; dz < 2; ++dz)
-                    for (int dy = 0; dy < 2; ++dy)
-                        for (int dx = 0; dx < 2; ++dx) {
-                            const int i = 2 * I + dx, j = 2 * J + dy, k = 2 * K + dz;
-                            if (i >= fx || j >= fy || k >= fz) continue;
+                int i0, i1, j0, j1, k0, k1;
+                amg_children1(I, fown_lo[0], fown_hi[0], cown_lo[0], i0, i1);
+                amg_children1(J, fown_lo[1], fown_hi[1], cown_lo[1], j0, j1);
+                amg_children1(K, fown_lo[2], fown_hi[2], cown_lo[2], k0, k1);
+                for (int k = k0; k < k1; ++k)
+                    for (int j = j0; j < j1; ++j)
+                        for (int i = i0; i < i1; ++i) {
                             const size_t row = (size_t)i + (size_t)fx * (j + (size_t)fy * k);
                             const double* p = fA + (size_t)f_rowptr[row] * bb;
-                            if (dim > 2 && k > 0) { add(dz == 0 ? 0 : 3, p); p += bb; }
-                            if (dim > 1 && j > 0) { add(dy == 0 ? 1 : 3, p); p += bb; }
-                            if (i > 0) { add(dx == 0 ? 2 : 3, p); p += bb; }
+                            if (dim > 2 && k > 0) { add(agg(2, k - 1) == K ? 3 : 0, p); p += bb; }
+                            if (dim > 1 && j > 0) { add(agg(1, j - 1) == J ? 3 : 1, p); p += bb; }
+                            if (i > 0) { add(agg(0, i - 1) == I ? 3 : 2, p); p += bb; }
                             add(3, p); p += bb;
-                            if (i + 1 < fx) { add(dx == 0 ? 3 : 4, p); p += bb; }
-                            if (dim > 1 && j + 1 < fy) { add(dy == 0 ? 3 : 5, p); p += bb; }
-                            if (dim > 2 && k + 1 < fz) { add(dz == 0 ? 3 : 6, p); p += bb; }
+                            if (i + 1 < fx) { add(agg(0, i + 1) == I ? 3 : 4, p); p += bb; }
+                            if (dim > 1 && j + 1 < fy) { add(agg(1, j + 1) == J ? 3 : 5, p); p += bb; }
+                            if (dim > 2 && k + 1 < fz) { add(agg(2, k + 1) == K ? 3 : 6, p); p += bb; }
                         }
                 double* out = cA + (size_t)c_rowptr[Ic] * bb;
                 const bool ex[7] = {dim > 2 && K > 0, dim > 1 && J > 0, I > 0, true, I + 1 < cx, dim > 1 && J + 1 < cy, dim > 2 && K + 1 < cz};

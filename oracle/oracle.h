@@ -97,8 +97,8 @@ void orc_parmt_apply(int kind, int iterations, double relaxation, int n, int b, 
                      double* v, const double* d);
 int  orc_parmt_colors(int n, const int* rowptr, const int* colidx, int* colors);
 /* aggregation AMG on the structured hierarchy (oracle/amg_oracle.py restates dumux_b200/csrc/amg.cu) */
-void orc_amg_galerkin(int b, int dim, const int* fcells, const int* f_rowptr, const double* fA, const int* ccells, const int* c_rowptr,
-                      double* cA);
+void orc_amg_galerkin(int b, int dim, const int* fcells, const int* fown_lo, const int* fown_hi, const int* f_rowptr, const double* fA,
+                      const int* ccells, const int* cown_lo, const int* c_rowptr, double* cA);
 int  orc_ssor_factor(int n, int b, const int* rowptr, const int* colidx, const double* A, double* out);
 /* tracer: binary diffusion coefficient D (FluidSystem::binaryDiffusionCoefficient) and SpatialParams.Tortuosity (default 0.5) of
    DiffusivityConstantTortuosity; D = 0 (the default) switches Fick's law off */

@@ -102,7 +102,7 @@ def lib():
         L.orc_parmt_solve.restype = C.c_int
         L.orc_parmt_apply.argtypes = [C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, _ip, _ip, _dp, _dp, _dp]
         L.orc_parmt_colors.argtypes = [C.c_int, _ip, _ip, _ip]
-        L.orc_amg_galerkin.argtypes = [C.c_int, C.c_int, _ip, _ip, _dp, _ip, _ip, _dp]
+        L.orc_amg_galerkin.argtypes = [C.c_int, C.c_int, _ip, _ip, _ip, _ip, _dp, _ip, _ip, _ip, _dp]
         L.orc_ssor_factor.argtypes = [C.c_int, C.c_int, _ip, _ip, _dp, _dp]
         L.orc_ssor_factor.restype = C.c_int
         L.orc_parmt_colors.restype = C.c_int

@@ -48,8 +48,10 @@ def _rank_job(rank_obj):
     x, st, its, red = rank_obj.bicgstab(jac, res, reduction=1e-11, maxit=500)
     xg, stg, itsg, redg = rank_obj.gmres(jac, res, reduction=1e-11, maxit=500, restart=10)
     u, nst, nsteps, lin_its = rank_obj.newton(rank_obj.spec.initial, rank_obj.spec.initial)
+    xa, sta, itsa, reda = rank_obj.bicgstab(jac, res, reduction=1e-11, maxit=500, precond="amg")
     return {"x": x, "st": st, "its": its, "red": red, "res": res, "u": u, "nst": nst, "nsteps": nsteps, "lin_its": lin_its,
-            "owner": rank_obj.owner.copy(), "xg": xg, "stg": stg, "itsg": itsg, "redg": redg, "jac": jac}
+            "owner": rank_obj.owner.copy(), "xg": xg, "stg": stg, "itsg": itsg, "redg": redg, "jac": jac,
+            "xa": xa, "sta": sta, "itsa": itsa}
 
 
 def _gloo_worker(rank, world, port, q, part=None):
@@ -170,6 +172,7 @@ def test_two_processes_over_gloo_match_reference(reference_runs):
         assert got[r]["stg"] == 0 and got[r]["itsg"] == two[r]["itsg"] and np.array_equal(got[r]["xg"], two[r]["xg"])
         assert got[r]["nsteps"] == two[r]["nsteps"] and got[r]["lin_its"] == two[r]["lin_its"]
         assert np.array_equal(got[r]["u"], two[r]["u"])
+        assert got[r]["sta"] == 0 and got[r]["itsa"] == two[r]["itsa"] and np.array_equal(got[r]["xa"], two[r]["xa"])
 
 
 # ------------------------------------------------------------------------------------------------------------------------
@@ -226,6 +229,57 @@ def test_block_decomposition_owned_rows_and_solution(reference_runs, block_runs,
     us = single["u"].reshape(-1, 2)
     assert np.linalg.norm(u[:, 0] - us[:, 0]) <= 1e-8 * np.linalg.norm(us[:, 0])
     assert np.linalg.norm(u[:, 1] - us[:, 1]) <= 1e-8 * max(1.0, np.linalg.norm(us[:, 1]))
+
+
+def test_block_decomposed_amg_is_partition_independent(reference_runs, block_runs):
+    """AMGBiCGSTABIstlSolver on a decomposition = the GLOBAL hierarchy cut like the grid (aggregates do not cross processor
+    boundaries, smoother = BlockPreconditioner<SeqSSOR>): the iteration count stays at the single-domain count (+-1) whatever the
+    partitioning, far below Schwarz-ILU0's; same solution; overlap copies equal their owners."""
+    single, two, three = reference_runs
+    assert single["sta"] == 0 and single["itsa"] * 3 < single["its"]
+    cases = [(None, 2, two), (None, 3, three)] + [(part, int(np.prod(part)), block_runs[part]) for part in BLOCK_PARTS]
+    for part, P, runs in cases:
+        assert all(o["sta"] == 0 for o in runs) and len({o["itsa"] for o in runs}) == 1
+        assert abs(runs[0]["itsa"] - single["itsa"]) <= 1, (part, runs[0]["itsa"], single["itsa"])
+        x = D.gather_owned([o["xa"] for o in runs], CELLS, P, 2, part)
+        assert np.linalg.norm(x - single["x"]) <= 1e-8 * np.linalg.norm(single["x"])
+        glob = x.reshape(CELLS[2], CELLS[1], CELLS[0], 2)
+        for r, o in enumerate(runs):
+            rng = problems.box_partition(CELLS, part if part is not None else problems.default_partitioning(3, P), r)
+            sl = tuple(slice(rng[a][0], rng[a][1]) for a in (2, 1, 0))
+            assert np.array_equal(o["xa"].reshape(glob[sl].shape), glob[sl])
+
+
+def test_amg_hierarchy_of_a_decomposition_tiles_the_global_levels():
+    """level boxes: on every level the owned ranges of the ranks tile the global box of that level, each rank holds its owned
+    range plus one overlap layer towards every neighbour, and an odd owned length ends in a single-cell aggregate"""
+    from oracle.amg_oracle import AmgOracle
+    cells, part = (13, 10, 9), (2, 1, 3)
+
+    def make(box):
+        return problems.twop_lens(cells, law="bc", heterogeneity_sigma=0.3, box=box)
+
+    def job(ro):
+        u0 = ro.spec.initial.reshape(-1)
+        res, jac = ro.o.assemble(u0, u0)
+        amg = AmgOracle(ro.local.cells, 3, ro.b, ro.o.rowptr, ro.o.colidx, jac, layout=ro.layout, part3=ro.part3, gcells=ro.cells)
+        return [(lv.gcells, lv.ranges) for lv in amg.levels]
+
+    out = D.run_threads(make, cells, 6, job, part)
+    nlev = len(out[0])
+    assert nlev >= 3 and all(len(o) == nlev for o in out)
+    for l in range(nlev):
+        g = out[0][l][0]
+        owners = np.zeros(g[::-1], dtype=int)
+        for r in range(6):
+            gc, rng = out[r][l]
+            assert gc == g
+            for a in range(3):
+                lo, hi, b0, b1 = rng[a]
+                assert lo == max(0, b0 - 1) and hi == min(g[a], b1 + 1) and b1 > b0
+            owners[tuple(slice(rng[a][2], rng[a][3]) for a in (2, 1, 0))] += 1
+        assert np.all(owners == 1)
+    assert int(np.prod(out[0][-1][0])) <= 8 or out[0][-1][0] == part
 
 
 def test_four_processes_over_gloo_block_partition(block_runs):
