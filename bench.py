@@ -508,13 +508,16 @@ def measure(comm, cells, upper, part, steps, warmup, e2e=True, label="bench", so
     prof = {k: eng.profile_read(v) for k, v in (("assembly", B.K_ASSEMBLY), ("spmv", B.K_SPMV),
                                                 ("ilu0_apply", B.K_ILU_APPLY), ("ilu0_factor", B.K_ILU_FACTOR),
                                                 ("blas1", B.K_BLAS1), ("halo", B.K_HALO), ("amg_transfer", B.K_AMG))}
+    amg_levels = None
+    if solver.startswith("amg"):
+        amg_levels = [{"cells": list(c), "ms_per_cycle": ms, "cycles": n} for c, (ms, n) in zip(eng.amg_levels(), eng.amg_level_profile())]
     eng.profile(False)
     ms_total = comm.maxreduce(ms_total)
     ms_per_step = ms_total / steps
     res = {"cells": cells, "part": part_, "n_local": n_local, "nnzb": eng.nnzb, "b": b, "dofs_global": dofs_global, "its": its,
            "ms_per_step": ms_per_step, "value": dofs_global / (ms_per_step * 1e-3) / 1e6, "buckets": [x / steps for x in buckets],
            "wall_ms_per_step": wall * 1e3 / steps, "launches": int(launches), "clocks": clocks, "prof": prof, "ms_total": ms_total,
-           "vec_bytes": int(u0.numel() * 8)}
+           "vec_bytes": int(u0.numel() * 8), "amg_levels": amg_levels}
     if e2e:
         for _ in range(2):
             host_step()
@@ -618,6 +621,7 @@ def run_b200(args):
                         "ilu0_bicgstab_iterations_per_step": res["its"], "gpu_launches": ares["launches"],
                         "buckets_ms_per_step": {"assemble": ares["buckets"][0], "solve": ares["buckets"][1], "update": ares["buckets"][2]},
                         "kernels": {k: {kk: v[kk] for kk in ("avg_ms", "share_of_step", "launches_timed") if kk in v} for k, v in ak.items()},
+                        "levels_rank0": ares["amg_levels"],
                         "note": "block-decomposed runs: the GLOBAL hierarchy cut like the grid (aggregates do not cross processor "
                                 "boundaries), smoother BlockPreconditioner<SeqSSOR>; smoothing sweeps are booked under ilu0_apply "
                                 "(same sweep kernels), Galerkin/transfer kernels under amg_transfer"}
@@ -641,7 +645,7 @@ def run_b200(args):
                    "linear_solver": SOLVER_TEXT[solver],
                    "ms_per_step": sres["ms_per_step"], "bicgstab_iterations_per_step": sres["its"], "value": sres["value"], "unit": UNIT,
                    "ms_per_bicgstab_iteration": sres["buckets"][1] / max(1, sres["its"]),
-                   "local_cells_rank0": sres["n_local"],
+                   "local_cells_rank0": sres["n_local"], "amg_levels_rank0": sres["amg_levels"],
                    # (AMG: spmv / sweep launches of all levels are averaged together, so no per-launch roofline fraction there)
                    "kernels": {k: {kk: v[kk] for kk in (("avg_ms", "share_of_step", "frac") if solver == "ilu0" else ("avg_ms", "share_of_step", "launches_timed"))
                                    if kk in v} for k, v in sk.items()}}

@@ -23,7 +23,7 @@ EXPORTS = [
     "dmx_default_options", "dmx_default_newton_params", "dmx_create", "dmx_create_distributed", "dmx_get_nccl_unique_id",
     "dmx_destroy", "dmx_last_error", "dmx_version", "dmx_grid_structured", "dmx_grid_tensor", "dmx_local_box",
     "dmx_local_box3", "dmx_set_partitioning", "dmx_set_preconditioner_params", "dmx_precond_apply",
-    "dmx_default_amg_params", "dmx_set_amg_params", "dmx_amg_levels", "dmx_amg_level_cells", "dmx_amg_level_nnz_blocks", "dmx_amg_level_matrix",
+    "dmx_default_amg_params", "dmx_set_amg_params", "dmx_amg_level_profile", "dmx_amg_levels", "dmx_amg_level_cells", "dmx_amg_level_nnz_blocks", "dmx_amg_level_matrix",
     "dmx_num_cells", "dmx_num_eq", "dmx_nnz_blocks", "dmx_pattern", "dmx_bcrs_pattern", "dmx_set_options",
     "dmx_set_cell_fields", "dmx_set_source", "dmx_set_material", "dmx_set_fluids", "dmx_set_fluid_table",
     "dmx_side_faces", "dmx_set_boundary", "dmx_vec_upload", "dmx_vec_download", "dmx_vec_copy", "dmx_jacobian_upload",
@@ -170,6 +170,7 @@ def load_library():
     L.dmx_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
     L.dmx_profile.argtypes = [vp, C.c_int]
     L.dmx_profile_read.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
+    L.dmx_amg_level_profile.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
     _lib = L
     return L
 
@@ -427,6 +428,15 @@ class Engine:
         for k, v in kw.items():
             setattr(p, k, v)
         self._check(self.L.dmx_set_amg_params(self.h, C.byref(p)))
+
+    def amg_level_profile(self):
+        """[(ms per cycle, cycles)] per level, exclusive of the coarser levels (timed while profile(True))"""
+        out = []
+        for l in range(self.L.dmx_amg_levels(self.h)):
+            ms, n = C.c_double(0.0), C.c_longlong(0)
+            self._check(self.L.dmx_amg_level_profile(self.h, l, C.byref(ms), C.byref(n)))
+            out.append((ms.value / max(1, n.value), int(n.value)))
+        return out
 
     def amg_levels(self):
         out = []

@@ -50,6 +50,11 @@ __device__ __forceinline__ void children1(int I, int flo, int fhi, int clo, int&
 struct AmgState {
     std::vector<AmgLevel> levels;
     double* own[3] = {nullptr, nullptr, nullptr};      // r, u, t of level 0
+    // per-level device time of the cycle (exclusive of the coarser levels), recorded while dmx_profile is on
+    struct LevelRec { int level; cudaEvent_t e[4]; };
+    std::vector<LevelRec> pending;
+    std::vector<double> level_ms;
+    std::vector<long long> level_n;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -170,6 +175,7 @@ void amg_free(dmx_ctx* ctx)
     AmgState* st = amg_of(ctx);
     if (!st) return;
     for (size_t l = 1; l < st->levels.size(); ++l) destroy_child_ctx(st->levels[l].c);
+    for (auto& r : st->pending) for (cudaEvent_t e : r.e) if (e) cudaEventDestroy(e);
     for (double* p : st->own) if (p) cudaFree(p);
     delete st;
     ctx->amg = nullptr;
@@ -298,7 +304,20 @@ static int amg_smooth_step(dmx_ctx* ctx, AmgLevel& L, bool first, bool need_defe
     return 0;
 }
 
+static int amg_cycle_level(dmx_ctx* ctx, AmgState* st, int l, cudaEvent_t* ev);
 static int amg_cycle(dmx_ctx* ctx, AmgState* st, int l)
+{
+    if (!ctx->prof_on) return amg_cycle_level(ctx, st, l, nullptr);
+    AmgState::LevelRec rec;
+    rec.level = l;
+    for (cudaEvent_t& e : rec.e) { e = nullptr; cudaEventCreate(&e); }
+    cudaEventRecord(rec.e[0], ctx->stream);
+    const int rc = amg_cycle_level(ctx, st, l, rec.e);
+    cudaEventRecord(rec.e[3], ctx->stream);
+    st->pending.push_back(rec);
+    return rc;
+}
+static int amg_cycle_level(dmx_ctx* ctx, AmgState* st, int l, cudaEvent_t* ev)
 {
     AmgLevel& L = st->levels[l];
     dmx_ctx* c = L.c;
@@ -308,6 +327,7 @@ static int amg_cycle(dmx_ctx* ctx, AmgState* st, int l)
         const int ns = std::max(1, prm.coarsest_steps);
         for (int s = 0; s < ns; ++s)
             if (int rc = amg_smooth_step(ctx, L, s == 0, s + 1 < ns)) return rc;
+        if (ev) { cudaEventRecord(ev[1], ctx->stream); cudaEventRecord(ev[2], ctx->stream); }
         return 0;
     }
     AmgLevel& C = st->levels[l + 1];
@@ -322,7 +342,9 @@ static int amg_cycle(dmx_ctx* ctx, AmgState* st, int l)
         else amg_restrict_kernel<1><<<grid, 256, 0, ctx->stream>>>(c->nc[0], c->nc[1], c->nc[2], cc->nc[0], cc->nc[1], cc->nc[2], M, L.r, C.r);
         DMX_CHECK_LAUNCH();
     }
+    if (ev) cudaEventRecord(ev[1], ctx->stream);
     if (int rc = amg_cycle(ctx, st, l + 1)) return rc;
+    if (ev) cudaEventRecord(ev[2], ctx->stream);
     {
         ProfScope ps(ctx, DMX_K_AMG);
         const int grid = (c->n + 255) / 256;
@@ -344,6 +366,31 @@ static int amg_cycle(dmx_ctx* ctx, AmgState* st, int l)
     }
     for (int s = 0; s < prm.post_steps; ++s)
         if (int rc = amg_smooth_step(ctx, L, false, s + 1 < prm.post_steps)) return rc;
+    return 0;
+}
+
+// accumulated device milliseconds one level spent in the cycles timed so far (exclusive of the coarser levels) and the number of
+// cycles; call after a synchronisation.  Reset by dmx_profile(ctx, 1).
+int amg_level_profile(dmx_ctx* ctx, int level, double* ms, long long* n, bool reset)
+{
+    AmgState* st = amg_of(ctx);
+    if (!st) return 0;
+    st->level_ms.resize(st->levels.size(), 0.0);
+    st->level_n.resize(st->levels.size(), 0);
+    for (auto& r : st->pending) {
+        float a = 0.f, b = 0.f;
+        if (cudaEventElapsedTime(&a, r.e[0], r.e[1]) == cudaSuccess && cudaEventElapsedTime(&b, r.e[2], r.e[3]) == cudaSuccess &&
+            r.level < (int)st->level_ms.size()) {
+            st->level_ms[r.level] += a + b;
+            st->level_n[r.level]++;
+        }
+        for (cudaEvent_t e : r.e) cudaEventDestroy(e);
+    }
+    st->pending.clear();
+    if (reset) { std::fill(st->level_ms.begin(), st->level_ms.end(), 0.0); std::fill(st->level_n.begin(), st->level_n.end(), 0); return 0; }
+    if (level < 0 || level >= (int)st->levels.size()) return DMX_ERR_USAGE;
+    if (ms) *ms = st->level_ms[level];
+    if (n) *n = st->level_n[level];
     return 0;
 }
 

@@ -605,7 +605,17 @@ int dmx_profile(dmx_ctx* ctx, int enable)
     if (enable) {
         for (int k = 0; k < DMX_NUM_KCLASS; ++k) { ctx->prof_ms[k] = 0.0; ctx->prof_n[k] = 0; }
     }
+    amg_level_profile(ctx, 0, nullptr, nullptr, enable != 0);
     ctx->prof_on = enable != 0;
+    return 0;
+}
+int dmx_amg_level_profile(dmx_ctx* ctx, int level, double* ms_total, long long* cycles)
+{
+    DMX_CUDA(cudaSetDevice(ctx->device));
+    DMX_CUDA(cudaStreamSynchronize(ctx->stream));
+    *ms_total = 0.0;
+    *cycles = 0;
+    if (amg_level_profile(ctx, level, ms_total, cycles, false)) return fail(ctx, DMX_ERR_USAGE, "no such AMG level");
     return 0;
 }
 int dmx_profile_read(dmx_ctx* ctx, int kclass, double* ms_total, long long* units)

@@ -320,6 +320,7 @@ int amg_setup(dmx_ctx* ctx);
 int amg_apply(dmx_ctx* ctx, const double* d, double* v);
 int amg_num_levels(dmx_ctx* ctx);
 dmx_ctx* amg_level_ctx(dmx_ctx* ctx, int level);
+int amg_level_profile(dmx_ctx* ctx, int level, double* ms, long long* n, bool reset);
 // implemented in api.cu: level contexts of a hierarchy (own grid, matrix and vectors; the parent's device and stream)
 // `gcells`: global cells of the level; distributed parent: off / nc = local box (overlap included), own_lo / own_hi = owned range
 // in local indices (all per axis); single domain: pass nullptr for the four

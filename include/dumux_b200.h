@@ -266,6 +266,9 @@ enum { DMX_K_ASSEMBLY = 0, DMX_K_SPMV = 1, DMX_K_ILU_APPLY = 2, DMX_K_ILU_FACTOR
        DMX_K_HALO = 6, DMX_K_JACOBI = 7 };
 int  dmx_profile(dmx_ctx* ctx, int enable);
 int  dmx_profile_read(dmx_ctx* ctx, int kclass, double* ms_total, long long* units);
+/* device milliseconds one level of the AMG hierarchy spent in the V-cycles timed while dmx_profile was on (exclusive of the
+   coarser levels) and the number of cycles */
+int  dmx_amg_level_profile(dmx_ctx* ctx, int level, double* ms_total, long long* cycles);
 int  dmx_synchronize(dmx_ctx* ctx);
 /* device stopwatch on the ctx stream (CUDA events): start records, stop records + waits and returns the milliseconds */
 int  dmx_timer_start(dmx_ctx* ctx);
