@@ -172,6 +172,7 @@ struct dmx_ctx {
 
     // halo (distributed)
     double *d_send = nullptr, *d_recv = nullptr;
+    double* d_gather = nullptr;      // all-gathered partial sums of a scalar product [nranks][<= 8]
 
     cudaEvent_t ev[6] = {};
 

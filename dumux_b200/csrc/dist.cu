@@ -26,6 +26,7 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
@@ -48,12 +49,13 @@ bool load_nccl()
     g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(h, "ncclCommInitRank");
     g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(h, "ncclCommDestroy");
     g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(h, "ncclAllReduce");
+    g_nccl.AllGather = (decltype(g_nccl.AllGather))dlsym(h, "ncclAllGather");
     g_nccl.Send = (decltype(g_nccl.Send))dlsym(h, "ncclSend");
     g_nccl.Recv = (decltype(g_nccl.Recv))dlsym(h, "ncclRecv");
     g_nccl.GroupStart = (decltype(g_nccl.GroupStart))dlsym(h, "ncclGroupStart");
     g_nccl.GroupEnd = (decltype(g_nccl.GroupEnd))dlsym(h, "ncclGroupEnd");
     g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(h, "ncclGetErrorString");
-    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.Send || !g_nccl.Recv || !g_nccl.GroupStart ||
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.AllGather || !g_nccl.Send || !g_nccl.Recv || !g_nccl.GroupStart ||
         !g_nccl.GroupEnd)
         return false;
     g_nccl.handle = h;
@@ -158,10 +160,27 @@ int halo_exchange(dmx_ctx* ctx, double* v)
     return 0;
 }
 
+// Global sums of the scalar products (OverlappingSchwarzScalarProduct: MPI_Allreduce).  The order in which an all-reduce adds
+// the per-rank partial sums is the library's choice and changes the last bits of every dot product, which BiCGSTAB amplifies
+// into iteration counts that wander by several per cent.  So the partial sums are ALL-GATHERED (count <= 8 doubles per rank)
+// and every rank adds them in rank order: deterministic, identical on all ranks, and the order the CPU multi-rank oracle uses
+// (oracle/dist_oracle.py ThreadComm.allreduce) -- iteration counts can be compared with == for any number of ranks.
+__global__ void ordered_sum_kernel(int nranks, int count, const double* __restrict__ gathered, double* __restrict__ out)
+{
+    const int q = threadIdx.x;
+    if (q >= count) return;
+    double acc = gathered[q];
+    for (int r = 1; r < nranks; ++r) acc = acc + gathered[(size_t)r * count + q];
+    out[q] = acc;
+}
 int allreduce_sum(dmx_ctx* ctx, double* d_buf, int count)
 {
     if (ctx->nranks == 1) return 0;
-    DMX_NCCL(g_nccl.AllReduce(d_buf, d_buf, count, ncclFloat64, ncclSum, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+    if (count > 8) return fail(ctx, DMX_ERR_USAGE, "allreduce_sum: at most 8 scalars");
+    if (!ctx->d_gather) DMX_CUDA(cudaMalloc((void**)&ctx->d_gather, (size_t)ctx->nranks * 8 * sizeof(double)));
+    DMX_NCCL(g_nccl.AllGather(d_buf, ctx->d_gather, count, ncclFloat64, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+    ordered_sum_kernel<<<1, 32, 0, ctx->stream>>>(ctx->nranks, count, ctx->d_gather, d_buf);
+    DMX_CHECK_LAUNCH();
     return 0;
 }
 int allreduce_max(dmx_ctx* ctx, double* d_buf, int count)

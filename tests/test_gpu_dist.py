@@ -141,7 +141,8 @@ def test_decomposed_newton_step_matches_cpu_reference(world, part):
     from dumux_b200 import binding as B
     from dumux_b200 import problems
     from oracle import dist_oracle as D
-    # the oracle adds every scalar product in the device's reduction tree -> identical Krylov iterations for 2 ranks
+    # the oracle adds every scalar product in the device's reduction tree and the per-rank sums in rank order (as dist.cu does)
+    # -> identical Krylov iterations for any number of ranks
     ref = D.run_threads(_make_spec, CELLS, world, _cpu_rank_job, part, gpu_reduction=True)
     uid = B.Engine.nccl_unique_id()
     ctx = mp.get_context("spawn")
@@ -170,10 +171,10 @@ def test_decomposed_newton_step_matches_cpu_reference(world, part):
         # owner-masked, all-reduced norm is the same number on every rank
         assert g["norm"] == got[0]["norm"]
         # Schwarz-BiCGSTAB: same iteration count, solution at the solver tolerance
-        assert g["st"] == 0 and c["st"] == 0 and abs(g["its"] - c["its"]) <= (0 if world == 2 else 2), (g["its"], c["its"])
+        assert g["st"] == 0 and c["st"] == 0 and g["its"] == c["its"], (g["its"], c["its"])
         assert np.linalg.norm(g["x"] - c["x"]) <= 1e-7 * np.linalg.norm(c["x"])
         # Schwarz-GMRes(10) (ILURestartedGMResIstlSolver on the overlapping decomposition): same count, reduction and solution
-        assert g["stg"] == 0 and c["stg"] == 0 and abs(g["itsg"] - c["itsg"]) <= (0 if world == 2 else 2), (g["itsg"], c["itsg"])
+        assert g["stg"] == 0 and c["stg"] == 0 and g["itsg"] == c["itsg"], (g["itsg"], c["itsg"])
         if g["itsg"] == c["itsg"]:
             assert g["redg"] == pytest.approx(c["redg"], rel=1e-5)
         assert np.linalg.norm(g["xg"] - c["xg"]) <= 1e-7 * np.linalg.norm(c["xg"])
@@ -181,7 +182,7 @@ def test_decomposed_newton_step_matches_cpu_reference(world, part):
         # the other block preconditioners on the decomposition: same counts (2 ranks: identical iteration), same solution
         for name in ("ssor", "par_mt_ssor", "amg"):
             (xa, sta, ita, _), (xb, stb, itb, _) = g["other"][name], c["other"][name]
-            assert sta == 0 and stb == 0 and abs(ita - itb) <= (0 if world == 2 else 2), (name, ita, itb)
+            assert sta == 0 and stb == 0 and ita == itb, (name, ita, itb)
             assert np.linalg.norm(xa - xb) <= 1e-6 * np.linalg.norm(xb)
         # AMG on the decomposition = the GLOBAL hierarchy cut like the grid: same level boxes, bit-identical Galerkin matrices
         # and V-cycle on every rank, and a mesh- and partition-independent iteration count (far below Schwarz-ILU0's)
@@ -192,8 +193,7 @@ def test_decomposed_newton_step_matches_cpu_reference(world, part):
         assert g["other"]["amg"][2] * 3 < g["its"]
         # Newton: same iteration count, fields to 1e-8
         assert g["nst"] == 0 and g["nsteps"] == c["nsteps"]
-        if world == 2:
-            assert g["lin_its"] == c["lin_its"], (g["lin_its"], c["lin_its"])
+        assert g["lin_its"] == c["lin_its"], (g["lin_its"], c["lin_its"])
         ug, uc = g["u"].reshape(-1, 2), c["u"].reshape(-1, 2)
         assert np.linalg.norm(ug[:, 0] - uc[:, 0]) <= 1e-8 * np.linalg.norm(uc[:, 0])
         assert np.linalg.norm(ug[:, 1] - uc[:, 1]) <= 1e-8 * max(1.0, np.linalg.norm(uc[:, 1]))
