@@ -690,7 +690,31 @@ struct SkewState {
     long long* trace = nullptr;            // 2 kernels x 2 tiles x 64 chunks x 24 stamps (DMX_SK_TRACE=1)
     unsigned long long* ll = nullptr;      // flag-in-data halo words [tile][step][dir 2][edge 16][2*b]
     unsigned int ll_seq = 0;               // tag counter of the flag-in-data sweeps
+    bool diag_only = false;                // block-diagonal Jacobian: the factorisation is Dinv alone, no streams were built
 };
+
+// ILU(0) application for a block-diagonal Jacobian (explicit tracer step): every L and U block is exactly zero, so the lower
+// sweep returns its right-hand side and the upper sweep v_i = Dinv_i * y_i (sum from 0) -- the same bits as the sweeps,
+// without streaming two sets of zero factors
+template <int B>
+__global__ void __launch_bounds__(256) dinv_apply_kernel(size_t n, const double* __restrict__ Dinv, const double* __restrict__ d,
+                                                         double* __restrict__ v)
+{
+    const size_t I = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (I >= n) return;
+    double r[B], o[B];
+#pragma unroll
+    for (int e = 0; e < B; ++e) r[e] = d[I * B + e];
+#pragma unroll
+    for (int rr = 0; rr < B; ++rr) {
+        double acc = 0.0;
+#pragma unroll
+        for (int cc = 0; cc < B; ++cc) acc += Dinv[I * B * B + rr * B + cc] * r[cc];
+        o[rr] = acc;
+    }
+#pragma unroll
+    for (int e = 0; e < B; ++e) v[I * B + e] = o[e];
+}
 
 template <int B, bool UPPER>
 static int sweep_launch_ll(dmx_ctx* ctx, SkewState* st, const double* stream, double* out, unsigned int tag, const int* order,
@@ -788,11 +812,14 @@ static int sk_factor_t(dmx_ctx* ctx, SkewState* st)
         // Dinv_i = A_ii^-1: exact ILU(0) of a block-diagonal matrix, or SeqSSOR in factorised form (L~ = L D^-1, U = D + U)
         ilu_diag_only_kernel<B><<<(unsigned)((ctx->n + 255) / 256), 256, 0, ctx->stream>>>(ctx->n, ctx->d_diag, ctx->d_J, st->Dinv, ctx->d_flag);
         DMX_CHECK_LAUNCH();
+        st->diag_only = ctx->jac_diagonal && !ctx->ssor_factorised;
+        if (st->diag_only) return 0;              // applied by dinv_apply_kernel, no streams needed
         const unsigned grid = (unsigned)((size_t)g.ntiles * g.NS);
         ilu_skew_kernel<B><<<grid, SK_THREADS, 0, ctx->stream>>>(g, ctx->d_diag, ctx->d_J, st->Dinv, st->Lsk, st->Usk);
         DMX_CHECK_LAUNCH();
         return 0;
     }
+    st->diag_only = false;
     DMX_CUDA(cudaMemsetAsync(ctx->d_barrier, 0, sizeof(unsigned int), ctx->stream));
     SkewGrid gg = g;
     const int* diag = ctx->d_diag;
@@ -830,6 +857,11 @@ template <int B>
 static int sk_apply_t(dmx_ctx* ctx, SkewState* st, const double* d, double* v)
 {
     const SkewGrid& g = st->g;
+    if (st->diag_only) {
+        dinv_apply_kernel<B><<<(unsigned)((ctx->n + 255) / 256), 256, 0, ctx->stream>>>((size_t)ctx->n, st->Dinv, d, v);
+        DMX_CHECK_LAUNCH();
+        return 0;
+    }
     unsigned long long* tick_lo = st->ctl;
     unsigned long long* tick_up = st->ctl + 1;
     // The device ticket counters advance by ntiles per sweep; the host mirrors (seq_lo / seq_up) advance only once the sweep

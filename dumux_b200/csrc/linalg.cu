@@ -87,9 +87,36 @@ __global__ void __launch_bounds__(128) stencil_spmv_kernel(int nx, int ny, int n
     y[(size_t)row * B + e] = acc;
 }
 
+// BCRSMatrix::mv for a Jacobian whose off-diagonal blocks are all exactly zero (explicit tracer step): only the diagonal
+// block contributes to the row sum (the skipped terms are 0 * x_j = 0), so six of the seven blocks per row are not read
+template <int B>
+__global__ void __launch_bounds__(256) diag_spmv_kernel(size_t len, const int* __restrict__ diag, const double* __restrict__ A,
+                                                        const double* __restrict__ x, double* __restrict__ y,
+                                                        const unsigned char* __restrict__ owner)
+{
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= len) return;
+    const size_t row = t / B;
+    const int e = (int)(t % B);
+    const size_t kpos = (size_t)diag[row];
+    double acc = 0.0;
+#pragma unroll
+    for (int c = 0; c < B; ++c) acc += A[kpos * B * B + e * B + c] * x[row * B + c];
+    if (owner && !owner[row]) acc = 0.0;
+    y[t] = acc;
+}
+
 static int launch_spmv_owner(dmx_ctx* ctx, const double* x, double* y, const unsigned char* owner)
 {
     ProfScope ps(ctx, DMX_K_SPMV);
+    if (ctx->jac_diagonal && ctx->d_diag) {
+        const size_t len = (size_t)ctx->n * ctx->b;
+        const unsigned grid = (unsigned)((len + 255) / 256);
+        if (ctx->b == 2) diag_spmv_kernel<2><<<grid, 256, 0, ctx->stream>>>(len, ctx->d_diag, ctx->d_J, x, y, owner);
+        else diag_spmv_kernel<1><<<grid, 256, 0, ctx->stream>>>(len, ctx->d_diag, ctx->d_J, x, y, owner);
+        DMX_CHECK_LAUNCH();
+        return 0;
+    }
     if (ctx->has_grid && ctx->nc[1] <= 65535 && ctx->nc[2] <= 65535) {
         const int bs = 128;
         const dim3 grid((unsigned)((ctx->nc[0] * ctx->b + bs - 1) / bs), (unsigned)ctx->nc[1], (unsigned)ctx->nc[2]);

@@ -473,15 +473,17 @@ def onep_tracer_pressure(cells=(50, 50)) -> ProblemSpec:
 # component, D = 0, porosity 0.2, fluid density 1000; all boundaries Neumann: outflow volumeFlux*X*rho/area at the top,
 # zero elsewhere; initial X = 1e-9 * M_tracer / M_fluid (0.300 / 18.0) below y = 0.1.
 # ------------------------------------------------------------------------------------------------------
-def tracer_transport(cells, volume_flux, dt=10.0, implicit=False) -> ProblemSpec:
+def tracer_transport(cells, volume_flux, dt=10.0, implicit=False, box=None) -> ProblemSpec:
+    """`box` = per-axis (lo, hi): build only that block (ProblemSpec.box); `volume_flux` then covers the block too"""
     dim = len(cells)
     lower, upper = tuple([0.0] * dim), tuple([1.0] * dim)
-    n = int(np.prod(cells))
-    ctr = cell_centers(cells, lower, upper)
+    bx = _as_box(cells, None, box)
+    n = int(np.prod(cells)) if bx is None else int(np.prod([hi - lo for lo, hi in bx]))
+    ctr = cell_centers(cells, lower, upper, box=bx)
     zmax = upper[dim - 1]
     bc_type, bc_values = {}, {}
     for side in range(2 * dim):
-        fc = side_face_centers(cells, lower, upper, side)
+        fc = side_face_centers(cells, lower, upper, side, box=bx)
         top = fc[:, dim - 1] > zmax - 1e-6
         bc_type[side] = np.where(top, BC_OUTFLOW, BC_NEUMANN).astype(np.int32)
         bc_values[side] = np.zeros((fc.shape[0], 1))
@@ -492,7 +494,37 @@ def tracer_transport(cells, volume_flux, dt=10.0, implicit=False) -> ProblemSpec
         name="tracer", model=MODEL_TRACER, dim=dim, cells=tuple(cells), lower=lower, upper=upper,
         K=np.ones(n), phi=np.full(n, 0.2), region=np.zeros(n, dtype=np.int32), materials=[],
         rho=(1000.0,), mu=(1e-3,), bc_type=bc_type, bc_values=bc_values,
-        options=Options(stationary=False, dt=dt, enable_gravity=False), initial=init, volume_flux=vf, implicit=implicit)
+        options=Options(stationary=False, dt=dt, enable_gravity=False), initial=init, volume_flux=vf, implicit=implicit,
+        box=None if box is None else tuple(tuple(b) for b in box))
+
+
+def onep_tracer_pressure_large(cells, box=None, sigma=0.5, seed=0) -> ProblemSpec:
+    """The stationary 1p problem of examples/1ptracer at benchmark size (BASELINE config 5): same boundary conditions and lens as
+    onep_tracer_pressure, K = {1e-10, lens 1e-11} x exp(N(0, sigma)) drawn per layer (plane_lognormal_multiplier: the field
+    does not depend on the decomposition; the mt19937 replay of the 50 x 50 example is a Python loop).  `box`: one block."""
+    dim = len(cells)
+    lower, upper = tuple([0.0] * dim), tuple([1.0] * dim)
+    bx = _as_box(cells, None, box)
+    n = int(np.prod(cells)) if bx is None else int(np.prod([hi - lo for lo, hi in bx]))
+    ctr = cell_centers(cells, lower, upper, box=bx)
+    lens = _in_box(ctr, [0.2] * dim, [0.8] * dim, 1.5e-7)
+    K = np.where(lens, 1e-11, 1e-10) * plane_lognormal_multiplier(cells, sigma, seed, box=bx)
+    ymax = upper[dim - 1]
+    bc_type, bc_values = {}, {}
+    for side in range(2 * dim):
+        fc = side_face_centers(cells, lower, upper, side, box=bx)
+        y = fc[:, dim - 1]
+        dirichlet = (y < 1e-6) | (y > ymax - 1e-6)
+        bc_type[side] = np.where(dirichlet, BC_DIRICHLET, BC_NEUMANN).astype(np.int32)
+        vals = np.zeros((fc.shape[0], 1))
+        vals[dirichlet, 0] = 1.0e5 * (1.1 - y[dirichlet] * 0.1)
+        bc_values[side] = vals
+    return ProblemSpec(
+        name="1ptracer_pressure_large", model=MODEL_1P, dim=dim, cells=tuple(cells), lower=lower, upper=upper,
+        K=K, phi=np.full(n, 0.2), region=np.zeros(n, dtype=np.int32), materials=[],
+        rho=(1000.0,), mu=(1e-3,), bc_type=bc_type, bc_values=bc_values,
+        options=Options(stationary=True, base_eps=0.1, privar_magnitude=(1e5, -1.0)), initial=np.zeros((n, 1)),
+        box=None if box is None else tuple(tuple(b) for b in box))
 
 
 # ------------------------------------------------------------------------------------------------------
