@@ -15,9 +15,11 @@ for s in $STEPS; do
     list)  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv \
              python scripts/profile_step.py 256 6 > $OUT/list.log 2>&1; tail -2 $OUT/list.log;;
     listbench) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_bench.csv \
-             python bench.py --steps 2 --warmup 1 > $OUT/listbench.log 2>&1; tail -2 $OUT/listbench.log;;
+             python bench.py --steps 2 --warmup 1 --no-strong --no-amg --no-cpu-baseline --no-parity-check > $OUT/listbench.log 2>&1; tail -2 $OUT/listbench.log;;
     full)  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"assemble_tile|ilu_sweep|ilu_diag|ilu_skew|stencil_spmv|vec_skew|axpy3|axpy_r|p_update|dot_kernel" \
              -c 16 -f -o $OUT/prof python scripts/profile_step.py 256 2 > $OUT/full.log 2>&1; tail -2 $OUT/full.log;;
+    fullamg) timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"amg_|stencil_spmv|ilu_sweep|vec_skew" \
+             -c 60 -f -o $OUT/prof_amg python scripts/profile_step.py 256 1 amg > $OUT/fullamg.log 2>&1; tail -2 $OUT/fullamg.log;;
     trace) timeout 300 python scripts/sweep_trace.py 256 > $OUT/trace.log 2>&1; tail -30 $OUT/trace.log;;
     bench) timeout 900 python bench.py --steps 3 --warmup 3 > $OUT/bench.json 2> $OUT/bench.err; tail -c 3000 $OUT/bench.json;;
     stream) nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/stream_probe scripts/probes/stream_probe.cu && timeout 600 /tmp/stream_probe > $OUT/stream.log 2>&1; tail -80 $OUT/stream.log;;
