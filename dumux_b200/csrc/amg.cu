@@ -50,6 +50,7 @@ __device__ __forceinline__ void children1(int I, int flo, int fhi, int clo, int&
 struct AmgState {
     std::vector<AmgLevel> levels;
     double* own[3] = {nullptr, nullptr, nullptr};      // r, u, t of level 0
+    const double* rhs = nullptr;                       // right-hand side of the cycle being applied (level 0)
     // per-level device time of the cycle (exclusive of the coarser levels), recorded while dmx_profile is on
     struct LevelRec { int level; cudaEvent_t e[4]; };
     std::vector<LevelRec> pending;
@@ -288,13 +289,19 @@ int amg_setup(dmx_ctx* ctx)
     return 0;
 }
 
-static int amg_smooth_step(dmx_ctx* ctx, AmgLevel& L, bool first, bool need_defect)
+// `rin`: where the defect of this step is read from (L.r, or the caller's right-hand side in the first step of level 0, which
+// saves copying it); the updated defect always goes to L.r
+static int amg_smooth_step(dmx_ctx* ctx, AmgLevel& L, bool first, bool need_defect, const double* rin = nullptr)
 {
     dmx_ctx* c = L.c;
     const size_t len = (size_t)c->n * c->b;
-    if (int rc = ilu0_apply(c, L.r, L.u)) return rc;                          // update = M^-1 defect (from update = 0)
+    if (!rin) rin = L.r;
+    if (int rc = ilu0_apply(c, rin, L.u)) return rc;                          // update = M^-1 defect (from update = 0)
     if (c->nranks > 1)
         if (int rc = halo_exchange(c, L.u)) return rc;                        // BlockPreconditioner::apply: copyOwnerToAll
+    if (need_defect && spmv_update_supported(c))
+        return launch_spmv_update(c, L.u, rin, L.r, L.x, true, first);        // lhs += update; defect -= A update, one pass
+    if (rin != L.r) DMX_CUDA(cudaMemcpyAsync(L.r, rin, len * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
     if (need_defect)
         if (int rc = launch_spmv(c, L.u, L.t)) return rc;                     // A update (block-decomposed: projected)
     ProfScope ps(ctx, DMX_K_AMG);
@@ -322,18 +329,22 @@ static int amg_cycle_level(dmx_ctx* ctx, AmgState* st, int l, cudaEvent_t* ev)
     AmgLevel& L = st->levels[l];
     dmx_ctx* c = L.c;
     const auto& prm = ctx->amg_prm;
+    // level 0: the first smoothing step reads the caller's right-hand side in place
+    const double* rhs0 = (l == 0) ? st->rhs : nullptr;
     if (l + 1 == (int)st->levels.size()) {
         // coarsest level: coarsest_steps smoothing steps instead of dune's direct solve
         const int ns = std::max(1, prm.coarsest_steps);
         for (int s = 0; s < ns; ++s)
-            if (int rc = amg_smooth_step(ctx, L, s == 0, s + 1 < ns)) return rc;
+            if (int rc = amg_smooth_step(ctx, L, s == 0, s + 1 < ns, s == 0 ? rhs0 : nullptr)) return rc;
         if (ev) { cudaEventRecord(ev[1], ctx->stream); cudaEventRecord(ev[2], ctx->stream); }
         return 0;
     }
     AmgLevel& C = st->levels[l + 1];
     dmx_ctx* cc = C.c;
     for (int s = 0; s < prm.pre_steps; ++s)
-        if (int rc = amg_smooth_step(ctx, L, s == 0, true)) return rc;
+        if (int rc = amg_smooth_step(ctx, L, s == 0, true, s == 0 ? rhs0 : nullptr)) return rc;
+    if (rhs0 && prm.pre_steps == 0)
+        DMX_CUDA(cudaMemcpyAsync(L.r, rhs0, (size_t)c->n * c->b * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
     {
         ProfScope ps(ctx, DMX_K_AMG);
         const int grid = (cc->n + 255) / 256;
@@ -357,12 +368,16 @@ static int amg_cycle_level(dmx_ctx* ctx, AmgState* st, int l, cudaEvent_t* ev)
         DMX_CHECK_LAUNCH();
     }
     if (prm.post_steps > 0) {
-        if (int rc = launch_spmv(c, L.u, L.t)) return rc;
-        ProfScope ps(ctx, DMX_K_AMG);
-        const size_t len = (size_t)c->n * c->b;
-        const int grid = (int)std::min<size_t>((len + 255) / 256, 148 * 8);
-        amg_update_kernel<<<grid, 256, 0, ctx->stream>>>(len, L.u, L.t, L.x, L.r, 0, 0, 1);
-        DMX_CHECK_LAUNCH();
+        if (spmv_update_supported(c)) {
+            if (int rc = launch_spmv_update(c, L.u, L.r, L.r, L.x, false, false)) return rc;      // defect -= A (coarse-grid correction)
+        } else {
+            if (int rc = launch_spmv(c, L.u, L.t)) return rc;
+            ProfScope ps(ctx, DMX_K_AMG);
+            const size_t len = (size_t)c->n * c->b;
+            const int grid = (int)std::min<size_t>((len + 255) / 256, 148 * 8);
+            amg_update_kernel<<<grid, 256, 0, ctx->stream>>>(len, L.u, L.t, L.x, L.r, 0, 0, 1);
+            DMX_CHECK_LAUNCH();
+        }
     }
     for (int s = 0; s < prm.post_steps; ++s)
         if (int rc = amg_smooth_step(ctx, L, false, s + 1 < prm.post_steps)) return rc;
@@ -401,7 +416,8 @@ int amg_apply(dmx_ctx* ctx, const double* d, double* v)
     if (!st) return fail(ctx, DMX_ERR_USAGE, "AMG apply before set-up");
     AmgLevel& L0 = st->levels[0];
     const size_t len = (size_t)ctx->n * ctx->b;
-    DMX_CUDA(cudaMemcpyAsync(L0.r, d, len * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    (void)len;
+    st->rhs = d;
     L0.x = v;
     return amg_cycle(ctx, st, 0);
 }

@@ -151,6 +151,7 @@ struct dmx_ctx {
     double* d_gm = nullptr;           // GMRes basis: restart+1 vectors, w, defect
     int gm_vectors = 0;
     void* skew = nullptr;             // SkewState of ilu_structured.cu (structured-grid ILU sweeps), null: generic kernels
+    int sk_tile = 16;                 // tile edge of the sweep kernels serving this context (16 or 8, see ilu_structured.cu)
     bool ssor_factorised = false;     // the "ILU" machinery holds SeqSSOR in factorised form: Dinv_i = A_ii^-1 instead of the ILU(0) recurrence
     void* amg = nullptr;              // AmgState of amg.cu
     dmx_amg_params amg_prm;
@@ -294,6 +295,8 @@ int build_diag(dmx_ctx* ctx);
 int build_level_schedule(dmx_ctx* ctx);
 int launch_spmv(dmx_ctx* ctx, const double* x, double* y);
 int launch_spmv_local(dmx_ctx* ctx, const double* x, double* y);     // without the owner projection
+bool spmv_update_supported(const dmx_ctx* ctx);
+int launch_spmv_update(dmx_ctx* ctx, const double* u, const double* r_in, double* r_out, double* x, bool with_x, bool first);
 int ilu0_factor(dmx_ctx* ctx);
 int ilu0_factor_bcrs(dmx_ctx* ctx);
 int ilu0_apply(dmx_ctx* ctx, const double* d, double* v);

@@ -30,11 +30,24 @@
 
 #include "common.cuh"
 
-namespace dmx {
-
+// This file is compiled TWICE into the library (csrc/Makefile): with 16 x 16 tiles (namespace sk16) and with 8 x 8 tiles
+// (-DSK_TILE=8, namespace sk8; 64 compute threads, four CTAs per SM).  The dmx::sk_* entry points at the end of the 16 x 16
+// build pick the variant per context.  Measured on B200 (AMG hierarchy of 256^3, 2x2 blocks, ms per V-cycle and level with
+// 16 x 16 / 8 x 8 tiles): 128^3 2.57 / 2.61, 64^3 1.14 / 1.11, 32^3 0.56 / 0.54, 8^3 0.24 / 0.21, 4^3 0.21 / 0.18; 1x1 blocks at
+// 256^3: 0.88 / 1.20 ms per application.  Small boxes are bound by steps x step latency (mbarrier hand-offs, the step barrier, the
+// L2 round trip of the tile-to-tile words), which the smaller tile shortens only marginally -- so 8 x 8 serves boxes up to 64.
 #ifndef SK_TILE
 #define SK_TILE 16       // edge of the square (i,j) tile of a CTA (power of two, <= 16)
 #endif
+#if SK_TILE == 16
+#define SK_VNS sk16
+#else
+#define SK_VNS sk8
+#endif
+
+namespace dmx {
+namespace SK_VNS {
+
 constexpr int SK_TI = SK_TILE, SK_TJ = SK_TILE, SK_THREADS = SK_TI * SK_TJ;
 #ifndef SK_CTAS_PER_SM
 #define SK_CTAS_PER_SM ((SK_TILE == 16) ? 1 : 4)
@@ -905,5 +918,40 @@ int sk_trace_read(dmx_ctx* ctx, long long* out)
     DMX_CUDA(cudaMemcpy(out, st->trace, 2 * 2 * 64 * 24 * sizeof(long long), cudaMemcpyDeviceToHost));
     return 0;
 }
+
+} // namespace SK_VNS
+
+#if SK_TILE == 16
+namespace sk8 {
+void sk_free(dmx_ctx* ctx);
+int sk_setup(dmx_ctx* ctx);
+int sk_factor(dmx_ctx* ctx);
+int sk_export_bcrs(dmx_ctx* ctx, double* out);
+int sk_apply(dmx_ctx* ctx, const double* d, double* v);
+int sk_trace_read(dmx_ctx* ctx, long long* out);
+}
+// Tile edge of a context: 8 x 8 tiles for in-plane boxes up to DMX_SK8_MAX_EDGE (default 64) cells per axis, 16 x 16 otherwise.
+// Same arithmetic, same bits.
+static int sk_choose_tile(const dmx_ctx* ctx)
+{
+    static int max_edge = -1;
+    if (max_edge < 0) {
+        const char* env = getenv("DMX_SK8_MAX_EDGE");
+        max_edge = env ? atoi(env) : 64;
+    }
+    return std::max(ctx->nc[0], ctx->nc[1]) <= max_edge ? 8 : 16;
+}
+void sk_free(dmx_ctx* ctx) { if (ctx->sk_tile == 8) sk8::sk_free(ctx); else sk16::sk_free(ctx); }
+int sk_setup(dmx_ctx* ctx)
+{
+    sk_free(ctx);
+    ctx->sk_tile = sk_choose_tile(ctx);
+    return ctx->sk_tile == 8 ? sk8::sk_setup(ctx) : sk16::sk_setup(ctx);
+}
+int sk_factor(dmx_ctx* ctx) { return ctx->sk_tile == 8 ? sk8::sk_factor(ctx) : sk16::sk_factor(ctx); }
+int sk_export_bcrs(dmx_ctx* ctx, double* out) { return ctx->sk_tile == 8 ? sk8::sk_export_bcrs(ctx, out) : sk16::sk_export_bcrs(ctx, out); }
+int sk_apply(dmx_ctx* ctx, const double* d, double* v) { return ctx->sk_tile == 8 ? sk8::sk_apply(ctx, d, v) : sk16::sk_apply(ctx, d, v); }
+int sk_trace_read(dmx_ctx* ctx, long long* out) { return ctx->sk_tile == 8 ? sk8::sk_trace_read(ctx, out) : sk16::sk_trace_read(ctx, out); }
+#endif
 
 } // namespace dmx

@@ -87,6 +87,51 @@ __global__ void __launch_bounds__(128) stencil_spmv_kernel(int nx, int ny, int n
     y[(size_t)row * B + e] = acc;
 }
 
+// The defect update of a multigrid smoothing step fused into the operator application: t = A u (row sum in column order from 0,
+// projected to the owner rows in a block-decomposed context), r_out = r_in - t, and lhs += u (lhs = u if `first`) -- what
+// "lhs += update; defect -= A update" of dune-istl's AMG does [DUNE-ext paamg/amg.hh], without writing and re-reading A u.
+// Every output entry is produced by the thread that computed the row sum; u is only read.  Same operations, same bits.
+template <int B>
+__global__ void __launch_bounds__(128) stencil_spmv_update_kernel(int nx, int ny, int nz, int dim, const int* __restrict__ rowptr,
+                                                                  const double* __restrict__ A, const double* __restrict__ u,
+                                                                  const double* r_in, double* r_out, double* x, int with_x, int first,
+                                                                  const unsigned char* __restrict__ owner)
+{
+    const int tx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = tx / B, e = tx % B;
+    const int j = blockIdx.y, k = blockIdx.z;
+    if (i >= nx) return;
+    const int row = i + nx * (j + ny * k);
+    const int sx = 1, sy = nx, sz = nx * ny;
+    int kpos = rowptr[row];
+    double acc = 0.0;
+    auto term = [&](int c) {
+        if (B == 2) {
+            const double2 a = *reinterpret_cast<const double2*>(A + ((size_t)kpos * 4 + e * 2));
+            const double2 xv = *reinterpret_cast<const double2*>(u + (size_t)c * 2);
+            acc += a.x * xv.x;
+            acc += a.y * xv.y;
+        } else {
+            acc += A[kpos] * u[c];
+        }
+        ++kpos;
+    };
+    if (dim > 2 && k > 0) term(row - sz);
+    if (dim > 1 && j > 0) term(row - sy);
+    if (i > 0) term(row - sx);
+    term(row);
+    if (i + 1 < nx) term(row + sx);
+    if (dim > 1 && j + 1 < ny) term(row + sy);
+    if (dim > 2 && k + 1 < nz) term(row + sz);
+    if (owner && !owner[row]) acc = 0.0;
+    const size_t o = (size_t)row * B + e;
+    r_out[o] = r_in[o] - acc;
+    if (with_x) {
+        const double uv = u[o];
+        x[o] = first ? uv : x[o] + uv;
+    }
+}
+
 // BCRSMatrix::mv for a Jacobian whose off-diagonal blocks are all exactly zero (explicit tracer step): only the diagonal
 // block contributes to the row sum (the skipped terms are 0 * x_j = 0), so six of the seven blocks per row are not read
 template <int B>
@@ -134,6 +179,22 @@ static int launch_spmv_owner(dmx_ctx* ctx, const double* x, double* y, const uns
         bcrs_spmv_kernel<2><<<grid, bs, 0, ctx->stream>>>(ctx->n, ctx->d_rowptr, ctx->d_colidx, ctx->d_J, x, y, owner);
     else
         bcrs_spmv_kernel<1><<<grid, bs, 0, ctx->stream>>>(ctx->n, ctx->d_rowptr, ctx->d_colidx, ctx->d_J, x, y, owner);
+    DMX_CHECK_LAUNCH();
+    return 0;
+}
+// r_out = r_in - A u (projected), optionally lhs (+)= u, in one pass; false: this context has no structured SpMV (caller falls back)
+bool spmv_update_supported(const dmx_ctx* ctx) { return ctx->has_grid && ctx->nc[1] <= 65535 && ctx->nc[2] <= 65535 && !ctx->jac_diagonal; }
+int launch_spmv_update(dmx_ctx* ctx, const double* u, const double* r_in, double* r_out, double* x, bool with_x, bool first)
+{
+    ProfScope ps(ctx, DMX_K_SPMV);
+    const int bs = 128;
+    const dim3 grid((unsigned)((ctx->nc[0] * ctx->b + bs - 1) / bs), (unsigned)ctx->nc[1], (unsigned)ctx->nc[2]);
+    if (ctx->b == 2)
+        stencil_spmv_update_kernel<2><<<grid, bs, 0, ctx->stream>>>(ctx->nc[0], ctx->nc[1], ctx->nc[2], ctx->dim, ctx->d_rowptr, ctx->d_J, u, r_in, r_out, x,
+                                                                    with_x ? 1 : 0, first ? 1 : 0, ctx->d_owner);
+    else
+        stencil_spmv_update_kernel<1><<<grid, bs, 0, ctx->stream>>>(ctx->nc[0], ctx->nc[1], ctx->nc[2], ctx->dim, ctx->d_rowptr, ctx->d_J, u, r_in, r_out, x,
+                                                                    with_x ? 1 : 0, first ? 1 : 0, ctx->d_owner);
     DMX_CHECK_LAUNCH();
     return 0;
 }
