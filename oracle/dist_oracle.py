@@ -245,6 +245,14 @@ class BoxRank:
         self.layout = RankLayout(comm, part3, list(self.ranges) + [(0, 1, 0, 1)] * (3 - dim), self.b)
         self.part3 = part3
         self.shape, self.own_rng, self.owner, self.neighbours = self.layout.shape, self.layout.own_rng, self.layout.owner, self.layout.neighbours
+        # index lists of the owner / non-owner entries and gather buffers: the same compact arrays a boolean mask would produce,
+        # without rebuilding them (and holding the interpreter lock) in every scalar product of the Krylov loops
+        if comm.nranks > 1:
+            self._oidx = np.flatnonzero(self.owner)
+            self._nidx = np.flatnonzero(~self.owner)
+            self._ga, self._gb = np.empty(self._oidx.size), np.empty(self._oidx.size)
+        else:
+            self._oidx = self._nidx = None
 
     def copy_owner_to_all(self, v):
         self.layout.copy_owner_to_all(v)
@@ -264,12 +272,22 @@ class BoxRank:
     def dot(self, a, b):
         if self.gpu_reduction:
             return self.comm.allreduce(gpu_sum(np.where(self.owner, a * b, 0.0)), "sum")
-        return self.comm.allreduce(float(np.dot(a[self.owner], b[self.owner])), "sum")
+        if self._oidx is None:
+            return self.comm.allreduce(float(np.dot(a, b)), "sum")
+        a.take(self._oidx, out=self._ga)
+        if b is a:
+            return self.comm.allreduce(float(np.dot(self._ga, self._ga)), "sum")
+        b.take(self._oidx, out=self._gb)
+        return self.comm.allreduce(float(np.dot(self._ga, self._gb)), "sum")
+
+    def project(self, y):
+        """OverlappingSchwarzOperator: zero the non-owner entries"""
+        if self._nidx is not None:
+            y[self._nidx] = 0.0
+        return y
 
     def apply_operator(self, jac, x):
-        y = O.spmv(self.n, self.b, self.o.rowptr, self.o.colidx, jac, x)
-        y[~self.owner] = 0.0                                         # project()
-        return y
+        return self.project(O.spmv(self.n, self.b, self.o.rowptr, self.o.colidx, jac, x))
 
     def local_preconditioner(self, jac, precond="ilu0", iterations=1, relaxation=1.0):
         """The sequential preconditioner of this rank's (interior + overlap) matrix: d -> M^-1 d, or None if the set-up fails
@@ -307,7 +325,7 @@ class BoxRank:
         x = np.zeros_like(rhs)
         self.copy_owner_to_all(x)                                    # BlockPreconditioner::pre
         r = rhs - O.spmv(self.n, self.b, self.o.rowptr, self.o.colidx, jac, x)
-        r[~self.owner] = 0.0                                         # applyscaleadd(-1, x, r) projects r
+        self.project(r)                                              # applyscaleadd(-1, x, r) projects r
         rt = r.copy()
         norm0 = math.sqrt(self.dot(r, r))
         norm = norm0
@@ -318,6 +336,7 @@ class BoxRank:
             return x, 0, 0, (1.0 if norm0 > 0 else 0.0)
         p = np.zeros_like(rhs)
         v = np.zeros_like(rhs)
+        tmp = np.empty_like(rhs)                                     # the updates below are the same operations in place
         rho = alpha = omega = 1.0
         it = 0.5
         status = 1
@@ -330,7 +349,10 @@ class BoxRank:
                 p = r.copy()
             else:
                 beta = (rho_new / rho) * (alpha / omega)
-                p = (p + (-omega) * v) * beta + r
+                np.multiply(v, -omega, out=tmp)                      # p = (p + (-omega) v) beta + r
+                np.add(p, tmp, out=p)
+                np.multiply(p, beta, out=p)
+                np.add(p, r, out=p)
             y = prec(p)
             v = self.apply_operator(jac, y)
             h = self.dot(rt, v)
@@ -338,8 +360,10 @@ class BoxRank:
                 status = 2
                 break
             alpha = rho_new / h
-            x += alpha * y
-            r += (-alpha) * v
+            np.multiply(y, alpha, out=tmp)
+            np.add(x, tmp, out=x)                                    # x += alpha y
+            np.multiply(v, -alpha, out=tmp)
+            np.add(r, tmp, out=r)                                    # r += (-alpha) v
             norm = math.sqrt(self.dot(r, r))
             if not math.isfinite(norm):
                 status = 3
@@ -351,8 +375,10 @@ class BoxRank:
             y = prec(r)
             t = self.apply_operator(jac, y)
             omega = self.dot(t, r) / self.dot(t, t)
-            x += omega * y
-            r += (-omega) * t
+            np.multiply(y, omega, out=tmp)
+            np.add(x, tmp, out=x)                                    # x += omega y
+            np.multiply(t, -omega, out=tmp)
+            np.add(r, tmp, out=r)                                    # r += (-omega) t
             rho = rho_new
             norm = math.sqrt(self.dot(r, r))
             if not math.isfinite(norm):
@@ -379,7 +405,7 @@ class BoxRank:
         x = np.zeros_like(rhs)
         self.copy_owner_to_all(x)
         b = rhs - O.spmv(self.n, self.b, self.o.rowptr, self.o.colidx, jac, x)
-        b[~self.owner] = 0.0
+        self.project(b)
         def0 = math.sqrt(self.dot(b, b))
         if not math.isfinite(def0):
             return x, 3, 0, 1.0
@@ -445,7 +471,7 @@ class BoxRank:
 
         def defect():
             b = rhs - O.spmv(self.n, self.b, self.o.rowptr, self.o.colidx, jac, x)
-            b[~self.owner] = 0.0                                     # applyscaleadd projects
+            self.project(b)                                          # applyscaleadd projects
             v0 = prec(b)
             return v0, math.sqrt(self.dot(v0, v0))
 
@@ -544,9 +570,14 @@ def single_rank(spec, gpu_reduction=True, num_threads=0):
 
 def run_threads(make_spec, cells, nranks, fn, part=None, num_threads=0, gpu_reduction=False):
     """Runs fn(BoxRank) on `nranks` threads; returns the per-rank results."""
+    import sys
     shared = ThreadComm.Shared(nranks)
     out = [None] * nranks
     err = []
+    # the ranks hand over to each other at every collective (two barrier waits per all-reduce): with CPython's default 5 ms
+    # switch interval a rank that arrives at a barrier can wait that long for the interpreter lock
+    old_interval = sys.getswitchinterval()
+    sys.setswitchinterval(2e-5)
 
     def work(r):
         try:
@@ -560,6 +591,7 @@ def run_threads(make_spec, cells, nranks, fn, part=None, num_threads=0, gpu_redu
         t.start()
     for t in th:
         t.join()
+    sys.setswitchinterval(old_interval)
     if err:
         raise err[0]
     return out
