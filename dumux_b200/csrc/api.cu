@@ -188,6 +188,7 @@ int finish_grid(dmx_ctx* ctx, int model, int dim, const int* cells, const std::v
     if (int rc = up(&ctx->d_region, ctx->h_region)) return rc;
     if (ctx->d_q) { cudaFree(ctx->d_q); ctx->d_q = nullptr; }
     for (int a = 0; a < 3; ++a) if (ctx->d_tij[a]) { cudaFree(ctx->d_tij[a]); ctx->d_tij[a] = nullptr; }
+    if (ctx->d_law_rec) { cudaFree(ctx->d_law_rec); ctx->d_law_rec = nullptr; }
     if (int rc = upload_pattern(ctx)) return rc;
     if (int rc = alloc_vectors(ctx)) return rc;
     // structured-grid ILU sweeps (DMX_ILU_GENERIC=1 keeps the level-scheduled generic kernels, for A/B runs)
@@ -326,7 +327,7 @@ int dmx_destroy(dmx_ctx* ctx)
     void* ptrs[] = {ctx->d_geom, ctx->d_K, ctx->d_phi, ctx->d_q, ctx->d_region, ctx->d_tij[0], ctx->d_tij[1], ctx->d_tij[2], ctx->d_laws,
                     ctx->d_tab_buf, ctx->d_rowptr, ctx->d_colidx, ctx->d_diag, ctx->d_J, ctx->d_ilu, ctx->d_rt, ctx->d_p, ctx->d_v, ctx->d_t,
                     ctx->d_y, ctx->d_z, ctx->d_dinv, ctx->d_gm, ctx->d_vf, ctx->d_color_rows, ctx->d_xold, ctx->d_lrows, ctx->d_urows, ctx->d_lptr, ctx->d_uptr, ctx->d_barrier, ctx->d_partials,
-                    ctx->d_scalars, ctx->d_flag, ctx->d_owner, ctx->d_send, ctx->d_recv, ctx->d_gather};
+                    ctx->d_scalars, ctx->d_flag, ctx->d_owner, ctx->d_send, ctx->d_recv, ctx->d_gather, ctx->d_law_rec};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int v = 0; v < DMX_NUM_VECS; ++v) if (ctx->d_vec[v]) cudaFree(ctx->d_vec[v]);
     for (int s = 0; s < 6; ++s) {

@@ -710,30 +710,52 @@ __global__ void __launch_bounds__(256) onep_analytic_jacobian_kernel(const AsmPa
 // (assembly/cclocalassembler.hh:490-600) + TwoPIncompressibleLocalResidual (porousmediumflow/2p/incompressiblelocalresidual.hh:
 // 80-101 storage derivatives, :137-234 TPFA flux derivatives, :420-481 Dirichlet faces; Neumann faces contribute nothing).
 // One thread per block row, rows written whole, blocks [eq][priVar] with priVars (p_w, S_n); the residual comes from the
-// JAC = false instantiation of the tile kernel.  Same operation sequence as the oracle (bit-identical); not tuned -- the
-// numerically differentiated tile kernel stays the benchmarked path.
+// JAC = false instantiation of the tile kernel.  Same operation sequence as the oracle (bit-identical).
+// Two kernels: twop_analytic_record_kernel evaluates the material law of every cell ONCE -- pc, the two mobilities and the three
+// regularised derivatives -dkrw/dSw, -dkrn/dSw, -dpc/dSw, six pow-heavy evaluations -- into a structure-of-arrays scratch
+// (6 doubles per cell); the row kernel then reads the records of its cell and its six neighbours (L2 hits) instead of
+// re-evaluating them seven times per row.
 // ================================================================================================
 struct TwoPState {
     double p[2], mob[2], Sw, K;
     int region;
+    double dKrw_dSn, dKrn_dSn, dpc_dSn;
 };
-__device__ __forceinline__ TwoPState twop_state(const AsmParams& P, size_t C)
+__global__ void __launch_bounds__(256) twop_analytic_record_kernel(const AsmParams P, double* __restrict__ rec)
+{
+    const size_t C = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t n = (size_t)P.n;
+    if (C >= n) return;
+    const double Sn = P.cur[C * 2 + 1];
+    const MaterialLaw& law = P.laws[P.region[C]];
+    const double Sw = 1 - Sn;
+    rec[0 * n + C] = law_pc(law, Sw);
+    rec[1 * n + C] = law_krw(law, Sw) / P.mu[0];
+    rec[2 * n + C] = law_krn(law, Sw) / P.mu[1];
+    rec[3 * n + C] = -1.0 * law_dkrw_dsw(law, Sw);
+    rec[4 * n + C] = -1.0 * law_dkrn_dsw(law, Sw);
+    rec[5 * n + C] = -1.0 * law_dpc_dsw(law, Sw);
+}
+__device__ __forceinline__ TwoPState twop_state_rec(const AsmParams& P, const double* __restrict__ rec, size_t C)
 {
     TwoPState s;
+    const size_t n = (size_t)P.n;
     const double2 u = reinterpret_cast<const double2*>(P.cur)[C];
-    s.region = P.region[C];
+    s.region = 0;
     s.K = P.K[C];
-    const MaterialLaw& law = P.laws[s.region];
     s.Sw = 1 - u.y;
-    const double pc = law_pc(law, s.Sw);
+    const double pc = rec[0 * n + C];
     s.p[0] = u.x;
     s.p[1] = u.x + pc;
-    s.mob[0] = law_krw(law, s.Sw) / P.mu[0];
-    s.mob[1] = law_krn(law, s.Sw) / P.mu[1];
+    s.mob[0] = rec[1 * n + C];
+    s.mob[1] = rec[2 * n + C];
+    s.dKrw_dSn = rec[3 * n + C];
+    s.dKrn_dSn = rec[4 * n + C];
+    s.dpc_dSn = rec[5 * n + C];
     return s;
 }
 template <int DIM>
-__global__ void __launch_bounds__(128) twop_analytic_jacobian_kernel(const AsmParams P)
+__global__ void __launch_bounds__(128) twop_analytic_jacobian_kernel(const AsmParams P, const double* __restrict__ rec)
 {
     const size_t I = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (I >= (size_t)P.n) return;
@@ -753,14 +775,13 @@ __global__ void __launch_bounds__(128) twop_analytic_jacobian_kernel(const AsmPa
     pos[3] = pos[1] + (ex[1] ? 1 : 0);
     pos[5] = pos[3] + (ex[3] ? 1 : 0);
 
-    const TwoPState sI = twop_state(P, I);
-    const MaterialLaw& lawI = P.laws[sI.region];
+    const TwoPState sI = twop_state_rec(P, rec, I);
     const double w = P.upwind_weight, extr = P.extrusion;
     const double rho_w = P.rho[0], rho_n = P.rho[1];
     const double rhow_muw = rho_w / P.mu[0], rhon_mun = rho_n / P.mu[1];
-    const double dKrw_dSn_inside = -1.0 * law_dkrw_dsw(lawI, sI.Sw);
-    const double dKrn_dSn_inside = -1.0 * law_dkrn_dsw(lawI, sI.Sw);
-    const double dpc_dSn_inside = -1.0 * law_dpc_dsw(lawI, sI.Sw);
+    const double dKrw_dSn_inside = sI.dKrw_dSn;
+    const double dKrn_dSn_inside = sI.dKrn_dSn;
+    const double dpc_dSn_inside = sI.dpc_dSn;
     double wdt[3] = {P.width[0][ci[0]], DIM > 1 ? P.width[1][ci[1]] : 1.0, DIM > 2 ? P.width[2][ci[2]] : 1.0};
     double AII[4] = {0.0, 0.0, 0.0, 0.0};
     if (!P.stationary) {
@@ -791,8 +812,7 @@ __global__ void __launch_bounds__(128) twop_analytic_jacobian_kernel(const AsmPa
         if (ex[s]) {
             const size_t J = hi ? I + stride[a] : I - stride[a];
             const int cj = hi ? ci[a] + 1 : ci[a] - 1;
-            const TwoPState sJ = twop_state(P, J);
-            const MaterialLaw& lawJ = P.laws[sJ.region];
+            const TwoPState sJ = twop_state_rec(P, rec, J);
             tij = hi ? P.tij[a][I] : P.tij[a][J];
             pJ[0] = sJ.p[0]; pJ[1] = sJ.p[1];
             upJ[0] = rho_w * sJ.mob[0]; upJ[1] = rho_n * sJ.mob[1];
@@ -808,9 +828,9 @@ __global__ void __launch_bounds__(128) twop_analytic_jacobian_kernel(const AsmPa
                 }
                 flux[ph] = f;
             }
-            dKrw_dSn_outside = -1.0 * law_dkrw_dsw(lawJ, sJ.Sw);
-            dKrn_dSn_outside = -1.0 * law_dkrn_dsw(lawJ, sJ.Sw);
-            dpc_dSn_outside = -1.0 * law_dpc_dsw(lawJ, sJ.Sw);
+            dKrw_dSn_outside = sJ.dKrw_dSn;
+            dKrn_dSn_outside = sJ.dKrn_dSn;
+            dpc_dSn_outside = sJ.dpc_dSn;
         } else {
             int f_;
             if (a == 0) f_ = ci[1] + ny * ci[2];
@@ -1303,9 +1323,12 @@ static int launch_impl(dmx_ctx* ctx, bool with_jac, bool volvars_only)
             if (int rc = launch_tile<DMX_MODEL_2P, false>(ctx, P, false)) return rc;      // residual
             if (!with_jac) return 0;
             ProfScope ps__(ctx, DMX_K_ASSEMBLY);
-            if (ctx->dim == 3) twop_analytic_jacobian_kernel<3><<<grid, 128, 0, ctx->stream>>>(P);
-            else if (ctx->dim == 2) twop_analytic_jacobian_kernel<2><<<grid, 128, 0, ctx->stream>>>(P);
-            else twop_analytic_jacobian_kernel<1><<<grid, 128, 0, ctx->stream>>>(P);
+            if (!ctx->d_law_rec) DMX_CUDA(cudaMalloc((void**)&ctx->d_law_rec, (size_t)ctx->n * 6 * sizeof(double)));
+            twop_analytic_record_kernel<<<(unsigned)((ctx->n + 255) / 256), 256, 0, ctx->stream>>>(P, ctx->d_law_rec);
+            DMX_CHECK_LAUNCH();
+            if (ctx->dim == 3) twop_analytic_jacobian_kernel<3><<<grid, 128, 0, ctx->stream>>>(P, ctx->d_law_rec);
+            else if (ctx->dim == 2) twop_analytic_jacobian_kernel<2><<<grid, 128, 0, ctx->stream>>>(P, ctx->d_law_rec);
+            else twop_analytic_jacobian_kernel<1><<<grid, 128, 0, ctx->stream>>>(P, ctx->d_law_rec);
             DMX_CHECK_LAUNCH();
             return 0;
         }

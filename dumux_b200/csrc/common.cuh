@@ -107,6 +107,7 @@ struct dmx_ctx {
     int* d_region = nullptr;
     double* d_tij[3] = {nullptr, nullptr, nullptr};
     double* d_vf = nullptr;             // tracer: frozen volume fluxes [n][2*dim]
+    double* d_law_rec = nullptr;        // DiffMethod::analytic (2p): per-cell material-law record [6][n], allocated on first use
     int tracer_implicit = 0;
     double tracer_D = 0.0, tracer_tau = 0.5;
 

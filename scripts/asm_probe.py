@@ -8,7 +8,7 @@ from dumux_b200 import problems
 
 edge = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
-spec = problems.twop_lens((edge, edge, edge), law="bc", heterogeneity_sigma=0.5, dt=250.0, plane_rng=True)
+spec = problems.twop_lens((edge, edge, edge), law="bc", heterogeneity_sigma=0.5, dt=250.0, plane_rng=True, analytic=os.environ.get("ANALYTIC", "0") == "1")
 e = B.Engine(spec)
 n = spec.num_cells
 rng = np.random.RandomState(5)
