@@ -364,6 +364,7 @@ def parity_check(comm):
     out = {"ranks": world, "layouts": []}
     layouts = [None] if world == 1 else [None, STRONG_PART.get(world, balanced_partition(world))]
     ok_all = True
+    amg_all = True
     for part in layouts:
         part_ = part if part is not None else problems.default_partitioning(3, world)
         cells = tuple(24 * p if p > 1 else 32 for p in part_) if part is not None else (32, 32, 16 * world)
@@ -378,6 +379,10 @@ def parity_check(comm):
         u, st, rep = eng.newton(spec.initial, spec.initial)
         mine = {"st": st, "nsteps": rep.newton_iterations, "lin_its": [rep.linear_iterations[i] for i in range(rep.newton_iterations)],
                 "u": u}
+        # the same solve with the AMG preconditioner (the block-decomposed global hierarchy of csrc/amg.cu)
+        ua, sta, repa = eng.newton(spec.initial, spec.initial, preconditioner=B.PRECOND_AMG)
+        mine.update(st_amg=sta, nsteps_amg=repa.newton_iterations, u_amg=ua,
+                    lin_its_amg=[repa.linear_iterations[i] for i in range(repa.newton_iterations)])
         agree = None
         if world > 1:
             bad = spec.initial.copy()
@@ -395,7 +400,9 @@ def parity_check(comm):
 
             def job(ro):
                 uu, nst, nsteps, lin_its = ro.newton(ro.spec.initial, ro.spec.initial)
-                return {"u": uu, "st": nst, "nsteps": nsteps, "lin_its": lin_its}
+                ua_, nsta, nstepsa, lin_itsa = ro.newton(ro.spec.initial, ro.spec.initial, precond="amg")
+                return {"u": uu, "st": nst, "nsteps": nsteps, "lin_its": lin_its,
+                        "u_amg": ua_, "st_amg": nsta, "nsteps_amg": nstepsa, "lin_its_amg": lin_itsa}
 
             ref = D.run_threads(make, cells, world, job, part, gpu_reduction=True)
             ug = D.gather_owned([g["u"] for g in got], cells, world, 2, part).reshape(-1, 2)
@@ -420,10 +427,22 @@ def parity_check(comm):
             entry["bicgstab_its_first_diff"] = first_diff
             band = all(abs(a - b) <= max(1, 0.15 * b) for a, b in zip(its_g, its_c)) and len(its_g) == len(its_c)
             ok = entry["newton_its_equal"] and entry["field_rel_l2"] <= 1e-8 and (agree is None or agree) and band
+            # AMG-BiCGSTAB on the same ranks: Newton count, BiCGSTAB counts and fields against the oracle's block-decomposed hierarchy
+            uga = D.gather_owned([g["u_amg"] for g in got], cells, world, 2, part).reshape(-1, 2)
+            uca = D.gather_owned([c["u_amg"] for c in ref], cells, world, 2, part).reshape(-1, 2)
+            rela = max(float(np.linalg.norm(uga[:, 0] - uca[:, 0]) / np.linalg.norm(uca[:, 0])),
+                       float(np.linalg.norm(uga[:, 1] - uca[:, 1]) / max(1.0, np.linalg.norm(uca[:, 1]))))
+            amg_ok = all(g["st_amg"] == 0 and g["nsteps_amg"] == c["nsteps_amg"] for g, c in zip(got, ref)) and rela <= 1e-8 \
+                and all(abs(a - b) <= 1 for a, b in zip(got[0]["lin_its_amg"], ref[0]["lin_its_amg"]))
+            entry["amg"] = {"newton_its": got[0]["nsteps_amg"], "newton_its_oracle": ref[0]["nsteps_amg"],
+                            "bicgstab_its": got[0]["lin_its_amg"], "bicgstab_its_oracle": ref[0]["lin_its_amg"],
+                            "bicgstab_its_equal": got[0]["lin_its_amg"] == ref[0]["lin_its_amg"], "field_rel_l2": rela, "ok": bool(amg_ok)}
+            amg_all = amg_all and amg_ok
             entry["ok"] = bool(ok)
             ok_all = ok_all and ok
             out["layouts"].append(entry)
-    verdict = comm.gather(ok_all if rank == 0 else None)[0]
+    verdict, amg_verdict = comm.gather((ok_all, amg_all) if rank == 0 else None)[0]
+    out["amg_ok"] = bool(amg_verdict)
     if rank == 0:
         first = out["layouts"][0]
         out.update(newton_its_equal=all(e["newton_its_equal"] for e in out["layouts"]),
@@ -433,6 +452,8 @@ def parity_check(comm):
         log(f"[bench] parity_check: {json.dumps(out)}")
     if not verdict:
         raise SystemExit("bench.py: parity_check against the CPU oracle FAILED -- not timing a wrong result")
+    if not amg_verdict:
+        log("[bench] parity_check of the AMG preconditioner FAILED: the AMG regions are not timed")
     return out
 
 
@@ -613,6 +634,10 @@ def run_b200(args):
 
     # ---- the same workload with the AMG preconditioner (AMGBiCGSTABIstlSolver, istlsolvers.hh:716-757): its own timed region ----
     amg_line = None
+    amg_parity_ok = parity is None or parity.get("amg_ok", True)
+    if not amg_parity_ok:
+        amg_line = {"error": "parity_check of the AMG preconditioner failed on these ranks; region not timed"}
+        args.no_amg = True
     if args.solver == "ilu0" and not args.no_amg:
         try:
             ares = measure(comm, cells, upper, part, args.steps, 2, e2e=False, label="amg", solver="amg")
