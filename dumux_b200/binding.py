@@ -59,7 +59,8 @@ class DmxNewtonParams(C.Structure):
 
 class DmxAmgParams(C.Structure):
     _fields_ = [("pre_steps", C.c_int), ("post_steps", C.c_int), ("prolongation_damping", C.c_double), ("smoother", C.c_int),
-                ("coarsest_cells", C.c_int), ("coarsest_steps", C.c_int), ("max_levels", C.c_int)]
+                ("coarsest_cells", C.c_int), ("coarsest_steps", C.c_int), ("max_levels", C.c_int),
+                ("smoother_iterations", C.c_int), ("smoother_relaxation", C.c_double)]
 
 
 class DmxNewtonReport(C.Structure):
@@ -421,8 +422,9 @@ class Engine:
         self._check(self.L.dmx_set_preconditioner_params(self.h, iterations, relaxation))
 
     def set_amg_params(self, **kw):
-        """dune-istl's AMG parameter names: pre_steps, post_steps, prolongation_damping, smoother (PRECOND_SSOR | PRECOND_ILU0),
-        coarsest_cells, coarsest_steps, max_levels; unspecified ones keep dune's defaults"""
+        """dune-istl's AMG parameter names: pre_steps, post_steps, prolongation_damping, smoother (PRECOND_SSOR | PRECOND_ILU0 |
+        PRECOND_PARMT_*), smoother_iterations, smoother_relaxation, coarsest_cells, coarsest_steps, max_levels; unspecified ones keep
+        dune's defaults"""
         p = DmxAmgParams()
         self.L.dmx_default_amg_params(C.byref(p))
         for k, v in kw.items():

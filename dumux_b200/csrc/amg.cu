@@ -261,7 +261,9 @@ int amg_setup(dmx_ctx* ctx)
         st = amg_of(ctx);
     }
     const int smoother = ctx->amg_prm.smoother;
-    if (smoother != DMX_PRECOND_SSOR && smoother != DMX_PRECOND_ILU0) return fail(ctx, DMX_ERR_USAGE, "AMG smoother must be DMX_PRECOND_SSOR or DMX_PRECOND_ILU0");
+    const bool parmt = smoother == DMX_PRECOND_PARMT_JAC || smoother == DMX_PRECOND_PARMT_SOR || smoother == DMX_PRECOND_PARMT_SSOR;
+    if (smoother != DMX_PRECOND_SSOR && smoother != DMX_PRECOND_ILU0 && !parmt)
+        return fail(ctx, DMX_ERR_USAGE, "AMG smoother must be DMX_PRECOND_SSOR, DMX_PRECOND_ILU0 or DMX_PRECOND_PARMT_*");
     for (size_t l = 0; l < st->levels.size(); ++l) {
         dmx_ctx* c = st->levels[l].c;
         if (l > 0) {
@@ -277,6 +279,14 @@ int amg_setup(dmx_ctx* ctx)
                                                                       f->d_rowptr, f->d_J, c->d_rowptr, c->d_J);
             DMX_CHECK_LAUNCH();
             c->jac_diagonal = false;
+        }
+        if (parmt) {
+            // Dumux::ParMTJac / ParMTSOR / ParMTSSOR as the smoother: no factorisation, the colour sets of the level's pattern
+            if (int rc = precond_setup(c, smoother)) {
+                if (c != ctx) ctx->err = c->err;
+                return rc;
+            }
+            continue;
         }
         // smoother set-up: the ILU machinery with Dinv = A_ii^-1 (factorised SSOR) or the ILU(0) recurrence
         c->ssor_factorised = (smoother == DMX_PRECOND_SSOR);
@@ -296,7 +306,12 @@ static int amg_smooth_step(dmx_ctx* ctx, AmgLevel& L, bool first, bool need_defe
     dmx_ctx* c = L.c;
     const size_t len = (size_t)c->n * c->b;
     if (!rin) rin = L.r;
-    if (int rc = ilu0_apply(c, rin, L.u)) return rc;                          // update = M^-1 defect (from update = 0)
+    const int sm = ctx->amg_prm.smoother;
+    if (sm == DMX_PRECOND_SSOR || sm == DMX_PRECOND_ILU0) {
+        if (int rc = ilu0_apply(c, rin, L.u)) return rc;                      // update = M^-1 defect (from update = 0)
+    } else {
+        if (int rc = parmt_apply_prm(c, sm, rin, L.u, ctx->amg_prm.smoother_iterations, ctx->amg_prm.smoother_relaxation)) return rc;
+    }
     if (c->nranks > 1)
         if (int rc = halo_exchange(c, L.u)) return rc;                        // BlockPreconditioner::apply: copyOwnerToAll
     if (need_defect && spmv_update_supported(c))

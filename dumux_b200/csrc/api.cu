@@ -267,6 +267,7 @@ void dmx_default_amg_params(dmx_amg_params* p)
 {
     p->pre_steps = 2; p->post_steps = 2; p->prolongation_damping = 1.6; p->smoother = DMX_PRECOND_SSOR;
     p->coarsest_cells = 8; p->coarsest_steps = 8; p->max_levels = 15;
+    p->smoother_iterations = 1; p->smoother_relaxation = 1.0;
 }
 void dmx_default_newton_params(dmx_newton_params* p)
 {
@@ -921,7 +922,12 @@ int dmx_ssor_apply(dmx_ctx* ctx, int d_vec, int v_vec)
 int dmx_set_amg_params(dmx_ctx* ctx, const dmx_amg_params* p)
 {
     if (p->pre_steps < 0 || p->post_steps < 0 || p->pre_steps + p->post_steps < 1) return fail(ctx, DMX_ERR_USAGE, "AMG: preSteps + postSteps must be >= 1");
-    if (p->smoother != DMX_PRECOND_SSOR && p->smoother != DMX_PRECOND_ILU0) return fail(ctx, DMX_ERR_USAGE, "AMG smoother must be DMX_PRECOND_SSOR or DMX_PRECOND_ILU0");
+    const bool parmt = p->smoother == DMX_PRECOND_PARMT_JAC || p->smoother == DMX_PRECOND_PARMT_SOR || p->smoother == DMX_PRECOND_PARMT_SSOR;
+    if (p->smoother != DMX_PRECOND_SSOR && p->smoother != DMX_PRECOND_ILU0 && !parmt)
+        return fail(ctx, DMX_ERR_USAGE, "AMG smoother must be DMX_PRECOND_SSOR, DMX_PRECOND_ILU0 or DMX_PRECOND_PARMT_*");
+    if (p->smoother_iterations < 1) return fail(ctx, DMX_ERR_USAGE, "AMG: smoother_iterations must be >= 1");
+    if (!parmt && (p->smoother_iterations != 1 || p->smoother_relaxation != 1.0))
+        return fail(ctx, DMX_ERR_USAGE, "AMG: the ssor / ilu smoothers run one iteration with relaxation 1 (factorised sweeps)");
     if (p->coarsest_cells < 1 || p->coarsest_steps < 1 || p->max_levels < 1) return fail(ctx, DMX_ERR_USAGE, "AMG: coarsest_cells, coarsest_steps, max_levels must be >= 1");
     if (p->coarsest_cells != ctx->amg_prm.coarsest_cells || p->max_levels != ctx->amg_prm.max_levels) ctx->amg_dirty = true;
     ctx->amg_prm = *p;

@@ -305,6 +305,7 @@ int ssor_apply(dmx_ctx* ctx, const double* d, double* v);
 int block_jacobi_setup(dmx_ctx* ctx);
 int block_jacobi_apply(dmx_ctx* ctx, const double* d, double* v);
 int parmt_apply(dmx_ctx* ctx, int precond, const double* d, double* v);
+int parmt_apply_prm(dmx_ctx* ctx, int precond, const double* d, double* v, int iterations, double relaxation);
 int precond_apply_local(dmx_ctx* ctx, int precond, const double* d, double* v);
 int precond_setup(dmx_ctx* ctx, int precond);
 int dot(dmx_ctx* ctx, const double* a, const double* b, double* out);

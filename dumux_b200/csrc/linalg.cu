@@ -980,10 +980,15 @@ static int parmt_build_colors(dmx_ctx* ctx)
 // v = ParMT{Jac,SOR,SSOR}(J)(d) from v = 0
 int parmt_apply(dmx_ctx* ctx, int precond, const double* d, double* v)
 {
+    return parmt_apply_prm(ctx, precond, d, v, ctx->precond_iterations, ctx->precond_relaxation);
+}
+// ... with the iteration count and relaxation factor handed in (as an AMG smoother: SmootherArgs of the hierarchy)
+int parmt_apply_prm(dmx_ctx* ctx, int precond, const double* d, double* v, int iterations, double relaxation)
+{
     ProfScope ps(ctx, DMX_K_JACOBI);
     const size_t len = (size_t)ctx->n * ctx->b;
     DMX_CUDA(cudaMemsetAsync(v, 0, len * sizeof(double), ctx->stream));
-    const double w = ctx->precond_relaxation;
+    const double w = relaxation;
     auto launch = [&](int nrows, const int* rows, const double* xin, double* xout) -> int {
         if (nrows <= 0) return 0;
         const int grid = (nrows + 255) / 256;
@@ -996,7 +1001,7 @@ int parmt_apply(dmx_ctx* ctx, int precond, const double* d, double* v)
     };
     if (precond == DMX_PRECOND_PARMT_JAC) {
         if (!ctx->d_xold) DMX_CUDA(cudaMalloc((void**)&ctx->d_xold, len * sizeof(double)));
-        for (int it = 0; it < ctx->precond_iterations; ++it) {
+        for (int it = 0; it < iterations; ++it) {
             DMX_CUDA(cudaMemcpyAsync(ctx->d_xold, v, len * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
             if (int rc = launch(ctx->n, nullptr, ctx->d_xold, v)) return rc;
         }
@@ -1010,7 +1015,7 @@ int parmt_apply(dmx_ctx* ctx, int precond, const double* d, double* v)
         }
         return 0;
     };
-    for (int it = 0; it < ctx->precond_iterations; ++it) {
+    for (int it = 0; it < iterations; ++it) {
         if (int rc = sweep(true)) return rc;
         if (precond == DMX_PRECOND_PARMT_SSOR)
             if (int rc = sweep(false)) return rc;

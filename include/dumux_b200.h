@@ -109,10 +109,14 @@ typedef struct {
     int    pre_steps;             /* preSteps  2 */
     int    post_steps;            /* postSteps 2 */
     double prolongation_damping;  /* prolongationDampingFactor 1.6 */
-    int    smoother;              /* DMX_PRECOND_SSOR (default, "ssor") or DMX_PRECOND_ILU0 ("ilu") */
+    int    smoother;              /* DMX_PRECOND_SSOR (default, "ssor"), DMX_PRECOND_ILU0 ("ilu"), or DuMux's multithreaded smoothers
+                                     DMX_PRECOND_PARMT_JAC / _SOR / _SSOR (Dune::Amg::AMG<LOP, Vector, Dumux::ParMTSSOR<...>>,
+                                     test/linear/test_parallel_amg_smoothers.cc:25-40, linear/stokes_solver.hh:261) */
     int    coarsest_cells;        /* stop coarsening at <= this many cells (default 8) */
     int    coarsest_steps;        /* smoothing steps on the coarsest level (default 8) */
     int    max_levels;            /* maxLevel 15 */
+    int    smoother_iterations;   /* SmootherArgs::iterations (default 1); honoured by the ParMT smoothers, must be 1 for ssor / ilu */
+    double smoother_relaxation;   /* SmootherArgs::relaxationFactor (default 1.0); honoured by the ParMT smoothers, must be 1 for ssor / ilu */
 } dmx_amg_params;
 
 /* ---- lifetime ------------------------------------------------------------------------------------------ */

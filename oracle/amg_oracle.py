@@ -15,6 +15,8 @@ import numpy as np
 from oracle import oracle_py as O
 
 SMOOTHER_SSOR, SMOOTHER_ILU0 = "ssor", "ilu"
+# Dumux::ParMTJac / ParMTSOR / ParMTSSOR as AMG smoothers (test/linear/test_parallel_amg_smoothers.cc:25-40)
+PARMT_SMOOTHERS = {"par_mt_jac": O.PARMT_JAC, "par_mt_sor": O.PARMT_SOR, "par_mt_ssor": O.PARMT_SSOR}
 
 
 def grid_pattern(cells, dim):
@@ -48,8 +50,10 @@ class AmgOracle:
     local mv + project."""
 
     def __init__(self, cells, dim, b, rowptr, colidx, values, pre_steps=2, post_steps=2, damping=1.6, smoother=SMOOTHER_SSOR,
-                 coarsest_cells=8, coarsest_steps=8, max_levels=15, layout=None, part3=None, gcells=None):
+                 coarsest_cells=8, coarsest_steps=8, max_levels=15, layout=None, part3=None, gcells=None,
+                 smoother_iterations=1, smoother_relaxation=1.0):
         self.b, self.dim = b, dim
+        self.smoother, self.sm_it, self.sm_w = smoother, smoother_iterations, smoother_relaxation
         self.pre, self.post, self.damp, self.coarsest_steps = pre_steps, post_steps, damping, coarsest_steps
         self.levels = []
         c3 = tuple(cells) + (1,) * (3 - len(cells))
@@ -109,6 +113,8 @@ class AmgOracle:
             self.levels.append(lv)
         self.status = 0
         for lv in self.levels:
+            if smoother in PARMT_SMOOTHERS:
+                continue
             if smoother == SMOOTHER_SSOR:
                 lv.fac, st = O.ssor_factor(lv.n, b, lv.rowptr, lv.colidx, lv.values)
             else:
@@ -173,7 +179,10 @@ class AmgOracle:
         return t
 
     def _smooth_step(self, lv, x, r, first, need_defect):
-        u = O.ilu0_apply(lv.n, self.b, lv.rowptr, lv.colidx, lv.fac, r)
+        if self.smoother in PARMT_SMOOTHERS:
+            u = O.parmt_apply(PARMT_SMOOTHERS[self.smoother], lv.n, self.b, lv.rowptr, lv.colidx, lv.values, r, self.sm_it, self.sm_w)
+        else:
+            u = O.ilu0_apply(lv.n, self.b, lv.rowptr, lv.colidx, lv.fac, r)
         if lv.layout is not None:
             lv.layout.copy_owner_to_all(u)                 # BlockPreconditioner::apply
         x = u if first else x + u

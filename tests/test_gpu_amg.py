@@ -113,3 +113,60 @@ def test_amg_at_64_cubed_is_mesh_independent(engine_factory):
     e.upload(B.VEC_CUR, spec.initial)
     st2, its_ilu, *_ = e.newton_step(e.newton_params(lin_maxit=2000))
     assert st == 0 and st2 == 0 and its_amg <= 8 and its_ilu > 60
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# test/linear/test_parallel_amg_smoothers.cc: Dune::Amg::AMG with Dumux::ParMTSSOR / ParMTSOR / ParMTJac as the smoother
+# (SmootherArgs: 2 iterations, relaxation 0.8) preconditioning CG on the CCTpfa Helmholtz operator -div grad u + u of a 300 x 300
+# YaspGrid (homogeneous Neumann), right-hand side b = A 1, reduction 1e-15, at most 200 iterations; accepted if the solver
+# converged and | |x|^2 - N | <= 1e-10 N.  Same set-up here (the hierarchy is this library's).
+# ------------------------------------------------------------------------------------------------------------------------
+def helmholtz_system(N, o):
+    """makeHelmholtzMatrix<CCTpfaModel>(gridView, a = 1, b = 1) on the unit square (linear/helmholtzoperator.hh:96-146): t_ij = 1 on a
+    uniform 2-D grid, diagonal = number of neighbours + b h^2"""
+    rp, ci = o.rowptr, o.colidx
+    n, h = N * N, 1.0 / N
+    rows = np.repeat(np.arange(n), np.diff(rp))
+    vals = np.where(ci == rows, 0.0, -1.0)
+    vals[ci == rows] = (np.diff(rp) - 1) + h * h
+    return vals, O.spmv(n, 1, rp, ci, vals, np.ones(n))
+
+
+PARMT = {"par_mt_ssor": B.PRECOND_PARMT_SSOR, "par_mt_sor": B.PRECOND_PARMT_SOR, "par_mt_jac": B.PRECOND_PARMT_JAC}
+
+
+@pytest.mark.parametrize("smoother", list(PARMT))
+def test_parallel_amg_smoothers_helmholtz(engine_factory, smoother):
+    N = 300
+    spec = problems.onep_incompressible((N, N))
+    ro = D.single_rank(spec)
+    vals, b = helmholtz_system(N, ro.o)
+    e = engine_factory(spec)
+    e.set_amg_params(smoother=PARMT[smoother], smoother_iterations=2, smoother_relaxation=0.8)
+    e.set_linear_solver("cg")
+    x, st, its, red = e.solve(vals, b, reduction=1e-15, maxit=200, precond=B.PRECOND_AMG)
+    e.set_linear_solver("bicgstab")
+    e.set_amg_params()
+    assert st == 0, "Solver did not converge!"
+    assert abs(np.dot(x, x) - x.size) <= 1e-10 * x.size
+    # ... and it is the iteration the oracle runs (device summation tree for the scalar products)
+    ro.amg_params = dict(smoother=smoother, smoother_iterations=2, smoother_relaxation=0.8)
+    xo, sto, ito, redo = ro.cg(vals, b, 1e-15, 200, precond="amg")
+    assert sto == 0 and abs(its - ito) <= 1, (its, ito)
+    assert np.linalg.norm(x - xo) <= 1e-12 * np.linalg.norm(xo)
+
+
+@pytest.mark.parametrize("smoother", list(PARMT))
+def test_parmt_smoothed_vcycle_bit_exact(engine_factory, smoother):
+    spec = SPECS["2p-3d-odd"]()
+    o, res, jac = _system(spec)
+    amg = AmgOracle(spec.cells, spec.dim, o.b, o.rowptr, o.colidx, jac, smoother=smoother, smoother_iterations=2, smoother_relaxation=0.8)
+    e = engine_factory(spec)
+    e.set_amg_params(smoother=PARMT[smoother], smoother_iterations=2, smoother_relaxation=0.8)
+    e.upload_jacobian(jac)
+    e.upload(B.VEC_WORK0, res)
+    e.precond_apply(B.PRECOND_AMG, B.VEC_WORK0, B.VEC_WORK1)
+    assert np.array_equal(e.download(B.VEC_WORK1), amg.apply(res))
+    e.set_amg_params()
+    with pytest.raises(B.DmxError):
+        e.set_amg_params(smoother=B.PRECOND_SSOR, smoother_iterations=2)       # the factorised sweeps run one iteration

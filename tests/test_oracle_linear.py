@@ -273,3 +273,25 @@ def test_max_relative_shift_and_norms():
     assert L.orc_max_relative_shift(4, u1, u2) == pytest.approx(0.05)
     a = np.arange(1.0, 6.0)
     assert L.orc_norm2(5, a) == pytest.approx(np.sqrt(55.0)) and L.orc_dot(5, a, a) == 55.0
+
+
+# test/linear/test_parallel_amg_smoothers.cc restated on the oracle: AMG with Dumux::ParMTSSOR / ParMTSOR / ParMTJac smoothers
+# (2 iterations, relaxation 0.8) preconditioning CG on the CCTpfa Helmholtz operator of a 300 x 300 grid, b = A 1, reduction 1e-15,
+# at most 200 iterations; the reference accepts "converged and | |x|^2 - N | <= 1e-10 N"
+@pytest.mark.parametrize("smoother", ["par_mt_ssor", "par_mt_sor", "par_mt_jac"])
+def test_parallel_amg_smoothers_helmholtz_oracle(smoother):
+    from dumux_b200 import problems
+    from oracle import dist_oracle as D
+    N = 300
+    spec = problems.onep_incompressible((N, N))
+    ro = D.single_rank(spec, gpu_reduction=False)
+    rp, ci = ro.o.rowptr, ro.o.colidx
+    n, h = N * N, 1.0 / N
+    rows = np.repeat(np.arange(n), np.diff(rp))
+    vals = np.where(ci == rows, 0.0, -1.0)
+    vals[ci == rows] = (np.diff(rp) - 1) + h * h
+    b = O.spmv(n, 1, rp, ci, vals, np.ones(n))
+    ro.amg_params = dict(smoother=smoother, smoother_iterations=2, smoother_relaxation=0.8)
+    x, st, its, red = ro.cg(vals, b, 1e-15, 200, precond="amg")
+    assert st == 0 and its < 60
+    assert abs(np.dot(x, x) - n) <= 1e-10 * n
