@@ -439,6 +439,95 @@ def twop_lens(cells=(48, 32), law="vg", lower=None, upper=None, lens_lower=None,
 
 
 # ------------------------------------------------------------------------------------------------------
+# test/porousmediumflow/2p/buckleyleverett (params.input, problem.hh:52-140, spatialparams.hh:40-100, properties.hh:52-82):
+# pseudo-1-D displacement of the non-wetting phase by water on a 100 x 1 YaspGrid over [0,100] x [0,75] m, no gravity,
+# BrooksCoreyDefault with lambda 4, entry pressure 0, Swr = Snr = 0.2, K = 1.01936799e-14, porosity 0.2, both fluids with
+# density 1000 and viscosity 1e-3; Dirichlet on the left (p = 2e5, Sn = Snr), Neumann elsewhere: the non-wetting phase leaves
+# through the right boundary with totalVelocity * density = 3e-7 * 1000 kg/(m^2 s), no flow at top and bottom; initial
+# p = 2e5, Sn = 1 - Swr.  TimeLoop: dt0 1e3 s, tEnd 1e7 s, MaxTimeStepSize 5e5 s.
+# ------------------------------------------------------------------------------------------------------
+def twop_buckleyleverett(cells=(100, 1), total_velocity=3e-7, injection_pressure=2e5) -> ProblemSpec:
+    dim = 2
+    lower, upper = (0.0, 0.0), (100.0, 75.0)
+    n = int(np.prod(cells))
+    swr = snr = 0.2
+    mats = [Material(LAW_BC, (0.0, 4.0), swr=swr, snr=snr, reg=(0.01,))]
+    bc_type, bc_values = {}, {}
+    eps = 1e-6
+    for side in range(2 * dim):
+        fc = side_face_centers(cells, lower, upper, side)
+        nf = fc.shape[0]
+        left = fc[:, 0] < lower[0] + eps
+        right = fc[:, 0] > upper[0] - eps
+        bc_type[side] = np.where(left, BC_DIRICHLET, BC_NEUMANN).astype(np.int32)
+        vals = np.zeros((nf, 2))
+        vals[left, 0] = injection_pressure
+        vals[left, 1] = snr
+        vals[right & ~left, 1] = total_velocity * 1000.0
+        bc_values[side] = vals
+    init = np.zeros((n, 2))
+    init[:, 0] = injection_pressure
+    init[:, 1] = 1.0 - swr
+    return ProblemSpec(
+        name="2p_buckleyleverett", model=MODEL_2P, dim=dim, cells=tuple(cells), lower=lower, upper=upper,
+        K=np.full(n, 1.01936799e-14), phi=np.full(n, 0.2), region=np.zeros(n, dtype=np.int32), materials=mats,
+        rho=(1000.0, 1000.0), mu=(1e-3, 1e-3), bc_type=bc_type, bc_values=bc_values,
+        options=Options(stationary=False, dt=1e3, enable_gravity=False), initial=init)
+
+
+class BuckleyLeverettAnalyticSolution:
+    """test/porousmediumflow/2p/buckleyleverett/analyticsolution.hh:32-185: Welge tangent construction for the shock saturation
+    (Brent root of f_w'(S) - (f_w(S) - f_w(Swr))/(S - Swr)), rarefaction wave behind the shock by inverting
+    v/phi f_w'(S) = x/t.  `law(which, sw)` evaluates krw (1), krn (2), dkrw/dSw (4), dkrn/dSw (5) of the material law."""
+
+    def __init__(self, law, total_velocity=3e-7, porosity=0.2, swr=0.2, snr=0.2, mu_w=1e-3, mu_n=1e-3):
+        from scipy.optimize import brentq
+        self.law, self.v, self.phi, self.swr, self.snr, self.mu_w, self.mu_n = law, total_velocity, porosity, swr, snr, mu_w, mu_n
+        self._brentq = brentq
+        self.sw_left, self.sw_right = 1.0 - snr, swr
+        eps = 1e-12
+        tangent = lambda sw: (self.fw(sw) - self.fw(self.swr)) / (sw - self.swr)
+        self.sw_shock = brentq(lambda sw: self.dfw(sw) - tangent(sw), self.sw_right + eps, self.sw_left - eps, xtol=1e-14)
+        self.shock_speed = self.v / self.phi * self.dfw(self.sw_shock)
+
+    def fw(self, sw):
+        mw, mn = self.law(1, sw) / self.mu_w, self.law(2, sw) / self.mu_n
+        return mw / (mw + mn)
+
+    def dfw(self, sw):
+        mw, mn = self.law(1, sw) / self.mu_w, self.law(2, sw) / self.mu_n
+        dmw, dmn = self.law(4, sw) / self.mu_w, self.law(5, sw) / self.mu_n
+        return (dmw * (mw + mn) - mw * (dmw + dmn)) / ((mw + mn) * (mw + mn))
+
+    def saturation(self, x, time):
+        if time <= 0.0:
+            return self.swr
+        xi = x / time
+        xi_lower = self.v / self.phi * self.dfw(1.0 - self.snr)
+        if xi <= xi_lower:
+            return 1.0 - self.snr
+        if xi < self.shock_speed:
+            return self._brentq(lambda sw: self.v / self.phi * self.dfw(sw) - xi, self.sw_shock, self.sw_left, xtol=1e-14)
+        return self.swr
+
+    def check(self, spec, u, t_end, density_w=1000.0):
+        """main.cc:140-205: relative errors of the wetting-phase centre of mass and total mass against the analytic profile"""
+        from scipy.integrate import quad
+        x_min, x_max = spec.lower[0], spec.upper[0]
+        width = spec.upper[1] - spec.lower[1]
+        pts = [x_min + self.shock_speed * t_end] if x_min < self.shock_speed * t_end < x_max else None
+        m1 = quad(lambda x: x * density_w * self.saturation(x, t_end) * self.phi * width, x_min, x_max, points=pts, limit=400)[0]
+        m0 = quad(lambda x: density_w * self.saturation(x, t_end) * self.phi * width, x_min, x_max, points=pts, limit=400)[0]
+        ctr = cell_centers(spec.cells, spec.lower, spec.upper)
+        nodes = node_coords(spec.cells, spec.lower, spec.upper)
+        vol = np.outer(np.diff(nodes[1]), np.diff(nodes[0])).reshape(-1)
+        sw = 1.0 - np.asarray(u).reshape(-1, 2)[:, 1]
+        mass = density_w * self.phi * vol * sw
+        com_num, com_ana = float((ctr[:, 0] * mass).sum() / mass.sum()), m1 / m0
+        return abs(com_ana - com_num) / com_ana, abs(m0 - float(mass.sum())) / m0
+
+
+# ------------------------------------------------------------------------------------------------------
 # 1p incompressible on the log-normal field of examples/1ptracer (spatialparams_1p.hh:95-104, problem_1p.hh)
 # ------------------------------------------------------------------------------------------------------
 def onep_tracer_pressure(cells=(50, 50)) -> ProblemSpec:

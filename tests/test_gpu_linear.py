@@ -189,6 +189,37 @@ def test_generic_bcrs_2x2_laplacian(engine_factory):
         assert np.linalg.norm(r) <= 1e-11 * np.linalg.norm(b)
 
 
+@pytest.mark.parametrize("N", [2, 20])
+def test_linearsolver_cc_amg_and_ssor_solvers(engine_factory, N):
+    """test/linear/test_linearsolver.cc as the reference runs it: setupLaplacian(A, ProblemSize) with 2x2 blocks, x = 0, b = 1, solved
+    with AMGBiCGSTABIstlSolver, then the factory's "AMGCG" and "SSORCG" (test/linear/params.input), each accepted if
+    `result.converged`; ProblemSize = 2 is the reference's value, 20 a grid with a real hierarchy.  The N x N Laplacian has the
+    pattern of the structured 2-D grid, so the AMG (which needs the grid) applies; also compared with the oracle's counts."""
+    from oracle import dist_oracle as D
+    spec = problems.twop_lens((N, N), law="vg")
+    ro = D.single_rank(spec)
+    rp, ci = ro.o.rowptr, ro.o.colidx
+    n = N * N
+    rows = np.repeat(np.arange(n), np.diff(rp))
+    vals = np.zeros((len(ci), 2, 2))
+    vals[rows == ci] = 4.0 * np.eye(2)
+    vals[rows != ci] = -1.0 * np.eye(2)
+    vals = vals.reshape(-1)
+    b = np.ones(n * 2)
+    e = engine_factory(spec)
+    for solver, krylov, pre, opre in (("AMGBiCGSTAB", "bicgstab", B.PRECOND_AMG, "amg"), ("AMGCG", "cg", B.PRECOND_AMG, "amg"),
+                                      ("SSORCG", "cg", B.PRECOND_SSOR, "ssor")):
+        e.set_linear_solver(krylov)
+        x, st, it, red = e.solve(vals, b, reduction=1e-13, maxit=250, precond=pre)
+        assert st == 0, f"{solver} did not converge!"
+        r = b - O.spmv(n, 2, rp, ci, vals, x)
+        assert np.linalg.norm(r) <= 1e-11 * np.linalg.norm(b), solver
+        xo, sto, ito, redo = (ro.bicgstab if krylov == "bicgstab" else ro.cg)(vals, b, 1e-13, 250, precond=opre)
+        assert sto == 0 and it == ito, (solver, it, ito)
+        assert np.linalg.norm(x - xo) <= 1e-10 * np.linalg.norm(xo)
+    e.set_linear_solver("bicgstab")
+
+
 def test_norm_dot_update(engine_factory):
     spec = problems.twop_lens((24, 16), law="vg")
     e = engine_factory(spec)
