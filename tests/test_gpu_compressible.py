@@ -65,6 +65,21 @@ def test_instationary_checkpoint_loop_matches_oracle_and_golden(engine_factory):
     assert np.abs(ug.ravel() / g - 1).max() < 1e-4
 
 
+def test_stationary_newton_matches_oracle_and_golden(engine_factory):
+    """test_1p_compressible_stationary_tpfa: one stationary Newton solve, compared by the reference with test_1p_cc-reference.vtu"""
+    import dataclasses
+    spec = problems.onep_compressible((10, 10))
+    spec.options = dataclasses.replace(spec.options, stationary=True)
+    uo, sto, repo = Oracle(spec).newton(spec.initial, spec.initial)
+    e = engine_factory(spec)
+    ug, stg, repg = e.newton(spec.initial, spec.initial)
+    assert sto == 0 and stg == 0 and repg.newton_iterations == repo.newton_iterations
+    assert np.linalg.norm(ug - uo) <= 1e-8 * np.linalg.norm(uo)
+    g = np.load(os.path.join(GOLDEN, "test_1p_cc.npz"))["p"].astype(np.float64)
+    d = np.abs(ug - g)
+    assert np.all(d <= 1e-2 * np.maximum(np.abs(ug), np.abs(g)))
+
+
 def test_newton_step_3d_lognormal(engine_factory):
     spec = problems.onep_compressible((24, 16, 20), lognormal=True, dt=0.002)
     uo, sto, repo = Oracle(spec).newton(spec.initial, spec.initial)

@@ -44,6 +44,20 @@ def test_1p_incompressible_10x10_reference_vtu():
     assert np.linalg.norm(r2) <= 1e-9 * np.linalg.norm(r0)
 
 
+def test_1p_compressible_stationary_reference_vtu():
+    """test_1p_compressible_stationary_tpfa (test/porousmediumflow/1p/compressible/stationary: the compressible 1p problem with
+    tabulated water solved as ONE stationary Newton solve with ILUBiCGSTABIstlSolver, main.cc:100-114) is compared by the reference
+    with the SAME test_1p_cc-reference.vtu as the incompressible test, at the fuzzy bar (relative 1e-2)."""
+    import dataclasses
+    spec = problems.onep_compressible((10, 10))
+    spec.options = dataclasses.replace(spec.options, stationary=True)
+    u, st, rep = Oracle(spec).newton(spec.initial, spec.initial)
+    assert st == 0 and 2 <= rep.newton_iterations <= 5
+    g = np.load(os.path.join(GOLDEN, "test_1p_cc.npz"))["p"].astype(np.float64)
+    assert _fuzzy_ok(u, g)
+    assert np.abs(u / g - 1).max() < 1e-4          # the water's compressibility moves the pressure by 2e-5 of its value
+
+
 def test_1p_incompressible_analytic_reference_vtu():
     """test_1p_incompressible_tpfa (DiffMethod::analytic, the reference's default for this test) -> the same
     test_1p_cc-reference.vtu; the analytic Jacobian (1p/incompressiblelocalresidual.hh:76-123,204-221) is exact, so it equals the
