@@ -439,6 +439,34 @@ def twop_lens(cells=(48, 32), law="vg", lower=None, upper=None, lens_lower=None,
 
 
 # ------------------------------------------------------------------------------------------------------
+# test/porousmediumflow/1p/pointsources/timeindependent (params.input, problem.hh:33-130, properties.hh:40-50):
+# incompressible 1p (SimpleH2O) on a 100 x 100 YaspGrid over [-1,1]^2, K = 1e-10, porosity 0.3, no gravity, Dirichlet p = 1e5 on the
+# whole boundary, a point source of 10 kg/s at the origin; one time step dt = 1 s.  The origin is a grid vertex: DuMux's point-source
+# helper divides the rate equally among the elements that contain the point (common/pointsource.hh BoundingBoxTreePointSourceHelper),
+# i.e. 2.5 kg/s for each of the four cells around it -- a source density q = rate / volume in those cells.
+# ------------------------------------------------------------------------------------------------------
+def onep_pointsource(cells=(100, 100), rate=10.0) -> ProblemSpec:
+    dim = 2
+    lower, upper = (-1.0, -1.0), (1.0, 1.0)
+    n = int(np.prod(cells))
+    bc_type, bc_values = {}, {}
+    for side in range(2 * dim):
+        fc = side_face_centers(cells, lower, upper, side)
+        bc_type[side] = np.full(fc.shape[0], BC_DIRICHLET, dtype=np.int32)
+        bc_values[side] = np.full((fc.shape[0], 1), 1.0e5)
+    ctr = cell_centers(cells, lower, upper)
+    h = [(upper[a] - lower[a]) / cells[a] for a in range(dim)]
+    holds = (np.abs(ctr[:, 0]) <= 0.5 * h[0] * (1 + 1e-9)) & (np.abs(ctr[:, 1]) <= 0.5 * h[1] * (1 + 1e-9))      # cells containing the origin
+    q = np.zeros((n, 1))
+    q[holds, 0] = rate / holds.sum() / (h[0] * h[1])
+    return ProblemSpec(
+        name="1p_pointsource", model=MODEL_1P, dim=dim, cells=tuple(cells), lower=lower, upper=upper,
+        K=np.full(n, 1e-10), phi=np.full(n, 0.3), region=np.zeros(n, dtype=np.int32), materials=[],
+        rho=(1000.0,), mu=(1e-3,), bc_type=bc_type, bc_values=bc_values,
+        options=Options(stationary=False, dt=1.0, enable_gravity=False), initial=np.full((n, 1), 1.0e5), source=q)
+
+
+# ------------------------------------------------------------------------------------------------------
 # test/porousmediumflow/2p/buckleyleverett (params.input, problem.hh:52-140, spatialparams.hh:40-100, properties.hh:52-82):
 # pseudo-1-D displacement of the non-wetting phase by water on a 100 x 1 YaspGrid over [0,100] x [0,75] m, no gravity,
 # BrooksCoreyDefault with lambda 4, entry pressure 0, Swr = Snr = 0.2, K = 1.01936799e-14, porosity 0.2, both fluids with

@@ -145,3 +145,20 @@ def test_line_search_and_residual_criteria_match_oracle(engine_factory):
     # the damped first step really happened
     uo, sto, repo, relax_o, red_o = o.newton_ex(hard, spec.initial, use_line_search=1)
     assert relax_o[0] < 1.0
+
+
+def test_1p_pointsource_golden(engine_factory):
+    """test_1p_pointsources_timeindependent_tpfa on the device (source term, all-Dirichlet boundary, AMGBiCGSTAB as in the
+    reference's main.cc:113) vs the oracle and vs test_1p_pointsources_timeindependent_cc-reference.vtu"""
+    from dumux_b200 import binding as B
+    spec = problems.onep_pointsource()
+    uo, sto, repo = Oracle(spec).newton(spec.initial, spec.initial)
+    e = engine_factory(spec)
+    ug, stg, repg = e.newton(spec.initial, spec.initial)
+    assert sto == 0 and stg == 0 and repg.newton_iterations == repo.newton_iterations
+    assert _rel_l2(ug, uo) <= 1e-8
+    ua, sta, repa = e.newton(spec.initial, spec.initial, preconditioner=B.PRECOND_AMG)
+    assert sta == 0 and _rel_l2(ua, uo) <= 1e-7
+    g = np.load(os.path.join(GOLDEN, "test_1p_pointsources_timeindependent_cc.npz"))["p"].astype(np.float64)
+    for u in (ug, ua):
+        assert np.abs(u / g - 1).max() < 1e-5

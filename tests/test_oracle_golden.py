@@ -58,6 +58,19 @@ def test_1p_compressible_stationary_reference_vtu():
     assert np.abs(u / g - 1).max() < 1e-4          # the water's compressibility moves the pressure by 2e-5 of its value
 
 
+def test_1p_pointsource_reference_vtu():
+    """test_1p_pointsources_timeindependent_tpfa -> test_1p_pointsources_timeindependent_cc-reference.vtu: 10 kg/s at a grid vertex,
+    shared by the four cells around it (pointsource.hh); pins the source term of the local residual (fvlocalresidual.hh:319-333)"""
+    spec = problems.onep_pointsource()
+    assert int((spec.source[:, 0] > 0).sum()) == 4
+    u, st, rep = Oracle(spec).newton(spec.initial, spec.initial)
+    assert st == 0
+    g = np.load(os.path.join(GOLDEN, "test_1p_pointsources_timeindependent_cc.npz"))["p"].astype(np.float64)
+    assert _fuzzy_ok(u, g)
+    assert np.abs(u / g - 1).max() < 1e-5          # Float32 storage of the file
+    assert u.max() > 1.6e5 and np.argmax(u) in np.flatnonzero(spec.source[:, 0] > 0)
+
+
 def test_1p_incompressible_analytic_reference_vtu():
     """test_1p_incompressible_tpfa (DiffMethod::analytic, the reference's default for this test) -> the same
     test_1p_cc-reference.vtu; the analytic Jacobian (1p/incompressiblelocalresidual.hh:76-123,204-221) is exact, so it equals the
