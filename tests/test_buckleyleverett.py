@@ -42,25 +42,36 @@ def test_buckleyleverett_oracle_meets_the_reference_criterion():
 
 @pytest.mark.gpu
 def test_buckleyleverett_device_matches_oracle_and_reference_criterion(engine_factory):
+    import dataclasses
     from dumux_b200 import binding as B
     spec = problems.twop_buckleyleverett()
     o = Oracle(spec)
     uo, nso, itso, dtso = o.run_timeloop(spec.initial, T_END, DT0, MAX_DT)
+    # (1) step-wise parity: every one of the first time steps, started from the oracle's state, is the same Newton solve on the
+    # device -- bit-identical assembly, same iteration count, same shifts, same fields
+    u = spec.initial.reshape(-1).copy()
+    for k in range(6):
+        sp = dataclasses.replace(spec, options=dataclasses.replace(spec.options, dt=float(dtso[k])))
+        ok = Oracle(sp)
+        e = engine_factory(sp)
+        ro, jo = ok.assemble(u, u)
+        rg, jg = e.assemble(u.reshape(-1, 2), u.reshape(-1, 2))
+        assert np.array_equal(ro, rg) and np.array_equal(jo, jg), k
+        un, sto, repo = ok.newton(u, u)
+        ug, stg, repg = e.newton(u.reshape(-1, 2), u.reshape(-1, 2))
+        assert sto == 0 and stg == 0 and repg.newton_iterations == repo.newton_iterations == itso[k], k
+        assert np.linalg.norm(ug - un) <= 1e-12 * np.linalg.norm(un)
+        e.close()
+        u = un
+    # (2) the whole device-resident run.  With zero entry pressure the pressure field is fixed by the fluxes alone and the last
+    # Newton update of a step is rounding noise of the size of the shift criterion (1.7e-8 against 4e-9 from start states that
+    # differ by 5e-10 Pa), so the Newton counts of a 36-step run -- and with them the step sizes -- are not reproducible between two
+    # implementations (or two compilers); the reference's own criterion is what such a run is judged by.
     e = engine_factory(spec)
-    ug, itsg, dtsg = e.run_timeloop(spec.initial, T_END, DT0, MAX_DT)
-    assert list(itsg) == list(itso), (itsg, itso)
-    assert np.allclose(dtsg, dtso, rtol=0, atol=0)
-    a, b = ug.reshape(-1, 2), uo.reshape(-1, 2)
-    assert np.linalg.norm(a[:, 0] - b[:, 0]) <= 1e-8 * np.linalg.norm(b[:, 0])
-    assert np.linalg.norm(a[:, 1] - b[:, 1]) <= 1e-8 * np.linalg.norm(b[:, 1])
     ana = _analytic(o)
-    err_com, err_mass = ana.check(spec, ug, T_END)
-    assert err_com <= MAX_REL_ERROR and err_mass <= MAX_REL_ERROR, (err_com, err_mass)
-    # ... and with the linear solver of the reference's main.cc:78 (AMGBiCGSTABIstlSolver)
-    ua, itsa, dtsa = e.run_timeloop(spec.initial, T_END, DT0, MAX_DT, preconditioner=B.PRECOND_AMG)
-    assert abs(len(itsa) - len(itsg)) <= 3 and np.isclose(np.sum(dtsa), T_END, rtol=1e-12)
-    err_com, err_mass = ana.check(spec, ua, T_END)
-    assert err_com <= MAX_REL_ERROR and err_mass <= MAX_REL_ERROR, (err_com, err_mass)
-    # (a Newton count that differs in one step changes the later step sizes, so the two runs agree to the time-discretisation
-    # error, not to the solver tolerance)
-    assert np.abs(ua.reshape(-1, 2)[:, 1] - a[:, 1]).max() <= 0.05
+    for kw in ({}, {"preconditioner": B.PRECOND_AMG}):          # ILU0-BiCGSTAB, and the reference's AMGBiCGSTABIstlSolver (main.cc:78)
+        ug, itsg, dtsg = e.run_timeloop(spec.initial, T_END, DT0, MAX_DT, **kw)
+        assert abs(len(itsg) - nso) <= 4 and np.isclose(np.sum(dtsg), T_END, rtol=1e-12) and np.max(dtsg) <= MAX_DT * (1 + 1e-12)
+        err_com, err_mass = ana.check(spec, ug, T_END)
+        assert err_com <= MAX_REL_ERROR and err_mass <= MAX_REL_ERROR, (kw, err_com, err_mass)
+        assert np.abs(ug.reshape(-1, 2)[:, 1] - uo.reshape(-1, 2)[:, 1]).max() <= 0.05
