@@ -597,6 +597,69 @@ def run_threads(make_spec, cells, nranks, fn, part=None, num_threads=0, gpu_redu
     return out
 
 
+def native_schwarz_bicgstab(cells, part, b, systems, reduction=1e-6, maxit=250):
+    """dist_oracle.BoxRank.bicgstab for ALL ranks at once in native code (oracle.cpp orc_schwarz_ilu0_bicgstab: one OpenMP
+    thread per rank, no interpreter in the loop) -- what bench.py's CPU arms time.  `systems[r]` = (rowptr, colidx, values, rhs)
+    of rank r's local box (overlap rows included); returns (x per rank, status, iterations, achieved reduction, seconds)."""
+    import ctypes as C
+    dim = len(cells)
+    part = tuple(part) if part is not None else problems.default_partitioning(dim, len(systems))
+    nranks = int(np.prod(part))
+    assert nranks == len(systems)
+    part3 = tuple(part) + (1,) * (3 - dim)
+    c3 = tuple(cells) + (1,) * (3 - dim)
+    rngs = [problems.box_partition(cells, part, r) + [(0, 1, 0, 1)] * (3 - dim) for r in range(nranks)]
+    # owner coordinate of every global index per axis
+    owner_coord = []
+    for a in range(3):
+        oc = np.zeros(c3[a], dtype=np.int64)
+        for c in range(part3[a]):
+            lo, hi, b0, b1 = problems.axis_partition(c3[a], part3[a], c)
+            oc[b0:b1] = c
+        owner_coord.append(oc)
+    owners, dsts, src_ranks, src_idxs, ns = [], [], [], [], []
+    for r in range(nranks):
+        rg = rngs[r]
+        gi = [np.arange(rg[a][0], rg[a][1]) for a in range(3)]
+        lc = [g.size for g in gi]
+        own1 = [(gi[a] >= rg[a][2]) & (gi[a] < rg[a][3]) for a in range(3)]
+        own = (own1[2][:, None, None] & own1[1][None, :, None] & own1[0][None, None, :]).reshape(-1)
+        K, J, I = np.meshgrid(gi[2], gi[1], gi[0], indexing="ij")
+        K, J, I = K.reshape(-1)[~own], J.reshape(-1)[~own], I.reshape(-1)[~own]
+        oc = [owner_coord[0][I], owner_coord[1][J], owner_coord[2][K]]
+        orank = oc[0] + part3[0] * (oc[1] + part3[1] * oc[2])
+        sidx = np.zeros(orank.size, dtype=np.int64)
+        for q in np.unique(orank):
+            m = orank == q
+            rq = rngs[int(q)]
+            nxq, nyq = rq[0][1] - rq[0][0], rq[1][1] - rq[1][0]
+            sidx[m] = (I[m] - rq[0][0]) + nxq * ((J[m] - rq[1][0]) + nyq * (K[m] - rq[2][0]))
+        owners.append(np.ascontiguousarray(own, dtype=np.uint8))
+        dsts.append(np.ascontiguousarray(np.flatnonzero(~own), dtype=np.int32))
+        src_ranks.append(np.ascontiguousarray(orank, dtype=np.int32))
+        src_idxs.append(np.ascontiguousarray(sidx, dtype=np.int32))
+        ns.append(int(np.prod(lc)))
+    rps = [np.ascontiguousarray(s_[0], dtype=np.int32) for s_ in systems]
+    cis = [np.ascontiguousarray(s_[1], dtype=np.int32) for s_ in systems]
+    vals = [np.ascontiguousarray(s_[2], dtype=np.float64) for s_ in systems]
+    rhss = [np.ascontiguousarray(s_[3], dtype=np.float64) for s_ in systems]
+    xs = [np.zeros(ns[r] * b) for r in range(nranks)]
+    assert all(rps[r].size == ns[r] + 1 for r in range(nranks))
+
+    def ptrs(arrs, ctype):
+        return (C.POINTER(ctype) * nranks)(*[a.ctypes.data_as(C.POINTER(ctype)) for a in arrs])
+
+    its, ach, secs = C.c_int(0), C.c_double(0.0), C.c_double(0.0)
+    L = O.lib()
+    L.orc_schwarz_ilu0_bicgstab.restype = C.c_int
+    st = L.orc_schwarz_ilu0_bicgstab(
+        C.c_int(nranks), C.c_int(b), (C.c_int * nranks)(*ns), ptrs(rps, C.c_int), ptrs(cis, C.c_int), ptrs(vals, C.c_double),
+        ptrs(xs, C.c_double), ptrs(rhss, C.c_double), ptrs(owners, C.c_ubyte), (C.c_int * nranks)(*[d.size for d in dsts]),
+        ptrs(dsts, C.c_int), ptrs(src_ranks, C.c_int), ptrs(src_idxs, C.c_int), C.c_double(reduction), C.c_int(maxit),
+        C.byref(its), C.byref(ach), C.byref(secs))
+    return xs, int(st), its.value, ach.value, secs.value
+
+
 def gather_owned(results, cells, nranks, b, part=None):
     """Assemble the owned blocks of per-rank local vectors (x fastest) into the global vector."""
     dim = len(cells)

@@ -1531,6 +1531,83 @@ int orc_ilu0_bicgstab(int n, int b, const int* rowptr, const int* colidx, const 
         [&](const double* a, const double* c) { return dot(N, a, c); }, x, rhs, reduction, maxit, iterations, achieved);
 }
 
+// The same solver on P MPI ranks, the way DuMux runs it on a decomposed grid (linear/linearsolvertraits.hh:79-91 +
+// istlsolvers.hh:550-566): dune-istl's OverlappingSchwarzOperator (local mv, then project = zero the non-owner entries),
+// OverlappingSchwarzScalarProduct (owner-masked dot + global sum) and BlockPreconditioner (local SeqILU, then copyOwnerToAll)
+// around the SAME BiCGSTABSolver::apply.  The ranks are OpenMP threads of this process (no MPI in this image): every thread runs
+// bicgstab() on its local box, collectives are a shared slot per rank and a barrier, the global sum adds the per-rank values in
+// rank order.  copyOwnerToAll is a copy list per rank: local cell `dst` takes the value of cell `src_idx` of rank `src_rank`
+// (its owner).  Used by bench.py's CPU arms: one native thread per rank, no interpreter in the loop.
+// x[r] / rhs[r]: local vectors of rank r (rhs may hold the incomplete residual rows of the overlap cells: they are projected out).
+int orc_schwarz_ilu0_bicgstab(int nranks, int b, const int* n, const int* const* rowptr, const int* const* colidx,
+                              const double* const* values, double* const* x, const double* const* rhs,
+                              const unsigned char* const* owner, const int* ncopy, const int* const* copy_dst,
+                              const int* const* copy_src_rank, const int* const* copy_src_idx, double reduction, int maxit,
+                              int* iterations, double* achieved, double* seconds)
+{
+    std::vector<double> red(nranks, 0.0);
+    std::vector<const double*> vec(nranks, nullptr);
+    std::vector<int> status(nranks, 0), its(nranks, 0), bad(nranks, 0);
+    std::vector<double> ach(nranks, 1.0), secs(nranks, 0.0);
+#pragma omp parallel num_threads(nranks)
+    {
+        const int r = omp_get_thread_num();
+        const int nr = n[r];
+        const size_t N = (size_t)nr * b;
+        const unsigned char* own = owner[r];
+        std::vector<double> ilu((size_t)rowptr[r][nr] * b * b);
+        std::memcpy(ilu.data(), values[r], sizeof(double) * ilu.size());
+        std::vector<double> rhsP(rhs[r], rhs[r] + N);
+        for (int i = 0; i < nr; ++i)
+            if (!own[i]) for (int e = 0; e < b; ++e) rhsP[(size_t)i * b + e] = 0.0;      // applyscaleadd(-1, x, r) projects r
+#pragma omp barrier
+        const double t0 = omp_get_wtime();
+        bad[r] = ilu0Factor(nr, b, rowptr[r], colidx[r], ilu.data());
+#pragma omp barrier
+        int anyBad = 0;
+        for (int q = 0; q < nranks; ++q) anyBad |= bad[q];
+        if (anyBad) {
+            status[r] = 2;
+        } else {
+            auto op = [&](const double* in, double* out) {
+                spmv(nr, b, rowptr[r], colidx[r], values[r], in, out);
+                for (int i = 0; i < nr; ++i)
+                    if (!own[i]) for (int e = 0; e < b; ++e) out[(size_t)i * b + e] = 0.0;
+            };
+            auto prec = [&](double* v, const double* d) {
+                ilu0Apply(nr, b, rowptr[r], colidx[r], ilu.data(), v, d);
+                vec[r] = v;
+#pragma omp barrier
+                for (int k = 0; k < ncopy[r]; ++k) {
+                    const double* src = vec[copy_src_rank[r][k]] + (size_t)copy_src_idx[r][k] * b;
+                    double* dst = v + (size_t)copy_dst[r][k] * b;
+                    for (int e = 0; e < b; ++e) dst[e] = src[e];
+                }
+#pragma omp barrier
+            };
+            auto sp = [&](const double* a, const double* c) {
+                double s = 0.0;
+                for (int i = 0; i < nr; ++i)
+                    if (own[i]) for (int e = 0; e < b; ++e) s += a[(size_t)i * b + e] * c[(size_t)i * b + e];
+                red[r] = s;
+#pragma omp barrier
+                double total = red[0];
+                for (int q = 1; q < nranks; ++q) total = total + red[q];
+#pragma omp barrier
+                return total;
+            };
+            status[r] = bicgstab(N, op, prec, sp, x[r], rhsP.data(), reduction, maxit, &its[r], &ach[r]);
+        }
+        secs[r] = omp_get_wtime() - t0;
+    }
+    *iterations = its[0];
+    *achieved = ach[0];
+    double smax = 0.0;
+    for (int q = 0; q < nranks; ++q) smax = std::max(smax, secs[q]);
+    if (seconds) *seconds = smax;
+    return status[0];
+}
+
 // ILURestartedGMResIstlSolver (dumux/linear/istlsolvers.hh:660-667): SeqILU(0) + Dune::RestartedGMResSolver,
 // restart = LinearSolver.GMResRestart (default 10, linearsolverparameters.hh:115-116,138)
 int orc_ilu0_gmres(int n, int b, const int* rowptr, const int* colidx, const double* values, double* x, const double* rhs,

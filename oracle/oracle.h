@@ -78,6 +78,12 @@ void orc_assemble(orc_problem* p, const double* cur, const double* prev, double*
 void orc_volvars(orc_problem* p, const double* cur, double* out);
 
 /* dune-istl restatement. x: in initial guess / out solution; b is NOT modified. status 0 ok, 1 not converged, 2 breakdown, 3 non-finite */
+/* the same solver on `nranks` overlapping-Schwarz ranks (OpenMP threads of this process), see oracle.cpp */
+int  orc_schwarz_ilu0_bicgstab(int nranks, int b, const int* n, const int* const* rowptr, const int* const* colidx,
+                               const double* const* values, double* const* x, const double* const* rhs,
+                               const unsigned char* const* owner, const int* ncopy, const int* const* copy_dst,
+                               const int* const* copy_src_rank, const int* const* copy_src_idx, double reduction, int maxit,
+                               int* iterations, double* achieved, double* seconds);
 int  orc_ilu0_bicgstab(int n, int b, const int* rowptr, const int* colidx, const double* values,
                        double* x, const double* rhs, double reduction, int maxit,
                        int* iterations, double* achieved_reduction);

@@ -282,6 +282,26 @@ def test_amg_hierarchy_of_a_decomposition_tiles_the_global_levels():
     assert int(np.prod(out[0][-1][0])) <= 8 or out[0][-1][0] == part
 
 
+@pytest.mark.parametrize("part", [None] + BLOCK_PARTS)
+def test_native_multi_rank_solver_equals_the_python_ranks(reference_runs, block_runs, part):
+    """oracle.cpp orc_schwarz_ilu0_bicgstab (what bench.py's CPU arm times: one OpenMP thread per rank) against
+    BoxRank.bicgstab rank by rank: same iteration count (+-1: the C dot sums the owned entries sequentially, numpy's in blocks),
+    same solution incl. the overlap copies"""
+    from oracle.amg_oracle import grid_pattern
+    runs = reference_runs[1] if part is None else block_runs[part]
+    part_ = part if part is not None else problems.default_partitioning(3, 2)
+    P = int(np.prod(part_))
+    systems = []
+    for r in range(P):
+        rng = problems.box_partition(CELLS, part_, r)
+        rp, ci = grid_pattern(tuple(x[1] - x[0] for x in rng), 3)
+        systems.append((rp, ci, runs[r]["jac"], runs[r]["res"]))
+    xs, st, its, red, secs = D.native_schwarz_bicgstab(CELLS, part_, 2, systems, 1e-11, 500)
+    assert st == 0 and abs(its - runs[0]["its"]) <= 1 and red <= 1e-11 and secs > 0
+    for r in range(P):
+        assert np.linalg.norm(xs[r] - runs[r]["x"]) <= 1e-8 * np.linalg.norm(runs[r]["x"])
+
+
 def test_four_processes_over_gloo_block_partition(block_runs):
     """world_size 4 over gloo with Grid.Partitioning "2 1 2": identical to the in-process reference (real messages to face and
     edge neighbours)."""
