@@ -25,7 +25,7 @@ EXPORTS = [
     "dmx_local_box3", "dmx_set_partitioning", "dmx_set_preconditioner_params", "dmx_precond_apply",
     "dmx_default_amg_params", "dmx_set_amg_params", "dmx_amg_level_profile", "dmx_amg_levels", "dmx_amg_level_cells", "dmx_amg_level_nnz_blocks", "dmx_amg_level_matrix",
     "dmx_num_cells", "dmx_num_eq", "dmx_nnz_blocks", "dmx_pattern", "dmx_bcrs_pattern", "dmx_set_options",
-    "dmx_set_cell_fields", "dmx_set_source", "dmx_set_material", "dmx_set_fluids", "dmx_set_fluid_table",
+    "dmx_set_cell_fields", "dmx_set_permeability_diagonal", "dmx_set_source", "dmx_set_material", "dmx_set_fluids", "dmx_set_fluid_table",
     "dmx_side_faces", "dmx_set_boundary", "dmx_vec_upload", "dmx_vec_download", "dmx_vec_copy", "dmx_jacobian_upload",
     "dmx_jacobian_download", "dmx_vec_device_ptr", "dmx_jacobian_device_ptr", "dmx_assemble", "dmx_assemble_host",
     "dmx_linear_solve", "dmx_linear_solve_host", "dmx_norm2", "dmx_newton_update", "dmx_newton_solve",
@@ -110,6 +110,7 @@ def load_library():
     L.dmx_bcrs_pattern.argtypes = [vp, C.c_int, C.c_int, _ip, _ip]
     L.dmx_set_options.argtypes = [vp, C.POINTER(DmxOptions)]
     L.dmx_set_cell_fields.argtypes = [vp, _dp, _dp, _ip]
+    L.dmx_set_permeability_diagonal.argtypes = [vp, C.c_void_p, C.c_void_p, C.c_void_p]
     L.dmx_set_source.argtypes = [vp, _dp]
     L.dmx_set_material.argtypes = [vp, C.c_int, C.c_int, _dp, C.c_double, C.c_double, C.c_int, _dp]
     L.dmx_set_fluids.argtypes = [vp, _dp, _dp]
@@ -267,8 +268,13 @@ class Engine:
         self.opt.dt = o.dt
         self.opt.extrusion = o.extrusion
         self._check(L.dmx_set_options(self.h, C.byref(self.opt)))
-        self._check(L.dmx_set_cell_fields(self.h, self.localize_cells(spec.K), self.localize_cells(spec.phi),
+        K = self.localize_cells(np.asarray(spec.K, dtype=np.float64))
+        self._check(L.dmx_set_cell_fields(self.h, np.ascontiguousarray(K if K.ndim == 1 else K[:, spec.dim - 1]), self.localize_cells(spec.phi),
                                           self.localize_cells(spec.region.astype(np.int32))))
+        if K.ndim == 2:          # diagonal permeability tensor: K[:, a] = K_aa (dmx_set_permeability_diagonal)
+            ks = [np.ascontiguousarray(K[:, a]) for a in range(spec.dim)]
+            ptr = [k.ctypes.data_as(C.c_void_p) for k in ks] + [None] * (3 - spec.dim)
+            self._check(L.dmx_set_permeability_diagonal(self.h, *ptr))
         for r, m in enumerate(spec.materials):
             reg = np.ascontiguousarray(m.reg if len(m.reg) else [0.01, 0.99, 0.1, 0.9], dtype=np.float64)
             self._check(L.dmx_set_material(self.h, r, m.law, np.ascontiguousarray(m.params, dtype=np.float64),

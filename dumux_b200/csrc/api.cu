@@ -188,6 +188,7 @@ int finish_grid(dmx_ctx* ctx, int model, int dim, const int* cells, const std::v
     if (int rc = up(&ctx->d_region, ctx->h_region)) return rc;
     if (ctx->d_q) { cudaFree(ctx->d_q); ctx->d_q = nullptr; }
     for (int a = 0; a < 3; ++a) if (ctx->d_tij[a]) { cudaFree(ctx->d_tij[a]); ctx->d_tij[a] = nullptr; }
+    for (int a = 0; a < 3; ++a) if (ctx->d_Kaxis[a]) { cudaFree(ctx->d_Kaxis[a]); ctx->d_Kaxis[a] = nullptr; }
     if (ctx->d_law_rec) { cudaFree(ctx->d_law_rec); ctx->d_law_rec = nullptr; }
     if (int rc = upload_pattern(ctx)) return rc;
     if (int rc = alloc_vectors(ctx)) return rc;
@@ -328,7 +329,8 @@ int dmx_destroy(dmx_ctx* ctx)
     void* ptrs[] = {ctx->d_geom, ctx->d_K, ctx->d_phi, ctx->d_q, ctx->d_region, ctx->d_tij[0], ctx->d_tij[1], ctx->d_tij[2], ctx->d_laws,
                     ctx->d_tab_buf, ctx->d_rowptr, ctx->d_colidx, ctx->d_diag, ctx->d_J, ctx->d_ilu, ctx->d_rt, ctx->d_p, ctx->d_v, ctx->d_t,
                     ctx->d_y, ctx->d_z, ctx->d_dinv, ctx->d_gm, ctx->d_vf, ctx->d_color_rows, ctx->d_xold, ctx->d_lrows, ctx->d_urows, ctx->d_lptr, ctx->d_uptr, ctx->d_barrier, ctx->d_partials,
-                    ctx->d_scalars, ctx->d_flag, ctx->d_owner, ctx->d_send, ctx->d_recv, ctx->d_gather, ctx->d_law_rec};
+                    ctx->d_scalars, ctx->d_flag, ctx->d_owner, ctx->d_send, ctx->d_recv, ctx->d_gather, ctx->d_law_rec,
+                    ctx->d_Kaxis[0], ctx->d_Kaxis[1], ctx->d_Kaxis[2]};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int v = 0; v < DMX_NUM_VECS; ++v) if (ctx->d_vec[v]) cudaFree(ctx->d_vec[v]);
     for (int s = 0; s < 6; ++s) {
@@ -450,6 +452,29 @@ int dmx_set_cell_fields(dmx_ctx* ctx, const double* K, const double* phi, const 
         DMX_CUDA(cudaMemcpy(ctx->d_region, region, n * sizeof(int), cudaMemcpyHostToDevice));
     }
     ctx->prepared = false;
+    return 0;
+}
+int dmx_set_permeability_diagonal(dmx_ctx* ctx, const double* kx, const double* ky, const double* kz)
+{
+    if (!ctx->has_grid) return fail(ctx, DMX_ERR_USAGE, "set grid first");
+    DMX_CUDA(cudaSetDevice(ctx->device));
+    const double* k[3] = {kx, ky, kz};
+    const size_t n = (size_t)ctx->n;
+    bool any = false;
+    for (int a = 0; a < ctx->dim; ++a) any = any || k[a];
+    for (int a = 0; a < 3; ++a)
+        if (ctx->d_Kaxis[a]) { cudaFree(ctx->d_Kaxis[a]); ctx->d_Kaxis[a] = nullptr; }
+    ctx->prepared = false;
+    if (!any) return 0;
+    for (int a = 0; a < ctx->dim; ++a) {
+        if (!k[a]) return fail(ctx, DMX_ERR_USAGE, "permeability_diagonal: one array per grid axis");
+        DMX_CUDA(cudaMalloc((void**)&ctx->d_Kaxis[a], n * sizeof(double)));
+        DMX_CUDA(cudaMemcpy(ctx->d_Kaxis[a], k[a], n * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    // the scalar field keeps the entry along the gravity axis (what the gravity terms of the vertical faces use)
+    const int va = ctx->dim - 1;
+    ctx->h_K.assign(k[va], k[va] + n);
+    DMX_CUDA(cudaMemcpy(ctx->d_K, k[va], n * sizeof(double), cudaMemcpyHostToDevice));
     return 0;
 }
 int dmx_set_source(dmx_ctx* ctx, const double* q)

@@ -28,6 +28,12 @@ namespace dmx {
 // ------------------------------------------------------------------------------------------------
 // setup: transmissibilities of the +faces.  tij = A * ti*tj/(ti+tj) (0 if ti*tj <= 0)
 // ------------------------------------------------------------------------------------------------
+// permeability entering a face with normal e_a: K_aa of a diagonal tensor, else the scalar
+__device__ __forceinline__ double perm_axis(const AsmParams& P, int a, size_t C, double Kscalar)
+{
+    return P.Kaxis[a] ? __ldg(P.Kaxis[a] + C) : Kscalar;
+}
+
 __global__ void transmissibility_kernel(AsmParams P, double* t0, double* t1, double* t2)
 {
     const int I = blockIdx.x * blockDim.x + threadIdx.x;
@@ -45,8 +51,8 @@ __global__ void transmissibility_kernel(AsmParams P, double* t0, double* t1, dou
             double area = 1.0;
             for (int d = 0; d < P.dim; ++d)
                 if (d != a) area *= P.width[d][c[d]];
-            const double ti = KI * P.extrusion * P.gf_hi[a][c[a]];
-            const double tj = P.K[I + stride[a]] * P.extrusion * P.gf_lo[a][c[a] + 1];
+            const double ti = perm_axis(P, a, I, KI) * P.extrusion * P.gf_hi[a][c[a]];
+            const double tj = perm_axis(P, a, I + stride[a], P.K[I + stride[a]]) * P.extrusion * P.gf_lo[a][c[a] + 1];
             if (ti * tj <= 0.0) tij = 0;
             else tij = area * (ti * tj) / (ti + tj);
         }
@@ -538,7 +544,7 @@ __global__ void __launch_bounds__(AT_THREADS, (ND == 1) ? 2 : 1) assemble_tile_k
                     const int type = P.bc_type[s] ? P.bc_type[s][f] : DMX_BC_NEUMANN;
                     if (type == DMX_BC_DIRICHLET) {
                         F.interior = false;
-                        const double ti = KI * extr * (hi ? P.gf_hi[a][ci[a]] : P.gf_lo[a][ci[a]]);
+                        const double ti = perm_axis(P, a, I, KI) * extr * (hi ? P.gf_hi[a][ci[a]] : P.gf_lo[a][ci[a]]);
                         F.tij = area * ti;
                         CellState<NPH> sD;
 #pragma unroll
@@ -697,7 +703,7 @@ __global__ void __launch_bounds__(256) onep_analytic_jacobian_kernel(const AsmPa
                 if (a != 0) area *= P.width[0][ci[0]];
                 if (a != 1 && DIM > 1) area *= P.width[1][ci[1]];
                 if (a != 2 && DIM > 2) area *= P.width[2][ci[2]];
-                const double ti = P.K[I] * P.extrusion * (hi ? P.gf_hi[a][ci[a]] : P.gf_lo[a][ci[a]]);
+                const double ti = perm_axis(P, a, I, P.K[I]) * P.extrusion * (hi ? P.gf_hi[a][ci[a]] : P.gf_lo[a][ci[a]]);
                 diag += (area * ti) * up;
             }
         }
@@ -839,7 +845,7 @@ __global__ void __launch_bounds__(128) twop_analytic_jacobian_kernel(const AsmPa
             const int type = P.bc_type[s] ? P.bc_type[s][f_] : DMX_BC_NEUMANN;
             if (type != DMX_BC_DIRICHLET) continue;
             boundary = true;
-            const double ti = sI.K * extr * (hi ? P.gf_hi[a][ci[a]] : P.gf_lo[a][ci[a]]);
+            const double ti = perm_axis(P, a, I, sI.K) * extr * (hi ? P.gf_hi[a][ci[a]] : P.gf_lo[a][ci[a]]);
             tij = area * ti;
 #pragma unroll
             for (int ph = 0; ph < 2; ++ph) {
@@ -949,7 +955,7 @@ __global__ void __launch_bounds__(256) volume_flux_kernel(const AsmParams P, dou
                 const double pD = P.bc_p[s][(size_t)fidx * 2];
                 double rhoD, mobD;
                 fluid(pD, &rhoD, &mobD);
-                const double ti = KI * extr * (hi ? P.gf_hi[a][ci[a]] : P.gf_lo[a][ci[a]]);
+                const double ti = perm_axis(P, a, I, KI) * extr * (hi ? P.gf_hi[a][ci[a]] : P.gf_lo[a][ci[a]]);
                 const double tij = area * ti;
                 double f = tij * (pI - pD);
                 if (grav) f = f + rhoD * area * alphaI;
@@ -1112,6 +1118,7 @@ static void fill_params(dmx_ctx* ctx, AsmParams& P)
     P.gravity = o.gravity; P.upwind_weight = o.upwind_weight; P.base_eps = o.base_eps;
     P.mag[0] = o.privar_magnitude[0]; P.mag[1] = o.privar_magnitude[1];
     P.dt = o.dt; P.extrusion = o.extrusion;
+    for (int a = 0; a < 3; ++a) P.Kaxis[a] = ctx->d_Kaxis[a];
     P.K = ctx->d_K; P.phi = ctx->d_phi; P.region = ctx->d_region; P.q = ctx->d_q;
     for (int i = 0; i < 2; ++i) { P.rho[i] = ctx->rho[i]; P.mu[i] = ctx->mu[i]; P.rmu[i] = 1.0 / ctx->mu[i]; }
     P.rdt = 1.0 / o.dt;

@@ -31,7 +31,8 @@ struct AsmParams {
     const double* gf_lo[3];
     const double* gf_hi[3];
     // cell fields
-    const double* K;
+    const double* K;          // scalar permeability; with a diagonal tensor: its entry along the gravity axis
+    const double* Kaxis[3];   // diagonal tensor: K_aa per axis, null = scalar K
     const double* phi;
     const int* region;
     const double* q;          // may be null
@@ -104,6 +105,7 @@ struct dmx_ctx {
     std::vector<double> h_K, h_phi;
     std::vector<int> h_region;
     double *d_K = nullptr, *d_phi = nullptr, *d_q = nullptr;
+    double* d_Kaxis[3] = {nullptr, nullptr, nullptr};      // diagonal permeability tensor (dmx_set_permeability_diagonal), null = scalar
     int* d_region = nullptr;
     double* d_tij[3] = {nullptr, nullptr, nullptr};
     double* d_vf = nullptr;             // tracer: frozen volume fluxes [n][2*dim]

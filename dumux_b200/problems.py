@@ -439,6 +439,51 @@ def twop_lens(cells=(48, 32), law="vg", lower=None, upper=None, lens_lower=None,
 
 
 # ------------------------------------------------------------------------------------------------------
+# test/porousmediumflow/1p/convergence/analyticsolution (test_1p_convergence_analytic_tpfa_structured: params.input with
+# -Problem.C 0.0, problem.hh:60-150, spatialparams.hh:60-75): stationary incompressible 1p on [0,1]^2 with density 1 and kinematic
+# viscosity 1, the permeability TENSOR K = [[1, -c/(2w) sin(wx)], [-c/(2w) sin(wx), exp(-2)(1 + c cos(wx))]], w = pi, which for the
+# structured TPFA variant (c = 0) is the diagonal tensor diag(1, exp(-2)); Dirichlet values from the analytic pressure
+# p = (exp(y+1) + 2 - exp(2)) sin(wx) + 10 on the whole boundary and the matching source term.  The reference runs refinements
+# 0..3 of a 10 x 10 grid and accepts a mean convergence rate of the discrete L2 error >= 1.8 (convergencetest.py).
+# ------------------------------------------------------------------------------------------------------
+def onep_convergence_exact(x, y):
+    return (np.exp(y + 1.0) + 2.0 - np.exp(2.0)) * np.sin(np.pi * x) + 10.0
+
+
+def onep_convergence(cells=(10, 10)) -> ProblemSpec:
+    dim = 2
+    lower, upper = (0.0, 0.0), (1.0, 1.0)
+    n = int(np.prod(cells))
+    om = np.pi
+    ctr = cell_centers(cells, lower, upper)
+    x, y = ctr[:, 0], ctr[:, 1]
+    q = np.zeros((n, 1))
+    q[:, 0] = (-(0.0 * np.cos(om * x) + 1.0) * np.exp(y - 1.0) + 1.5 * 0.0 * np.exp(y + 1.0) * np.cos(om * x)
+               + om * om * (np.exp(y + 1.0) - np.exp(2.0) + 2.0)) * np.sin(om * x)
+    K = np.empty((n, 2))
+    K[:, 0] = 1.0
+    K[:, 1] = np.exp(-2.0)
+    bc_type, bc_values = {}, {}
+    for side in range(2 * dim):
+        fc = side_face_centers(cells, lower, upper, side)
+        bc_type[side] = np.full(fc.shape[0], BC_DIRICHLET, dtype=np.int32)
+        bc_values[side] = onep_convergence_exact(fc[:, 0], fc[:, 1]).reshape(-1, 1)
+    return ProblemSpec(
+        name="1p_convergence", model=MODEL_1P, dim=dim, cells=tuple(cells), lower=lower, upper=upper,
+        K=K, phi=np.full(n, 1.0), region=np.zeros(n, dtype=np.int32), materials=[],
+        rho=(1.0,), mu=(1.0,), bc_type=bc_type, bc_values=bc_values,
+        options=Options(stationary=True, enable_gravity=False), initial=np.zeros((n, 1)), source=q)
+
+
+def onep_convergence_l2_error(spec, p):
+    """main.cc:39-57: sqrt(sum_scv volume (p_h - p_exact(dofPosition))^2)"""
+    ctr = cell_centers(spec.cells, spec.lower, spec.upper)
+    vol = np.prod([(spec.upper[a] - spec.lower[a]) / spec.cells[a] for a in range(spec.dim)])
+    d = np.asarray(p).reshape(-1) - onep_convergence_exact(ctr[:, 0], ctr[:, 1])
+    return float(np.sqrt(np.sum(vol * d * d)))
+
+
+# ------------------------------------------------------------------------------------------------------
 # test/porousmediumflow/1p/pointsources/timeindependent (params.input, problem.hh:33-130, properties.hh:40-50):
 # incompressible 1p (SimpleH2O) on a 100 x 100 YaspGrid over [-1,1]^2, K = 1e-10, porosity 0.3, no gravity, Dirichlet p = 1e5 on the
 # whole boundary, a point source of 10 kg/s at the origin; one time step dt = 1 s.  The origin is a grid vertex: DuMux's point-source

@@ -165,6 +165,12 @@ int  dmx_bcrs_pattern(dmx_ctx* ctx, int n, int b, const int* rowptr, const int* 
         porousmediumflow/fvspatialparams.hh:83-99, common/fvporousmediumspatialparams.hh:75-118).  LOCAL arrays. ---- */
 int  dmx_set_options(dmx_ctx* ctx, const dmx_options* o);
 int  dmx_set_cell_fields(dmx_ctx* ctx, const double* permeability, const double* porosity, const int* region);
+/* Diagonal permeability tensor K = diag(Kx, Ky, Kz) per cell (SpatialParams::permeability returning a FieldMatrix whose
+   off-diagonal entries vanish, e.g. test/porousmediumflow/1p/convergence/analyticsolution with Problem.C = 0): on an axis-aligned
+   grid the TPFA transmissibility of a face with normal e_a needs n.K.n = K_aa and the gravity term n.K.g = K_aa g_a only.
+   Arrays of length num_cells per grid axis (LOCAL box), NULL for axes the grid does not have; NULL for all = back to the scalar
+   field of dmx_set_cell_fields.  Full tensors (off-diagonal entries) are not supported by the TPFA kernels. */
+int  dmx_set_permeability_diagonal(dmx_ctx* ctx, const double* kx, const double* ky, const double* kz);
 int  dmx_set_source(dmx_ctx* ctx, const double* q);
 /* BC: params {pcEntry, lambda}, reg {pcLowSwe}; VG: params {alpha, n, l}, reg {pcLowSwe, pcHighSwe, krnLowSwe, krwHighSwe} */
 int  dmx_set_material(dmx_ctx* ctx, int region, int law, const double* params, double swr, double snr,

@@ -122,9 +122,12 @@ struct ProblemData {
     //! The adapter that samples a DuMux Problem sets these when the problem overrides the solution-dependent interfaces
     //! neumann(element, fvGeometry, elemVolVars, elemFluxVarsCache, scvf) / source(element, fvGeometry, elemVolVars, scv)
     //! (common/fvproblem.hh:262-283,307-331) instead of neumannAtPos / sourceAtPos, or returns a tensor from
-    //! SpatialParams::permeability (porousmediumflow/fvspatialparams.hh:83-99): the kernels take sampled arrays and a scalar K,
-    //! so the assembler refuses such a problem instead of silently freezing the values (DESIGN.md "Out of scope").
+    //! SpatialParams::permeability (porousmediumflow/fvspatialparams.hh:83-99) with OFF-DIAGONAL entries: the kernels take sampled
+    //! arrays and a scalar or diagonal K, so the assembler refuses such a problem instead of silently freezing the values
+    //! (DESIGN.md "Out of scope").  A diagonal tensor goes into permeabilityDiagonal.
     bool solutionDependentNeumann = false, solutionDependentSource = false, tensorPermeability = false;
+    //! K = diag(K_xx, K_yy, K_zz) per cell: one array per grid axis (dmx_set_permeability_diagonal); empty = scalar `permeability`
+    std::vector<double> permeabilityDiagonal[3];
     dmx_options options;
     ProblemData() { dmx_default_options(&options); }
 };
@@ -229,7 +232,7 @@ private:
     {
         if (p.solutionDependentNeumann || p.solutionDependentSource)
             throw InvalidState("GpuFVAssembler: solution-dependent Neumann fluxes / sources are not supported (only the tracer outflow, DMX_BC_OUTFLOW)");
-        if (p.tensorPermeability) throw InvalidState("GpuFVAssembler: tensor-valued permeability is not supported (scalar K only)");
+        if (p.tensorPermeability) throw InvalidState("GpuFVAssembler: permeability tensors with off-diagonal entries are not supported (scalar or diagonal K)");
         dmx_ctx* c = ctx_->get();
         ctx_->check(dmx_grid_structured(c, p.model, p.dim, p.cells.data(), p.lower.data(), p.upper.data()));
         numEq_ = dmx_num_eq(c);
@@ -239,6 +242,10 @@ private:
         ctx_->check(dmx_set_options(c, &options_));
         ctx_->check(dmx_set_cell_fields(c, p.permeability.empty() ? nullptr : p.permeability.data(),
                                         p.porosity.empty() ? nullptr : p.porosity.data(), p.region.empty() ? nullptr : p.region.data()));
+        if (!p.permeabilityDiagonal[0].empty())
+            ctx_->check(dmx_set_permeability_diagonal(c, p.permeabilityDiagonal[0].data(),
+                                                      p.permeabilityDiagonal[1].empty() ? nullptr : p.permeabilityDiagonal[1].data(),
+                                                      p.permeabilityDiagonal[2].empty() ? nullptr : p.permeabilityDiagonal[2].data()));
         for (std::size_t r = 0; r < p.materials.size(); ++r) {
             const auto& m = p.materials[r];
             ctx_->check(dmx_set_material(c, static_cast<int>(r), m.law, m.params.data(), m.swr, m.snr, m.regularize ? 1 : 0,

@@ -321,6 +321,7 @@ struct Fluids {
 // ---------------------------------------------------------------------------------------------
 struct VolVars {
     double p[2], S[2], rho[2], mu[2], mob[2], pc, porosity, K, extr;
+    double Kd[3];      // permeability entering a face with normal e_a: K_aa of a diagonal tensor, else the scalar K
 };
 
 } // namespace
@@ -332,6 +333,7 @@ struct orc_problem {
     int n = 0;
     orc_options opt;
     std::vector<double> K, phi, q;
+    std::vector<double> Kdiag[3];              // diagonal permeability tensor per axis (empty: scalar K)
     std::vector<int> region;
     std::vector<Law> laws;
     Fluids fluids;
@@ -399,6 +401,7 @@ struct orc_problem {
         const double phiInert = 1.0 - phi[cell];
         v.porosity = 1.0 - phiInert;
         v.K = K[cell];
+        for (int a = 0; a < 3; ++a) v.Kd[a] = Kdiag[a].empty() ? K[cell] : Kdiag[a][cell];
         v.extr = opt.extrusion;
         if (model == ORC_MODEL_1P) {
             v.S[0] = 1.0; v.S[1] = 0.0;
@@ -456,12 +459,13 @@ struct orc_problem {
     {
         const int a = side / 2;
         const double area = faceArea(a, cI);
-        const double ti = computeTpfaTransmissibility(cI, side, cI, in.K, in.extr);
+        // vtmv(n, K, n) = K_aa for the axis-aligned normal of this face (diagonal tensor or scalar)
+        const double ti = computeTpfaTransmissibility(cI, side, cI, in.Kd[a], in.extr);
         double tij, tj = 0.0;
         if (boundary)
             tij = area * ti;
         else {
-            tj = -1.0 * computeTpfaTransmissibility(cI, side, cJ, out.K, out.extr);
+            tj = -1.0 * computeTpfaTransmissibility(cI, side, cJ, out.Kd[a], out.extr);
             if (ti * tj <= 0.0) tij = 0;
             else tij = area * (ti * tj) / (ti + tj);
         }
@@ -478,11 +482,11 @@ struct orc_problem {
                 const double pOutside = out.p[ph];
                 double ng = 0.0;
                 for (int d = 0; d < dim; ++d) ng += nrm[d] * g[d];
-                const double alpha_inside = in.K * ng * in.extr;      // vtmv(n,K,g)*extr, dumux/common/math.hh:908-913
+                const double alpha_inside = in.Kd[a] * ng * in.extr;  // vtmv(n,K,g)*extr, dumux/common/math.hh:908-913
                 f = tij * (pInside - pOutside) + rho * area * alpha_inside;
                 if (!boundary) {
                     const double outsideTi = tj;                       // same expression as in calculateTransmissibility
-                    const double alpha_outside = out.K * ng * out.extr;
+                    const double alpha_outside = out.Kd[a] * ng * out.extr;
                     f -= rho * tij / outsideTi * (alpha_inside - alpha_outside);
                 }
             } else {
@@ -625,14 +629,14 @@ struct orc_problem {
         for (int side = 0; side < 2 * dim; ++side) {
             const int J = nbIdx[side];
             if (J >= 0) {
-                const double deriv = advectionTij(cI, side, vvI.K, vvI.extr, false, nbC[side], nb[side].K, nb[side].extr) * up;
+                const double deriv = advectionTij(cI, side, vvI.Kd[side / 2], vvI.extr, false, nbC[side], nb[side].Kd[side / 2], nb[side].extr) * up;
                 jac[kd] += deriv;
                 jac[findEntry(I, J)] -= deriv;
             } else {
                 const int fidx = sideFaceIndex(side, cI);
                 const int type = bcType[side].empty() ? ORC_BC_NEUMANN : bcType[side][fidx];
                 if (type == ORC_BC_DIRICHLET) {
-                    const double deriv = advectionTij(cI, side, vvI.K, vvI.extr, true, nullptr, 0.0, 0.0) * up;
+                    const double deriv = advectionTij(cI, side, vvI.Kd[side / 2], vvI.extr, true, nullptr, 0.0, 0.0) * up;
                     jac[kd] += deriv;
                 }
             }
@@ -705,8 +709,8 @@ struct orc_problem {
             const double outsideWeight_n = 1.0 - insideWeight_n;
             const double rhowKrw_muw_inside = rho_w * vvI.mob[0], rhonKrn_mun_inside = rho_n * vvI.mob[1];
             const double rhowKrw_muw_outside = rho_w * out->mob[0], rhonKrn_mun_outside = rho_n * out->mob[1];
-            const double tij = boundary ? advectionTij(cI, side, vvI.K, vvI.extr, true, nullptr, 0.0, 0.0)
-                                        : advectionTij(cI, side, vvI.K, vvI.extr, false, nbC[side], out->K, out->extr);
+            const double tij = boundary ? advectionTij(cI, side, vvI.Kd[side / 2], vvI.extr, true, nullptr, 0.0, 0.0)
+                                        : advectionTij(cI, side, vvI.Kd[side / 2], vvI.extr, false, nbC[side], out->Kd[side / 2], out->extr);
             const double up_w = rhowKrw_muw_inside * insideWeight_w + rhowKrw_muw_outside * outsideWeight_w;
             const double up_n = rhonKrn_mun_inside * insideWeight_n + rhonKrn_mun_outside * outsideWeight_n;
             if (boundary) {
@@ -1395,6 +1399,17 @@ void orc_set_cell_fields(orc_problem* p, const double* K, const double* phi, con
     if (K) p->K.assign(K, K + p->n);
     if (phi) p->phi.assign(phi, phi + p->n);
     if (region) p->region.assign(region, region + p->n);
+}
+// diagonal permeability tensor (SpatialParams::permeability returning a FieldMatrix without off-diagonal entries): one array per
+// grid axis, all null = back to the scalar field
+void orc_set_permeability_diagonal(orc_problem* p, const double* kx, const double* ky, const double* kz)
+{
+    const double* k[3] = {kx, ky, kz};
+    for (int a = 0; a < 3; ++a) {
+        p->Kdiag[a].clear();
+        if (k[a] && a < p->dim) p->Kdiag[a].assign(k[a], k[a] + p->n);
+    }
+    if (k[p->dim - 1]) p->K.assign(k[p->dim - 1], k[p->dim - 1] + p->n);
 }
 void orc_set_source(orc_problem* p, const double* q) { p->q.assign(q, q + (size_t)p->n * p->b); }
 

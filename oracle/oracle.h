@@ -53,6 +53,7 @@ int  orc_num_cells(const orc_problem* p);
 int  orc_num_eq(const orc_problem* p);
 void orc_set_options(orc_problem* p, const orc_options* o);
 void orc_set_cell_fields(orc_problem* p, const double* K, const double* phi, const int* region);
+void orc_set_permeability_diagonal(orc_problem* p, const double* kx, const double* ky, const double* kz);
 void orc_set_source(orc_problem* p, const double* q);
 /* BC: params = {pcEntry, lambda}, reg = {pcLowSwe}; VG: params = {alpha, n, l}, reg = {pcLowSwe, pcHighSwe, krnLowSwe, krwHighSwe} */
 void orc_set_material(orc_problem* p, int region, int law, const double* params, double swr, double snr,

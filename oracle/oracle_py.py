@@ -68,6 +68,7 @@ def lib():
         L.orc_set_options.argtypes = [vp, C.POINTER(OrcOptions)]
         L.orc_set_cell_fields.argtypes = [vp, _dp, _dp, _ip]
         L.orc_set_source.argtypes = [vp, _dp]
+        L.orc_set_permeability_diagonal.argtypes = [vp, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_set_material.argtypes = [vp, C.c_int, C.c_int, _dp, C.c_double, C.c_double, C.c_int, _dp]
         L.orc_set_wetting_phase.argtypes = [vp, C.c_int, C.c_int]
         L.orc_set_fluids.argtypes = [vp, _dp, _dp]
@@ -167,9 +168,14 @@ class Oracle:
         self.opt.use_std_pow = int(use_std_pow)
         self.opt.num_threads = num_threads
         L.orc_set_options(self.h, C.byref(self.opt))
-        L.orc_set_cell_fields(self.h, np.ascontiguousarray(spec.K, dtype=np.float64),
+        K = np.asarray(spec.K, dtype=np.float64)
+        L.orc_set_cell_fields(self.h, np.ascontiguousarray(K if K.ndim == 1 else K[:, spec.dim - 1]),
                               np.ascontiguousarray(spec.phi, dtype=np.float64),
                               np.ascontiguousarray(spec.region, dtype=np.int32))
+        if K.ndim == 2:          # diagonal permeability tensor: K[:, a] = K_aa
+            ks = [np.ascontiguousarray(K[:, a]) for a in range(spec.dim)]
+            ptr = [k.ctypes.data_as(C.c_void_p) for k in ks] + [None] * (3 - spec.dim)
+            L.orc_set_permeability_diagonal(self.h, *ptr)
         for r, m in enumerate(spec.materials):
             reg = np.ascontiguousarray(m.reg if len(m.reg) else [0.01, 0.99, 0.1, 0.9], dtype=np.float64)
             L.orc_set_material(self.h, r, m.law, np.ascontiguousarray(m.params, dtype=np.float64), m.swr, m.snr,
