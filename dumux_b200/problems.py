@@ -439,6 +439,29 @@ def twop_lens(cells=(48, 32), law="vg", lower=None, upper=None, lens_lower=None,
 
 
 # ------------------------------------------------------------------------------------------------------
+# test_1p_incompressible_tpfa_extrude (test/porousmediumflow/1p/incompressible/CMakeLists.txt:144-152): the 1p test with
+# -Problem.ExtrusionFactor 10 -Problem.CheckIsConstantVelocity true -Problem.EnableGravity false: homogeneous K (no lens,
+# spatialparams.hh:70), analytic Jacobian; the reference checks that the Darcy velocity -K dp/dy / mu is reproduced exactly
+# (main.cc:165-203).  `constant_velocity_check` does that on the face volume fluxes.
+# ------------------------------------------------------------------------------------------------------
+def onep_extrude(cells=(10, 10), extrusion=10.0) -> ProblemSpec:
+    spec = onep_incompressible(cells, analytic=True)
+    n = int(np.prod(cells))
+    return dataclasses.replace(spec, name="1p_extrude", K=np.full(n, 1e-10),
+                               options=dataclasses.replace(spec.options, extrusion=extrusion, enable_gravity=False))
+
+
+def constant_velocity_check(spec, volume_flux):
+    """volume flux / (face area * extrusion factor) on every face: vertical component equal to 1e-10 * 1e5 / 1e-3 to 1e-8
+    relative, horizontal component below 1e-10 (the tolerances of main.cc:196-198); returns the two deviations"""
+    h = [(spec.upper[a] - spec.lower[a]) / spec.cells[a] for a in range(2)]
+    v = np.asarray(volume_flux) / (np.array([h[1], h[1], h[0], h[0]]) * spec.options.extrusion)
+    exact = 1e-10 * 1.0e5 / 1e-3
+    dev_y = max(np.abs(v[:, 3] / exact - 1).max(), np.abs(-v[:, 2] / exact - 1).max())
+    return float(dev_y), float(np.abs(v[:, :2]).max())
+
+
+# ------------------------------------------------------------------------------------------------------
 # test/porousmediumflow/1p/convergence/analyticsolution (test_1p_convergence_analytic_tpfa_structured: params.input with
 # -Problem.C 0.0, problem.hh:60-150, spatialparams.hh:60-75): stationary incompressible 1p on [0,1]^2 with density 1 and kinematic
 # viscosity 1, the permeability TENSOR K = [[1, -c/(2w) sin(wx)], [-c/(2w) sin(wx), exp(-2)(1 + c cos(wx))]], w = pi, which for the

@@ -162,3 +162,17 @@ def test_1p_pointsource_golden(engine_factory):
     g = np.load(os.path.join(GOLDEN, "test_1p_pointsources_timeindependent_cc.npz"))["p"].astype(np.float64)
     for u in (ug, ua):
         assert np.abs(u / g - 1).max() < 1e-5
+
+
+def test_1p_incompressible_tpfa_extrude_constant_velocity(engine_factory):
+    """test_1p_incompressible_tpfa_extrude on the device: extrusion factor 10, the velocity check of the reference's main.cc:165-203"""
+    spec = problems.onep_extrude()
+    o = Oracle(spec)
+    uo, sto, repo = o.newton(spec.initial, spec.initial)
+    e = engine_factory(spec)
+    ug, stg, repg = e.newton(spec.initial, spec.initial)
+    assert stg == 0 and repg.newton_iterations == repo.newton_iterations and _rel_l2(ug, uo) <= 1e-10
+    vg = e.volume_flux(ug)
+    assert np.array_equal(vg, o.volume_flux(ug))
+    dev_y, dev_x = problems.constant_velocity_check(spec, vg)
+    assert dev_y <= 1e-8 and dev_x <= 1e-10

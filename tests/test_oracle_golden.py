@@ -58,6 +58,22 @@ def test_1p_compressible_stationary_reference_vtu():
     assert np.abs(u / g - 1).max() < 1e-4          # the water's compressibility moves the pressure by 2e-5 of its value
 
 
+def test_1p_incompressible_tpfa_extrude_constant_velocity():
+    """test_1p_incompressible_tpfa_extrude (-Problem.ExtrusionFactor 10 -Problem.CheckIsConstantVelocity true -Problem.EnableGravity
+    false): homogeneous K, the analytic Jacobian, extrusion factor 10 in transmissibilities and fluxes"""
+    import dataclasses
+    spec = problems.onep_extrude()
+    o = Oracle(spec)
+    u, st, rep = o.newton(spec.initial, spec.initial)
+    assert st == 0
+    dev_y, dev_x = problems.constant_velocity_check(spec, o.volume_flux(u))
+    assert dev_y <= 1e-8 and dev_x <= 1e-10
+    # the pressure does not depend on the extrusion factor
+    s1 = problems.onep_extrude(extrusion=1.0)
+    u1, st1, _ = Oracle(s1).newton(s1.initial, s1.initial)
+    assert np.abs(u / u1 - 1).max() <= 1e-12
+
+
 def test_1p_pointsource_reference_vtu():
     """test_1p_pointsources_timeindependent_tpfa -> test_1p_pointsources_timeindependent_cc-reference.vtu: 10 kg/s at a grid vertex,
     shared by the four cells around it (pointsource.hh); pins the source term of the local residual (fvlocalresidual.hh:319-333)"""
