@@ -58,6 +58,18 @@ def test_1p_compressible_stationary_reference_vtu():
     assert np.abs(u / g - 1).max() < 1e-4          # the water's compressibility moves the pressure by 2e-5 of its value
 
 
+def test_1p_isothermal_tpfa_reference_vtu():
+    """test_1p_tpfa (test/porousmediumflow/1p/isothermal: SimpleH2O, one implicit Euler step dt = 1 s with the Newton solver,
+    Dirichlet p = 1e5 (2 - y) at top and bottom, gravity, lens) -> test_1p_cc-reference.vtu"""
+    import dataclasses
+    spec = problems.onep_compressible((10, 10))
+    spec = dataclasses.replace(spec, fluid_table=None, options=dataclasses.replace(spec.options, dt=1.0))
+    u, st, rep = Oracle(spec).newton(spec.initial, spec.initial)
+    assert st == 0
+    g = np.load(os.path.join(GOLDEN, "test_1p_cc.npz"))["p"].astype(np.float64)
+    assert _fuzzy_ok(u, g) and np.abs(u / g - 1).max() < 5e-6
+
+
 def test_1p_incompressible_tpfa_extrude_constant_velocity():
     """test_1p_incompressible_tpfa_extrude (-Problem.ExtrusionFactor 10 -Problem.CheckIsConstantVelocity true -Problem.EnableGravity
     false): homogeneous K, the analytic Jacobian, extrusion factor 10 in transmissibilities and fluxes"""
