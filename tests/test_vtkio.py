@@ -64,6 +64,31 @@ def test_restart_from_vtu_continues_the_run(tmp_path):
         vtkio.load_solution(path, ["p_liq"])
 
 
+def test_2p_incompressible_tpfa_restart_as_the_reference_runs_it(tmp_path):
+    """test_2p_incompressible_tpfa_restart (test/porousmediumflow/2p/incompressible/CMakeLists.txt:30-40): the reference restarts
+    the 48 x 32 lens run from its fifth output file with `-Restart.Time 2054.01 -TimeLoop.DtInitial 603.14` and compares the SECOND
+    output of the restarted run with test_2p_incompressible_cc-reference.vtu (t = 3000 s).  Two things are pinned by that command
+    line: (i) the uninterrupted run is at t = 2054.01 s after five time steps -- the step sizes follow from the Newton iteration
+    counts (suggestTimeStepSize), so the counts of the first four steps are the reference's; (ii) from the restart file (Float32
+    ASCII like the reference's) two more time steps reach t = 3000 s with the golden fields."""
+    spec = problems.twop_lens((48, 32), law="vg")
+    o = Oracle(spec)
+    u_all, n_all, its_all, dts_all = o.run_timeloop(spec.initial, 3000.0, 250.0)
+    assert n_all == 7 and abs(np.sum(dts_all[:5]) - 2054.01) <= 5e-3          # "Restart.Time 2054.01" (six digits)
+    u5, n5, its5, dts5 = o.run_timeloop(spec.initial, float(np.sum(dts_all[:5])), 250.0)
+    assert n5 == 5 and list(its5) == list(its_all[:5])
+    path = str(tmp_path / "test_2p_incompressible_tpfa-00005.vtu")
+    vtkio.write_vtu(path, problems.node_coords(spec.cells, spec.lower, spec.upper), _fields_from_oracle(o, u5))
+    u0 = vtkio.load_solution(path, ["p_aq", "S_napl"])
+    u_end, n2, its2, dts2 = Oracle(spec).run_timeloop(u0, 3000.0 - 2054.01, 603.14)
+    assert n2 == 2 and dts2[0] == 603.14                                       # the compared file is output number 00002
+    g = np.load(os.path.join(GOLDEN, "test_2p_incompressible_cc.npz"))
+    for name, col in (("p_aq", 0), ("S_napl", 1)):
+        ref = g[name].astype(np.float64)
+        d = np.abs(u_end.reshape(-1, 2)[:, col] - ref)
+        assert np.all((d <= 1.5e-7) | (d <= 1e-2 * np.abs(ref))), name          # the reference's fuzzy bar
+
+
 def test_3d_and_1d_grids(tmp_path):
     for cells in ((4, 3, 2), (5,)):
         dim = len(cells)
