@@ -750,6 +750,17 @@ def run_b200(args):
                 "ms_per_step": res["e2e_ms"]},
         "gpu_launches": res["launches"], "clocks": res["clocks"],
         "parity_check": parity, "amg": amg_line, "strong_512": strong, "strong_512_amg": strong_amg,
+        "notes": {
+            "parity": "the 1e-10 / 1e-8 / equal-count bars are CUDA against the oracle (bit-identical assembly, SpMV, ILU0; same Krylov "
+                      "iteration through a shared summation tree); the oracle is pinned to the reference's golden VTU files at their "
+                      "Float32 precision and to its tests' own criteria (DESIGN.md section 2); its dune-istl half is a restatement without a "
+                      "dune-istl build to compare with, and against a -O3 -march=native build of the reference FD Jacobian entries can "
+                      "differ by up to 1e-4 of the row scale (FMA contraction, libm pow)",
+            "headline": "ILU0-BiCGSTAB is the BASELINE metric (value, e2e, roofline, kernels); `amg` / `strong_512_amg` time the same workloads "
+                        "with the AMG preconditioner (this library's structured hierarchy, dune-istl's default cycle)",
+            "cpu": "`--impl reference` runs the full 256^3 configuration on min(16, cores) overlapping-Schwarz ranks of the oracle port; the "
+                   "`cpu_baseline` object of this line is a bounded 96^3 single-rank sample",
+        },
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu
