@@ -33,7 +33,7 @@ EXPORTS = [
     "dmx_ilu0_factor", "dmx_ilu0_apply", "dmx_ilu0_download", "dmx_dot", "dmx_halo_exchange", "dmx_time_kernel",
     "dmx_kernel_launch_count", "dmx_synchronize", "dmx_profile", "dmx_profile_read",
     "dmx_newton_step_host", "dmx_timer_start", "dmx_timer_stop", "dmx_debug_sweep_trace",
-    "dmx_volume_flux", "dmx_set_volume_flux", "dmx_set_tracer", "dmx_set_wetting_phase", "dmx_set_linear_solver", "dmx_ssor_apply", "dmx_num_output_fields", "dmx_output_fields", "dmx_set_tracer_diffusion",
+    "dmx_volume_flux", "dmx_set_volume_flux", "dmx_set_tracer", "dmx_set_wetting_phase", "dmx_set_linear_solver", "dmx_ssor_apply", "dmx_num_output_fields", "dmx_output_fields", "dmx_set_tracer_diffusion", "dmx_set_tracer_dispersion",
 ]
 SOLVER_BICGSTAB, SOLVER_RESTARTED_GMRES, SOLVER_CG = 0, 1, 2
 PRECOND_SSOR = 2
@@ -120,6 +120,7 @@ def load_library():
     L.dmx_set_volume_flux.argtypes = [vp, _dp]
     L.dmx_set_tracer.argtypes = [vp, C.c_int]
     L.dmx_set_tracer_diffusion.argtypes = [vp, C.c_double, C.c_double]
+    L.dmx_set_tracer_dispersion.argtypes = [vp, C.c_void_p]
     L.dmx_set_wetting_phase.argtypes = [vp, C.c_int, C.c_int]
     L.dmx_set_linear_solver.argtypes = [vp, C.c_int, C.c_int]
     L.dmx_ssor_apply.argtypes = [vp, C.c_int, C.c_int]
@@ -299,6 +300,9 @@ class Engine:
             self._check(L.dmx_set_volume_flux(self.h, np.ascontiguousarray(self.localize_cells(spec.volume_flux), dtype=np.float64).reshape(-1)))
             self._check(L.dmx_set_tracer(self.h, int(spec.implicit)))
             self._check(L.dmx_set_tracer_diffusion(self.h, float(spec.tracer_diffusion[0]), float(spec.tracer_diffusion[1])))
+            if getattr(spec, "tracer_dispersion", None) is not None:
+                disp = np.ascontiguousarray(self.localize_cells(spec.tracer_dispersion), dtype=np.float64).reshape(-1)
+                self._check(L.dmx_set_tracer_dispersion(self.h, disp.ctypes.data_as(C.c_void_p)))
 
     def owner_mask(self):
         """bool[n]: cells this rank owns (interior partition), x fastest"""

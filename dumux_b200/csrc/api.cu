@@ -190,6 +190,7 @@ int finish_grid(dmx_ctx* ctx, int model, int dim, const int* cells, const std::v
     for (int a = 0; a < 3; ++a) if (ctx->d_tij[a]) { cudaFree(ctx->d_tij[a]); ctx->d_tij[a] = nullptr; }
     for (int a = 0; a < 3; ++a) if (ctx->d_Kaxis[a]) { cudaFree(ctx->d_Kaxis[a]); ctx->d_Kaxis[a] = nullptr; }
     if (ctx->d_law_rec) { cudaFree(ctx->d_law_rec); ctx->d_law_rec = nullptr; }
+    if (ctx->d_disp) { cudaFree(ctx->d_disp); ctx->d_disp = nullptr; }
     if (int rc = upload_pattern(ctx)) return rc;
     if (int rc = alloc_vectors(ctx)) return rc;
     // structured-grid ILU sweeps (DMX_ILU_GENERIC=1 keeps the level-scheduled generic kernels, for A/B runs)
@@ -330,7 +331,7 @@ int dmx_destroy(dmx_ctx* ctx)
                     ctx->d_tab_buf, ctx->d_rowptr, ctx->d_colidx, ctx->d_diag, ctx->d_J, ctx->d_ilu, ctx->d_rt, ctx->d_p, ctx->d_v, ctx->d_t,
                     ctx->d_y, ctx->d_z, ctx->d_dinv, ctx->d_gm, ctx->d_vf, ctx->d_color_rows, ctx->d_xold, ctx->d_lrows, ctx->d_urows, ctx->d_lptr, ctx->d_uptr, ctx->d_barrier, ctx->d_partials,
                     ctx->d_scalars, ctx->d_flag, ctx->d_owner, ctx->d_send, ctx->d_recv, ctx->d_gather, ctx->d_law_rec,
-                    ctx->d_Kaxis[0], ctx->d_Kaxis[1], ctx->d_Kaxis[2]};
+                    ctx->d_Kaxis[0], ctx->d_Kaxis[1], ctx->d_Kaxis[2], ctx->d_disp};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int v = 0; v < DMX_NUM_VECS; ++v) if (ctx->d_vec[v]) cudaFree(ctx->d_vec[v]);
     for (int s = 0; s < 6; ++s) {
@@ -681,6 +682,17 @@ int dmx_set_volume_flux(dmx_ctx* ctx, const double* vf)
     if (!ctx->d_vf) DMX_CUDA(cudaMalloc((void**)&ctx->d_vf, len * sizeof(double)));
     DMX_CUDA(cudaMemcpyAsync(ctx->d_vf, vf, len * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     DMX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+int dmx_set_tracer_dispersion(dmx_ctx* ctx, const double* disp)
+{
+    if (!ctx->has_grid || ctx->model != DMX_MODEL_TRACER) return fail(ctx, DMX_ERR_USAGE, "set_tracer_dispersion: needs a tracer context with a grid");
+    DMX_CUDA(cudaSetDevice(ctx->device));
+    if (ctx->d_disp) { cudaFree(ctx->d_disp); ctx->d_disp = nullptr; }
+    if (!disp) return 0;
+    const size_t len = (size_t)ctx->n * 2 * ctx->dim;
+    DMX_CUDA(cudaMalloc((void**)&ctx->d_disp, len * sizeof(double)));
+    DMX_CUDA(cudaMemcpy(ctx->d_disp, disp, len * sizeof(double), cudaMemcpyHostToDevice));
     return 0;
 }
 int dmx_set_tracer_diffusion(dmx_ctx* ctx, double D, double tortuosity)

@@ -1050,6 +1050,18 @@ __global__ void __launch_bounds__(256) tracer_assemble_kernel(const AsmParams P)
             double flux = 0.0;
             flux += vflux * mult;
             flux += rhoAvg * dTij * (XI - X[J]);
+            if (P.disp) {
+                // mechanical dispersion (flux/cctpfa/dispersionflux.hh:93-104,172-213): the tensor is given at the face, D_i = D_j, and
+                // only its normal entry enters the TPFA transmissibility; no derivative in the Jacobian, as in the reference's
+                // TracerLocalResidual::addFluxDerivatives (tracer/localresidual.hh:237-291)
+                const double Dd = P.disp[I * (2 * DIM) + s];
+                const double mi = Dd * extr * (hi ? P.gf_hi[a][ci[a]] : P.gf_lo[a][ci[a]]);
+                const double mj = Dd * extr * (hi ? P.gf_lo[a][cj] : P.gf_hi[a][cj]);
+                double mTij;
+                if (mi * mj <= 0.0) mTij = 0;
+                else mTij = areaF * (mi * mj) / (mi + mj);
+                flux += rhoAvg * mTij * (XI - X[J]);
+            }
             res += flux;
             if constexpr (JAC) {
                 double offdiag = 0.0;
@@ -1141,7 +1153,7 @@ static void fill_params(dmx_ctx* ctx, AsmParams& P)
         P.bc_p[s] = ctx->d_bc_p[s]; P.bc_up[s] = ctx->d_bc_up[s]; P.bc_rho[s] = ctx->d_bc_rho[s];
     }
     P.cur = ctx->d_vec[DMX_VEC_CUR]; P.prev = ctx->d_vec[DMX_VEC_PREV];
-    P.vf = ctx->d_vf; P.tracer_implicit = ctx->tracer_implicit;
+    P.vf = ctx->d_vf; P.disp = ctx->d_disp; P.tracer_implicit = ctx->tracer_implicit;
     P.tracer_D = ctx->tracer_D; P.tracer_tau = ctx->tracer_tau;
     P.rowptr = ctx->d_rowptr; P.residual = ctx->d_vec[DMX_VEC_RESIDUAL]; P.jac = ctx->d_J;
     P.flag_nonfinite = ctx->d_flag;

@@ -38,6 +38,7 @@ struct AsmParams {
     const double* q;          // may be null
     const double* tij[3];     // transmissibility of the + face of each cell along axis a
     const double* vf;         // tracer: frozen volume fluxes [n][2*dim]
+    const double* disp;       // tracer: n.D.n of the mechanical dispersion tensor at every face [n][2*dim], null = off
     int tracer_implicit;
     double tracer_D, tracer_tau;          // Fick's law: binary diffusion coefficient, constant tortuosity
     // fluids
@@ -109,6 +110,7 @@ struct dmx_ctx {
     int* d_region = nullptr;
     double* d_tij[3] = {nullptr, nullptr, nullptr};
     double* d_vf = nullptr;             // tracer: frozen volume fluxes [n][2*dim]
+    double* d_disp = nullptr;           // tracer: dispersion-tensor entries at the faces [n][2*dim] (dmx_set_tracer_dispersion)
     double* d_law_rec = nullptr;        // DiffMethod::analytic (2p): per-cell material-law record [6][n], allocated on first use
     int tracer_implicit = 0;
     double tracer_D = 0.0, tracer_tau = 0.5;

@@ -73,6 +73,8 @@ class ProblemSpec:
     implicit: bool = False
     # tracer: (binary diffusion coefficient D, SpatialParams.Tortuosity) of Fick's law with DiffusivityConstantTortuosity; D = 0: off
     tracer_diffusion: Tuple[float, float] = (0.0, 0.5)
+    # tracer: mechanical dispersion -- n.D.n of the dispersion tensor at every face [n, 2*dim] (sides as volume_flux); None: off
+    tracer_dispersion: Optional[np.ndarray] = None
     # slab-local spec (multi-GPU set-up without materialising the global arrays): the per-cell / per-face arrays above
     # cover only the layers [slab[0], slab[1]) of the last axis (overlap included); cells/lower/upper stay GLOBAL.
     slab: Optional[Tuple[int, int]] = None
@@ -719,7 +721,18 @@ def onep_tracer_pressure_large(cells, box=None, sigma=0.5, seed=0) -> ProblemSpe
 # The test carries two decoupled components: D = 1e-8 (Problem.D) for the first, D2 = 0 (pure advection) for the second; one
 # spec describes one of them (`D`).
 # ------------------------------------------------------------------------------------------------------
-def tracer_constvel(cells=(50, 50), dt=1.0e4, implicit=False, D=0.0) -> ProblemSpec:
+def scheidegger_normal_entry(vel, axis, alpha_l, alpha_t):
+    """n.D.n of Scheidegger's dispersion tensor D = (aL - aT) v v^T / |v| + aT |v| I (dispersiontensors/scheidegger.hh:152-176) for
+    the face normal e_axis; `vel` = velocity vectors [m, dim] at the face centres"""
+    vel = np.asarray(vel, dtype=np.float64)
+    vnorm = np.sqrt(np.sum(vel * vel, axis=1))
+    vv = vel[:, axis] * vel[:, axis]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        t = np.where(vnorm < 1e-20, 0.0, vv / vnorm)
+    return t * (alpha_l - alpha_t) + vnorm * alpha_t
+
+
+def tracer_constvel(cells=(50, 50), dt=1.0e4, implicit=False, D=0.0, alpha_l=0.0, alpha_t=0.0) -> ProblemSpec:
     dim = 2
     lower, upper = (0.0, 0.0), (1.0, 1.0)
     n = int(np.prod(cells))
@@ -740,6 +753,15 @@ def tracer_constvel(cells=(50, 50), dt=1.0e4, implicit=False, D=0.0) -> ProblemS
     vf[:, 1] = vel(xn[0][i + 1], yc)[0] * hy[j]
     vf[:, 2] = -vel(xc, xn[1][j])[1] * hx[i]
     vf[:, 3] = vel(xc, xn[1][j + 1])[1] * hx[i]
+    disp = None
+    if alpha_l != 0.0 or alpha_t != 0.0:
+        # test_tracer_implicit_dispersion_tpfa (-Problem.AlphaL 0.02 -Problem.AlphaT 0.008): Scheidegger's tensor from the analytic
+        # velocity at the face centres (spatialparams.hh:75-87,104-107)
+        disp = np.zeros((n, 4))
+        faces = [(xn[0][i], yc, 0), (xn[0][i + 1], yc, 0), (xc, xn[1][j], 1), (xc, xn[1][j + 1], 1)]
+        for side, (fx, fy, axis) in enumerate(faces):
+            v = np.stack(vel(fx, fy), axis=1)
+            disp[:, side] = scheidegger_normal_entry(v, axis, alpha_l, alpha_t)
     bc_type, bc_values = {}, {}
     for side in range(4):
         nf = cells[1] if side < 2 else cells[0]
@@ -753,4 +775,4 @@ def tracer_constvel(cells=(50, 50), dt=1.0e4, implicit=False, D=0.0) -> ProblemS
         K=np.ones(n), phi=np.full(n, 0.2), region=np.zeros(n, dtype=np.int32), materials=[],
         rho=(1000.0,), mu=(1e-3,), bc_type=bc_type, bc_values=bc_values,
         options=Options(stationary=False, dt=dt, enable_gravity=False), initial=init, volume_flux=vf, implicit=implicit,
-        tracer_diffusion=(D, 0.5))
+        tracer_diffusion=(D, 0.5), tracer_dispersion=disp)

@@ -195,6 +195,13 @@ int  dmx_set_tracer(dmx_ctx* ctx, int implicit);
 /* tracer ctx: Fick's law (flux/cctpfa/fickslaw.hh) with DiffusivityConstantTortuosity (material/fluidmatrixinteractions/
    diffusivityconstanttortuosity.hh:55-63): D = FluidSystem::binaryDiffusionCoefficient (constant), tortuosity =
    SpatialParams.Tortuosity (default 0.5); mass fractions, mass-averaged reference system.  D = 0 (default): no diffusion. */
+/* Mechanical dispersion of the tracer model (EnableCompositionalDispersion; flux/cctpfa/dispersionflux.hh:66-113 with e.g.
+   ScheideggersDispersionTensor, material/fluidmatrixinteractions/dispersiontensors/scheidegger.hh:44-176): with a stationary velocity
+   field the dispersion tensor at a face does not depend on the solution, so the adapter samples it once like the volume fluxes:
+   disp[cell][side] = n.D.n (sides -x,+x,-y,+y,-z,+z; LOCAL box) -- the only entry a TPFA transmissibility of an axis-aligned face
+   uses.  The flux rho * tij(D) * (X_I - X_J) enters the residual; like the reference's analytic tracer Jacobian
+   (tracer/localresidual.hh:237-291) the Jacobian has no dispersion derivative.  NULL = off. */
+int  dmx_set_tracer_dispersion(dmx_ctx* ctx, const double* disp);
 int  dmx_set_tracer_diffusion(dmx_ctx* ctx, double D, double tortuosity);
 int  dmx_side_faces(const dmx_ctx* ctx, int side);
 int  dmx_set_boundary(dmx_ctx* ctx, int side, const int* type, const double* values);

@@ -342,6 +342,7 @@ struct orc_problem {
     std::vector<int> rowptr, colidx;
     int linearSolver = ORC_SOLVER_BICGSTAB, gmresRestart = 10;   // orc_set_linear_solver
     double tracerD = 0.0, tracerTau = 0.5;     // binary diffusion coefficient of the tracer and SpatialParams.Tortuosity
+    std::vector<double> tracerDisp;            // mechanical dispersion: n.D.n of the dispersion tensor at every face [n][2*dim]
     bool volumeFluxMode = false;               // upwind term = mobility only (examples/1ptracer/main.cc:170)
 
     // ---- grid geometry: YaspGrid equidistant / tensor coordinates, AxisAlignedCubeGeometry [DUNE-ext] ----
@@ -1765,6 +1766,15 @@ int orc_ssor_factor(int n, int b, const int* rowptr, const int* colidx, const do
         }
     return bad;
 }
+// Mechanical dispersion (EnableCompositionalDispersion, flux/cctpfa/dispersionflux.hh:66-113): the dispersion tensor is given at
+// the scvfs (Scheidegger: D = (aL - aT) v v^T / |v| + aT |v| I from the STATIONARY velocity field, scheidegger.hh:152-176), so it
+// is a sampled array like the volume fluxes: for every cell and side the entry n.D.n, which is all a TPFA transmissibility of an
+// axis-aligned face sees.  null = off.
+void orc_set_tracer_dispersion(orc_problem* p, const double* disp)
+{
+    if (disp) p->tracerDisp.assign(disp, disp + (size_t)p->n * 2 * p->dim);
+    else p->tracerDisp.clear();
+}
 void orc_set_tracer_diffusion(orc_problem* p, double D, double tortuosity)
 {
     p->tracerD = D;
@@ -2063,6 +2073,13 @@ void orc_tracer_assemble(orc_problem* p, const double* vf, const double* cur, co
                 double flux = 0.0;
                 flux += vflux * mult;
                 flux += rhoAvg * dTij * (X[I] - X[J]);
+                if (!p->tracerDisp.empty()) {
+                    // dispersionflux.hh:93-104 + calculateTransmissibility_ :172-213 with D_i = D_j = the tensor at the face; the
+                    // reference's analytic Jacobian (localresidual.hh:237-291) has NO dispersion derivative, so neither has this one
+                    const double Dd = p->tracerDisp[(size_t)I * 2 * dim + side];
+                    const double mTij = p->advectionTij(cI, side, Dd, extr, false, cJ, Dd, extr);
+                    flux += rhoAvg * mTij * (X[I] - X[J]);
+                }
                 res += flux;
                 if (jac && implicit) {
                     const double insideWeight = std::signbit(vflux) ? (1.0 - w) : w;

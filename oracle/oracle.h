@@ -109,6 +109,7 @@ void orc_amg_galerkin(int b, int dim, const int* fcells, const int* fown_lo, con
 int  orc_ssor_factor(int n, int b, const int* rowptr, const int* colidx, const double* A, double* out);
 /* tracer: binary diffusion coefficient D (FluidSystem::binaryDiffusionCoefficient) and SpatialParams.Tortuosity (default 0.5) of
    DiffusivityConstantTortuosity; D = 0 (the default) switches Fick's law off */
+void orc_set_tracer_dispersion(orc_problem* p, const double* disp);     /* n.D.n of the dispersion tensor per cell and side, NULL = off */
 void orc_set_tracer_diffusion(orc_problem* p, double D, double tortuosity);
 /* linear solver used by orc_newton_solve(_ex) / orc_run_timeloop: ORC_SOLVER_*; restart <= 0: 10 (LinearSolver.GMResRestart) */
 void orc_set_linear_solver(orc_problem* p, int kind, int restart);

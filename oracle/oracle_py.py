@@ -94,6 +94,7 @@ def lib():
         L.orc_ilu0_gmres.restype = C.c_int
         L.orc_set_linear_solver.argtypes = [vp, C.c_int, C.c_int]
         L.orc_set_tracer_diffusion.argtypes = [vp, C.c_double, C.c_double]
+        L.orc_set_tracer_dispersion.argtypes = [vp, C.c_void_p]
         L.orc_ssor_solve.argtypes = [C.c_int, C.c_int, _ip, _ip, _dp, _dp, _dp, C.c_int, C.c_double, C.c_int,
                                      C.POINTER(C.c_int), C.POINTER(C.c_double)]
         L.orc_ssor_solve.restype = C.c_int
@@ -183,6 +184,9 @@ class Oracle:
             L.orc_set_wetting_phase(self.h, r, int(m.wetting))
         if spec.model == 3:
             L.orc_set_tracer_diffusion(self.h, float(spec.tracer_diffusion[0]), float(spec.tracer_diffusion[1]))
+            if getattr(spec, "tracer_dispersion", None) is not None:
+                self._disp = np.ascontiguousarray(spec.tracer_dispersion, dtype=np.float64).reshape(-1)
+                L.orc_set_tracer_dispersion(self.h, self._disp.ctypes.data_as(C.c_void_p))
         if spec.fluid_table is not None:
             t = spec.fluid_table
             L.orc_set_fluid_table(self.h, t["nT"], t["nP"], t["Tmin"], t["Tmax"],

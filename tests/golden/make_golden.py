@@ -8,6 +8,7 @@ Source files (reference tree, test/references/):
   test_tracer_{explicit,implicit}_tpfa-reference.vtu  tracer/constvel, 50x50, t = 1e6 s (output 10), two components (D = 1e-8, 0)
   test_1ptracer_pressure-reference.vtu        1p on log-normal K, 50x50                       (p, permeability)
   test_1ptracer_transport-reference.vtu       tracer after 5000 s                             (x, X, rho, velocity)
+  test_tracer_implicit_dispersion_tpfa-reference.vtu  tracer/constvel with Scheidegger dispersion (AlphaL 0.02, AlphaT 0.008), output 10
   test_1p_pointsources_timeindependent_cc-reference.vtu  1p with a 10 kg/s point source at the origin, 100x100 on [-1,1]^2  (p)
 All are Float32 ASCII cell data in element (x-fastest) order; the reference's own comparison is
 fuzzy: relative 1e-2, absolute 1.5e-7 (bin/testing/dumux_runtest.py / fuzzycomparevtu.py).
@@ -31,6 +32,7 @@ FILES = {
     "test_1ptracer_pressure": "test/references/test_1ptracer_pressure-reference.vtu",
     "test_1ptracer_transport": "test/references/test_1ptracer_transport-reference.vtu",
     "test_1p_pointsources_timeindependent_cc": "test/references/test_1p_pointsources_timeindependent_cc-reference.vtu",
+    "test_tracer_implicit_dispersion_tpfa": "test/references/test_tracer_implicit_dispersion_tpfa-reference.vtu",
 }
 
 
