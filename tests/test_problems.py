@@ -68,3 +68,45 @@ def test_mt19937_lognormal_is_deterministic_and_lens_aware():
     assert np.array_equal(a, b) and np.all(a > 0)
     # ln K ~ N(ln 1e-10, 0.1*|ln 1e-10|): sample statistics in the right ballpark
     assert abs(np.log(a).mean() - np.log(1e-10)) < 1.0 and 1.5 < np.log(a).std() < 3.2
+
+
+def test_buckleyleverett_problem_matches_reference_setup():
+    """test/porousmediumflow/2p/buckleyleverett: params.input, problem.hh:52-140, spatialparams.hh:40-100"""
+    s = P.twop_buckleyleverett()
+    assert s.cells == (100, 1) and s.upper == (100.0, 75.0) and not s.options.enable_gravity
+    m = s.materials[0]
+    assert m.law == P.LAW_BC and m.params == (0.0, 4.0) and (m.swr, m.snr) == (0.2, 0.2)
+    assert np.all(s.K == 1.01936799e-14) and np.all(s.phi == 0.2) and s.rho == (1000.0, 1000.0) and s.mu == (1e-3, 1e-3)
+    assert np.all(s.bc_type[0] == P.BC_DIRICHLET) and np.all(s.bc_values[0] == [2e5, 0.2])          # left: p = 2e5, Sn = Snr
+    assert np.all(s.bc_type[1] == P.BC_NEUMANN) and np.allclose(s.bc_values[1], [0.0, 3e-4])        # right: v_t * rho_n leaves
+    assert np.all(s.bc_type[2] == P.BC_NEUMANN) and not s.bc_values[2].any() and not s.bc_values[3].any()
+    assert np.all(s.initial == [2e5, 0.8])
+
+
+def test_pointsource_convergence_and_extrusion_problems():
+    ps = P.onep_pointsource()
+    hot = np.flatnonzero(ps.source[:, 0])
+    ctr = P.cell_centers(ps.cells, ps.lower, ps.upper)
+    assert hot.size == 4 and np.allclose(np.abs(ctr[hot]), 0.01)               # the four cells around the origin of [-1,1]^2
+    assert ps.source[hot, 0].sum() * 0.02 * 0.02 == pytest.approx(10.0)       # 10 kg/s in total
+    cv = P.onep_convergence((20, 20))
+    assert cv.K.shape == (400, 2) and np.all(cv.K[:, 0] == 1.0) and np.allclose(cv.K[:, 1], np.exp(-2.0))
+    assert all(np.all(cv.bc_type[s] == P.BC_DIRICHLET) for s in range(4))
+    fc = P.side_face_centers(cv.cells, cv.lower, cv.upper, 3)
+    assert np.allclose(cv.bc_values[3][:, 0], P.onep_convergence_exact(fc[:, 0], fc[:, 1]))
+    ex = P.onep_extrude()
+    assert ex.options.extrusion == 10.0 and not ex.options.enable_gravity and np.all(ex.K == 1e-10)
+
+
+def test_scheidegger_normal_entry():
+    """D = (aL - aT) v v^T / |v| + aT |v| I: along the flow n.D.n = aL |v|, across it aT |v|; zero velocity -> zero"""
+    v = np.array([[2e-5, 0.0], [0.0, 3e-5], [0.0, 0.0], [3e-5, 4e-5]])
+    d0 = P.scheidegger_normal_entry(v, 0, 0.02, 0.008)
+    d1 = P.scheidegger_normal_entry(v, 1, 0.02, 0.008)
+    assert np.allclose(d0[:3], [0.02 * 2e-5, 0.008 * 3e-5, 0.0]) and np.allclose(d1[:3], [0.008 * 2e-5, 0.02 * 3e-5, 0.0])
+    assert d0[3] == pytest.approx(0.012 * 9e-10 / 5e-5 + 0.008 * 5e-5)
+    ts = P.tracer_constvel((10, 8), implicit=True, alpha_l=0.02, alpha_t=0.008)
+    # the entry of a face is the same seen from both cells
+    nx = 10
+    d = ts.tracer_dispersion.reshape(8, 10, 4)
+    assert np.allclose(d[:, :-1, 1], d[:, 1:, 0]) and np.allclose(d[:-1, :, 3], d[1:, :, 2])
