@@ -786,6 +786,9 @@ def main():
     ap.add_argument("--solver", default="ilu0", choices=["ilu0", "amg", "amg-ilu"],
                     help="preconditioner of the timed step: ilu0 (the headline, north_star), amg (AMGBiCGSTABIstlSolver with dune-istl's default "
                          "cycle: SSOR smoother, 2 pre + 2 post steps), amg-ilu (ILU0 smoother, 1 + 1 steps)")
+    ap.add_argument("--config", default="2p", choices=["2p", "1p-incompressible", "1p-compressible", "2p-third-step", "tracer"],
+                    help="2p = the BASELINE metric (default).  The others print the measured line of another BASELINE configuration "
+                         "(C1, C2, C3(ii), C5: scripts/baseline_table.py, the lines behind BASELINE.md section 4) instead")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cache", action="store_true", help="reference arm: time again even if this box already holds the measurement")
     ap.add_argument("--no-parity-check", action="store_true")
@@ -794,6 +797,16 @@ def main():
     ap.add_argument("--strong-cells", type=int, default=512)
     ap.add_argument("--strong-steps", type=int, default=2)
     args = ap.parse_args()
+    if args.config != "2p":
+        # other BASELINE configurations: their own script (one JSON line per configuration on stdout; under torchrun the tracer
+        # configuration runs block-decomposed on the N ranks)
+        only = {"1p-incompressible": "c1", "1p-compressible": "c2", "2p-third-step": "c3", "tracer": "c5"}[args.config]
+        cmd = [sys.executable, os.path.join(ROOT, "scripts", "baseline_table.py"), "--only", only, "--edge", str(args.cells),
+               "--tracer-edge", str(args.cells if args.cells != 256 else 512)] + (["--no-cpu"] if args.no_cpu_baseline else [])
+        done = subprocess.run(cmd, stdout=subprocess.PIPE, text=True)
+        _RESULT_OUT.write(done.stdout)
+        _RESULT_OUT.flush()
+        return done.returncode
     if args.impl == "reference":
         return run_reference(args)
     return run_b200(args)
